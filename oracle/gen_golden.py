@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE — generate golden vectors from the UNMODIFIED reference.
+
+Imports the reference's own hot-path modules from ``/root/reference`` behind the import
+shim (``oracle/refshim/install_shims.py``), drives
+``ScenarioRoadTraffic`` through the VMAS ``Environment.step`` call order with seeded
+random actions and records, for every step, the pre-step state, the action and everything
+the step produced.  The ``.npz`` fixtures land in ``tests/golden/`` and are committed,
+because ``/root/reference`` cannot travel to the GPU box.
+
+Re-run (here only):  ``python oracle/gen_golden.py``
+
+Recorded per step t (arrays are [T, B, N, ...]):
+  pre_*   : pos, rot, speed, steering, path_id, scenario_id, step   (state the step starts from,
+            i.e. after the previous step's respawns / env resets)
+  action  : [T,B,N,2]
+  post_*  : pos, rot, speed, steering, vel, sideslip                 (helper_training.py:856-861)
+  obs [T,B,N,D], reward [T,B,N], done [T,B]                          (road_traffic.py:925,1334,1368)
+  col_agents [T,B,N,N], col_lane/col_entry/col_exit [T,B,N]          (world_state_rt_sim.py:379-424)
+  d_ref, d_left[...,5], d_right[...,5], d_bound, d_agents[T,B,N,N], idx_ref,
+  short_term [T,B,N,3,2], vertices [T,B,N,5,2]                       (world_state_rt.py:582-684)
+  reset_mask [T,B]  : env was reset after step t (reset_at), followed by
+  reset_obs [T,B,N,D], reset_pos/rot/speed/vel/path_id/point_id/scenario_id  (post-reset state of those envs)
+  respawn_mask [T,B,N] : agent was respawned inside done() (road_traffic.py:1462-1472)
+"""
+import os
+import sys
+
+os.environ["CICD_TESTING"] = "true"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+import install_shims  # noqa: E402,F401
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from vmas.simulator.environment import Environment  # noqa: E402
+from sigmarl.helper_common import Parameters  # noqa: E402
+from sigmarl.scenarios.road_traffic import ScenarioRoadTraffic  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# name -> config.  mode "kwargs": scenario built from make_world(**kwargs) (dt=0.05 ...);
+# mode "params": a Parameters object from sigmarl/config.json (dt=0.1 ...), as mappo_cavs.py:168 does.
+CONFIGS = {
+    # BASELINE.json configs[0]
+    "c1_intersection_B4_N2": dict(st="intersection_1", B=4, N=2, T=100, mode="kwargs", seed=0),
+    "cpm_entire_B8_N8_distance": dict(st="cpm_entire", B=8, N=8, T=50, mode="params", seed=1),
+    "cpm_entire_B8_N8_sparse_kw": dict(st="cpm_entire", B=8, N=8, T=40, mode="kwargs", seed=2,
+                                      extra=dict(rew_method="sparse")),
+    "cpm_mixed_B8_N6_ttc_sparse": dict(st="cpm_mixed", B=8, N=6, T=60, mode="params", seed=3,
+                                       extra=dict(rew_method="ttc_sparse",
+                                                  threshold_near_other_agents_c2c_low=0.1635)),
+    # NB: cpm_mixed with merge-in/merge-out path sets (cpm_scenario_probabilities != [1,0,0]) cannot be
+    # generated: the reference's own unbounded rejection sampling (world_state_rt_sim.py:232-311) never
+    # terminates there for N >= 2 and N = 1 crashes in observation_provider_rt.py:790 (probed).
+    "on_ramp_2_B8_N12": dict(st="on_ramp_2_multilane", B=8, N=12, T=40, mode="kwargs", seed=5),
+    "roundabout_2_B8_N12_ttc": dict(st="roundabout_2", B=8, N=12, T=40, mode="params", seed=6,
+                                   extra=dict(rew_method="ttc")),
+    "cpm_entire_B4_N3_k1": dict(st="cpm_entire", B=4, N=3, T=40, mode="params", seed=7,
+                               extra=dict(n_nearing_agents_observed=1)),
+}
+
+
+def stack_agents(agents, get):
+    return torch.stack([get(a) for a in agents], dim=1)
+
+
+def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
+    extra = dict(extra or {})
+    torch.manual_seed(seed)
+    sc = ScenarioRoadTraffic()
+    kw = {}
+    if mode == "params":
+        p = Parameters.from_json("/root/reference/sigmarl/config.json")
+        p.scenario_type = st
+        p.n_agents = N
+        p.num_vmas_envs = B
+        p.max_steps = max_steps
+        for k, v in extra.items():
+            assert hasattr(p, k), k
+            setattr(p, k, v)
+        sc.parameters = p
+    else:
+        kw = dict(scenario_type=st, n_agents=N, is_obs_noise=False)
+        rew_method = extra.pop("rew_method", None)
+        kw.update(extra)
+    env = Environment(sc, num_envs=B, device="cpu", max_steps=max_steps, **kw)
+    if mode == "kwargs":
+        sc.parameters.max_steps = max_steps
+        if rew_method is not None:
+            sc.parameters.rew_method = rew_method
+    ws = sc.world_state
+    agents = env.agents
+    ur = torch.tensor([float(sc.max_speed), float(sc.max_steering)])
+    rec = {}
+
+    def push(k, v):
+        rec.setdefault(k, []).append(np.asarray(v.detach().cpu().numpy() if torch.is_tensor(v) else v).copy())
+
+    def snap_state(prefix):
+        push(prefix + "pos", stack_agents(agents, lambda a: a.state.pos))
+        push(prefix + "rot", stack_agents(agents, lambda a: a.state.rot.squeeze(-1)))
+        push(prefix + "speed", stack_agents(agents, lambda a: a.state.speed.squeeze(-1)))
+        push(prefix + "steering", stack_agents(agents, lambda a: a.state.steering.squeeze(-1)))
+        push(prefix + "path_id", ws.ref_paths_agent_related.path_id.clone())
+        push(prefix + "scenario_id", ws.ref_paths_agent_related.scenario_id.clone())
+
+    for t in range(T):
+        snap_state("pre_")
+        push("pre_step", sc.timer.step.clone())
+        if gentle:
+            acts = [torch.stack([0.3 + 0.4 * torch.rand(B), (torch.rand(B) * 2 - 1) * 0.08], dim=1) for _ in range(N)]
+        else:
+            acts = [(torch.rand(B, 2) * 2 - 1) * ur for _ in range(N)]
+        push("action", torch.stack(acts, dim=1))
+        pid_before = ws.ref_paths_agent_related.point_id.clone()
+        path_before = ws.ref_paths_agent_related.path_id.clone()
+        # intercept per-agent respawns inside done()
+        respawn = torch.zeros(B, N, dtype=torch.bool)
+        orig_reset = sc.reset_world_at
+
+        def spy(env_index=None, agent_index=None, _o=orig_reset, _r=respawn):
+            if agent_index is not None:
+                _r[int(env_index), int(agent_index)] = True
+            return _o(env_index=env_index, agent_index=agent_index)
+
+        sc.reset_world_at = spy
+        # the post-step / pre-respawn state must be captured before done() runs: wrap done
+        orig_done = sc.done
+        holder = {}
+
+        def done_spy(_o=orig_done):
+            holder["pos"] = stack_agents(agents, lambda a: a.state.pos).clone()
+            holder["rot"] = stack_agents(agents, lambda a: a.state.rot.squeeze(-1)).clone()
+            holder["speed"] = stack_agents(agents, lambda a: a.state.speed.squeeze(-1)).clone()
+            holder["steering"] = stack_agents(agents, lambda a: a.state.steering.squeeze(-1)).clone()
+            holder["vel"] = stack_agents(agents, lambda a: a.state.vel).clone()
+            holder["sideslip"] = stack_agents(agents, lambda a: a.state.sideslip_angle.squeeze(-1)).clone()
+            holder["col_agents"] = ws.collisions.with_agents.clone()
+            holder["col_lane"] = ws.collisions.with_lanelets.clone()
+            holder["col_entry"] = ws.collisions.with_entry_segments.clone()
+            holder["col_exit"] = ws.collisions.with_exit_segments.clone()
+            holder["d_ref"] = ws.distances.ref_paths.clone()
+            holder["d_left"] = ws.distances.left_boundaries.clone()
+            holder["d_right"] = ws.distances.right_boundaries.clone()
+            holder["d_bound"] = ws.distances.boundaries.clone()
+            holder["d_agents"] = ws.distances.agents.clone()
+            holder["idx_ref"] = ws.distances.closest_point_on_ref_path.clone()
+            holder["short_term"] = ws.ref_paths_agent_related.short_term.clone()
+            holder["vertices"] = ws.vertices.clone()
+            return _o()
+
+        sc.done = done_spy
+        obs, rew, done, info = env.step(acts)
+        sc.done = orig_done
+        sc.reset_world_at = orig_reset
+        for k, v in holder.items():
+            push(("post_" + k) if k in ("pos", "rot", "speed", "steering", "vel", "sideslip") else k, v)
+        push("obs", torch.stack(obs, dim=1))
+        push("reward", torch.stack(rew, dim=1))
+        push("done", done)
+        push("respawn_mask", respawn)
+        # post-respawn state of respawned agents (read back from the world)
+        push("respawn_pos", stack_agents(agents, lambda a: a.state.pos))
+        push("respawn_rot", stack_agents(agents, lambda a: a.state.rot.squeeze(-1)))
+        push("respawn_speed", stack_agents(agents, lambda a: a.state.speed.squeeze(-1)))
+        push("respawn_path_id", ws.ref_paths_agent_related.path_id.clone())
+        push("respawn_point_id", ws.ref_paths_agent_related.point_id.clone())
+        # env resets, TorchRL-style: reset_at(i) for each done env, then one observation pass
+        reset_obs = torch.zeros(B, N, obs[0].shape[-1])
+        for e in torch.where(done)[0]:
+            o = env.reset_at(int(e), return_observations=True)[0]
+            reset_obs[int(e)] = torch.stack(o, dim=1)[int(e)]
+        push("reset_mask", done)
+        push("reset_obs", reset_obs)
+        push("reset_pos", stack_agents(agents, lambda a: a.state.pos))
+        push("reset_rot", stack_agents(agents, lambda a: a.state.rot.squeeze(-1)))
+        push("reset_speed", stack_agents(agents, lambda a: a.state.speed.squeeze(-1)))
+        push("reset_vel", stack_agents(agents, lambda a: a.state.vel))
+        push("reset_path_id", ws.ref_paths_agent_related.path_id.clone())
+        push("reset_point_id", ws.ref_paths_agent_related.point_id.clone())
+        push("reset_scenario_id", ws.ref_paths_agent_related.scenario_id.clone())
+
+    out = {k: np.stack(v) for k, v in rec.items()}
+    th, pen, nrm = sc.thresholds, sc.penalties, sc.normalizers
+    cfg = dict(
+        scenario_type=st, B=B, N=N, T=T, mode=mode, seed=seed, dt=float(env.world.dt),
+        max_steps=int(sc.parameters.max_steps), rew_method=str(sc.parameters.rew_method),
+        n_nearing_agents_observed=int(sc.parameters.n_nearing_agents_observed),
+        reward_progress=float(sc.rewards.progress),
+        near_boundary_low=float(th.near_boundary_low), near_boundary_high=float(th.near_boundary_high),
+        near_other_agents_low=float(th.near_other_agents_low), near_other_agents_high=float(th.near_other_agents_high),
+        ttc_low=float(th.ttc_low), ttc_high=float(th.ttc_high),
+        penalty_near_boundary=float(pen.near_boundary), penalty_near_other_agents=float(pen.near_other_agents),
+        penalty_collide_with_agents=float(pen.collide_with_agents),
+        penalty_collide_with_boundaries=float(pen.collide_with_boundaries),
+        norm_pos=float(nrm.pos[0]), norm_v=float(nrm.v), norm_rot=float(nrm.rot),
+        norm_distance_lanelet=float(nrm.distance_lanelet),
+        is_testing_mode=bool(sc.parameters.is_testing_mode),
+        max_ref_path_points=int(ws.params.max_ref_path_points), gentle=bool(gentle),
+    )
+    for k, v in cfg.items():
+        out["cfg_" + k] = np.asarray(v)
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: dones={int(out['done'].sum())} respawns={int(out['respawn_mask'].sum())} "
+          f"col_agents={int(out['col_agents'].any(-1).sum())} col_lane={int(out['col_lane'].sum())} "
+          f"size={os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    only = sys.argv[1:]
+    for name, c in CONFIGS.items():
+        if only and name not in only:
+            continue
+        run(name, **c)
