@@ -56,6 +56,9 @@ CONFIGS = {
     "on_ramp_2_B8_N12": dict(st="on_ramp_2_multilane", B=8, N=12, T=40, mode="kwargs", seed=5),
     "roundabout_2_B8_N12_ttc": dict(st="roundabout_2", B=8, N=12, T=40, mode="params", seed=6,
                                    extra=dict(rew_method="ttc")),
+    # forward-driving actions: long episodes, agents reach path ends -> exit crossings + respawns
+    "cpm_mixed_B8_N4_gentle": dict(st="cpm_mixed", B=8, N=4, T=80, mode="params", seed=8, gentle=True,
+                                  extra=dict(rew_method="distance_sparse")),
     "cpm_entire_B4_N3_k1": dict(st="cpm_entire", B=4, N=3, T=40, mode="params", seed=7,
                                extra=dict(n_nearing_agents_observed=1)),
 }
@@ -105,11 +108,18 @@ def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
         push(prefix + "path_id", ws.ref_paths_agent_related.path_id.clone())
         push(prefix + "scenario_id", ws.ref_paths_agent_related.scenario_id.clone())
 
+    last_obs = [sc.observation(a).clone() for a in agents]
     for t in range(T):
         snap_state("pre_")
         push("pre_step", sc.timer.step.clone())
         if gentle:
-            acts = [torch.stack([0.3 + 0.4 * torch.rand(B), (torch.rand(B) * 2 - 1) * 0.08], dim=1) for _ in range(N)]
+            # pure-pursuit on the 2nd short-term reference point seen in the ego frame (obs[3:5])
+            acts = []
+            for i in range(N):
+                o = last_obs[i]
+                steer = torch.clamp(1.5 * torch.atan2(o[:, 4], o[:, 3]) + (torch.rand(B) * 2 - 1) * 0.03,
+                                    -float(sc.max_steering), float(sc.max_steering))
+                acts.append(torch.stack([0.5 + 0.3 * torch.rand(B), steer], dim=1))
         else:
             acts = [(torch.rand(B, 2) * 2 - 1) * ur for _ in range(N)]
         push("action", torch.stack(acts, dim=1))
@@ -171,6 +181,11 @@ def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
         for e in torch.where(done)[0]:
             o = env.reset_at(int(e), return_observations=True)[0]
             reset_obs[int(e)] = torch.stack(o, dim=1)[int(e)]
+        last_obs = [o.clone() for o in obs]
+        if done.any():
+            fresh = [sc.observation(a) for a in agents]
+            for i in range(N):
+                last_obs[i][done] = fresh[i][done]
         push("reset_mask", done)
         push("reset_obs", reset_obs)
         push("reset_pos", stack_agents(agents, lambda a: a.state.pos))

@@ -1,0 +1,654 @@
+/*
+ * sigmarl_oracle.c — TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT PATH.
+ *
+ * A plain-C, scalar-fp32 CPU restatement of SigmaRL's vectorised road-traffic environment
+ * step, written in the reference's own *sequential* order (world.step -> for each agent
+ * {reward, observation} -> done) with the reference's own persistent world state, so that the
+ * one-step-stale values the VMAS call order produces fall out of the ordering
+ * instead of being coded as formulas.  Every function cites the reference file:line it follows
+ * (paths are relative to /root/reference/sigmarl/).
+ *
+ * PARITY PINNING: the reference's own tests hold no golden vector for this path,
+ * and two pieces of arithmetic live in un-vendored dependencies (torchdiffeq==0.2.5 fixed-grid
+ * Euler, vmas==1.4.3 call order).  This oracle is therefore pinned against outputs of the
+ * UNMODIFIED reference code run in the build container behind an import shim
+ * (oracle/refshim/install_shims.py, oracle/gen_golden.py -> tests/golden/ *.npz); see
+ * tests/test_oracle_golden.py.  Only tests/, __graft_entry__.smoke() and bench.py's CPU
+ * baseline legs may load this file.
+ *
+ * Build: gcc -O2 -pthread -ffp-contract=off -fno-fast-math -shared -fPIC (oracle/Makefile).
+ * -ffp-contract=off matters: the reference evaluates every ATen op with its own rounding, and
+ * argmin / strict-sign decisions below depend on it.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MAX_AGENTS 32
+#define ORC_NST 3 /* n_points_short_term */
+
+typedef struct {
+    int n_paths, P;                        /* P = max_ref_path_points (road_traffic.py:505-530) */
+    const float *center, *left, *right;    /* [n_paths][P][2], padded as world_state_rt.py:313-392 */
+    const int *n_center, *n_left, *n_right;
+    const uint8_t *is_loop;
+    const float *yaw;                      /* [n_paths][P] center_line_yaw (n_center-1 valid) */
+} orc_map;
+
+typedef struct {
+    float dt, max_speed, max_steering, max_acc, max_steering_rate;
+    float l_wb, lr_over_lwb, half_length, half_width, diag;
+    float w_ref[ORC_NST];
+    float speed_dt;          /* float32(max_speed * dt)            road_traffic.py:986 */
+    float reward_progress;
+    float nb_low, nb_high, na_low, na_high, ttc_low, ttc_high;
+    float pen_near_boundary, pen_near_agents, pen_collide_agents, pen_collide_lane;
+    float norm_pos, norm_v, norm_rot, norm_dist;
+    float dsafe_sq;          /* float32(d_safe*d_safe in double)    road_traffic.py:1291 */
+    float reset_min_dist_sq; /* reset_agent_min_distance**2         world_state_rt_sim.py:305 */
+    int rew_exact_sparse, rew_has_ttc, rew_has_distance, rew_has_sparse;
+    int k_near, max_steps, is_cpm_entire, sample_interval;
+} orc_cfg;
+
+typedef struct {
+    int B, N;
+    orc_map map;
+    orc_cfg cfg;
+    /* agent state (helper_common.py:290-430) */
+    float *pos, *rot, *speed, *steering, *vel, *sideslip; /* [B][N][2|1] */
+    int *path_id;                                         /* global path index */
+    /* world state (world_state_rt.py:119-277, world_state_rt_sim.py:36-55) */
+    float *vertices;                                      /* [B][N][5][2] */
+    float *d_agents;                                      /* [B][N][N] */
+    float *d_ref, *d_left, *d_right, *d_bound;            /* [B][N], [B][N][5] */
+    int *idx_ref;
+    float *short_term;                                    /* [B][N][3][2] */
+    float *prev_pos;                                      /* state_buffer latest */
+    uint8_t *col_agents, *col_lane, *col_entry, *col_exit;
+    int *step;                                            /* timer.step [B] */
+} orc_world;
+
+/* ---------------------------------------------------------------- geometry primitives */
+
+/* helper_scenario.py:829-889 get_perpendicular_distances.  Returns min distance, *idx = argmin+1. */
+static float orc_perp(const float p[2], const float *poly, int P, int n, int *idx) {
+    float d[1024];
+    int S = P - 1;
+    for (int s = 0; s < S; s++) {
+        float ax = poly[2 * s], ay = poly[2 * s + 1];
+        float bx = poly[2 * s + 2], by = poly[2 * s + 3];
+        float lx = bx - ax, ly = by - ay;                 /* line_vecs  :857 */
+        float px = p[0] - ax, py = p[1] - ay;             /* point_vecs :858 */
+        float len2 = lx * lx + ly * ly;                   /* :861 */
+        float t = (px * lx + py * ly) / len2;             /* :862 */
+        /* torch.clamp(x, 0, 1) propagates NaN :865 */
+        if (t < 0.0f) t = 0.0f;
+        else if (t > 1.0f) t = 1.0f;
+        float cx = ax + lx * t, cy = ay + ly * t;         /* :868 */
+        float ex = cx - p[0], ey = cy - p[1];
+        d[s] = sqrtf(ex * ex + ey * ey);                  /* torch.norm :871 */
+    }
+    for (int s = n - 1; s < S; s++) d[s] = d[n - 2];      /* :873-879 */
+    int best = 0;
+    float bd = d[0];
+    for (int s = 1; s < S; s++) {                         /* torch.min: first minimal index :883 */
+        if (d[s] < bd || (d[s] != d[s] && bd == bd)) { bd = d[s]; best = s; }
+    }
+    *idx = best + 1;                                      /* :885-887 */
+    return bd;
+}
+
+/* helper_scenario.py:1148-1229 interX (is_return_points=False): any strict segment crossing. */
+static int orc_interx(const float *L1, int n1, const float *L2, int n2) {
+    int hit = 0;
+    for (int i = 0; i + 1 < n1; i++) {
+        float x1a = L1[2 * i], y1a = L1[2 * i + 1], x1b = L1[2 * i + 2], y1b = L1[2 * i + 3];
+        float dx1 = x1b - x1a, dy1 = y1b - y1a;
+        float S1 = dx1 * y1a - dy1 * x1a;                 /* :1176 */
+        for (int j = 0; j + 1 < n2; j++) {
+            float x2a = L2[2 * j], y2a = L2[2 * j + 1], x2b = L2[2 * j + 2], y2b = L2[2 * j + 3];
+            float dx2 = x2b - x2a, dy2 = y2b - y2a;
+            float S2 = dx2 * y2a - dy2 * x2a;             /* :1177 */
+            float f_a = (dx1 * y2a - dy1 * x2a) - S1;     /* :1183-1189 */
+            float f_b = (dx1 * y2b - dy1 * x2b) - S1;
+            int C1 = (f_a * f_b) < 0.0f;
+            float g_a = (y1a * dx2 - x1a * dy2) - S2;     /* :1190-1198 */
+            float g_b = (y1b * dx2 - x1b * dy2) - S2;
+            int C2 = (g_a * g_b) < 0.0f;
+            hit |= (C1 & C2);
+        }
+    }
+    return hit;
+}
+
+/* helper_scenario.py:695-826 get_rectangle_vertices (closed, 5 vertices); the 2x2 . 2x5 matmul
+ * goes through ATen's small-matrix kernel: r = c*vx, r += (-s)*vy with float accumulation. */
+static void orc_rect(const orc_cfg *c, const float pos[2], float yaw, float *out) {
+    const float hl = c->half_length, hw = c->half_width;
+    const float bx[5] = {hl, hl, -hl, -hl, hl};
+    const float by[5] = {hw, -hw, -hw, hw, hw};
+    float cy = cosf(yaw), sy = sinf(yaw);
+    float nsy = -sy;
+    for (int v = 0; v < 5; v++) {
+        float rx = cy * bx[v] + nsy * by[v];
+        float ry = sy * bx[v] + cy * by[v];
+        out[2 * v] = rx + pos[0];
+        out[2 * v + 1] = ry + pos[1];
+    }
+}
+
+/* helper_scenario.py:1276-1289 angle_eliminate_two_pi */
+static float orc_wrap(float a) {
+    const float two_pi = (float)(2.0 * M_PI);
+    float m = fmodf(a, two_pi);                           /* torch `%`: sign of divisor */
+    if (m != 0.0f && m < 0.0f) m += two_pi;
+    if (m > (float)M_PI) m -= two_pi;
+    return m;
+}
+
+/* helper_scenario.py:1241-1273 transform_from_global_to_local_coordinate (one point) */
+static void orc_local(const float pi[2], float rot_i, const float pj[2], float out[2]) {
+    float vx = pj[0] - pi[0], vy = pj[1] - pi[1];
+    float a = sqrtf(vx * vx + vy * vy);
+    float r = atan2f(vy, vx) - rot_i;
+    out[0] = cosf(r) * a;
+    out[1] = sinf(r) * a;
+}
+
+/* helper_scenario.py:960-996 decreasing_fcn(type="linear") */
+static float orc_dec(float x, float x0, float x1) {
+    if (x < x0) x = x0;
+    else if (x > x1) x = x1;
+    float denom = x1 - x0;
+    return 1.0f - (x - x0) / denom;
+}
+
+/* helper_scenario.py:892-957 get_short_term_reference_path (n_points_shift=1) */
+static void orc_short_term(const orc_world *w, int path, int idx, float *out) {
+    const orc_map *m = &w->map;
+    int n = m->n_center[path];
+    const float *poly = m->center + (size_t)path * m->P * 2;
+    for (int k = 0; k < ORC_NST; k++) {
+        int fi = k * w->cfg.sample_interval + idx + 1;    /* :928-932 */
+        if (m->is_loop[path] && fi >= n - 1) fi = (fi + 1) % n; /* :941-946 */
+        out[2 * k] = poly[2 * fi];
+        out[2 * k + 1] = poly[2 * fi + 1];
+    }
+}
+
+/* ---------------------------------------------------------------- world-state updates */
+
+#define AG(b, a) ((size_t)(b) * N + (a))
+
+/* world_state_rt_sim.py:360-373 + helper_scenario.py:1012-1029,1140-1143 (c2c) */
+static void orc_mutual(orc_world *w, int b) {
+    int N = w->N;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) {
+            float dx = w->pos[AG(b, i) * 2] - w->pos[AG(b, j) * 2];
+            float dy = w->pos[AG(b, i) * 2 + 1] - w->pos[AG(b, j) * 2 + 1];
+            float d = sqrtf(dx * dx + dy * dy);
+            if (i == j) d = w->cfg.diag;
+            w->d_agents[(AG(b, i)) * N + j] = d;
+        }
+}
+
+/* world_state_rt.py:582-656 update_distances (the per-agent part) */
+static void orc_update_distances(orc_world *w, int b, int i) {
+    int N = w->N;
+    const orc_map *m = &w->map;
+    size_t g = AG(b, i);
+    int path = w->path_id[g];
+    const float *cen = m->center + (size_t)path * m->P * 2;
+    const float *lef = m->left + (size_t)path * m->P * 2;
+    const float *rig = m->right + (size_t)path * m->P * 2;
+    int dummy;
+    w->d_ref[g] = orc_perp(&w->pos[g * 2], cen, m->P, m->n_center[path], &w->idx_ref[g]);
+    w->d_left[g * 5] = orc_perp(&w->pos[g * 2], lef, m->P, m->n_left[path], &dummy) - w->cfg.half_width;
+    w->d_right[g * 5] = orc_perp(&w->pos[g * 2], rig, m->P, m->n_right[path], &dummy) - w->cfg.half_width;
+    for (int c = 0; c < 4; c++) {
+        const float *v = &w->vertices[(g * 5 + c) * 2];
+        w->d_left[g * 5 + c + 1] = orc_perp(v, lef, m->P, m->n_left[path], &dummy);
+        w->d_right[g * 5 + c + 1] = orc_perp(v, rig, m->P, m->n_right[path], &dummy);
+    }
+    float mn = w->d_left[g * 5];
+    for (int c = 0; c < 5; c++) {
+        if (w->d_left[g * 5 + c] < mn) mn = w->d_left[g * 5 + c];
+        if (w->d_right[g * 5 + c] < mn) mn = w->d_right[g * 5 + c];
+    }
+    w->d_bound[g] = mn;
+}
+
+/* world_state_rt_sim.py:379-424 update_collisions */
+static void orc_update_collisions(orc_world *w, int b) {
+    int N = w->N;
+    const orc_map *m = &w->map;
+    for (int i = 0; i < N; i++) {
+        size_t g = AG(b, i);
+        const float *vi = &w->vertices[g * 10];
+        for (int j = i + 1; j < N; j++) {
+            if (orc_interx(vi, 5, &w->vertices[AG(b, j) * 10], 5)) {
+                w->col_agents[g * N + j] = 1;
+                w->col_agents[AG(b, j) * N + i] = 1;
+            }
+        }
+        int path = w->path_id[g];
+        const float *lef = m->left + (size_t)path * m->P * 2;
+        const float *rig = m->right + (size_t)path * m->P * 2;
+        if (orc_interx(vi, 5, lef, m->P) | orc_interx(vi, 5, rig, m->P)) w->col_lane[g] = 1;
+        /* entry/exit only when no env has this agent on a loop (:414); a map set is all-loop or
+         * no-loop, so this is a per-path flag here. */
+        if (!m->is_loop[path]) {
+            float entry[4] = {lef[0], lef[1], rig[0], rig[1]};   /* world_state_rt.py:394-406 */
+            int nl = m->n_left[path], nr = m->n_right[path];
+            float exit_[4] = {lef[2 * (nl - 1)], lef[2 * (nl - 1) + 1], rig[2 * (nr - 1)], rig[2 * (nr - 1) + 1]};
+            w->col_entry[g] = (uint8_t)orc_interx(vi, 5, entry, 2);
+            w->col_exit[g] = (uint8_t)orc_interx(vi, 5, exit_, 2);
+        }
+    }
+}
+
+static void orc_reset_collisions(orc_world *w, int b) {
+    int N = w->N;
+    memset(&w->col_agents[AG(b, 0) * N], 0, (size_t)N * N);
+    memset(&w->col_lane[AG(b, 0)], 0, N);
+    memset(&w->col_entry[AG(b, 0)], 0, N);
+    memset(&w->col_exit[AG(b, 0)], 0, N);
+}
+
+/* world_state_rt.py:422-529 reset_init_distances_and_short_term_ref_path: everything fresh */
+static void orc_refresh_agent(orc_world *w, int b, int i) {
+    int N = w->N;
+    size_t g = AG(b, i);
+    orc_rect(&w->cfg, &w->pos[g * 2], w->rot[g], &w->vertices[g * 10]);
+    orc_update_distances(w, b, i); /* same 11 scans, but vertices are fresh here (:470-476) */
+    orc_short_term(w, w->path_id[g], w->idx_ref[g], &w->short_term[g * 6]);
+}
+
+/* road_traffic.py:897-923: after (re)placing agents of env b (all agents, or one respawned agent). */
+void orc_refresh_env(orc_world *w, int b, int agent /* -1 = all */) {
+    int N = w->N;
+    for (int i = 0; i < N; i++)
+        if (agent < 0 || agent == i) orc_refresh_agent(w, b, i);
+    orc_mutual(w, b);
+    orc_reset_collisions(w, b);
+    for (int i = 0; i < N; i++) { /* state_buffer.reset(); add(current) :910-923 */
+        w->prev_pos[AG(b, i) * 2] = w->pos[AG(b, i) * 2];
+        w->prev_pos[AG(b, i) * 2 + 1] = w->pos[AG(b, i) * 2 + 1];
+    }
+}
+
+/* ---------------------------------------------------------------- dynamics */
+
+/* helper_training.py:797-861 WorldCustom.step + dynamics.py:62-192 (Euler, one tick) */
+static void orc_dynamics(orc_world *w, int b, int a, float *action /* in/out: clamped */) {
+    int N = w->N;
+    const orc_cfg *c = &w->cfg;
+    size_t g = AG(b, a);
+    float u0 = action[0], u1 = action[1];
+    if (u0 < -c->max_speed) u0 = -c->max_speed; else if (u0 > c->max_speed) u0 = c->max_speed;
+    if (u1 < -c->max_steering) u1 = -c->max_steering; else if (u1 > c->max_steering) u1 = c->max_steering;
+    action[0] = u0; action[1] = u1;                       /* written back :808-818 */
+    float v = w->speed[g], delta = w->steering[g], psi = w->rot[g];
+    float acc = (u0 - v) / c->dt;                         /* :821 */
+    float rate = (u1 - delta) / c->dt;
+    if (acc < -c->max_acc) acc = -c->max_acc; else if (acc > c->max_acc) acc = c->max_acc;
+    if (rate < -c->max_steering_rate) rate = -c->max_steering_rate;
+    else if (rate > c->max_steering_rate) rate = c->max_steering_rate;
+    float td = tanf(delta);
+    float beta = atanf(c->lr_over_lwb * td);              /* dynamics.py:102 */
+    float f0 = v * cosf(psi + beta);
+    float f1 = v * sinf(psi + beta);
+    float f2 = ((v / c->l_wb) * td) * cosf(beta);         /* :108-110 */
+    /* torchdiffeq fixed-grid Euler: y1 = y0 + (t1 - t0) * f(t0, y0) */
+    float x1 = w->pos[g * 2] + c->dt * f0;
+    float y1 = w->pos[g * 2 + 1] + c->dt * f1;
+    float psi1 = psi + c->dt * f2;
+    float v1 = v + c->dt * acc;
+    float d1 = delta + c->dt * rate;
+    const float pi_f = (float)M_PI, two_pi = (float)(2.0 * M_PI);
+    float t = d1 + pi_f;                                  /* :158 */
+    float mth = fmodf(t, two_pi);
+    if (mth != 0.0f && mth < 0.0f) mth += two_pi;
+    d1 = mth - pi_f;
+    float beta1 = atanf(c->lr_over_lwb * tanf(d1));       /* :161-163 */
+    float course = psi1 + beta1;
+    w->pos[g * 2] = x1; w->pos[g * 2 + 1] = y1;
+    w->rot[g] = psi1; w->speed[g] = v1; w->steering[g] = d1;
+    w->vel[g * 2] = v1 * cosf(course);
+    w->vel[g * 2 + 1] = v1 * sinf(course);
+    w->sideslip[g] = beta1;
+}
+
+/* ---------------------------------------------------------------- reward / observation */
+
+/* road_traffic.py:1255-1332 */
+static float orc_ttc_penalty(const orc_world *w, int b, int i) {
+    int N = w->N;
+    const orc_cfg *c = &w->cfg;
+    const float eps = 1e-6f;
+    float sum = 0.0f;
+    for (int j = 0; j < N; j++) {
+        float px = w->pos[AG(b, j) * 2] - w->pos[AG(b, i) * 2];
+        float py = w->pos[AG(b, j) * 2 + 1] - w->pos[AG(b, i) * 2 + 1];
+        float vx = w->vel[AG(b, j) * 2] - w->vel[AG(b, i) * 2];
+        float vy = w->vel[AG(b, j) * 2 + 1] - w->vel[AG(b, i) * 2 + 1];
+        float qa = vx * vx + vy * vy;
+        float qb = 2.0f * (px * vx + py * vy);
+        float pp = px * px + py * py;
+        float qc = pp - c->dsafe_sq;
+        float disc = qb * qb - (4.0f * qa) * qc;
+        float sq = sqrtf(disc < 0.0f ? 0.0f : disc);
+        float dist = sqrtf(pp < 0.0f ? 0.0f : pp);
+        int valid = (qa > eps) && (disc > 0.0f) && (qb < 0.0f);
+        float cand = (-qb - sq) / (2.0f * qa + eps);
+        float ttc = INFINITY;
+        if (valid && cand > 0.0f) ttc = cand;
+        if (dist <= c->na_low) ttc = 0.0f;
+        if (j == i) ttc = INFINITY;
+        if (!(dist <= c->na_high)) ttc = INFINITY;
+        if (ttc > c->ttc_high) ttc = c->ttc_high;
+        sum += orc_dec(ttc, c->ttc_low, c->ttc_high);
+    }
+    float risk = sum / (float)(N - 1 > 1 ? N - 1 : 1);
+    return risk * c->pen_near_agents;
+}
+
+/* road_traffic.py:925-1253 reward(agent i) for env b, incl. the state updates it triggers */
+static float orc_reward(orc_world *w, int b, int i) {
+    int N = w->N;
+    const orc_cfg *c = &w->cfg;
+    size_t g = AG(b, i);
+    if (i == 0) w->step[b] += 1;                          /* :954-962 */
+    /* update_state_before_rewarding world_state_rt_sim.py:432-448 */
+    if (i == 0) orc_mutual(w, b);
+    orc_update_distances(w, b, i);
+    if (i == 0) {
+        orc_reset_collisions(w, b);
+        for (int a = 0; a < N; a++) orc_rect(c, &w->pos[AG(b, a) * 2], w->rot[AG(b, a)], &w->vertices[AG(b, a) * 10]);
+        orc_update_collisions(w, b);
+    }
+    /* forward movement :971-989 */
+    float mvx = w->pos[g * 2] - w->prev_pos[g * 2], mvy = w->pos[g * 2 + 1] - w->prev_pos[g * 2 + 1];
+    float acc = 0.0f;
+    for (int k = 0; k < ORC_NST; k++) {
+        float rx = w->short_term[g * 6 + 2 * k] - w->prev_pos[g * 2];
+        float ry = w->short_term[g * 6 + 2 * k + 1] - w->prev_pos[g * 2 + 1];
+        float mp = mvx * rx + mvy * ry;
+        acc += mp * c->w_ref[k];                          /* torch.matmul [B,3].[3] */
+    }
+    float rew = 0.0f;
+    rew += (acc / c->speed_dt) * c->reward_progress;
+    int any_a2a = 0;
+    for (int j = 0; j < N; j++) any_a2a |= w->col_agents[g * N + j];
+    float pen_a2a = (float)any_a2a * c->pen_collide_agents;
+    float pen_lane = (float)w->col_lane[g] * c->pen_collide_lane;
+    float pen_nb = orc_dec(w->d_bound[g], c->nb_low, c->nb_high) * c->pen_near_boundary; /* :1040-1048 */
+    if (c->rew_exact_sparse) { rew += pen_a2a; rew += pen_lane; }                      /* :1058-1062 */
+    if (c->rew_has_ttc) {                                                               /* :1064-1085 */
+        rew += orc_ttc_penalty(w, b, i);
+        rew += pen_nb;
+        rew += pen_a2a; rew += pen_lane;
+        if (c->rew_has_sparse) { rew += pen_a2a; rew += pen_lane; }
+    }
+    if (c->rew_has_distance) {                                                          /* :1087-1112 */
+        float s = 0.0f;
+        for (int j = 0; j < N; j++) s += orc_dec(w->d_agents[g * N + j], c->na_low, c->na_high);
+        rew += s * c->pen_near_agents;
+        rew += pen_nb;
+        if (c->rew_has_sparse) { rew += pen_a2a; rew += pen_lane; }
+    }
+    if (i == N - 1)                                       /* state_buffer.add :1226-1240 */
+        for (int a = 0; a < N; a++) {
+            w->prev_pos[AG(b, a) * 2] = w->pos[AG(b, a) * 2];
+            w->prev_pos[AG(b, a) * 2 + 1] = w->pos[AG(b, a) * 2 + 1];
+        }
+    orc_short_term(w, w->path_id[g], w->idx_ref[g], &w->short_term[g * 6]); /* :1243, world_state_rt.py:668 */
+    if (rew < -1.0f) rew = -1.0f; else if (rew > 1.0f) rew = 1.0f;          /* :1249 */
+    return rew;
+}
+
+/* what observation_provider_rt.py:345-588 update_state snapshots at observation(agent 0) time and
+ * that later reward(i>=1) calls would otherwise overwrite */
+typedef struct {
+    float short_term[ORC_MAX_AGENTS][6];
+    float d_ref[ORC_MAX_AGENTS], min_l[ORC_MAX_AGENTS], min_r[ORC_MAX_AGENTS];
+} orc_snap;
+
+static void orc_take_snapshot(const orc_world *w, int b, orc_snap *s) {
+    int N = w->N;
+    for (int j = 0; j < N; j++) {
+        size_t g = AG(b, j);
+        memcpy(s->short_term[j], &w->short_term[g * 6], 6 * sizeof(float));
+        s->d_ref[j] = w->d_ref[g];
+        float ml = w->d_left[g * 5], mr = w->d_right[g * 5];
+        for (int c = 1; c < 5; c++) {
+            if (w->d_left[g * 5 + c] < ml) ml = w->d_left[g * 5 + c];
+            if (w->d_right[g * 5 + c] < mr) mr = w->d_right[g * 5 + c];
+        }
+        s->min_l[j] = ml; s->min_r[j] = mr;
+    }
+}
+
+/* observation_provider_rt.py:594-925 get_observation, default flags (ego view, partial obs,
+ * vertices, distance to agents/boundaries/centre line, no mask/noise/steering). D = 10 + 11 k. */
+static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, float *obs) {
+    int N = w->N;
+    const orc_cfg *c = &w->cfg;
+    size_t g = AG(b, i);
+    const float *pi = &w->pos[g * 2];
+    float rot_i = w->rot[g];
+    int o = 0;
+    /* own speed: past_vel[i,i,0] = |vel_i| * cos(wrap(0)) / v_norm  (:434-441, :866-869) */
+    {
+        float vabs = sqrtf(w->vel[g * 2] * w->vel[g * 2] + w->vel[g * 2 + 1] * w->vel[g * 2 + 1]);
+        float rr = orc_wrap(rot_i - rot_i);
+        obs[o++] = (vabs * cosf(rr)) / c->norm_v;
+    }
+    for (int k = 0; k < ORC_NST; k++) {                   /* own short-term path :444-452 */
+        float loc[2];
+        orc_local(pi, rot_i, &s->short_term[i][2 * k], loc);
+        obs[o++] = loc[0] / c->norm_pos;
+        obs[o++] = loc[1] / c->norm_pos;
+    }
+    obs[o++] = s->d_ref[i] / c->norm_dist;                /* :373-375 */
+    obs[o++] = s->min_l[i] / c->norm_dist;                /* :376-383 */
+    obs[o++] = s->min_r[i] / c->norm_dist;
+    /* torch.topk(distances.agents[:, i], k, largest=False) :627-636 */
+    int used[ORC_MAX_AGENTS] = {0};
+    for (int kk = 0; kk < c->k_near; kk++) {
+        int bj = -1;
+        float bd = INFINITY;
+        for (int j = 0; j < N; j++)
+            if (!used[j] && (bj < 0 || w->d_agents[g * N + j] < bd)) { bd = w->d_agents[g * N + j]; bj = j; }
+        used[bj] = 1;
+        size_t gj = AG(b, bj);
+        for (int v = 0; v < 4; v++) {                     /* vertices :484-492 */
+            float loc[2];
+            orc_local(pi, rot_i, &w->vertices[(gj * 5 + v) * 2], loc);
+            obs[o++] = loc[0] / c->norm_pos;
+            obs[o++] = loc[1] / c->norm_pos;
+        }
+        float rr = orc_wrap(w->rot[gj] - rot_i);          /* :427 */
+        float vabs = sqrtf(w->vel[gj * 2] * w->vel[gj * 2] + w->vel[gj * 2 + 1] * w->vel[gj * 2 + 1]);
+        obs[o++] = (vabs * cosf(rr)) / c->norm_v;         /* :432-441 */
+        obs[o++] = (vabs * sinf(rr)) / c->norm_v;
+        obs[o++] = bd / c->norm_dist;                     /* :369-371 */
+    }
+}
+
+int orc_obs_dim(const orc_world *w) { return 10 + 11 * w->cfg.k_near; }
+
+/* ---------------------------------------------------------------- the step */
+
+/* vmas Environment.step order: world.step(); for agent i: reward(i), observation(i);
+ * done().  Outputs: obs [B][N][D], reward [B][N], done [B], respawn_request [B][N]. */
+typedef struct {
+    orc_world *w;
+    float *actions, *obs, *reward;
+    uint8_t *done, *respawn_request;
+    int b0, b1;
+} orc_job;
+
+static void *orc_step_range(void *arg) {
+    orc_job *jb = (orc_job *)arg;
+    orc_world *w = jb->w;
+    int N = w->N, D = orc_obs_dim(w);
+    for (int b = jb->b0; b < jb->b1; b++) {
+        for (int a = 0; a < N; a++) orc_dynamics(w, b, a, &jb->actions[AG(b, a) * 2]);
+        orc_snap snap;
+        for (int i = 0; i < N; i++) {
+            jb->reward[AG(b, i)] = orc_reward(w, b, i);
+            if (i == 0) orc_take_snapshot(w, b, &snap);
+            orc_observe(w, b, i, &snap, &jb->obs[AG(b, i) * D]);
+        }
+        /* done() road_traffic.py:1368-1487 (training mode) */
+        int any = (w->step[b] == w->cfg.max_steps - 1);
+        for (int a = 0; a < N; a++) {
+            any |= w->col_lane[AG(b, a)];
+            for (int j = 0; j < N; j++) any |= w->col_agents[AG(b, a) * N + j];
+        }
+        jb->done[b] = (uint8_t)any;
+        for (int a = 0; a < N; a++)
+            jb->respawn_request[AG(b, a)] =
+                (uint8_t)(!w->cfg.is_cpm_entire && !any && (w->col_entry[AG(b, a)] | w->col_exit[AG(b, a)]));
+    }
+    return NULL;
+}
+
+/* n_threads <= 1: run inline; otherwise envs are split in contiguous ranges over pthreads (envs are
+ * independent; the image's gcc has no libgomp). */
+void orc_step(orc_world *w, float *actions, float *obs, float *reward, uint8_t *done, uint8_t *respawn_request,
+              int n_threads) {
+    int B = w->B;
+    if (n_threads > B) n_threads = B;
+    if (n_threads <= 1) {
+        orc_job jb = {w, actions, obs, reward, done, respawn_request, 0, B};
+        orc_step_range(&jb);
+        return;
+    }
+    pthread_t th[256];
+    orc_job jobs[256];
+    if (n_threads > 256) n_threads = 256;
+    for (int t = 0; t < n_threads; t++) {
+        jobs[t] = (orc_job){w, actions, obs, reward, done, respawn_request,
+                            (int)((long long)B * t / n_threads), (int)((long long)B * (t + 1) / n_threads)};
+        pthread_create(&th[t], NULL, orc_step_range, &jobs[t]);
+    }
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+}
+
+/* Observation pass right after a reset (vmas Environment.reset_at -> get_from_scenario(obs only)):
+ * observation(0) snapshots a world state in which everything is fresh. */
+void orc_fresh_obs(orc_world *w, float *obs) {
+    int N = w->N, D = orc_obs_dim(w);
+    for (int b = 0; b < w->B; b++) {
+        orc_snap snap;
+        orc_take_snapshot(w, b, &snap);
+        for (int i = 0; i < N; i++) orc_observe(w, b, i, &snap, &obs[AG(b, i) * D]);
+    }
+}
+
+/* ---------------------------------------------------------------- reset (own RNG; distribution of
+ * world_state_rt_sim.py:215-311: uniform path, uniform point in [3, n/2), >= min distance apart) */
+static uint64_t orc_rng_next(uint64_t *s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+/* place agent `a` of env b at (path, point) with speed; world_state_rt_sim.py:143-213 */
+void orc_place(orc_world *w, int b, int a, int path, int point, float speed) {
+    int N = w->N;
+    const orc_map *m = &w->map;
+    size_t g = AG(b, a);
+    w->path_id[g] = path;
+    w->pos[g * 2] = m->center[((size_t)path * m->P + point) * 2];
+    w->pos[g * 2 + 1] = m->center[((size_t)path * m->P + point) * 2 + 1];
+    float yaw = m->yaw[(size_t)path * m->P + point];
+    w->rot[g] = yaw;
+    w->steering[g] = 0.0f;
+    w->sideslip[g] = 0.0f;
+    w->speed[g] = speed;
+    w->vel[g * 2] = speed * cosf(0.0f + yaw);
+    w->vel[g * 2 + 1] = speed * sinf(0.0f + yaw);
+}
+
+/* full reset of env b (agent < 0) or respawn of one agent; returns 0, or -1 if no feasible placement
+ * was found in `max_tries` (the reference would spin forever). */
+int orc_reset_env(orc_world *w, int b, int agent, int path_lo, int path_hi, uint64_t *rng, int max_tries) {
+    int N = w->N;
+    const orc_map *m = &w->map;
+    for (int a = 0; a < N; a++) {
+        if (agent >= 0 && a != agent) continue;
+        int ok = 0;
+        for (int tries = 0; tries < max_tries && !ok; tries++) {
+            int path = path_lo + (int)(orc_rng_next(rng) % (uint64_t)(path_hi - path_lo));
+            int end = m->n_center[path] / 2;
+            int point = 3 + (int)(orc_rng_next(rng) % (uint64_t)(end - 3));
+            const float *p = &m->center[((size_t)path * m->P + point) * 2];
+            ok = 1;
+            int lim = (agent >= 0) ? N : a;
+            for (int o = 0; o < lim && ok; o++) {
+                if (o == a) continue;
+                float dx = p[0] - w->pos[AG(b, o) * 2], dy = p[1] - w->pos[AG(b, o) * 2 + 1];
+                float dsq = dx * dx + dy * dy;
+                if (!(dsq >= w->cfg.reset_min_dist_sq)) ok = 0;
+            }
+            if (ok) {
+                float speed = (float)((orc_rng_next(rng) >> 40) * (1.0 / 16777216.0)) * w->cfg.max_speed;
+                orc_place(w, b, a, path, point, speed);
+            }
+        }
+        if (!ok) return -1;
+    }
+    if (agent < 0) w->step[b] = 0;
+    orc_refresh_env(w, b, agent);
+    return 0;
+}
+
+/* ---------------------------------------------------------------- lifetime */
+
+orc_world *orc_create(int B, int N, const orc_map *map, const orc_cfg *cfg) {
+    if (N > ORC_MAX_AGENTS || map->P > 1024) return NULL;
+    orc_world *w = (orc_world *)calloc(1, sizeof(orc_world));
+    w->B = B; w->N = N; w->map = *map; w->cfg = *cfg;
+    size_t BN = (size_t)B * N;
+    w->pos = calloc(BN * 2, 4); w->rot = calloc(BN, 4); w->speed = calloc(BN, 4);
+    w->steering = calloc(BN, 4); w->vel = calloc(BN * 2, 4); w->sideslip = calloc(BN, 4);
+    w->path_id = calloc(BN, 4); w->vertices = calloc(BN * 10, 4); w->d_agents = calloc(BN * N, 4);
+    w->d_ref = calloc(BN, 4); w->d_left = calloc(BN * 5, 4); w->d_right = calloc(BN * 5, 4);
+    w->d_bound = calloc(BN, 4); w->idx_ref = calloc(BN, 4); w->short_term = calloc(BN * 6, 4);
+    w->prev_pos = calloc(BN * 2, 4); w->col_agents = calloc(BN * N, 1); w->col_lane = calloc(BN, 1);
+    w->col_entry = calloc(BN, 1); w->col_exit = calloc(BN, 1); w->step = calloc(B, 4);
+    return w;
+}
+
+void orc_destroy(orc_world *w) {
+    if (!w) return;
+    free(w->pos); free(w->rot); free(w->speed); free(w->steering); free(w->vel); free(w->sideslip);
+    free(w->path_id); free(w->vertices); free(w->d_agents); free(w->d_ref); free(w->d_left);
+    free(w->d_right); free(w->d_bound); free(w->idx_ref); free(w->short_term); free(w->prev_pos);
+    free(w->col_agents); free(w->col_lane); free(w->col_entry); free(w->col_exit); free(w->step);
+    free(w);
+}
+
+/* raw field access for the ctypes wrapper (name -> pointer) */
+void *orc_field(orc_world *w, const char *name) {
+#define F(n) if (!strcmp(name, #n)) return (void *)w->n;
+    F(pos) F(rot) F(speed) F(steering) F(vel) F(sideslip) F(path_id) F(vertices) F(d_agents) F(d_ref)
+    F(d_left) F(d_right) F(d_bound) F(idx_ref) F(short_term) F(prev_pos) F(col_agents) F(col_lane)
+    F(col_entry) F(col_exit) F(step)
+#undef F
+    return NULL;
+}
+
+/* function-level entry points for known-answer tests */
+float orc_test_perp(const float *p, const float *poly, int P, int n, int *idx) { return orc_perp(p, poly, P, n, idx); }
+int orc_test_interx(const float *L1, int n1, const float *L2, int n2) { return orc_interx(L1, n1, L2, n2); }
+void orc_test_rect(float hl, float hw, const float *pos, float yaw, float *out) {
+    orc_cfg c; memset(&c, 0, sizeof c); c.half_length = hl; c.half_width = hw; orc_rect(&c, pos, yaw, out);
+}

@@ -1,0 +1,102 @@
+"""CPU: pin the C oracle (oracle/sigmarl_oracle.c) against golden vectors produced by the UNMODIFIED
+reference (oracle/gen_golden.py, run behind the import shim).  Teacher-forced: every step starts from
+the reference's recorded pre-step state, so this also checks SURVEY.md A.6's claim that the step is a
+pure function of the pre-step state.
+
+Tolerances: bit-exact for done / collision masks / closest-point indices / short-term path points;
+1e-5 abs (BASELINE.json north_star) for fp32 state, obs and reward — measured max is 2.4e-6, the
+residual being glibc vs ATen(Sleef) transcendentals.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_files
+
+TOL = 1e-5
+
+
+def _run(O, path):
+    g = np.load(path)
+    st = str(g["cfg_scenario_type"])
+    B, N, T = int(g["cfg_B"]), int(g["cfg_N"]), int(g["cfg_T"])
+    pm = O.PaddedMap(st)
+    assert pm.P == int(g["cfg_max_ref_path_points"])
+    w = O.OracleWorld(st, B, N, config=O.config_from_golden(g), pmap=pm)
+    assert w.D == g["obs"].shape[-1]
+    for t in range(T):
+        gp = pm.global_path(g["pre_scenario_id"][t], g["pre_path_id"][t])
+        w.set_state(g["pre_pos"][t], g["pre_rot"][t], g["pre_speed"][t], g["pre_steering"][t], gp)
+        w.step_count[:] = g["pre_step"][t]
+        obs, rew, done, resp = w.step(g["action"][t])
+        for name, got, want in [
+            ("pos", w.pos, g["post_pos"][t]), ("rot", w.rot, g["post_rot"][t]),
+            ("speed", w.speed, g["post_speed"][t]), ("steering", w.steering, g["post_steering"][t]),
+            ("vel", w.vel, g["post_vel"][t]), ("sideslip", w.sideslip, g["post_sideslip"][t]),
+            ("vertices", w.vertices, g["vertices"][t]), ("d_ref", w.d_ref, g["d_ref"][t]),
+            ("d_left", w.d_left, g["d_left"][t]), ("d_right", w.d_right, g["d_right"][t]),
+            ("d_bound", w.d_bound, g["d_bound"][t]), ("d_agents", w.d_agents, g["d_agents"][t]),
+            ("obs", obs, g["obs"][t]), ("reward", rew, g["reward"][t]),
+        ]:
+            err = np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)))
+            assert err <= TOL, f"{os.path.basename(path)} step {t} {name}: max abs err {err}"
+        for name, got, want in [
+            ("idx_ref", w.idx_ref, g["idx_ref"][t]), ("short_term", w.short_term, g["short_term"][t]),
+            ("done", done, g["done"][t]), ("col_agents", w.col_agents.astype(bool), g["col_agents"][t]),
+            ("col_lane", w.col_lane.astype(bool), g["col_lane"][t]),
+            ("col_entry", w.col_entry.astype(bool), g["col_entry"][t]),
+            ("col_exit", w.col_exit.astype(bool), g["col_exit"][t]),
+            ("respawn", resp, g["respawn_mask"][t]),
+        ]:
+            assert np.array_equal(got, want), f"{os.path.basename(path)} step {t} {name}: not bit-exact"
+    return g
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_oracle_matches_reference_teacher_forced(oracle_mod, path):
+    g = _run(oracle_mod, path)
+    # the fixtures must actually exercise the interesting branches
+    assert g["done"].sum() > 0
+
+
+def test_goldens_cover_collisions_and_respawn():
+    tot = dict(col_agents=0, col_lane=0, respawn=0, col_exit=0)
+    for p in golden_files():
+        g = np.load(p)
+        tot["col_agents"] += int(g["col_agents"].sum())
+        tot["col_lane"] += int(g["col_lane"].sum())
+        tot["respawn"] += int(g["respawn_mask"].sum())
+        tot["col_exit"] += int(g["col_exit"].sum())
+    assert all(v > 0 for v in tot.values()), tot
+
+
+def test_oracle_reset_obs_matches_reference(oracle_mod):
+    """Obs right after an env reset (all quantities fresh): reference reset_at + observation pass."""
+    O = oracle_mod
+    n_checked = 0
+    for path in golden_files():
+        g = np.load(path)
+        st = str(g["cfg_scenario_type"])
+        B, N, T = int(g["cfg_B"]), int(g["cfg_N"]), int(g["cfg_T"])
+        pm = O.PaddedMap(st)
+        w = O.OracleWorld(st, B, N, config=O.config_from_golden(g), pmap=pm)
+        for t in range(T):
+            if not g["reset_mask"][t].any():
+                continue
+            gp = pm.global_path(g["reset_scenario_id"][t], g["reset_path_id"][t])
+            for b in np.where(g["reset_mask"][t])[0]:
+                for a in range(N):
+                    w.place(b, a, gp[b, a], g["reset_point_id"][t, b, a], g["reset_speed"][t, b, a])
+                w.refresh(b)
+                assert np.array_equal(w.pos[b], g["reset_pos"][t, b])
+                assert np.max(np.abs(w.rot[b] - g["reset_rot"][t, b])) == 0
+                assert np.max(np.abs(w.vel[b] - g["reset_vel"][t, b])) <= TOL
+            # zero action keeps the pose almost unchanged?  No: obs after reset is a pure function of the
+            # reset pose; compute it through a zero-dt-free path: the oracle's observe on fresh state.
+            obs = O.fresh_obs(w)
+            for b in np.where(g["reset_mask"][t])[0]:
+                err = np.max(np.abs(obs[b] - g["reset_obs"][t, b]))
+                assert err <= TOL, (os.path.basename(path), t, b, err)
+                n_checked += 1
+    assert n_checked > 50
