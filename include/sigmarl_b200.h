@@ -1,0 +1,191 @@
+/*
+ * sigmarl_b200.h — C-ABI of libsigmarl_b200.so: SigmaRL's vectorised road-traffic environment
+ * step as hand-written CUDA for sm_100a (NVIDIA B200).
+ *
+ * The reference has no FFI — its hot path is Python/PyTorch behind the VMAS `BaseScenario` plug-in
+ * API.  The entry points below are what a binding for that path has to expose; each one names the
+ * reference interface it replaces (paths relative to /root/reference/sigmarl/).  INTEGRATION.md
+ * shows the ctypes stub that plugs them into `ScenarioRoadTraffic`.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types; every call returns 0 (SGB_OK) or a
+ *     negative sgb_status; nothing throws.
+ *   - The CALLER owns every state / output buffer (device memory; from PyTorch pass
+ *     tensor.data_ptr()).  The library owns only the opaque context (map geometry + config on the
+ *     device, a [B]-byte scratch mask).
+ *   - All launches are asynchronous on the `stream` passed (a cudaStream_t cast to void*; NULL = the
+ *     legacy default stream).  A context is bound to one device; it is not thread-safe.
+ *   - Layouts are row-major, env-major / agent-minor: index (b, a) -> b*N + a.
+ *   - All arithmetic is fp32 with the reference's operation order (no FMA contraction on anything
+ *     that feeds an argmin or a collision predicate); masks are bytes.
+ */
+#ifndef SIGMARL_B200_H
+#define SIGMARL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB_VERSION 100
+#define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
+#define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
+
+typedef enum {
+    SGB_OK = 0,
+    SGB_ERR_ARG = -1,        /* NULL / out-of-range argument */
+    SGB_ERR_CUDA = -2,       /* a CUDA runtime call failed; see sgb_last_error() */
+    SGB_ERR_NO_DEVICE = -3,  /* no CUDA device / wrong architecture: there is NO CPU fallback */
+    SGB_ERR_MAP = -4,        /* map does not fit in shared memory / malformed polyline */
+    SGB_ERR_UNSUPPORTED = -5 /* config flag outside the hot path (e.g. MTV distance, testing mode) */
+} sgb_status;
+
+/* Flat map: the polylines of `map_manager.py:13-40` / `parse_xml.py:785-797` (one entry per reference
+ * path).  Replaces the per-(env, agent) copies of `world_state_rt.py:155-175, 313-392`: the library
+ * keeps ONE read-only copy and agents carry an int path index.  Host pointers; copied at create. */
+typedef struct {
+    int32_t n_paths;
+    const float*   center_xy;   /* [center_off[n_paths]][2]  centre lines ("center_line")            */
+    const int32_t* center_off;  /* [n_paths+1] offsets in points                                    */
+    const float*   left_xy;     /* "left_boundary_shared"                                           */
+    const int32_t* left_off;
+    const float*   right_xy;    /* "right_boundary_shared"                                          */
+    const int32_t* right_off;
+    const float*   center_yaw;  /* [center_off[n_paths] - n_paths] "center_line_yaw" (n-1 per path)  */
+    const uint8_t* is_loop;     /* [n_paths]                                                        */
+} sgb_map_desc;
+
+/* reward composition flags == the substring tests of road_traffic.py:1058-1112 */
+#define SGB_REW_EXACT_SPARSE 1u /* rew_method == "sparse"        */
+#define SGB_REW_TTC 2u          /* "ttc" in rew_method           */
+#define SGB_REW_DISTANCE 4u     /* "distance" in rew_method      */
+#define SGB_REW_SPARSE 8u       /* "sparse" in rew_method        */
+
+/* Everything `road_traffic.py:_init_params` (:112-768) bakes into the scenario, as fp32 the way the
+ * reference holds it (torch.tensor(..., dtype=float32)).  Replaces Thresholds / Penalties / Rewards /
+ * Normalizers (helper_scenario.py:13-100) and the AGENTS table (constants.py:628-647). */
+typedef struct {
+    float dt;                 /* world.dt                                 helper_training.py:821 */
+    float max_speed, max_steering, max_acc, max_steering_rate;         /* constants.py:638-644 */
+    float l_wb, lr_over_lwb;  /* wheelbase, l_r / l_wb                    dynamics.py:102-110    */
+    float half_length, half_width;                                     /* constants.py:630-631 */
+    float diag;               /* sqrt(x_semidim^2 + y_semidim^2)          helper_scenario.py:1140 */
+    float w_ref[SGB_N_SHORT_TERM]; /* weighting_ref_directions            road_traffic.py:536-543 */
+    float speed_dt;           /* float32(max_speed * dt)                  road_traffic.py:986    */
+    float reward_progress;
+    float near_boundary_low, near_boundary_high;
+    float near_agents_low, near_agents_high;
+    float ttc_low, ttc_high;
+    float penalty_near_boundary, penalty_near_agents;
+    float penalty_collide_agents, penalty_collide_lane;
+    float norm_pos, norm_v, norm_rot, norm_dist;                        /* road_traffic.py:587-608 */
+    float dsafe_sq;           /* float32(d_safe * d_safe)                 road_traffic.py:1291   */
+    float reset_min_dist_sq;  /* reset_agent_min_distance ** 2            world_state_rt_sim.py:305 */
+    uint32_t rew_flags;       /* SGB_REW_*                                                        */
+    int32_t k_near;           /* min(n_nearing_agents_observed, N-1)      road_traffic.py:441-443 */
+    int32_t max_steps;        /* timer.step == max_steps-1 -> done        road_traffic.py:1413   */
+    int32_t respawn_on_exit;  /* scenario_type != "cpm_entire"            road_traffic.py:1449   */
+    int32_t exhaustive;       /* debug: 1 = scan every segment (no pruning); results must not change */
+} sgb_config;
+
+/* Device buffers of one batch of B envs x N agents.  in = read, out = written, io = both. */
+typedef struct {
+    float*   pose;        /* io [B,N,4]  x, y, psi, v          Vehicle state helper_common.py:290-430 */
+    float*   aux;         /* io [B,N,4]  delta, vx, vy, beta   (steering, vel, sideslip_angle)      */
+    int32_t* path_id;     /* in [B,N]    index into the map's paths                                 */
+    float*   carry;       /* io [B,N,4]  d_ref, min dL, min dR, (int) idx_ref of the pre-step pose — */
+                          /*             the one-step-stale values the VMAS call order exposes      */
+                          /*             (SURVEY.md A.6); (re)built by sgb_refresh                  */
+    float*   action;      /* io [B,N,2]  target speed, target steering; clamped in place            */
+                          /*             helper_training.py:807-818                                 */
+    int32_t* step_count;  /* io [B]      timer.step                     road_traffic.py:449-460    */
+    float*   obs;         /* out [B,N,D] D = sgb_obs_dim()              road_traffic.py:1334       */
+    float*   reward;      /* out [B,N]                                  road_traffic.py:925        */
+    uint8_t* done;        /* out [B]                                    road_traffic.py:1368       */
+    uint8_t* agent_flags; /* out [B,N]   SGB_FLAG_* collision bits      world_state_rt_sim.py:36-55 */
+    uint32_t* collide_with; /* out [B,N] bit j = collisions.with_agents[b,a,j]; may be NULL        */
+    float*   dbg;         /* out [B,N,16] internals for parity tests; may be NULL:                  */
+                          /*   0 d_ref 1 (int)idx_ref 2..6 dL[0..4] 7..11 dR[0..4] 12 d_bound       */
+                          /*   13 nearest-agent index 14 second-nearest index 15 reserved           */
+} sgb_buffers;
+
+#define SGB_FLAG_COLLIDE_AGENT 1u /* any collisions.with_agents[b,a,:]  */
+#define SGB_FLAG_COLLIDE_LANE 2u  /* collisions.with_lanelets[b,a]      */
+#define SGB_FLAG_ENTRY 4u         /* collisions.with_entry_segments     */
+#define SGB_FLAG_EXIT 8u          /* collisions.with_exit_segments (= info["is_reach_goal"]) */
+
+typedef struct sgb_ctx sgb_ctx;
+
+/* Build a context on `device`: packs the map (centre lines + 6 extension points
+ * world_state_rt.py:279-311, boundaries, per-chunk bounding boxes) into one blob that every CTA
+ * bulk-copies (TMA) into shared memory.  Replaces ScenarioRoadTraffic.make_world's map/constant
+ * set-up (road_traffic.py:104-110, 112-768). */
+int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, const sgb_config* cfg);
+int sgb_destroy(sgb_ctx* ctx);
+
+/* Observation width D = 10 + 11*k_near (observation_provider_rt.py:594-925, default flags). */
+int sgb_obs_dim(const sgb_ctx* ctx);
+/* max_ref_path_points the reference would use for this map (road_traffic.py:505-530). */
+int sgb_max_ref_path_points(const sgb_ctx* ctx);
+
+/* ONE fused kernel per rollout step.  Replaces vmas Environment.step's scenario work:
+ * WorldCustom.step (helper_training.py:797-861) + KinematicBicycleModel.step (dynamics.py:120-192)
+ * + for every agent reward() (road_traffic.py:925-1253), observation() (:1334-1366) + done()
+ * (:1368-1487, without the respawn side effect — see sgb_reset).  Pure function of
+ * (pose, aux, path_id, carry, step_count, action). */
+int sgb_step(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, void* stream);
+
+/* Recompute everything derived from the current pose for the envs with env_mask[b] != 0
+ * (NULL = all): aux.vx/vy/beta from (psi, v, delta), carry, collision flags cleared; if write_obs,
+ * also the all-fresh observation the reference returns right after a reset.  Replaces
+ * reset_world_at's tail (road_traffic.py:897-923; world_state_rt.py:422-529). */
+int sgb_refresh(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* env_mask,
+                int32_t write_obs, void* stream);
+
+/* Put agents at given path points: pose = (center[path][point], center_yaw[path][point], speed),
+ * delta = 0 — for the (b,a) with agent_mask != 0 (NULL = all).  Replaces _reset_init_state
+ * (world_state_rt_sim.py:143-213) when the caller supplies the draws (parity mode).  Follow with
+ * sgb_refresh. */
+int sgb_place(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* agent_mask,
+              const int32_t* path, const int32_t* point, const float* speed, void* stream);
+
+/* Device-side masked reset + respawn after a step.  For envs with done[b]: re-place all N agents by
+ * bounded rejection sampling (uniform path in [path_lo, path_hi), uniform point in [3, n/2), every
+ * pair >= reset_min_dist apart) and zero step_count; for not-done envs (when cfg.respawn_on_exit)
+ * respawn the agents whose flags carry ENTRY/EXIT; then refresh the touched envs (fresh obs written
+ * for reset envs only if write_obs).  Counter-based RNG keyed by (seed, step counter `epoch`, global
+ * env index env_offset + b, agent, try) so results do not depend on how envs are sharded over GPUs.
+ * Replaces reset_world_at (road_traffic.py:816-923) and _generate_feasible_initial_positions
+ * (world_state_rt_sim.py:215-311); distribution-equivalent, not stream-equivalent, to the reference's
+ * global torch CPU generator.  n_failed (device int32, may be NULL) counts agents for which no
+ * feasible point was found in `max_tries` (the reference would spin forever). */
+int sgb_reset(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
+              uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t write_obs,
+              int32_t* n_failed, void* stream);
+
+/* Same as sgb_reset but for ALL envs regardless of `done` (Environment.reset()). */
+int sgb_reset_all(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
+                  uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t* n_failed,
+                  void* stream);
+
+/* Host-buffer convenience for callers whose policy lives on the host (the reference's default device
+ * is the CPU, config.json:5): copies `h_action` [B,N,2] to buf->action, runs sgb_step, copies
+ * obs / reward / done back into the host pointers (pinned memory recommended) and synchronises the
+ * stream before returning. */
+int sgb_step_host(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
+                  float* h_obs, float* h_reward, uint8_t* h_done, void* stream);
+
+/* Number of kernels this context has launched since creation (for launch accounting in benchmarks). */
+int64_t sgb_launch_count(const sgb_ctx* ctx);
+/* Bytes of the packed map blob each CTA stages into shared memory. */
+int64_t sgb_map_bytes(const sgb_ctx* ctx);
+
+const char* sgb_status_string(int status);
+const char* sgb_last_error(void); /* text of the last CUDA error seen by this thread */
+int sgb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGMARL_B200_H */

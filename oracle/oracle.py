@@ -136,7 +136,9 @@ def default_config(scenario_type, pmap, n_agents, mode="params", rew_method="dis
     ``helper_common.py:129-137``, dt from ``config.json:4``).  mode "kwargs": built from
     ``make_world(**kwargs)`` (``road_traffic.py:176-212, 317``).
     """
-    lane_width = pmap.lane_width
+    # road_traffic.py:116-123: with a Parameters object and no kwargs, `scenario_type` defaults to
+    # "cpm_entire" inside _init_params, so normalisers use the CPM lane width (0.15) on every map.
+    lane_width = 0.15 if mode == "params" else pmap.lane_width
     if mode == "params":
         c = dict(reward_progress=0.1, nb_high=0.02, nb_low=0.0, na_high=0.3, na_low=0.0, ttc_low=0.0, ttc_high=3.75,
                  pen_near_boundary=-0.2, pen_near_agents=-0.2, dt=0.1)

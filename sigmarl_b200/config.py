@@ -1,0 +1,169 @@
+"""EnvConfig: every constant ``ScenarioRoadTraffic._init_params`` (``road_traffic.py:112-768``) bakes into the
+scenario, for its two construction modes, lowered to the POD ``sgb_config`` the kernels read.
+
+mode "params": a ``Parameters`` object was attached before ``make_world`` (``mappo_cavs.py:168-169``); the
+thresholds come from ``helper_common.py:129-137`` and ``dt`` from ``config.json:4``.
+mode "kwargs": the scenario is built from ``make_world(**kwargs)`` with the defaults of
+``road_traffic.py:176-212, 317``.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import lib as _lib
+
+# constants.py:628-647 (AGENTS)
+AGENT_WIDTH, AGENT_LENGTH = 0.107, 0.22
+L_F, L_R, L_WB = 0.075, 0.075, 0.15
+MAX_SPEED, MAX_STEERING = 1.0, 31 * math.pi / 180
+MAX_ACC, MAX_STEERING_RATE = 5.0, math.pi / 2
+R_P_NORMALIZER = 100  # road_traffic.py:126-128
+CPM_LANE_WIDTH = 0.15  # constants.py:21
+
+_REW_METHODS = ("distance", "ttc", "sparse", "distance_sparse", "ttc_sparse")
+
+
+def _f32(x):
+    return np.float32(x)
+
+
+@dataclass
+class EnvConfig:
+    scenario_type: str = "cpm_entire"
+    n_agents: Optional[int] = None          # None -> SCENARIOS[scenario_type]["n_agents"]
+    mode: str = "params"                    # "params" | "kwargs" (see module docstring)
+    dt: Optional[float] = None              # None -> 0.1 (params) / 0.05 (kwargs)
+    max_steps: int = 128                    # helper_common.py:49
+    rew_method: str = "distance"            # helper_common.py:128
+    n_nearing_agents_observed: int = 2      # config.json:29
+    reward_progress: Optional[float] = None
+    threshold_near_boundary_high: Optional[float] = None
+    threshold_near_boundary_low: Optional[float] = None
+    threshold_near_other_agents_c2c_high: Optional[float] = None
+    threshold_near_other_agents_c2c_low: Optional[float] = None
+    ttc_low: Optional[float] = None
+    ttc_high: Optional[float] = None
+    penalty_near_boundary: Optional[float] = None
+    penalty_near_other_agents: Optional[float] = None
+    penalty_collide_with_agents: float = -100 / R_P_NORMALIZER
+    penalty_collide_with_boundaries: float = -100 / R_P_NORMALIZER
+    cpm_scenario_probabilities: tuple = (1.0, 0.0, 0.0)
+    exhaustive: bool = False                # debug: disable the pruned search (results must not change)
+    # flags of the reference that select code OUTSIDE the supported hot path; must keep these values
+    is_testing_mode: bool = False
+    is_use_mtv_distance: bool = False
+    is_ego_view: bool = True
+    is_partial_observation: bool = True
+    is_observe_vertices: bool = True
+    is_observe_distance_to_agents: bool = True
+    is_observe_distance_to_boundaries: bool = True
+    is_observe_distance_to_center_line: bool = True
+    is_apply_mask: bool = False
+    is_obs_noise: bool = False
+    is_obs_steering: bool = False
+    is_observe_ref_path_other_agents: bool = False
+    extras: dict = field(default_factory=dict)
+
+    def validate(self):
+        if self.rew_method not in _REW_METHODS:
+            raise NotImplementedError(f"rew_method {self.rew_method!r}: supported {_REW_METHODS} (cbf variants are out of scope)")
+        want = dict(is_testing_mode=False, is_use_mtv_distance=False, is_ego_view=True, is_partial_observation=True,
+                    is_observe_vertices=True, is_observe_distance_to_agents=True,
+                    is_observe_distance_to_boundaries=True, is_observe_distance_to_center_line=True,
+                    is_apply_mask=False, is_obs_noise=False, is_obs_steering=False,
+                    is_observe_ref_path_other_agents=False)
+        for k, v in want.items():
+            if getattr(self, k) != v:
+                raise NotImplementedError(f"{k}={getattr(self, k)} selects a non-default observation/reset variant "
+                                          f"that is outside the accelerated hot path (SURVEY.md §8f-4)")
+        if self.mode not in ("params", "kwargs"):
+            raise ValueError("mode must be 'params' or 'kwargs'")
+
+    @classmethod
+    def from_parameters(cls, p, **over):
+        """From a SigmaRL ``Parameters``-like object (``helper_common.py:26-252``); unknown attributes are ignored."""
+        kw = dict(mode="params")
+        for name in cls.__dataclass_fields__:
+            if name in ("mode", "extras", "exhaustive"):
+                continue
+            if hasattr(p, name) and getattr(p, name) is not None:
+                v = getattr(p, name)
+                kw[name] = tuple(v) if name == "cpm_scenario_probabilities" else v
+        kw.update(over)
+        return cls(**kw)
+
+    def resolved(self, lane_width: float, default_n_agents: int):
+        """Fill the mode-dependent defaults (returns a plain dict of python floats)."""
+        m = self.mode
+        pick = lambda v, d: d if v is None else v  # noqa: E731
+        if m == "params":
+            d = dict(dt=0.1, reward_progress=0.1, nb_high=0.02, nb_low=0.0, na_high=0.3, na_low=0.0,
+                     ttc_low=0.0, ttc_high=3.75, pen_nb=-0.2, pen_na=-0.2)
+        else:
+            d = dict(dt=0.05, reward_progress=10 / R_P_NORMALIZER,
+                     nb_high=(lane_width - AGENT_WIDTH) / 2 * 0.9, nb_low=0.0,
+                     na_high=AGENT_LENGTH + AGENT_WIDTH, na_low=(AGENT_LENGTH + AGENT_WIDTH) / 2,
+                     ttc_low=0.0, ttc_high=3.75, pen_nb=-20 / R_P_NORMALIZER, pen_na=-20 / R_P_NORMALIZER)
+        n = self.n_agents or default_n_agents
+        return dict(
+            n_agents=n,
+            dt=pick(self.dt, d["dt"]),
+            reward_progress=pick(self.reward_progress, d["reward_progress"]),
+            nb_high=pick(self.threshold_near_boundary_high, d["nb_high"]),
+            nb_low=pick(self.threshold_near_boundary_low, d["nb_low"]),
+            na_high=pick(self.threshold_near_other_agents_c2c_high, d["na_high"]),
+            na_low=pick(self.threshold_near_other_agents_c2c_low, d["na_low"]),
+            ttc_low=pick(self.ttc_low, d["ttc_low"]), ttc_high=pick(self.ttc_high, d["ttc_high"]),
+            pen_nb=pick(self.penalty_near_boundary, d["pen_nb"]),
+            pen_na=pick(self.penalty_near_other_agents, d["pen_na"]),
+            k_near=min(self.n_nearing_agents_observed, n - 1),      # road_traffic.py:441-443
+        )
+
+    def lane_width(self, maplib) -> float:
+        """Lane width the reference derives normalisers / kwargs-thresholds from.  Quirk reproduced on purpose:
+        ``_init_params`` reads ``kwargs.pop("scenario_type", "cpm_entire")`` (road_traffic.py:116-123), so when the
+        scenario is configured through a ``Parameters`` object (no kwargs) it uses the CPM lane width (0.15 m)
+        whatever map is loaded."""
+        return CPM_LANE_WIDTH if self.mode == "params" else maplib.lane_width
+
+    def lower(self, maplib) -> "_lib.Config":
+        """-> ctypes ``sgb_config``; every float is rounded to fp32 exactly where the reference does."""
+        self.validate()
+        r = self.resolved(self.lane_width(maplib), maplib.default_n_agents)
+        c = _lib.Config()
+        # torch.linspace(1, 0.2, 3, float32) / sum   (road_traffic.py:536-543)
+        w = np.asarray([_f32(1.0), _f32(1.0) + _f32(1.0) * ((_f32(0.2) - _f32(1.0)) / _f32(2.0)), _f32(0.2)], np.float32)
+        w = w / (w[0] + w[1] + w[2])
+        x, y = _f32(maplib.world_x_dim), _f32(maplib.world_y_dim)
+        na_low32 = float(_f32(r["na_low"]))
+        vals = dict(
+            dt=r["dt"], max_speed=MAX_SPEED, max_steering=MAX_STEERING, max_acc=MAX_ACC,
+            max_steering_rate=MAX_STEERING_RATE, l_wb=L_WB, lr_over_lwb=L_R / L_WB,
+            half_length=AGENT_LENGTH / 2, half_width=AGENT_WIDTH / 2,
+            diag=np.sqrt(x * x + y * y, dtype=np.float32),                 # helper_scenario.py:1140-1143
+            w_ref0=w[0], w_ref1=w[1], w_ref2=w[2],
+            speed_dt=MAX_SPEED * r["dt"],                                   # road_traffic.py:986
+            reward_progress=r["reward_progress"],
+            near_boundary_low=r["nb_low"], near_boundary_high=r["nb_high"],
+            near_agents_low=r["na_low"], near_agents_high=r["na_high"],
+            ttc_low=r["ttc_low"], ttc_high=r["ttc_high"],
+            penalty_near_boundary=r["pen_nb"], penalty_near_agents=r["pen_na"],
+            penalty_collide_agents=self.penalty_collide_with_agents,
+            penalty_collide_lane=self.penalty_collide_with_boundaries,
+            norm_pos=AGENT_LENGTH * 10, norm_v=MAX_SPEED, norm_rot=2 * math.pi,
+            norm_dist=self.lane_width(maplib) * 3,                               # road_traffic.py:587-608
+            dsafe_sq=na_low32 * na_low32,                                   # road_traffic.py:1279,1291
+            reset_min_dist_sq=(np.sqrt(_f32(AGENT_LENGTH ** 2 + AGENT_WIDTH ** 2)) * _f32(1.5)) ** 2,
+        )
+        for k, v in vals.items():
+            setattr(c, k, float(_f32(v)))
+        rm = self.rew_method
+        c.rew_flags = ((_lib.SGB_REW_EXACT_SPARSE if rm == "sparse" else 0) | (_lib.SGB_REW_TTC if "ttc" in rm else 0) |
+                       (_lib.SGB_REW_DISTANCE if "distance" in rm else 0) | (_lib.SGB_REW_SPARSE if "sparse" in rm else 0))
+        c.k_near = int(r["k_near"])
+        c.max_steps = int(self.max_steps)
+        c.respawn_on_exit = int(self.scenario_type != "cpm_entire")       # road_traffic.py:1449
+        c.exhaustive = int(self.exhaustive)
+        return c

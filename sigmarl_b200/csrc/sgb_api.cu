@@ -1,0 +1,357 @@
+// sgb_api.cu — the C-ABI of libsigmarl_b200.so (include/sigmarl_b200.h): context, map packing, launches.
+// There is deliberately NO CPU implementation here: without a CUDA device sgb_create fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "sgb_kernels.cuh"
+
+using namespace sgb;
+
+struct sgb_ctx {
+    int device = 0;
+    sgb_config cfg{};
+    unsigned char* d_blob = nullptr;
+    float* d_yaw = nullptr;          // yaw per centre point, indexed like the blob's centre points
+    uint8_t* d_touched = nullptr;    // [cap] scratch mask for reset -> refresh
+    int32_t touched_cap = 0;
+    int32_t blob_bytes = 0;
+    int32_t n_paths = 0;
+    int32_t max_center = 0;
+    int32_t num_sms = 0;
+    int32_t max_smem_optin = 0;
+    int64_t launches = 0;
+    void* h_pin = nullptr;           // lazily allocated pinned staging for sgb_step_host? (unused: caller pins)
+};
+
+static thread_local char g_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+    return SGB_ERR_CUDA;
+}
+#define CK(call)                                             \
+    do {                                                     \
+        cudaError_t _e = (call);                             \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call);  \
+    } while (0)
+
+extern "C" const char* sgb_last_error(void) { return g_err; }
+extern "C" int sgb_version(void) { return SGB_VERSION; }
+extern "C" const char* sgb_status_string(int s) {
+    switch (s) {
+        case SGB_OK: return "ok";
+        case SGB_ERR_ARG: return "invalid argument";
+        case SGB_ERR_CUDA: return "CUDA runtime error";
+        case SGB_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case SGB_ERR_MAP: return "map rejected (degenerate polyline or does not fit in shared memory)";
+        case SGB_ERR_UNSUPPORTED: return "configuration outside the supported hot path";
+        default: return "unknown status";
+    }
+}
+
+// ---- map packing (host) -------------------------------------------------------------------------------
+namespace {
+
+struct Packed {
+    std::vector<unsigned char> blob;
+    std::vector<float> yaw;
+    int max_center = 0;
+};
+
+void add_boxes(std::vector<float>& boxes, const float* xy, int n_pts) {
+    const int nseg = n_pts - 1;
+    for (int s0 = 0; s0 < nseg; s0 += kChunk) {
+        const int s1 = std::min(s0 + kChunk, nseg);
+        float x0 = xy[2 * s0], x1 = x0, y0 = xy[2 * s0 + 1], y1 = y0;
+        for (int k = s0; k <= s1; k++) {
+            x0 = std::min(x0, xy[2 * k]); x1 = std::max(x1, xy[2 * k]);
+            y0 = std::min(y0, xy[2 * k + 1]); y1 = std::max(y1, xy[2 * k + 1]);
+        }
+        boxes.insert(boxes.end(), {x0, y0, x1, y1});
+    }
+}
+
+bool degenerate(const float* xy, int n) {
+    if (n < 2) return true;
+    for (int s = 0; s + 1 < n; s++)
+        if (xy[2 * s] == xy[2 * s + 2] && xy[2 * s + 1] == xy[2 * s + 3]) return true; // zero-length segment -> NaN in the reference
+    return false;
+}
+
+int pack_map(const sgb_map_desc* m, Packed& out) {
+    if (!m || m->n_paths <= 0 || !m->center_xy || !m->center_off || !m->left_xy || !m->left_off || !m->right_xy ||
+        !m->right_off || !m->center_yaw || !m->is_loop)
+        return SGB_ERR_ARG;
+    const int n = m->n_paths;
+    std::vector<PathRec> recs(n);
+    std::vector<float> pts, boxes;
+    out.yaw.clear();
+    int yaw_in = 0;
+    for (int i = 0; i < n; i++) {
+        PathRec& r = recs[i];
+        std::memset(&r, 0, sizeof r);
+        const int nc = m->center_off[i + 1] - m->center_off[i];
+        const int nl = m->left_off[i + 1] - m->left_off[i];
+        const int nr = m->right_off[i + 1] - m->right_off[i];
+        const float* c = m->center_xy + 2 * (size_t)m->center_off[i];
+        const float* l = m->left_xy + 2 * (size_t)m->left_off[i];
+        const float* rr = m->right_xy + 2 * (size_t)m->right_off[i];
+        if (nc < 8 || degenerate(c, nc) || degenerate(l, nl) || degenerate(rr, nr)) return SGB_ERR_MAP;
+        out.max_center = std::max(out.max_center, nc);
+        r.is_loop = m->is_loop[i] ? 1 : 0;
+        r.c_off = (int)(pts.size() / 2);
+        r.n_c = nc;
+        r.cbox = (int)(boxes.size() / 4);
+        add_boxes(boxes, c, nc);
+        pts.insert(pts.end(), c, c + 2 * nc);
+        // world_state_rt.py:279-311: extension points last + m * (last - prev), m = 1..6 (fp32, no contraction)
+        {
+            volatile float dx = c[2 * (nc - 1)] - c[2 * (nc - 2)];
+            volatile float dy = c[2 * (nc - 1) + 1] - c[2 * (nc - 2) + 1];
+            for (int k = 1; k <= kExt; k++) {
+                volatile float mx = (float)k * dx, my = (float)k * dy;
+                volatile float ex = c[2 * (nc - 1)] + mx, ey = c[2 * (nc - 1) + 1] + my;
+                pts.push_back((float)ex);
+                pts.push_back((float)ey);
+            }
+        }
+        // yaw aligned with the centre points (n-1 values + padding for the extension slots)
+        for (int k = 0; k < nc - 1; k++) out.yaw.push_back(m->center_yaw[yaw_in + k]);
+        yaw_in += nc - 1;
+        for (int k = 0; k < kExt + 1; k++) out.yaw.push_back(0.0f);
+        r.l_off = (int)(pts.size() / 2);
+        r.n_l = nl;
+        r.lbox = (int)(boxes.size() / 4);
+        add_boxes(boxes, l, nl);
+        pts.insert(pts.end(), l, l + 2 * nl);
+        r.r_off = (int)(pts.size() / 2);
+        r.n_r = nr;
+        r.rbox = (int)(boxes.size() / 4);
+        add_boxes(boxes, rr, nr);
+        pts.insert(pts.end(), rr, rr + 2 * nr);
+    }
+    // yaw must be indexable by (c_off + point): rebuild it on the blob's point numbering
+    std::vector<float> yaw_by_pt(pts.size() / 2, 0.0f);
+    {
+        size_t src = 0;
+        for (int i = 0; i < n; i++) {
+            for (int k = 0; k < recs[i].n_c + kExt; k++) yaw_by_pt[recs[i].c_off + k] = out.yaw[src + k];
+            src += recs[i].n_c + kExt;
+        }
+    }
+    out.yaw.swap(yaw_by_pt);
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    BlobHeader h{};
+    h.n_paths = n;
+    h.path_off = (int32_t)align16(sizeof(BlobHeader));
+    h.pts_off = (int32_t)align16(h.path_off + sizeof(PathRec) * n);
+    h.box_off = (int32_t)align16(h.pts_off + sizeof(float) * pts.size());
+    h.total_bytes = (int32_t)align16(h.box_off + sizeof(float) * boxes.size());
+    out.blob.assign(h.total_bytes, 0);
+    std::memcpy(out.blob.data(), &h, sizeof h);
+    std::memcpy(out.blob.data() + h.path_off, recs.data(), sizeof(PathRec) * n);
+    std::memcpy(out.blob.data() + h.pts_off, pts.data(), sizeof(float) * pts.size());
+    std::memcpy(out.blob.data() + h.box_off, boxes.data(), sizeof(float) * boxes.size());
+    return SGB_OK;
+}
+
+int check_buffers(const sgb_buffers* b, int step) {
+    if (!b || !b->pose || !b->aux || !b->path_id || !b->carry || !b->agent_flags) return SGB_ERR_ARG;
+    if (step && (!b->action || !b->step_count || !b->obs || !b->reward || !b->done)) return SGB_ERR_ARG;
+    return SGB_OK;
+}
+
+// lanes per agent: enough agents per tile to keep whole envs together, as many lanes as still fit
+int pick_group(int N) {
+    if (N <= 8) return 4;   // 64 agent slots per tile
+    if (N <= 16) return 4;
+    return 2;               // up to 32 agents per env
+}
+
+template <int G>
+int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
+    const int slots = kThreads / G;
+    p.envs_per_tile = slots / p.N;
+    if (p.envs_per_tile < 1) return SGB_ERR_ARG;
+    p.n_tiles = (p.B + p.envs_per_tile - 1) / p.envs_per_tile;
+    const size_t smem = ((size_t)ctx->blob_bytes + 127) / 128 * 128 + tile_smem_bytes(slots, p.N, p.D) + 128;
+    if ((int64_t)smem > ctx->max_smem_optin) {
+        snprintf(g_err, sizeof g_err, "map blob %d B + tile arrays need %zu B of shared memory, device offers %d B",
+                 ctx->blob_bytes, smem, ctx->max_smem_optin);
+        return SGB_ERR_MAP;
+    }
+    static thread_local size_t configured = 0;
+    if (configured < smem) {
+        CK(cudaFuncSetAttribute(env_step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int grid = std::min(p.n_tiles, ctx->num_sms);
+    env_step_kernel<G><<<grid, kThreads, smem, st>>>(p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return SGB_OK;
+}
+
+int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, const uint8_t* env_mask, int write_obs,
+               cudaStream_t st) {
+    Params p{};
+    p.cfg = ctx->cfg;
+    p.buf = *buf;
+    p.blob = ctx->d_blob;
+    p.env_mask = env_mask;
+    p.B = B; p.N = N; p.D = 10 + 11 * ctx->cfg.k_near;
+    p.blob_bytes = ctx->blob_bytes;
+    p.mode = mode;
+    p.write_obs = write_obs;
+    switch (pick_group(N)) {
+        case 4: return launch_env_kernel<4>(ctx, p, st);
+        default: return launch_env_kernel<2>(ctx, p, st);
+    }
+}
+
+} // namespace
+
+// ---- C-ABI ---------------------------------------------------------------------------------------------
+extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, const sgb_config* cfg) {
+    if (!out || !map || !cfg) return SGB_ERR_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0 || device < 0 || device >= n_dev) {
+        snprintf(g_err, sizeof g_err, "no CUDA device %d (found %d)", device, n_dev);
+        return SGB_ERR_NO_DEVICE;
+    }
+    if (cfg->k_near < 0 || cfg->k_near >= SGB_MAX_AGENTS || cfg->max_steps < 2 || !(cfg->dt > 0.0f)) return SGB_ERR_ARG;
+    Packed pk;
+    int rc = pack_map(map, pk);
+    if (rc != SGB_OK) return rc;
+    CK(cudaSetDevice(device));
+    sgb_ctx* c = new (std::nothrow) sgb_ctx();
+    if (!c) return SGB_ERR_ARG;
+    c->device = device;
+    c->cfg = *cfg;
+    c->n_paths = map->n_paths;
+    c->max_center = pk.max_center;
+    c->blob_bytes = (int32_t)pk.blob.size();
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int32_t)prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) {
+        snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        delete c;
+        return SGB_ERR_NO_DEVICE;
+    }
+    CK(cudaMalloc(&c->d_blob, pk.blob.size()));
+    CK(cudaMemcpy(c->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_yaw, pk.yaw.size() * sizeof(float)));
+    CK(cudaMemcpy(c->d_yaw, pk.yaw.data(), pk.yaw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = c;
+    return SGB_OK;
+}
+
+extern "C" int sgb_destroy(sgb_ctx* c) {
+    if (!c) return SGB_ERR_ARG;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_blob);
+    cudaFree(c->d_yaw);
+    cudaFree(c->d_touched);
+    delete c;
+    return SGB_OK;
+}
+
+extern "C" int sgb_obs_dim(const sgb_ctx* c) { return c ? 10 + 11 * c->cfg.k_near : SGB_ERR_ARG; }
+extern "C" int sgb_max_ref_path_points(const sgb_ctx* c) { return c ? c->max_center + kExt + 2 : SGB_ERR_ARG; }
+extern "C" int64_t sgb_launch_count(const sgb_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t sgb_map_bytes(const sgb_ctx* c) { return c ? c->blob_bytes : 0; }
+
+extern "C" int sgb_step(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, void* stream) {
+    if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || c->cfg.k_near > N - 1) return SGB_ERR_ARG;
+    int rc = check_buffers(buf, 1);
+    if (rc) return rc;
+    return launch_env(c, B, N, buf, 0, nullptr, 1, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_refresh(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* env_mask,
+                           int32_t write_obs, void* stream) {
+    if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || c->cfg.k_near > N - 1) return SGB_ERR_ARG;
+    int rc = check_buffers(buf, 0);
+    if (rc) return rc;
+    if (write_obs && !buf->obs) return SGB_ERR_ARG;
+    return launch_env(c, B, N, buf, 1, env_mask, write_obs, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* agent_mask,
+                         const int32_t* path, const int32_t* point, const float* speed, void* stream) {
+    if (!c || B <= 0 || N <= 0 || !path || !point || !speed) return SGB_ERR_ARG;
+    int rc = check_buffers(buf, 0);
+    if (rc) return rc;
+    PlaceParams p{};
+    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw;
+    p.agent_mask = agent_mask; p.path = path; p.point = point; p.speed = speed; p.B = B; p.N = N;
+    const int n = B * N;
+    place_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return SGB_OK;
+}
+
+static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
+                      uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t write_obs,
+                      int32_t* n_failed, int all, cudaStream_t st) {
+    if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || path_lo < 0 || path_hi > c->n_paths || path_lo >= path_hi ||
+        max_tries <= 0)
+        return SGB_ERR_ARG;
+    int rc = check_buffers(buf, 0);
+    if (rc) return rc;
+    if (!buf->step_count || (!all && !buf->done)) return SGB_ERR_ARG;
+    if (c->touched_cap < B) {
+        cudaFree(c->d_touched);
+        c->d_touched = nullptr;
+        CK(cudaMalloc(&c->d_touched, (size_t)B));
+        c->touched_cap = B;
+    }
+    ResetParams p{};
+    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.touched = c->d_touched;
+    p.n_failed = n_failed; p.seed = seed; p.epoch = epoch; p.env_offset = env_offset;
+    p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
+    reset_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return launch_env(c, B, N, buf, 1, c->d_touched, write_obs, st);
+}
+
+extern "C" int sgb_reset(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
+                         uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t write_obs,
+                         int32_t* n_failed, void* stream) {
+    return reset_impl(c, B, N, buf, path_lo, path_hi, seed, epoch, env_offset, max_tries, write_obs, n_failed, 0,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int sgb_reset_all(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
+                             uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t* n_failed,
+                             void* stream) {
+    return reset_impl(c, B, N, buf, path_lo, path_hi, seed, epoch, env_offset, max_tries, buf && buf->obs ? 1 : 0,
+                      n_failed, 1, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
+                             float* h_obs, float* h_reward, uint8_t* h_done, void* stream) {
+    if (!c || !h_action || !h_obs || !h_reward || !h_done) return SGB_ERR_ARG;
+    int rc = check_buffers(buf, 1);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t bn = (size_t)B * N;
+    const int D = 10 + 11 * c->cfg.k_near;
+    CK(cudaMemcpyAsync(buf->action, h_action, bn * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = sgb_step(c, B, N, buf, stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_obs, buf->obs, bn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_reward, buf->reward, bn * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_done, buf->done, (size_t)B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SGB_OK;
+}

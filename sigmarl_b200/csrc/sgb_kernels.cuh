@@ -1,0 +1,876 @@
+// sgb_kernels.cuh — device code of libsigmarl_b200: the fused road-traffic environment step for sm_100a.
+//
+// One persistent CTA per SM.  Each CTA bulk-copies (TMA, cp.async.bulk + mbarrier) the packed map
+// blob into shared memory once, then loops over tiles of whole envs:
+//   phase A  one thread per agent : kinematic-bicycle Euler tick, rectangle vertices  -> smem
+//   phase B  G lanes per agent    : point->polyline distances (centre line, left/right boundary) and
+//                                   rectangle-vs-boundary crossing tests out of the smem map, pruned
+//                                   with per-chunk bounding boxes; warp-shuffle reductions
+//   phase C  G lanes per agent    : centre distances / rectangle crossings / TTC against the other
+//                                   agents of the env, k-nearest selection, reward, observation -> smem
+//   phase D  whole CTA            : coalesced float4 write-back of the observation tile
+//
+// Arithmetic contract (see DESIGN.md "Exactness"): this translation unit is compiled with
+// -fmad=false, IEEE sqrt/div, no fast-math; every value that feeds an argmin or a strict-sign
+// collision predicate is evaluated with the reference's operation order
+// (helper_scenario.py:829-889, :1148-1229), so those decisions are bit-identical to the reference
+// given the same inputs.  Pruning never changes a result: distance chunks are skipped only when a
+// lower bound exceeds the running best by a margin 30x larger than the fp32 evaluation error, and
+// crossing tests are skipped only when every edge-line sign is certified with a margin.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sigmarl_b200.h"
+
+namespace sgb {
+
+constexpr int kThreads = 256;        // threads per CTA
+constexpr int kChunk = 8;            // polyline segments per bounding-box chunk
+constexpr int kExt = 6;              // extension points behind a centre line (3 short-term pts x interval 2)
+constexpr float kDistMargin = 1e-4f; // [m]  >> fp32 error of a point-segment distance (~3e-6)
+constexpr float kSignMargin = 1e-4f; // [m^2] >> fp32 error of an edge-line sign function (~6e-6)
+
+// ---- packed map blob (global memory -> shared memory, byte-identical) ---------------------------------
+struct BlobHeader {      // 32 bytes
+    int32_t n_paths;
+    int32_t path_off;    // byte offsets from blob start
+    int32_t pts_off;
+    int32_t box_off;
+    int32_t total_bytes; // multiple of 16
+    int32_t pad[3];
+};
+struct PathRec {         // 48 bytes; point offsets in float2 units, box offsets in float4 units
+    int32_t c_off, n_c;  // centre line: n_c real points followed by kExt extension points
+    int32_t l_off, n_l;
+    int32_t r_off, n_r;
+    int32_t cbox, lbox, rbox;
+    int32_t is_loop;
+    int32_t pad[2];
+};
+
+struct Params {
+    sgb_config cfg;
+    sgb_buffers buf;
+    const unsigned char* blob; // device copy of the packed map
+    const uint8_t* env_mask;   // refresh: which envs (NULL = all)
+    int32_t B, N, D;
+    int32_t envs_per_tile, n_tiles;
+    int32_t blob_bytes;
+    int32_t mode;              // 0 = step, 1 = refresh
+    int32_t write_obs;
+};
+
+// ---- small helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(phase)
+        : "memory");
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// torch `%` (sign of the divisor) for a positive divisor
+__device__ __forceinline__ float pymod(float a, float m) {
+    float r = fmodf(a, m);
+    if (r != 0.0f && r < 0.0f) r += m;
+    return r;
+}
+
+// helper_scenario.py:960-996 decreasing_fcn(type="linear")
+__device__ __forceinline__ float dec_lin(float x, float x0, float x1) {
+    x = clampf(x, x0, x1);
+    return 1.0f - (x - x0) / (x1 - x0);
+}
+
+// running minimum of sqrt(q) with the reference's "first minimal index" rule; sqrt only on improvement
+struct Best {
+    float q, d;
+    int idx;
+    __device__ __forceinline__ void init() { q = __int_as_float(0x7f800000); d = q; idx = 0x7fffffff; }
+    __device__ __forceinline__ void upd(float qq, int s) {
+        if (qq < q) {
+            float dd = sqrtf(qq);
+            if (dd < d) { d = dd; idx = s; }
+            q = qq;
+        }
+    }
+};
+struct BestD { // distance only
+    float q, d;
+    __device__ __forceinline__ void init() { q = __int_as_float(0x7f800000); d = q; }
+    __device__ __forceinline__ void upd(float qq) {
+        if (qq < q) { d = fminf(d, sqrtf(qq)); q = qq; }
+    }
+};
+
+// squared point-segment distance, operation order of helper_scenario.py:856-871
+__device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, float len2, float px, float py) {
+    float vx = px - ax, vy = py - ay;
+    float t = (vx * lx + vy * ly) / len2;
+    t = clampf(t, 0.0f, 1.0f);
+    float cx = ax + lx * t, cy = ay + ly * t;
+    float ex = cx - px, ey = cy - py;
+    return ex * ex + ey * ey;
+}
+
+// distance from a point to an axis-aligned box (lower bound for every polyline point inside it)
+__device__ __forceinline__ float box_lb(float4 bx, float px, float py) {
+    float dx = fmaxf(fmaxf(bx.x - px, px - bx.z), 0.0f);
+    float dy = fmaxf(fmaxf(bx.y - py, py - bx.w), 0.0f);
+    return sqrtf(dx * dx + dy * dy);
+}
+
+// The agent's rectangle as interX sees it (helper_scenario.py:1148-1229): closed 5-vertex polyline.
+struct Rect {
+    float vx[4], vy[4];    // vertices 0..3 (vertex 4 == vertex 0)
+    float dx[4], dy[4], S[4]; // per edge i: v[i] -> v[i+1]
+    __device__ __forceinline__ void finish() {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int j = (i + 1) & 3;
+            dx[i] = vx[j] - vx[i];
+            dy[i] = vy[j] - vy[i];
+            S[i] = dx[i] * vy[i] - dy[i] * vx[i];
+        }
+    }
+};
+
+// interX of the rectangle (as L1) against ONE segment a->b of L2; exact predicate
+__device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by) {
+    float dx2 = bx - ax, dy2 = by - ay;
+    float S2 = dx2 * ay - dy2 * ax;
+    float g[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) g[i] = (r.vy[i] * dx2 - r.vx[i] * dy2) - S2;
+    bool hit = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float fa = (r.dx[i] * ay - r.dy[i] * ax) - r.S[i];
+        float fb = (r.dx[i] * by - r.dy[i] * bx) - r.S[i];
+        bool c1 = (fa * fb) < 0.0f;
+        bool c2 = (g[i] * g[(i + 1) & 3]) < 0.0f;
+        hit |= (c1 & c2);
+    }
+    return hit;
+}
+
+// interX(L1 = rectangle lo, L2 = rectangle hi): 4 x 4 edge pairs
+__device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx, const float* hy) {
+    bool hit = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int jn = (j + 1) & 3;
+        hit |= rect_cross_seg_L1(lo, hx[j], hy[j], hx[jn], hy[jn]);
+    }
+    return hit;
+}
+
+// Certified "no edge line of the rectangle separates points of this box": for every edge i the sign of
+// f_i(x,y) = dx_i*y - dy_i*x - S_i is the same for all (x,y) in the box, with a margin far above the fp32
+// evaluation error, hence C1 of interX is false for every segment inside the box -> no crossing.
+__device__ __forceinline__ bool box_sign_definite(const Rect& r, float4 bx) {
+    float cx = 0.5f * (bx.x + bx.z), cy = 0.5f * (bx.y + bx.w);
+    float hx = 0.5f * (bx.z - bx.x), hy = 0.5f * (bx.w - bx.y);
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float f = (r.dx[i] * cy - r.dy[i] * cx) - r.S[i];
+        float rad = fabsf(r.dx[i]) * hy + fabsf(r.dy[i]) * hx + kSignMargin;
+        ok &= (fabsf(f) > rad);
+    }
+    return ok;
+}
+
+template <int G>
+__device__ __forceinline__ float group_min(float v) {
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ uint32_t group_or(uint32_t v) {
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// ---- per-tile shared arrays (SoA, one slot per agent of the tile) --------------------------------------
+struct TileSmem {
+    float* px;  float* py;      // post-step (or current, in refresh mode) centre position
+    float* ox;  float* oy;      // pre-step position (reward progress)
+    float* cs;  float* sn;      // cos / sin of the heading
+    float* vx;  float* vy;  float* vabs;
+    float* vtx;                 // [8][A]: x0..x3, y0..y3
+    float* car;                 // [4][A]: carry of the pre-step pose
+    float* sc;                  // [8][A]: phase-B results: d_ref, idx(int), dLcg, dRcg, min4L, min4R, flags(int), spare
+    float* dij;                 // [A][N] centre distances
+    float* obs;                 // [A][D]
+    int* path;
+    int* flags;
+};
+
+__device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, int D, TileSmem& t) {
+    float* f = reinterpret_cast<float*>(base);
+    t.px = f; f += A; t.py = f; f += A; t.ox = f; f += A; t.oy = f; f += A;
+    t.cs = f; f += A; t.sn = f; f += A; t.vx = f; f += A; t.vy = f; f += A; t.vabs = f; f += A;
+    t.vtx = f; f += 8 * A; t.car = f; f += 4 * A; t.sc = f; f += 8 * A;
+    t.dij = f; f += A * N; t.obs = f; f += A * D;
+    t.path = reinterpret_cast<int*>(f); f += A; t.flags = reinterpret_cast<int*>(f); f += A;
+}
+__host__ __device__ inline size_t tile_smem_bytes(int A, int N, int D) {
+    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 2) + (size_t)A * N + (size_t)A * D);
+}
+
+// ---- phase B building blocks ------------------------------------------------------------------------------
+
+// centre line: min distance + closest index from (px,py); lanes of the group split the work
+template <int G>
+__device__ __forceinline__ void scan_center(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_c,
+                                            int hint_seg, bool exhaustive, float px, float py, int lane, float& d_out,
+                                            int& idx_out) {
+    const int nseg = n_c - 1;
+    const int nch = (nseg + kChunk - 1) / kChunk;
+    int c0 = hint_seg / kChunk;
+    c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
+    Best b;
+    b.init();
+    {   // hint chunk, cooperatively
+        int s1 = min(c0 * kChunk + kChunk, nseg);
+        for (int s = c0 * kChunk + lane; s < s1; s += G) {
+            float2 a = pts[s], e = pts[s + 1];
+            float lx = e.x - a.x, ly = e.y - a.y;
+            b.upd(seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py), s);
+        }
+    }
+    float thr = group_min<G>(b.d) + kDistMargin;
+    for (int c = lane; c < nch; c += G) {
+        if (c == c0) continue;
+        if (!exhaustive && box_lb(boxes[c], px, py) > thr) continue;
+        int s1 = min(c * kChunk + kChunk, nseg);
+        for (int s = c * kChunk; s < s1; s++) {
+            float2 a = pts[s], e = pts[s + 1];
+            float lx = e.x - a.x, ly = e.y - a.y;
+            b.upd(seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py), s);
+        }
+    }
+    // (d, idx) lexicographic min across the group == torch.min's first minimal index
+    float d = b.d;
+    int idx = b.idx;
+#pragma unroll
+    for (int m = 1; m < G; m <<= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, d, m);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, m);
+        if (od < d || (od == d && oi < idx)) { d = od; idx = oi; }
+    }
+    d_out = d;
+    idx_out = idx + 1; // helper_scenario.py:885-887
+}
+
+// boundary: distances of the centre + 4 vertices, and the rectangle-crossing flag
+template <int G>
+__device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_b,
+                                              int hint_seg, bool exhaustive, float px, float py, const Rect& r,
+                                              float rect_radius, int lane, float& d_cg, float dv[4], bool& hit_out) {
+    const int nseg = n_b - 1;
+    const int nch = (nseg + kChunk - 1) / kChunk;
+    int c0 = hint_seg / kChunk;
+    c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
+    BestD bc, bv[4];
+    bc.init();
+#pragma unroll
+    for (int v = 0; v < 4; v++) bv[v].init();
+    bool hit = false;
+    {
+        int s1 = min(c0 * kChunk + kChunk, nseg);
+        for (int s = c0 * kChunk + lane; s < s1; s += G) {
+            float2 a = pts[s], e = pts[s + 1];
+            float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
+            bc.upd(seg_q(a.x, a.y, lx, ly, len2, px, py));
+#pragma unroll
+            for (int v = 0; v < 4; v++) bv[v].upd(seg_q(a.x, a.y, lx, ly, len2, r.vx[v], r.vy[v]));
+            hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
+        }
+    }
+    // group-wide bound (lanes that got no segment of the hint chunk hold +inf)
+    float gb = group_min<G>(bc.d);
+#pragma unroll
+    for (int v = 0; v < 4; v++) gb = fmaxf(gb, group_min<G>(bv[v].d));
+    const float thr = gb + rect_radius + kDistMargin; // lb(vertex) >= lb(centre) - rect_radius
+    for (int c = lane; c < nch; c += G) {
+        if (c == c0) continue;
+        float4 bx = boxes[c];
+        bool do_dist = exhaustive || !(box_lb(bx, px, py) > thr);
+        bool do_x = exhaustive || !box_sign_definite(r, bx);
+        if (!(do_dist | do_x)) continue;
+        int s1 = min(c * kChunk + kChunk, nseg);
+        for (int s = c * kChunk; s < s1; s++) {
+            float2 a = pts[s], e = pts[s + 1];
+            if (do_dist) {
+                float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
+                bc.upd(seg_q(a.x, a.y, lx, ly, len2, px, py));
+#pragma unroll
+                for (int v = 0; v < 4; v++) bv[v].upd(seg_q(a.x, a.y, lx, ly, len2, r.vx[v], r.vy[v]));
+            }
+            if (do_x) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
+        }
+    }
+    d_cg = group_min<G>(bc.d);
+#pragma unroll
+    for (int v = 0; v < 4; v++) dv[v] = group_min<G>(bv[v].d);
+    hit_out = group_or<G>(hit ? 1u : 0u) != 0u;
+}
+
+// helper_scenario.py:892-957 short-term reference path (n_points_shift = 1, sample interval 2)
+__device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int n_c, bool is_loop, int idx, float2 out[3]) {
+#pragma unroll
+    for (int k = 0; k < SGB_N_SHORT_TERM; k++) {
+        int fi = 2 * k + idx + 1;
+        if (is_loop && fi >= n_c - 1) fi = (fi + 1) % n_c;
+        out[k] = cpts[fi];
+    }
+}
+
+// ---- the fused kernel -------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+
+    const int tid = threadIdx.x;
+    const int N = p.N, D = p.D;
+    const int A = p.envs_per_tile * N;      // agent slots in use per tile
+    const sgb_config& cfg = p.cfg;
+
+    // --- stage the map: one elected thread arms the mbarrier and issues the bulk copies -------------
+    const uint32_t bar = smem_u32(&mbar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, (uint32_t)p.blob_bytes);
+        const uint32_t dst = smem_u32(smem);
+        for (int off = 0; off < p.blob_bytes; off += 32768) {
+            int n = min(32768, p.blob_bytes - off);
+            tma_bulk_g2s(dst + off, p.blob + off, (uint32_t)n, bar);
+        }
+    }
+    bool map_ready = false;
+
+    const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(smem);
+    TileSmem ts;
+    const int AS = kThreads / G;            // slot stride of the SoA arrays
+    carve_tile(smem + ((p.blob_bytes + 127) & ~127), AS, N, D, ts);
+
+    const int slot_b = tid / G;             // agent slot this thread works for in phases B/C
+    const int lane = tid % G;
+    const float rect_radius = sqrtf(cfg.half_length * cfg.half_length + cfg.half_width * cfg.half_width) * 1.0001f;
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int env0 = tile * p.envs_per_tile;
+
+        // ================= phase A: one thread per agent ==========================================
+        if (tid < A) {
+            const int e = env0 + tid / N;
+            const int i = tid % N;
+            bool active = e < p.B;
+            if (active && p.mode == 1 && p.env_mask && !p.env_mask[e]) active = false;
+            int flags0 = active ? 0 : -1; // -1 marks an inactive slot
+            if (active) {
+                const size_t g = (size_t)e * N + i;
+                float4 pose = reinterpret_cast<const float4*>(p.buf.pose)[g];
+                float delta = p.buf.aux[4 * g];
+                float4 car = reinterpret_cast<const float4*>(p.buf.carry)[g];
+                float x = pose.x, y = pose.y, psi = pose.z, v = pose.w;
+                ts.ox[tid] = x;
+                ts.oy[tid] = y;
+                float beta1;
+                if (p.mode == 0) {
+                    // helper_training.py:807-836
+                    float2 u = reinterpret_cast<const float2*>(p.buf.action)[g];
+                    u.x = clampf(u.x, -cfg.max_speed, cfg.max_speed);
+                    u.y = clampf(u.y, -cfg.max_steering, cfg.max_steering);
+                    reinterpret_cast<float2*>(p.buf.action)[g] = u;
+                    float acc = clampf((u.x - v) / cfg.dt, -cfg.max_acc, cfg.max_acc);
+                    float rate = clampf((u.y - delta) / cfg.dt, -cfg.max_steering_rate, cfg.max_steering_rate);
+                    // dynamics.py:62-118 + fixed-grid Euler (torchdiffeq)
+                    float td = tanf(delta);
+                    float beta = atanf(cfg.lr_over_lwb * td);
+                    float sb, cb;
+                    sincosf(psi + beta, &sb, &cb);
+                    float f0 = v * cb, f1 = v * sb;
+                    float f2 = ((v / cfg.l_wb) * td) * cosf(beta);
+                    x = x + cfg.dt * f0;
+                    y = y + cfg.dt * f1;
+                    psi = psi + cfg.dt * f2;
+                    v = v + cfg.dt * acc;
+                    delta = delta + cfg.dt * rate;
+                    const float pi_f = 3.14159274101257324f, two_pi = 6.28318548202514648f;
+                    delta = pymod(delta + pi_f, two_pi) - pi_f; // dynamics.py:158
+                }
+                beta1 = atanf(cfg.lr_over_lwb * tanf(delta));   // dynamics.py:161-163
+                float sc_, cc_;
+                sincosf(psi + beta1, &sc_, &cc_);
+                float vx = v * cc_, vy = v * sc_;
+                reinterpret_cast<float4*>(p.buf.pose)[g] = make_float4(x, y, psi, v);
+                reinterpret_cast<float4*>(p.buf.aux)[g] = make_float4(delta, vx, vy, beta1);
+                // helper_scenario.py:742-826 rectangle vertices
+                float sy, cy;
+                sincosf(psi, &sy, &cy);
+                const float hl = cfg.half_length, hw = cfg.half_width;
+                const float nsy = -sy;
+                const float bxs[4] = {hl, hl, -hl, -hl};
+                const float bys[4] = {hw, -hw, -hw, hw};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    ts.vtx[k * AS + tid] = (cy * bxs[k] + nsy * bys[k]) + x;
+                    ts.vtx[(4 + k) * AS + tid] = (sy * bxs[k] + cy * bys[k]) + y;
+                }
+                ts.px[tid] = x; ts.py[tid] = y; ts.cs[tid] = cy; ts.sn[tid] = sy;
+                ts.vx[tid] = vx; ts.vy[tid] = vy; ts.vabs[tid] = sqrtf(vx * vx + vy * vy);
+                ts.car[0 * AS + tid] = car.x; ts.car[1 * AS + tid] = car.y;
+                ts.car[2 * AS + tid] = car.z; ts.car[3 * AS + tid] = car.w;
+                ts.path[tid] = p.buf.path_id[g];
+            }
+            ts.flags[tid] = flags0;
+        }
+        __syncthreads();
+        if (!map_ready) { mbar_wait(bar, 0); map_ready = true; }
+
+        // ================= phase B: G lanes per agent, polyline queries out of the smem map =======
+        const bool slot_ok = (slot_b < A) && (ts.flags[slot_b] >= 0);
+        // all 32 lanes of a warp take part in the shuffles, so inactive slots of a live warp run on
+        // dummy-safe data; a warp without any active slot skips phases B and C altogether
+        const bool warp_live = __any_sync(0xffffffffu, slot_ok);
+        if (warp_live) {
+            const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
+            const float2* pts = reinterpret_cast<const float2*>(smem + hdr->pts_off);
+            const float4* boxes = reinterpret_cast<const float4*>(smem + hdr->box_off);
+            const int sl = slot_ok ? slot_b : 0;
+            int path = slot_ok ? ts.path[sl] : 0;
+            path = (path < 0 || path >= hdr->n_paths) ? 0 : path;
+            const PathRec pr = paths[path];
+            const float px = slot_ok ? ts.px[sl] : 0.0f, py = slot_ok ? ts.py[sl] : 0.0f;
+            Rect r;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                r.vx[k] = slot_ok ? ts.vtx[k * AS + sl] : 0.0f;
+                r.vy[k] = slot_ok ? ts.vtx[(4 + k) * AS + sl] : 0.0f;
+            }
+            r.finish();
+            const bool ex = cfg.exhaustive != 0;
+            int hint = __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1; // last closest segment
+            if (p.mode == 1) hint = 0x3fffffff / kChunk;                          // no history: start at the far end
+            float d_ref, dLc, dRc, dLv[4], dRv[4];
+            int idx_ref;
+            bool hitL, hitR;
+            scan_center<G>(pts + pr.c_off, boxes + pr.cbox, pr.n_c, hint, ex, px, py, lane, d_ref, idx_ref);
+            // the boundaries run alongside the centre line: reuse its closest segment as the hint
+            const int h2 = idx_ref - 1;
+            scan_boundary<G>(pts + pr.l_off, boxes + pr.lbox, pr.n_l, h2, ex, px, py, r, rect_radius, lane, dLc, dLv, hitL);
+            scan_boundary<G>(pts + pr.r_off, boxes + pr.rbox, pr.n_r, h2, ex, px, py, r, rect_radius, lane, dRc, dRv, hitR);
+            dLc = dLc - cfg.half_width; // world_state_rt.py:608-610
+            dRc = dRc - cfg.half_width;
+            int fl = (hitL | hitR) ? (int)SGB_FLAG_COLLIDE_LANE : 0;
+            if (!pr.is_loop && lane == 0) {
+                // entry / exit segments (world_state_rt.py:394-406, world_state_rt_sim.py:412-424)
+                const float2* L = pts + pr.l_off;
+                const float2* R = pts + pr.r_off;
+                if (rect_cross_seg_L1(r, L[0].x, L[0].y, R[0].x, R[0].y)) fl |= (int)SGB_FLAG_ENTRY;
+                if (rect_cross_seg_L1(r, L[pr.n_l - 1].x, L[pr.n_l - 1].y, R[pr.n_r - 1].x, R[pr.n_r - 1].y))
+                    fl |= (int)SGB_FLAG_EXIT;
+            }
+            if (slot_ok && lane == 0) {
+                float m4L = fminf(fminf(dLv[0], dLv[1]), fminf(dLv[2], dLv[3]));
+                float m4R = fminf(fminf(dRv[0], dRv[1]), fminf(dRv[2], dRv[3]));
+                ts.sc[0 * AS + sl] = d_ref;
+                ts.sc[1 * AS + sl] = __int_as_float(idx_ref);
+                ts.sc[2 * AS + sl] = dLc;
+                ts.sc[3 * AS + sl] = dRc;
+                ts.sc[4 * AS + sl] = m4L;
+                ts.sc[5 * AS + sl] = m4R;
+                ts.flags[sl] = (p.mode == 0) ? fl : 0;
+                if (p.buf.dbg) {
+                    const int e = env0 + sl / N;
+                    float* dbg = p.buf.dbg + ((size_t)e * N + sl % N) * 16;
+                    dbg[0] = d_ref; dbg[1] = __int_as_float(idx_ref); dbg[2] = dLc; dbg[7] = dRc;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) { dbg[3 + v] = dLv[v]; dbg[8 + v] = dRv[v]; }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= phase C: interactions inside the env, reward, observation ===============
+        if (warp_live) {
+            const int sl = slot_ok ? slot_b : 0;
+            const int i = sl % N;
+            const int base = sl - i; // slot of agent 0 of this env
+            const float pix = ts.px[sl], piy = ts.py[sl];
+            Rect ri;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { ri.vx[k] = ts.vtx[k * AS + sl]; ri.vy[k] = ts.vtx[(4 + k) * AS + sl]; }
+            ri.finish();
+            uint32_t coll = 0;
+            float ttc_sum = 0.0f;
+            const bool step_mode = (p.mode == 0);
+            if (slot_ok) {
+                for (int j = lane; j < N; j += G) {
+                    const int sj = base + j;
+                    float dx = pix - ts.px[sj], dy = piy - ts.py[sj];
+                    float pp = dx * dx + dy * dy;
+                    float dist = sqrtf(pp);                       // helper_scenario.py:1012-1029
+                    ts.dij[sl * N + j] = (j == i) ? cfg.diag : dist;
+                    if (!step_mode) continue;
+                    if (j != i) {
+                        // world_state_rt_sim.py:384-393: interX(vertices[lo], vertices[hi]), lo < hi
+                        float hx[4], hy[4];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) { hx[k] = ts.vtx[k * AS + sj]; hy[k] = ts.vtx[(4 + k) * AS + sj]; }
+                        bool hit;
+                        if (i < j) {
+                            hit = rect_cross_rect(ri, hx, hy);
+                        } else {
+                            Rect rj;
+#pragma unroll
+                            for (int k = 0; k < 4; k++) { rj.vx[k] = hx[k]; rj.vy[k] = hy[k]; }
+                            rj.finish();
+                            hit = rect_cross_rect(rj, ri.vx, ri.vy);
+                        }
+                        if (hit) coll |= (1u << j);
+                    }
+                    if (cfg.rew_flags & SGB_REW_TTC) {
+                        // road_traffic.py:1255-1332 (p_rel = p_j - p_i)
+                        const float eps = 1e-6f;
+                        float rx = ts.px[sj] - pix, ry = ts.py[sj] - piy;
+                        float wx = ts.vx[sj] - ts.vx[sl], wy = ts.vy[sj] - ts.vy[sl];
+                        float qa = wx * wx + wy * wy;
+                        float qb = 2.0f * (rx * wx + ry * wy);
+                        float rr = rx * rx + ry * ry;
+                        float qc = rr - cfg.dsafe_sq;
+                        float disc = qb * qb - (4.0f * qa) * qc;
+                        float sq = sqrtf(fmaxf(disc, 0.0f));
+                        float dd = sqrtf(fmaxf(rr, 0.0f));
+                        bool valid = (qa > eps) && (disc > 0.0f) && (qb < 0.0f);
+                        float cand = (-qb - sq) / (2.0f * qa + eps);
+                        float ttc = __int_as_float(0x7f800000);
+                        if (valid && cand > 0.0f) ttc = cand;
+                        if (dd <= cfg.near_agents_low) ttc = 0.0f;
+                        if (j == i) ttc = __int_as_float(0x7f800000);
+                        if (!(dd <= cfg.near_agents_high)) ttc = __int_as_float(0x7f800000);
+                        ttc = fminf(ttc, cfg.ttc_high);
+                        ttc_sum += dec_lin(ttc, cfg.ttc_low, cfg.ttc_high);
+                    }
+                }
+            }
+            coll = group_or<G>(coll);
+            ttc_sum = group_sum<G>(ttc_sum);
+            __syncwarp();
+            if (slot_ok && lane == 0) {
+                const int e = env0 + sl / N;
+                const size_t g = (size_t)e * N + i;
+                const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
+                const float2* pts = reinterpret_cast<const float2*>(smem + hdr->pts_off);
+                int path = ts.path[sl];
+                path = (path < 0 || path >= hdr->n_paths) ? 0 : path;
+                const PathRec pr = paths[path];
+                const float d_ref_n = ts.sc[0 * AS + sl];
+                const int idx_n = __float_as_int(ts.sc[1 * AS + sl]);
+                const float dLc = ts.sc[2 * AS + sl], dRc = ts.sc[3 * AS + sl];
+                const float m4L = ts.sc[4 * AS + sl], m4R = ts.sc[5 * AS + sl];
+                const float c_dref = ts.car[0 * AS + sl], c_mL = ts.car[1 * AS + sl], c_mR = ts.car[2 * AS + sl];
+                const int c_idx = __float_as_int(ts.car[3 * AS + sl]);
+                float2 st_new[3], st_old[3];
+                short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, idx_n, st_new);
+                // what agent i's reward and observation see:
+                float o_dref, o_mL, o_mR, d_bound;
+                const float2* o_st;
+                if (!step_mode) {               // right after a reset everything is fresh
+                    o_dref = d_ref_n; o_mL = fminf(dLc, m4L); o_mR = fminf(dRc, m4R); o_st = st_new;
+                    d_bound = fminf(o_mL, o_mR);
+                } else if (i == 0) {            // agent 0: fresh centre queries, vertex queries of the OLD rectangle
+                    o_dref = d_ref_n; o_mL = fminf(dLc, c_mL); o_mR = fminf(dRc, c_mR); o_st = st_new;
+                    d_bound = fminf(o_mL, o_mR);
+                } else {                        // agents >= 1: reward is fresh, observation is one step stale
+                    short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, c_idx, st_old);
+                    o_dref = c_dref; o_mL = c_mL; o_mR = c_mR; o_st = st_old;
+                    d_bound = fminf(fminf(dLc, m4L), fminf(dRc, m4R));
+                }
+                int fl = ts.flags[sl];
+                if (coll) fl |= (int)SGB_FLAG_COLLIDE_AGENT;
+                ts.flags[sl] = fl;
+
+                if (step_mode) {
+                    // ---- reward: road_traffic.py:947-1253 (short-term path of the PREVIOUS step) ----
+                    if (i == 0) short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, c_idx, st_old);
+                    const float oxp = ts.ox[sl], oyp = ts.oy[sl];
+                    float mvx = pix - oxp, mvy = piy - oyp;
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        float rx = st_old[k].x - oxp, ry = st_old[k].y - oyp;
+                        acc += (mvx * rx + mvy * ry) * cfg.w_ref[k];
+                    }
+                    float rew = 0.0f;
+                    rew += (acc / cfg.speed_dt) * cfg.reward_progress;
+                    const float pen_a2a = (coll ? 1.0f : 0.0f) * cfg.penalty_collide_agents;
+                    const float pen_lane = ((fl & SGB_FLAG_COLLIDE_LANE) ? 1.0f : 0.0f) * cfg.penalty_collide_lane;
+                    const float pen_nb = dec_lin(d_bound, cfg.near_boundary_low, cfg.near_boundary_high) * cfg.penalty_near_boundary;
+                    if (cfg.rew_flags & SGB_REW_EXACT_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                    if (cfg.rew_flags & SGB_REW_TTC) {
+                        float risk = ttc_sum / (float)(N - 1 > 1 ? N - 1 : 1);
+                        rew += risk * cfg.penalty_near_agents;
+                        rew += pen_nb;
+                        rew += pen_a2a; rew += pen_lane;
+                        if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                    }
+                    if (cfg.rew_flags & SGB_REW_DISTANCE) {
+                        float s = 0.0f;
+                        for (int j = 0; j < N; j++) s += dec_lin(ts.dij[sl * N + j], cfg.near_agents_low, cfg.near_agents_high);
+                        rew += s * cfg.penalty_near_agents;
+                        rew += pen_nb;
+                        if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                    }
+                    p.buf.reward[g] = clampf(rew, -1.0f, 1.0f);
+                    p.buf.agent_flags[g] = (uint8_t)fl;
+                    if (p.buf.collide_with) p.buf.collide_with[g] = coll;
+                } else {
+                    p.buf.agent_flags[g] = 0;
+                    if (p.buf.collide_with) p.buf.collide_with[g] = 0;
+                }
+                // ---- next step's carry ----
+                {
+                    float4 nc;
+                    nc.x = d_ref_n;
+                    nc.y = (i == 0) ? m4L : fminf(dLc, m4L);
+                    nc.z = (i == 0) ? m4R : fminf(dRc, m4R);
+                    nc.w = __int_as_float(idx_n);
+                    reinterpret_cast<float4*>(p.buf.carry)[g] = nc;
+                }
+                if (p.buf.dbg) p.buf.dbg[g * 16 + 12] = d_bound;
+
+                // ---- observation: observation_provider_rt.py:594-925 (ego view, default flags) ----
+                if (step_mode || p.write_obs) {
+                    float* o = ts.obs + (size_t)sl * D;
+                    const float cs = ts.cs[sl], sn = ts.sn[sl];
+                    int n = 0;
+                    o[n++] = ts.vabs[sl] / cfg.norm_v;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        float dx = o_st[k].x - pix, dy = o_st[k].y - piy;
+                        o[n++] = (dx * cs + dy * sn) / cfg.norm_pos;
+                        o[n++] = (dy * cs - dx * sn) / cfg.norm_pos;
+                    }
+                    o[n++] = o_dref / cfg.norm_dist;
+                    o[n++] = o_mL / cfg.norm_dist;
+                    o[n++] = o_mR / cfg.norm_dist;
+                    // torch.topk(k, largest=False) over distances.agents[i, :]
+                    uint32_t used = 0;
+                    for (int kk = 0; kk < cfg.k_near; kk++) {
+                        int bj = -1;
+                        float bd = __int_as_float(0x7f800000);
+                        for (int j = 0; j < N; j++) {
+                            float dj = ts.dij[sl * N + j];
+                            if (!((used >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
+                        }
+                        used |= 1u << bj;
+                        const int sj = base + bj;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            float dx = ts.vtx[v * AS + sj] - pix, dy = ts.vtx[(4 + v) * AS + sj] - piy;
+                            o[n++] = (dx * cs + dy * sn) / cfg.norm_pos;
+                            o[n++] = (dy * cs - dx * sn) / cfg.norm_pos;
+                        }
+                        // |v_j| * (cos, sin)(psi_j - psi_i) via the stored cos/sin of both headings
+                        const float cj = ts.cs[sj], sj_ = ts.sn[sj];
+                        const float cr = cj * cs + sj_ * sn, sr = sj_ * cs - cj * sn;
+                        o[n++] = (ts.vabs[sj] * cr) / cfg.norm_v;
+                        o[n++] = (ts.vabs[sj] * sr) / cfg.norm_v;
+                        o[n++] = bd / cfg.norm_dist;
+                        if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ================= phase D: per-env outputs + coalesced observation write-back ============
+        if (p.mode == 0 && tid < A && (tid % N) == 0 && ts.flags[tid] >= 0) {
+            const int e = env0 + tid / N;
+            int any = 0;
+            for (int j = 0; j < N; j++) any |= ts.flags[tid + j];
+            const int step = p.buf.step_count[e] + 1;          // road_traffic.py:954-962
+            p.buf.step_count[e] = step;
+            // road_traffic.py:1451-1457 (training mode)
+            const bool dn = (step == cfg.max_steps - 1) || (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE));
+            p.buf.done[e] = dn ? 1 : 0;
+        }
+        if (p.mode == 0 || p.write_obs) {
+            const int n_env = min(p.envs_per_tile, p.B - env0);
+            const int nf = n_env * N * D;                       // floats of this tile (contiguous in HBM)
+            float* dst = p.buf.obs + (size_t)env0 * N * D;
+            if (p.mode == 0 && ((nf & 3) == 0) && ((((size_t)env0 * N * D) & 3) == 0)) {
+                const float4* s4 = reinterpret_cast<const float4*>(ts.obs);
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int k = tid; k < nf / 4; k += kThreads) d4[k] = s4[k];
+            } else {
+                for (int k = tid; k < nf; k += kThreads) {
+                    const int slot = k / D;
+                    if (ts.flags[slot] >= 0) dst[k] = ts.obs[k];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!map_ready) mbar_wait(bar, 0); // never leave with a bulk copy in flight
+}
+
+// ---- placement / reset kernels ------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// counter-based: one 64-bit draw per (seed, epoch, env, agent, try, which)
+__device__ __forceinline__ uint64_t draw(uint64_t seed, uint64_t epoch, uint64_t env, uint32_t agent, uint32_t tr, uint32_t which) {
+    uint64_t h = mix64(seed ^ mix64(epoch));
+    h = mix64(h ^ env);
+    h = mix64(h ^ (((uint64_t)agent << 40) | ((uint64_t)tr << 8) | which));
+    return h;
+}
+
+struct PlaceParams {
+    sgb_config cfg;
+    sgb_buffers buf;
+    const unsigned char* blob;
+    const float* yaw;          // [pts of centre lines] indexed like the blob's centre points (c_off + point)
+    const uint8_t* agent_mask;
+    const int32_t* path;
+    const int32_t* point;
+    const float* speed;
+    int32_t B, N;
+};
+
+__device__ __forceinline__ void place_agent(const sgb_config& cfg, const sgb_buffers& buf, const unsigned char* blob,
+                                            const float* yaw, size_t g, int path, int point, float speed) {
+    const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(blob);
+    const PathRec* paths = reinterpret_cast<const PathRec*>(blob + hdr->path_off);
+    const float2* pts = reinterpret_cast<const float2*>(blob + hdr->pts_off);
+    const PathRec pr = paths[path];
+    float2 c = pts[pr.c_off + point];
+    float psi = yaw[pr.c_off + point];
+    // world_state_rt_sim.py:189-211: steering 0, sideslip 0, vel = speed * (cos, sin)(0 + yaw)
+    reinterpret_cast<float4*>(buf.pose)[g] = make_float4(c.x, c.y, psi, speed);
+    float s, co;
+    sincosf(0.0f + psi, &s, &co);
+    reinterpret_cast<float4*>(buf.aux)[g] = make_float4(0.0f, speed * co, speed * s, 0.0f);
+    buf.path_id[g] = path;
+}
+
+__global__ void place_kernel(const PlaceParams p) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)p.B * p.N) return;
+    if (p.agent_mask && !p.agent_mask[g]) return;
+    place_agent(p.cfg, p.buf, p.blob, p.yaw, g, p.path[g], p.point[g], p.speed[g]);
+}
+
+struct ResetParams {
+    sgb_config cfg;
+    sgb_buffers buf;
+    const unsigned char* blob;
+    const float* yaw;
+    uint8_t* touched;          // [B] out: env needs a refresh
+    int32_t* n_failed;
+    uint64_t seed, epoch;
+    int64_t env_offset;
+    int32_t B, N, path_lo, path_hi, max_tries, all;
+};
+
+// one thread per env: sequential bounded rejection sampling (world_state_rt_sim.py:215-311)
+__global__ void reset_kernel(const ResetParams p) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.B) return;
+    const int N = p.N;
+    const bool full = p.all || p.buf.done[e];
+    uint32_t respawn = 0;
+    if (!full) {
+        if (!p.cfg.respawn_on_exit) { p.touched[e] = 0; return; }
+        for (int a = 0; a < N; a++)
+            if (p.buf.agent_flags[(size_t)e * N + a] & (SGB_FLAG_ENTRY | SGB_FLAG_EXIT)) respawn |= 1u << a;
+        if (!respawn) { p.touched[e] = 0; return; }
+    }
+    const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(p.blob);
+    const PathRec* paths = reinterpret_cast<const PathRec*>(p.blob + hdr->path_off);
+    const float2* pts = reinterpret_cast<const float2*>(p.blob + hdr->pts_off);
+    float qx[SGB_MAX_AGENTS], qy[SGB_MAX_AGENTS];
+    for (int a = 0; a < N; a++) {
+        float4 ps = reinterpret_cast<const float4*>(p.buf.pose)[(size_t)e * N + a];
+        qx[a] = ps.x; qy[a] = ps.y;
+    }
+    const uint64_t env_g = (uint64_t)(p.env_offset + e);
+    int failed = 0;
+    for (int a = 0; a < N; a++) {
+        if (!full && !((respawn >> a) & 1u)) continue;
+        bool ok = false;
+        int path = p.path_lo, point = 3;
+        for (int tr = 0; tr < p.max_tries && !ok; tr++) {
+            path = p.path_lo + (int)(draw(p.seed, p.epoch, env_g, a, tr, 0) % (uint64_t)(p.path_hi - p.path_lo));
+            const PathRec pr = paths[path];
+            const int end = pr.n_c / 2;
+            point = 3 + (int)(draw(p.seed, p.epoch, env_g, a, tr, 1) % (uint64_t)(end - 3 > 0 ? end - 3 : 1));
+            const float2 c = pts[pr.c_off + point];
+            ok = true;
+            // full reset: against agents 0..a-1 (agent 0 always feasible); respawn: against all others
+            const int lim = full ? a : N;
+            for (int o = 0; o < lim; o++) {
+                if (o == a) continue;
+                float dx = c.x - qx[o], dy = c.y - qy[o];
+                if (!((dx * dx + dy * dy) >= p.cfg.reset_min_dist_sq)) { ok = false; break; }
+            }
+            if (ok) { qx[a] = c.x; qy[a] = c.y; }
+        }
+        if (!ok) {   // keep the last candidate rather than spinning forever; report it
+            failed++;
+            const PathRec pr = paths[path];
+            const float2 c = pts[pr.c_off + point];
+            qx[a] = c.x; qy[a] = c.y;
+        }
+        const float u = (float)(draw(p.seed, p.epoch, env_g, a, 0, 2) >> 40) * (1.0f / 16777216.0f);
+        place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + a, path, point, u * p.cfg.max_speed);
+    }
+    if (full) p.buf.step_count[e] = 0; // road_traffic.py:875-877
+    p.touched[e] = full ? 2 : 1;
+    if (failed && p.n_failed) atomicAdd(p.n_failed, failed);
+}
+
+} // namespace sgb

@@ -1,0 +1,175 @@
+"""RoadTrafficEnv — batched tensor front-end of the fused CUDA environment step.
+
+Owns the device buffers (torch tensors; the C library only sees ``data_ptr()``) and one ``sgb_ctx``.
+State layout (env-major, agent-minor — DESIGN.md "Data layout in HBM"):
+    pose [B,N,4]  x, y, psi, v            aux [B,N,4]  delta, vx, vy, beta
+    path_id [B,N] int32                   carry [B,N,4]  d_ref, min dL, min dR, idx_ref (pre-step pose)
+    action [B,N,2]  obs [B,N,D]  reward [B,N]  done [B] u8  agent_flags [B,N] u8  step_count [B] i32
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .config import EnvConfig
+from .maps import MapLibrary
+
+
+class RoadTrafficEnv:
+    def __init__(self, config: EnvConfig = None, num_envs: int = 32, device="cuda:0", seed: int = 0,
+                 env_offset: int = 0, debug: bool = False, max_reset_tries: int = 64, **cfg_kwargs):
+        self.config = config or EnvConfig(**cfg_kwargs)
+        self.L = _lib.load_library()                      # raises if the .so is missing
+        if not torch.cuda.is_available():
+            raise _lib.SgbError("RoadTrafficEnv needs a CUDA device: the environment step exists only as CUDA "
+                                "kernels (no CPU fallback)")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SgbError(f"device must be a CUDA device, got {device}")
+        self.map = MapLibrary(self.config.scenario_type)
+        self.cfg = self.config.lower(self.map)
+        r = self.config.resolved(self.config.lane_width(self.map), self.map.default_n_agents)
+        self.B, self.N = int(num_envs), int(r["n_agents"])
+        if not 1 <= self.N <= _lib.SGB_MAX_AGENTS:
+            raise ValueError(f"n_agents must be in [1, {_lib.SGB_MAX_AGENTS}]")
+        self.dt = r["dt"]
+        self.seed, self.env_offset, self.epoch = int(seed), int(env_offset), 0
+        self.max_reset_tries = int(max_reset_tries)
+        self.path_lo, self.path_hi = self.map.default_path_range(self.config.cpm_scenario_probabilities)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._ctx = C.c_void_p()
+        d = self.map.desc()
+        with torch.cuda.device(idx):
+            _lib.check(self.L.sgb_create(C.byref(self._ctx), idx, C.byref(d), C.byref(self.cfg)), "sgb_create")
+        self.D = self.L.sgb_obs_dim(self._ctx)
+        B, N, dev = self.B, self.N, self.device
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)  # noqa: E731
+        self.pose, self.aux, self.carry = z(B, N, 4), z(B, N, 4), z(B, N, 4)
+        self.path_id = z(B, N, dtype=torch.int32)
+        self.action = z(B, N, 2)
+        self.step_count = z(B, dtype=torch.int32)
+        self.obs, self.reward = z(B, N, self.D), z(B, N)
+        self.done = z(B, dtype=torch.uint8)
+        self.agent_flags = z(B, N, dtype=torch.uint8)
+        self.collide_with = z(B, N, dtype=torch.int32)
+        self.dbg = z(B, N, 16) if debug else None
+        self.n_failed = z(1, dtype=torch.int32)
+        self._buf = _lib.Buffers()
+        for name in _lib.BUFFER_FIELDS:
+            t = getattr(self, name)
+            setattr(self._buf, name, t.data_ptr() if t is not None else None)
+        self._h = None  # pinned host staging for step_host
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.L.sgb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.L.sgb_launch_count(self._ctx))
+
+    @property
+    def map_bytes(self):
+        return int(self.L.sgb_map_bytes(self._ctx))
+
+    # ------------------------------------------------------------------ the path
+    def step(self, action: torch.Tensor = None, auto_reset: bool = False):
+        """One fused-kernel environment step.  Returns views (obs [B,N,D], reward [B,N], done [B] uint8)."""
+        if action is not None:
+            self.action.copy_(action.reshape(self.B, self.N, 2))
+        _lib.check(self.L.sgb_step(self._ctx, self.B, self.N, C.byref(self._buf), self._stream()), "sgb_step")
+        if auto_reset:
+            self.reset_done(write_obs=False)
+        return self.obs, self.reward, self.done
+
+    def reset_done(self, write_obs: bool = True):
+        """Masked device-side reset of done envs + respawn of agents that crossed an entry/exit segment."""
+        self.epoch += 1
+        _lib.check(self.L.sgb_reset(self._ctx, self.B, self.N, C.byref(self._buf), self.path_lo, self.path_hi,
+                                    self.seed, self.epoch, self.env_offset, self.max_reset_tries, int(write_obs),
+                                    C.c_void_p(self.n_failed.data_ptr()), self._stream()), "sgb_reset")
+
+    def reset(self):
+        """Environment.reset(): (re)place every agent of every env; returns the fresh observation."""
+        self.epoch += 1
+        _lib.check(self.L.sgb_reset_all(self._ctx, self.B, self.N, C.byref(self._buf), self.path_lo, self.path_hi,
+                                        self.seed, self.epoch, self.env_offset, self.max_reset_tries,
+                                        C.c_void_p(self.n_failed.data_ptr()), self._stream()), "sgb_reset_all")
+        self.done.zero_()
+        return self.obs
+
+    def refresh(self, env_mask: torch.Tensor = None, write_obs: bool = False):
+        m = None
+        if env_mask is not None:
+            m = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _lib.check(self.L.sgb_refresh(self._ctx, self.B, self.N, C.byref(self._buf),
+                                      C.c_void_p(m.data_ptr()) if m is not None else None, int(write_obs),
+                                      self._stream()), "sgb_refresh")
+        return self.obs
+
+    def place(self, path, point, speed, agent_mask=None):
+        """Put agents at (path, point) with `speed` (parity mode: the caller supplies the reset draws)."""
+        dev = self.device
+        path = torch.as_tensor(np.asarray(path), dtype=torch.int32, device=dev).contiguous()
+        point = torch.as_tensor(np.asarray(point), dtype=torch.int32, device=dev).contiguous()
+        speed = torch.as_tensor(np.asarray(speed), dtype=torch.float32, device=dev).contiguous()
+        m = None
+        if agent_mask is not None:
+            m = torch.as_tensor(np.asarray(agent_mask), device=dev).to(torch.uint8).contiguous()
+        _lib.check(self.L.sgb_place(self._ctx, self.B, self.N, C.byref(self._buf),
+                                    C.c_void_p(m.data_ptr()) if m is not None else None,
+                                    C.c_void_p(path.data_ptr()), C.c_void_p(point.data_ptr()),
+                                    C.c_void_p(speed.data_ptr()), self._stream()), "sgb_place")
+
+    def set_state(self, pos, rot, speed, steering, path_id, step_count=None, write_obs=False):
+        """Teacher forcing: inject a state, then rebuild everything derived from it (sgb_refresh)."""
+        dev = self.device
+        t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32, device=dev)  # noqa: E731
+        self.pose[..., 0:2] = t(pos)
+        self.pose[..., 2] = t(rot)
+        self.pose[..., 3] = t(speed)
+        self.aux[..., 0] = t(steering)
+        self.path_id.copy_(torch.as_tensor(np.asarray(path_id), dtype=torch.int32, device=dev))
+        if step_count is not None:
+            self.step_count.copy_(torch.as_tensor(np.asarray(step_count), dtype=torch.int32, device=dev))
+        return self.refresh(write_obs=write_obs)
+
+    def step_host(self, h_action: torch.Tensor):
+        """End-to-end step with HOST buffers through sgb_step_host (H2D action, D2H obs/reward/done inside)."""
+        if self._h is None:
+            pin = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype).pin_memory()  # noqa: E731
+            self._h = dict(obs=pin(self.B, self.N, self.D), reward=pin(self.B, self.N),
+                           done=pin(self.B, dtype=torch.uint8))
+        h = self._h
+        assert h_action.device.type == "cpu" and h_action.dtype == torch.float32 and h_action.is_contiguous()
+        _lib.check(self.L.sgb_step_host(self._ctx, self.B, self.N, C.byref(self._buf),
+                                        C.c_void_p(h_action.data_ptr()), C.c_void_p(h["obs"].data_ptr()),
+                                        C.c_void_p(h["reward"].data_ptr()), C.c_void_p(h["done"].data_ptr()),
+                                        self._stream()), "sgb_step_host")
+        return h["obs"], h["reward"], h["done"]
+
+    # ------------------------------------------------------------------ reference-named views
+    @property
+    def pos(self): return self.pose[..., 0:2]
+    @property
+    def rot(self): return self.pose[..., 2]
+    @property
+    def speed(self): return self.pose[..., 3]
+    @property
+    def steering(self): return self.aux[..., 0]
+    @property
+    def vel(self): return self.aux[..., 1:3]
+    @property
+    def sideslip_angle(self): return self.aux[..., 3]

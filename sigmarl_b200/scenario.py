@@ -1,0 +1,314 @@
+"""VMAS ``BaseScenario``-shaped facade over the fused CUDA step — the drop-in boundary.
+
+Mirrors ``ScenarioRoadTraffic`` (``sigmarl/scenarios/road_traffic.py``): ``make_world`` (:104),
+``reset_world_at`` (:816), ``process_action`` (no-op, ``dynamics.py:194``), ``reward`` (:925),
+``observation`` (:1334), ``done`` (:1368), ``info`` (:1489) and ``world.step()``
+(``WorldCustom.step``, ``helper_training.py:797``), with the same argument meaning and the same
+attribute names on ``world.agents[i]`` (``state.pos/rot/vel/speed/steering/sideslip_angle``,
+``action.u``, ``u_range``, ``max_speed``, ``dynamics.needed_action_size``).
+
+How the per-agent VMAS protocol maps onto ONE kernel launch per step: ``world.step()`` launches the fused
+kernel, which already produces every agent's reward / observation / flags; ``reward(agent_i)`` /
+``observation(agent_i)`` return the ``[:, i]`` slice of the output buffers (VMAS clones them), ``done()``
+returns the done mask and — like the reference (:1462-1472) — respawns agents that crossed an entry/exit
+segment.  The stale-value semantics of the interleaved call order are reproduced inside
+the kernel, so the calls may come in any order after ``world.step()``.
+
+If the real ``vmas`` package is importable the scenario subclasses its ``BaseScenario``; otherwise a
+minimal stand-in with the same surface is used (vmas is not installable in the build image).
+"""
+import math
+from typing import Dict, Optional
+
+import torch
+
+from .config import AGENT_LENGTH, AGENT_WIDTH, EnvConfig, MAX_SPEED, MAX_STEERING
+from .env import RoadTrafficEnv
+from . import lib as _lib
+
+try:  # pragma: no cover - vmas is absent in the build image
+    from vmas.simulator.scenario import BaseScenario as _VmasBaseScenario
+    _HAVE_VMAS = True
+except Exception:  # noqa: BLE001
+    _VmasBaseScenario = object
+    _HAVE_VMAS = False
+
+
+class _Dynamics:
+    """Stands in for ``KinematicBicycleModel`` (dynamics.py): the integration itself runs in the kernel."""
+    needed_action_size = 2
+    max_speed, max_steering = MAX_SPEED, MAX_STEERING
+
+    def process_action(self):
+        pass
+
+    def check_and_process_action(self):
+        pass
+
+
+class _Action:
+    def __init__(self, env: RoadTrafficEnv, i: int):
+        self._env, self._i = env, i
+        self.u_range = [MAX_SPEED, MAX_STEERING]
+        self.u_multiplier = [1, 1]
+
+    @property
+    def u(self) -> torch.Tensor:
+        return self._env.action[:, self._i]
+
+    @u.setter
+    def u(self, value: torch.Tensor):
+        self._env.action[:, self._i].copy_(value)
+
+
+class _VehicleState:
+    """``VehicleState`` (helper_common.py:290-430) as views into the packed device state."""
+
+    def __init__(self, env: RoadTrafficEnv, i: int):
+        self._env, self._i = env, i
+
+    pos = property(lambda s: s._env.pose[:, s._i, 0:2])
+    rot = property(lambda s: s._env.pose[:, s._i, 2:3])
+    speed = property(lambda s: s._env.pose[:, s._i, 3:4])
+    steering = property(lambda s: s._env.aux[:, s._i, 0:1])
+    vel = property(lambda s: s._env.aux[:, s._i, 1:3])
+    sideslip_angle = property(lambda s: s._env.aux[:, s._i, 3:4])
+
+
+class Vehicle:
+    """``Vehicle`` (helper_common.py) / ``vmas.Agent`` surface used by the trainer and evaluation code."""
+
+    def __init__(self, env: RoadTrafficEnv, i: int):
+        self.name = f"agent_{i}"
+        self.index = i
+        self.state = _VehicleState(env, i)
+        self.action = _Action(env, i)
+        self.u_range = [MAX_SPEED, MAX_STEERING]
+        self.max_speed = MAX_SPEED
+        self.dynamics = _Dynamics()
+        self.shape = type("Box", (), dict(length=AGENT_LENGTH, width=AGENT_WIDTH))()
+        self.action_script = None
+
+
+class WorldB200:
+    """``WorldCustom`` surface (helper_training.py:791-861): ``step()`` is the fused kernel launch."""
+
+    def __init__(self, env: RoadTrafficEnv, scenario):
+        self._env, self._scenario = env, scenario
+        self.batch_dim, self.device, self.dt = env.B, env.device, env.dt
+        self.x_semidim = torch.tensor(env.map.world_x_dim, device=env.device, dtype=torch.float32)
+        self.y_semidim = torch.tensor(env.map.world_y_dim, device=env.device, dtype=torch.float32)
+        self.agents = [Vehicle(env, i) for i in range(env.N)]
+        self.parameters = None
+
+    @property
+    def policy_agents(self):
+        return self.agents
+
+    @property
+    def entities(self):
+        return self.agents
+
+    def step(self):
+        self._env.step(None)
+        self._scenario._stepped = True
+
+    def reset(self, env_index=None):
+        pass  # state is overwritten by reset_world_at (vmas zeroes it first; nothing reads the zeros)
+
+
+class ScenarioRoadTrafficB200(_VmasBaseScenario):
+    def __init__(self):
+        if _HAVE_VMAS:  # pragma: no cover
+            super().__init__()
+        self._world = None
+        self.env: Optional[RoadTrafficEnv] = None
+        self.i_iter = 0
+        self._stepped = False
+
+    # -- vmas BaseScenario plumbing when vmas itself is absent
+    if not _HAVE_VMAS:
+        @property
+        def world(self):
+            return self._world
+
+        def env_make_world(self, batch_dim, device, **kwargs):
+            self._world = self.make_world(batch_dim, device, **kwargs)
+            return self._world
+
+        def env_reset_world_at(self, env_index):
+            self.world.reset(env_index)
+            self.reset_world_at(env_index)
+
+        def env_process_action(self, agent):
+            self.process_action(agent)
+            agent.dynamics.check_and_process_action()
+
+        def pre_step(self):
+            pass
+
+        def post_step(self):
+            pass
+
+    # -- road_traffic.py:104
+    def make_world(self, batch_dim: int, device, **kwargs):
+        seed = kwargs.pop("seed", 0)
+        env_offset = kwargs.pop("env_offset", 0)
+        debug = kwargs.pop("debug", False)
+        if hasattr(self, "parameters") and self.parameters is not None:
+            cfg = EnvConfig.from_parameters(self.parameters, **{k: v for k, v in kwargs.items()
+                                                                if k in EnvConfig.__dataclass_fields__})
+        else:
+            known = {k: v for k, v in kwargs.items() if k in EnvConfig.__dataclass_fields__}
+            known.setdefault("scenario_type", "cpm_entire")
+            cfg = EnvConfig(mode="kwargs", **known)
+        self.config = cfg
+        self.env = RoadTrafficEnv(cfg, num_envs=batch_dim, device=device, seed=seed, env_offset=env_offset, debug=debug)
+        self.n_agents = self.env.N
+        self.max_speed, self.max_steering = MAX_SPEED, torch.tensor(MAX_STEERING, device=self.env.device)
+        world = WorldB200(self.env, self)
+        world.parameters = getattr(self, "parameters", None)
+        self._world = world
+        self.num_task_tries = torch.zeros(batch_dim, device=self.env.device, dtype=torch.int32)
+        self.task_success_times = torch.zeros(batch_dim, device=self.env.device, dtype=torch.int32)
+        return world
+
+    # -- road_traffic.py:816
+    def reset_world_at(self, env_index: Optional[int] = None, agent_index: Optional[int] = None):
+        e = self.env
+        if env_index is None:
+            e.reset()
+            return
+        if agent_index is not None:
+            # single-agent respawn: flag the agent as an exit-crosser and let the masked kernel re-place it
+            flags = torch.zeros_like(e.agent_flags)
+            flags[int(env_index), int(agent_index)] = _lib.SGB_FLAG_EXIT
+            keep_f, keep_d = e.agent_flags.clone(), e.done.clone()
+            e.agent_flags.copy_(flags)
+            e.done.zero_()
+            e.reset_done(write_obs=False)
+            keep_f[int(env_index)] = 0
+            e.agent_flags.copy_(keep_f)
+            e.done.copy_(keep_d)
+            return
+        keep_d, keep_f = e.done.clone(), e.agent_flags.clone()
+        e.done.zero_()
+        e.done[int(env_index)] = 1
+        e.agent_flags.zero_()
+        e.reset_done(write_obs=True)
+        keep_f[int(env_index)] = 0
+        e.agent_flags.copy_(keep_f)
+        keep_d[int(env_index)] = 0
+        e.done.copy_(keep_d)
+
+    def process_action(self, agent):
+        pass
+
+    # -- road_traffic.py:925 / :1334 / :1368
+    def reward(self, agent) -> torch.Tensor:
+        return self.env.reward[:, agent.index]
+
+    def observation(self, agent) -> torch.Tensor:
+        return self.env.obs[:, agent.index]
+
+    def done(self) -> torch.Tensor:
+        e = self.env
+        is_done = e.done.bool().clone()
+        if e.cfg.respawn_on_exit and self._stepped:
+            # :1462-1472 — respawn entry/exit crossers of envs that are NOT done (done envs are reset by the caller)
+            keep = e.done.clone()
+            e.done.zero_()
+            crossing = (e.agent_flags & (_lib.SGB_FLAG_ENTRY | _lib.SGB_FLAG_EXIT)) != 0
+            crossing &= ~is_done.unsqueeze(1)
+            saved = e.agent_flags.clone()
+            e.agent_flags.mul_(crossing.to(torch.uint8))
+            e.reset_done(write_obs=False)
+            touched = crossing.any(dim=1)
+            saved[touched] = 0
+            e.agent_flags.copy_(saved)
+            e.done.copy_(keep)
+        self._stepped = False
+        return is_done
+
+    # -- road_traffic.py:1489 (the keys evaluation / training code reads)
+    def info(self, agent) -> Dict[str, torch.Tensor]:
+        e, i = self.env, agent.index
+        fl = e.agent_flags[:, i]
+        two_pi = 2 * math.pi
+        rot = torch.remainder(e.pose[:, i, 2:3], two_pi)
+        rot = torch.where(rot > math.pi, rot - two_pi, rot)
+        return {
+            "pos": e.pose[:, i, 0:2], "rot": rot, "vel": e.aux[:, i, 1:3],
+            "act_vel": e.action[:, i, 0:1], "act_steer": e.action[:, i, 1:2],
+            "distance_ref": e.carry[:, i, 0:1],
+            "is_collision_with_agents": (fl & _lib.SGB_FLAG_COLLIDE_AGENT) != 0,
+            "is_collision_with_lanelets": (fl & _lib.SGB_FLAG_COLLIDE_LANE) != 0,
+            "is_reach_goal": (fl & _lib.SGB_FLAG_EXIT) != 0,
+            "path_id": e.path_id[:, i],
+            "rew_total": e.reward[:, i],
+        }
+
+    def extra_render(self, env_index: int = 0):
+        return []
+
+
+class VmasLikeEnvironment:
+    """The slice of ``vmas.Environment`` the reference is driven through (step / reset / reset_at /
+    get_from_scenario order) for hosts where vmas itself is not installed."""
+
+    def __init__(self, scenario, num_envs, device="cuda:0", max_steps=None, seed=None, **kwargs):
+        self.scenario, self.num_envs, self.device, self.max_steps = scenario, num_envs, device, max_steps
+        if seed is not None:
+            kwargs["seed"] = seed
+        self.world = scenario.env_make_world(num_envs, device, **kwargs)
+        self.agents = self.world.policy_agents
+        self.n_agents = len(self.agents)
+        self.reset()
+
+    def reset(self, return_observations=True):
+        self.scenario.env_reset_world_at(None)
+        self.steps = torch.zeros(self.num_envs, device=self.scenario.env.device)
+        return self.get_from_scenario(return_observations, False, False, False)[0]
+
+    def reset_at(self, index, return_observations=True):
+        self.scenario.env_reset_world_at(index)
+        self.steps[index] = 0
+        return self.get_from_scenario(return_observations, False, False, False)[0]
+
+    def get_from_scenario(self, get_observations, get_rewards, get_infos, get_dones):
+        obs, rews, infos = [], [], []
+        for agent in self.agents:
+            if get_rewards:
+                rews.append(self.scenario.reward(agent).clone())
+            if get_observations:
+                obs.append(self.scenario.observation(agent).clone())
+            if get_infos:
+                infos.append({k: v.clone() for k, v in self.scenario.info(agent).items()})
+        dones = None
+        if get_dones:
+            dones = self.scenario.done().clone()
+            if self.max_steps is not None:
+                dones = dones | (self.steps >= self.max_steps)
+        return obs, rews, dones, infos
+
+    def step(self, actions):
+        for a, agent in zip(actions, self.agents):
+            agent.action.u = a.to(torch.float32)
+        for agent in self.world.agents:
+            self.scenario.env_process_action(agent)
+        self.scenario.pre_step()
+        self.world.step()
+        self.scenario.post_step()
+        self.steps += 1
+        return self.get_from_scenario(True, True, True, True)
+
+
+def make_env(scenario_type="cpm_entire", num_envs=32, device="cuda:0", max_steps=128, parameters=None, **kwargs):
+    """Convenience: scenario + (vmas or vmas-like) Environment, as ``mappo_cavs.py:166-184`` sets it up."""
+    sc = ScenarioRoadTrafficB200()
+    if parameters is not None:
+        sc.parameters = parameters
+    else:
+        kwargs.setdefault("scenario_type", scenario_type)
+    kwargs.setdefault("max_steps", max_steps)
+    return VmasLikeEnvironment(sc, num_envs=num_envs, device=device, max_steps=max_steps, **kwargs)

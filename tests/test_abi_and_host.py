@@ -1,0 +1,142 @@
+"""CPU (-m "not gpu"): the C-ABI library loads and exports every symbol include/sigmarl_b200.h declares,
+refuses to run without a GPU (no CPU fallback), and the host-side mirrors (map library, config lowering)
+agree with the oracle's independent restatement of the same reference constants."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    import __graft_entry__ as ge
+    ge.build()
+    from sigmarl_b200 import lib
+    return lib.load_library()
+
+
+def test_header_symbols_are_exported(L):
+    from sigmarl_b200 import lib
+    hdr = open(os.path.join(REPO, "include", "sigmarl_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(sgb_[a-z_]+)\s*\(", hdr)))
+    assert declared == sorted(lib.EXPORTS), (declared, sorted(lib.EXPORTS))
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.sgb_version() == int(re.search(r"#define SGB_VERSION (\d+)", hdr).group(1))
+
+
+def test_struct_layouts_match_header():
+    from sigmarl_b200 import lib
+    hdr = open(os.path.join(REPO, "include", "sigmarl_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {\n    float dt;"):hdr.index("} sgb_config;")]
+    n_float = sum(len(re.sub(r"/\*.*?\*/", "", line).split(";")[0].split(",")) if line.strip().startswith("float ") else 0
+                  for line in body.splitlines())
+    n_float += 2  # w_ref[3] is declared as one name
+    assert n_float == len(lib.CONFIG_FLOATS), (n_float, len(lib.CONFIG_FLOATS))
+    assert C.sizeof(lib.Config) == 4 * (len(lib.CONFIG_FLOATS) + 5)
+    bufs = hdr[hdr.index("typedef struct {\n    float*   pose;"):hdr.index("} sgb_buffers;")]
+    names = re.findall(r"\*\s*([a-z_]+);", bufs)
+    assert names == lib.BUFFER_FIELDS
+
+
+def test_no_cpu_fallback(L):
+    from sigmarl_b200 import EnvConfig, MapLibrary, RoadTrafficEnv, SgbError, lib
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(SgbError):
+        RoadTrafficEnv(EnvConfig(), num_envs=4)
+    m = MapLibrary("cpm_entire")
+    cfg = EnvConfig(scenario_type="cpm_entire", n_agents=4).lower(m)
+    ctx = C.c_void_p()
+    d = m.desc()
+    rc = L.sgb_create(C.byref(ctx), 0, C.byref(d), C.byref(cfg))
+    assert rc == -3 and not ctx.value, "sgb_create must fail with SGB_ERR_NO_DEVICE when there is no GPU"
+    assert b"CPU fallback" in L.sgb_status_string(rc)
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "sigmarl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("oracle/gen_maps.py", "").replace("oracle/gen_golden.py", ""), f
+
+
+@pytest.mark.parametrize("st", ["cpm_entire", "cpm_mixed", "intersection_1", "on_ramp_2_multilane", "roundabout_2"])
+def test_map_library_matches_oracle_padding(st):
+    from oracle import oracle as O
+    from sigmarl_b200 import MapLibrary
+    m, pm = MapLibrary(st), O.PaddedMap(st)
+    assert m.n_paths == pm.n_paths and m.max_ref_path_points == pm.P
+    assert np.array_equal(m.n_center, pm.n_center)
+    for i in range(m.n_paths):
+        a, b = m.center_off[i], m.center_off[i + 1]
+        assert np.array_equal(m.center_xy[a:b], pm.center[i, :b - a])
+        assert np.array_equal(m.left_xy[m.left_off[i]:m.left_off[i + 1]], pm.left[i, :pm.n_left[i]])
+    assert np.array_equal(m.is_loop, pm.is_loop)
+
+
+@pytest.mark.parametrize("mode,rew", [("params", "distance"), ("kwargs", "ttc_sparse"), ("params", "sparse")])
+@pytest.mark.parametrize("st", ["cpm_entire", "intersection_1"])
+def test_config_lowering_matches_oracle_constants(st, mode, rew):
+    """Two independent restatements of road_traffic.py:_init_params must produce identical fp32 constants."""
+    from oracle import oracle as O
+    from sigmarl_b200 import EnvConfig, MapLibrary, lib
+    m, pm = MapLibrary(st), O.PaddedMap(st)
+    N = 4
+    c = EnvConfig(scenario_type=st, n_agents=N, mode=mode, rew_method=rew).lower(m)
+    o = O.make_cfg(st, pm, O.default_config(st, pm, N, mode=mode, rew_method=rew))
+    pairs = dict(dt="dt", max_speed="max_speed", max_steering="max_steering", max_acc="max_acc",
+                 max_steering_rate="max_steering_rate", l_wb="l_wb", lr_over_lwb="lr_over_lwb",
+                 half_length="half_length", half_width="half_width", diag="diag", w_ref0="w_ref0", w_ref1="w_ref1",
+                 w_ref2="w_ref2", speed_dt="speed_dt", reward_progress="reward_progress",
+                 near_boundary_low="nb_low", near_boundary_high="nb_high", near_agents_low="na_low",
+                 near_agents_high="na_high", ttc_low="ttc_low", ttc_high="ttc_high",
+                 penalty_near_boundary="pen_near_boundary", penalty_near_agents="pen_near_agents",
+                 penalty_collide_agents="pen_collide_agents", penalty_collide_lane="pen_collide_lane",
+                 norm_pos="norm_pos", norm_v="norm_v", norm_rot="norm_rot", norm_dist="norm_dist",
+                 dsafe_sq="dsafe_sq", reset_min_dist_sq="reset_min_dist_sq")
+    for a, b in pairs.items():
+        assert getattr(c, a) == getattr(o, b), (a, getattr(c, a), getattr(o, b))
+    assert c.k_near == o.k_near and c.max_steps == o.max_steps
+    assert bool(c.rew_flags & lib.SGB_REW_TTC) == bool(o.rew_has_ttc)
+    assert bool(c.rew_flags & lib.SGB_REW_DISTANCE) == bool(o.rew_has_distance)
+    assert bool(c.rew_flags & lib.SGB_REW_SPARSE) == bool(o.rew_has_sparse)
+    assert bool(c.rew_flags & lib.SGB_REW_EXACT_SPARSE) == bool(o.rew_exact_sparse)
+    assert bool(c.respawn_on_exit) == (not o.is_cpm_entire)
+
+
+def test_config_matches_reference_constants_in_goldens():
+    """...and both agree with what the reference run itself reported (cfg_* entries of the goldens)."""
+    import glob
+    from sigmarl_b200 import EnvConfig, MapLibrary
+    for p in sorted(glob.glob(os.path.join(REPO, "tests", "golden", "*.npz"))):
+        g = np.load(p)
+        st, mode = str(g["cfg_scenario_type"]), str(g["cfg_mode"])
+        extra = {}
+        if "ttc_sparse" in p and "cpm_mixed" in p:
+            extra["threshold_near_other_agents_c2c_low"] = 0.1635
+        c = EnvConfig(scenario_type=st, n_agents=int(g["cfg_N"]), mode=mode, rew_method=str(g["cfg_rew_method"]),
+                      n_nearing_agents_observed=int(g["cfg_n_nearing_agents_observed"]), **extra).lower(MapLibrary(st))
+        f32 = lambda k: float(np.float32(g[k]))  # noqa: E731
+        assert c.dt == f32("cfg_dt") and c.reward_progress == f32("cfg_reward_progress"), p
+        assert c.near_boundary_high == f32("cfg_near_boundary_high") and c.near_agents_low == f32("cfg_near_other_agents_low"), p
+        assert c.near_agents_high == f32("cfg_near_other_agents_high") and c.ttc_high == f32("cfg_ttc_high"), p
+        assert c.penalty_near_boundary == f32("cfg_penalty_near_boundary"), p
+        assert c.norm_pos == f32("cfg_norm_pos") and c.norm_dist == f32("cfg_norm_distance_lanelet"), p
+        assert c.k_near == int(g["cfg_n_nearing_agents_observed"]), p
+
+
+def test_unsupported_flags_fail_loudly():
+    from sigmarl_b200 import EnvConfig, MapLibrary
+    m = MapLibrary("cpm_entire")
+    for kw in (dict(is_use_mtv_distance=True), dict(is_testing_mode=True), dict(rew_method="cbf"), dict(is_obs_noise=True)):
+        with pytest.raises(NotImplementedError):
+            EnvConfig(scenario_type="cpm_entire", **kw).lower(m)
+    with pytest.raises(ValueError):
+        MapLibrary("no_such_map")

@@ -1,0 +1,310 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C-ABI (ctypes), against
+  (1) golden vectors from the unmodified reference (tests/golden, teacher-forced),
+  (2) the CPU oracle on seeded random states at sizes the oracle finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances (BASELINE.json north_star): 1e-5 abs for fp32 state / obs / reward, bit-exact masks & indices.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_files
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+UR = np.asarray([1.0, 31 * np.pi / 180], np.float32)
+
+
+def _env_from_golden(g, B=None, **over):
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    cfg = EnvConfig(
+        scenario_type=str(g["cfg_scenario_type"]), n_agents=int(g["cfg_N"]), mode=str(g["cfg_mode"]),
+        dt=float(g["cfg_dt"]), max_steps=int(g["cfg_max_steps"]), rew_method=str(g["cfg_rew_method"]),
+        n_nearing_agents_observed=int(g["cfg_n_nearing_agents_observed"]),
+        reward_progress=float(g["cfg_reward_progress"]),
+        threshold_near_boundary_high=float(g["cfg_near_boundary_high"]),
+        threshold_near_boundary_low=float(g["cfg_near_boundary_low"]),
+        threshold_near_other_agents_c2c_high=float(g["cfg_near_other_agents_high"]),
+        threshold_near_other_agents_c2c_low=float(g["cfg_near_other_agents_low"]),
+        ttc_low=float(g["cfg_ttc_low"]), ttc_high=float(g["cfg_ttc_high"]),
+        penalty_near_boundary=float(g["cfg_penalty_near_boundary"]),
+        penalty_near_other_agents=float(g["cfg_penalty_near_other_agents"]), **over)
+    return RoadTrafficEnv(cfg, num_envs=B or int(g["cfg_B"]), device="cuda:0", debug=True)
+
+
+def _coll_matrix(env):
+    cw = env.collide_with.cpu().numpy().astype(np.uint32)
+    N = env.N
+    return ((cw[..., None] >> np.arange(N, dtype=np.uint32)) & 1).astype(bool)
+
+
+def _close(name, got, want, ctx):
+    err = float(np.max(np.abs(np.asarray(got, np.float64) - np.asarray(want, np.float64)))) if np.size(got) else 0.0
+    assert err <= TOL, f"{ctx} {name}: max abs err {err:.3e}"
+    return err
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+@pytest.mark.parametrize("exhaustive", [False, True], ids=["pruned", "exhaustive"])
+def test_cuda_matches_reference_goldens(path, exhaustive):
+    g = np.load(path)
+    env = _env_from_golden(g, exhaustive=exhaustive)
+    assert env.D == g["obs"].shape[-1]
+    assert env.map.max_ref_path_points == int(g["cfg_max_ref_path_points"])
+    T, N = int(g["cfg_T"]), env.N
+    for t in range(T):
+        ctx = f"{os.path.basename(path)} t={t}"
+        gp = env.map.global_path(g["pre_scenario_id"][t], g["pre_path_id"][t])
+        env.set_state(g["pre_pos"][t], g["pre_rot"][t], g["pre_speed"][t], g["pre_steering"][t], gp,
+                      step_count=g["pre_step"][t])
+        obs, rew, done = env.step(torch.as_tensor(g["action"][t]).cuda())
+        torch.cuda.synchronize()
+        _close("pos", env.pos.cpu(), g["post_pos"][t], ctx)
+        _close("rot", env.rot.cpu(), g["post_rot"][t], ctx)
+        _close("speed", env.speed.cpu(), g["post_speed"][t], ctx)
+        _close("steering", env.steering.cpu(), g["post_steering"][t], ctx)
+        _close("vel", env.vel.cpu(), g["post_vel"][t], ctx)
+        _close("sideslip", env.sideslip_angle.cpu(), g["post_sideslip"][t], ctx)
+        _close("obs", obs.cpu(), g["obs"][t], ctx)
+        _close("reward", rew.cpu(), g["reward"][t], ctx)
+        dbg = env.dbg.cpu().numpy()
+        _close("d_ref", dbg[..., 0], g["d_ref"][t], ctx)
+        _close("d_left_cg", dbg[..., 2], g["d_left"][t][..., 0], ctx)
+        _close("d_right_cg", dbg[..., 7], g["d_right"][t][..., 0], ctx)
+        if N > 1:  # agent 0's stored vertex distances are one step stale in the reference
+            _close("d_left_v", dbg[:, 1:, 3:7], g["d_left"][t][:, 1:, 1:], ctx)
+            _close("d_right_v", dbg[:, 1:, 8:12], g["d_right"][t][:, 1:, 1:], ctx)
+        _close("d_bound", dbg[..., 12], g["d_bound"][t], ctx)
+        assert np.array_equal(dbg[..., 1].view(np.int32), g["idx_ref"][t]), f"{ctx} idx_ref"
+        fl = env.agent_flags.cpu().numpy()
+        assert np.array_equal(done.cpu().numpy().astype(bool), g["done"][t]), f"{ctx} done"
+        assert np.array_equal((fl & 2) != 0, g["col_lane"][t]), f"{ctx} col_lane"
+        assert np.array_equal((fl & 4) != 0, g["col_entry"][t]), f"{ctx} col_entry"
+        assert np.array_equal((fl & 8) != 0, g["col_exit"][t]), f"{ctx} col_exit"
+        assert np.array_equal(_coll_matrix(env), g["col_agents"][t]), f"{ctx} col_agents"
+        assert np.array_equal((fl & 1) != 0, g["col_agents"][t].any(-1)), f"{ctx} any col_agents"
+        # respawn requests = entry/exit crossers of not-done envs (road_traffic.py:1462-1472)
+        req = ((fl & 12) != 0) & ~g["done"][t][:, None] & (str(g["cfg_scenario_type"]) != "cpm_entire")
+        assert np.array_equal(req, g["respawn_mask"][t]), f"{ctx} respawn"
+        assert np.array_equal(env.step_count.cpu().numpy(), g["pre_step"][t] + 1), f"{ctx} step_count"
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_reset_obs_matches_reference(path):
+    """place + refresh(write_obs) reproduces the reference's post-reset state and its all-fresh observation."""
+    g = np.load(path)
+    env = _env_from_golden(g)
+    n = 0
+    for t in range(int(g["cfg_T"])):
+        m = g["reset_mask"][t]
+        if not m.any():
+            continue
+        gp = env.map.global_path(g["reset_scenario_id"][t], g["reset_path_id"][t])
+        amask = np.repeat(m[:, None], env.N, axis=1)
+        env.place(gp, g["reset_point_id"][t], g["reset_speed"][t], agent_mask=amask)
+        obs = env.refresh(env_mask=torch.as_tensor(m), write_obs=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(env.pos.cpu().numpy()[m], g["reset_pos"][t][m])
+        assert np.array_equal(env.rot.cpu().numpy()[m], g["reset_rot"][t][m])
+        _close("reset_vel", env.vel.cpu().numpy()[m], g["reset_vel"][t][m], f"t={t}")
+        _close("reset_obs", obs.cpu().numpy()[m], g["reset_obs"][t][m], f"{os.path.basename(path)} t={t}")
+        n += int(m.sum())
+    assert n > 0
+
+
+def _oracle_for(env, O, rew_method, mode):
+    return O.OracleWorld(env.config.scenario_type, env.B, env.N, mode=mode, rew_method=rew_method,
+                         n_nearing_agents_observed=env.config.n_nearing_agents_observed,
+                         max_steps=env.config.max_steps)
+
+
+@pytest.mark.parametrize("scenario,N,rew,mode,B", [
+    ("cpm_entire", 8, "distance", "params", 1024),
+    ("cpm_entire", 8, "ttc_sparse", "kwargs", 512),
+    ("cpm_mixed", 8, "distance_sparse", "params", 512),
+    ("intersection_1", 2, "distance", "kwargs", 256),
+    ("on_ramp_2_multilane", 12, "ttc", "kwargs", 256),
+    ("roundabout_2", 12, "sparse", "params", 256),
+])
+def test_cuda_matches_oracle_free_running_with_device_resets(oracle_mod, scenario, N, rew, mode, B):
+    """GPU drives (device resets included); every step the oracle is teacher-forced from the GPU's pre-step state."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    O = oracle_mod
+    env = RoadTrafficEnv(EnvConfig(scenario_type=scenario, n_agents=N, mode=mode, rew_method=rew),
+                         num_envs=B, device="cuda:0", seed=7, debug=True)
+    w = _oracle_for(env, O, rew, mode)
+    env.reset()
+    rng = np.random.default_rng(0)
+    n_done = n_lane = n_a2a = 0
+    for t in range(30):
+        torch.cuda.synchronize()
+        assert int(env.n_failed.item()) == 0
+        w.set_state(env.pos.cpu().numpy(), env.rot.cpu().numpy(), env.speed.cpu().numpy(),
+                    env.steering.cpu().numpy(), env.path_id.cpu().numpy())
+        w.step_count[:] = env.step_count.cpu().numpy()
+        # the carried (stale) values on the GPU come from its own history, the oracle's from a refresh
+        if t % 3 == 0:
+            act = ((rng.random((B, N, 2), np.float32) * 2 - 1) * UR).astype(np.float32)
+        else:  # gentler actions: longer episodes, more agent-agent encounters
+            act = np.stack([0.3 + 0.5 * rng.random((B, N), np.float32),
+                            (rng.random((B, N), np.float32) * 2 - 1) * 0.15], -1).astype(np.float32)
+        obs, rew_, done = env.step(torch.as_tensor(act).cuda())
+        o_obs, o_rew, o_done, o_resp = w.step(act, n_threads=8)
+        torch.cuda.synchronize()
+        ctx = f"{scenario} t={t}"
+        _close("pos", env.pos.cpu(), w.pos, ctx)
+        _close("rot", env.rot.cpu(), w.rot, ctx)
+        _close("vel", env.vel.cpu(), w.vel, ctx)
+        _close("obs", obs.cpu(), o_obs, ctx)
+        _close("reward", rew_.cpu(), o_rew, ctx)
+        fl = env.agent_flags.cpu().numpy()
+        assert np.array_equal(done.cpu().numpy().astype(bool), o_done), f"{ctx} done"
+        assert np.array_equal((fl & 2) != 0, w.col_lane.astype(bool)), f"{ctx} col_lane"
+        assert np.array_equal(_coll_matrix(env), w.col_agents.astype(bool)), f"{ctx} col_agents"
+        assert np.array_equal((fl & 4) != 0, w.col_entry.astype(bool)), f"{ctx} col_entry"
+        assert np.array_equal((fl & 8) != 0, w.col_exit.astype(bool)), f"{ctx} col_exit"
+        assert np.array_equal(env.dbg.cpu().numpy()[..., 1].view(np.int32), w.idx_ref), f"{ctx} idx_ref"
+        n_done += int(o_done.sum()); n_lane += int(w.col_lane.sum()); n_a2a += int(w.col_agents.sum())
+        env.reset_done()
+    assert n_done > 0 and n_lane > 0
+
+
+def test_pruned_equals_exhaustive_bitwise_at_c2_size():
+    """BASELINE configs[1] size (B=8192, N=8): the pruned search must not change a single bit."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    B, N = 8192, 8
+    envs = [RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=N, rew_method="ttc_sparse",
+                                     threshold_near_other_agents_c2c_low=0.1635, exhaustive=ex),
+                           num_envs=B, device="cuda:0", seed=11, debug=True) for ex in (False, True)]
+    for e in envs:
+        e.reset()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ur = torch.as_tensor(UR).cuda()
+    for t in range(12):
+        act = (torch.rand(B, N, 2, device="cuda", generator=g) * 2 - 1) * ur
+        if t % 2:
+            act[..., 0] = act[..., 0].abs() * 0.6 + 0.2
+            act[..., 1] *= 0.2
+        for e in envs:
+            e.step(act)
+        for name in ("pose", "aux", "carry", "obs", "reward", "done", "agent_flags", "collide_with", "step_count", "dbg"):
+            a, b = getattr(envs[0], name), getattr(envs[1], name)
+            assert torch.equal(a, b), f"t={t} {name} differs between pruned and exhaustive search"
+        for e in envs:
+            e.reset_done()
+        assert torch.equal(envs[0].pose, envs[1].pose)
+
+
+def test_properties_at_full_size_and_sharding_invariance():
+    """BASELINE configs[2] size (B=65536, N=8): invariants + env-sharded run == unsharded run, bit for bit."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    B, N = 65536, 8
+    cfg = EnvConfig(scenario_type="cpm_entire", n_agents=N, rew_method="distance")
+    full = RoadTrafficEnv(cfg, num_envs=B, device="cuda:0", seed=5)
+    halves = [RoadTrafficEnv(cfg, num_envs=B // 2, device="cuda:0", seed=5, env_offset=k * (B // 2)) for k in range(2)]
+    full.reset()
+    for h in halves:
+        h.reset()
+    # reset invariants (world_state_rt_sim.py:215-311)
+    pos = full.pos
+    d = (pos[:, :, None, :] - pos[:, None, :, :]).norm(dim=-1) + torch.eye(N, device="cuda") * 10
+    assert float(d.min()) >= 0.3669, "agents spawned closer than reset_agent_min_distance"
+    assert int(full.n_failed.item()) == 0 and int(full.step_count.abs().sum()) == 0
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ur = torch.as_tensor(UR).cuda()
+    dones = 0
+    for t in range(10):
+        act = (torch.rand(B, N, 2, device="cuda", generator=g) * 2 - 1) * ur
+        obs, rew, done = full.step(act)
+        for k, h in enumerate(halves):
+            h.step(act[k * (B // 2):(k + 1) * (B // 2)])
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert float(rew.min()) >= -1.0 and float(rew.max()) <= 1.0
+        fl = full.agent_flags
+        cw = full.collide_with
+        # collision symmetry: bit j of agent i == bit i of agent j (world_state_rt_sim.py:389-393)
+        m = ((cw.unsqueeze(-1) >> torch.arange(N, device="cuda", dtype=torch.int32)) & 1).bool()
+        assert torch.equal(m, m.transpose(1, 2)) and not m.diagonal(dim1=1, dim2=2).any()
+        assert torch.equal((fl & 1) != 0, m.any(-1))
+        want_done = ((fl & 3) != 0).any(dim=1) | (full.step_count == cfg.max_steps - 1)
+        assert torch.equal(done.bool(), want_done)
+        for name in ("pose", "aux", "obs", "reward", "done", "agent_flags", "carry"):
+            cat = torch.cat([getattr(h, name) for h in halves], dim=0)
+            assert torch.equal(cat, getattr(full, name)), f"t={t} sharded {name} != unsharded"
+        dones += int(done.sum())
+        full.reset_done()
+        for h in halves:
+            h.reset_done()
+        assert torch.equal(torch.cat([h.pose for h in halves], 0), full.pose), "sharded reset != unsharded reset"
+    assert dones > 0
+
+
+def test_step_is_idempotent_under_refresh():
+    """Rebuilding the carried values from the pose (sgb_refresh) must reproduce what the step itself carried."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    env = RoadTrafficEnv(EnvConfig(scenario_type="cpm_mixed", n_agents=6, rew_method="distance"), num_envs=2048,
+                         device="cuda:0", seed=2)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for t in range(6):
+        act = torch.stack([torch.rand(env.B, env.N, device="cuda", generator=g) * 0.7,
+                           (torch.rand(env.B, env.N, device="cuda", generator=g) - 0.5) * 0.3], -1)
+        env.step(act)
+        carried = env.carry.clone()
+        aux = env.aux.clone()
+        env.refresh()
+        assert torch.equal(carried, env.carry)
+        assert torch.equal(aux, env.aux)
+        env.reset_done()
+
+
+def test_vmas_facade_drives_the_same_kernel():
+    """The BaseScenario-shaped facade (make_world / world.step / reward / observation / done / reset_world_at)."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv, make_env
+    env = make_env(scenario_type="cpm_mixed", num_envs=64, device="cuda:0", n_agents=4, seed=3, max_steps=128)
+    sc = env.scenario
+    ref = RoadTrafficEnv(EnvConfig(scenario_type="cpm_mixed", n_agents=4, mode="kwargs"), num_envs=64, device="cuda:0", seed=3)
+    ref.reset()
+    assert torch.equal(ref.pose, sc.env.pose)
+    assert sc.world.agents[0].state.pos.shape == (64, 2) and sc.world.agents[0].state.rot.shape == (64, 1)
+    assert sc.world.agents[0].dynamics.needed_action_size == 2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(5):
+        acts = [torch.stack([torch.rand(64, device="cuda", generator=g) * 0.8,
+                             (torch.rand(64, device="cuda", generator=g) - 0.5) * 0.4], -1) for _ in range(4)]
+        obs, rews, dones, infos = env.step(acts)
+        r_obs, r_rew, r_done = ref.step(torch.stack(acts, 1))
+        assert torch.equal(torch.stack(obs, 1), r_obs) and torch.equal(torch.stack(rews, 1), r_rew)
+        assert torch.equal(dones, r_done.bool())
+        assert infos[0]["pos"].shape == (64, 2)
+        for e in torch.where(dones)[0].tolist():
+            env.reset_at(e)
+        ref.reset_done()
+        # both paths reset the same envs; positions of non-reset envs must agree exactly
+        keep = ~dones
+        touched = ((ref.agent_flags & 12) != 0).any(1)
+        assert torch.equal(sc.env.pose[keep & ~touched], ref.pose[keep & ~touched])
+        ref.pose.copy_(sc.env.pose); ref.aux.copy_(sc.env.aux); ref.path_id.copy_(sc.env.path_id)
+        ref.carry.copy_(sc.env.carry); ref.step_count.copy_(sc.env.step_count)
+
+
+def test_host_buffer_step_matches_device_step():
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    a = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=512, device="cuda:0", seed=4)
+    b = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=512, device="cuda:0", seed=4)
+    a.reset(); b.reset()
+    act = ((torch.rand(512, 8, 2) * 2 - 1) * torch.as_tensor(UR)).contiguous().pin_memory()
+    h_obs, h_rew, h_done = a.step_host(act)
+    obs, rew, done = b.step(act.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(h_obs, obs.cpu()) and torch.equal(h_rew, rew.cpu()) and torch.equal(h_done, done.cpu())
+
+
+def test_library_refuses_bad_arguments():
+    import ctypes as C
+    from sigmarl_b200 import lib
+    L = lib.load_library()
+    assert L.sgb_step(None, 1, 1, None, None) == -1
+    assert L.sgb_version() == 100
