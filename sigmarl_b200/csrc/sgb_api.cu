@@ -16,8 +16,9 @@ struct sgb_ctx {
     sgb_config cfg{};
     unsigned char* d_blob = nullptr;
     float* d_yaw = nullptr;          // yaw per centre point, indexed like the blob's centre points
-    uint8_t* d_touched = nullptr;    // [cap] scratch mask for reset -> refresh
-    int32_t touched_cap = 0;
+    int32_t* d_list = nullptr;       // [cap] compacted env indices for a masked refresh
+    int32_t* d_count = nullptr;      // number of entries of d_list
+    int32_t list_cap = 0;
     int32_t blob_bytes = 0;
     int32_t n_paths = 0;
     int32_t max_center = 0;
@@ -101,6 +102,7 @@ int pack_map(const sgb_map_desc* m, Packed& out) {
         const float* l = m->left_xy + 2 * (size_t)m->left_off[i];
         const float* rr = m->right_xy + 2 * (size_t)m->right_off[i];
         if (nc < 8 || degenerate(c, nc) || degenerate(l, nl) || degenerate(rr, nr)) return SGB_ERR_MAP;
+        if (std::max(nc, std::max(nl, nr)) - 1 > 32 * kChunk) return SGB_ERR_MAP; // candidate-chunk masks are 32-bit
         out.max_center = std::max(out.max_center, nc);
         r.is_loop = m->is_loop[i] ? 1 : 0;
         r.c_off = (int)(pts.size() / 2);
@@ -172,6 +174,16 @@ int pick_group(int N) {
     return 2;               // up to 32 agents per env
 }
 
+int ensure_list(sgb_ctx* c, int B) {
+    if (c->list_cap >= B) return SGB_OK;
+    cudaFree(c->d_list);
+    c->d_list = nullptr;
+    CK(cudaMalloc(&c->d_list, sizeof(int32_t) * (size_t)B));
+    if (!c->d_count) CK(cudaMalloc(&c->d_count, sizeof(int32_t)));
+    c->list_cap = B;
+    return SGB_OK;
+}
+
 template <int G>
 int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int slots = kThreads / G;
@@ -196,13 +208,14 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     return SGB_OK;
 }
 
-int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, const uint8_t* env_mask, int write_obs,
-               cudaStream_t st) {
+int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, const int32_t* env_list,
+               const int32_t* env_count, int write_obs, cudaStream_t st) {
     Params p{};
     p.cfg = ctx->cfg;
     p.buf = *buf;
     p.blob = ctx->d_blob;
-    p.env_mask = env_mask;
+    p.env_list = env_list;
+    p.env_count = env_count;
     p.B = B; p.N = N; p.D = 10 + 11 * ctx->cfg.k_near;
     p.blob_bytes = ctx->blob_bytes;
     p.mode = mode;
@@ -258,7 +271,8 @@ extern "C" int sgb_destroy(sgb_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_blob);
     cudaFree(c->d_yaw);
-    cudaFree(c->d_touched);
+    cudaFree(c->d_list);
+    cudaFree(c->d_count);
     delete c;
     return SGB_OK;
 }
@@ -272,7 +286,7 @@ extern "C" int sgb_step(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf
     if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || c->cfg.k_near > N - 1) return SGB_ERR_ARG;
     int rc = check_buffers(buf, 1);
     if (rc) return rc;
-    return launch_env(c, B, N, buf, 0, nullptr, 1, (cudaStream_t)stream);
+    return launch_env(c, B, N, buf, 0, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
 
 extern "C" int sgb_refresh(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* env_mask,
@@ -281,7 +295,15 @@ extern "C" int sgb_refresh(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* 
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
     if (write_obs && !buf->obs) return SGB_ERR_ARG;
-    return launch_env(c, B, N, buf, 1, env_mask, write_obs, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!env_mask) return launch_env(c, B, N, buf, 1, nullptr, nullptr, write_obs, st);
+    rc = ensure_list(c, B);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->d_count, 0, sizeof(int32_t), st));
+    mask_to_list_kernel<<<(B + 255) / 256, 256, 0, st>>>(env_mask, B, c->d_list, c->d_count);
+    c->launches++;
+    CK(cudaGetLastError());
+    return launch_env(c, B, N, buf, 1, c->d_list, c->d_count, write_obs, st);
 }
 
 extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* agent_mask,
@@ -308,20 +330,17 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
     if (!buf->step_count || (!all && !buf->done)) return SGB_ERR_ARG;
-    if (c->touched_cap < B) {
-        cudaFree(c->d_touched);
-        c->d_touched = nullptr;
-        CK(cudaMalloc(&c->d_touched, (size_t)B));
-        c->touched_cap = B;
-    }
+    rc = ensure_list(c, B);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(c->d_count, 0, sizeof(int32_t), st));
     ResetParams p{};
-    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.touched = c->d_touched;
+    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.list = c->d_list; p.count = c->d_count;
     p.n_failed = n_failed; p.seed = seed; p.epoch = epoch; p.env_offset = env_offset;
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
     reset_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
     c->launches++;
     CK(cudaGetLastError());
-    return launch_env(c, B, N, buf, 1, c->d_touched, write_obs, st);
+    return launch_env(c, B, N, buf, 1, c->d_list, c->d_count, write_obs, st);
 }
 
 extern "C" int sgb_reset(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,

@@ -25,7 +25,7 @@
 
 namespace sgb {
 
-constexpr int kThreads = 256;        // threads per CTA
+constexpr int kThreads = 512;        // threads per CTA (16 warps; 128 regs/thread fill the register file)
 constexpr int kChunk = 8;            // polyline segments per bounding-box chunk
 constexpr int kExt = 6;              // extension points behind a centre line (3 short-term pts x interval 2)
 constexpr float kDistMargin = 1e-4f; // [m]  >> fp32 error of a point-segment distance (~3e-6)
@@ -53,7 +53,8 @@ struct Params {
     sgb_config cfg;
     sgb_buffers buf;
     const unsigned char* blob; // device copy of the packed map
-    const uint8_t* env_mask;   // refresh: which envs (NULL = all)
+    const int32_t* env_list;   // refresh: compacted list of env indices (NULL = all B envs, in order)
+    const int32_t* env_count;  // device pointer: number of entries of env_list
     int32_t B, N, D;
     int32_t envs_per_tile, n_tiles;
     int32_t blob_bytes;
@@ -104,16 +105,19 @@ __device__ __forceinline__ float dec_lin(float x, float x0, float x1) {
     return 1.0f - (x - x0) / (x1 - x0);
 }
 
-// running minimum of sqrt(q) with the reference's "first minimal index" rule; sqrt only on improvement
+// Running minimum of d = sqrt(q) with torch.min's "first minimal index" rule, for segments visited in ANY
+// order (the hint chunk is scanned first): a candidate wins if d is smaller, or equal with a smaller index.
+// sqrt is monotone, so min d = sqrt(min q); distinct q within ~1.2e-7 relative can round to the same d, hence
+// the exact (d, idx) comparison runs for every q <= qmin * (1 + 5e-7) and is skipped (no sqrt) otherwise.
 struct Best {
-    float q, d;
+    float qmin, qlim, d;
     int idx;
-    __device__ __forceinline__ void init() { q = __int_as_float(0x7f800000); d = q; idx = 0x7fffffff; }
+    __device__ __forceinline__ void init() { qmin = __int_as_float(0x7f800000); qlim = qmin; d = qmin; idx = 0x7fffffff; }
     __device__ __forceinline__ void upd(float qq, int s) {
-        if (qq < q) {
+        if (qq <= qlim) {
             float dd = sqrtf(qq);
-            if (dd < d) { d = dd; idx = s; }
-            q = qq;
+            if (dd < d || (dd == d && s < idx)) { d = dd; idx = s; }
+            if (qq < qmin) { qmin = qq; qlim = qq * 1.0000005f; }
         }
     }
 };
@@ -157,32 +161,54 @@ struct Rect {
     }
 };
 
-// interX of the rectangle (as L1) against ONE segment a->b of L2; exact predicate
+// interX of the rectangle (as L1) against ONE segment a->b of L2; exact predicate.  C2 first: when all four
+// vertices lie strictly on one side of (or on) the segment's line no edge can cross it, and the four C1 terms
+// are skipped (same values as the reference would compute, just not evaluated).
 __device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by) {
     float dx2 = bx - ax, dy2 = by - ay;
     float S2 = dx2 * ay - dy2 * ax;
     float g[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) g[i] = (r.vy[i] * dx2 - r.vx[i] * dy2) - S2;
+    bool c2[4];
+    bool any2 = false;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { c2[i] = (g[i] * g[(i + 1) & 3]) < 0.0f; any2 |= c2[i]; }
+    if (!any2) return false;
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         float fa = (r.dx[i] * ay - r.dy[i] * ax) - r.S[i];
         float fb = (r.dx[i] * by - r.dy[i] * bx) - r.S[i];
-        bool c1 = (fa * fb) < 0.0f;
-        bool c2 = (g[i] * g[(i + 1) & 3]) < 0.0f;
-        hit |= (c1 & c2);
+        hit |= (((fa * fb) < 0.0f) & c2[i]);
     }
     return hit;
 }
 
-// interX(L1 = rectangle lo, L2 = rectangle hi): 4 x 4 edge pairs
+// interX(L1 = rectangle lo, L2 = rectangle hi), 4 x 4 edge pairs.  C1 first: f_i at hi's four vertices; if no
+// edge line of lo separates two consecutive vertices of hi there is no crossing and C2 is not evaluated.
 __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx, const float* hy) {
+    uint32_t c1 = 0; // bit 4*i + j
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float f[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) f[j] = (lo.dx[i] * hy[j] - lo.dy[i] * hx[j]) - lo.S[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) c1 |= ((f[j] * f[(j + 1) & 3]) < 0.0f) ? (1u << (4 * i + j)) : 0u;
+    }
+    if (!c1) return false;
     bool hit = false;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        int jn = (j + 1) & 3;
-        hit |= rect_cross_seg_L1(lo, hx[j], hy[j], hx[jn], hy[jn]);
+        const int jn = (j + 1) & 3;
+        float dx2 = hx[jn] - hx[j], dy2 = hy[jn] - hy[j];
+        float S2 = dx2 * hy[j] - dy2 * hx[j];
+        float g[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) g[i] = (lo.vy[i] * dx2 - lo.vx[i] * dy2) - S2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) hit |= (((g[i] * g[(i + 1) & 3]) < 0.0f) & (((c1 >> (4 * i + j)) & 1u) != 0u));
     }
     return hit;
 }
@@ -235,6 +261,7 @@ struct TileSmem {
     float* obs;                 // [A][D]
     int* path;
     int* flags;
+    int* env;                   // global env index of the slot (-1: inactive)
 };
 
 __device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, int D, TileSmem& t) {
@@ -244,14 +271,21 @@ __device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, in
     t.vtx = f; f += 8 * A; t.car = f; f += 4 * A; t.sc = f; f += 8 * A;
     t.dij = f; f += A * N; t.obs = f; f += A * D;
     t.path = reinterpret_cast<int*>(f); f += A; t.flags = reinterpret_cast<int*>(f); f += A;
+    t.env = reinterpret_cast<int*>(f); f += A;
 }
 __host__ __device__ inline size_t tile_smem_bytes(int A, int N, int D) {
-    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 2) + (size_t)A * N + (size_t)A * D);
+    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 3) + (size_t)A * N + (size_t)A * D);
 }
 
 // ---- phase B building blocks ------------------------------------------------------------------------------
 
-// centre line: min distance + closest index from (px,py); lanes of the group split the work
+// Phase-B scans.  Per polyline: (0) the G lanes of the agent's group scan the hint chunk together, which gives
+// a tight upper bound; (1) the lanes split the chunk boxes and vote two bitmasks — chunks whose box could hold
+// a closer segment, chunks whose box is not sign-certified against the rectangle's edge lines; (2) the group
+// walks the set bits together, every lane taking segments lane, lane+G, ... of the chunk.  All lanes of a
+// group stay busy; only the number of candidate chunks differs between the groups of a warp.
+
+// centre line: min distance + closest index from (px,py)
 template <int G>
 __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_c,
                                             int hint_seg, bool exhaustive, float px, float py, int lane, float& d_out,
@@ -262,20 +296,24 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
     Best b;
     b.init();
-    {   // hint chunk, cooperatively
-        int s1 = min(c0 * kChunk + kChunk, nseg);
+    {
+        const int s1 = min(c0 * kChunk + kChunk, nseg);
         for (int s = c0 * kChunk + lane; s < s1; s += G) {
             float2 a = pts[s], e = pts[s + 1];
             float lx = e.x - a.x, ly = e.y - a.y;
             b.upd(seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py), s);
         }
     }
-    float thr = group_min<G>(b.d) + kDistMargin;
-    for (int c = lane; c < nch; c += G) {
-        if (c == c0) continue;
-        if (!exhaustive && box_lb(boxes[c], px, py) > thr) continue;
-        int s1 = min(c * kChunk + kChunk, nseg);
-        for (int s = c * kChunk; s < s1; s++) {
+    const float thr = group_min<G>(b.d) + kDistMargin;
+    uint32_t m = 0;
+    for (int c = lane; c < nch; c += G)
+        if (c != c0 && (exhaustive || !(box_lb(boxes[c], px, py) > thr))) m |= 1u << c;
+    m = group_or<G>(m);
+    while (m) {
+        const int c = __ffs(m) - 1;
+        m &= m - 1;
+        const int s1 = min(c * kChunk + kChunk, nseg);
+        for (int s = c * kChunk + lane; s < s1; s += G) {
             float2 a = pts[s], e = pts[s + 1];
             float lx = e.x - a.x, ly = e.y - a.y;
             b.upd(seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py), s);
@@ -285,9 +323,9 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
     float d = b.d;
     int idx = b.idx;
 #pragma unroll
-    for (int m = 1; m < G; m <<= 1) {
-        float od = __shfl_xor_sync(0xffffffffu, d, m);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, m);
+    for (int k = 1; k < G; k <<= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, d, k);
+        int oi = __shfl_xor_sync(0xffffffffu, idx, k);
         if (od < d || (od == d && oi < idx)) { d = od; idx = oi; }
     }
     d_out = d;
@@ -309,7 +347,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
     for (int v = 0; v < 4; v++) bv[v].init();
     bool hit = false;
     {
-        int s1 = min(c0 * kChunk + kChunk, nseg);
+        const int s1 = min(c0 * kChunk + kChunk, nseg);
         for (int s = c0 * kChunk + lane; s < s1; s += G) {
             float2 a = pts[s], e = pts[s + 1];
             float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
@@ -324,14 +362,22 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
 #pragma unroll
     for (int v = 0; v < 4; v++) gb = fmaxf(gb, group_min<G>(bv[v].d));
     const float thr = gb + rect_radius + kDistMargin; // lb(vertex) >= lb(centre) - rect_radius
+    uint32_t md = 0, mx = 0;
     for (int c = lane; c < nch; c += G) {
         if (c == c0) continue;
-        float4 bx = boxes[c];
-        bool do_dist = exhaustive || !(box_lb(bx, px, py) > thr);
-        bool do_x = exhaustive || !box_sign_definite(r, bx);
-        if (!(do_dist | do_x)) continue;
-        int s1 = min(c * kChunk + kChunk, nseg);
-        for (int s = c * kChunk; s < s1; s++) {
+        const float4 bx = boxes[c];
+        if (exhaustive || !(box_lb(bx, px, py) > thr)) md |= 1u << c;
+        if (exhaustive || !box_sign_definite(r, bx)) mx |= 1u << c;
+    }
+    md = group_or<G>(md);
+    mx = group_or<G>(mx);
+    uint32_t m = md | mx;
+    while (m) {
+        const int c = __ffs(m) - 1;
+        m &= m - 1;
+        const bool do_dist = (md >> c) & 1u, do_x = (mx >> c) & 1u;
+        const int s1 = min(c * kChunk + kChunk, nseg);
+        for (int s = c * kChunk + lane; s < s1; s += G) {
             float2 a = pts[s], e = pts[s + 1];
             if (do_dist) {
                 float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
@@ -368,6 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     const int N = p.N, D = p.D;
     const int A = p.envs_per_tile * N;      // agent slots in use per tile
     const sgb_config& cfg = p.cfg;
+    const bool step_mode = (p.mode == 0);
 
     // --- stage the map: one elected thread arms the mbarrier and issues the bulk copies -------------
     const uint32_t bar = smem_u32(&mbar);
@@ -376,6 +423,10 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // refresh over a compacted env list: the number of envs is only known on the device
+    const int n_envs = p.env_list ? *p.env_count : p.B;
+    const int n_tiles = (n_envs + p.envs_per_tile - 1) / p.envs_per_tile;
+    if ((int)blockIdx.x >= n_tiles) return;  // nothing to do for this CTA: do not even stage the map
     if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)p.blob_bytes);
         const uint32_t dst = smem_u32(smem);
@@ -395,17 +446,17 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     const int lane = tid % G;
     const float rect_radius = sqrtf(cfg.half_length * cfg.half_length + cfg.half_width * cfg.half_width) * 1.0001f;
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const int env0 = tile * p.envs_per_tile;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int env0 = tile * p.envs_per_tile;   // first env (or first list entry) of this tile
 
         // ================= phase A: one thread per agent ==========================================
         if (tid < A) {
-            const int e = env0 + tid / N;
+            const int ei = env0 + tid / N;
             const int i = tid % N;
-            bool active = e < p.B;
-            if (active && p.mode == 1 && p.env_mask && !p.env_mask[e]) active = false;
-            int flags0 = active ? 0 : -1; // -1 marks an inactive slot
+            const bool active = ei < n_envs;
+            int e = -1;
             if (active) {
+                e = p.env_list ? p.env_list[ei] : ei;
                 const size_t g = (size_t)e * N + i;
                 float4 pose = reinterpret_cast<const float4*>(p.buf.pose)[g];
                 float delta = p.buf.aux[4 * g];
@@ -413,8 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 float x = pose.x, y = pose.y, psi = pose.z, v = pose.w;
                 ts.ox[tid] = x;
                 ts.oy[tid] = y;
-                float beta1;
-                if (p.mode == 0) {
+                if (step_mode) {
                     // helper_training.py:807-836
                     float2 u = reinterpret_cast<const float2*>(p.buf.action)[g];
                     u.x = clampf(u.x, -cfg.max_speed, cfg.max_speed);
@@ -437,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     const float pi_f = 3.14159274101257324f, two_pi = 6.28318548202514648f;
                     delta = pymod(delta + pi_f, two_pi) - pi_f; // dynamics.py:158
                 }
-                beta1 = atanf(cfg.lr_over_lwb * tanf(delta));   // dynamics.py:161-163
+                const float beta1 = atanf(cfg.lr_over_lwb * tanf(delta));   // dynamics.py:161-163
                 float sc_, cc_;
                 sincosf(psi + beta1, &sc_, &cc_);
                 float vx = v * cc_, vy = v * sc_;
@@ -461,24 +511,26 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 ts.car[2 * AS + tid] = car.z; ts.car[3 * AS + tid] = car.w;
                 ts.path[tid] = p.buf.path_id[g];
             }
-            ts.flags[tid] = flags0;
+            ts.flags[tid] = active ? 0 : -1; // -1 marks an inactive slot
+            ts.env[tid] = e;
         }
         __syncthreads();
         if (!map_ready) { mbar_wait(bar, 0); map_ready = true; }
+
+        const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
+        const float2* pts = reinterpret_cast<const float2*>(smem + hdr->pts_off);
+        const float4* boxes = reinterpret_cast<const float4*>(smem + hdr->box_off);
 
         // ================= phase B: G lanes per agent, polyline queries out of the smem map =======
         const bool slot_ok = (slot_b < A) && (ts.flags[slot_b] >= 0);
         // all 32 lanes of a warp take part in the shuffles, so inactive slots of a live warp run on
         // dummy-safe data; a warp without any active slot skips phases B and C altogether
         const bool warp_live = __any_sync(0xffffffffu, slot_ok);
+        const int sl = slot_ok ? slot_b : 0;
+        int path = slot_ok ? ts.path[sl] : 0;
+        path = (path < 0 || path >= hdr->n_paths) ? 0 : path;
+        const PathRec pr = paths[path];
         if (warp_live) {
-            const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
-            const float2* pts = reinterpret_cast<const float2*>(smem + hdr->pts_off);
-            const float4* boxes = reinterpret_cast<const float4*>(smem + hdr->box_off);
-            const int sl = slot_ok ? slot_b : 0;
-            int path = slot_ok ? ts.path[sl] : 0;
-            path = (path < 0 || path >= hdr->n_paths) ? 0 : path;
-            const PathRec pr = paths[path];
             const float px = slot_ok ? ts.px[sl] : 0.0f, py = slot_ok ? ts.py[sl] : 0.0f;
             Rect r;
 #pragma unroll
@@ -488,8 +540,9 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             }
             r.finish();
             const bool ex = cfg.exhaustive != 0;
-            int hint = __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1; // last closest segment
-            if (p.mode == 1) hint = 0x3fffffff / kChunk;                          // no history: start at the far end
+            // hint = last closest segment (step) / the spawn point written by place_agent (refresh); any value
+            // is valid, a good one lets the first chunk scanned set a tight pruning bound
+            const int hint = __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1;
             float d_ref, dLc, dRc, dLv[4], dRv[4];
             int idx_ref;
             bool hitL, hitR;
@@ -518,10 +571,9 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 ts.sc[3 * AS + sl] = dRc;
                 ts.sc[4 * AS + sl] = m4L;
                 ts.sc[5 * AS + sl] = m4R;
-                ts.flags[sl] = (p.mode == 0) ? fl : 0;
+                ts.flags[sl] = step_mode ? fl : 0;
                 if (p.buf.dbg) {
-                    const int e = env0 + sl / N;
-                    float* dbg = p.buf.dbg + ((size_t)e * N + sl % N) * 16;
+                    float* dbg = p.buf.dbg + ((size_t)ts.env[sl] * N + sl % N) * 16;
                     dbg[0] = d_ref; dbg[1] = __int_as_float(idx_ref); dbg[2] = dLc; dbg[7] = dRc;
 #pragma unroll
                     for (int v = 0; v < 4; v++) { dbg[3 + v] = dLv[v]; dbg[8 + v] = dRv[v]; }
@@ -532,7 +584,6 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
 
         // ================= phase C: interactions inside the env, reward, observation ===============
         if (warp_live) {
-            const int sl = slot_ok ? slot_b : 0;
             const int i = sl % N;
             const int base = sl - i; // slot of agent 0 of this env
             const float pix = ts.px[sl], piy = ts.py[sl];
@@ -541,16 +592,18 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             for (int k = 0; k < 4; k++) { ri.vx[k] = ts.vtx[k * AS + sl]; ri.vy[k] = ts.vtx[(4 + k) * AS + sl]; }
             ri.finish();
             uint32_t coll = 0;
-            float ttc_sum = 0.0f;
-            const bool step_mode = (p.mode == 0);
+            float ttc_sum = 0.0f, near_sum = 0.0f;
+            // ---- C1: the lanes of the group split the other agents j ----
             if (slot_ok) {
                 for (int j = lane; j < N; j += G) {
                     const int sj = base + j;
-                    float dx = pix - ts.px[sj], dy = piy - ts.py[sj];
+                    const float pjx = ts.px[sj], pjy = ts.py[sj];
+                    float dx = pix - pjx, dy = piy - pjy;
                     float pp = dx * dx + dy * dy;
-                    float dist = sqrtf(pp);                       // helper_scenario.py:1012-1029
-                    ts.dij[sl * N + j] = (j == i) ? cfg.diag : dist;
+                    float dist = (j == i) ? cfg.diag : sqrtf(pp);  // helper_scenario.py:1012-1029, :1140-1143
+                    ts.dij[sl * N + j] = dist;
                     if (!step_mode) continue;
+                    near_sum += dec_lin(dist, cfg.near_agents_low, cfg.near_agents_high);
                     if (j != i) {
                         // world_state_rt_sim.py:384-393: interX(vertices[lo], vertices[hi]), lo < hi
                         float hx[4], hy[4];
@@ -571,7 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     if (cfg.rew_flags & SGB_REW_TTC) {
                         // road_traffic.py:1255-1332 (p_rel = p_j - p_i)
                         const float eps = 1e-6f;
-                        float rx = ts.px[sj] - pix, ry = ts.py[sj] - piy;
+                        float rx = pjx - pix, ry = pjy - piy;
                         float wx = ts.vx[sj] - ts.vx[sl], wy = ts.vy[sj] - ts.vy[sl];
                         float qa = wx * wx + wy * wy;
                         float qb = 2.0f * (rx * wx + ry * wy);
@@ -594,129 +647,147 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             }
             coll = group_or<G>(coll);
             ttc_sum = group_sum<G>(ttc_sum);
-            __syncwarp();
-            if (slot_ok && lane == 0) {
-                const int e = env0 + sl / N;
-                const size_t g = (size_t)e * N + i;
-                const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
-                const float2* pts = reinterpret_cast<const float2*>(smem + hdr->pts_off);
-                int path = ts.path[sl];
-                path = (path < 0 || path >= hdr->n_paths) ? 0 : path;
-                const PathRec pr = paths[path];
+            near_sum = group_sum<G>(near_sum);
+            __syncwarp(); // dij of this group is complete
+
+            // ---- C2: every lane of the group picks the k nearest (same result in all lanes), then the lanes
+            //          take roles: role 0 = own block of the observation, roles 1..k = one neighbour block each,
+            //          role k+1 = reward / flags / carry.  torch.topk(k, largest=False), ties -> lower index.
+            const int k_near = cfg.k_near;
+            int nb_j[2] = {0, 0};          // the first two neighbours stay in registers, the rest is re-derived
+            float nb_d[2] = {0.0f, 0.0f};
+            uint32_t used = 0;
+            if (slot_ok) {
+                for (int kk = 0; kk < k_near && kk < 2; kk++) {
+                    int bj = -1;
+                    float bd = __int_as_float(0x7f800000);
+                    for (int j = 0; j < N; j++) {
+                        float dj = ts.dij[sl * N + j];
+                        if (!((used >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
+                    }
+                    used |= 1u << bj;
+                    nb_j[kk] = bj; nb_d[kk] = bd;
+                }
+            }
+            if (slot_ok) {
+                const size_t g = (size_t)ts.env[sl] * N + i;
                 const float d_ref_n = ts.sc[0 * AS + sl];
                 const int idx_n = __float_as_int(ts.sc[1 * AS + sl]);
                 const float dLc = ts.sc[2 * AS + sl], dRc = ts.sc[3 * AS + sl];
                 const float m4L = ts.sc[4 * AS + sl], m4R = ts.sc[5 * AS + sl];
                 const float c_dref = ts.car[0 * AS + sl], c_mL = ts.car[1 * AS + sl], c_mR = ts.car[2 * AS + sl];
                 const int c_idx = __float_as_int(ts.car[3 * AS + sl]);
-                float2 st_new[3], st_old[3];
-                short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, idx_n, st_new);
-                // what agent i's reward and observation see:
-                float o_dref, o_mL, o_mR, d_bound;
-                const float2* o_st;
-                if (!step_mode) {               // right after a reset everything is fresh
-                    o_dref = d_ref_n; o_mL = fminf(dLc, m4L); o_mR = fminf(dRc, m4R); o_st = st_new;
-                    d_bound = fminf(o_mL, o_mR);
-                } else if (i == 0) {            // agent 0: fresh centre queries, vertex queries of the OLD rectangle
-                    o_dref = d_ref_n; o_mL = fminf(dLc, c_mL); o_mR = fminf(dRc, c_mR); o_st = st_new;
-                    d_bound = fminf(o_mL, o_mR);
-                } else {                        // agents >= 1: reward is fresh, observation is one step stale
-                    short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, c_idx, st_old);
-                    o_dref = c_dref; o_mL = c_mL; o_mR = c_mR; o_st = st_old;
-                    d_bound = fminf(fminf(dLc, m4L), fminf(dRc, m4R));
-                }
-                int fl = ts.flags[sl];
-                if (coll) fl |= (int)SGB_FLAG_COLLIDE_AGENT;
-                ts.flags[sl] = fl;
-
-                if (step_mode) {
-                    // ---- reward: road_traffic.py:947-1253 (short-term path of the PREVIOUS step) ----
-                    if (i == 0) short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, c_idx, st_old);
-                    const float oxp = ts.ox[sl], oyp = ts.oy[sl];
-                    float mvx = pix - oxp, mvy = piy - oyp;
-                    float acc = 0.0f;
+                const bool write_obs = step_mode || p.write_obs;
+                float* o = ts.obs + (size_t)sl * D;
+                const float cs = ts.cs[sl], sn = ts.sn[sl];
+                const int n_roles = k_near + 2;
+                for (int role = lane; role < n_roles; role += G) {
+                    if (role == 0) {
+                        if (!write_obs) continue;
+                        // ---- own block: observation_provider_rt.py:857-925.  What agent i's observation sees
+                        // (SURVEY.md A.2 / A.6): after a reset everything is fresh; in a step agent 0 sees fresh
+                        // centre queries + vertex queries of the OLD rectangle, agents >= 1 see last step's values.
+                        float o_dref, o_mL, o_mR;
+                        int o_idx;
+                        if (!step_mode) { o_dref = d_ref_n; o_mL = fminf(dLc, m4L); o_mR = fminf(dRc, m4R); o_idx = idx_n; }
+                        else if (i == 0) { o_dref = d_ref_n; o_mL = fminf(dLc, c_mL); o_mR = fminf(dRc, c_mR); o_idx = idx_n; }
+                        else { o_dref = c_dref; o_mL = c_mL; o_mR = c_mR; o_idx = c_idx; }
+                        float2 st[3];
+                        short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, o_idx, st);
+                        o[0] = ts.vabs[sl] / cfg.norm_v;
 #pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        float rx = st_old[k].x - oxp, ry = st_old[k].y - oyp;
-                        acc += (mvx * rx + mvy * ry) * cfg.w_ref[k];
-                    }
-                    float rew = 0.0f;
-                    rew += (acc / cfg.speed_dt) * cfg.reward_progress;
-                    const float pen_a2a = (coll ? 1.0f : 0.0f) * cfg.penalty_collide_agents;
-                    const float pen_lane = ((fl & SGB_FLAG_COLLIDE_LANE) ? 1.0f : 0.0f) * cfg.penalty_collide_lane;
-                    const float pen_nb = dec_lin(d_bound, cfg.near_boundary_low, cfg.near_boundary_high) * cfg.penalty_near_boundary;
-                    if (cfg.rew_flags & SGB_REW_EXACT_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                    if (cfg.rew_flags & SGB_REW_TTC) {
-                        float risk = ttc_sum / (float)(N - 1 > 1 ? N - 1 : 1);
-                        rew += risk * cfg.penalty_near_agents;
-                        rew += pen_nb;
-                        rew += pen_a2a; rew += pen_lane;
-                        if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                    }
-                    if (cfg.rew_flags & SGB_REW_DISTANCE) {
-                        float s = 0.0f;
-                        for (int j = 0; j < N; j++) s += dec_lin(ts.dij[sl * N + j], cfg.near_agents_low, cfg.near_agents_high);
-                        rew += s * cfg.penalty_near_agents;
-                        rew += pen_nb;
-                        if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                    }
-                    p.buf.reward[g] = clampf(rew, -1.0f, 1.0f);
-                    p.buf.agent_flags[g] = (uint8_t)fl;
-                    if (p.buf.collide_with) p.buf.collide_with[g] = coll;
-                } else {
-                    p.buf.agent_flags[g] = 0;
-                    if (p.buf.collide_with) p.buf.collide_with[g] = 0;
-                }
-                // ---- next step's carry ----
-                {
-                    float4 nc;
-                    nc.x = d_ref_n;
-                    nc.y = (i == 0) ? m4L : fminf(dLc, m4L);
-                    nc.z = (i == 0) ? m4R : fminf(dRc, m4R);
-                    nc.w = __int_as_float(idx_n);
-                    reinterpret_cast<float4*>(p.buf.carry)[g] = nc;
-                }
-                if (p.buf.dbg) p.buf.dbg[g * 16 + 12] = d_bound;
-
-                // ---- observation: observation_provider_rt.py:594-925 (ego view, default flags) ----
-                if (step_mode || p.write_obs) {
-                    float* o = ts.obs + (size_t)sl * D;
-                    const float cs = ts.cs[sl], sn = ts.sn[sl];
-                    int n = 0;
-                    o[n++] = ts.vabs[sl] / cfg.norm_v;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        float dx = o_st[k].x - pix, dy = o_st[k].y - piy;
-                        o[n++] = (dx * cs + dy * sn) / cfg.norm_pos;
-                        o[n++] = (dy * cs - dx * sn) / cfg.norm_pos;
-                    }
-                    o[n++] = o_dref / cfg.norm_dist;
-                    o[n++] = o_mL / cfg.norm_dist;
-                    o[n++] = o_mR / cfg.norm_dist;
-                    // torch.topk(k, largest=False) over distances.agents[i, :]
-                    uint32_t used = 0;
-                    for (int kk = 0; kk < cfg.k_near; kk++) {
-                        int bj = -1;
-                        float bd = __int_as_float(0x7f800000);
-                        for (int j = 0; j < N; j++) {
-                            float dj = ts.dij[sl * N + j];
-                            if (!((used >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
+                        for (int k = 0; k < 3; k++) {
+                            float dx = st[k].x - pix, dy = st[k].y - piy;
+                            o[1 + 2 * k] = (dx * cs + dy * sn) / cfg.norm_pos;
+                            o[2 + 2 * k] = (dy * cs - dx * sn) / cfg.norm_pos;
                         }
-                        used |= 1u << bj;
+                        o[7] = o_dref / cfg.norm_dist;
+                        o[8] = o_mL / cfg.norm_dist;
+                        o[9] = o_mR / cfg.norm_dist;
+                    } else if (role <= k_near) {
+                        if (!write_obs) continue;
+                        // ---- neighbour block kk: observation_provider_rt.py:622-855 ----
+                        const int kk = role - 1;
+                        int bj;
+                        float bd;
+                        if (kk < 2) { bj = nb_j[kk]; bd = nb_d[kk]; }
+                        else {      // k_near > 2: redo the selection up to rank kk
+                            uint32_t u2 = 0;
+                            bj = -1; bd = 0.0f;
+                            for (int q = 0; q <= kk; q++) {
+                                bj = -1; bd = __int_as_float(0x7f800000);
+                                for (int j = 0; j < N; j++) {
+                                    float dj = ts.dij[sl * N + j];
+                                    if (!((u2 >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
+                                }
+                                u2 |= 1u << bj;
+                            }
+                        }
                         const int sj = base + bj;
+                        float* ob = o + 10 + 11 * kk;
 #pragma unroll
                         for (int v = 0; v < 4; v++) {
                             float dx = ts.vtx[v * AS + sj] - pix, dy = ts.vtx[(4 + v) * AS + sj] - piy;
-                            o[n++] = (dx * cs + dy * sn) / cfg.norm_pos;
-                            o[n++] = (dy * cs - dx * sn) / cfg.norm_pos;
+                            ob[2 * v] = (dx * cs + dy * sn) / cfg.norm_pos;
+                            ob[2 * v + 1] = (dy * cs - dx * sn) / cfg.norm_pos;
                         }
                         // |v_j| * (cos, sin)(psi_j - psi_i) via the stored cos/sin of both headings
                         const float cj = ts.cs[sj], sj_ = ts.sn[sj];
-                        const float cr = cj * cs + sj_ * sn, sr = sj_ * cs - cj * sn;
-                        o[n++] = (ts.vabs[sj] * cr) / cfg.norm_v;
-                        o[n++] = (ts.vabs[sj] * sr) / cfg.norm_v;
-                        o[n++] = bd / cfg.norm_dist;
+                        ob[8] = (ts.vabs[sj] * (cj * cs + sj_ * sn)) / cfg.norm_v;
+                        ob[9] = (ts.vabs[sj] * (sj_ * cs - cj * sn)) / cfg.norm_v;
+                        ob[10] = bd / cfg.norm_dist;
                         if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
+                    } else {
+                        // ---- reward (road_traffic.py:947-1253), flags, next step's carry ----
+                        int fl = ts.flags[sl];
+                        if (coll) fl |= (int)SGB_FLAG_COLLIDE_AGENT;
+                        ts.flags[sl] = fl;
+                        float d_bound;
+                        if (!step_mode || i != 0) d_bound = fminf(fminf(dLc, m4L), fminf(dRc, m4R));
+                        else d_bound = fminf(fminf(dLc, c_mL), fminf(dRc, c_mR)); // agent 0: stale vertices
+                        if (step_mode) {
+                            float2 st_old[3];   // short-term path of the PREVIOUS step
+                            short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, c_idx, st_old);
+                            const float oxp = ts.ox[sl], oyp = ts.oy[sl];
+                            float mvx = pix - oxp, mvy = piy - oyp;
+                            float acc = 0.0f;
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                float rx = st_old[k].x - oxp, ry = st_old[k].y - oyp;
+                                acc += (mvx * rx + mvy * ry) * cfg.w_ref[k];
+                            }
+                            float rew = 0.0f;
+                            rew += (acc / cfg.speed_dt) * cfg.reward_progress;
+                            const float pen_a2a = (coll ? 1.0f : 0.0f) * cfg.penalty_collide_agents;
+                            const float pen_lane = ((fl & SGB_FLAG_COLLIDE_LANE) ? 1.0f : 0.0f) * cfg.penalty_collide_lane;
+                            const float pen_nb = dec_lin(d_bound, cfg.near_boundary_low, cfg.near_boundary_high) * cfg.penalty_near_boundary;
+                            if (cfg.rew_flags & SGB_REW_EXACT_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                            if (cfg.rew_flags & SGB_REW_TTC) {
+                                float risk = ttc_sum / (float)(N - 1 > 1 ? N - 1 : 1);
+                                rew += risk * cfg.penalty_near_agents;
+                                rew += pen_nb;
+                                rew += pen_a2a; rew += pen_lane;
+                                if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                            }
+                            if (cfg.rew_flags & SGB_REW_DISTANCE) {
+                                rew += near_sum * cfg.penalty_near_agents;
+                                rew += pen_nb;
+                                if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                            }
+                            p.buf.reward[g] = clampf(rew, -1.0f, 1.0f);
+                            p.buf.agent_flags[g] = (uint8_t)fl;
+                            if (p.buf.collide_with) p.buf.collide_with[g] = coll;
+                        } else {
+                            p.buf.agent_flags[g] = 0;
+                            if (p.buf.collide_with) p.buf.collide_with[g] = 0;
+                        }
+                        float4 nc;
+                        nc.x = d_ref_n;
+                        nc.y = (i == 0) ? m4L : fminf(dLc, m4L);
+                        nc.z = (i == 0) ? m4R : fminf(dRc, m4R);
+                        nc.w = __int_as_float(idx_n);
+                        reinterpret_cast<float4*>(p.buf.carry)[g] = nc;
+                        if (p.buf.dbg) p.buf.dbg[g * 16 + 12] = d_bound;
                     }
                 }
             }
@@ -724,8 +795,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         __syncthreads();
 
         // ================= phase D: per-env outputs + coalesced observation write-back ============
-        if (p.mode == 0 && tid < A && (tid % N) == 0 && ts.flags[tid] >= 0) {
-            const int e = env0 + tid / N;
+        if (step_mode && tid < A && (tid % N) == 0 && ts.flags[tid] >= 0) {
+            const int e = ts.env[tid];
             int any = 0;
             for (int j = 0; j < N; j++) any |= ts.flags[tid + j];
             const int step = p.buf.step_count[e] + 1;          // road_traffic.py:954-962
@@ -734,18 +805,19 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             const bool dn = (step == cfg.max_steps - 1) || (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE));
             p.buf.done[e] = dn ? 1 : 0;
         }
-        if (p.mode == 0 || p.write_obs) {
-            const int n_env = min(p.envs_per_tile, p.B - env0);
-            const int nf = n_env * N * D;                       // floats of this tile (contiguous in HBM)
-            float* dst = p.buf.obs + (size_t)env0 * N * D;
-            if (p.mode == 0 && ((nf & 3) == 0) && ((((size_t)env0 * N * D) & 3) == 0)) {
+        if (step_mode || p.write_obs) {
+            const int n_env_t = min(p.envs_per_tile, n_envs - env0);
+            const int nf = n_env_t * N * D;                     // floats of this tile
+            if (!p.env_list && ((nf & 3) == 0) && ((((size_t)env0 * N * D) & 3) == 0)) {
+                // envs of the tile are contiguous in HBM: one coalesced float4 stream
                 const float4* s4 = reinterpret_cast<const float4*>(ts.obs);
-                float4* d4 = reinterpret_cast<float4*>(dst);
+                float4* d4 = reinterpret_cast<float4*>(p.buf.obs + (size_t)env0 * N * D);
                 for (int k = tid; k < nf / 4; k += kThreads) d4[k] = s4[k];
             } else {
+                const int ND = N * D;
                 for (int k = tid; k < nf; k += kThreads) {
-                    const int slot = k / D;
-                    if (ts.flags[slot] >= 0) dst[k] = ts.obs[k];
+                    const int el = k / ND;                      // env of the tile
+                    p.buf.obs[(size_t)ts.env[el * N] * ND + (k - el * ND)] = ts.obs[k];
                 }
             }
         }
@@ -794,6 +866,7 @@ __device__ __forceinline__ void place_agent(const sgb_config& cfg, const sgb_buf
     float s, co;
     sincosf(0.0f + psi, &s, &co);
     reinterpret_cast<float4*>(buf.aux)[g] = make_float4(0.0f, speed * co, speed * s, 0.0f);
+    reinterpret_cast<float4*>(buf.carry)[g] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(point + 1)); // search hint
     buf.path_id[g] = path;
 }
 
@@ -809,7 +882,8 @@ struct ResetParams {
     sgb_buffers buf;
     const unsigned char* blob;
     const float* yaw;
-    uint8_t* touched;          // [B] out: env needs a refresh
+    int32_t* list;             // [B] out: compacted indices of the envs that need a refresh
+    int32_t* count;            // out: number of entries (zeroed by the host before the launch)
     int32_t* n_failed;
     uint64_t seed, epoch;
     int64_t env_offset;
@@ -824,10 +898,10 @@ __global__ void reset_kernel(const ResetParams p) {
     const bool full = p.all || p.buf.done[e];
     uint32_t respawn = 0;
     if (!full) {
-        if (!p.cfg.respawn_on_exit) { p.touched[e] = 0; return; }
+        if (!p.cfg.respawn_on_exit) return;
         for (int a = 0; a < N; a++)
             if (p.buf.agent_flags[(size_t)e * N + a] & (SGB_FLAG_ENTRY | SGB_FLAG_EXIT)) respawn |= 1u << a;
-        if (!respawn) { p.touched[e] = 0; return; }
+        if (!respawn) return;
     }
     const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(p.blob);
     const PathRec* paths = reinterpret_cast<const PathRec*>(p.blob + hdr->path_off);
@@ -869,8 +943,14 @@ __global__ void reset_kernel(const ResetParams p) {
         place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + a, path, point, u * p.cfg.max_speed);
     }
     if (full) p.buf.step_count[e] = 0; // road_traffic.py:875-877
-    p.touched[e] = full ? 2 : 1;
+    p.list[atomicAdd(p.count, 1)] = e;
     if (failed && p.n_failed) atomicAdd(p.n_failed, failed);
+}
+
+// byte mask -> compacted index list (order is irrelevant: envs are independent)
+__global__ void mask_to_list_kernel(const uint8_t* mask, int B, int32_t* list, int32_t* count) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < B && mask[e]) list[atomicAdd(count, 1)] = e;
 }
 
 } // namespace sgb

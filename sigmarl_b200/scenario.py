@@ -260,6 +260,8 @@ class VmasLikeEnvironment:
         self.scenario, self.num_envs, self.device, self.max_steps = scenario, num_envs, device, max_steps
         if seed is not None:
             kwargs["seed"] = seed
+        if max_steps is not None and not hasattr(scenario, "parameters"):
+            kwargs.setdefault("max_steps", max_steps)  # kwargs mode: the scenario's own time limit (road_traffic.py:1413)
         self.world = scenario.env_make_world(num_envs, device, **kwargs)
         self.agents = self.world.policy_agents
         self.n_agents = len(self.agents)
@@ -310,5 +312,4 @@ def make_env(scenario_type="cpm_entire", num_envs=32, device="cuda:0", max_steps
         sc.parameters = parameters
     else:
         kwargs.setdefault("scenario_type", scenario_type)
-    kwargs.setdefault("max_steps", max_steps)
     return VmasLikeEnvironment(sc, num_envs=num_envs, device=device, max_steps=max_steps, **kwargs)
