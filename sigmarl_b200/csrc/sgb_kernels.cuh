@@ -121,15 +121,18 @@ struct Best {
         }
     }
 };
-struct BestD { // distance only
-    float q, d;
-    __device__ __forceinline__ void init() { q = __int_as_float(0x7f800000); d = q; }
-    __device__ __forceinline__ void upd(float qq) {
-        if (qq < q) { d = fminf(d, sqrtf(qq)); q = qq; }
-    }
+// boundary distances feed only continuous outputs (observation / reward, 1e-5 tolerance), never an argmin
+// or a predicate, so they are tracked as min q = min d^2 and square-rooted once: min sqrt(q) == sqrt(min q).
+struct BestQ {
+    float q;
+    __device__ __forceinline__ void init() { q = __int_as_float(0x7f800000); }
+    __device__ __forceinline__ void upd(float qq) { q = fminf(q, qq); }
+    // conservative "a box at squared distance lb2 cannot improve on q": lb > sqrt(q) + 3e-6 is implied
+    __device__ __forceinline__ bool box_useless(float lb2) const { return lb2 > q * 1.01f + 1e-7f; }
 };
 
-// squared point-segment distance, operation order of helper_scenario.py:856-871
+// squared point-segment distance, operation order of helper_scenario.py:856-871 (IEEE division): used for the
+// centre line, whose argmin must be bit-identical to the reference
 __device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, float len2, float px, float py) {
     float vx = px - ax, vy = py - ay;
     float t = (vx * lx + vy * ly) / len2;
@@ -138,13 +141,24 @@ __device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, f
     float ex = cx - px, ey = cy - py;
     return ex * ex + ey * ey;
 }
+// same with the projection parameter computed as dot * (1/len2): t differs from the reference's quotient by
+// <= 1.5 ulp, i.e. the distance by ~1e-8 m.  Used for the boundaries only (one reciprocal shared by 5 points).
+__device__ __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly, float rlen2, float px, float py) {
+    float vx = px - ax, vy = py - ay;
+    float t = (vx * lx + vy * ly) * rlen2;
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    float cx = ax + lx * t, cy = ay + ly * t;
+    float ex = cx - px, ey = cy - py;
+    return ex * ex + ey * ey;
+}
 
 // distance from a point to an axis-aligned box (lower bound for every polyline point inside it)
-__device__ __forceinline__ float box_lb(float4 bx, float px, float py) {
+__device__ __forceinline__ float box_lb2(float4 bx, float px, float py) {
     float dx = fmaxf(fmaxf(bx.x - px, px - bx.z), 0.0f);
     float dy = fmaxf(fmaxf(bx.y - py, py - bx.w), 0.0f);
-    return sqrtf(dx * dx + dy * dy);
+    return dx * dx + dy * dy;
 }
+__device__ __forceinline__ float box_lb(float4 bx, float px, float py) { return sqrtf(box_lb2(bx, px, py)); }
 
 // The agent's rectangle as interX sees it (helper_scenario.py:1148-1229): closed 5-vertex polyline.
 struct Rect {
@@ -341,32 +355,33 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
     const int nch = (nseg + kChunk - 1) / kChunk;
     int c0 = hint_seg / kChunk;
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
-    BestD bc, bv[4];
-    bc.init();
+    BestQ bq[5]; // 0 = centre, 1..4 = vertices
 #pragma unroll
-    for (int v = 0; v < 4; v++) bv[v].init();
+    for (int v = 0; v < 5; v++) bq[v].init();
     bool hit = false;
     {
         const int s1 = min(c0 * kChunk + kChunk, nseg);
         for (int s = c0 * kChunk + lane; s < s1; s += G) {
             float2 a = pts[s], e = pts[s + 1];
-            float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
-            bc.upd(seg_q(a.x, a.y, lx, ly, len2, px, py));
+            float lx = e.x - a.x, ly = e.y - a.y, rl = 1.0f / (lx * lx + ly * ly);
+            bq[0].upd(seg_q_r(a.x, a.y, lx, ly, rl, px, py));
 #pragma unroll
-            for (int v = 0; v < 4; v++) bv[v].upd(seg_q(a.x, a.y, lx, ly, len2, r.vx[v], r.vy[v]));
+            for (int v = 0; v < 4; v++) bq[v + 1].upd(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]));
             hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
         }
     }
-    // group-wide bound (lanes that got no segment of the hint chunk hold +inf)
-    float gb = group_min<G>(bc.d);
+    // group-wide bound (lanes that got no segment of the hint chunk hold +inf): every point is within
+    // rect_radius of the centre, so a chunk can matter for some point only if lb(centre) <= max best + radius
+    float gq = group_min<G>(bq[0].q);
 #pragma unroll
-    for (int v = 0; v < 4; v++) gb = fmaxf(gb, group_min<G>(bv[v].d));
-    const float thr = gb + rect_radius + kDistMargin; // lb(vertex) >= lb(centre) - rect_radius
+    for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
+    float thr = sqrtf(gq) + rect_radius + kDistMargin;
+    thr = thr * thr;
     uint32_t md = 0, mx = 0;
     for (int c = lane; c < nch; c += G) {
         if (c == c0) continue;
         const float4 bx = boxes[c];
-        if (exhaustive || !(box_lb(bx, px, py) > thr)) md |= 1u << c;
+        if (exhaustive || !(box_lb2(bx, px, py) > thr)) md |= 1u << c;
         if (exhaustive || !box_sign_definite(r, bx)) mx |= 1u << c;
     }
     md = group_or<G>(md);
@@ -375,23 +390,52 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
     while (m) {
         const int c = __ffs(m) - 1;
         m &= m - 1;
-        const bool do_dist = (md >> c) & 1u, do_x = (mx >> c) & 1u;
+        const bool do_x = (mx >> c) & 1u;
+        // per-point refinement of the coarse vote: which of the 5 points can still improve inside this box
+        uint32_t need = 0;
+        if ((md >> c) & 1u) {
+            const float4 bx = boxes[c];
+            if (exhaustive || !bq[0].box_useless(box_lb2(bx, px, py))) need |= 1u;
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                if (exhaustive || !bq[v + 1].box_useless(box_lb2(bx, r.vx[v], r.vy[v]))) need |= 2u << v;
+        }
+        if (!(need | (do_x ? 1u : 0u))) continue;
         const int s1 = min(c * kChunk + kChunk, nseg);
         for (int s = c * kChunk + lane; s < s1; s += G) {
             float2 a = pts[s], e = pts[s + 1];
-            if (do_dist) {
-                float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
-                bc.upd(seg_q(a.x, a.y, lx, ly, len2, px, py));
+            if (need) {
+                float lx = e.x - a.x, ly = e.y - a.y, rl = 1.0f / (lx * lx + ly * ly);
+                if (need & 1u) bq[0].upd(seg_q_r(a.x, a.y, lx, ly, rl, px, py));
 #pragma unroll
-                for (int v = 0; v < 4; v++) bv[v].upd(seg_q(a.x, a.y, lx, ly, len2, r.vx[v], r.vy[v]));
+                for (int v = 0; v < 4; v++)
+                    if (need & (2u << v)) bq[v + 1].upd(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]));
             }
             if (do_x) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
         }
     }
-    d_cg = group_min<G>(bc.d);
+    d_cg = sqrtf(group_min<G>(bq[0].q));
 #pragma unroll
-    for (int v = 0; v < 4; v++) dv[v] = group_min<G>(bv[v].d);
+    for (int v = 0; v < 4; v++) dv[v] = sqrtf(group_min<G>(bq[v + 1].q));
     hit_out = group_or<G>(hit ? 1u : 0u) != 0u;
+}
+
+// index (and distance) of the rank-kk nearest agent: torch.topk(k, largest=False) order, ties -> lower index
+__device__ __forceinline__ int kth_nearest(const float* dij, int N, int kk, float* d_out) {
+    uint32_t used = 0;
+    int bj = 0;
+    float bd = 0.0f;
+    for (int q = 0; q <= kk; q++) {
+        bj = -1;
+        bd = __int_as_float(0x7f800000);
+        for (int j = 0; j < N; j++) {
+            float dj = dij[j];
+            if (!((used >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
+        }
+        used |= 1u << bj;
+    }
+    if (d_out) *d_out = bd;
+    return bj;
 }
 
 // helper_scenario.py:892-957 short-term reference path (n_points_shift = 1, sample interval 2)
@@ -680,115 +724,114 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 const bool write_obs = step_mode || p.write_obs;
                 float* o = ts.obs + (size_t)sl * D;
                 const float cs = ts.cs[sl], sn = ts.sn[sl];
-                const int n_roles = k_near + 2;
-                for (int role = lane; role < n_roles; role += G) {
-                    if (role == 0) {
-                        if (!write_obs) continue;
-                        // ---- own block: observation_provider_rt.py:857-925.  What agent i's observation sees
-                        // (SURVEY.md A.2 / A.6): after a reset everything is fresh; in a step agent 0 sees fresh
-                        // centre queries + vertex queries of the OLD rectangle, agents >= 1 see last step's values.
-                        float o_dref, o_mL, o_mR;
-                        int o_idx;
-                        if (!step_mode) { o_dref = d_ref_n; o_mL = fminf(dLc, m4L); o_mR = fminf(dRc, m4R); o_idx = idx_n; }
-                        else if (i == 0) { o_dref = d_ref_n; o_mL = fminf(dLc, c_mL); o_mR = fminf(dRc, c_mR); o_idx = idx_n; }
-                        else { o_dref = c_dref; o_mL = c_mL; o_mR = c_mR; o_idx = c_idx; }
-                        float2 st[3];
-                        short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, o_idx, st);
-                        o[0] = ts.vabs[sl] / cfg.norm_v;
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            float dx = st[k].x - pix, dy = st[k].y - piy;
-                            o[1 + 2 * k] = (dx * cs + dy * sn) / cfg.norm_pos;
-                            o[2 + 2 * k] = (dy * cs - dx * sn) / cfg.norm_pos;
+                const float2* cpts = pts + pr.c_off;
+                // What agent i's observation sees: after a reset everything is fresh; in a
+                // step agent 0 sees fresh centre queries + vertex queries of the OLD rectangle, agents >= 1 see
+                // last step's values (observation_provider_rt.py:857-925).
+                float o_dref, o_mL, o_mR;
+                int o_idx;
+                if (!step_mode) { o_dref = d_ref_n; o_mL = fminf(dLc, m4L); o_mR = fminf(dRc, m4R); o_idx = idx_n; }
+                else if (i == 0) { o_dref = d_ref_n; o_mL = fminf(dLc, c_mL); o_mR = fminf(dRc, c_mR); o_idx = idx_n; }
+                else { o_dref = c_dref; o_mL = c_mL; o_mR = c_mR; o_idx = c_idx; }
+                if (write_obs) {
+                    // ---- point transforms into the ego frame, split evenly over the lanes: 3 short-term points
+                    //      of the agent itself + 4 vertices of each observed neighbour (rotation form of
+                    //      helper_scenario.py:1241-1273, cos/sin of the heading come from phase A)
+                    const int n_pts = 3 + 4 * k_near;
+                    for (int t = lane; t < n_pts; t += G) {
+                        float qx, qy;
+                        float* dst;
+                        if (t < 3) {
+                            int fi = 2 * t + o_idx + 1;                                  // helper_scenario.py:928-946
+                            if (pr.is_loop && fi >= pr.n_c - 1) fi = (fi + 1) % pr.n_c;
+                            const float2 q = cpts[fi];
+                            qx = q.x; qy = q.y;
+                            dst = o + 1 + 2 * t;
+                        } else {
+                            const int kk = (t - 3) >> 2, v = (t - 3) & 3;
+                            const int bj = kk == 0 ? nb_j[0] : (kk == 1 ? nb_j[1] : kth_nearest(ts.dij + sl * N, N, kk, nullptr));
+                            const int sj = base + bj;
+                            qx = ts.vtx[v * AS + sj]; qy = ts.vtx[(4 + v) * AS + sj];
+                            dst = o + 10 + 11 * kk + 2 * v;
                         }
+                        const float dx = qx - pix, dy = qy - piy;
+                        dst[0] = (dx * cs + dy * sn) / cfg.norm_pos;
+                        dst[1] = (dy * cs - dx * sn) / cfg.norm_pos;
+                    }
+                    if (lane == 0) {
+                        o[0] = ts.vabs[sl] / cfg.norm_v;
                         o[7] = o_dref / cfg.norm_dist;
                         o[8] = o_mL / cfg.norm_dist;
                         o[9] = o_mR / cfg.norm_dist;
-                    } else if (role <= k_near) {
-                        if (!write_obs) continue;
-                        // ---- neighbour block kk: observation_provider_rt.py:622-855 ----
-                        const int kk = role - 1;
-                        int bj;
-                        float bd;
-                        if (kk < 2) { bj = nb_j[kk]; bd = nb_d[kk]; }
-                        else {      // k_near > 2: redo the selection up to rank kk
-                            uint32_t u2 = 0;
-                            bj = -1; bd = 0.0f;
-                            for (int q = 0; q <= kk; q++) {
-                                bj = -1; bd = __int_as_float(0x7f800000);
-                                for (int j = 0; j < N; j++) {
-                                    float dj = ts.dij[sl * N + j];
-                                    if (!((u2 >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
-                                }
-                                u2 |= 1u << bj;
-                            }
-                        }
-                        const int sj = base + bj;
-                        float* ob = o + 10 + 11 * kk;
-#pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            float dx = ts.vtx[v * AS + sj] - pix, dy = ts.vtx[(4 + v) * AS + sj] - piy;
-                            ob[2 * v] = (dx * cs + dy * sn) / cfg.norm_pos;
-                            ob[2 * v + 1] = (dy * cs - dx * sn) / cfg.norm_pos;
-                        }
-                        // |v_j| * (cos, sin)(psi_j - psi_i) via the stored cos/sin of both headings
-                        const float cj = ts.cs[sj], sj_ = ts.sn[sj];
-                        ob[8] = (ts.vabs[sj] * (cj * cs + sj_ * sn)) / cfg.norm_v;
-                        ob[9] = (ts.vabs[sj] * (sj_ * cs - cj * sn)) / cfg.norm_v;
-                        ob[10] = bd / cfg.norm_dist;
-                        if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
-                    } else {
-                        // ---- reward (road_traffic.py:947-1253), flags, next step's carry ----
-                        int fl = ts.flags[sl];
-                        if (coll) fl |= (int)SGB_FLAG_COLLIDE_AGENT;
-                        ts.flags[sl] = fl;
-                        float d_bound;
-                        if (!step_mode || i != 0) d_bound = fminf(fminf(dLc, m4L), fminf(dRc, m4R));
-                        else d_bound = fminf(fminf(dLc, c_mL), fminf(dRc, c_mR)); // agent 0: stale vertices
-                        if (step_mode) {
-                            float2 st_old[3];   // short-term path of the PREVIOUS step
-                            short_term(pts + pr.c_off, pr.n_c, pr.is_loop != 0, c_idx, st_old);
-                            const float oxp = ts.ox[sl], oyp = ts.oy[sl];
-                            float mvx = pix - oxp, mvy = piy - oyp;
-                            float acc = 0.0f;
-#pragma unroll
-                            for (int k = 0; k < 3; k++) {
-                                float rx = st_old[k].x - oxp, ry = st_old[k].y - oyp;
-                                acc += (mvx * rx + mvy * ry) * cfg.w_ref[k];
-                            }
-                            float rew = 0.0f;
-                            rew += (acc / cfg.speed_dt) * cfg.reward_progress;
-                            const float pen_a2a = (coll ? 1.0f : 0.0f) * cfg.penalty_collide_agents;
-                            const float pen_lane = ((fl & SGB_FLAG_COLLIDE_LANE) ? 1.0f : 0.0f) * cfg.penalty_collide_lane;
-                            const float pen_nb = dec_lin(d_bound, cfg.near_boundary_low, cfg.near_boundary_high) * cfg.penalty_near_boundary;
-                            if (cfg.rew_flags & SGB_REW_EXACT_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                            if (cfg.rew_flags & SGB_REW_TTC) {
-                                float risk = ttc_sum / (float)(N - 1 > 1 ? N - 1 : 1);
-                                rew += risk * cfg.penalty_near_agents;
-                                rew += pen_nb;
-                                rew += pen_a2a; rew += pen_lane;
-                                if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                            }
-                            if (cfg.rew_flags & SGB_REW_DISTANCE) {
-                                rew += near_sum * cfg.penalty_near_agents;
-                                rew += pen_nb;
-                                if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                            }
-                            p.buf.reward[g] = clampf(rew, -1.0f, 1.0f);
-                            p.buf.agent_flags[g] = (uint8_t)fl;
-                            if (p.buf.collide_with) p.buf.collide_with[g] = coll;
-                        } else {
-                            p.buf.agent_flags[g] = 0;
-                            if (p.buf.collide_with) p.buf.collide_with[g] = 0;
-                        }
-                        float4 nc;
-                        nc.x = d_ref_n;
-                        nc.y = (i == 0) ? m4L : fminf(dLc, m4L);
-                        nc.z = (i == 0) ? m4R : fminf(dRc, m4R);
-                        nc.w = __int_as_float(idx_n);
-                        reinterpret_cast<float4*>(p.buf.carry)[g] = nc;
-                        if (p.buf.dbg) p.buf.dbg[g * 16 + 12] = d_bound;
                     }
+                    if (lane == 1 % G) {
+                        for (int kk = 0; kk < k_near; kk++) {
+                            int bj;
+                            float bd;
+                            if (kk < 2) { bj = nb_j[kk]; bd = nb_d[kk]; }
+                            else bj = kth_nearest(ts.dij + sl * N, N, kk, &bd);
+                            const int sj = base + bj;
+                            float* ob = o + 10 + 11 * kk;
+                            // |v_j| * (cos, sin)(psi_j - psi_i) via the stored cos/sin of both headings
+                            const float cj = ts.cs[sj], sj_ = ts.sn[sj];
+                            ob[8] = (ts.vabs[sj] * (cj * cs + sj_ * sn)) / cfg.norm_v;
+                            ob[9] = (ts.vabs[sj] * (sj_ * cs - cj * sn)) / cfg.norm_v;
+                            ob[10] = bd / cfg.norm_dist;
+                            if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
+                        }
+                    }
+                }
+                if (lane == 2 % G) {
+                    // ---- reward (road_traffic.py:947-1253), flags, next step's carry ----
+                    int fl = ts.flags[sl];
+                    if (coll) fl |= (int)SGB_FLAG_COLLIDE_AGENT;
+                    ts.flags[sl] = fl;
+                    float d_bound;
+                    if (!step_mode || i != 0) d_bound = fminf(fminf(dLc, m4L), fminf(dRc, m4R));
+                    else d_bound = fminf(fminf(dLc, c_mL), fminf(dRc, c_mR)); // agent 0: stale vertices
+                    if (step_mode) {
+                        float2 st_old[3];   // short-term path of the PREVIOUS step
+                        short_term(cpts, pr.n_c, pr.is_loop != 0, c_idx, st_old);
+                        const float oxp = ts.ox[sl], oyp = ts.oy[sl];
+                        float mvx = pix - oxp, mvy = piy - oyp;
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            float rx = st_old[k].x - oxp, ry = st_old[k].y - oyp;
+                            acc += (mvx * rx + mvy * ry) * cfg.w_ref[k];
+                        }
+                        float rew = 0.0f;
+                        rew += (acc / cfg.speed_dt) * cfg.reward_progress;
+                        const float pen_a2a = (coll ? 1.0f : 0.0f) * cfg.penalty_collide_agents;
+                        const float pen_lane = ((fl & SGB_FLAG_COLLIDE_LANE) ? 1.0f : 0.0f) * cfg.penalty_collide_lane;
+                        const float pen_nb = dec_lin(d_bound, cfg.near_boundary_low, cfg.near_boundary_high) * cfg.penalty_near_boundary;
+                        if (cfg.rew_flags & SGB_REW_EXACT_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                        if (cfg.rew_flags & SGB_REW_TTC) {
+                            float risk = ttc_sum / (float)(N - 1 > 1 ? N - 1 : 1);
+                            rew += risk * cfg.penalty_near_agents;
+                            rew += pen_nb;
+                            rew += pen_a2a; rew += pen_lane;
+                            if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                        }
+                        if (cfg.rew_flags & SGB_REW_DISTANCE) {
+                            rew += near_sum * cfg.penalty_near_agents;
+                            rew += pen_nb;
+                            if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                        }
+                        p.buf.reward[g] = clampf(rew, -1.0f, 1.0f);
+                        p.buf.agent_flags[g] = (uint8_t)fl;
+                        if (p.buf.collide_with) p.buf.collide_with[g] = coll;
+                    } else {
+                        p.buf.agent_flags[g] = 0;
+                        if (p.buf.collide_with) p.buf.collide_with[g] = 0;
+                    }
+                    float4 nc;
+                    nc.x = d_ref_n;
+                    nc.y = (i == 0) ? m4L : fminf(dLc, m4L);
+                    nc.z = (i == 0) ? m4R : fminf(dRc, m4R);
+                    nc.w = __int_as_float(idx_n);
+                    reinterpret_cast<float4*>(p.buf.carry)[g] = nc;
+                    if (p.buf.dbg) p.buf.dbg[g * 16 + 12] = d_bound;
                 }
             }
         }
