@@ -167,11 +167,11 @@ int check_buffers(const sgb_buffers* b, int step) {
     return SGB_OK;
 }
 
-// lanes per agent: enough agents per tile to keep whole envs together, as many lanes as still fit
+// lanes per agent: a warp must hold whole envs (N * G <= 32); as many lanes as still fit, at most 4
 int pick_group(int N) {
-    if (N <= 8) return 4;   // 64 agent slots per tile
-    if (N <= 16) return 4;
-    return 2;               // up to 32 agents per env
+    if (N <= 8) return 4;
+    if (N <= 16) return 2;
+    return 1;
 }
 
 int ensure_list(sgb_ctx* c, int B) {
@@ -187,9 +187,9 @@ int ensure_list(sgb_ctx* c, int B) {
 template <int G>
 int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int slots = kThreads / G;
-    p.envs_per_tile = slots / p.N;
-    if (p.envs_per_tile < 1) return SGB_ERR_ARG;
-    p.n_tiles = (p.B + p.envs_per_tile - 1) / p.envs_per_tile;
+    const int envs_per_warp = 32 / (p.N * G);
+    if (envs_per_warp < 1) return SGB_ERR_ARG;
+    const int n_wt = (p.B + envs_per_warp - 1) / envs_per_warp;   // upper bound (a list may hold fewer envs)
     const size_t smem = ((size_t)ctx->blob_bytes + 127) / 128 * 128 + tile_smem_bytes(slots, p.N, p.D) + 128;
     if ((int64_t)smem > ctx->max_smem_optin) {
         snprintf(g_err, sizeof g_err, "map blob %d B + tile arrays need %zu B of shared memory, device offers %d B",
@@ -201,7 +201,8 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
         CK(cudaFuncSetAttribute(env_step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int grid = std::min(p.n_tiles, ctx->num_sms);
+    const int warps = kThreads / 32;
+    const int grid = std::min((n_wt + warps - 1) / warps, ctx->num_sms);
     env_step_kernel<G><<<grid, kThreads, smem, st>>>(p);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -222,7 +223,8 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.write_obs = write_obs;
     switch (pick_group(N)) {
         case 4: return launch_env_kernel<4>(ctx, p, st);
-        default: return launch_env_kernel<2>(ctx, p, st);
+        case 2: return launch_env_kernel<2>(ctx, p, st);
+        default: return launch_env_kernel<1>(ctx, p, st);
     }
 }
 

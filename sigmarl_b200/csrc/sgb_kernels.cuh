@@ -56,7 +56,6 @@ struct Params {
     const int32_t* env_list;   // refresh: compacted list of env indices (NULL = all B envs, in order)
     const int32_t* env_count;  // device pointer: number of entries of env_list
     int32_t B, N, D;
-    int32_t envs_per_tile, n_tiles;
     int32_t blob_bytes;
     int32_t mode;              // 0 = step, 1 = refresh
     int32_t write_obs;
@@ -89,6 +88,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         "r"(phase)
         : "memory");
 }
+
+__device__ __noinline__ void sincos_ool(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+__device__ __noinline__ float tan_ool(float x) { return tanf(x); }
+__device__ __noinline__ float atan_ool(float x) { return atanf(x); }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
@@ -164,7 +167,10 @@ __device__ __forceinline__ float box_lb(float4 bx, float px, float py) { return 
 struct Rect {
     float vx[4], vy[4];    // vertices 0..3 (vertex 4 == vertex 0)
     float dx[4], dy[4], S[4]; // per edge i: v[i] -> v[i+1]
+    float x0, x1, y0, y1;  // axis-aligned bounding box of the four vertices
     __device__ __forceinline__ void finish() {
+        x0 = fminf(fminf(vx[0], vx[1]), fminf(vx[2], vx[3])); x1 = fmaxf(fmaxf(vx[0], vx[1]), fmaxf(vx[2], vx[3]));
+        y0 = fminf(fminf(vy[0], vy[1]), fminf(vy[2], vy[3])); y1 = fmaxf(fmaxf(vy[0], vy[1]), fmaxf(vy[2], vy[3]));
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             int j = (i + 1) & 3;
@@ -181,6 +187,16 @@ struct Rect {
 __device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by) {
     float dx2 = bx - ax, dy2 = by - ay;
     float S2 = dx2 * ay - dy2 * ax;
+    {
+        // g(v) = fl(fl(fl(vy*dx2) - fl(vx*dy2)) - S2) is monotone in vy and in vx (every IEEE operation is
+        // monotone), so its extremes over the rectangle's bounding box are attained at two box corners.  If
+        // both have the same strict sign, all four g[i] have it too (bit-exactly) and no C2 term can be true.
+        const float ya = dx2 >= 0.0f ? r.y1 : r.y0, yb = dx2 >= 0.0f ? r.y0 : r.y1;
+        const float xa = dy2 >= 0.0f ? r.x0 : r.x1, xb = dy2 >= 0.0f ? r.x1 : r.x0;
+        const float gmax = (ya * dx2 - xa * dy2) - S2;
+        const float gmin = (yb * dx2 - xb * dy2) - S2;
+        if (gmin > 0.0f || gmax < 0.0f) return false;
+    }
     float g[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) g[i] = (r.vy[i] * dx2 - r.vx[i] * dy2) - S2;
@@ -230,17 +246,25 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
 // Certified "no edge line of the rectangle separates points of this box": for every edge i the sign of
 // f_i(x,y) = dx_i*y - dy_i*x - S_i is the same for all (x,y) in the box, with a margin far above the fp32
 // evaluation error, hence C1 of interX is false for every segment inside the box -> no crossing.
-__device__ __forceinline__ bool box_sign_definite(const Rect& r, float4 bx) {
-    float cx = 0.5f * (bx.x + bx.z), cy = 0.5f * (bx.y + bx.w);
-    float hx = 0.5f * (bx.z - bx.x), hy = 0.5f * (bx.w - bx.y);
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float f = (r.dx[i] * cy - r.dy[i] * cx) - r.S[i];
-        float rad = fabsf(r.dx[i]) * hy + fabsf(r.dy[i]) * hx + kSignMargin;
-        ok &= (fabsf(f) > rad);
+// Edges 0/2 and 1/3 are anti-parallel (d_2 = -d_0 up to ~1e-6 rounding), so f_2(q) = f_0(v_2) - f_0(q) and
+// f_3(q) = f_1(v_3) - f_1(q) up to ~1e-5, which kSignMargin absorbs: two evaluations certify four edges.
+struct SignCert {
+    float k0, k1;           // f_0(v_2), f_1(v_3)
+    float ax0, ay0, ax1, ay1; // |dx|, |dy| of edges 0 and 1
+    __device__ __forceinline__ void init(const Rect& r) {
+        k0 = (r.dx[0] * r.vy[2] - r.dy[0] * r.vx[2]) - r.S[0];
+        k1 = (r.dx[1] * r.vy[3] - r.dy[1] * r.vx[3]) - r.S[1];
+        ax0 = fabsf(r.dx[0]); ay0 = fabsf(r.dy[0]); ax1 = fabsf(r.dx[1]); ay1 = fabsf(r.dy[1]);
     }
-    return ok;
+};
+__device__ __forceinline__ bool box_sign_definite(const Rect& r, const SignCert& sc, float4 bx) {
+    const float cx = 0.5f * (bx.x + bx.z), cy = 0.5f * (bx.y + bx.w);
+    const float hx = 0.5f * (bx.z - bx.x), hy = 0.5f * (bx.w - bx.y);
+    const float f0 = (r.dx[0] * cy - r.dy[0] * cx) - r.S[0];
+    const float f1 = (r.dx[1] * cy - r.dy[1] * cx) - r.S[1];
+    const float rad0 = sc.ax0 * hy + sc.ay0 * hx + kSignMargin;
+    const float rad1 = sc.ax1 * hy + sc.ay1 * hx + kSignMargin;
+    return (fabsf(f0) > rad0) & (fabsf(sc.k0 - f0) > rad0) & (fabsf(f1) > rad1) & (fabsf(sc.k1 - f1) > rad1);
 }
 
 template <int G>
@@ -276,6 +300,7 @@ struct TileSmem {
     int* path;
     int* flags;
     int* env;                   // global env index of the slot (-1: inactive)
+    int* coll;                  // bit j: rectangle crossing with agent j of the same env
 };
 
 __device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, int D, TileSmem& t) {
@@ -286,9 +311,10 @@ __device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, in
     t.dij = f; f += A * N; t.obs = f; f += A * D;
     t.path = reinterpret_cast<int*>(f); f += A; t.flags = reinterpret_cast<int*>(f); f += A;
     t.env = reinterpret_cast<int*>(f); f += A;
+    t.coll = reinterpret_cast<int*>(f); f += A;
 }
 __host__ __device__ inline size_t tile_smem_bytes(int A, int N, int D) {
-    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 3) + (size_t)A * N + (size_t)A * D);
+    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 4) + (size_t)A * N + (size_t)A * D);
 }
 
 // ---- phase B building blocks ------------------------------------------------------------------------------
@@ -346,7 +372,9 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
     idx_out = idx + 1; // helper_scenario.py:885-887
 }
 
-// boundary: distances of the centre + 4 vertices, and the rectangle-crossing flag
+// boundary: distances of the centre + 4 vertices, and the rectangle-crossing flag.  Pass 0 scans the hint
+// chunk (all points, crossing test on), pass 1 the voted chunks; the segment body exists once (code size
+// matters: the warps of an SM run different phases at the same time and share the instruction caches).
 template <int G>
 __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_b,
                                               int hint_seg, bool exhaustive, float px, float py, const Rect& r,
@@ -355,64 +383,64 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
     const int nch = (nseg + kChunk - 1) / kChunk;
     int c0 = hint_seg / kChunk;
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
+    SignCert cert;
+    cert.init(r);
     BestQ bq[5]; // 0 = centre, 1..4 = vertices
 #pragma unroll
     for (int v = 0; v < 5; v++) bq[v].init();
     bool hit = false;
-    {
-        const int s1 = min(c0 * kChunk + kChunk, nseg);
-        for (int s = c0 * kChunk + lane; s < s1; s += G) {
-            float2 a = pts[s], e = pts[s + 1];
-            float lx = e.x - a.x, ly = e.y - a.y, rl = 1.0f / (lx * lx + ly * ly);
-            bq[0].upd(seg_q_r(a.x, a.y, lx, ly, rl, px, py));
+    uint32_t md = 1u << c0, mx = 1u << c0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        uint32_t m = md | mx;
+#pragma unroll 1
+        while (m) {
+            const int c = __ffs(m) - 1;
+            m &= m - 1;
+            const bool do_x = (mx >> c) & 1u;
+            uint32_t need = 0;
+            if ((md >> c) & 1u) {
+                need = 31u;
+                if (pass && !exhaustive) {
+                    // per-point refinement of the coarse vote: which of the 5 points can still improve in this box
+                    const float4 bx = boxes[c];
+                    need = bq[0].box_useless(box_lb2(bx, px, py)) ? 0u : 1u;
 #pragma unroll
-            for (int v = 0; v < 4; v++) bq[v + 1].upd(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]));
-            hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
-        }
-    }
-    // group-wide bound (lanes that got no segment of the hint chunk hold +inf): every point is within
-    // rect_radius of the centre, so a chunk can matter for some point only if lb(centre) <= max best + radius
-    float gq = group_min<G>(bq[0].q);
-#pragma unroll
-    for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
-    float thr = sqrtf(gq) + rect_radius + kDistMargin;
-    thr = thr * thr;
-    uint32_t md = 0, mx = 0;
-    for (int c = lane; c < nch; c += G) {
-        if (c == c0) continue;
-        const float4 bx = boxes[c];
-        if (exhaustive || !(box_lb2(bx, px, py) > thr)) md |= 1u << c;
-        if (exhaustive || !box_sign_definite(r, bx)) mx |= 1u << c;
-    }
-    md = group_or<G>(md);
-    mx = group_or<G>(mx);
-    uint32_t m = md | mx;
-    while (m) {
-        const int c = __ffs(m) - 1;
-        m &= m - 1;
-        const bool do_x = (mx >> c) & 1u;
-        // per-point refinement of the coarse vote: which of the 5 points can still improve inside this box
-        uint32_t need = 0;
-        if ((md >> c) & 1u) {
-            const float4 bx = boxes[c];
-            if (exhaustive || !bq[0].box_useless(box_lb2(bx, px, py))) need |= 1u;
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-                if (exhaustive || !bq[v + 1].box_useless(box_lb2(bx, r.vx[v], r.vy[v]))) need |= 2u << v;
-        }
-        if (!(need | (do_x ? 1u : 0u))) continue;
-        const int s1 = min(c * kChunk + kChunk, nseg);
-        for (int s = c * kChunk + lane; s < s1; s += G) {
-            float2 a = pts[s], e = pts[s + 1];
-            if (need) {
-                float lx = e.x - a.x, ly = e.y - a.y, rl = 1.0f / (lx * lx + ly * ly);
-                if (need & 1u) bq[0].upd(seg_q_r(a.x, a.y, lx, ly, rl, px, py));
-#pragma unroll
-                for (int v = 0; v < 4; v++)
-                    if (need & (2u << v)) bq[v + 1].upd(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]));
+                    for (int v = 0; v < 4; v++)
+                        if (!bq[v + 1].box_useless(box_lb2(bx, r.vx[v], r.vy[v]))) need |= 2u << v;
+                }
             }
-            if (do_x) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
+            if (!(need | (do_x ? 1u : 0u))) continue;
+            const int s1 = min(c * kChunk + kChunk, nseg);
+            for (int s = c * kChunk + lane; s < s1; s += G) {
+                const float2 a = pts[s], e = pts[s + 1];
+                if (need) {
+                    const float lx = e.x - a.x, ly = e.y - a.y, rl = 1.0f / (lx * lx + ly * ly);
+                    if (need & 1u) bq[0].upd(seg_q_r(a.x, a.y, lx, ly, rl, px, py));
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+                        if (need & (2u << v)) bq[v + 1].upd(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]));
+                }
+                if (do_x) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
+            }
         }
+        if (pass) break;
+        // group-wide bound (lanes that got no segment of the hint chunk hold +inf): every point is within
+        // rect_radius of the centre, so a chunk can matter for some point only if lb(centre) <= max best + radius
+        float gq = group_min<G>(bq[0].q);
+#pragma unroll
+        for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
+        float thr = sqrtf(gq) + rect_radius + kDistMargin;
+        thr = thr * thr;
+        md = 0; mx = 0;
+        for (int c = lane; c < nch; c += G) {
+            if (c == c0) continue;
+            const float4 bx = boxes[c];
+            if (exhaustive || !(box_lb2(bx, px, py) > thr)) md |= 1u << c;
+            if (exhaustive || !box_sign_definite(r, cert, bx)) mx |= 1u << c;
+        }
+        md = group_or<G>(md);
+        mx = group_or<G>(mx);
     }
     d_cg = sqrtf(group_min<G>(bq[0].q));
 #pragma unroll
@@ -449,6 +477,10 @@ __device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int 
 }
 
 // ---- the fused kernel -------------------------------------------------------------------------------------
+// Work decomposition: a WARP owns whole envs.  With G lanes per agent an env takes N*G lanes, a warp holds
+// EW = 32 / (N*G) envs (N = 8, G = 4: exactly one env per warp).  After the CTA-wide map staging there is no
+// CTA barrier any more: every warp runs phases A-D of its envs on its own (only __syncwarp), so warps drift
+// apart and overlap their ALU / MUFU / shared-memory phases.
 template <int G>
 __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -456,9 +488,12 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
 
     const int tid = threadIdx.x;
     const int N = p.N, D = p.D;
-    const int A = p.envs_per_tile * N;      // agent slots in use per tile
     const sgb_config& cfg = p.cfg;
     const bool step_mode = (p.mode == 0);
+    constexpr int kWarps = kThreads / 32;
+    constexpr int SPW = 32 / G;                 // agent slots per warp
+    const int env_lanes = N * G;                // lanes per env
+    const int EW = 32 / env_lanes;              // envs per warp (>= 1, checked by the host)
 
     // --- stage the map: one elected thread arms the mbarrier and issues the bulk copies -------------
     const uint32_t bar = smem_u32(&mbar);
@@ -469,8 +504,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     __syncthreads();
     // refresh over a compacted env list: the number of envs is only known on the device
     const int n_envs = p.env_list ? *p.env_count : p.B;
-    const int n_tiles = (n_envs + p.envs_per_tile - 1) / p.envs_per_tile;
-    if ((int)blockIdx.x >= n_tiles) return;  // nothing to do for this CTA: do not even stage the map
+    const int n_wt = (n_envs + EW - 1) / EW;    // warp-tiles
+    if ((int)blockIdx.x * kWarps >= n_wt) return;  // nothing to do for this CTA: do not even stage the map
     if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)p.blob_bytes);
         const uint32_t dst = smem_u32(smem);
@@ -483,20 +518,23 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
 
     const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(smem);
     TileSmem ts;
-    const int AS = kThreads / G;            // slot stride of the SoA arrays
+    constexpr int AS = kThreads / G;            // slot stride of the SoA arrays (all warps)
     carve_tile(smem + ((p.blob_bytes + 127) & ~127), AS, N, D, ts);
 
-    const int slot_b = tid / G;             // agent slot this thread works for in phases B/C
-    const int lane = tid % G;
+    const int w = tid >> 5, ln = tid & 31;
+    const int slot0 = w * SPW;                  // first slot of this warp
+    const int n_slots = EW * N;                 // slots this warp uses
+    const int lane = ln % G;                    // lane within the agent's group
+    const int sl_l = ln / G;                    // slot (within the warp) this lane works for in phases B/C
     const float rect_radius = sqrtf(cfg.half_length * cfg.half_length + cfg.half_width * cfg.half_width) * 1.0001f;
+    const float r_pos = 1.0f / cfg.norm_pos, r_v = 1.0f / cfg.norm_v, r_dist = 1.0f / cfg.norm_dist;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int env0 = tile * p.envs_per_tile;   // first env (or first list entry) of this tile
-
-        // ================= phase A: one thread per agent ==========================================
-        if (tid < A) {
-            const int ei = env0 + tid / N;
-            const int i = tid % N;
+    for (int wt = blockIdx.x * kWarps + w; wt < n_wt; wt += gridDim.x * kWarps) {
+        // ================= phase A: one lane per agent ============================================
+        if (ln < n_slots) {
+            const int st = slot0 + ln;
+            const int ei = wt * EW + ln / N;
+            const int i = ln % N;
             const bool active = ei < n_envs;
             int e = -1;
             if (active) {
@@ -506,8 +544,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 float delta = p.buf.aux[4 * g];
                 float4 car = reinterpret_cast<const float4*>(p.buf.carry)[g];
                 float x = pose.x, y = pose.y, psi = pose.z, v = pose.w;
-                ts.ox[tid] = x;
-                ts.oy[tid] = y;
+                ts.ox[st] = x;
+                ts.oy[st] = y;
                 if (step_mode) {
                     // helper_training.py:807-836
                     float2 u = reinterpret_cast<const float2*>(p.buf.action)[g];
@@ -517,12 +555,14 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     float acc = clampf((u.x - v) / cfg.dt, -cfg.max_acc, cfg.max_acc);
                     float rate = clampf((u.y - delta) / cfg.dt, -cfg.max_steering_rate, cfg.max_steering_rate);
                     // dynamics.py:62-118 + fixed-grid Euler (torchdiffeq)
-                    float td = tanf(delta);
-                    float beta = atanf(cfg.lr_over_lwb * td);
+                    float td = tan_ool(delta);
+                    float beta = atan_ool(cfg.lr_over_lwb * td);
                     float sb, cb;
-                    sincosf(psi + beta, &sb, &cb);
+                    sincos_ool(psi + beta, &sb, &cb);
                     float f0 = v * cb, f1 = v * sb;
-                    float f2 = ((v / cfg.l_wb) * td) * cosf(beta);
+                    float sb2, cb2;
+                    sincos_ool(beta, &sb2, &cb2);
+                    float f2 = ((v / cfg.l_wb) * td) * cb2;
                     x = x + cfg.dt * f0;
                     y = y + cfg.dt * f1;
                     psi = psi + cfg.dt * f2;
@@ -531,34 +571,35 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     const float pi_f = 3.14159274101257324f, two_pi = 6.28318548202514648f;
                     delta = pymod(delta + pi_f, two_pi) - pi_f; // dynamics.py:158
                 }
-                const float beta1 = atanf(cfg.lr_over_lwb * tanf(delta));   // dynamics.py:161-163
+                const float beta1 = atan_ool(cfg.lr_over_lwb * tan_ool(delta));   // dynamics.py:161-163
                 float sc_, cc_;
-                sincosf(psi + beta1, &sc_, &cc_);
+                sincos_ool(psi + beta1, &sc_, &cc_);
                 float vx = v * cc_, vy = v * sc_;
                 reinterpret_cast<float4*>(p.buf.pose)[g] = make_float4(x, y, psi, v);
                 reinterpret_cast<float4*>(p.buf.aux)[g] = make_float4(delta, vx, vy, beta1);
                 // helper_scenario.py:742-826 rectangle vertices
                 float sy, cy;
-                sincosf(psi, &sy, &cy);
+                sincos_ool(psi, &sy, &cy);
                 const float hl = cfg.half_length, hw = cfg.half_width;
                 const float nsy = -sy;
                 const float bxs[4] = {hl, hl, -hl, -hl};
                 const float bys[4] = {hw, -hw, -hw, hw};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    ts.vtx[k * AS + tid] = (cy * bxs[k] + nsy * bys[k]) + x;
-                    ts.vtx[(4 + k) * AS + tid] = (sy * bxs[k] + cy * bys[k]) + y;
+                    ts.vtx[k * AS + st] = (cy * bxs[k] + nsy * bys[k]) + x;
+                    ts.vtx[(4 + k) * AS + st] = (sy * bxs[k] + cy * bys[k]) + y;
                 }
-                ts.px[tid] = x; ts.py[tid] = y; ts.cs[tid] = cy; ts.sn[tid] = sy;
-                ts.vx[tid] = vx; ts.vy[tid] = vy; ts.vabs[tid] = sqrtf(vx * vx + vy * vy);
-                ts.car[0 * AS + tid] = car.x; ts.car[1 * AS + tid] = car.y;
-                ts.car[2 * AS + tid] = car.z; ts.car[3 * AS + tid] = car.w;
-                ts.path[tid] = p.buf.path_id[g];
+                ts.px[st] = x; ts.py[st] = y; ts.cs[st] = cy; ts.sn[st] = sy;
+                ts.vx[st] = vx; ts.vy[st] = vy; ts.vabs[st] = sqrtf(vx * vx + vy * vy);
+                ts.car[0 * AS + st] = car.x; ts.car[1 * AS + st] = car.y;
+                ts.car[2 * AS + st] = car.z; ts.car[3 * AS + st] = car.w;
+                ts.path[st] = p.buf.path_id[g];
             }
-            ts.flags[tid] = active ? 0 : -1; // -1 marks an inactive slot
-            ts.env[tid] = e;
+            ts.flags[st] = active ? 0 : -1; // -1 marks an inactive slot
+            ts.env[st] = e;
+            ts.coll[st] = 0;
         }
-        __syncthreads();
+        __syncwarp();
         if (!map_ready) { mbar_wait(bar, 0); map_ready = true; }
 
         const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
@@ -566,15 +607,14 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         const float4* boxes = reinterpret_cast<const float4*>(smem + hdr->box_off);
 
         // ================= phase B: G lanes per agent, polyline queries out of the smem map =======
-        const bool slot_ok = (slot_b < A) && (ts.flags[slot_b] >= 0);
-        // all 32 lanes of a warp take part in the shuffles, so inactive slots of a live warp run on
-        // dummy-safe data; a warp without any active slot skips phases B and C altogether
-        const bool warp_live = __any_sync(0xffffffffu, slot_ok);
-        const int sl = slot_ok ? slot_b : 0;
+        const bool slot_ok = (sl_l < n_slots) && (ts.flags[slot0 + sl_l] >= 0);
+        if (!__any_sync(0xffffffffu, slot_ok)) continue;   // a warp-tile past the end of a short batch
+        // all 32 lanes take part in the shuffles, so lanes without a live slot run on dummy-safe data (slot 0)
+        const int sl = slot_ok ? slot0 + sl_l : slot0;
         int path = slot_ok ? ts.path[sl] : 0;
         path = (path < 0 || path >= hdr->n_paths) ? 0 : path;
         const PathRec pr = paths[path];
-        if (warp_live) {
+        {
             const float px = slot_ok ? ts.px[sl] : 0.0f, py = slot_ok ? ts.py[sl] : 0.0f;
             Rect r;
 #pragma unroll
@@ -587,14 +627,22 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             // hint = last closest segment (step) / the spawn point written by place_agent (refresh); any value
             // is valid, a good one lets the first chunk scanned set a tight pruning bound
             const int hint = __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1;
-            float d_ref, dLc, dRc, dLv[4], dRv[4];
+            float d_ref, dLc = 0.0f, dRc = 0.0f, dLv[4], dRv[4];
             int idx_ref;
-            bool hitL, hitR;
+            bool hitL = false, hitR = false;
             scan_center<G>(pts + pr.c_off, boxes + pr.cbox, pr.n_c, hint, ex, px, py, lane, d_ref, idx_ref);
-            // the boundaries run alongside the centre line: reuse its closest segment as the hint
+            // the boundaries run alongside the centre line: reuse its closest segment as the hint.
+            // One rolled loop over {left, right}: a single copy of the scan in the instruction stream.
             const int h2 = idx_ref - 1;
-            scan_boundary<G>(pts + pr.l_off, boxes + pr.lbox, pr.n_l, h2, ex, px, py, r, rect_radius, lane, dLc, dLv, hitL);
-            scan_boundary<G>(pts + pr.r_off, boxes + pr.rbox, pr.n_r, h2, ex, px, py, r, rect_radius, lane, dRc, dRv, hitR);
+#pragma unroll 1
+            for (int side = 0; side < 2; side++) {
+                float dc, dvv[4];
+                bool hit;
+                scan_boundary<G>(pts + (side ? pr.r_off : pr.l_off), boxes + (side ? pr.rbox : pr.lbox),
+                                 side ? pr.n_r : pr.n_l, h2, ex, px, py, r, rect_radius, lane, dc, dvv, hit);
+                if (side) { dRc = dc; hitR = hit; dRv[0] = dvv[0]; dRv[1] = dvv[1]; dRv[2] = dvv[2]; dRv[3] = dvv[3]; }
+                else      { dLc = dc; hitL = hit; dLv[0] = dvv[0]; dLv[1] = dvv[1]; dLv[2] = dvv[2]; dLv[3] = dvv[3]; }
+            }
             dLc = dLc - cfg.half_width; // world_state_rt.py:608-610
             dRc = dRc - cfg.half_width;
             int fl = (hitL | hitR) ? (int)SGB_FLAG_COLLIDE_LANE : 0;
@@ -602,9 +650,11 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 // entry / exit segments (world_state_rt.py:394-406, world_state_rt_sim.py:412-424)
                 const float2* L = pts + pr.l_off;
                 const float2* R = pts + pr.r_off;
-                if (rect_cross_seg_L1(r, L[0].x, L[0].y, R[0].x, R[0].y)) fl |= (int)SGB_FLAG_ENTRY;
-                if (rect_cross_seg_L1(r, L[pr.n_l - 1].x, L[pr.n_l - 1].y, R[pr.n_r - 1].x, R[pr.n_r - 1].y))
-                    fl |= (int)SGB_FLAG_EXIT;
+#pragma unroll 1
+                for (int k = 0; k < 2; k++) {
+                    const float2 a = L[k ? pr.n_l - 1 : 0], e = R[k ? pr.n_r - 1 : 0];
+                    if (rect_cross_seg_L1(r, a.x, a.y, e.x, e.y)) fl |= (int)(k ? SGB_FLAG_EXIT : SGB_FLAG_ENTRY);
+                }
             }
             if (slot_ok && lane == 0) {
                 float m4L = fminf(fminf(dLv[0], dLv[1]), fminf(dLv[2], dLv[3]));
@@ -617,25 +667,49 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 ts.sc[5 * AS + sl] = m4R;
                 ts.flags[sl] = step_mode ? fl : 0;
                 if (p.buf.dbg) {
-                    float* dbg = p.buf.dbg + ((size_t)ts.env[sl] * N + sl % N) * 16;
+                    float* dbg = p.buf.dbg + ((size_t)ts.env[sl] * N + (sl - slot0) % N) * 16;
                     dbg[0] = d_ref; dbg[1] = __int_as_float(idx_ref); dbg[2] = dLc; dbg[7] = dRc;
 #pragma unroll
                     for (int v = 0; v < 4; v++) { dbg[3 + v] = dLv[v]; dbg[8 + v] = dRv[v]; }
                 }
             }
         }
-        __syncthreads();
+        // ---- rectangle-rectangle crossings: the N(N-1)/2 unordered pairs of an env are dealt round-robin to
+        //      the env's N*G lanes; interX(vertices[lo], vertices[hi]) with lo < hi exactly as
+        //      world_state_rt_sim.py:384-393, result OR-ed into both agents' masks
+        if (step_mode && ln < EW * env_lanes) {
+            const int el = ln / env_lanes;             // env within the warp
+            const int q = ln - el * env_lanes;         // lane within the env
+            const int sbase = slot0 + el * N;
+            if (ts.flags[sbase] >= 0) {
+                const int n_pairs = N * (N - 1) / 2;
+                for (int pi = q; pi < n_pairs; pi += env_lanes) {
+                    int lo = 0, rem = pi;               // pair index -> (lo, hi), lo < hi
+                    while (rem >= N - 1 - lo) { rem -= N - 1 - lo; lo++; }
+                    const int hi = lo + 1 + rem;
+                    Rect rl;
+                    float hx[4], hy[4];
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        rl.vx[k] = ts.vtx[k * AS + sbase + lo]; rl.vy[k] = ts.vtx[(4 + k) * AS + sbase + lo];
+                        hx[k] = ts.vtx[k * AS + sbase + hi]; hy[k] = ts.vtx[(4 + k) * AS + sbase + hi];
+                    }
+                    rl.finish();
+                    if (rect_cross_rect(rl, hx, hy)) {
+                        atomicOr(&ts.coll[sbase + lo], 1 << hi);
+                        atomicOr(&ts.coll[sbase + hi], 1 << lo);
+                    }
+                }
+            }
+        }
+        __syncwarp();
 
         // ================= phase C: interactions inside the env, reward, observation ===============
-        if (warp_live) {
-            const int i = sl % N;
+        {
+            const int i = (sl - slot0) % N;
             const int base = sl - i; // slot of agent 0 of this env
             const float pix = ts.px[sl], piy = ts.py[sl];
-            Rect ri;
-#pragma unroll
-            for (int k = 0; k < 4; k++) { ri.vx[k] = ts.vtx[k * AS + sl]; ri.vy[k] = ts.vtx[(4 + k) * AS + sl]; }
-            ri.finish();
-            uint32_t coll = 0;
+            const uint32_t coll = (uint32_t)ts.coll[sl];
             float ttc_sum = 0.0f, near_sum = 0.0f;
             // ---- C1: the lanes of the group split the other agents j ----
             if (slot_ok) {
@@ -648,23 +722,6 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     ts.dij[sl * N + j] = dist;
                     if (!step_mode) continue;
                     near_sum += dec_lin(dist, cfg.near_agents_low, cfg.near_agents_high);
-                    if (j != i) {
-                        // world_state_rt_sim.py:384-393: interX(vertices[lo], vertices[hi]), lo < hi
-                        float hx[4], hy[4];
-#pragma unroll
-                        for (int k = 0; k < 4; k++) { hx[k] = ts.vtx[k * AS + sj]; hy[k] = ts.vtx[(4 + k) * AS + sj]; }
-                        bool hit;
-                        if (i < j) {
-                            hit = rect_cross_rect(ri, hx, hy);
-                        } else {
-                            Rect rj;
-#pragma unroll
-                            for (int k = 0; k < 4; k++) { rj.vx[k] = hx[k]; rj.vy[k] = hy[k]; }
-                            rj.finish();
-                            hit = rect_cross_rect(rj, ri.vx, ri.vy);
-                        }
-                        if (hit) coll |= (1u << j);
-                    }
                     if (cfg.rew_flags & SGB_REW_TTC) {
                         // road_traffic.py:1255-1332 (p_rel = p_j - p_i)
                         const float eps = 1e-6f;
@@ -689,14 +746,12 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     }
                 }
             }
-            coll = group_or<G>(coll);
             ttc_sum = group_sum<G>(ttc_sum);
             near_sum = group_sum<G>(near_sum);
             __syncwarp(); // dij of this group is complete
 
-            // ---- C2: every lane of the group picks the k nearest (same result in all lanes), then the lanes
-            //          take roles: role 0 = own block of the observation, roles 1..k = one neighbour block each,
-            //          role k+1 = reward / flags / carry.  torch.topk(k, largest=False), ties -> lower index.
+            // ---- C2: every lane of the group picks the k nearest (same result in all lanes);
+            //          torch.topk(k, largest=False), ties -> lower index.
             const int k_near = cfg.k_near;
             int nb_j[2] = {0, 0};          // the first two neighbours stay in registers, the rest is re-derived
             float nb_d[2] = {0.0f, 0.0f};
@@ -736,7 +791,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 if (write_obs) {
                     // ---- point transforms into the ego frame, split evenly over the lanes: 3 short-term points
                     //      of the agent itself + 4 vertices of each observed neighbour (rotation form of
-                    //      helper_scenario.py:1241-1273, cos/sin of the heading come from phase A)
+                    //      helper_scenario.py:1241-1273, cos/sin of the heading come from phase A; normalisers
+                    //      applied as reciprocals: <= 1 ulp from the reference's division, tolerance is 1e-5)
                     const int n_pts = 3 + 4 * k_near;
                     for (int t = lane; t < n_pts; t += G) {
                         float qx, qy;
@@ -755,14 +811,14 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                             dst = o + 10 + 11 * kk + 2 * v;
                         }
                         const float dx = qx - pix, dy = qy - piy;
-                        dst[0] = (dx * cs + dy * sn) / cfg.norm_pos;
-                        dst[1] = (dy * cs - dx * sn) / cfg.norm_pos;
+                        dst[0] = (dx * cs + dy * sn) * r_pos;
+                        dst[1] = (dy * cs - dx * sn) * r_pos;
                     }
                     if (lane == 0) {
-                        o[0] = ts.vabs[sl] / cfg.norm_v;
-                        o[7] = o_dref / cfg.norm_dist;
-                        o[8] = o_mL / cfg.norm_dist;
-                        o[9] = o_mR / cfg.norm_dist;
+                        o[0] = ts.vabs[sl] * r_v;
+                        o[7] = o_dref * r_dist;
+                        o[8] = o_mL * r_dist;
+                        o[9] = o_mR * r_dist;
                     }
                     if (lane == 1 % G) {
                         for (int kk = 0; kk < k_near; kk++) {
@@ -774,9 +830,9 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                             float* ob = o + 10 + 11 * kk;
                             // |v_j| * (cos, sin)(psi_j - psi_i) via the stored cos/sin of both headings
                             const float cj = ts.cs[sj], sj_ = ts.sn[sj];
-                            ob[8] = (ts.vabs[sj] * (cj * cs + sj_ * sn)) / cfg.norm_v;
-                            ob[9] = (ts.vabs[sj] * (sj_ * cs - cj * sn)) / cfg.norm_v;
-                            ob[10] = bd / cfg.norm_dist;
+                            ob[8] = (ts.vabs[sj] * (cj * cs + sj_ * sn)) * r_v;
+                            ob[9] = (ts.vabs[sj] * (sj_ * cs - cj * sn)) * r_v;
+                            ob[10] = bd * r_dist;
                             if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
                         }
                     }
@@ -835,13 +891,14 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
 
         // ================= phase D: per-env outputs + coalesced observation write-back ============
-        if (step_mode && tid < A && (tid % N) == 0 && ts.flags[tid] >= 0) {
-            const int e = ts.env[tid];
+        if (step_mode && ln < n_slots && (ln % N) == 0 && ts.flags[slot0 + ln] >= 0) {
+            const int st = slot0 + ln;
+            const int e = ts.env[st];
             int any = 0;
-            for (int j = 0; j < N; j++) any |= ts.flags[tid + j];
+            for (int j = 0; j < N; j++) any |= ts.flags[st + j];
             const int step = p.buf.step_count[e] + 1;          // road_traffic.py:954-962
             p.buf.step_count[e] = step;
             // road_traffic.py:1451-1457 (training mode)
@@ -849,22 +906,24 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             p.buf.done[e] = dn ? 1 : 0;
         }
         if (step_mode || p.write_obs) {
-            const int n_env_t = min(p.envs_per_tile, n_envs - env0);
-            const int nf = n_env_t * N * D;                     // floats of this tile
-            if (!p.env_list && ((nf & 3) == 0) && ((((size_t)env0 * N * D) & 3) == 0)) {
-                // envs of the tile are contiguous in HBM: one coalesced float4 stream
-                const float4* s4 = reinterpret_cast<const float4*>(ts.obs);
-                float4* d4 = reinterpret_cast<float4*>(p.buf.obs + (size_t)env0 * N * D);
-                for (int k = tid; k < nf / 4; k += kThreads) d4[k] = s4[k];
+            const int env_first = wt * EW;
+            const int n_env_w = min(EW, n_envs - env_first);
+            const int nf = n_env_w * N * D;                     // floats of this warp-tile
+            const float* src = ts.obs + (size_t)slot0 * D;
+            if (!p.env_list && ((nf & 3) == 0) && ((((size_t)env_first * N * D) & 3) == 0) && (((slot0 * D) & 3) == 0)) {
+                // the warp's envs are contiguous in HBM: one coalesced float4 stream
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4* d4 = reinterpret_cast<float4*>(p.buf.obs + (size_t)env_first * N * D);
+                for (int k = ln; k < nf / 4; k += 32) d4[k] = s4[k];
             } else {
                 const int ND = N * D;
-                for (int k = tid; k < nf; k += kThreads) {
-                    const int el = k / ND;                      // env of the tile
-                    p.buf.obs[(size_t)ts.env[el * N] * ND + (k - el * ND)] = ts.obs[k];
+                for (int k = ln; k < nf; k += 32) {
+                    const int el = k / ND;                      // env within the warp-tile
+                    p.buf.obs[(size_t)ts.env[slot0 + el * N] * ND + (k - el * ND)] = src[k];
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (!map_ready) mbar_wait(bar, 0); // never leave with a bulk copy in flight
 }
