@@ -176,6 +176,14 @@ int sgb_reset_all(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, in
 int sgb_step_host(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
                   float* h_obs, float* h_reward, uint8_t* h_done, void* stream);
 
+/* "Next" row: generalised advantage estimation over a finished rollout, written straight
+ * into caller-provided buffers (e.g. this rank's slot of the all-gather buffer).  All pointers are device
+ * memory; reward / value / next_value / adv / target are [T,B,N] fp32, done is [T,B] bytes (terminated ==
+ * done).  Replaces TorchRL GAE as configured in optimization_module.py:62-67 (gamma 0.99, lambda 0.9, no
+ * advantage normalisation) and the done expansion of mappo_cavs.py:342-355. */
+int sgb_gae(int32_t T, int32_t B, int32_t N, const float* reward, const float* value, const float* next_value,
+            const uint8_t* done, float gamma, float lmbda, float* adv, float* target, void* stream);
+
 /* Number of kernels this context has launched since creation (for launch accounting in benchmarks). */
 int64_t sgb_launch_count(const sgb_ctx* ctx);
 /* Bytes of the packed map blob each CTA stages into shared memory. */

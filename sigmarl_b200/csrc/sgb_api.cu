@@ -376,3 +376,13 @@ extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
     CK(cudaStreamSynchronize(st));
     return SGB_OK;
 }
+
+extern "C" int sgb_gae(int32_t T, int32_t B, int32_t N, const float* reward, const float* value, const float* next_value,
+                       const uint8_t* done, float gamma, float lmbda, float* adv, float* target, void* stream) {
+    if (T <= 0 || B <= 0 || N <= 0 || !reward || !value || !next_value || !done || !adv || !target) return SGB_ERR_ARG;
+    const int bn = B * N;
+    gae_kernel<<<(bn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, bn, N, reward, value, next_value, done, gamma, lmbda,
+                                                                  adv, target);
+    CK(cudaGetLastError());
+    return SGB_OK;
+}

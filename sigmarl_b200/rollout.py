@@ -1,0 +1,96 @@
+"""Rollout collection + GAE + the one collective of the design ("next" row).
+
+Replaces, for this path, ``SyncDataCollectorCustom.rollout`` (``helper_training.py:686-788``) and the TorchRL
+GAE configured in ``optimization_module.py:62-67`` / ``mappo_cavs.py:342-378``:
+
+* ``RolloutBuffer`` keeps ``[T, B, N, ...]`` tensors on the device, written in place each step (no per-step
+  TensorDict stacking).
+* ``collect`` drives ``RoadTrafficEnv`` for T steps with a policy callable, with masked device resets.
+* ``compute_gae`` runs the reverse-scan CUDA kernel (``sgb_gae``) and writes advantage / value target
+  DIRECTLY into this rank's slot of the all-gather buffers, so the collective that follows needs no copy.
+* ``all_gather_advantages`` is the single data exchange of the multi-GPU design: envs are sharded by index
+  over ranks with no communication during the rollout; at PPO-update time every rank gathers everyone's
+  ``[T, B_local, N]`` advantage and value-target buffers (NCCL ``all_gather_into_tensor``, in place).
+"""
+import ctypes as C
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import lib as _lib
+
+
+def shard_range(num_envs_total: int, rank: int, world: int):
+    """Contiguous env-index range owned by `rank` (envs are independent: SURVEY.md A.7)."""
+    if num_envs_total % world:
+        raise ValueError(f"num_envs_total={num_envs_total} must be divisible by world size {world}")
+    per = num_envs_total // world
+    return rank * per, per
+
+
+class RolloutBuffer:
+    def __init__(self, T: int, B: int, N: int, D: int, device, world: int = 1, rank: int = 0):
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=device)  # noqa: E731
+        self.T, self.B, self.N, self.D, self.world, self.rank = T, B, N, D, world, rank
+        self.obs = z(T, B, N, D)
+        self.action = z(T, B, N, 2)
+        self.reward = z(T, B, N)
+        self.done = z(T, B, dtype=torch.uint8)
+        self.value = z(T, B, N)
+        self.next_value = z(T, B, N)
+        # all-gather buffers [world, T, B, N]; this rank's GAE output is written into slot `rank`
+        self.adv_all = z(world, T, B, N)
+        self.target_all = z(world, T, B, N)
+
+    @property
+    def advantage(self):
+        return self.adv_all[self.rank]
+
+    @property
+    def value_target(self):
+        return self.target_all[self.rank]
+
+
+def collect(env, policy: Callable[[torch.Tensor], torch.Tensor], buf: RolloutBuffer,
+            value_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+    """T environment steps.  `policy(obs[B,N,D]) -> action[B,N,2]`; `value_fn(obs) -> [B,N]` (optional).
+
+    TorchRL semantics kept (SURVEY.md assumption A5): the stored next-state value of a done env is the value of
+    its step-time observation (before the reset); the observation the policy sees next is the post-reset one."""
+    obs = env.obs
+    for t in range(buf.T):
+        buf.obs[t].copy_(obs)
+        if value_fn is not None:
+            buf.value[t].copy_(value_fn(obs))
+        act = policy(obs)
+        buf.action[t].copy_(act)
+        obs, rew, done = env.step(act)
+        buf.reward[t].copy_(rew)
+        buf.done[t].copy_(done)
+        if value_fn is not None:
+            buf.next_value[t].copy_(value_fn(obs))
+        env.reset_done(write_obs=True)   # fresh observation for reset envs, step-time observation elsewhere
+        obs = env.obs
+    return buf
+
+
+def compute_gae(buf: RolloutBuffer, gamma: float = 0.99, lmbda: float = 0.9):
+    """Reverse scan over T on the GPU (sgb_gae); output lands in this rank's slot of the gather buffers."""
+    if buf.reward.device.type != "cuda":
+        raise _lib.SgbError("compute_gae runs only on CUDA tensors (no CPU fallback)")
+    L = _lib.load_library()
+    st = C.c_void_p(torch.cuda.current_stream(buf.reward.device).cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(L.sgb_gae(buf.T, buf.B, buf.N, p(buf.reward), p(buf.value), p(buf.next_value), p(buf.done),
+                         gamma, lmbda, p(buf.advantage), p(buf.value_target), st), "sgb_gae")
+    return buf.advantage, buf.value_target
+
+
+def all_gather_advantages(buf: RolloutBuffer, group=None):
+    """The single collective: in-place all-gather of [T, B_local, N] advantage and value-target buffers."""
+    if buf.world == 1:
+        return buf.adv_all, buf.target_all
+    for full in (buf.adv_all, buf.target_all):
+        dist.all_gather_into_tensor(full.view(-1), full[buf.rank].reshape(-1), group=group)
+    return buf.adv_all, buf.target_all

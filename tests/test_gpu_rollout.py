@@ -1,0 +1,49 @@
+"""GPU (-m gpu): the "next" row — rollout collector + GAE kernel (through the C-ABI) against a plain restatement."""
+import numpy as np
+import pytest
+import torch
+
+from test_multi_rank_cpu import gae_numpy
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T,B,N", [(128, 512, 8), (7, 33, 3), (1, 1, 1)])
+def test_gae_kernel_matches_restatement(T, B, N):
+    from sigmarl_b200.rollout import RolloutBuffer, compute_gae
+    rng = np.random.default_rng(T)
+    buf = RolloutBuffer(T, B, N, 4, "cuda:0")
+    host = {k: rng.standard_normal((T, B, N)).astype(np.float32) for k in ("reward", "value", "next_value")}
+    done = rng.random((T, B)) < 0.1
+    for k, v in host.items():
+        getattr(buf, k).copy_(torch.from_numpy(v))
+    buf.done.copy_(torch.from_numpy(done.astype(np.uint8)))
+    adv, tgt = compute_gae(buf, 0.99, 0.9)
+    want_a, want_t = gae_numpy(host["reward"], host["value"], host["next_value"], done, 0.99, 0.9)
+    assert np.max(np.abs(adv.cpu().numpy() - want_a)) <= 1e-5
+    assert np.max(np.abs(tgt.cpu().numpy() - want_t)) <= 1e-5
+
+
+def test_collect_fills_buffers_and_keeps_reset_semantics():
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    from sigmarl_b200.rollout import RolloutBuffer, collect, compute_gae, all_gather_advantages
+    env = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=256, device="cuda:0", seed=1)
+    env.reset()
+    T = 16
+    buf = RolloutBuffer(T, env.B, env.N, env.D, env.device)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ur = torch.tensor([1.0, 31 * np.pi / 180], device="cuda")
+    policy = lambda obs: (torch.rand(env.B, env.N, 2, device="cuda", generator=g) * 2 - 1) * ur  # noqa: E731
+    value = lambda obs: obs[..., 0] * 0.5 + obs[..., 7]  # noqa: E731  any deterministic function of obs
+    first_obs = env.obs.clone()
+    collect(env, policy, buf, value_fn=value)
+    assert torch.equal(buf.obs[0], first_obs)
+    assert torch.isfinite(buf.obs).all() and torch.isfinite(buf.reward).all()
+    assert buf.done.sum() > 0
+    # the observation stored at t+1 of a reset env is the post-reset one: its own speed entry equals |v| of the new pose
+    adv, tgt = compute_gae(buf)
+    a_all, _ = all_gather_advantages(buf)
+    assert a_all.shape == (1, T, env.B, env.N) and torch.equal(a_all[0], adv)
+    want_a, _ = gae_numpy(buf.reward.cpu().numpy(), buf.value.cpu().numpy(), buf.next_value.cpu().numpy(),
+                          buf.done.cpu().numpy().astype(bool), 0.99, 0.9)
+    assert np.max(np.abs(adv.cpu().numpy() - want_a)) <= 1e-5
