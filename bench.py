@@ -29,6 +29,18 @@ ALGO_BYTES = lambda D: 65 + 4 * D  # noqa: E731  SURVEY.md §8(d): algorithmic H
 METRIC = "agent-steps/sec (num_envs x n_agents / step_time), CPM map"
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the fused step kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(REPO, "profiles", "ncu_step_kernel_r1.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+        except Exception:
+            return None
+    return None
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -36,28 +48,39 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe): one
+    `nvidia-smi -lms 20` process streams samples while the timed loop runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.proc, self.rows = index, None, []
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            self.proc.stdout.readline()      # first sample = the sampler is up before the timed region starts
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.03)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=3)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        self.rows = [[c.strip() for c in line.split(",")] for line in out.strip().splitlines() if line.strip()]
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        num = lambda v: v.replace(".", "", 1).isdigit()  # noqa: E731
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and num(r[0])]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and num(r[1])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
@@ -179,8 +202,7 @@ def run_ours(args):
         env.reset_done(write_obs=False)
     barrier()
     t_e2e = time.perf_counter() - t0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
 
     times = torch.tensor([t_total, t_step, t_e2e / Ke * K], device=dev, dtype=torch.float64)
     if world > 1:
@@ -204,7 +226,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": B * N * 2 * 4, "d2h_bytes_per_step": B * N * D * 4 + B * N * 4 + B,
                 "note": "sgb_step_host: pinned host action in, obs/reward/done out, plus device reset"},
         "roofline": {"bound": "hbm", "kernel": "env_step_kernel (fused step)", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_agent_step": ALGO_BYTES(D), "kernel_ms": 1e3 * t_step / K,
                      "note": "path is fp32-ALU/shared-memory bound, not HBM bound (DESIGN.md roofline section)"},
         "clocks": sampler.summary(),
@@ -224,7 +246,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")

@@ -25,7 +25,10 @@ struct sgb_ctx {
     int32_t num_sms = 0;
     int32_t max_smem_optin = 0;
     int64_t launches = 0;
-    void* h_pin = nullptr;           // lazily allocated pinned staging for sgb_step_host? (unused: caller pins)
+    cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // sgb_step_host: chunked copy/compute pipeline
+    cudaEvent_t pipe_event[2] = {nullptr, nullptr};
+    cudaEvent_t pipe_start = nullptr;
+    bool pipe_ready = false;
 };
 
 static thread_local char g_err[256] = "";
@@ -184,7 +187,7 @@ int ensure_list(sgb_ctx* c, int B) {
     return SGB_OK;
 }
 
-template <int G>
+template <int G, int MODE>
 int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int slots = kThreads / G;
     const int envs_per_warp = 32 / (p.N * G);
@@ -198,12 +201,12 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     }
     static thread_local size_t configured = 0;
     if (configured < smem) {
-        CK(cudaFuncSetAttribute(env_step_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(env_step_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int warps = kThreads / 32;
     const int grid = std::min((n_wt + warps - 1) / warps, ctx->num_sms);
-    env_step_kernel<G><<<grid, kThreads, smem, st>>>(p);
+    env_step_kernel<G, MODE><<<grid, kThreads, smem, st>>>(p);
     ctx->launches++;
     CK(cudaGetLastError());
     return SGB_OK;
@@ -221,11 +224,15 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.blob_bytes = ctx->blob_bytes;
     p.mode = mode;
     p.write_obs = write_obs;
-    switch (pick_group(N)) {
-        case 4: return launch_env_kernel<4>(ctx, p, st);
-        case 2: return launch_env_kernel<2>(ctx, p, st);
-        default: return launch_env_kernel<1>(ctx, p, st);
+    const int g = pick_group(N);
+    if (mode == 0) {
+        if (g == 4) return launch_env_kernel<4, 0>(ctx, p, st);
+        if (g == 2) return launch_env_kernel<2, 0>(ctx, p, st);
+        return launch_env_kernel<1, 0>(ctx, p, st);
     }
+    if (g == 4) return launch_env_kernel<4, 1>(ctx, p, st);
+    if (g == 2) return launch_env_kernel<2, 1>(ctx, p, st);
+    return launch_env_kernel<1, 1>(ctx, p, st);
 }
 
 } // namespace
@@ -275,6 +282,10 @@ extern "C" int sgb_destroy(sgb_ctx* c) {
     cudaFree(c->d_yaw);
     cudaFree(c->d_list);
     cudaFree(c->d_count);
+    if (c->pipe_ready) {
+        for (int i = 0; i < 2; i++) { cudaStreamDestroy(c->pipe_stream[i]); cudaEventDestroy(c->pipe_event[i]); }
+        cudaEventDestroy(c->pipe_start);
+    }
     delete c;
     return SGB_OK;
 }
@@ -359,20 +370,48 @@ extern "C" int sgb_reset_all(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
                       n_failed, 1, (cudaStream_t)stream);
 }
 
+// Host-buffer step, pipelined: the batch is cut into chunks that alternate between two internal streams, so
+// the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).
 extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
                              float* h_obs, float* h_reward, uint8_t* h_done, void* stream) {
-    if (!c || !h_action || !h_obs || !h_reward || !h_done) return SGB_ERR_ARG;
+    if (!c || !h_action || !h_obs || !h_reward || !h_done || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS) return SGB_ERR_ARG;
     int rc = check_buffers(buf, 1);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t bn = (size_t)B * N;
     const int D = 10 + 11 * c->cfg.k_near;
-    CK(cudaMemcpyAsync(buf->action, h_action, bn * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-    rc = sgb_step(c, B, N, buf, stream);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h_obs, buf->obs, bn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_reward, buf->reward, bn * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_done, buf->done, (size_t)B, cudaMemcpyDeviceToHost, st));
+    if (!c->pipe_ready) {
+        for (int i = 0; i < 2; i++) {
+            CK(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c->pipe_event[i], cudaEventDisableTiming));
+        }
+        CK(cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
+        c->pipe_ready = true;
+    }
+    const int n_chunks = B >= 8192 ? 8 : (B >= 1024 ? 2 : 1);
+    CK(cudaEventRecord(c->pipe_start, st));
+    for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(c->pipe_stream[i], c->pipe_start, 0));
+    for (int k = 0; k < n_chunks; k++) {
+        cudaStream_t s = c->pipe_stream[k & 1];
+        const int e0 = (int)((int64_t)B * k / n_chunks), e1 = (int)((int64_t)B * (k + 1) / n_chunks);
+        const int nb = e1 - e0;
+        if (nb <= 0) continue;
+        const size_t a0 = (size_t)e0 * N;
+        sgb_buffers sub = *buf;
+        sub.pose += a0 * 4; sub.aux += a0 * 4; sub.path_id += a0; sub.carry += a0 * 4; sub.action += a0 * 2;
+        sub.step_count += e0; sub.obs += a0 * D; sub.reward += a0; sub.done += e0; sub.agent_flags += a0;
+        if (sub.collide_with) sub.collide_with += a0;
+        if (sub.dbg) sub.dbg += a0 * 16;
+        CK(cudaMemcpyAsync(sub.action, h_action + a0 * 2, (size_t)nb * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+        rc = launch_env(c, nb, N, &sub, 0, nullptr, nullptr, 1, s);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h_obs + a0 * D, sub.obs, (size_t)nb * N * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_reward + a0, sub.reward, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h_done + e0, sub.done, (size_t)nb, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventRecord(c->pipe_event[i], c->pipe_stream[i]));
+        CK(cudaStreamWaitEvent(st, c->pipe_event[i], 0));
+    }
     CK(cudaStreamSynchronize(st));
     return SGB_OK;
 }

@@ -481,7 +481,8 @@ __device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int 
 // EW = 32 / (N*G) envs (N = 8, G = 4: exactly one env per warp).  After the CTA-wide map staging there is no
 // CTA barrier any more: every warp runs phases A-D of its envs on its own (only __syncwarp), so warps drift
 // apart and overlap their ALU / MUFU / shared-memory phases.
-template <int G>
+// MODE 0 = step, MODE 1 = refresh (rebuild carry / observation from the current pose; no dynamics, no reward).
+template <int G, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     const int tid = threadIdx.x;
     const int N = p.N, D = p.D;
     const sgb_config& cfg = p.cfg;
-    const bool step_mode = (p.mode == 0);
+    constexpr bool step_mode = (MODE == 0);
     constexpr int kWarps = kThreads / 32;
     constexpr int SPW = 32 / G;                 // agent slots per warp
     const int env_lanes = N * G;                // lanes per env
