@@ -308,3 +308,41 @@ def test_library_refuses_bad_arguments():
     L = lib.load_library()
     assert L.sgb_step(None, 1, 1, None, None) == -1
     assert L.sgb_version() == 100
+
+
+@pytest.mark.parametrize("name", ["c1_intersection_B4_N2", "cpm_entire_B8_N8_distance", "cpm_mixed_B8_N4_gentle"])
+def test_cuda_free_running_matches_reference(name):
+    """BASELINE configs[0] literally: start from the reference's initial state and run FREE (state is never
+    re-synced; only the reference's own reset / respawn draws are replayed through sgb_place), 1e-5 abs on
+    state / obs / reward and exact masks over the whole trajectory — i.e. fp drift stays inside the tolerance."""
+    path = os.path.join(os.path.dirname(__file__), "golden", name + ".npz")
+    g = np.load(path)
+    env = _env_from_golden(g)
+    T, B, N = int(g["cfg_T"]), env.B, env.N
+    gp0 = env.map.global_path(g["pre_scenario_id"][0], g["pre_path_id"][0])
+    env.set_state(g["pre_pos"][0], g["pre_rot"][0], g["pre_speed"][0], g["pre_steering"][0], gp0, step_count=g["pre_step"][0])
+    worst = 0.0
+    for t in range(T):
+        ctx = f"{name} free-run t={t}"
+        obs, rew, done = env.step(torch.as_tensor(g["action"][t]).cuda())
+        torch.cuda.synchronize()
+        for nm, got, want in [("pos", env.pos, g["post_pos"][t]), ("rot", env.rot, g["post_rot"][t]),
+                              ("speed", env.speed, g["post_speed"][t]), ("steering", env.steering, g["post_steering"][t]),
+                              ("vel", env.vel, g["post_vel"][t]), ("obs", obs, g["obs"][t]), ("reward", rew, g["reward"][t])]:
+            worst = max(worst, _close(nm, got.cpu(), want, ctx))
+        fl = env.agent_flags.cpu().numpy()
+        assert np.array_equal(done.cpu().numpy().astype(bool), g["done"][t]), f"{ctx} done"
+        assert np.array_equal((fl & 2) != 0, g["col_lane"][t]) and np.array_equal(_coll_matrix(env), g["col_agents"][t]), ctx
+        assert np.array_equal((fl & 8) != 0, g["col_exit"][t]) and np.array_equal((fl & 4) != 0, g["col_entry"][t]), ctx
+        # replay the reference's respawn (inside done()) and env-reset draws
+        resp, rst = g["respawn_mask"][t], g["reset_mask"][t]
+        if resp.any():
+            gp = env.map.global_path(g["pre_scenario_id"][t], g["respawn_path_id"][t])  # a respawn keeps the scenario
+            env.place(gp, g["respawn_point_id"][t], g["respawn_speed"][t], agent_mask=resp)
+            env.refresh(env_mask=torch.as_tensor(resp.any(1)))
+        if rst.any():
+            gp = env.map.global_path(g["reset_scenario_id"][t], g["reset_path_id"][t])
+            env.place(gp, g["reset_point_id"][t], g["reset_speed"][t], agent_mask=np.repeat(rst[:, None], N, 1))
+            env.refresh(env_mask=torch.as_tensor(rst))
+            env.step_count[torch.as_tensor(rst).cuda()] = 0
+    assert worst <= TOL
