@@ -8,7 +8,7 @@
 //                                   with per-chunk bounding boxes; warp-shuffle reductions
 //   phase C  G lanes per agent    : centre distances / rectangle crossings / TTC against the other
 //                                   agents of the env, k-nearest selection, reward, observation -> smem
-//   phase D  whole CTA            : coalesced float4 write-back of the observation tile
+//   phase D  one lane per env     : done flag, step counter
 //
 // Arithmetic contract (see DESIGN.md "Exactness"): this translation unit is compiled with
 // -fmad=false, IEEE sqrt/div, no fast-math; every value that feeds an argmin or a strict-sign
@@ -25,7 +25,10 @@
 
 namespace sgb {
 
-constexpr int kThreads = 512;        // threads per CTA (16 warps; 128 regs/thread fill the register file)
+#ifndef SGB_THREADS
+#define SGB_THREADS 1024
+#endif
+constexpr int kThreads = SGB_THREADS; // threads per CTA (one CTA per SM: the map blob fills most of the shared memory)
 constexpr int kChunk = 8;            // polyline segments per bounding-box chunk
 constexpr int kExt = 6;              // extension points behind a centre line (3 short-term pts x interval 2)
 constexpr float kDistMargin = 1e-4f; // [m]  >> fp32 error of a point-segment distance (~3e-6)
@@ -296,7 +299,6 @@ struct TileSmem {
     float* car;                 // [4][A]: carry of the pre-step pose
     float* sc;                  // [8][A]: phase-B results: d_ref, idx(int), dLcg, dRcg, min4L, min4R, flags(int), spare
     float* dij;                 // [A][N] centre distances
-    float* obs;                 // [A][D]
     int* path;
     int* flags;
     int* env;                   // global env index of the slot (-1: inactive)
@@ -308,13 +310,14 @@ __device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, in
     t.px = f; f += A; t.py = f; f += A; t.ox = f; f += A; t.oy = f; f += A;
     t.cs = f; f += A; t.sn = f; f += A; t.vx = f; f += A; t.vy = f; f += A; t.vabs = f; f += A;
     t.vtx = f; f += 8 * A; t.car = f; f += 4 * A; t.sc = f; f += 8 * A;
-    t.dij = f; f += A * N; t.obs = f; f += A * D;
+    t.dij = f; f += A * N;
     t.path = reinterpret_cast<int*>(f); f += A; t.flags = reinterpret_cast<int*>(f); f += A;
     t.env = reinterpret_cast<int*>(f); f += A;
     t.coll = reinterpret_cast<int*>(f); f += A;
 }
 __host__ __device__ inline size_t tile_smem_bytes(int A, int N, int D) {
-    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 4) + (size_t)A * N + (size_t)A * D);
+    (void)D;
+    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 4) + (size_t)A * N);
 }
 
 // ---- phase B building blocks ------------------------------------------------------------------------------
@@ -336,28 +339,31 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
     Best b;
     b.init();
-    {
-        const int s1 = min(c0 * kChunk + kChunk, nseg);
-        for (int s = c0 * kChunk + lane; s < s1; s += G) {
-            float2 a = pts[s], e = pts[s + 1];
-            float lx = e.x - a.x, ly = e.y - a.y;
-            b.upd(seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py), s);
+    // Every lane takes two segments per iteration (s and s+G): two independent dependency chains in flight.
+    // When s+G runs past the chunk the index is clamped, i.e. a segment is evaluated twice — harmless for a min.
+    auto chunk = [&](int c) {
+        const int s1 = min(c * kChunk + kChunk, nseg);
+        for (int s = c * kChunk + lane; s < s1; s += 2 * G) {
+            const int s2 = min(s + G, s1 - 1);
+            const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
+            const float lx = e.x - a.x, ly = e.y - a.y, lx2 = e2.x - a2.x, ly2 = e2.y - a2.y;
+            const float q1 = seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py);
+            const float q2 = seg_q(a2.x, a2.y, lx2, ly2, lx2 * lx2 + ly2 * ly2, px, py);
+            b.upd(q1, s);
+            b.upd(q2, s2);
         }
-    }
+    };
+    chunk(c0);
     const float thr = group_min<G>(b.d) + kDistMargin;
     uint32_t m = 0;
     for (int c = lane; c < nch; c += G)
         if (c != c0 && (exhaustive || !(box_lb(boxes[c], px, py) > thr))) m |= 1u << c;
     m = group_or<G>(m);
+#pragma unroll 1
     while (m) {
         const int c = __ffs(m) - 1;
         m &= m - 1;
-        const int s1 = min(c * kChunk + kChunk, nseg);
-        for (int s = c * kChunk + lane; s < s1; s += G) {
-            float2 a = pts[s], e = pts[s + 1];
-            float lx = e.x - a.x, ly = e.y - a.y;
-            b.upd(seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py), s);
-        }
+        chunk(c);
     }
     // (d, idx) lexicographic min across the group == torch.min's first minimal index
     float d = b.d;
@@ -412,16 +418,22 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
             }
             if (!(need | (do_x ? 1u : 0u))) continue;
             const int s1 = min(c * kChunk + kChunk, nseg);
-            for (int s = c * kChunk + lane; s < s1; s += G) {
-                const float2 a = pts[s], e = pts[s + 1];
+            for (int s = c * kChunk + lane; s < s1; s += 2 * G) {
+                // two segments per lane-iteration (s, s+G): independent chains; a clamped duplicate is harmless
+                const int s2 = min(s + G, s1 - 1);
+                const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
                 if (need) {
                     const float lx = e.x - a.x, ly = e.y - a.y, rl = 1.0f / (lx * lx + ly * ly);
-                    if (need & 1u) bq[0].upd(seg_q_r(a.x, a.y, lx, ly, rl, px, py));
+                    const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, rl2 = 1.0f / (lx2 * lx2 + ly2 * ly2);
+                    if (need & 1u)
+                        bq[0].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, px, py), seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py)));
 #pragma unroll
                     for (int v = 0; v < 4; v++)
-                        if (need & (2u << v)) bq[v + 1].upd(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]));
+                        if (need & (2u << v))
+                            bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]),
+                                                seg_q_r(a2.x, a2.y, lx2, ly2, rl2, r.vx[v], r.vy[v])));
                 }
-                if (do_x) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y);
+                if (do_x) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y) | rect_cross_seg_L1(r, a2.x, a2.y, e2.x, e2.y);
             }
         }
         if (pass) break;
@@ -778,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 const float c_dref = ts.car[0 * AS + sl], c_mL = ts.car[1 * AS + sl], c_mR = ts.car[2 * AS + sl];
                 const int c_idx = __float_as_int(ts.car[3 * AS + sl]);
                 const bool write_obs = step_mode || p.write_obs;
-                float* o = ts.obs + (size_t)sl * D;
+                float* o = p.buf.obs + g * D;   // written in place: 128 B per agent, L2 merges the partial sectors
                 const float cs = ts.cs[sl], sn = ts.sn[sl];
                 const float2* cpts = pts + pr.c_off;
                 // What agent i's observation sees: after a reset everything is fresh; in a
@@ -894,7 +906,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         }
         __syncwarp();
 
-        // ================= phase D: per-env outputs + coalesced observation write-back ============
+        // ================= phase D: per-env outputs ===============================================
         if (step_mode && ln < n_slots && (ln % N) == 0 && ts.flags[slot0 + ln] >= 0) {
             const int st = slot0 + ln;
             const int e = ts.env[st];
@@ -905,24 +917,6 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             // road_traffic.py:1451-1457 (training mode)
             const bool dn = (step == cfg.max_steps - 1) || (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE));
             p.buf.done[e] = dn ? 1 : 0;
-        }
-        if (step_mode || p.write_obs) {
-            const int env_first = wt * EW;
-            const int n_env_w = min(EW, n_envs - env_first);
-            const int nf = n_env_w * N * D;                     // floats of this warp-tile
-            const float* src = ts.obs + (size_t)slot0 * D;
-            if (!p.env_list && ((nf & 3) == 0) && ((((size_t)env_first * N * D) & 3) == 0) && (((slot0 * D) & 3) == 0)) {
-                // the warp's envs are contiguous in HBM: one coalesced float4 stream
-                const float4* s4 = reinterpret_cast<const float4*>(src);
-                float4* d4 = reinterpret_cast<float4*>(p.buf.obs + (size_t)env_first * N * D);
-                for (int k = ln; k < nf / 4; k += 32) d4[k] = s4[k];
-            } else {
-                const int ND = N * D;
-                for (int k = ln; k < nf; k += 32) {
-                    const int el = k / ND;                      // env within the warp-tile
-                    p.buf.obs[(size_t)ts.env[slot0 + el * N] * ND + (k - el * ND)] = src[k];
-                }
-            }
         }
         __syncwarp();
     }

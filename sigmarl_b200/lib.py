@@ -57,7 +57,7 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(HERE, _LIB_NAME)
+    return os.environ.get("SGB_LIBRARY", os.path.join(HERE, _LIB_NAME))
 
 
 def load_library():
