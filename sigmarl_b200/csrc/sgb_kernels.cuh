@@ -158,6 +158,13 @@ __device__ __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly,
     return ex * ex + ey * ey;
 }
 
+// 1/x with MUFU.RCP (<= 1 ulp): only used where the result feeds continuous outputs
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // distance from a point to an axis-aligned box (lower bound for every polyline point inside it)
 __device__ __forceinline__ float box_lb2(float4 bx, float px, float py) {
     float dx = fmaxf(fmaxf(bx.x - px, px - bx.z), 0.0f);
@@ -395,6 +402,16 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
 #pragma unroll
     for (int v = 0; v < 5; v++) bq[v].init();
     bool hit = false;
+    float gq_pt[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; // group-wide best q per point after the hint chunk
+    const uint32_t gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
+    float myvx[(4 + G - 1) / G], myvy[(4 + G - 1) / G], myq[(4 + G - 1) / G];
+#pragma unroll
+    for (int k = 0; k < (4 + G - 1) / G; k++) {         // select without dynamic register indexing
+        const int v = lane + k * G;
+        myvx[k] = v == 0 ? r.vx[0] : (v == 1 ? r.vx[1] : (v == 2 ? r.vx[2] : r.vx[3]));
+        myvy[k] = v == 0 ? r.vy[0] : (v == 1 ? r.vy[1] : (v == 2 ? r.vy[2] : r.vy[3]));
+        myq[k] = 0.0f;
+    }
     uint32_t md = 1u << c0, mx = 1u << c0;
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
@@ -408,12 +425,19 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
             if ((md >> c) & 1u) {
                 need = 31u;
                 if (pass && !exhaustive) {
-                    // per-point refinement of the coarse vote: which of the 5 points can still improve in this box
+                    // per-point refinement of the coarse vote: which of the 5 points can still improve in this box.
+                    // The lanes of the group share the test (lane v takes vertex v, lane 0 also the centre) against
+                    // the GROUP-wide best, then OR their bits: one box distance per lane instead of five.
                     const float4 bx = boxes[c];
-                    need = bq[0].box_useless(box_lb2(bx, px, py)) ? 0u : 1u;
+                    need = 0;
 #pragma unroll
-                    for (int v = 0; v < 4; v++)
-                        if (!bq[v + 1].box_useless(box_lb2(bx, r.vx[v], r.vy[v]))) need |= 2u << v;
+                    for (int k = 0; k < (4 + G - 1) / G; k++)   // this lane's vertices: lane, lane+G, ...
+                        if (lane + k * G < 4 && !(box_lb2(bx, myvx[k], myvy[k]) > myq[k] * 1.01f + 1e-7f))
+                            need |= 2u << (lane + k * G);
+                    if (lane == 0 && !(box_lb2(bx, px, py) > gq_pt[0] * 1.01f + 1e-7f)) need |= 1u;
+                    // the groups of a warp sit in different iterations here: shuffle within the group's own lanes
+#pragma unroll
+                    for (int k = 1; k < G; k <<= 1) need |= __shfl_xor_sync(gmask, need, k);
                 }
             }
             if (!(need | (do_x ? 1u : 0u))) continue;
@@ -423,8 +447,8 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                 const int s2 = min(s + G, s1 - 1);
                 const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
                 if (need) {
-                    const float lx = e.x - a.x, ly = e.y - a.y, rl = 1.0f / (lx * lx + ly * ly);
-                    const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, rl2 = 1.0f / (lx2 * lx2 + ly2 * ly2);
+                    const float lx = e.x - a.x, ly = e.y - a.y, rl = rcp_fast(lx * lx + ly * ly);
+                    const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, rl2 = rcp_fast(lx2 * lx2 + ly2 * ly2);
                     if (need & 1u)
                         bq[0].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, px, py), seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py)));
 #pragma unroll
@@ -439,9 +463,16 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
         if (pass) break;
         // group-wide bound (lanes that got no segment of the hint chunk hold +inf): every point is within
         // rect_radius of the centre, so a chunk can matter for some point only if lb(centre) <= max best + radius
-        float gq = group_min<G>(bq[0].q);
 #pragma unroll
-        for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
+        for (int v = 0; v < 5; v++) gq_pt[v] = group_min<G>(bq[v].q);
+        float gq = gq_pt[0];
+#pragma unroll
+        for (int v = 1; v < 5; v++) gq = fmaxf(gq, gq_pt[v]);
+#pragma unroll
+        for (int k = 0; k < (4 + G - 1) / G; k++) {
+            const int v = lane + k * G;
+            myq[k] = v == 0 ? gq_pt[1] : (v == 1 ? gq_pt[2] : (v == 2 ? gq_pt[3] : gq_pt[4]));
+        }
         float thr = sqrtf(gq) + rect_radius + kDistMargin;
         thr = thr * thr;
         md = 0; mx = 0;

@@ -357,12 +357,18 @@ def test_config4_maps_pruned_equals_exhaustive_at_scale(scenario, N, B):
                                      exhaustive=ex), num_envs=B, device="cuda:0", seed=21) for ex in (False, True)]
     for e in envs:
         e.reset()
-    assert int(envs[0].n_failed.item()) == 0
+    # sequential rejection sampling without backtracking can dead-end at N = 12 (the reference would spin forever,
+    # SURVEY.md §4); the bounded device reset reports those instead — they must stay rare
+    assert int(envs[0].n_failed.item()) <= 0.002 * B * N
     g = torch.Generator(device="cuda").manual_seed(5)
     n_exit = 0
     for t in range(40):
-        act = torch.stack([0.5 + 0.4 * torch.rand(B, N, device="cuda", generator=g),
-                           (torch.rand(B, N, device="cuda", generator=g) - 0.5) * 0.2], -1)
+        # pure pursuit on the 2nd short-term reference point of the ego-frame observation (obs[3:5]) so that agents
+        # actually travel to their path ends; both envs hold identical observations, so the actions are identical
+        o = envs[0].obs
+        steer = torch.clamp(1.5 * torch.atan2(o[..., 4], o[..., 3]) + (torch.rand(B, N, device="cuda", generator=g) - 0.5) * 0.06,
+                            -float(UR[1]), float(UR[1]))
+        act = torch.stack([0.6 + 0.4 * torch.rand(B, N, device="cuda", generator=g), steer], -1)
         for e in envs:
             e.step(act)
         for name in ("pose", "aux", "carry", "obs", "reward", "done", "agent_flags", "collide_with"):
@@ -370,8 +376,8 @@ def test_config4_maps_pruned_equals_exhaustive_at_scale(scenario, N, B):
         n_exit += int(((envs[0].agent_flags & 8) != 0).sum())
         assert torch.isfinite(envs[0].obs).all()
         for e in envs:
-            e.reset_done()
-        assert torch.equal(envs[0].pose, envs[1].pose)
+            e.reset_done(write_obs=True)
+        assert torch.equal(envs[0].pose, envs[1].pose) and torch.equal(envs[0].obs, envs[1].obs)
     assert n_exit > 0, "no agent ever reached its path end: the respawn branch was not exercised"
 
 
