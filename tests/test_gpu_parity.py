@@ -387,13 +387,14 @@ def test_facade_done_respawns_exit_crossers_like_reference_flow():
     """VMAS order through the facade: done() must respawn entry/exit crossers of not-done envs (road_traffic.py:1462-1472)
     and leave done envs to the caller's reset_at."""
     from sigmarl_b200 import make_env
-    env = make_env(scenario_type="cpm_mixed", num_envs=512, device="cuda:0", n_agents=4, seed=9, max_steps=128)
+    env = make_env(scenario_type="cpm_mixed", num_envs=512, device="cuda:0", n_agents=4, seed=9, max_steps=128, dt=0.1)
     sc = env.scenario
     g = torch.Generator(device="cuda").manual_seed(2)
     respawned = 0
-    for t in range(60):
-        acts = [torch.stack([0.6 + 0.3 * torch.rand(512, device="cuda", generator=g),
-                             (torch.rand(512, device="cuda", generator=g) - 0.5) * 0.1], -1) for _ in range(4)]
+    for t in range(80):
+        o = sc.env.obs   # pure pursuit on the 2nd short-term point so that agents reach their path ends
+        steer = torch.clamp(1.5 * torch.atan2(o[..., 4], o[..., 3]), -float(UR[1]), float(UR[1]))
+        acts = [torch.stack([0.6 + 0.3 * torch.rand(512, device="cuda", generator=g), steer[:, i]], -1) for i in range(4)]
         for a, agent in zip(acts, env.agents):
             agent.action.u = a
         sc.world.step()
@@ -408,5 +409,5 @@ def test_facade_done_respawns_exit_crossers_like_reference_flow():
         respawned += int(crossing.sum())
         for e in torch.where(dones)[0].tolist()[:8]:
             env.reset_at(e)
-        sc.env.reset_done()  # remaining done envs in one launch
+        sc.env.reset_done(write_obs=True)  # remaining done envs in one launch
     assert respawned > 0
