@@ -10,9 +10,10 @@
 //                                   agents of the env, k-nearest selection, reward, observation -> smem
 //   phase D  one lane per env     : done flag, step counter
 //
-// Arithmetic contract (see DESIGN.md "Exactness"): this translation unit is compiled with
-// -fmad=false, IEEE sqrt/div, no fast-math; every value that feeds an argmin or a strict-sign
-// collision predicate is evaluated with the reference's operation order
+// Arithmetic contract (see DESIGN.md "Exactness"): IEEE sqrt/div, no fast-math.  FMA contraction is
+// left ON for the compiler, but every value that feeds an argmin, a strict-sign collision predicate
+// or the integrated state is written with never-contracted __fmul_rn/__fadd_rn/__fsub_rn in the
+// reference's operation order
 // (helper_scenario.py:829-889, :1148-1229), so those decisions are bit-identical to the reference
 // given the same inputs.  Pruning never changes a result: distance chunks are skipped only when a
 // lower bound exceeds the running best by a margin 30x larger than the fp32 evaluation error, and
@@ -92,6 +93,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
         : "memory");
 }
 
+// Separately-rounded fp32 operations (never contracted into FMA).  The file is compiled with FMA contraction ON;
+// every value that feeds an argmin, a strict-sign predicate or the integrated state is written with these so
+// that it rounds exactly like the reference's one-ATen-op-at-a-time evaluation.
+__device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
+// a*b - c*d and a*b + c*d with three roundings
+__device__ __forceinline__ float msub2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+__device__ __forceinline__ float madd2(float a, float b, float c, float d) { return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+
 __device__ __noinline__ void sincos_ool(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
 __device__ __noinline__ float tan_ool(float x) { return tanf(x); }
 __device__ __noinline__ float atan_ool(float x) { return atanf(x); }
@@ -140,12 +151,12 @@ struct BestQ {
 // squared point-segment distance, operation order of helper_scenario.py:856-871 (IEEE division): used for the
 // centre line, whose argmin must be bit-identical to the reference
 __device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, float len2, float px, float py) {
-    float vx = px - ax, vy = py - ay;
-    float t = (vx * lx + vy * ly) / len2;
+    const float vx = subr(px, ax), vy = subr(py, ay);
+    float t = madd2(vx, lx, vy, ly) / len2;
     t = clampf(t, 0.0f, 1.0f);
-    float cx = ax + lx * t, cy = ay + ly * t;
-    float ex = cx - px, ey = cy - py;
-    return ex * ex + ey * ey;
+    const float cx = addr(ax, mulr(lx, t)), cy = addr(ay, mulr(ly, t));
+    const float ex = subr(cx, px), ey = subr(cy, py);
+    return madd2(ex, ex, ey, ey);
 }
 // same with the projection parameter computed as dot * (1/len2): t differs from the reference's quotient by
 // <= 1.5 ulp, i.e. the distance by ~1e-8 m.  Used for the boundaries only (one reciprocal shared by 5 points).
@@ -186,7 +197,7 @@ struct Rect {
             int j = (i + 1) & 3;
             dx[i] = vx[j] - vx[i];
             dy[i] = vy[j] - vy[i];
-            S[i] = dx[i] * vy[i] - dy[i] * vx[i];
+            S[i] = msub2(dx[i], vy[i], dy[i], vx[i]);
         }
     }
 };
@@ -195,21 +206,21 @@ struct Rect {
 // vertices lie strictly on one side of (or on) the segment's line no edge can cross it, and the four C1 terms
 // are skipped (same values as the reference would compute, just not evaluated).
 __device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by) {
-    float dx2 = bx - ax, dy2 = by - ay;
-    float S2 = dx2 * ay - dy2 * ax;
+    const float dx2 = bx - ax, dy2 = by - ay;
+    const float S2 = msub2(dx2, ay, dy2, ax);
     {
         // g(v) = fl(fl(fl(vy*dx2) - fl(vx*dy2)) - S2) is monotone in vy and in vx (every IEEE operation is
         // monotone), so its extremes over the rectangle's bounding box are attained at two box corners.  If
         // both have the same strict sign, all four g[i] have it too (bit-exactly) and no C2 term can be true.
         const float ya = dx2 >= 0.0f ? r.y1 : r.y0, yb = dx2 >= 0.0f ? r.y0 : r.y1;
         const float xa = dy2 >= 0.0f ? r.x0 : r.x1, xb = dy2 >= 0.0f ? r.x1 : r.x0;
-        const float gmax = (ya * dx2 - xa * dy2) - S2;
-        const float gmin = (yb * dx2 - xb * dy2) - S2;
+        const float gmax = subr(msub2(ya, dx2, xa, dy2), S2);
+        const float gmin = subr(msub2(yb, dx2, xb, dy2), S2);
         if (gmin > 0.0f || gmax < 0.0f) return false;
     }
     float g[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) g[i] = (r.vy[i] * dx2 - r.vx[i] * dy2) - S2;
+    for (int i = 0; i < 4; i++) g[i] = subr(msub2(r.vy[i], dx2, r.vx[i], dy2), S2);
     bool c2[4];
     bool any2 = false;
 #pragma unroll
@@ -218,8 +229,8 @@ __device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        float fa = (r.dx[i] * ay - r.dy[i] * ax) - r.S[i];
-        float fb = (r.dx[i] * by - r.dy[i] * bx) - r.S[i];
+        const float fa = subr(msub2(r.dx[i], ay, r.dy[i], ax), r.S[i]);
+        const float fb = subr(msub2(r.dx[i], by, r.dy[i], bx), r.S[i]);
         hit |= (((fa * fb) < 0.0f) & c2[i]);
     }
     return hit;
@@ -233,7 +244,7 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
     for (int i = 0; i < 4; i++) {
         float f[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) f[j] = (lo.dx[i] * hy[j] - lo.dy[i] * hx[j]) - lo.S[i];
+        for (int j = 0; j < 4; j++) f[j] = subr(msub2(lo.dx[i], hy[j], lo.dy[i], hx[j]), lo.S[i]);
 #pragma unroll
         for (int j = 0; j < 4; j++) c1 |= ((f[j] * f[(j + 1) & 3]) < 0.0f) ? (1u << (4 * i + j)) : 0u;
     }
@@ -242,11 +253,11 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int jn = (j + 1) & 3;
-        float dx2 = hx[jn] - hx[j], dy2 = hy[jn] - hy[j];
-        float S2 = dx2 * hy[j] - dy2 * hx[j];
+        const float dx2 = hx[jn] - hx[j], dy2 = hy[jn] - hy[j];
+        const float S2 = msub2(dx2, hy[j], dy2, hx[j]);
         float g[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) g[i] = (lo.vy[i] * dx2 - lo.vx[i] * dy2) - S2;
+        for (int i = 0; i < 4; i++) g[i] = subr(msub2(lo.vy[i], dx2, lo.vx[i], dy2), S2);
 #pragma unroll
         for (int i = 0; i < 4; i++) hit |= (((g[i] * g[(i + 1) & 3]) < 0.0f) & (((c1 >> (4 * i + j)) & 1u) != 0u));
     }
@@ -354,8 +365,8 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
             const int s2 = min(s + G, s1 - 1);
             const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
             const float lx = e.x - a.x, ly = e.y - a.y, lx2 = e2.x - a2.x, ly2 = e2.y - a2.y;
-            const float q1 = seg_q(a.x, a.y, lx, ly, lx * lx + ly * ly, px, py);
-            const float q2 = seg_q(a2.x, a2.y, lx2, ly2, lx2 * lx2 + ly2 * ly2, px, py);
+            const float q1 = seg_q(a.x, a.y, lx, ly, madd2(lx, lx, ly, ly), px, py);
+            const float q2 = seg_q(a2.x, a2.y, lx2, ly2, madd2(lx2, lx2, ly2, ly2), px, py);
             b.upd(q1, s);
             b.upd(q2, s2);
         }
@@ -600,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     float rate = clampf((u.y - delta) / cfg.dt, -cfg.max_steering_rate, cfg.max_steering_rate);
                     // dynamics.py:62-118 + fixed-grid Euler (torchdiffeq)
                     float td = tan_ool(delta);
-                    float beta = atan_ool(cfg.lr_over_lwb * td);
+                    float beta = atan_ool(mulr(cfg.lr_over_lwb, td));
                     float sb, cb;
                     sincos_ool(psi + beta, &sb, &cb);
                     float f0 = v * cb, f1 = v * sb;
@@ -615,10 +626,10 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     const float pi_f = 3.14159274101257324f, two_pi = 6.28318548202514648f;
                     delta = pymod(delta + pi_f, two_pi) - pi_f; // dynamics.py:158
                 }
-                const float beta1 = atan_ool(cfg.lr_over_lwb * tan_ool(delta));   // dynamics.py:161-163
+                const float beta1 = atan_ool(mulr(cfg.lr_over_lwb, tan_ool(delta)));   // dynamics.py:161-163
                 float sc_, cc_;
                 sincos_ool(psi + beta1, &sc_, &cc_);
-                float vx = v * cc_, vy = v * sc_;
+                float vx = mulr(v, cc_), vy = mulr(v, sc_);
                 reinterpret_cast<float4*>(p.buf.pose)[g] = make_float4(x, y, psi, v);
                 reinterpret_cast<float4*>(p.buf.aux)[g] = make_float4(delta, vx, vy, beta1);
                 // helper_scenario.py:742-826 rectangle vertices
@@ -630,11 +641,11 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 const float bys[4] = {hw, -hw, -hw, hw};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
-                    ts.vtx[k * AS + st] = (cy * bxs[k] + nsy * bys[k]) + x;
-                    ts.vtx[(4 + k) * AS + st] = (sy * bxs[k] + cy * bys[k]) + y;
+                    ts.vtx[k * AS + st] = addr(madd2(cy, bxs[k], nsy, bys[k]), x);
+                    ts.vtx[(4 + k) * AS + st] = addr(madd2(sy, bxs[k], cy, bys[k]), y);
                 }
                 ts.px[st] = x; ts.py[st] = y; ts.cs[st] = cy; ts.sn[st] = sy;
-                ts.vx[st] = vx; ts.vy[st] = vy; ts.vabs[st] = sqrtf(vx * vx + vy * vy);
+                ts.vx[st] = vx; ts.vy[st] = vy; ts.vabs[st] = sqrtf(madd2(vx, vx, vy, vy));
                 ts.car[0 * AS + st] = car.x; ts.car[1 * AS + st] = car.y;
                 ts.car[2 * AS + st] = car.z; ts.car[3 * AS + st] = car.w;
                 ts.path[st] = p.buf.path_id[g];
@@ -760,8 +771,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 for (int j = lane; j < N; j += G) {
                     const int sj = base + j;
                     const float pjx = ts.px[sj], pjy = ts.py[sj];
-                    float dx = pix - pjx, dy = piy - pjy;
-                    float pp = dx * dx + dy * dy;
+                    const float dx = pix - pjx, dy = piy - pjy;
+                    const float pp = madd2(dx, dx, dy, dy);
                     float dist = (j == i) ? cfg.diag : sqrtf(pp);  // helper_scenario.py:1012-1029, :1140-1143
                     ts.dij[sl * N + j] = dist;
                     if (!step_mode) continue;
@@ -769,17 +780,17 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     if (cfg.rew_flags & SGB_REW_TTC) {
                         // road_traffic.py:1255-1332 (p_rel = p_j - p_i)
                         const float eps = 1e-6f;
-                        float rx = pjx - pix, ry = pjy - piy;
-                        float wx = ts.vx[sj] - ts.vx[sl], wy = ts.vy[sj] - ts.vy[sl];
-                        float qa = wx * wx + wy * wy;
-                        float qb = 2.0f * (rx * wx + ry * wy);
-                        float rr = rx * rx + ry * ry;
-                        float qc = rr - cfg.dsafe_sq;
-                        float disc = qb * qb - (4.0f * qa) * qc;
-                        float sq = sqrtf(fmaxf(disc, 0.0f));
-                        float dd = sqrtf(fmaxf(rr, 0.0f));
-                        bool valid = (qa > eps) && (disc > 0.0f) && (qb < 0.0f);
-                        float cand = (-qb - sq) / (2.0f * qa + eps);
+                        const float rx = pjx - pix, ry = pjy - piy;
+                        const float wx = ts.vx[sj] - ts.vx[sl], wy = ts.vy[sj] - ts.vy[sl];
+                        const float qa = madd2(wx, wx, wy, wy);
+                        const float qb = mulr(2.0f, madd2(rx, wx, ry, wy));
+                        const float rr = madd2(rx, rx, ry, ry);
+                        const float qc = subr(rr, cfg.dsafe_sq);
+                        const float disc = subr(mulr(qb, qb), mulr(mulr(4.0f, qa), qc));
+                        const float sq = sqrtf(fmaxf(disc, 0.0f));
+                        const float dd = sqrtf(fmaxf(rr, 0.0f));
+                        const bool valid = (qa > eps) && (disc > 0.0f) && (qb < 0.0f);
+                        const float cand = subr(-qb, sq) / addr(mulr(2.0f, qa), eps);
                         float ttc = __int_as_float(0x7f800000);
                         if (valid && cand > 0.0f) ttc = cand;
                         if (dd <= cfg.near_agents_low) ttc = 0.0f;
@@ -1057,7 +1068,7 @@ __global__ void reset_kernel(const ResetParams p) {
             for (int o = 0; o < lim; o++) {
                 if (o == a) continue;
                 float dx = c.x - qx[o], dy = c.y - qy[o];
-                if (!((dx * dx + dy * dy) >= p.cfg.reset_min_dist_sq)) { ok = false; break; }
+                if (!(madd2(dx, dx, dy, dy) >= p.cfg.reset_min_dist_sq)) { ok = false; break; }
             }
             if (ok) { qx[a] = c.x; qy[a] = c.y; }
         }
