@@ -188,10 +188,12 @@ __device__ __forceinline__ float box_lb(float4 bx, float px, float py) { return 
 struct Rect {
     float vx[4], vy[4];    // vertices 0..3 (vertex 4 == vertex 0)
     float dx[4], dy[4], S[4]; // per edge i: v[i] -> v[i+1]
-    float x0, x1, y0, y1;  // axis-aligned bounding box of the four vertices
+    float bcx, bcy, bhx, bhy; // centre and half extents of the axis-aligned bounding box of the four vertices
     __device__ __forceinline__ void finish() {
-        x0 = fminf(fminf(vx[0], vx[1]), fminf(vx[2], vx[3])); x1 = fmaxf(fmaxf(vx[0], vx[1]), fmaxf(vx[2], vx[3]));
-        y0 = fminf(fminf(vy[0], vy[1]), fminf(vy[2], vy[3])); y1 = fmaxf(fmaxf(vy[0], vy[1]), fmaxf(vy[2], vy[3]));
+        const float x0 = fminf(fminf(vx[0], vx[1]), fminf(vx[2], vx[3])), x1 = fmaxf(fmaxf(vx[0], vx[1]), fmaxf(vx[2], vx[3]));
+        const float y0 = fminf(fminf(vy[0], vy[1]), fminf(vy[2], vy[3])), y1 = fmaxf(fmaxf(vy[0], vy[1]), fmaxf(vy[2], vy[3]));
+        bcx = 0.5f * (x0 + x1); bcy = 0.5f * (y0 + y1);
+        bhx = 0.5f * (x1 - x0) + 1e-6f; bhy = 0.5f * (y1 - y0) + 1e-6f;   // + rounding slack of the centre
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             int j = (i + 1) & 3;
@@ -207,17 +209,14 @@ struct Rect {
 // are skipped (same values as the reference would compute, just not evaluated).
 __device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by) {
     const float dx2 = bx - ax, dy2 = by - ay;
-    const float S2 = msub2(dx2, ay, dy2, ax);
     {
-        // g(v) = fl(fl(fl(vy*dx2) - fl(vx*dy2)) - S2) is monotone in vy and in vx (every IEEE operation is
-        // monotone), so its extremes over the rectangle's bounding box are attained at two box corners.  If
-        // both have the same strict sign, all four g[i] have it too (bit-exactly) and no C2 term can be true.
-        const float ya = dx2 >= 0.0f ? r.y1 : r.y0, yb = dx2 >= 0.0f ? r.y0 : r.y1;
-        const float xa = dy2 >= 0.0f ? r.x0 : r.x1, xb = dy2 >= 0.0f ? r.x1 : r.x0;
-        const float gmax = subr(msub2(ya, dx2, xa, dy2), S2);
-        const float gmin = subr(msub2(yb, dx2, xb, dy2), S2);
-        if (gmin > 0.0f || gmax < 0.0f) return false;
+        // Cheapest filter first (fused arithmetic, certified by a margin): g at the bounding-box centre, and the
+        // largest change of g over the box.  |g(c)| - (|dx2| hy + |dy2| hx) > 1e-5 >> fp32 error of g (~3e-7)
+        // => all four vertices are strictly on one side of the segment's line => no C2 term can be true.
+        const float gc = dx2 * (r.bcy - ay) - dy2 * (r.bcx - ax);
+        if (fabsf(gc) > fabsf(dx2) * r.bhy + fabsf(dy2) * r.bhx + 1e-5f) return false;
     }
+    const float S2 = msub2(dx2, ay, dy2, ax);
     float g[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) g[i] = subr(msub2(r.vy[i], dx2, r.vx[i], dy2), S2);
