@@ -79,6 +79,34 @@ void add_boxes(std::vector<float>& boxes, const float* xy, int n_pts) {
     }
 }
 
+// Direction cone of a chunk's segments as undirected lines (angles mod pi): mid angle and half width, widened by
+// asin(kCollinear) + the fp16 storage error.  A far segment can only fire interX through fp32 noise if it is
+// collinear with an edge of the rectangle within kCollinear (sgb_kernels.cuh), so a chunk whose cone contains
+// neither the heading nor its normal holds no such segment.  half >= pi/2 means "always test".
+void add_cones(std::vector<__half2>& cones, const float* xy, int n_pts) {
+    const double PI = 3.14159265358979323846;
+    const int nseg = n_pts - 1;
+    for (int s0 = 0; s0 < nseg; s0 += kChunk) {
+        const int s1 = std::min(s0 + kChunk, nseg);
+        double a0 = 0.0, lo = 0.0, hi = 0.0;
+        for (int k = s0; k < s1; k++) {
+            const double a = std::atan2((double)xy[2 * k + 3] - xy[2 * k + 1], (double)xy[2 * k + 2] - xy[2 * k]);
+            if (k == s0) { a0 = a; continue; }
+            double rel = std::fmod(a - a0, PI);          // (-pi, pi)
+            if (rel > PI / 2) rel -= PI;
+            if (rel <= -PI / 2) rel += PI;                // (-pi/2, pi/2]
+            lo = std::min(lo, rel); hi = std::max(hi, rel);
+        }
+        double half = 0.5 * (hi - lo), mid = a0 + 0.5 * (hi + lo);
+        // a chunk that turns by more than ~80 degrees may not unwrap uniquely: always test it
+        if (hi - lo > 1.4) half = 4.0;
+        else half += std::asin((double)kCollinear) + 4e-3;  // + fp16 rounding of mid (<= 1e-3) and half, fp32 psi mod pi
+        mid = std::fmod(mid, PI);
+        if (mid < 0) mid += PI;
+        cones.push_back(__halves2half2(__float2half_rn((float)mid), __float2half_rn((float)half)));
+    }
+}
+
 bool degenerate(const float* xy, int n) {
     if (n < 2) return true;
     for (int s = 0; s + 1 < n; s++)
@@ -93,6 +121,7 @@ int pack_map(const sgb_map_desc* m, Packed& out) {
     const int n = m->n_paths;
     std::vector<PathRec> recs(n);
     std::vector<float> pts, boxes;
+    std::vector<__half2> cones;
     out.yaw.clear();
     int yaw_in = 0;
     for (int i = 0; i < n; i++) {
@@ -132,11 +161,15 @@ int pack_map(const sgb_map_desc* m, Packed& out) {
         r.n_l = nl;
         r.lbox = (int)(boxes.size() / 4);
         add_boxes(boxes, l, nl);
+        r.lcone = (int)cones.size();
+        add_cones(cones, l, nl);
         pts.insert(pts.end(), l, l + 2 * nl);
         r.r_off = (int)(pts.size() / 2);
         r.n_r = nr;
         r.rbox = (int)(boxes.size() / 4);
         add_boxes(boxes, rr, nr);
+        r.rcone = (int)cones.size();
+        add_cones(cones, rr, nr);
         pts.insert(pts.end(), rr, rr + 2 * nr);
     }
     // yaw must be indexable by (c_off + point): rebuild it on the blob's point numbering
@@ -155,12 +188,14 @@ int pack_map(const sgb_map_desc* m, Packed& out) {
     h.path_off = (int32_t)align16(sizeof(BlobHeader));
     h.pts_off = (int32_t)align16(h.path_off + sizeof(PathRec) * n);
     h.box_off = (int32_t)align16(h.pts_off + sizeof(float) * pts.size());
-    h.total_bytes = (int32_t)align16(h.box_off + sizeof(float) * boxes.size());
+    h.cone_off = (int32_t)align16(h.box_off + sizeof(float) * boxes.size());
+    h.total_bytes = (int32_t)align16(h.cone_off + sizeof(__half2) * cones.size());
     out.blob.assign(h.total_bytes, 0);
     std::memcpy(out.blob.data(), &h, sizeof h);
     std::memcpy(out.blob.data() + h.path_off, recs.data(), sizeof(PathRec) * n);
     std::memcpy(out.blob.data() + h.pts_off, pts.data(), sizeof(float) * pts.size());
     std::memcpy(out.blob.data() + h.box_off, boxes.data(), sizeof(float) * boxes.size());
+    std::memcpy(out.blob.data() + h.cone_off, cones.data(), sizeof(__half2) * cones.size());
     return SGB_OK;
 }
 

@@ -19,6 +19,7 @@
 // lower bound exceeds the running best by a margin 30x larger than the fp32 evaluation error, and
 // crossing tests are skipped only when every edge-line sign is certified with a margin.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -34,6 +35,12 @@ constexpr int kChunk = 8;            // polyline segments per bounding-box chunk
 constexpr int kExt = 6;              // extension points behind a centre line (3 short-term pts x interval 2)
 constexpr float kDistMargin = 1e-4f; // [m]  >> fp32 error of a point-segment distance (~3e-6)
 constexpr float kSignMargin = 1e-4f; // [m^2] >> fp32 error of an edge-line sign function (~6e-6)
+// Crossing tests against FAR segments (DESIGN.md "Exactness"): a segment whose distance to the rectangle exceeds
+// kFarMargin cannot truly cross it, and interX can only fire on it through fp32 sign noise, which needs the
+// segment's line and an edge's line to be collinear within (eps_i + eps_j) / kFarMargin ~ 2e-3 rad (eps ~ 1e-5 m =
+// evaluation error of a line function / its gradient).  kCollinear is 5x that bound.
+constexpr float kFarMargin = 0.01f;  // [m]
+constexpr float kCollinear = 0.01f;  // |sin(angle between segment and edge direction)|
 
 // ---- packed map blob (global memory -> shared memory, byte-identical) ---------------------------------
 struct BlobHeader {      // 32 bytes
@@ -42,7 +49,8 @@ struct BlobHeader {      // 32 bytes
     int32_t pts_off;
     int32_t box_off;
     int32_t total_bytes; // multiple of 16
-    int32_t pad[3];
+    int32_t cone_off;    // half2 (mid angle mod pi, half width incl. slack) per BOUNDARY chunk
+    int32_t pad[2];
 };
 struct PathRec {         // 48 bytes; point offsets in float2 units, box offsets in float4 units
     int32_t c_off, n_c;  // centre line: n_c real points followed by kExt extension points
@@ -50,7 +58,7 @@ struct PathRec {         // 48 bytes; point offsets in float2 units, box offsets
     int32_t r_off, n_r;
     int32_t cbox, lbox, rbox;
     int32_t is_loop;
-    int32_t pad[2];
+    int32_t lcone, rcone; // cone offsets (half2 units) of the left / right boundary chunks
 };
 
 struct Params {
@@ -66,6 +74,7 @@ struct Params {
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------------
+// @region small helpers (msub2 etc.)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -126,6 +135,7 @@ __device__ __forceinline__ float dec_lin(float x, float x0, float x1) {
 // order (the hint chunk is scanned first): a candidate wins if d is smaller, or equal with a smaller index.
 // sqrt is monotone, so min d = sqrt(min q); distinct q within ~1.2e-7 relative can round to the same d, hence
 // the exact (d, idx) comparison runs for every q <= qmin * (1 + 5e-7) and is skipped (no sqrt) otherwise.
+// @region Best (centre argmin)
 struct Best {
     float qmin, qlim, d;
     int idx;
@@ -140,6 +150,7 @@ struct Best {
 };
 // boundary distances feed only continuous outputs (observation / reward, 1e-5 tolerance), never an argmin
 // or a predicate, so they are tracked as min q = min d^2 and square-rooted once: min sqrt(q) == sqrt(min q).
+// @region BestQ
 struct BestQ {
     float q;
     __device__ __forceinline__ void init() { q = __int_as_float(0x7f800000); }
@@ -148,7 +159,7 @@ struct BestQ {
     __device__ __forceinline__ bool box_useless(float lb2) const { return lb2 > q * 1.01f + 1e-7f; }
 };
 
-// squared point-segment distance, operation order of helper_scenario.py:856-871 (IEEE division): used for the
+// squared point-segment distance, operation order of helper_scenario.py:856-871 (IEEE division): used for the  @region seg_q exact (centre)
 // centre line, whose argmin must be bit-identical to the reference
 __device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, float len2, float px, float py) {
     const float vx = subr(px, ax), vy = subr(py, ay);
@@ -158,7 +169,7 @@ __device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, f
     const float ex = subr(cx, px), ey = subr(cy, py);
     return madd2(ex, ex, ey, ey);
 }
-// same with the projection parameter computed as dot * (1/len2): t differs from the reference's quotient by
+// same with the projection parameter computed as dot * (1/len2): t differs from the reference's quotient by  @region seg_q_r (boundary)
 // <= 1.5 ulp, i.e. the distance by ~1e-8 m.  Used for the boundaries only (one reciprocal shared by 5 points).
 __device__ __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly, float rlen2, float px, float py) {
     float vx = px - ax, vy = py - ay;
@@ -169,7 +180,7 @@ __device__ __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly,
     return ex * ex + ey * ey;
 }
 
-// 1/x with MUFU.RCP (<= 1 ulp): only used where the result feeds continuous outputs
+// 1/x with MUFU.RCP (<= 1 ulp): only used where the result feeds continuous outputs  @region rcp/box_lb
 __device__ __forceinline__ float rcp_fast(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -184,7 +195,7 @@ __device__ __forceinline__ float box_lb2(float4 bx, float px, float py) {
 }
 __device__ __forceinline__ float box_lb(float4 bx, float px, float py) { return sqrtf(box_lb2(bx, px, py)); }
 
-// The agent's rectangle as interX sees it (helper_scenario.py:1148-1229): closed 5-vertex polyline.
+// The agent's rectangle as interX sees it (helper_scenario.py:1148-1229): closed 5-vertex polyline.  @region Rect.finish
 struct Rect {
     float vx[4], vy[4];    // vertices 0..3 (vertex 4 == vertex 0)
     float dx[4], dy[4], S[4]; // per edge i: v[i] -> v[i+1]
@@ -204,12 +215,13 @@ struct Rect {
     }
 };
 
-// interX of the rectangle (as L1) against ONE segment a->b of L2; exact predicate.  C2 first: when all four
+// interX of the rectangle (as L1) against ONE segment a->b of L2; exact predicate.  C2 first: when all four  @region rect_cross_seg_L1
 // vertices lie strictly on one side of (or on) the segment's line no edge can cross it, and the four C1 terms
 // are skipped (same values as the reference would compute, just not evaluated).
-__device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by) {
+__device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by,
+                                                  bool no_filter = false) {
     const float dx2 = bx - ax, dy2 = by - ay;
-    {
+    if (!no_filter) {
         // Cheapest filter first (fused arithmetic, certified by a margin): g at the bounding-box centre, and the
         // largest change of g over the box.  |g(c)| - (|dx2| hy + |dy2| hx) > 1e-5 >> fp32 error of g (~3e-7)
         // => all four vertices are strictly on one side of the segment's line => no C2 term can be true.
@@ -235,7 +247,7 @@ __device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float
     return hit;
 }
 
-// interX(L1 = rectangle lo, L2 = rectangle hi), 4 x 4 edge pairs.  C1 first: f_i at hi's four vertices; if no
+// interX(L1 = rectangle lo, L2 = rectangle hi), 4 x 4 edge pairs.  C1 first: f_i at hi's four vertices; if no  @region rect_cross_rect
 // edge line of lo separates two consecutive vertices of hi there is no crossing and C2 is not evaluated.
 __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx, const float* hy) {
     uint32_t c1 = 0; // bit 4*i + j
@@ -263,7 +275,7 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
     return hit;
 }
 
-// Certified "no edge line of the rectangle separates points of this box": for every edge i the sign of
+// Certified "no edge line of the rectangle separates points of this box": for every edge i the sign of  @region SignCert/box_sign_definite
 // f_i(x,y) = dx_i*y - dy_i*x - S_i is the same for all (x,y) in the box, with a margin far above the fp32
 // evaluation error, hence C1 of interX is false for every segment inside the box -> no crossing.
 // Edges 0/2 and 1/3 are anti-parallel (d_2 = -d_0 up to ~1e-6 rounding), so f_2(q) = f_0(v_2) - f_0(q) and
@@ -287,6 +299,7 @@ __device__ __forceinline__ bool box_sign_definite(const Rect& r, const SignCert&
     return (fabsf(f0) > rad0) & (fabsf(sc.k0 - f0) > rad0) & (fabsf(f1) > rad1) & (fabsf(sc.k1 - f1) > rad1);
 }
 
+// @region group shuffles
 template <int G>
 __device__ __forceinline__ float group_min(float v) {
 #pragma unroll
@@ -306,12 +319,13 @@ __device__ __forceinline__ float group_sum(float v) {
     return v;
 }
 
-// ---- per-tile shared arrays (SoA, one slot per agent of the tile) --------------------------------------
+// ---- per-tile shared arrays (SoA, one slot per agent of the tile) --------------------------------------  @region tile smem
 struct TileSmem {
     float* px;  float* py;      // post-step (or current, in refresh mode) centre position
     float* ox;  float* oy;      // pre-step position (reward progress)
     float* cs;  float* sn;      // cos / sin of the heading
     float* vx;  float* vy;  float* vabs;
+    float* psim;                // heading mod pi (direction-cone tests)
     float* vtx;                 // [8][A]: x0..x3, y0..y3
     float* car;                 // [4][A]: carry of the pre-step pose
     float* sc;                  // [8][A]: phase-B results: d_ref, idx(int), dLcg, dRcg, min4L, min4R, flags(int), spare
@@ -325,7 +339,7 @@ struct TileSmem {
 __device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, int D, TileSmem& t) {
     float* f = reinterpret_cast<float*>(base);
     t.px = f; f += A; t.py = f; f += A; t.ox = f; f += A; t.oy = f; f += A;
-    t.cs = f; f += A; t.sn = f; f += A; t.vx = f; f += A; t.vy = f; f += A; t.vabs = f; f += A;
+    t.cs = f; f += A; t.sn = f; f += A; t.vx = f; f += A; t.vy = f; f += A; t.vabs = f; f += A; t.psim = f; f += A;
     t.vtx = f; f += 8 * A; t.car = f; f += 4 * A; t.sc = f; f += 8 * A;
     t.dij = f; f += A * N;
     t.path = reinterpret_cast<int*>(f); f += A; t.flags = reinterpret_cast<int*>(f); f += A;
@@ -334,7 +348,7 @@ __device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, in
 }
 __host__ __device__ inline size_t tile_smem_bytes(int A, int N, int D) {
     (void)D;
-    return sizeof(float) * ((size_t)A * (9 + 8 + 4 + 8 + 4) + (size_t)A * N);
+    return sizeof(float) * ((size_t)A * (10 + 8 + 4 + 8 + 4) + (size_t)A * N);
 }
 
 // ---- phase B building blocks ------------------------------------------------------------------------------
@@ -345,7 +359,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int A, int N, int D) {
 // walks the set bits together, every lane taking segments lane, lane+G, ... of the chunk.  All lanes of a
 // group stay busy; only the number of candidate chunks differs between the groups of a warp.
 
-// centre line: min distance + closest index from (px,py)
+// centre line: min distance + closest index from (px,py)  @region scan_center
 template <int G>
 __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_c,
                                             int hint_seg, bool exhaustive, float px, float py, int lane, float& d_out,
@@ -395,12 +409,13 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
     idx_out = idx + 1; // helper_scenario.py:885-887
 }
 
-// boundary: distances of the centre + 4 vertices, and the rectangle-crossing flag.  Pass 0 scans the hint
+// boundary: distances of the centre + 4 vertices, and the rectangle-crossing flag.  Pass 0 scans the hint  @region scan_boundary
 // chunk (all points, crossing test on), pass 1 the voted chunks; the segment body exists once (code size
 // matters: the warps of an SM run different phases at the same time and share the instruction caches).
 template <int G>
-__device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_b,
-                                              int hint_seg, bool exhaustive, float px, float py, const Rect& r,
+__device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes,
+                                              const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
+                                              float px, float py, float cs, float sn, float psi_m, const Rect& r,
                                               float rect_radius, int lane, float& d_cg, float dv[4], bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
@@ -408,6 +423,8 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
     SignCert cert;
     cert.init(r);
+    const float near_r = rect_radius + kFarMargin;
+    const float near2 = near_r * near_r;      // segments farther than this from the centre cannot touch the rectangle
     BestQ bq[5]; // 0 = centre, 1..4 = vertices
 #pragma unroll
     for (int v = 0; v < 5; v++) bq[v].init();
@@ -444,7 +461,8 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                     for (int k = 0; k < (4 + G - 1) / G; k++)   // this lane's vertices: lane, lane+G, ...
                         if (lane + k * G < 4 && !(box_lb2(bx, myvx[k], myvy[k]) > myq[k] * 1.01f + 1e-7f))
                             need |= 2u << (lane + k * G);
-                    if (lane == 0 && !(box_lb2(bx, px, py) > gq_pt[0] * 1.01f + 1e-7f)) need |= 1u;
+                    // (a chunk that may hold a near segment always gets its centre distances: the crossing gate reads them)
+                    if (lane == 0 && !(box_lb2(bx, px, py) > fmaxf(gq_pt[0] * 1.01f + 1e-7f, near2))) need |= 1u;
                     // the groups of a warp sit in different iterations here: shuffle within the group's own lanes
 #pragma unroll
                     for (int k = 1; k < G; k <<= 1) need |= __shfl_xor_sync(gmask, need, k);
@@ -456,18 +474,33 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                 // two segments per lane-iteration (s, s+G): independent chains; a clamped duplicate is harmless
                 const int s2 = min(s + G, s1 - 1);
                 const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
+                const float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
+                const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, len2b = lx2 * lx2 + ly2 * ly2;
+                float q0a = __int_as_float(0x7f800000), q0b = q0a;   // centre -> segment, +inf when not evaluated
                 if (need) {
-                    const float lx = e.x - a.x, ly = e.y - a.y, rl = rcp_fast(lx * lx + ly * ly);
-                    const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, rl2 = rcp_fast(lx2 * lx2 + ly2 * ly2);
-                    if (need & 1u)
-                        bq[0].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, px, py), seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py)));
+                    const float rl = rcp_fast(len2), rl2 = rcp_fast(len2b);
+                    if (need & 1u) {
+                        q0a = seg_q_r(a.x, a.y, lx, ly, rl, px, py);
+                        q0b = seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py);
+                        bq[0].upd(fminf(q0a, q0b));
+                    }
 #pragma unroll
                     for (int v = 0; v < 4; v++)
                         if (need & (2u << v))
                             bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]),
                                                 seg_q_r(a2.x, a2.y, lx2, ly2, rl2, r.vx[v], r.vy[v])));
                 }
-                if (do_x) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y) | rect_cross_seg_L1(r, a2.x, a2.y, e2.x, e2.y);
+                if (do_x) {
+                    // Gate of the exact predicate: the segment is near the rectangle (then the chunk is a near chunk
+                    // and q0 was evaluated), or it is collinear with an edge direction within kCollinear — the only
+                    // way fp32 sign noise can fire interX on a far segment.  Everything else is certified "no hit".
+                    const float cr = lx * sn - ly * cs, dt = lx * cs + ly * sn;
+                    const float cr2 = lx2 * sn - ly2 * cs, dt2 = lx2 * cs + ly2 * sn;
+                    const bool ga = exhaustive | (q0a <= near2) | (fminf(cr * cr, dt * dt) <= (kCollinear * kCollinear) * len2);
+                    const bool gb = exhaustive | (q0b <= near2) | (fminf(cr2 * cr2, dt2 * dt2) <= (kCollinear * kCollinear) * len2b);
+                    if (ga) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y, exhaustive);
+                    if (gb) hit |= rect_cross_seg_L1(r, a2.x, a2.y, e2.x, e2.y, exhaustive);
+                }
             }
         }
         if (pass) break;
@@ -483,14 +516,22 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
             const int v = lane + k * G;
             myq[k] = v == 0 ? gq_pt[1] : (v == 1 ? gq_pt[2] : (v == 2 ? gq_pt[3] : gq_pt[4]));
         }
-        float thr = sqrtf(gq) + rect_radius + kDistMargin;
+        float thr = fmaxf(sqrtf(gq) + rect_radius + kDistMargin, near_r + kDistMargin);   // near chunks are in md
         thr = thr * thr;
         md = 0; mx = 0;
+        const float pi_f = 3.14159274f, half_pi = 1.57079637f;
         for (int c = lane; c < nch; c += G) {
             if (c == c0) continue;
             const float4 bx = boxes[c];
-            if (exhaustive || !(box_lb2(bx, px, py) > thr)) md |= 1u << c;
-            if (exhaustive || !box_sign_definite(r, cert, bx)) mx |= 1u << c;
+            const float2 cone = __half22float2(cones[c]);
+            const float lb2 = box_lb2(bx, px, py);
+            if (exhaustive || !(lb2 > thr)) md |= 1u << c;
+            // crossing candidates: near chunks, and far chunks that hold a segment direction within the cone slack
+            // of the heading or its normal AND are crossed by an edge line (otherwise C1 is certified false)
+            float da = fabsf(psi_m - cone.x);
+            da = fminf(da, pi_f - da);
+            const bool in_cone = (da <= cone.y) | ((half_pi - da) <= cone.y);
+            if (exhaustive || !(lb2 > near2) || (in_cone && !box_sign_definite(r, cert, bx))) mx |= 1u << c;
         }
         md = group_or<G>(md);
         mx = group_or<G>(mx);
@@ -501,7 +542,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
     hit_out = group_or<G>(hit ? 1u : 0u) != 0u;
 }
 
-// index (and distance) of the rank-kk nearest agent: torch.topk(k, largest=False) order, ties -> lower index
+// index (and distance) of the rank-kk nearest agent: torch.topk(k, largest=False) order, ties -> lower index  @region kth_nearest/short_term
 __device__ __forceinline__ int kth_nearest(const float* dij, int N, int kk, float* d_out) {
     uint32_t used = 0;
     int bj = 0;
@@ -529,7 +570,7 @@ __device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int 
     }
 }
 
-// ---- the fused kernel -------------------------------------------------------------------------------------
+// ---- the fused kernel -------------------------------------------------------------------------------------  @region kernel prologue
 // Work decomposition: a WARP owns whole envs.  With G lanes per agent an env takes N*G lanes, a warp holds
 // EW = 32 / (N*G) envs (N = 8, G = 4: exactly one env per warp).  After the CTA-wide map staging there is no
 // CTA barrier any more: every warp runs phases A-D of its envs on its own (only __syncwarp), so warps drift
@@ -584,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     const float r_pos = 1.0f / cfg.norm_pos, r_v = 1.0f / cfg.norm_v, r_dist = 1.0f / cfg.norm_dist;
 
     for (int wt = blockIdx.x * kWarps + w; wt < n_wt; wt += gridDim.x * kWarps) {
-        // ================= phase A: one lane per agent ============================================
+        // ================= phase A: one lane per agent ============================================  @region phase A
         if (ln < n_slots) {
             const int st = slot0 + ln;
             const int ei = wt * EW + ln / N;
@@ -644,6 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     ts.vtx[(4 + k) * AS + st] = addr(madd2(sy, bxs[k], cy, bys[k]), y);
                 }
                 ts.px[st] = x; ts.py[st] = y; ts.cs[st] = cy; ts.sn[st] = sy;
+                ts.psim[st] = fmaf(-3.14159274f, floorf(psi * 0.318309873f), psi);
                 ts.vx[st] = vx; ts.vy[st] = vy; ts.vabs[st] = sqrtf(madd2(vx, vx, vy, vy));
                 ts.car[0 * AS + st] = car.x; ts.car[1 * AS + st] = car.y;
                 ts.car[2 * AS + st] = car.z; ts.car[3 * AS + st] = car.w;
@@ -659,8 +701,9 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
         const float2* pts = reinterpret_cast<const float2*>(smem + hdr->pts_off);
         const float4* boxes = reinterpret_cast<const float4*>(smem + hdr->box_off);
+        const __half2* cones = reinterpret_cast<const __half2*>(smem + hdr->cone_off);
 
-        // ================= phase B: G lanes per agent, polyline queries out of the smem map =======
+        // ================= phase B: G lanes per agent, polyline queries out of the smem map =======  @region phase B glue
         const bool slot_ok = (sl_l < n_slots) && (ts.flags[slot0 + sl_l] >= 0);
         if (!__any_sync(0xffffffffu, slot_ok)) continue;   // a warp-tile past the end of a short batch
         // all 32 lanes take part in the shuffles, so lanes without a live slot run on dummy-safe data (slot 0)
@@ -688,12 +731,15 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             // the boundaries run alongside the centre line: reuse its closest segment as the hint.
             // One rolled loop over {left, right}: a single copy of the scan in the instruction stream.
             const int h2 = idx_ref - 1;
+            const float cs_h = slot_ok ? ts.cs[sl] : 1.0f, sn_h = slot_ok ? ts.sn[sl] : 0.0f;
+            const float psi_m = slot_ok ? ts.psim[sl] : 0.0f;   // heading mod pi
 #pragma unroll 1
             for (int side = 0; side < 2; side++) {
                 float dc, dvv[4];
                 bool hit;
                 scan_boundary<G>(pts + (side ? pr.r_off : pr.l_off), boxes + (side ? pr.rbox : pr.lbox),
-                                 side ? pr.n_r : pr.n_l, h2, ex, px, py, r, rect_radius, lane, dc, dvv, hit);
+                                 cones + (side ? pr.rcone : pr.lcone), side ? pr.n_r : pr.n_l, h2, ex, px, py, cs_h, sn_h,
+                                 psi_m, r, rect_radius, lane, dc, dvv, hit);
                 if (side) { dRc = dc; hitR = hit; dRv[0] = dvv[0]; dRv[1] = dvv[1]; dRv[2] = dvv[2]; dRv[3] = dvv[3]; }
                 else      { dLc = dc; hitL = hit; dLv[0] = dvv[0]; dLv[1] = dvv[1]; dLv[2] = dvv[2]; dLv[3] = dvv[3]; }
             }
@@ -728,7 +774,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 }
             }
         }
-        // ---- rectangle-rectangle crossings: the N(N-1)/2 unordered pairs of an env are dealt round-robin to
+        // ---- rectangle-rectangle crossings: the N(N-1)/2 unordered pairs of an env are dealt round-robin to  @region pairs
         //      the env's N*G lanes; interX(vertices[lo], vertices[hi]) with lo < hi exactly as
         //      world_state_rt_sim.py:384-393, result OR-ed into both agents' masks
         if (step_mode && ln < EW * env_lanes) {
@@ -758,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         }
         __syncwarp();
 
-        // ================= phase C: interactions inside the env, reward, observation ===============
+        // ================= phase C: interactions inside the env, reward, observation ===============  @region phase C1
         {
             const int i = (sl - slot0) % N;
             const int base = sl - i; // slot of agent 0 of this env
@@ -804,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             near_sum = group_sum<G>(near_sum);
             __syncwarp(); // dij of this group is complete
 
-            // ---- C2: every lane of the group picks the k nearest (same result in all lanes);
+            // ---- C2: every lane of the group picks the k nearest (same result in all lanes);  @region C2 topk+obs
             //          torch.topk(k, largest=False), ties -> lower index.
             const int k_near = cfg.k_near;
             int nb_j[2] = {0, 0};          // the first two neighbours stay in registers, the rest is re-derived
@@ -891,6 +937,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                         }
                     }
                 }
+                // @region reward/carry
                 if (lane == 2 % G) {
                     // ---- reward (road_traffic.py:947-1253), flags, next step's carry ----
                     int fl = ts.flags[sl];
@@ -947,7 +994,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         }
         __syncwarp();
 
-        // ================= phase D: per-env outputs ===============================================
+        // ================= phase D: per-env outputs ===============================================  @region phase D
         if (step_mode && ln < n_slots && (ln % N) == 0 && ts.flags[slot0 + ln] >= 0) {
             const int st = slot0 + ln;
             const int e = ts.env[st];
@@ -964,7 +1011,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     if (!map_ready) mbar_wait(bar, 0); // never leave with a bulk copy in flight
 }
 
-// ---- placement / reset kernels ------------------------------------------------------------------------------
+// ---- placement / reset kernels ------------------------------------------------------------------------------  @region other kernels
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
