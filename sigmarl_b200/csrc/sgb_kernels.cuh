@@ -30,6 +30,17 @@ namespace sgb {
 #ifndef SGB_THREADS
 #define SGB_THREADS 1024
 #endif
+#ifndef SGB_SYNC_WARPS          // warps per phase-aligned group in the step kernel (0/1 = free-running warps)
+#define SGB_SYNC_WARPS 8
+#endif
+#ifndef SGB_SYNC_INTERLEAVED     // 1: group = warp %% n_groups (warps of one group share an SM sub-partition)
+#define SGB_SYNC_GROUP(w, sw) ((w) / (sw))
+#else
+#define SGB_SYNC_GROUP(w, sw) ((w) % (SGB_THREADS / 32 / (sw)))
+#endif
+#ifndef SGB_SYNC_WARPS_REFRESH  // same for the refresh kernel (short compacted env lists: free-running)
+#define SGB_SYNC_WARPS_REFRESH 0
+#endif
 constexpr int kThreads = SGB_THREADS; // threads per CTA (one CTA per SM: the map blob fills most of the shared memory)
 constexpr int kChunk = 8;            // polyline segments per bounding-box chunk
 constexpr int kExt = 6;              // extension points behind a centre line (3 short-term pts x interval 2)
@@ -624,7 +635,19 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     const float rect_radius = sqrtf(cfg.half_length * cfg.half_length + cfg.half_width * cfg.half_width) * 1.0001f;
     const float r_pos = 1.0f / cfg.norm_pos, r_v = 1.0f / cfg.norm_v, r_dist = 1.0f / cfg.norm_dist;
 
-    for (int wt = blockIdx.x * kWarps + w; wt < n_wt; wt += gridDim.x * kWarps) {
+    // Phase alignment (DESIGN.md "Instruction cache"): the kernel's code (~55 KB executed) does not fit the SM's
+    // 32 KB instruction cache, and 32 free-running warps keep all of it live at once.  Groups of SYNCW warps
+    // therefore walk the phases together (named barrier per group): at any time a group executes one phase's
+    // code only.  Every warp of the CTA runs the same number of tile iterations so that the barriers match.
+    constexpr int SYNCW = step_mode ? SGB_SYNC_WARPS : SGB_SYNC_WARPS_REFRESH;
+    auto phase_sync = [&]() {
+        if (SYNCW >= kWarps) __syncthreads();
+        else if (SYNCW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + SGB_SYNC_GROUP(w, (SYNCW > 0 ? SYNCW : 1))), "r"(SYNCW * 32) : "memory");
+        else __syncwarp();
+    };
+    const int stride_wt = gridDim.x * kWarps;
+    const int n_iter = SYNCW > 1 ? (n_wt - (int)blockIdx.x * kWarps + stride_wt - 1) / stride_wt : (1 << 30);
+    for (int it = 0, wt = blockIdx.x * kWarps + w; it < n_iter && (SYNCW > 1 || wt < n_wt); it++, wt += stride_wt) {
         // ================= phase A: one lane per agent ============================================  @region phase A
         if (ln < n_slots) {
             const int st = slot0 + ln;
@@ -695,7 +718,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             ts.env[st] = e;
             ts.coll[st] = 0;
         }
-        __syncwarp();
+        phase_sync();
         if (!map_ready) { mbar_wait(bar, 0); map_ready = true; }
 
         const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
@@ -705,7 +728,9 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
 
         // ================= phase B: G lanes per agent, polyline queries out of the smem map =======  @region phase B glue
         const bool slot_ok = (sl_l < n_slots) && (ts.flags[slot0 + sl_l] >= 0);
-        if (!__any_sync(0xffffffffu, slot_ok)) continue;   // a warp-tile past the end of a short batch
+        // a warp-tile past the end of a short batch: skip it (with phase alignment it runs on dummy-safe data
+        // instead, so that every warp arrives at every barrier)
+        if (SYNCW <= 1 && !__any_sync(0xffffffffu, slot_ok)) continue;
         // all 32 lanes take part in the shuffles, so lanes without a live slot run on dummy-safe data (slot 0)
         const int sl = slot_ok ? slot0 + sl_l : slot0;
         int path = slot_ok ? ts.path[sl] : 0;
@@ -802,7 +827,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 }
             }
         }
-        __syncwarp();
+        phase_sync();
 
         // ================= phase C: interactions inside the env, reward, observation ===============  @region phase C1
         {
@@ -992,7 +1017,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 }
             }
         }
-        __syncwarp();
+        phase_sync();
 
         // ================= phase D: per-env outputs ===============================================  @region phase D
         if (step_mode && ln < n_slots && (ln % N) == 0 && ts.flags[slot0 + ln] >= 0) {
@@ -1006,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             const bool dn = (step == cfg.max_steps - 1) || (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE));
             p.buf.done[e] = dn ? 1 : 0;
         }
-        __syncwarp();
+        __syncwarp();   // phase D -> next tile's phase A touch this warp's own slots only: no group barrier
     }
     if (!map_ready) mbar_wait(bar, 0); // never leave with a bulk copy in flight
 }
