@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 100
+#define SGB_VERSION 110
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -87,6 +87,11 @@ typedef struct {
     int32_t max_steps;        /* timer.step == max_steps-1 -> done        road_traffic.py:1413   */
     int32_t respawn_on_exit;  /* scenario_type != "cpm_entire"            road_traffic.py:1449   */
     int32_t exhaustive;       /* debug: 1 = scan every segment (no pruning); results must not change */
+    float reward_reach_goal;  /* rewards.reach_goal (info["rew_reach_goal"]; added to the reward only in testing
+                                 mode)                                    road_traffic.py:217-219, 996-1003 */
+    int32_t testing_mode;     /* parameters.is_testing_mode: sparse-only reward (:1050-1055), env done only at the
+                                 time limit and colliding / leaving agents respawned one by one (:1429-1447),
+                                 spawn range growing with the try count (world_state_rt_sim.py:254-261) */
 } sgb_config;
 
 /* Device buffers of one batch of B envs x N agents.  in = read, out = written, io = both. */
@@ -105,10 +110,18 @@ typedef struct {
     uint8_t* done;        /* out [B]                                    road_traffic.py:1368       */
     uint8_t* agent_flags; /* out [B,N]   SGB_FLAG_* collision bits      world_state_rt_sim.py:36-55 */
     uint32_t* collide_with; /* out [B,N] bit j = collisions.with_agents[b,a,j]; may be NULL        */
+    float*   info;        /* out [B,N,SGB_INFO_DIM] what info(agent) adds to the state (road_traffic.py:1547-1633); */
+                          /*   may be NULL.  0..5 "ref" (fresh short-term path) 6 distance_ref 7 distance_left_b     */
+                          /*   8 distance_right_b 9 rew_near_other_agents 10 rew_collide_other_agents              */
+                          /*   11 rew_collide_lane 12 rew_reach_goal 13 rew_total 14 distances.boundaries 15 spare */
+    int32_t* task_tries;  /* io [B] num_task_tries   (road_traffic.py:1029-1035); may be NULL                       */
+    int32_t* task_success;/* io [B] task_success_times (:998-1002); may be NULL                                     */
     float*   dbg;         /* out [B,N,16] internals for parity tests; may be NULL:                  */
                           /*   0 d_ref 1 (int)idx_ref 2..6 dL[0..4] 7..11 dR[0..4] 12 d_bound       */
                           /*   13 nearest-agent index 14 second-nearest index 15 reserved           */
 } sgb_buffers;
+
+#define SGB_INFO_DIM 16
 
 #define SGB_FLAG_COLLIDE_AGENT 1u /* any collisions.with_agents[b,a,:]  */
 #define SGB_FLAG_COLLIDE_LANE 2u  /* collisions.with_lanelets[b,a]      */

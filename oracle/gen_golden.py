@@ -22,6 +22,7 @@ Recorded per step t (arrays are [T, B, N, ...]):
   reset_mask [T,B]  : env was reset after step t (reset_at), followed by
   reset_obs [T,B,N,D], reset_pos/rot/speed/vel/path_id/point_id/scenario_id  (post-reset state of those envs)
   respawn_mask [T,B,N] : agent was respawned inside done() (road_traffic.py:1462-1472)
+  info_<key> [T,B,N,...] : every entry of info(agent) (road_traffic.py:1547-1633), num_task_tries / task_success_times [T,B]
 """
 import os
 import sys
@@ -38,6 +39,16 @@ from sigmarl.helper_common import Parameters  # noqa: E402
 from sigmarl.scenarios.road_traffic import ScenarioRoadTraffic  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# info() keys recorded in the fixtures; base/priority observations exist only with prioritized MARL
+INFO_KEYS = ["pos", "pos_nom", "rot", "rot_nom", "vel", "vel_nom", "act_vel", "act_vel_nom", "act_steer",
+             "act_steer_nom", "ref", "ref_nom", "distance_ref", "distance_ref_nom", "distance_left_b",
+             "distance_left_b_nom", "distance_right_b", "distance_right_b_nom", "is_collision_with_agents",
+             "is_collision_with_lanelets", "is_reach_goal", "ref_lanelet_ids", "path_id", "applied_action_vel",
+             "applied_action_steer", "nominal_action_vel", "nominal_action_steer",
+             "rew_progress", "rew_reach_goal", "rew_speed", "rew_centerline", "rew_near_other_agents",
+             "rew_near_left_lane", "rew_near_right_lane", "rew_collide_other_agents", "rew_collide_lane",
+             "rew_energy_acceleration", "rew_energy_steering", "rew_total"]
 
 # name -> config.  mode "kwargs": scenario built from make_world(**kwargs) (dt=0.05 ...);
 # mode "params": a Parameters object from sigmarl/config.json (dt=0.1 ...), as mappo_cavs.py:168 does.
@@ -59,6 +70,11 @@ CONFIGS = {
     # forward-driving actions: long episodes, agents reach path ends -> exit crossings + respawns
     "cpm_mixed_B8_N4_gentle": dict(st="cpm_mixed", B=8, N=4, T=80, mode="params", seed=8, gentle=True,
                                   extra=dict(rew_method="distance_sparse")),
+    # testing mode (road_traffic.py:1050-1055, 1429-1447): sparse reward, colliding agents respawned one by one
+    "cpm_entire_B4_N4_testing": dict(st="cpm_entire", B=4, N=4, T=60, mode="params", seed=11,
+                                    extra=dict(is_testing_mode=True), max_steps=40),
+    "cpm_mixed_B4_N4_testing_gentle": dict(st="cpm_mixed", B=4, N=4, T=80, mode="params", seed=12, gentle=True,
+                                          extra=dict(is_testing_mode=True, rew_method="ttc_sparse"), max_steps=48),
     "cpm_entire_B4_N3_k1": dict(st="cpm_entire", B=4, N=3, T=40, mode="params", seed=7,
                                extra=dict(n_nearing_agents_observed=1)),
 }
@@ -169,6 +185,11 @@ def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
         push("obs", torch.stack(obs, dim=1))
         push("reward", torch.stack(rew, dim=1))
         push("done", done)
+        # info(agent) as vmas returns it (road_traffic.py:1489-1635), stacked over agents: [B, N, ...]
+        for k in INFO_KEYS:
+            push("info_" + k, torch.stack([torch.as_tensor(d[k]).reshape(B, -1).squeeze(-1) for d in info], dim=1))
+        push("num_task_tries", sc.num_task_tries.clone())
+        push("task_success_times", sc.task_success_times.clone())
         push("respawn_mask", respawn)
         # post-respawn state of respawned agents (read back from the world)
         push("respawn_pos", stack_agents(agents, lambda a: a.state.pos))

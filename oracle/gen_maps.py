@@ -79,11 +79,16 @@ def main():
             yaw, yoff = flatten([{"y": q["center_line_yaw"].reshape(-1, 1)} for q in paths], "y")
             out[f"{name}_yaw"], out[f"{name}_yaw_off"] = yaw.reshape(-1), yoff
             out[f"{name}_is_loop"] = np.asarray([bool(q["is_loop"]) for q in paths], np.uint8)
+            # lanelet IDs of every path (info()["ref_lanelet_ids"], world_state_rt.py:411-417)
+            ids = [np.asarray(q["lanelet_IDs"], np.int32).reshape(-1) for q in paths]
+            out[f"{name}_lanelet_ids"] = np.concatenate(ids) if ids else np.zeros(0, np.int32)
+            out[f"{name}_lanelet_off"] = np.asarray(np.concatenate([[0], np.cumsum([len(a) for a in ids])]), np.int32)
         out["world_x_dim"] = np.float64(p.bounds["world_x_dim"])
         out["world_y_dim"] = np.float64(p.bounds["world_y_dim"])
         out["lane_width"] = np.float64(SCENARIOS[st]["lane_width"])
         out["default_n_agents"] = np.int32(SCENARIOS[st]["n_agents"])
         out["osm_lane_width"] = np.float64(OSM_LANE_WIDTH)
+        out["n_lanelets_all"] = np.int32(len(p.lanelets_all))   # width of ref_lanelet_ids (world_state_rt.py:152)
         np.savez_compressed(os.path.join(OUT, f"{st}.npz"), **out)
         nmax = int(np.diff(out["all_center_off"]).max())
         print(f"{st}: {len(p.reference_paths)} paths, max centre pts {nmax}, loops {int(out['all_is_loop'].sum())}")

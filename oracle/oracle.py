@@ -49,11 +49,12 @@ _CFG_FLOATS = ["dt", "max_speed", "max_steering", "max_acc", "max_steering_rate"
                "pen_near_agents", "pen_collide_agents", "pen_collide_lane", "norm_pos", "norm_v", "norm_rot",
                "norm_dist", "dsafe_sq", "reset_min_dist_sq"]
 _CFG_INTS = ["rew_exact_sparse", "rew_has_ttc", "rew_has_distance", "rew_has_sparse", "k_near", "max_steps",
-             "is_cpm_entire", "sample_interval"]
+             "is_cpm_entire", "sample_interval", "testing_mode"]
 
 
 class _Cfg(C.Structure):
-    _fields_ = [(n, C.c_float) for n in _CFG_FLOATS] + [(n, C.c_int) for n in _CFG_INTS]
+    _fields_ = ([(n, C.c_float) for n in _CFG_FLOATS] + [(n, C.c_int) for n in _CFG_INTS] +
+                [("reward_reach_goal", C.c_float)])
 
 
 def f32(x):
@@ -190,6 +191,8 @@ def make_cfg(scenario_type, pmap, c):
     cfg.max_steps = int(c["max_steps"])
     cfg.is_cpm_entire = int(scenario_type == "cpm_entire")
     cfg.sample_interval = SAMPLE_INTERVAL
+    cfg.testing_mode = int(bool(c.get("testing_mode", False)))
+    cfg.reward_reach_goal = float(f32(c.get("reward_reach_goal", 100 / 100)))     # road_traffic.py:217-219
     return cfg
 
 
@@ -313,4 +316,5 @@ def config_from_golden(g):
                 pen_collide_lane=float(g["cfg_penalty_collide_with_boundaries"]),
                 norm_pos=float(g["cfg_norm_pos"]), norm_v=float(g["cfg_norm_v"]), norm_rot=float(g["cfg_norm_rot"]),
                 norm_dist=float(g["cfg_norm_distance_lanelet"]), rew_method=str(g["cfg_rew_method"]),
-                max_steps=int(g["cfg_max_steps"]), k_near=int(g["cfg_n_nearing_agents_observed"]))
+                max_steps=int(g["cfg_max_steps"]), k_near=int(g["cfg_n_nearing_agents_observed"]),
+                testing_mode=bool(g["cfg_is_testing_mode"]))

@@ -50,6 +50,8 @@ typedef struct {
     float reset_min_dist_sq; /* reset_agent_min_distance**2         world_state_rt_sim.py:305 */
     int rew_exact_sparse, rew_has_ttc, rew_has_distance, rew_has_sparse;
     int k_near, max_steps, is_cpm_entire, sample_interval;
+    int testing_mode;        /* parameters.is_testing_mode          road_traffic.py:1050-1055, 1429-1447 */
+    float reward_reach_goal; /* rewards.reach_goal                  road_traffic.py:217-219 */
 } orc_cfg;
 
 typedef struct {
@@ -386,14 +388,18 @@ static float orc_reward(orc_world *w, int b, int i) {
     float pen_a2a = (float)any_a2a * c->pen_collide_agents;
     float pen_lane = (float)w->col_lane[g] * c->pen_collide_lane;
     float pen_nb = orc_dec(w->d_bound[g], c->nb_low, c->nb_high) * c->pen_near_boundary; /* :1040-1048 */
-    if (c->rew_exact_sparse) { rew += pen_a2a; rew += pen_lane; }                      /* :1058-1062 */
-    if (c->rew_has_ttc) {                                                               /* :1064-1085 */
+    if (c->testing_mode) {                                                              /* :1050-1055 */
+        rew += (float)w->col_exit[g] * c->reward_reach_goal;
+        rew += pen_a2a; rew += pen_lane;
+    }
+    if (!c->testing_mode && c->rew_exact_sparse) { rew += pen_a2a; rew += pen_lane; }  /* :1058-1062 */
+    if (!c->testing_mode && c->rew_has_ttc) {                                           /* :1064-1085 */
         rew += orc_ttc_penalty(w, b, i);
         rew += pen_nb;
         rew += pen_a2a; rew += pen_lane;
         if (c->rew_has_sparse) { rew += pen_a2a; rew += pen_lane; }
     }
-    if (c->rew_has_distance) {                                                          /* :1087-1112 */
+    if (!c->testing_mode && c->rew_has_distance) {                                      /* :1087-1112 */
         float s = 0.0f;
         for (int j = 0; j < N; j++) s += orc_dec(w->d_agents[g * N + j], c->na_low, c->na_high);
         rew += s * c->pen_near_agents;
@@ -504,16 +510,24 @@ static void *orc_step_range(void *arg) {
             if (i == 0) orc_take_snapshot(w, b, &snap);
             orc_observe(w, b, i, &snap, &jb->obs[AG(b, i) * D]);
         }
-        /* done() road_traffic.py:1368-1487 (training mode) */
+        /* done() road_traffic.py:1368-1487: training mode :1449-1457, testing mode :1429-1447 */
         int any = (w->step[b] == w->cfg.max_steps - 1);
-        for (int a = 0; a < N; a++) {
-            any |= w->col_lane[AG(b, a)];
-            for (int j = 0; j < N; j++) any |= w->col_agents[AG(b, a) * N + j];
-        }
+        if (!w->cfg.testing_mode)
+            for (int a = 0; a < N; a++) {
+                any |= w->col_lane[AG(b, a)];
+                for (int j = 0; j < N; j++) any |= w->col_agents[AG(b, a) * N + j];
+            }
         jb->done[b] = (uint8_t)any;
-        for (int a = 0; a < N; a++)
-            jb->respawn_request[AG(b, a)] =
-                (uint8_t)(!w->cfg.is_cpm_entire && !any && (w->col_entry[AG(b, a)] | w->col_exit[AG(b, a)]));
+        for (int a = 0; a < N; a++) {
+            int leave = w->col_entry[AG(b, a)] | w->col_exit[AG(b, a)];
+            if (w->cfg.testing_mode) {
+                int hit = w->col_lane[AG(b, a)];
+                for (int j = 0; j < N; j++) hit |= w->col_agents[AG(b, a) * N + j];
+                jb->respawn_request[AG(b, a)] = (uint8_t)(!any && (hit | leave));
+            } else {
+                jb->respawn_request[AG(b, a)] = (uint8_t)(!w->cfg.is_cpm_entire && !any && leave);
+            }
+        }
     }
     return NULL;
 }

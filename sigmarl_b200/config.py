@@ -51,8 +51,9 @@ class EnvConfig:
     penalty_collide_with_boundaries: float = -100 / R_P_NORMALIZER
     cpm_scenario_probabilities: tuple = (1.0, 0.0, 0.0)
     exhaustive: bool = False                # debug: disable the pruned search (results must not change)
+    is_testing_mode: bool = False           # road_traffic.py:1050-1055, 1429-1447; world_state_rt_sim.py:254-261
+    reward_reach_goal: float = 100 / R_P_NORMALIZER   # road_traffic.py:217-219
     # flags of the reference that select code OUTSIDE the supported hot path; must keep these values
-    is_testing_mode: bool = False
     is_use_mtv_distance: bool = False
     is_ego_view: bool = True
     is_partial_observation: bool = True
@@ -69,7 +70,7 @@ class EnvConfig:
     def validate(self):
         if self.rew_method not in _REW_METHODS:
             raise NotImplementedError(f"rew_method {self.rew_method!r}: supported {_REW_METHODS} (cbf variants are out of scope)")
-        want = dict(is_testing_mode=False, is_use_mtv_distance=False, is_ego_view=True, is_partial_observation=True,
+        want = dict(is_use_mtv_distance=False, is_ego_view=True, is_partial_observation=True,
                     is_observe_vertices=True, is_observe_distance_to_agents=True,
                     is_observe_distance_to_boundaries=True, is_observe_distance_to_center_line=True,
                     is_apply_mask=False, is_obs_noise=False, is_obs_steering=False,
@@ -166,4 +167,6 @@ class EnvConfig:
         c.max_steps = int(self.max_steps)
         c.respawn_on_exit = int(self.scenario_type != "cpm_entire")       # road_traffic.py:1449
         c.exhaustive = int(self.exhaustive)
+        c.reward_reach_goal = float(_f32(self.reward_reach_goal))
+        c.testing_mode = int(bool(self.is_testing_mode))
         return c

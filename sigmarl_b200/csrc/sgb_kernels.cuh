@@ -971,6 +971,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     float d_bound;
                     if (!step_mode || i != 0) d_bound = fminf(fminf(dLc, m4L), fminf(dRc, m4R));
                     else d_bound = fminf(fminf(dLc, c_mL), fminf(dRc, c_mR)); // agent 0: stale vertices
+                    float pen_near_agents = 0.0f, pen_a2a = 0.0f, pen_lane = 0.0f, rew_goal = 0.0f, rew_total = 0.0f;
                     if (step_mode) {
                         float2 st_old[3];   // short-term path of the PREVIOUS step
                         short_term(cpts, pr.n_c, pr.is_loop != 0, c_idx, st_old);
@@ -984,23 +985,31 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                         }
                         float rew = 0.0f;
                         rew += (acc / cfg.speed_dt) * cfg.reward_progress;
-                        const float pen_a2a = (coll ? 1.0f : 0.0f) * cfg.penalty_collide_agents;
-                        const float pen_lane = ((fl & SGB_FLAG_COLLIDE_LANE) ? 1.0f : 0.0f) * cfg.penalty_collide_lane;
+                        pen_a2a = (coll ? 1.0f : 0.0f) * cfg.penalty_collide_agents;
+                        pen_lane = ((fl & SGB_FLAG_COLLIDE_LANE) ? 1.0f : 0.0f) * cfg.penalty_collide_lane;
+                        rew_goal = ((fl & SGB_FLAG_EXIT) ? 1.0f : 0.0f) * cfg.reward_reach_goal;   // :996-997
                         const float pen_nb = dec_lin(d_bound, cfg.near_boundary_low, cfg.near_boundary_high) * cfg.penalty_near_boundary;
-                        if (cfg.rew_flags & SGB_REW_EXACT_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                        if (cfg.rew_flags & SGB_REW_TTC) {
-                            float risk = ttc_sum / (float)(N - 1 > 1 ? N - 1 : 1);
-                            rew += risk * cfg.penalty_near_agents;
-                            rew += pen_nb;
-                            rew += pen_a2a; rew += pen_lane;
-                            if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                        if (cfg.testing_mode) {                                              // :1050-1055
+                            rew += rew_goal; rew += pen_a2a; rew += pen_lane;
+                        } else {
+                            if (cfg.rew_flags & SGB_REW_EXACT_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                            if (cfg.rew_flags & SGB_REW_TTC) {
+                                float risk = ttc_sum / (float)(N - 1 > 1 ? N - 1 : 1);
+                                pen_near_agents = risk * cfg.penalty_near_agents;
+                                rew += pen_near_agents;
+                                rew += pen_nb;
+                                rew += pen_a2a; rew += pen_lane;
+                                if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                            }
+                            if (cfg.rew_flags & SGB_REW_DISTANCE) {
+                                pen_near_agents = near_sum * cfg.penalty_near_agents;
+                                rew += pen_near_agents;
+                                rew += pen_nb;
+                                if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
+                            }
                         }
-                        if (cfg.rew_flags & SGB_REW_DISTANCE) {
-                            rew += near_sum * cfg.penalty_near_agents;
-                            rew += pen_nb;
-                            if (cfg.rew_flags & SGB_REW_SPARSE) { rew += pen_a2a; rew += pen_lane; }
-                        }
-                        p.buf.reward[g] = clampf(rew, -1.0f, 1.0f);
+                        rew_total = clampf(rew, -1.0f, 1.0f);
+                        p.buf.reward[g] = rew_total;
                         p.buf.agent_flags[g] = (uint8_t)fl;
                         if (p.buf.collide_with) p.buf.collide_with[g] = coll;
                     } else {
@@ -1014,6 +1023,19 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     nc.w = __int_as_float(idx_n);
                     reinterpret_cast<float4*>(p.buf.carry)[g] = nc;
                     if (p.buf.dbg) p.buf.dbg[g * 16 + 12] = d_bound;
+                    if (p.buf.info) {
+                        // what info(agent_i) reads right after reward(i) / observation(i) (road_traffic.py:1574-1633):
+                        // agent i's own distances and short-term path are FRESH here (for i == 0 the vertex part of
+                        // the boundary distances is the stale one, as in its observation)
+                        float4* io = reinterpret_cast<float4*>(p.buf.info + g * SGB_INFO_DIM);
+                        float2 st_new[3];
+                        short_term(cpts, pr.n_c, pr.is_loop != 0, idx_n, st_new);
+                        const bool stale0 = step_mode && i == 0;
+                        io[0] = make_float4(st_new[0].x, st_new[0].y, st_new[1].x, st_new[1].y);
+                        io[1] = make_float4(st_new[2].x, st_new[2].y, d_ref_n, fminf(dLc, stale0 ? c_mL : m4L));
+                        io[2] = make_float4(fminf(dRc, stale0 ? c_mR : m4R), pen_near_agents, pen_a2a, pen_lane);
+                        io[3] = make_float4(rew_goal, rew_total, d_bound, 0.0f);
+                    }
                 }
             }
         }
@@ -1023,12 +1045,20 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         if (step_mode && ln < n_slots && (ln % N) == 0 && ts.flags[slot0 + ln] >= 0) {
             const int st = slot0 + ln;
             const int e = ts.env[st];
-            int any = 0;
-            for (int j = 0; j < N; j++) any |= ts.flags[st + j];
+            int any = 0, tries = 0, succ = 0;
+            for (int j = 0; j < N; j++) {
+                const int f = ts.flags[st + j];
+                any |= f;
+                tries += (f & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE | SGB_FLAG_EXIT)) ? 1 : 0;   // :1029-1035
+                succ += (f & (int)SGB_FLAG_EXIT) ? 1 : 0;                                                       // :998-1002
+            }
+            if (p.buf.task_tries && tries) p.buf.task_tries[e] += tries;
+            if (p.buf.task_success && succ) p.buf.task_success[e] += succ;
             const int step = p.buf.step_count[e] + 1;          // road_traffic.py:954-962
             p.buf.step_count[e] = step;
-            // road_traffic.py:1451-1457 (training mode)
-            const bool dn = (step == cfg.max_steps - 1) || (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE));
+            // road_traffic.py:1451-1457 (training mode) / :1429-1433 (testing mode: only the time limit ends an env)
+            const bool dn = (step == cfg.max_steps - 1) ||
+                            (!cfg.testing_mode && (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE)));
             p.buf.done[e] = dn ? 1 : 0;
         }
         __syncwarp();   // phase D -> next tile's phase A touch this warp's own slots only: no group barrier
@@ -1108,9 +1138,13 @@ __global__ void reset_kernel(const ResetParams p) {
     const bool full = p.all || p.buf.done[e];
     uint32_t respawn = 0;
     if (!full) {
-        if (!p.cfg.respawn_on_exit) return;
+        // training mode (:1449-1472): agents that crossed an entry / exit segment, maps with open paths only;
+        // testing mode (:1435-1447): every colliding or leaving agent, on every map
+        if (!p.cfg.respawn_on_exit && !p.cfg.testing_mode) return;
+        const uint32_t which = p.cfg.testing_mode ? (SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE | SGB_FLAG_ENTRY | SGB_FLAG_EXIT)
+                                                  : (SGB_FLAG_ENTRY | SGB_FLAG_EXIT);
         for (int a = 0; a < N; a++)
-            if (p.buf.agent_flags[(size_t)e * N + a] & (SGB_FLAG_ENTRY | SGB_FLAG_EXIT)) respawn |= 1u << a;
+            if (p.buf.agent_flags[(size_t)e * N + a] & which) respawn |= 1u << a;
         if (!respawn) return;
     }
     const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(p.blob);
@@ -1130,7 +1164,9 @@ __global__ void reset_kernel(const ResetParams p) {
         for (int tr = 0; tr < p.max_tries && !ok; tr++) {
             path = p.path_lo + (int)(draw(p.seed, p.epoch, env_g, a, tr, 0) % (uint64_t)(p.path_hi - p.path_lo));
             const PathRec pr = paths[path];
-            const int end = pr.n_c / 2;
+            int end = pr.n_c / 2;
+            // testing mode: the range starts as [3, 4) and grows by the try count (world_state_rt_sim.py:254-261)
+            if (p.cfg.testing_mode) end = min(end, 3 + (tr + 1) * (tr + 2) / 2);
             point = 3 + (int)(draw(p.seed, p.epoch, env_g, a, tr, 1) % (uint64_t)(end - 3 > 0 ? end - 3 : 1));
             const float2 c = pts[pr.c_off + point];
             ok = true;

@@ -5,6 +5,7 @@ State layout (env-major, agent-minor — DESIGN.md "Data layout in HBM"):
     pose [B,N,4]  x, y, psi, v            aux [B,N,4]  delta, vx, vy, beta
     path_id [B,N] int32                   carry [B,N,4]  d_ref, min dL, min dR, idx_ref (pre-step pose)
     action [B,N,2]  obs [B,N,D]  reward [B,N]  done [B] u8  agent_flags [B,N] u8  step_count [B] i32
+    info [B,N,16] (optional; layout in include/sigmarl_b200.h)  task_tries / task_success [B] i32 (optional)
 """
 import ctypes as C
 
@@ -18,7 +19,8 @@ from .maps import MapLibrary
 
 class RoadTrafficEnv:
     def __init__(self, config: EnvConfig = None, num_envs: int = 32, device="cuda:0", seed: int = 0,
-                 env_offset: int = 0, debug: bool = False, max_reset_tries: int = 64, **cfg_kwargs):
+                 env_offset: int = 0, debug: bool = False, max_reset_tries: int = 64, info: bool = False,
+                 **cfg_kwargs):
         self.config = config or EnvConfig(**cfg_kwargs)
         self.L = _lib.load_library()                      # raises if the .so is missing
         if not torch.cuda.is_available():
@@ -54,6 +56,10 @@ class RoadTrafficEnv:
         self.agent_flags = z(B, N, dtype=torch.uint8)
         self.collide_with = z(B, N, dtype=torch.int32)
         self.dbg = z(B, N, 16) if debug else None
+        # info(agent) extras + evaluation counters (road_traffic.py:1489-1635, :998-1035): only when asked for
+        self.info = z(B, N, _lib.SGB_INFO_DIM) if info else None
+        self.task_tries = z(B, dtype=torch.int32) if info else None
+        self.task_success = z(B, dtype=torch.int32) if info else None
         self.n_failed = z(1, dtype=torch.int32)
         self._buf = _lib.Buffers()
         for name in _lib.BUFFER_FIELDS:

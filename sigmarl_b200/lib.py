@@ -42,11 +42,13 @@ CONFIG_FLOATS = ["dt", "max_speed", "max_steering", "max_acc", "max_steering_rat
 class Config(C.Structure):
     _fields_ = ([(n, C.c_float) for n in CONFIG_FLOATS] +
                 [("rew_flags", C.c_uint32), ("k_near", C.c_int32), ("max_steps", C.c_int32),
-                 ("respawn_on_exit", C.c_int32), ("exhaustive", C.c_int32)])
+                 ("respawn_on_exit", C.c_int32), ("exhaustive", C.c_int32), ("reward_reach_goal", C.c_float),
+                 ("testing_mode", C.c_int32)])
 
 
 BUFFER_FIELDS = ["pose", "aux", "path_id", "carry", "action", "step_count", "obs", "reward", "done",
-                 "agent_flags", "collide_with", "dbg"]
+                 "agent_flags", "collide_with", "info", "task_tries", "task_success", "dbg"]
+SGB_INFO_DIM = 16
 
 
 class Buffers(C.Structure):

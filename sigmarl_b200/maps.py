@@ -41,7 +41,7 @@ class MapLibrary:
         self.lane_width = float(z["lane_width"])
         self.default_n_agents = int(z["default_n_agents"])
         self.set_names = ["intersection", "merge_in", "merge_out"] if "cpm_mixed" in scenario_type else ["all"]
-        cen, lef, rig, yaw, loop = [], [], [], [], []
+        cen, lef, rig, yaw, loop, lids = [], [], [], [], [], []
         c_off, l_off, r_off = [0], [0], [0]
         self.set_range = {}
         for s in self.set_names:
@@ -59,6 +59,8 @@ class MapLibrary:
                 r_off.append(r_off[-1] + (b - a))
                 a, b = z[f"{s}_yaw_off"][i:i + 2]
                 yaw.append(z[f"{s}_yaw"][a:b])
+                a, b = z[f"{s}_lanelet_off"][i:i + 2]
+                lids.append(z[f"{s}_lanelet_ids"][a:b])
             loop.append(z[f"{s}_is_loop"])
             self.set_range[s] = (lo, lo + n)
         self.center_xy = np.ascontiguousarray(np.concatenate(cen), np.float32)
@@ -70,6 +72,12 @@ class MapLibrary:
         self.right_off = np.asarray(r_off, np.int32)
         self.is_loop = np.ascontiguousarray(np.concatenate(loop), np.uint8)
         self.n_paths = len(c_off) - 1
+        # ref_lanelet_ids as the reference holds them per agent: zero-padded to len(lanelets_all)
+        # (world_state_rt.py:152, 242-246, 411-417)
+        self.n_lanelets_all = int(z["n_lanelets_all"])
+        self.lanelet_ids = np.zeros((self.n_paths, self.n_lanelets_all), np.int32)
+        for i, ids in enumerate(lids):
+            self.lanelet_ids[i, :len(ids)] = ids
         n_c = np.diff(self.center_off)
         # road_traffic.py:505-530
         self.max_ref_path_points = int(n_c.max()) + N_POINTS_SHORT_TERM * SAMPLE_INTERVAL_REF_PATH + 2

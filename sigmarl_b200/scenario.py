@@ -163,14 +163,26 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             known.setdefault("scenario_type", "cpm_entire")
             cfg = EnvConfig(mode="kwargs", **known)
         self.config = cfg
-        self.env = RoadTrafficEnv(cfg, num_envs=batch_dim, device=device, seed=seed, env_offset=env_offset, debug=debug)
+        self.env = RoadTrafficEnv(cfg, num_envs=batch_dim, device=device, seed=seed, env_offset=env_offset, debug=debug,
+                                  info=True)
         self.n_agents = self.env.N
         self.max_speed, self.max_steering = MAX_SPEED, torch.tensor(MAX_STEERING, device=self.env.device)
         world = WorldB200(self.env, self)
         world.parameters = getattr(self, "parameters", None)
         self._world = world
-        self.num_task_tries = torch.zeros(batch_dim, device=self.env.device, dtype=torch.int32)
-        self.task_success_times = torch.zeros(batch_dim, device=self.env.device, dtype=torch.int32)
+        # evaluation counters (road_traffic.py:763-768): incremented by the kernel, same tensors
+        self.num_task_tries = self.env.task_tries
+        self.task_success_times = self.env.task_success
+        dev = self.env.device
+        m = self.env.map
+        self._lanelet_ids = torch.as_tensor(m.lanelet_ids, device=dev)
+        self._norm = dict(                                                   # road_traffic.py:587-608
+            pos_world=torch.tensor([m.world_x_dim, m.world_y_dim], device=dev, dtype=torch.float32),
+            v=torch.tensor(MAX_SPEED, device=dev, dtype=torch.float32),
+            rot=torch.tensor(2 * math.pi, device=dev, dtype=torch.float32),
+            steering=torch.tensor(MAX_STEERING, device=dev, dtype=torch.float32),
+            dist=torch.tensor(cfg.lane_width(m) * 3, device=dev, dtype=torch.float32))
+        self._zeros_bn = torch.zeros(batch_dim, device=dev, dtype=torch.float32)
         return world
 
     # -- road_traffic.py:816
@@ -214,11 +226,14 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
     def done(self) -> torch.Tensor:
         e = self.env
         is_done = e.done.bool().clone()
-        if e.cfg.respawn_on_exit and self._stepped:
+        if (e.cfg.respawn_on_exit or e.cfg.testing_mode) and self._stepped:
             # :1462-1472 — respawn entry/exit crossers of envs that are NOT done (done envs are reset by the caller)
             keep = e.done.clone()
             e.done.zero_()
-            crossing = (e.agent_flags & (_lib.SGB_FLAG_ENTRY | _lib.SGB_FLAG_EXIT)) != 0
+            which = _lib.SGB_FLAG_ENTRY | _lib.SGB_FLAG_EXIT
+            if e.cfg.testing_mode:     # :1435-1447 — colliding agents are respawned one by one as well
+                which |= _lib.SGB_FLAG_COLLIDE_AGENT | _lib.SGB_FLAG_COLLIDE_LANE
+            crossing = (e.agent_flags & which) != 0
             crossing &= ~is_done.unsqueeze(1)
             saved = e.agent_flags.clone()
             e.agent_flags.mul_(crossing.to(torch.uint8))
@@ -230,22 +245,46 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
         self._stepped = False
         return is_done
 
-    # -- road_traffic.py:1489 (the keys evaluation / training code reads)
+    # -- road_traffic.py:1489-1635: every key of the reference's info dict
     def info(self, agent) -> Dict[str, torch.Tensor]:
-        e, i = self.env, agent.index
+        """Same keys, shapes and dtypes as ``ScenarioRoadTraffic.info``.  State entries are views of the packed
+        device state; what the step adds (fresh short-term path, distances, reward terms) comes from the
+        ``info`` block the fused kernel writes (``include/sigmarl_b200.h``); ``*_nom`` are the reference's
+        divisions by its normalizers (:587-608).  CBF / prioritized-MARL entries are out of scope."""
+        e, i, nm = self.env, agent.index, self._norm
         fl = e.agent_flags[:, i]
+        blk = e.info[:, i]
         two_pi = 2 * math.pi
-        rot = torch.remainder(e.pose[:, i, 2:3], two_pi)
+        rot = torch.remainder(e.pose[:, i, 2:3], two_pi)          # angle_eliminate_two_pi, helper_scenario.py:1276-1289
         rot = torch.where(rot > math.pi, rot - two_pi, rot)
+        pos, vel = e.pose[:, i, 0:2], e.aux[:, i, 1:3]
+        act_vel, act_steer = e.action[:, i, 0], e.action[:, i, 1]
+        ref = blk[:, 0:6]
+        d_ref, d_left, d_right = blk[:, 6], blk[:, 7], blk[:, 8]
+        z = self._zeros_bn
         return {
-            "pos": e.pose[:, i, 0:2], "rot": rot, "vel": e.aux[:, i, 1:3],
-            "act_vel": e.action[:, i, 0:1], "act_steer": e.action[:, i, 1:2],
-            "distance_ref": e.carry[:, i, 0:1],
+            "pos": pos, "pos_nom": pos / nm["pos_world"],
+            "rot": rot, "rot_nom": rot / nm["rot"],
+            "vel": vel, "vel_nom": vel / nm["v"],
+            "act_vel": act_vel, "act_vel_nom": act_vel / nm["v"],
+            "act_steer": act_steer, "act_steer_nom": act_steer / nm["steering"],
+            "ref": ref, "ref_nom": (ref.reshape(-1, 3, 2) / nm["pos_world"]).reshape(-1, 6),
+            "distance_ref": d_ref, "distance_ref_nom": d_ref / nm["dist"],
+            "distance_left_b": d_left, "distance_left_b_nom": d_left / nm["dist"],
+            "distance_right_b": d_right, "distance_right_b_nom": d_right / nm["dist"],
             "is_collision_with_agents": (fl & _lib.SGB_FLAG_COLLIDE_AGENT) != 0,
             "is_collision_with_lanelets": (fl & _lib.SGB_FLAG_COLLIDE_LANE) != 0,
             "is_reach_goal": (fl & _lib.SGB_FLAG_EXIT) != 0,
+            "ref_lanelet_ids": self._lanelet_ids[e.path_id[:, i].long()],
             "path_id": e.path_id[:, i],
-            "rew_total": e.reward[:, i],
+            # no CBF: nominal == applied == the policy's (clamped) action (:1527-1545)
+            "applied_action_vel": act_vel, "applied_action_steer": act_steer,
+            "nominal_action_vel": act_vel, "nominal_action_steer": act_steer,
+            # RewardInfo (helper_scenario.py:101-114): the reference writes five of the twelve fields
+            "rew_progress": z, "rew_reach_goal": blk[:, 12], "rew_speed": z, "rew_centerline": z,
+            "rew_near_other_agents": blk[:, 9], "rew_near_left_lane": z, "rew_near_right_lane": z,
+            "rew_collide_other_agents": blk[:, 10], "rew_collide_lane": blk[:, 11],
+            "rew_energy_acceleration": z, "rew_energy_steering": z, "rew_total": blk[:, 13],
         }
 
     def extra_render(self, env_index: int = 0):

@@ -34,11 +34,21 @@ def test_struct_layouts_match_header():
     from sigmarl_b200 import lib
     hdr = open(os.path.join(REPO, "include", "sigmarl_b200.h")).read()
     body = hdr[hdr.index("typedef struct {\n    float dt;"):hdr.index("} sgb_config;")]
-    n_float = sum(len(re.sub(r"/\*.*?\*/", "", line).split(";")[0].split(",")) if line.strip().startswith("float ") else 0
-                  for line in body.splitlines())
-    n_float += 2  # w_ref[3] is declared as one name
-    assert n_float == len(lib.CONFIG_FLOATS), (n_float, len(lib.CONFIG_FLOATS))
-    assert C.sizeof(lib.Config) == 4 * (len(lib.CONFIG_FLOATS) + 5)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S).replace("typedef struct {", "")
+    fields = []   # (name, ctype) in declaration order
+    ctypes_of = {"float": C.c_float, "int32_t": C.c_int32, "uint32_t": C.c_uint32}
+    for decl in body.split(";"):
+        m = re.match(r"\s*(float|int32_t|uint32_t)\s+(.*)", decl.strip().replace("\n", " "))
+        if not m:
+            continue
+        for name in m.group(2).split(","):
+            name = name.strip()
+            if name == "w_ref[SGB_N_SHORT_TERM]":
+                fields += [(f"w_ref{k}", C.c_float) for k in range(3)]
+            else:
+                fields.append((name, ctypes_of[m.group(1)]))
+    assert fields == list(lib.Config._fields_), (fields, lib.Config._fields_)
+    assert C.sizeof(lib.Config) == 4 * len(fields)
     bufs = hdr[hdr.index("typedef struct {\n    float*   pose;"):hdr.index("} sgb_buffers;")]
     names = re.findall(r"\*\s*([a-z_]+);", bufs)
     assert names == lib.BUFFER_FIELDS
@@ -135,8 +145,9 @@ def test_config_matches_reference_constants_in_goldens():
 def test_unsupported_flags_fail_loudly():
     from sigmarl_b200 import EnvConfig, MapLibrary
     m = MapLibrary("cpm_entire")
-    for kw in (dict(is_use_mtv_distance=True), dict(is_testing_mode=True), dict(rew_method="cbf"), dict(is_obs_noise=True)):
+    for kw in (dict(is_use_mtv_distance=True), dict(rew_method="cbf"), dict(is_obs_noise=True)):
         with pytest.raises(NotImplementedError):
             EnvConfig(scenario_type="cpm_entire", **kw).lower(m)
+    assert EnvConfig(scenario_type="cpm_entire", is_testing_mode=True).lower(m).testing_mode == 1   # supported since ABI 110
     with pytest.raises(ValueError):
         MapLibrary("no_such_map")

@@ -30,8 +30,9 @@ def _env_from_golden(g, B=None, **over):
         threshold_near_other_agents_c2c_low=float(g["cfg_near_other_agents_low"]),
         ttc_low=float(g["cfg_ttc_low"]), ttc_high=float(g["cfg_ttc_high"]),
         penalty_near_boundary=float(g["cfg_penalty_near_boundary"]),
-        penalty_near_other_agents=float(g["cfg_penalty_near_other_agents"]), **over)
-    return RoadTrafficEnv(cfg, num_envs=B or int(g["cfg_B"]), device="cuda:0", debug=True)
+        penalty_near_other_agents=float(g["cfg_penalty_near_other_agents"]),
+        is_testing_mode=bool(g["cfg_is_testing_mode"]), **over)
+    return RoadTrafficEnv(cfg, num_envs=B or int(g["cfg_B"]), device="cuda:0", debug=True, info=True)
 
 
 def _coll_matrix(env):
@@ -85,10 +86,28 @@ def test_cuda_matches_reference_goldens(path, exhaustive):
         assert np.array_equal((fl & 8) != 0, g["col_exit"][t]), f"{ctx} col_exit"
         assert np.array_equal(_coll_matrix(env), g["col_agents"][t]), f"{ctx} col_agents"
         assert np.array_equal((fl & 1) != 0, g["col_agents"][t].any(-1)), f"{ctx} any col_agents"
-        # respawn requests = entry/exit crossers of not-done envs (road_traffic.py:1462-1472)
-        req = ((fl & 12) != 0) & ~g["done"][t][:, None] & (str(g["cfg_scenario_type"]) != "cpm_entire")
+        # respawn requests = entry/exit crossers of not-done envs (road_traffic.py:1462-1472); in testing mode
+        # every colliding or leaving agent of a not-done env, on every map (:1435-1447)
+        if bool(g["cfg_is_testing_mode"]):
+            req = ((fl & 15) != 0) & ~g["done"][t][:, None]
+        else:
+            req = ((fl & 12) != 0) & ~g["done"][t][:, None] & (str(g["cfg_scenario_type"]) != "cpm_entire")
         assert np.array_equal(req, g["respawn_mask"][t]), f"{ctx} respawn"
         assert np.array_equal(env.step_count.cpu().numpy(), g["pre_step"][t] + 1), f"{ctx} step_count"
+        # the info block the kernel writes == what the reference's info(agent) returned in that step
+        blk = env.info.cpu().numpy()
+        _close("info.ref", blk[..., 0:6], g["info_ref"][t], ctx)
+        _close("info.distance_ref", blk[..., 6], g["info_distance_ref"][t], ctx)
+        _close("info.distance_left_b", blk[..., 7], g["info_distance_left_b"][t], ctx)
+        _close("info.distance_right_b", blk[..., 8], g["info_distance_right_b"][t], ctx)
+        _close("info.rew_near_other_agents", blk[..., 9], g["info_rew_near_other_agents"][t], ctx)
+        _close("info.rew_collide_other_agents", blk[..., 10], g["info_rew_collide_other_agents"][t], ctx)
+        _close("info.rew_collide_lane", blk[..., 11], g["info_rew_collide_lane"][t], ctx)
+        _close("info.rew_reach_goal", blk[..., 12], g["info_rew_reach_goal"][t], ctx)
+        _close("info.rew_total", blk[..., 13], g["info_rew_total"][t], ctx)
+        # evaluation counters accumulate over the run (:998-1002, :1029-1035)
+        assert np.array_equal(env.task_tries.cpu().numpy(), g["num_task_tries"][t]), f"{ctx} num_task_tries"
+        assert np.array_equal(env.task_success.cpu().numpy(), g["task_success_times"][t]), f"{ctx} task_success_times"
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
@@ -320,7 +339,7 @@ def test_library_refuses_bad_arguments():
     from sigmarl_b200 import lib
     L = lib.load_library()
     assert L.sgb_step(None, 1, 1, None, None) == -1
-    assert L.sgb_version() == 100
+    assert L.sgb_version() == 110
 
 
 @pytest.mark.parametrize("name", ["c1_intersection_B4_N2", "cpm_entire_B8_N8_distance", "cpm_mixed_B8_N4_gentle"])
@@ -424,3 +443,97 @@ def test_facade_done_respawns_exit_crossers_like_reference_flow():
             env.reset_at(e)
         sc.env.reset_done(write_obs=True)  # remaining done envs in one launch
     assert respawned > 0
+
+
+class _Params:
+    """Attribute bag standing in for the reference's ``Parameters`` object (helper_common.py:26-252)."""
+
+
+def _facade_from_golden(g):
+    from sigmarl_b200.scenario import ScenarioRoadTrafficB200
+    sc = ScenarioRoadTrafficB200()
+    kw = dict(
+        scenario_type=str(g["cfg_scenario_type"]), n_agents=int(g["cfg_N"]), dt=float(g["cfg_dt"]),
+        max_steps=int(g["cfg_max_steps"]), rew_method=str(g["cfg_rew_method"]),
+        n_nearing_agents_observed=int(g["cfg_n_nearing_agents_observed"]),
+        reward_progress=float(g["cfg_reward_progress"]),
+        threshold_near_boundary_high=float(g["cfg_near_boundary_high"]),
+        threshold_near_boundary_low=float(g["cfg_near_boundary_low"]),
+        threshold_near_other_agents_c2c_high=float(g["cfg_near_other_agents_high"]),
+        threshold_near_other_agents_c2c_low=float(g["cfg_near_other_agents_low"]),
+        ttc_low=float(g["cfg_ttc_low"]), ttc_high=float(g["cfg_ttc_high"]),
+        penalty_near_boundary=float(g["cfg_penalty_near_boundary"]),
+        penalty_near_other_agents=float(g["cfg_penalty_near_other_agents"]),
+        is_testing_mode=bool(g["cfg_is_testing_mode"]))
+    if str(g["cfg_mode"]) == "params":     # mappo_cavs.py:168-169: scenario.parameters = parameters; make_world(...)
+        p = _Params()
+        for k, v in kw.items():
+            setattr(p, k, v)
+        sc.parameters = p
+        world = sc.env_make_world(int(g["cfg_B"]), "cuda:0")
+    else:
+        world = sc.env_make_world(int(g["cfg_B"]), "cuda:0", **kw)
+    return sc, world
+
+
+@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+def test_facade_info_matches_reference_goldens(path):
+    """ScenarioRoadTrafficB200.info(agent): every key of the reference's info dict (road_traffic.py:1547-1633),
+    same shapes / dtypes, values within 1e-5 (bit-exact for masks and ids), teacher-forced from the goldens."""
+    g = np.load(path)
+    sc, world = _facade_from_golden(g)
+    env = sc.env
+    keys = sorted(k[5:] for k in g.files if k.startswith("info_"))
+    assert len(keys) == 39
+    for t in range(0, int(g["cfg_T"]), 3):
+        ctx = f"{os.path.basename(path)} t={t}"
+        gp = env.map.global_path(g["pre_scenario_id"][t], g["pre_path_id"][t])
+        env.set_state(g["pre_pos"][t], g["pre_rot"][t], g["pre_speed"][t], g["pre_steering"][t], gp,
+                      step_count=g["pre_step"][t])
+        for i, agent in enumerate(world.agents):
+            agent.action.u = torch.as_tensor(g["action"][t][:, i]).cuda()
+        world.step()
+        infos = [sc.info(agent) for agent in world.agents]
+        assert sorted(infos[0].keys()) == keys, f"{ctx}: info keys differ from the reference's"
+        # state entries of the fixtures are views the reference mutates when it respawns an agent inside done()
+        keep = ~g["respawn_mask"][t]
+        for k in keys:
+            want = g["info_" + k][t]
+            got = torch.stack([torch.as_tensor(d[k]).reshape(env.B, -1).squeeze(-1) for d in infos], dim=1).cpu().numpy()
+            assert got.shape == want.shape, f"{ctx} info[{k}] shape {got.shape} vs {want.shape}"
+            if want.dtype == np.bool_ or np.issubdtype(want.dtype, np.integer):
+                assert got.dtype == want.dtype, f"{ctx} info[{k}] dtype {got.dtype} vs {want.dtype}"
+                assert np.array_equal(got[keep], want[keep]), f"{ctx} info[{k}] not bit-exact"
+            else:
+                _close(f"info[{k}]", got[keep], want[keep], ctx)
+        sc.done()
+
+
+def test_facade_testing_mode_respawns_colliding_agents_and_never_ends_early():
+    """is_testing_mode (road_traffic.py:1429-1447): an env is done only at the time limit; colliding / leaving
+    agents of not-done envs are re-placed one by one inside done(); reward = progress + sparse terms (:1050-1055)."""
+    from sigmarl_b200 import make_env
+    B, N = 256, 6
+    env = make_env(scenario_type="cpm_entire", num_envs=B, device="cuda:0", n_agents=N, seed=3, max_steps=24, dt=0.1,
+                   is_testing_mode=True)
+    sc = env.scenario
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    ur = torch.as_tensor(UR).cuda()
+    n_resp = 0
+    for t in range(30):
+        for agent in env.agents:
+            agent.action.u = (torch.rand(B, 2, device="cuda", generator=gen) * 2 - 1) * ur
+        sc.world.step()
+        flags, pose_before = sc.env.agent_flags.clone(), sc.env.pose.clone()
+        step = sc.env.step_count.clone()
+        rew = sc.env.reward.clone()
+        dones = sc.done()
+        assert torch.equal(dones, step == 24 - 1), "testing mode: only the time limit ends an env"
+        hit = ((flags & 15) != 0) & ~dones[:, None]
+        moved = (sc.env.pose[..., :2] != pose_before[..., :2]).any(-1)
+        assert torch.equal(moved, hit)
+        # colliding agents carry the full collision penalty (reward clamps at -1)
+        assert bool((rew[(flags & 3) != 0] <= -0.8).all())
+        n_resp += int(hit.sum())
+        sc.env.reset_done(write_obs=True)
+    assert n_resp > 0 and int(sc.env.n_failed) == 0
