@@ -33,11 +33,6 @@ namespace sgb {
 #ifndef SGB_SYNC_WARPS          // warps per phase-aligned group in the step kernel (0/1 = free-running warps)
 #define SGB_SYNC_WARPS 8
 #endif
-#ifndef SGB_SYNC_INTERLEAVED     // 1: group = warp %% n_groups (warps of one group share an SM sub-partition)
-#define SGB_SYNC_GROUP(w, sw) ((w) / (sw))
-#else
-#define SGB_SYNC_GROUP(w, sw) ((w) % (SGB_THREADS / 32 / (sw)))
-#endif
 #ifndef SGB_SYNC_WARPS_REFRESH  // same for the refresh kernel (short compacted env lists: free-running)
 #define SGB_SYNC_WARPS_REFRESH 0
 #endif
@@ -642,17 +637,30 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     constexpr int SYNCW = step_mode ? SGB_SYNC_WARPS : SGB_SYNC_WARPS_REFRESH;
     auto phase_sync = [&]() {
         if (SYNCW >= kWarps) __syncthreads();
-        else if (SYNCW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + SGB_SYNC_GROUP(w, (SYNCW > 0 ? SYNCW : 1))), "r"(SYNCW * 32) : "memory");
+        else if (SYNCW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + w / (SYNCW > 0 ? SYNCW : 1)), "r"(SYNCW * 32) : "memory");
         else __syncwarp();
     };
     const int stride_wt = gridDim.x * kWarps;
     const int n_iter = SYNCW > 1 ? (n_wt - (int)blockIdx.x * kWarps + stride_wt - 1) / stride_wt : (1 << 30);
     for (int it = 0, wt = blockIdx.x * kWarps + w; it < n_iter && (SYNCW > 1 || wt < n_wt); it++, wt += stride_wt) {
         // ================= phase A: one lane per agent ============================================  @region phase A
-        if (ln < n_slots) {
-            const int st = slot0 + ln;
-            const int ei = wt * EW + ln / N;
-            const int i = ln % N;
+        // Which agent this thread integrates.  Free-running warps: lane l of a warp takes slot l of its own warp
+        // (n_slots of 32 lanes busy).  Phase-aligned groups: the group's SYNCW * n_slots agents are dealt to the
+        // first threads of the group, so whole warps are busy and the others go straight to the barrier (the
+        // transcendental-heavy phase then issues 32/n_slots x fewer warp instructions).
+        int a_w = w, a_sl = ln;
+        bool a_on = ln < n_slots;
+        if (SYNCW > 1 && SYNCW < kWarps + 1) {
+            const int gw0 = w - w % SYNCW;                       // first warp of this thread's group (consecutive grouping)
+            const int tg = (w - gw0) * 32 + ln;                  // thread index within the group
+            a_on = tg < SYNCW * n_slots;
+            a_w = gw0 + tg / n_slots;
+            a_sl = tg % n_slots;
+        }
+        if (a_on) {
+            const int st = a_w * SPW + a_sl;
+            const int ei = (wt - w + a_w) * EW + a_sl / N;
+            const int i = a_sl % N;
             const bool active = ei < n_envs;
             int e = -1;
             if (active) {
@@ -812,6 +820,18 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     int lo = 0, rem = pi;               // pair index -> (lo, hi), lo < hi
                     while (rem >= N - 1 - lo) { rem -= N - 1 - lo; lo++; }
                     const int hi = lo + 1 + rem;
+                    {
+                        // Gate (same certificate as for boundary segments): rectangles whose centres are farther
+                        // apart than two circumradii + kFarMargin cannot touch, and interX can then only fire
+                        // through fp32 sign noise on edges that are collinear within kCollinear.
+                        const float ddx = ts.px[sbase + hi] - ts.px[sbase + lo], ddy = ts.py[sbase + hi] - ts.py[sbase + lo];
+                        const float c1 = ts.cs[sbase + lo], s1 = ts.sn[sbase + lo], c2 = ts.cs[sbase + hi], s2 = ts.sn[sbase + hi];
+                        const float cr = c1 * s2 - s1 * c2, dt = c1 * c2 + s1 * s2;   // sin / cos of the heading difference
+                        const float reach = 2.0f * rect_radius + kFarMargin;
+                        if (!cfg.exhaustive && ddx * ddx + ddy * ddy > reach * reach &&
+                            fminf(fabsf(cr), fabsf(dt)) > kCollinear)
+                            continue;
+                    }
                     Rect rl;
                     float hx[4], hy[4];
 #pragma unroll
@@ -1039,7 +1059,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 }
             }
         }
-        phase_sync();
+        __syncwarp();   // phase D reads this warp's own slots only
 
         // ================= phase D: per-env outputs ===============================================  @region phase D
         if (step_mode && ln < n_slots && (ln % N) == 0 && ts.flags[slot0 + ln] >= 0) {
@@ -1061,7 +1081,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                             (!cfg.testing_mode && (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE)));
             p.buf.done[e] = dn ? 1 : 0;
         }
-        __syncwarp();   // phase D -> next tile's phase A touch this warp's own slots only: no group barrier
+        phase_sync();   // the next tile's phase A (dealt over the whole group) overwrites these slots
     }
     if (!map_ready) mbar_wait(bar, 0); // never leave with a bulk copy in flight
 }
