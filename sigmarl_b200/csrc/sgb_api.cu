@@ -436,6 +436,9 @@ extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
         sub.step_count += e0; sub.obs += a0 * D; sub.reward += a0; sub.done += e0; sub.agent_flags += a0;
         if (sub.collide_with) sub.collide_with += a0;
         if (sub.dbg) sub.dbg += a0 * 16;
+        if (sub.info) sub.info += a0 * SGB_INFO_DIM;
+        if (sub.task_tries) sub.task_tries += e0;
+        if (sub.task_success) sub.task_success += e0;
         CK(cudaMemcpyAsync(sub.action, h_action + a0 * 2, (size_t)nb * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
         rc = launch_env(c, nb, N, &sub, 0, nullptr, nullptr, 1, s);
         if (rc) return rc;

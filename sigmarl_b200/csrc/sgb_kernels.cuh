@@ -205,12 +205,7 @@ __device__ __forceinline__ float box_lb(float4 bx, float px, float py) { return 
 struct Rect {
     float vx[4], vy[4];    // vertices 0..3 (vertex 4 == vertex 0)
     float dx[4], dy[4], S[4]; // per edge i: v[i] -> v[i+1]
-    float bcx, bcy, bhx, bhy; // centre and half extents of the axis-aligned bounding box of the four vertices
     __device__ __forceinline__ void finish() {
-        const float x0 = fminf(fminf(vx[0], vx[1]), fminf(vx[2], vx[3])), x1 = fmaxf(fmaxf(vx[0], vx[1]), fmaxf(vx[2], vx[3]));
-        const float y0 = fminf(fminf(vy[0], vy[1]), fminf(vy[2], vy[3])), y1 = fmaxf(fmaxf(vy[0], vy[1]), fmaxf(vy[2], vy[3]));
-        bcx = 0.5f * (x0 + x1); bcy = 0.5f * (y0 + y1);
-        bhx = 0.5f * (x1 - x0) + 1e-6f; bhy = 0.5f * (y1 - y0) + 1e-6f;   // + rounding slack of the centre
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             int j = (i + 1) & 3;
@@ -224,20 +219,27 @@ struct Rect {
 // interX of the rectangle (as L1) against ONE segment a->b of L2; exact predicate.  C2 first: when all four  @region rect_cross_seg_L1
 // vertices lie strictly on one side of (or on) the segment's line no edge can cross it, and the four C1 terms
 // are skipped (same values as the reference would compute, just not evaluated).
-__device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float ay, float bx, float by,
+__device__ __forceinline__ bool rect_cross_seg_L1(const float* rvx, const float* rvy, float ax, float ay, float bx, float by,
                                                   bool no_filter = false) {
+    // Takes the bare vertices: the edge vectors / S_i and the bounding box are rebuilt here, in the same fp32
+    // operations as Rect::finish(), because this function runs for few segments (see the gate in scan_boundary)
+    // and the scan must not carry them in registers.
     const float dx2 = bx - ax, dy2 = by - ay;
     if (!no_filter) {
         // Cheapest filter first (fused arithmetic, certified by a margin): g at the bounding-box centre, and the
         // largest change of g over the box.  |g(c)| - (|dx2| hy + |dy2| hx) > 1e-5 >> fp32 error of g (~3e-7)
         // => all four vertices are strictly on one side of the segment's line => no C2 term can be true.
-        const float gc = dx2 * (r.bcy - ay) - dy2 * (r.bcx - ax);
-        if (fabsf(gc) > fabsf(dx2) * r.bhy + fabsf(dy2) * r.bhx + 1e-5f) return false;
+        const float x0 = fminf(fminf(rvx[0], rvx[1]), fminf(rvx[2], rvx[3])), x1 = fmaxf(fmaxf(rvx[0], rvx[1]), fmaxf(rvx[2], rvx[3]));
+        const float y0 = fminf(fminf(rvy[0], rvy[1]), fminf(rvy[2], rvy[3])), y1 = fmaxf(fmaxf(rvy[0], rvy[1]), fmaxf(rvy[2], rvy[3]));
+        const float bcx = 0.5f * (x0 + x1), bcy = 0.5f * (y0 + y1);
+        const float bhx = 0.5f * (x1 - x0) + 1e-6f, bhy = 0.5f * (y1 - y0) + 1e-6f;   // + rounding slack of the centre
+        const float gc = dx2 * (bcy - ay) - dy2 * (bcx - ax);
+        if (fabsf(gc) > fabsf(dx2) * bhy + fabsf(dy2) * bhx + 1e-5f) return false;
     }
     const float S2 = msub2(dx2, ay, dy2, ax);
     float g[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) g[i] = subr(msub2(r.vy[i], dx2, r.vx[i], dy2), S2);
+    for (int i = 0; i < 4; i++) g[i] = subr(msub2(rvy[i], dx2, rvx[i], dy2), S2);
     bool c2[4];
     bool any2 = false;
 #pragma unroll
@@ -246,8 +248,11 @@ __device__ __forceinline__ bool rect_cross_seg_L1(const Rect& r, float ax, float
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const float fa = subr(msub2(r.dx[i], ay, r.dy[i], ax), r.S[i]);
-        const float fb = subr(msub2(r.dx[i], by, r.dy[i], bx), r.S[i]);
+        const int j = (i + 1) & 3;
+        const float dxi = rvx[j] - rvx[i], dyi = rvy[j] - rvy[i];
+        const float Si = msub2(dxi, rvy[i], dyi, rvx[i]);
+        const float fa = subr(msub2(dxi, ay, dyi, ax), Si);
+        const float fb = subr(msub2(dxi, by, dyi, bx), Si);
         hit |= (((fa * fb) < 0.0f) & c2[i]);
     }
     return hit;
@@ -287,25 +292,25 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
 // Edges 0/2 and 1/3 are anti-parallel (d_2 = -d_0 up to ~1e-6 rounding), so f_2(q) = f_0(v_2) - f_0(q) and
 // f_3(q) = f_1(v_3) - f_1(q) up to ~1e-5, which kSignMargin absorbs: two evaluations certify four edges.
 struct SignCert {
-    float k0, k1;           // f_0(v_2), f_1(v_3)
-    float ax0, ay0, ax1, ay1; // |dx|, |dy| of edges 0 and 1
-    __device__ __forceinline__ void init(const Rect& r) {
-        k0 = (r.dx[0] * r.vy[2] - r.dy[0] * r.vx[2]) - r.S[0];
-        k1 = (r.dx[1] * r.vy[3] - r.dy[1] * r.vx[3]) - r.S[1];
-        ax0 = fabsf(r.dx[0]); ay0 = fabsf(r.dy[0]); ax1 = fabsf(r.dx[1]); ay1 = fabsf(r.dy[1]);
+    float dx0, dy0, S0, dx1, dy1, S1; // edges 0 and 1
+    float k0, k1;                     // f_0(v_2), f_1(v_3)
+    __device__ __forceinline__ void init(const float* vx, const float* vy) {
+        dx0 = vx[1] - vx[0]; dy0 = vy[1] - vy[0]; S0 = msub2(dx0, vy[0], dy0, vx[0]);
+        dx1 = vx[2] - vx[1]; dy1 = vy[2] - vy[1]; S1 = msub2(dx1, vy[1], dy1, vx[1]);
+        k0 = (dx0 * vy[2] - dy0 * vx[2]) - S0;
+        k1 = (dx1 * vy[3] - dy1 * vx[3]) - S1;
     }
 };
-__device__ __forceinline__ bool box_sign_definite(const Rect& r, const SignCert& sc, float4 bx) {
+__device__ __forceinline__ bool box_sign_definite(const SignCert& sc, float4 bx) {
     const float cx = 0.5f * (bx.x + bx.z), cy = 0.5f * (bx.y + bx.w);
     const float hx = 0.5f * (bx.z - bx.x), hy = 0.5f * (bx.w - bx.y);
-    const float f0 = (r.dx[0] * cy - r.dy[0] * cx) - r.S[0];
-    const float f1 = (r.dx[1] * cy - r.dy[1] * cx) - r.S[1];
-    const float rad0 = sc.ax0 * hy + sc.ay0 * hx + kSignMargin;
-    const float rad1 = sc.ax1 * hy + sc.ay1 * hx + kSignMargin;
+    const float f0 = (sc.dx0 * cy - sc.dy0 * cx) - sc.S0;
+    const float f1 = (sc.dx1 * cy - sc.dy1 * cx) - sc.S1;
+    const float rad0 = fabsf(sc.dx0) * hy + fabsf(sc.dy0) * hx + kSignMargin;
+    const float rad1 = fabsf(sc.dx1) * hy + fabsf(sc.dy1) * hx + kSignMargin;
     return (fabsf(f0) > rad0) & (fabsf(sc.k0 - f0) > rad0) & (fabsf(f1) > rad1) & (fabsf(sc.k1 - f1) > rad1);
 }
 
-// @region group shuffles
 template <int G>
 __device__ __forceinline__ float group_min(float v) {
 #pragma unroll
@@ -421,14 +426,14 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
 template <int G>
 __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes,
                                               const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
-                                              float px, float py, float cs, float sn, float psi_m, const Rect& r,
+                                              float px, float py, float cs, float sn, float psi_m, const float* rvx, const float* rvy,
                                               float rect_radius, int lane, float& d_cg, float dv[4], bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
     int c0 = hint_seg / kChunk;
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
     SignCert cert;
-    cert.init(r);
+    cert.init(rvx, rvy);
     const float near_r = rect_radius + kFarMargin;
     const float near2 = near_r * near_r;      // segments farther than this from the centre cannot touch the rectangle
     BestQ bq[5]; // 0 = centre, 1..4 = vertices
@@ -441,8 +446,8 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
 #pragma unroll
     for (int k = 0; k < (4 + G - 1) / G; k++) {         // select without dynamic register indexing
         const int v = lane + k * G;
-        myvx[k] = v == 0 ? r.vx[0] : (v == 1 ? r.vx[1] : (v == 2 ? r.vx[2] : r.vx[3]));
-        myvy[k] = v == 0 ? r.vy[0] : (v == 1 ? r.vy[1] : (v == 2 ? r.vy[2] : r.vy[3]));
+        myvx[k] = v == 0 ? rvx[0] : (v == 1 ? rvx[1] : (v == 2 ? rvx[2] : rvx[3]));
+        myvy[k] = v == 0 ? rvy[0] : (v == 1 ? rvy[1] : (v == 2 ? rvy[2] : rvy[3]));
         myq[k] = 0.0f;
     }
     uint32_t md = 1u << c0, mx = 1u << c0;
@@ -493,8 +498,8 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
 #pragma unroll
                     for (int v = 0; v < 4; v++)
                         if (need & (2u << v))
-                            bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, r.vx[v], r.vy[v]),
-                                                seg_q_r(a2.x, a2.y, lx2, ly2, rl2, r.vx[v], r.vy[v])));
+                            bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, rvx[v], rvy[v]),
+                                                seg_q_r(a2.x, a2.y, lx2, ly2, rl2, rvx[v], rvy[v])));
                 }
                 if (do_x) {
                     // Gate of the exact predicate: the segment is near the rectangle (then the chunk is a near chunk
@@ -504,8 +509,8 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                     const float cr2 = lx2 * sn - ly2 * cs, dt2 = lx2 * cs + ly2 * sn;
                     const bool ga = exhaustive | (q0a <= near2) | (fminf(cr * cr, dt * dt) <= (kCollinear * kCollinear) * len2);
                     const bool gb = exhaustive | (q0b <= near2) | (fminf(cr2 * cr2, dt2 * dt2) <= (kCollinear * kCollinear) * len2b);
-                    if (ga) hit |= rect_cross_seg_L1(r, a.x, a.y, e.x, e.y, exhaustive);
-                    if (gb) hit |= rect_cross_seg_L1(r, a2.x, a2.y, e2.x, e2.y, exhaustive);
+                    if (ga) hit |= rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y, exhaustive);
+                    if (gb) hit |= rect_cross_seg_L1(rvx, rvy, a2.x, a2.y, e2.x, e2.y, exhaustive);
                 }
             }
         }
@@ -537,7 +542,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
             float da = fabsf(psi_m - cone.x);
             da = fminf(da, pi_f - da);
             const bool in_cone = (da <= cone.y) | ((half_pi - da) <= cone.y);
-            if (exhaustive || !(lb2 > near2) || (in_cone && !box_sign_definite(r, cert, bx))) mx |= 1u << c;
+            if (exhaustive || !(lb2 > near2) || (in_cone && !box_sign_definite(cert, bx))) mx |= 1u << c;
         }
         md = group_or<G>(md);
         mx = group_or<G>(mx);
@@ -635,6 +640,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     // therefore walk the phases together (named barrier per group): at any time a group executes one phase's
     // code only.  Every warp of the CTA runs the same number of tile iterations so that the barriers match.
     constexpr int SYNCW = step_mode ? SGB_SYNC_WARPS : SGB_SYNC_WARPS_REFRESH;
+    static_assert(SYNCW <= 1 || (kWarps % (SYNCW > 0 ? SYNCW : 1) == 0 && kWarps / (SYNCW > 0 ? SYNCW : 1) <= 15), "phase-aligned groups must tile the CTA (named barriers 1..15)");
     auto phase_sync = [&]() {
         if (SYNCW >= kWarps) __syncthreads();
         else if (SYNCW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + w / (SYNCW > 0 ? SYNCW : 1)), "r"(SYNCW * 32) : "memory");
@@ -651,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         int a_w = w, a_sl = ln;
         bool a_on = ln < n_slots;
         if (SYNCW > 1 && SYNCW < kWarps + 1) {
-            const int gw0 = w - w % SYNCW;                       // first warp of this thread's group (consecutive grouping)
+            const int gw0 = w - w % (SYNCW > 0 ? SYNCW : 1);                       // first warp of this thread's group (consecutive grouping)
             const int tg = (w - gw0) * 32 + ln;                  // thread index within the group
             a_on = tg < SYNCW * n_slots;
             a_w = gw0 + tg / n_slots;
@@ -746,13 +752,12 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         const PathRec pr = paths[path];
         {
             const float px = slot_ok ? ts.px[sl] : 0.0f, py = slot_ok ? ts.py[sl] : 0.0f;
-            Rect r;
+            float rvx[4], rvy[4];   // the agent's rectangle (vertices only: keeps the scans' register footprint small)
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                r.vx[k] = slot_ok ? ts.vtx[k * AS + sl] : 0.0f;
-                r.vy[k] = slot_ok ? ts.vtx[(4 + k) * AS + sl] : 0.0f;
+                rvx[k] = slot_ok ? ts.vtx[k * AS + sl] : 0.0f;
+                rvy[k] = slot_ok ? ts.vtx[(4 + k) * AS + sl] : 0.0f;
             }
-            r.finish();
             const bool ex = cfg.exhaustive != 0;
             // hint = last closest segment (step) / the spawn point written by place_agent (refresh); any value
             // is valid, a good one lets the first chunk scanned set a tight pruning bound
@@ -772,7 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 bool hit;
                 scan_boundary<G>(pts + (side ? pr.r_off : pr.l_off), boxes + (side ? pr.rbox : pr.lbox),
                                  cones + (side ? pr.rcone : pr.lcone), side ? pr.n_r : pr.n_l, h2, ex, px, py, cs_h, sn_h,
-                                 psi_m, r, rect_radius, lane, dc, dvv, hit);
+                                 psi_m, rvx, rvy, rect_radius, lane, dc, dvv, hit);
                 if (side) { dRc = dc; hitR = hit; dRv[0] = dvv[0]; dRv[1] = dvv[1]; dRv[2] = dvv[2]; dRv[3] = dvv[3]; }
                 else      { dLc = dc; hitL = hit; dLv[0] = dvv[0]; dLv[1] = dvv[1]; dLv[2] = dvv[2]; dLv[3] = dvv[3]; }
             }
@@ -786,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
 #pragma unroll 1
                 for (int k = 0; k < 2; k++) {
                     const float2 a = L[k ? pr.n_l - 1 : 0], e = R[k ? pr.n_r - 1 : 0];
-                    if (rect_cross_seg_L1(r, a.x, a.y, e.x, e.y)) fl |= (int)(k ? SGB_FLAG_EXIT : SGB_FLAG_ENTRY);
+                    if (rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y)) fl |= (int)(k ? SGB_FLAG_EXIT : SGB_FLAG_ENTRY);
                 }
             }
             if (slot_ok && lane == 0) {

@@ -322,16 +322,22 @@ def test_vmas_facade_drives_the_same_kernel():
         ref.carry.copy_(sc.env.carry); ref.step_count.copy_(sc.env.step_count)
 
 
-def test_host_buffer_step_matches_device_step():
+@pytest.mark.parametrize("B", [512, 8192 + 40])
+def test_host_buffer_step_matches_device_step(B):
+    """sgb_step_host (chunked copy / compute pipeline for B >= 1024) == sgb_step on every buffer, incl. info."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
-    a = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=512, device="cuda:0", seed=4)
-    b = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=512, device="cuda:0", seed=4)
+    a = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=B, device="cuda:0", seed=4, info=True)
+    b = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=B, device="cuda:0", seed=4, info=True)
     a.reset(); b.reset()
-    act = ((torch.rand(512, 8, 2) * 2 - 1) * torch.as_tensor(UR)).contiguous().pin_memory()
-    h_obs, h_rew, h_done = a.step_host(act)
-    obs, rew, done = b.step(act.cuda())
-    torch.cuda.synchronize()
-    assert torch.equal(h_obs, obs.cpu()) and torch.equal(h_rew, rew.cpu()) and torch.equal(h_done, done.cpu())
+    for _ in range(3):
+        act = ((torch.rand(B, 8, 2) * 2 - 1) * torch.as_tensor(UR)).contiguous().pin_memory()
+        h_obs, h_rew, h_done = a.step_host(act)
+        obs, rew, done = b.step(act.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(h_obs, obs.cpu()) and torch.equal(h_rew, rew.cpu()) and torch.equal(h_done, done.cpu())
+        for name in ("pose", "aux", "carry", "agent_flags", "collide_with", "step_count", "info", "task_tries", "task_success"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        a.reset_done(); b.reset_done()
 
 
 def test_library_refuses_bad_arguments():
