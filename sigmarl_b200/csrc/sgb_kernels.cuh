@@ -396,11 +396,12 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
         }
     };
     chunk(c0);
-    const float thr = group_min<G>(b.d) + kDistMargin;
+    float thr = group_min<G>(b.d) + kDistMargin;
+    thr = thr * thr;
     uint32_t m = 0;
-    for (int c = lane; c < nch; c += G)
-        if (c != c0 && (exhaustive || !(box_lb(boxes[c], px, py) > thr))) m |= 1u << c;
-    m = group_or<G>(m);
+    for (int c = lane; c < nch; c += G) m |= (box_lb2(boxes[c], px, py) > thr) ? 0u : (1u << c);
+    if (exhaustive) m = 0xffffffffu;
+    m = group_or<G>(m) & (nch >= 32 ? 0xffffffffu : ((1u << nch) - 1u)) & ~(1u << c0);
 #pragma unroll 1
     while (m) {
         const int c = __ffs(m) - 1;
@@ -531,18 +532,23 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
         thr = thr * thr;
         md = 0; mx = 0;
         const float pi_f = 3.14159274f, half_pi = 1.57079637f;
-        for (int c = lane; c < nch; c += G) {
-            if (c == c0) continue;
+        for (int c = lane; c < nch; c += G) {   // branch-free except for the (rare) edge-line test; c0 is masked out below
             const float4 bx = boxes[c];
             const float2 cone = __half22float2(cones[c]);
             const float lb2 = box_lb2(bx, px, py);
-            if (exhaustive || !(lb2 > thr)) md |= 1u << c;
+            const uint32_t bit = 1u << c;
+            md |= (lb2 > thr) ? 0u : bit;
             // crossing candidates: near chunks, and far chunks that hold a segment direction within the cone slack
             // of the heading or its normal AND are crossed by an edge line (otherwise C1 is certified false)
             float da = fabsf(psi_m - cone.x);
-            da = fminf(da, pi_f - da);
-            const bool in_cone = (da <= cone.y) | ((half_pi - da) <= cone.y);
-            if (exhaustive || !(lb2 > near2) || (in_cone && !box_sign_definite(cert, bx))) mx |= 1u << c;
+            da = fminf(da, pi_f - da);                       // angle between heading and cone axis, mod pi
+            if (!(lb2 > near2)) mx |= bit;
+            else if (fminf(da, half_pi - da) <= cone.y && !box_sign_definite(cert, bx)) mx |= bit;
+        }
+        if (exhaustive) { md = 0xffffffffu; mx = 0xffffffffu; }
+        {
+            const uint32_t live = (nch >= 32 ? 0xffffffffu : ((1u << nch) - 1u)) & ~(1u << c0);
+            md &= live; mx &= live;
         }
         md = group_or<G>(md);
         mx = group_or<G>(mx);
