@@ -243,6 +243,81 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_rollout(args):
+    """--workload rollout: BASELINE configs[4] shape per GPU (CPM map, T=128 rollout + GAE + the all-gather of the
+    advantage / value-target buffers at PPO-update time).  The policy / critic networks are
+    dense NN work outside the path: actions and values are pre-generated on the device."""
+    import torch
+    import torch.distributed as dist
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    from sigmarl_b200.rollout import RolloutBuffer, all_gather_advantages, collect, compute_gae
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, T, K, W = args.envs, args.agents, args.horizon, args.steps, max(1, min(args.warmup, 2))
+    env = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=N, mode="params", rew_method="distance"),
+                         num_envs=B, device=dev, seed=args.seed, env_offset=rank * B)
+    env.reset()
+    buf = RolloutBuffer(T, B, N, env.D, dev, world=world, rank=rank)
+    ur = torch.tensor([1.0, 31 * np.pi / 180], device=dev)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    acts = (torch.rand(T, B, N, 2, device=dev, generator=gen) * 2 - 1) * ur
+    buf.value.copy_(torch.rand(T, B, N, device=dev, generator=gen))
+    buf.next_value.copy_(torch.rand(T, B, N, device=dev, generator=gen))
+    step = {"t": 0}
+
+    def policy(_obs):
+        a = acts[step["t"] % T]
+        step["t"] += 1
+        return a
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        collect(env, policy, buf)
+        ev[1].record()
+        compute_gae(buf, 0.99, 0.9)
+        ev[2].record()
+        all_gather_advantages(buf)
+        ev[3].record()
+        return ev
+
+    for _ in range(W):
+        one()
+    barrier()
+    l0 = env.launches
+    evs = [one() for _ in range(K)]
+    barrier()
+    t = torch.tensor([sum(e[0].elapsed_time(e[3]) for e in evs), sum(e[0].elapsed_time(e[1]) for e in evs),
+                      sum(e[1].elapsed_time(e[2]) for e in evs), sum(e[2].elapsed_time(e[3]) for e in evs)],
+                     device=dev, dtype=torch.float64) * 1e-3
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_all, t_col, t_gae, t_ag = [float(x) for x in t]
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC + " — full rollout + GAE + all-gather", "value": world * B * N * T * K / t_all,
+            "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": 1e3 * t_all / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cpm_entire num_envs={B} n_agents={N} per GPU, T={T} rollout (step + masked reset with fresh "
+                                   f"obs + [T,B,N,*] buffer writes) + GAE kernel + NCCL all-gather of advantage/value target",
+                       "policy": "pre-generated actions/values (NN forward is outside the path)"},
+            "breakdown_ms": {"collect": 1e3 * t_col / K, "gae": 1e3 * t_gae / K, "all_gather": 1e3 * t_ag / K},
+            "gathered_bytes_per_rank": 2 * T * B * N * 4, "gpu_launches": env.launches - l0 + K}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -254,8 +329,13 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=4096, help="bounded sample for the CPU arm")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="step", choices=["step", "rollout"],
+                    help="step = the headline metric (default); rollout = T-step rollout + GAE + all-gather (extra line)")
+    ap.add_argument("--horizon", type=int, default=128, help="rollout length T (max_steps, config.json)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "rollout" and args.impl == "ours":
+        run_rollout(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

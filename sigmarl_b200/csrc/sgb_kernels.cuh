@@ -755,7 +755,10 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         const int sl = slot_ok ? slot0 + sl_l : slot0;
         int path = slot_ok ? ts.path[sl] : 0;
         path = (path < 0 || path >= hdr->n_paths) ? 0 : path;
-        const PathRec pr = paths[path];
+        // Path record fields are read from shared memory where they are used, and every scan result goes to the
+        // slot arrays as soon as it exists: nothing but the path index stays live across the three scans (the
+        // kernel runs at the 64-register cap of a 1024-thread CTA; what is live across a scan gets spilled).
+        const PathRec* prp = paths + path;
         {
             const float px = slot_ok ? ts.px[sl] : 0.0f, py = slot_ok ? ts.py[sl] : 0.0f;
             float rvx[4], rvy[4];   // the agent's rectangle (vertices only: keeps the scans' register footprint small)
@@ -765,58 +768,58 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 rvy[k] = slot_ok ? ts.vtx[(4 + k) * AS + sl] : 0.0f;
             }
             const bool ex = cfg.exhaustive != 0;
+            const bool writer = slot_ok && lane == 0;
+            float* dbg = (p.buf.dbg && writer) ? p.buf.dbg + ((size_t)ts.env[sl] * N + (sl - slot0) % N) * 16 : nullptr;
             // hint = last closest segment (step) / the spawn point written by place_agent (refresh); any value
             // is valid, a good one lets the first chunk scanned set a tight pruning bound
             const int hint = __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1;
-            float d_ref, dLc = 0.0f, dRc = 0.0f, dLv[4], dRv[4];
-            int idx_ref;
-            bool hitL = false, hitR = false;
-            scan_center<G>(pts + pr.c_off, boxes + pr.cbox, pr.n_c, hint, ex, px, py, lane, d_ref, idx_ref);
-            // the boundaries run alongside the centre line: reuse its closest segment as the hint.
-            // One rolled loop over {left, right}: a single copy of the scan in the instruction stream.
-            const int h2 = idx_ref - 1;
+            int h2;
+            {
+                float d_ref;
+                int idx_ref;
+                scan_center<G>(pts + prp->c_off, boxes + prp->cbox, prp->n_c, hint, ex, px, py, lane, d_ref, idx_ref);
+                if (writer) {
+                    ts.sc[0 * AS + sl] = d_ref;
+                    ts.sc[1 * AS + sl] = __int_as_float(idx_ref);
+                    if (dbg) { dbg[0] = d_ref; dbg[1] = __int_as_float(idx_ref); }
+                }
+                // the boundaries run alongside the centre line: reuse its closest segment as the hint
+                h2 = idx_ref - 1;
+            }
             const float cs_h = slot_ok ? ts.cs[sl] : 1.0f, sn_h = slot_ok ? ts.sn[sl] : 0.0f;
             const float psi_m = slot_ok ? ts.psim[sl] : 0.0f;   // heading mod pi
+            int fl = 0;
+            // One rolled loop over {left, right}: a single copy of the scan in the instruction stream.
 #pragma unroll 1
             for (int side = 0; side < 2; side++) {
                 float dc, dvv[4];
                 bool hit;
-                scan_boundary<G>(pts + (side ? pr.r_off : pr.l_off), boxes + (side ? pr.rbox : pr.lbox),
-                                 cones + (side ? pr.rcone : pr.lcone), side ? pr.n_r : pr.n_l, h2, ex, px, py, cs_h, sn_h,
-                                 psi_m, rvx, rvy, rect_radius, lane, dc, dvv, hit);
-                if (side) { dRc = dc; hitR = hit; dRv[0] = dvv[0]; dRv[1] = dvv[1]; dRv[2] = dvv[2]; dRv[3] = dvv[3]; }
-                else      { dLc = dc; hitL = hit; dLv[0] = dvv[0]; dLv[1] = dvv[1]; dLv[2] = dvv[2]; dLv[3] = dvv[3]; }
+                scan_boundary<G>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
+                                 cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, ex, px, py, cs_h,
+                                 sn_h, psi_m, rvx, rvy, rect_radius, lane, dc, dvv, hit);
+                if (hit) fl = (int)SGB_FLAG_COLLIDE_LANE;
+                if (writer) {
+                    dc = dc - cfg.half_width;                                   // world_state_rt.py:608-610
+                    ts.sc[(2 + side) * AS + sl] = dc;
+                    ts.sc[(4 + side) * AS + sl] = fminf(fminf(dvv[0], dvv[1]), fminf(dvv[2], dvv[3]));
+                    if (dbg) {
+                        dbg[side ? 7 : 2] = dc;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) dbg[(side ? 8 : 3) + v] = dvv[v];
+                    }
+                }
             }
-            dLc = dLc - cfg.half_width; // world_state_rt.py:608-610
-            dRc = dRc - cfg.half_width;
-            int fl = (hitL | hitR) ? (int)SGB_FLAG_COLLIDE_LANE : 0;
-            if (!pr.is_loop && lane == 0) {
+            if (!prp->is_loop && lane == 0) {
                 // entry / exit segments (world_state_rt.py:394-406, world_state_rt_sim.py:412-424)
-                const float2* L = pts + pr.l_off;
-                const float2* R = pts + pr.r_off;
+                const float2* L = pts + prp->l_off;
+                const float2* R = pts + prp->r_off;
 #pragma unroll 1
                 for (int k = 0; k < 2; k++) {
-                    const float2 a = L[k ? pr.n_l - 1 : 0], e = R[k ? pr.n_r - 1 : 0];
+                    const float2 a = L[k ? prp->n_l - 1 : 0], e = R[k ? prp->n_r - 1 : 0];
                     if (rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y)) fl |= (int)(k ? SGB_FLAG_EXIT : SGB_FLAG_ENTRY);
                 }
             }
-            if (slot_ok && lane == 0) {
-                float m4L = fminf(fminf(dLv[0], dLv[1]), fminf(dLv[2], dLv[3]));
-                float m4R = fminf(fminf(dRv[0], dRv[1]), fminf(dRv[2], dRv[3]));
-                ts.sc[0 * AS + sl] = d_ref;
-                ts.sc[1 * AS + sl] = __int_as_float(idx_ref);
-                ts.sc[2 * AS + sl] = dLc;
-                ts.sc[3 * AS + sl] = dRc;
-                ts.sc[4 * AS + sl] = m4L;
-                ts.sc[5 * AS + sl] = m4R;
-                ts.flags[sl] = step_mode ? fl : 0;
-                if (p.buf.dbg) {
-                    float* dbg = p.buf.dbg + ((size_t)ts.env[sl] * N + (sl - slot0) % N) * 16;
-                    dbg[0] = d_ref; dbg[1] = __int_as_float(idx_ref); dbg[2] = dLc; dbg[7] = dRc;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) { dbg[3 + v] = dLv[v]; dbg[8 + v] = dRv[v]; }
-                }
-            }
+            if (writer) ts.flags[sl] = step_mode ? fl : 0;
         }
         // ---- rectangle-rectangle crossings: the N(N-1)/2 unordered pairs of an env are dealt round-robin to  @region pairs
         //      the env's N*G lanes; interX(vertices[lo], vertices[hi]) with lo < hi exactly as
@@ -935,7 +938,9 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 const bool write_obs = step_mode || p.write_obs;
                 float* o = p.buf.obs + g * D;   // written in place: 128 B per agent, L2 merges the partial sectors
                 const float cs = ts.cs[sl], sn = ts.sn[sl];
-                const float2* cpts = pts + pr.c_off;
+                const float2* cpts = pts + prp->c_off;
+                const int pr_nc = prp->n_c;
+                const bool pr_loop = prp->is_loop != 0;
                 // What agent i's observation sees: after a reset everything is fresh; in a
                 // step agent 0 sees fresh centre queries + vertex queries of the OLD rectangle, agents >= 1 see
                 // last step's values (observation_provider_rt.py:857-925).
@@ -955,7 +960,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                         float* dst;
                         if (t < 3) {
                             int fi = 2 * t + o_idx + 1;                                  // helper_scenario.py:928-946
-                            if (pr.is_loop && fi >= pr.n_c - 1) fi = (fi + 1) % pr.n_c;
+                            if (pr_loop && fi >= pr_nc - 1) fi = (fi + 1) % pr_nc;
                             const float2 q = cpts[fi];
                             qx = q.x; qy = q.y;
                             dst = o + 1 + 2 * t;
@@ -1005,7 +1010,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                     float pen_near_agents = 0.0f, pen_a2a = 0.0f, pen_lane = 0.0f, rew_goal = 0.0f, rew_total = 0.0f;
                     if (step_mode) {
                         float2 st_old[3];   // short-term path of the PREVIOUS step
-                        short_term(cpts, pr.n_c, pr.is_loop != 0, c_idx, st_old);
+                        short_term(cpts, pr_nc, pr_loop, c_idx, st_old);
                         const float oxp = ts.ox[sl], oyp = ts.oy[sl];
                         float mvx = pix - oxp, mvy = piy - oyp;
                         float acc = 0.0f;
@@ -1060,7 +1065,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                         // the boundary distances is the stale one, as in its observation)
                         float4* io = reinterpret_cast<float4*>(p.buf.info + g * SGB_INFO_DIM);
                         float2 st_new[3];
-                        short_term(cpts, pr.n_c, pr.is_loop != 0, idx_n, st_new);
+                        short_term(cpts, pr_nc, pr_loop, idx_n, st_new);
                         const bool stale0 = step_mode && i == 0;
                         io[0] = make_float4(st_new[0].x, st_new[0].y, st_new[1].x, st_new[1].y);
                         io[1] = make_float4(st_new[2].x, st_new[2].y, d_ref_n, fminf(dLc, stale0 ? c_mL : m4L));
