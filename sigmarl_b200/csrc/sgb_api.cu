@@ -228,7 +228,7 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int envs_per_warp = 32 / (p.N * G);
     if (envs_per_warp < 1) return SGB_ERR_ARG;
     const int n_wt = (p.B + envs_per_warp - 1) / envs_per_warp;   // upper bound (a list may hold fewer envs)
-    const size_t smem = ((size_t)ctx->blob_bytes + 127) / 128 * 128 + tile_smem_bytes(slots, p.N, p.D) + 128;
+    const size_t smem = ((size_t)ctx->blob_bytes + 127) / 128 * 128 + tile_smem_bytes(slots, p.N) + 128;
     if ((int64_t)smem > ctx->max_smem_optin) {
         snprintf(g_err, sizeof g_err, "map blob %d B + tile arrays need %zu B of shared memory, device offers %d B",
                  ctx->blob_bytes, smem, ctx->max_smem_optin);
@@ -259,6 +259,11 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.blob_bytes = ctx->blob_bytes;
     p.mode = mode;
     p.write_obs = write_obs;
+    p.rect_radius = std::sqrt(ctx->cfg.half_length * ctx->cfg.half_length + ctx->cfg.half_width * ctx->cfg.half_width) * 1.0001f;
+    p.near2 = (p.rect_radius + kFarMargin) * (p.rect_radius + kFarMargin);
+    p.r_pos = 1.0f / ctx->cfg.norm_pos;
+    p.r_v = 1.0f / ctx->cfg.norm_v;
+    p.r_dist = 1.0f / ctx->cfg.norm_dist;
     const int g = pick_group(N);
     if (mode == 0) {
         if (g == 4) return launch_env_kernel<4, 0>(ctx, p, st);

@@ -77,6 +77,10 @@ struct Params {
     int32_t blob_bytes;
     int32_t mode;              // 0 = step, 1 = refresh
     int32_t write_obs;
+    // derived on the host once per launch: kernel parameters live in the constant bank and cost no registers
+    float rect_radius;         // circumradius of the rectangle * 1.0001 (conservative reach for the pruning bounds)
+    float near2;               // (rect_radius + kFarMargin)^2
+    float r_pos, r_v, r_dist;  // reciprocals of the observation normalisers
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------------
@@ -347,19 +351,22 @@ struct TileSmem {
     int* coll;                  // bit j: rectangle crossing with agent j of the same env
 };
 
-__device__ __forceinline__ void carve_tile(unsigned char* base, int A, int N, int D, TileSmem& t) {
+// Dynamic shared memory layout: [ slot arrays (size fixed at compile time) | map blob | dij [A][N] ].  With the slot
+// arrays first, every t.x[...] is an LDS/STS at a compile-time constant address + index: no pointer registers.
+constexpr int kSlotFloats = 10 + 8 + 4 + 8 + 4;   // per slot: 10 scalars, vtx[8], car[4], sc[8], path/flags/env/coll
+__host__ __device__ constexpr size_t tile_fixed_bytes(int A) { return ((size_t)A * kSlotFloats * sizeof(float) + 127) & ~(size_t)127; }
+template <int A>
+__device__ __forceinline__ void carve_tile(unsigned char* base, TileSmem& t) {
     float* f = reinterpret_cast<float*>(base);
     t.px = f; f += A; t.py = f; f += A; t.ox = f; f += A; t.oy = f; f += A;
     t.cs = f; f += A; t.sn = f; f += A; t.vx = f; f += A; t.vy = f; f += A; t.vabs = f; f += A; t.psim = f; f += A;
     t.vtx = f; f += 8 * A; t.car = f; f += 4 * A; t.sc = f; f += 8 * A;
-    t.dij = f; f += A * N;
     t.path = reinterpret_cast<int*>(f); f += A; t.flags = reinterpret_cast<int*>(f); f += A;
     t.env = reinterpret_cast<int*>(f); f += A;
     t.coll = reinterpret_cast<int*>(f); f += A;
 }
-__host__ __device__ inline size_t tile_smem_bytes(int A, int N, int D) {
-    (void)D;
-    return sizeof(float) * ((size_t)A * (10 + 8 + 4 + 8 + 4) + (size_t)A * N);
+__host__ __device__ inline size_t tile_smem_bytes(int A, int N) {
+    return tile_fixed_bytes(A) + sizeof(float) * (size_t)A * N;   // + dij, placed behind the blob
 }
 
 // ---- phase B building blocks ------------------------------------------------------------------------------
@@ -428,15 +435,15 @@ template <int G>
 __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes,
                                               const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
                                               float px, float py, float cs, float sn, float psi_m, const float* rvx, const float* rvy,
-                                              float rect_radius, int lane, float& d_cg, float dv[4], bool& hit_out) {
+                                              float rect_radius, float near2, int lane, float& d_cg, float dv[4],
+                                              bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
     int c0 = hint_seg / kChunk;
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
     SignCert cert;
     cert.init(rvx, rvy);
-    const float near_r = rect_radius + kFarMargin;
-    const float near2 = near_r * near_r;      // segments farther than this from the centre cannot touch the rectangle
+    const float near_r = rect_radius + kFarMargin;   // segments farther than this from the centre cannot touch the rectangle
     BestQ bq[5]; // 0 = centre, 1..4 = vertices
 #pragma unroll
     for (int v = 0; v < 5; v++) bq[v].init();
@@ -620,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     if ((int)blockIdx.x * kWarps >= n_wt) return;  // nothing to do for this CTA: do not even stage the map
     if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)p.blob_bytes);
-        const uint32_t dst = smem_u32(smem);
+        const uint32_t dst = smem_u32(smem + tile_fixed_bytes(kThreads / G));
         for (int off = 0; off < p.blob_bytes; off += 32768) {
             int n = min(32768, p.blob_bytes - off);
             tma_bulk_g2s(dst + off, p.blob + off, (uint32_t)n, bar);
@@ -628,18 +635,20 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     }
     bool map_ready = false;
 
-    const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(smem);
-    TileSmem ts;
     constexpr int AS = kThreads / G;            // slot stride of the SoA arrays (all warps)
-    carve_tile(smem + ((p.blob_bytes + 127) & ~127), AS, N, D, ts);
+    unsigned char* const blob_s = smem + tile_fixed_bytes(AS);
+    const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(blob_s);
+    TileSmem ts;
+    carve_tile<AS>(smem, ts);
+    ts.dij = reinterpret_cast<float*>(blob_s + ((p.blob_bytes + 127) & ~127));
 
     const int w = tid >> 5, ln = tid & 31;
     const int slot0 = w * SPW;                  // first slot of this warp
     const int n_slots = EW * N;                 // slots this warp uses
     const int lane = ln % G;                    // lane within the agent's group
     const int sl_l = ln / G;                    // slot (within the warp) this lane works for in phases B/C
-    const float rect_radius = sqrtf(cfg.half_length * cfg.half_length + cfg.half_width * cfg.half_width) * 1.0001f;
-    const float r_pos = 1.0f / cfg.norm_pos, r_v = 1.0f / cfg.norm_v, r_dist = 1.0f / cfg.norm_dist;
+    const float rect_radius = p.rect_radius;
+    const float r_pos = p.r_pos, r_v = p.r_v, r_dist = p.r_dist;
 
     // Phase alignment (DESIGN.md "Instruction cache"): the kernel's code (~55 KB executed) does not fit the SM's
     // 32 KB instruction cache, and 32 free-running warps keep all of it live at once.  Groups of SYNCW warps
@@ -741,10 +750,10 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         phase_sync();
         if (!map_ready) { mbar_wait(bar, 0); map_ready = true; }
 
-        const PathRec* paths = reinterpret_cast<const PathRec*>(smem + hdr->path_off);
-        const float2* pts = reinterpret_cast<const float2*>(smem + hdr->pts_off);
-        const float4* boxes = reinterpret_cast<const float4*>(smem + hdr->box_off);
-        const __half2* cones = reinterpret_cast<const __half2*>(smem + hdr->cone_off);
+        const PathRec* paths = reinterpret_cast<const PathRec*>(blob_s + hdr->path_off);
+        const float2* pts = reinterpret_cast<const float2*>(blob_s + hdr->pts_off);
+        const float4* boxes = reinterpret_cast<const float4*>(blob_s + hdr->box_off);
+        const __half2* cones = reinterpret_cast<const __half2*>(blob_s + hdr->cone_off);
 
         // ================= phase B: G lanes per agent, polyline queries out of the smem map =======  @region phase B glue
         const bool slot_ok = (sl_l < n_slots) && (ts.flags[slot0 + sl_l] >= 0);
@@ -796,7 +805,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 bool hit;
                 scan_boundary<G>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
                                  cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, ex, px, py, cs_h,
-                                 sn_h, psi_m, rvx, rvy, rect_radius, lane, dc, dvv, hit);
+                                 sn_h, psi_m, rvx, rvy, rect_radius, p.near2, lane, dc, dvv, hit);
                 if (hit) fl = (int)SGB_FLAG_COLLIDE_LANE;
                 if (writer) {
                     dc = dc - cfg.half_width;                                   // world_state_rt.py:608-610
