@@ -434,15 +434,14 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
 template <int G>
 __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes,
                                               const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
-                                              float px, float py, float cs, float sn, float psi_m, const float* rvx, const float* rvy,
+                                              float px, float py, const float* cs_s, const float* sn_s, const float* psi_m_s, const float* rvx,
+                                              const float* rvy,
                                               float rect_radius, float near2, int lane, float& d_cg, float dv[4],
                                               bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
     int c0 = hint_seg / kChunk;
     c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
-    SignCert cert;
-    cert.init(rvx, rvy);
     const float near_r = rect_radius + kFarMargin;   // segments farther than this from the centre cannot touch the rectangle
     BestQ bq[5]; // 0 = centre, 1..4 = vertices
 #pragma unroll
@@ -513,6 +512,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                     // Gate of the exact predicate: the segment is near the rectangle (then the chunk is a near chunk
                     // and q0 was evaluated), or it is collinear with an edge direction within kCollinear — the only
                     // way fp32 sign noise can fire interX on a far segment.  Everything else is certified "no hit".
+                    const float cs = *cs_s, sn = *sn_s;   // heading; read here so that it is not live across the scan
                     const float cr = lx * sn - ly * cs, dt = lx * cs + ly * sn;
                     const float cr2 = lx2 * sn - ly2 * cs, dt2 = lx2 * cs + ly2 * sn;
                     const bool ga = exhaustive | (q0a <= near2) | (fminf(cr * cr, dt * dt) <= (kCollinear * kCollinear) * len2);
@@ -539,6 +539,9 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
         thr = thr * thr;
         md = 0; mx = 0;
         const float pi_f = 3.14159274f, half_pi = 1.57079637f;
+        SignCert cert;                       // only live during the vote
+        cert.init(rvx, rvy);
+        const float psi_m = *psi_m_s;
         for (int c = lane; c < nch; c += G) {   // branch-free except for the (rare) edge-line test; c0 is masked out below
             const float4 bx = boxes[c];
             const float2 cone = __half22float2(cones[c]);
@@ -795,8 +798,6 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 // the boundaries run alongside the centre line: reuse its closest segment as the hint
                 h2 = idx_ref - 1;
             }
-            const float cs_h = slot_ok ? ts.cs[sl] : 1.0f, sn_h = slot_ok ? ts.sn[sl] : 0.0f;
-            const float psi_m = slot_ok ? ts.psim[sl] : 0.0f;   // heading mod pi
             int fl = 0;
             // One rolled loop over {left, right}: a single copy of the scan in the instruction stream.
 #pragma unroll 1
@@ -804,8 +805,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 float dc, dvv[4];
                 bool hit;
                 scan_boundary<G>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
-                                 cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, ex, px, py, cs_h,
-                                 sn_h, psi_m, rvx, rvy, rect_radius, p.near2, lane, dc, dvv, hit);
+                                 cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, ex, px, py,
+                                 ts.cs + sl, ts.sn + sl, ts.psim + sl, rvx, rvy, rect_radius, p.near2, lane, dc, dvv, hit);
                 if (hit) fl = (int)SGB_FLAG_COLLIDE_LANE;
                 if (writer) {
                     dc = dc - cfg.half_width;                                   // world_state_rt.py:608-610
@@ -933,7 +934,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                         if (!((used >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
                     }
                     used |= 1u << bj;
-                    nb_j[kk] = bj; nb_d[kk] = bd;
+                    if (kk == 0) { nb_j[0] = bj; nb_d[0] = bd; } else { nb_j[1] = bj; nb_d[1] = bd; }   // no dynamic index
                 }
             }
             if (slot_ok) {
@@ -994,7 +995,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                         for (int kk = 0; kk < k_near; kk++) {
                             int bj;
                             float bd;
-                            if (kk < 2) { bj = nb_j[kk]; bd = nb_d[kk]; }
+                            if (kk == 0) { bj = nb_j[0]; bd = nb_d[0]; }
+                            else if (kk == 1) { bj = nb_j[1]; bd = nb_d[1]; }
                             else bj = kth_nearest(ts.dij + sl * N, N, kk, &bd);
                             const int sj = base + bj;
                             float* ob = o + 10 + 11 * kk;
