@@ -290,31 +290,7 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
     return hit;
 }
 
-// Certified "no edge line of the rectangle separates points of this box": for every edge i the sign of  @region SignCert/box_sign_definite
-// f_i(x,y) = dx_i*y - dy_i*x - S_i is the same for all (x,y) in the box, with a margin far above the fp32
-// evaluation error, hence C1 of interX is false for every segment inside the box -> no crossing.
-// Edges 0/2 and 1/3 are anti-parallel (d_2 = -d_0 up to ~1e-6 rounding), so f_2(q) = f_0(v_2) - f_0(q) and
-// f_3(q) = f_1(v_3) - f_1(q) up to ~1e-5, which kSignMargin absorbs: two evaluations certify four edges.
-struct SignCert {
-    float dx0, dy0, S0, dx1, dy1, S1; // edges 0 and 1
-    float k0, k1;                     // f_0(v_2), f_1(v_3)
-    __device__ __forceinline__ void init(const float* vx, const float* vy) {
-        dx0 = vx[1] - vx[0]; dy0 = vy[1] - vy[0]; S0 = msub2(dx0, vy[0], dy0, vx[0]);
-        dx1 = vx[2] - vx[1]; dy1 = vy[2] - vy[1]; S1 = msub2(dx1, vy[1], dy1, vx[1]);
-        k0 = (dx0 * vy[2] - dy0 * vx[2]) - S0;
-        k1 = (dx1 * vy[3] - dy1 * vx[3]) - S1;
-    }
-};
-__device__ __forceinline__ bool box_sign_definite(const SignCert& sc, float4 bx) {
-    const float cx = 0.5f * (bx.x + bx.z), cy = 0.5f * (bx.y + bx.w);
-    const float hx = 0.5f * (bx.z - bx.x), hy = 0.5f * (bx.w - bx.y);
-    const float f0 = (sc.dx0 * cy - sc.dy0 * cx) - sc.S0;
-    const float f1 = (sc.dx1 * cy - sc.dy1 * cx) - sc.S1;
-    const float rad0 = fabsf(sc.dx0) * hy + fabsf(sc.dy0) * hx + kSignMargin;
-    const float rad1 = fabsf(sc.dx1) * hy + fabsf(sc.dy1) * hx + kSignMargin;
-    return (fabsf(f0) > rad0) & (fabsf(sc.k0 - f0) > rad0) & (fabsf(f1) > rad1) & (fabsf(sc.k1 - f1) > rad1);
-}
-
+// @region group shuffles
 template <int G>
 __device__ __forceinline__ float group_min(float v) {
 #pragma unroll
@@ -436,8 +412,8 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                                               const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
                                               float px, float py, const float* cs_s, const float* sn_s, const float* psi_m_s, const float* rvx,
                                               const float* rvy,
-                                              float rect_radius, float near2, int lane, float& d_cg, float dv[4],
-                                              bool& hit_out) {
+                                              float rect_radius, float near2, float half_l, float half_w, bool want_dv,
+                                              int lane, float& d_cg, float dv[4], bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
     int c0 = hint_seg / kChunk;
@@ -539,21 +515,28 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
         thr = thr * thr;
         md = 0; mx = 0;
         const float pi_f = 3.14159274f, half_pi = 1.57079637f;
-        SignCert cert;                       // only live during the vote
-        cert.init(rvx, rvy);
-        const float psi_m = *psi_m_s;
-        for (int c = lane; c < nch; c += G) {   // branch-free except for the (rare) edge-line test; c0 is masked out below
+        const float psi_m = *psi_m_s, cs = *cs_s, sn = *sn_s;
+        const float acs = fabsf(cs), asn = fabsf(sn);
+        for (int c = lane; c < nch; c += G) {   // branch-free; c0 is masked out below
             const float4 bx = boxes[c];
             const float2 cone = __half22float2(cones[c]);
             const float lb2 = box_lb2(bx, px, py);
             const uint32_t bit = 1u << c;
             md |= (lb2 > thr) ? 0u : bit;
-            // crossing candidates: near chunks, and far chunks that hold a segment direction within the cone slack
-            // of the heading or its normal AND are crossed by an edge line (otherwise C1 is certified false)
+            // Crossing candidates: near chunks, and far chunks on which interX could fire through sign noise.  That
+            // needs a segment collinear (within kCollinear) with an edge whose LINE also passes through the chunk
+            // (DESIGN.md "Exactness").  The side edges lie on the two lines parallel to the heading at lateral offset
+            // +-half_width from the centre, the front/back edges on the two lines along the normal at +-half_length:
+            // the chunk qualifies if its direction cone contains that direction and its box reaches into the band
+            // between / around the two lines (band widened by 1 mm >> the 1e-7 m error of vertices and cos/sin).
             float da = fabsf(psi_m - cone.x);
             da = fminf(da, pi_f - da);                       // angle between heading and cone axis, mod pi
-            if (!(lb2 > near2)) mx |= bit;
-            else if (fminf(da, half_pi - da) <= cone.y && !box_sign_definite(cert, bx)) mx |= bit;
+            const float bcx = 0.5f * (bx.x + bx.z) - px, bcy = 0.5f * (bx.y + bx.w) - py;   // box centre, relative
+            const float hx = 0.5f * (bx.z - bx.x), hy = 0.5f * (bx.w - bx.y);
+            const bool side_band = fabsf(cs * bcy - sn * bcx) <= hx * asn + hy * acs + (half_w + 1e-3f);
+            const bool face_band = fabsf(cs * bcx + sn * bcy) <= hx * acs + hy * asn + (half_l + 1e-3f);
+            const bool far_cand = ((da <= cone.y) & side_band) | (((half_pi - da) <= cone.y) & face_band);
+            mx |= (!(lb2 > near2) | far_cand) ? bit : 0u;
         }
         if (exhaustive) { md = 0xffffffffu; mx = 0xffffffffu; }
         {
@@ -564,8 +547,13 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
         mx = group_or<G>(mx);
     }
     d_cg = sqrtf(group_min<G>(bq[0].q));
+    if (want_dv) {   // per-vertex distances are only reported in the debug buffer; consumers read their minimum
 #pragma unroll
-    for (int v = 0; v < 4; v++) dv[v] = sqrtf(group_min<G>(bq[v + 1].q));
+        for (int v = 0; v < 4; v++) dv[v] = sqrtf(group_min<G>(bq[v + 1].q));
+    } else {
+        const float m4 = sqrtf(group_min<G>(fminf(fminf(bq[1].q, bq[2].q), fminf(bq[3].q, bq[4].q))));
+        dv[0] = dv[1] = dv[2] = dv[3] = m4;
+    }
     hit_out = group_or<G>(hit ? 1u : 0u) != 0u;
 }
 
@@ -806,7 +794,8 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
                 bool hit;
                 scan_boundary<G>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
                                  cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, ex, px, py,
-                                 ts.cs + sl, ts.sn + sl, ts.psim + sl, rvx, rvy, rect_radius, p.near2, lane, dc, dvv, hit);
+                                 ts.cs + sl, ts.sn + sl, ts.psim + sl, rvx, rvy, rect_radius, p.near2, cfg.half_length,
+                                 cfg.half_width, p.buf.dbg != nullptr, lane, dc, dvv, hit);
                 if (hit) fl = (int)SGB_FLAG_COLLIDE_LANE;
                 if (writer) {
                     dc = dc - cfg.half_width;                                   // world_state_rt.py:608-610
