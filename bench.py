@@ -165,7 +165,7 @@ def run_ours(args):
     # ---------------- device-resident arm ----------------
     for _ in range(W):
         env.step(new_action())
-        env.reset_done(write_obs=False)
+        env.reset_done(write_obs=True)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -180,7 +180,7 @@ def run_ours(args):
         ev[k][0].record()
         env.step(None)
         ev[k][1].record()
-        env.reset_done(write_obs=False)
+        env.reset_done(write_obs=True)
         ev[k][2].record()
         done_rate += float(env.done.float().mean()) / K
     barrier()
@@ -193,13 +193,13 @@ def run_ours(args):
     h_act = [((torch.rand(B, N, 2) * 2 - 1) * ur.cpu()).contiguous().pin_memory() for _ in range(2)]
     for i in range(2):
         env.step_host(h_act[i % 2])
-        env.reset_done(write_obs=False)
+        env.reset_done(write_obs=True)
     barrier()
     Ke = max(3, min(K, 10))
     t0 = time.perf_counter()
     for k in range(Ke):
         h_obs, h_rew, h_done = env.step_host(h_act[k % 2])
-        env.reset_done(write_obs=False)
+        env.reset_done(write_obs=True)
     barrier()
     t_e2e = time.perf_counter() - t0
     sampler.stop()
@@ -217,7 +217,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cpm_entire num_envs={B} n_agents={N} per GPU (BASELINE configs[2] shape), fused step + masked device reset",
+        "config": {"workload": f"cpm_entire num_envs={B} n_agents={N} per GPU (BASELINE configs[2] shape), fused step + masked device reset/respawn with fresh observations for reset envs",
                    "obs_dim": D, "rew_method": "distance", "dt": 0.1, "l2": "flushed (512 MiB write) between timed iterations",
                    "actions": "U(-1,1)^2*[1.0, 31deg]", "done_rate_per_step": round(done_rate, 4),
                    "map_smem_bytes": env.map_bytes},

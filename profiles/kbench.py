@@ -17,7 +17,7 @@ for t in range(K + 5):
     env.action.copy_((torch.rand(B, 8, 2, device="cuda", generator=g) * 2 - 1) * ur)
     flush.zero_()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    e[0].record(); env.step(None); e[1].record(); env.reset_done(write_obs=False); e[2].record()
+    e[0].record(); env.step(None); e[1].record(); env.reset_done(write_obs=bool(int(os.environ.get('KB_WRITE_OBS', '0')))); e[2].record()
     torch.cuda.synchronize()
     if t >= 5:
         ts.append(e[0].elapsed_time(e[1])); tr.append(e[1].elapsed_time(e[2]))

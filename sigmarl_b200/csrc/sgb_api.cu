@@ -16,6 +16,10 @@ struct sgb_ctx {
     sgb_config cfg{};
     unsigned char* d_blob = nullptr;
     float* d_yaw = nullptr;          // yaw per centre point, indexed like the blob's centre points
+    float* d_spawn = nullptr;        // spawn table [centre points][8] (sgb_kernels.cuh: place_agent)
+    float* d_fresh = nullptr;        // [fresh_cap][4] scratch: spawn-pose boundary distances for the observation refresh
+    int64_t fresh_cap = 0;           // capacity of d_fresh in agents
+    int32_t n_points = 0;            // centre points incl. extension slots (rows of d_yaw / d_spawn)
     int32_t* d_list = nullptr;       // [cap] compacted env indices for a masked refresh
     int32_t* d_count = nullptr;      // number of entries of d_list
     int32_t list_cap = 0;
@@ -222,6 +226,15 @@ int ensure_list(sgb_ctx* c, int B) {
     return SGB_OK;
 }
 
+int ensure_fresh(sgb_ctx* c, int64_t agents) {
+    if (c->fresh_cap >= agents) return SGB_OK;
+    cudaFree(c->d_fresh);
+    c->d_fresh = nullptr;
+    CK(cudaMalloc(&c->d_fresh, sizeof(float) * 4 * (size_t)agents));
+    c->fresh_cap = agents;
+    return SGB_OK;
+}
+
 template <int G, int MODE>
 int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int slots = kThreads / G;
@@ -248,14 +261,17 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
 }
 
 int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, const int32_t* env_list,
-               const int32_t* env_count, int write_obs, cudaStream_t st) {
+               const int32_t* env_count, int write_obs, cudaStream_t st, int skip_scan = 0,
+               const sgb_config* cfg_override = nullptr) {
     Params p{};
-    p.cfg = ctx->cfg;
+    p.cfg = cfg_override ? *cfg_override : ctx->cfg;
+    p.skip_scan = skip_scan;
+    p.fresh = ctx->d_fresh;
     p.buf = *buf;
     p.blob = ctx->d_blob;
     p.env_list = env_list;
     p.env_count = env_count;
-    p.B = B; p.N = N; p.D = 10 + 11 * ctx->cfg.k_near;
+    p.B = B; p.N = N; p.D = 10 + 11 * p.cfg.k_near;
     p.blob_bytes = ctx->blob_bytes;
     p.mode = mode;
     p.write_obs = write_obs;
@@ -273,6 +289,64 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     if (g == 4) return launch_env_kernel<4, 1>(ctx, p, st);
     if (g == 2) return launch_env_kernel<2, 1>(ctx, p, st);
     return launch_env_kernel<1, 1>(ctx, p, st);
+}
+
+// Spawn table.  A device reset puts an agent exactly on a centre-line point with the path's yaw, so everything
+// sgb_refresh would derive from that pose (centre / boundary distances, closest index) depends on (path, point)
+// only.  It is computed ONCE here — by the refresh kernel itself, on one single-agent env per centre point, so the
+// values are bit-identical to a refresh of the reset pose — and looked up by reset_kernel afterwards: a masked
+// reset then needs no polyline scan at all.
+int build_spawn_table(sgb_ctx* c, const Packed& pk) {
+    const BlobHeader* h = reinterpret_cast<const BlobHeader*>(pk.blob.data());
+    const PathRec* recs = reinterpret_cast<const PathRec*>(pk.blob.data() + h->path_off);
+    const int M = c->n_points;
+    std::vector<int32_t> path(M, 0), point(M, 0);
+    std::vector<uint8_t> mask(M, 0);
+    for (int i = 0; i < h->n_paths; i++)
+        for (int k = 0; k < recs[i].n_c; k++) {
+            const int r = recs[i].c_off + k;     // row of d_yaw / d_spawn; NB c_off counts blob points (incl. boundaries)
+            if (r < 0 || r >= M) return SGB_ERR_MAP;
+            path[r] = i; point[r] = k; mask[r] = 1;
+        }
+    float *d_f = nullptr;                       // pose, aux, carry [M,4] each, speed [M], dbg [M,16]
+    int32_t* d_i = nullptr;                     // path_id, path, point [M] each
+    uint8_t* d_b = nullptr;                     // agent_flags, mask [M] each
+    auto cleanup = [&]() { cudaFree(d_f); cudaFree(d_i); cudaFree(d_b); };
+    if (cudaMalloc(&d_f, sizeof(float) * (size_t)M * (12 + 1 + 16)) != cudaSuccess ||
+        cudaMalloc(&d_i, sizeof(int32_t) * (size_t)M * 3) != cudaSuccess ||
+        cudaMalloc(&d_b, (size_t)M * 2) != cudaSuccess) { cleanup(); return cuda_fail(cudaErrorMemoryAllocation, "spawn table"); }
+    cudaMemset(d_f, 0, sizeof(float) * (size_t)M * 29);
+    cudaMemset(d_i, 0, sizeof(int32_t) * (size_t)M * 3);
+    cudaMemcpy(d_i + M, path.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_i + 2 * M, point.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_b + M, mask.data(), M, cudaMemcpyHostToDevice);
+    sgb_buffers b{};
+    b.pose = d_f; b.aux = d_f + 4 * (size_t)M; b.carry = d_f + 8 * (size_t)M; b.dbg = d_f + 13 * (size_t)M;
+    b.path_id = d_i; b.agent_flags = d_b;
+    PlaceParams pp{};
+    pp.cfg = c->cfg; pp.buf = b; pp.blob = c->d_blob; pp.yaw = c->d_yaw; pp.agent_mask = d_b + M;
+    pp.path = d_i + M; pp.point = d_i + 2 * M; pp.speed = d_f + 12 * (size_t)M; pp.B = M; pp.N = 1;
+    place_kernel<<<(M + 255) / 256, 256>>>(pp);
+    sgb_config one = c->cfg;
+    one.k_near = 0;                              // single-agent envs: nobody to observe
+    int rc = launch_env(c, M, 1, &b, 1, nullptr, nullptr, 0, nullptr, 0, &one);
+    if (rc == SGB_OK && cudaDeviceSynchronize() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "spawn table kernels");
+    if (rc != SGB_OK) { cleanup(); return rc; }
+    std::vector<float> dbg((size_t)M * 16), tab((size_t)M * 8, 0.0f);
+    cudaMemcpy(dbg.data(), b.dbg, sizeof(float) * dbg.size(), cudaMemcpyDeviceToHost);
+    for (int r = 0; r < M; r++) {
+        const float* d = &dbg[(size_t)r * 16];
+        float* t = &tab[(size_t)r * 8];
+        t[0] = d[0]; t[1] = d[1];                // d_ref, idx_ref (int bits)
+        t[2] = d[2]; t[3] = d[7];                // dLc, dRc (already minus half width)
+        t[4] = std::min(std::min(d[3], d[4]), std::min(d[5], d[6]));
+        t[5] = std::min(std::min(d[8], d[9]), std::min(d[10], d[11]));
+    }
+    cleanup();
+    CK(cudaMalloc(&c->d_spawn, sizeof(float) * tab.size()));
+    CK(cudaMemcpy(c->d_spawn, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice));
+    c->launches = 0;                             // set-up launches are not part of anyone's step accounting
+    return SGB_OK;
 }
 
 } // namespace
@@ -311,6 +385,9 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     CK(cudaMemcpy(c->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&c->d_yaw, pk.yaw.size() * sizeof(float)));
     CK(cudaMemcpy(c->d_yaw, pk.yaw.data(), pk.yaw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    c->n_points = (int32_t)pk.yaw.size();
+    rc = build_spawn_table(c, pk);
+    if (rc != SGB_OK) { sgb_destroy(c); return rc; }
     *out = c;
     return SGB_OK;
 }
@@ -322,6 +399,8 @@ extern "C" int sgb_destroy(sgb_ctx* c) {
     cudaFree(c->d_yaw);
     cudaFree(c->d_list);
     cudaFree(c->d_count);
+    cudaFree(c->d_spawn);
+    cudaFree(c->d_fresh);
     if (c->pipe_ready) {
         for (int i = 0; i < 2; i++) { cudaStreamDestroy(c->pipe_stream[i]); cudaEventDestroy(c->pipe_event[i]); }
         cudaEventDestroy(c->pipe_start);
@@ -383,17 +462,25 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
     if (!buf->step_count || (!all && !buf->done)) return SGB_ERR_ARG;
+    if (write_obs && !buf->obs) return SGB_ERR_ARG;
     rc = ensure_list(c, B);
+    if (rc) return rc;
+    rc = ensure_fresh(c, (int64_t)B * N);
     if (rc) return rc;
     CK(cudaMemsetAsync(c->d_count, 0, sizeof(int32_t), st));
     ResetParams p{};
     p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.list = c->d_list; p.count = c->d_count;
     p.n_failed = n_failed; p.seed = seed; p.epoch = epoch; p.env_offset = env_offset;
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
+    p.spawn_tab = c->d_spawn; p.fresh = c->d_fresh; p.list_full_only = 1;
     reset_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
     c->launches++;
     CK(cudaGetLastError());
-    return launch_env(c, B, N, buf, 1, c->d_list, c->d_count, write_obs, st);
+    // carry / aux / flags of every touched env are complete (spawn table); what is left is the all-fresh observation
+    // (and info block) of the FULLY reset envs — respawned agents keep their step-time observation, like the
+    // reference — which needs the other agents of the env but no polyline scan
+    if (!write_obs && !buf->info) return SGB_OK;
+    return launch_env(c, B, N, buf, 1, c->d_list, c->d_count, write_obs, st, 1);
 }
 
 extern "C" int sgb_reset(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,

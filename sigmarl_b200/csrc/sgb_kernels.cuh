@@ -33,8 +33,8 @@ namespace sgb {
 #ifndef SGB_SYNC_WARPS          // warps per phase-aligned group in the step kernel (0/1 = free-running warps)
 #define SGB_SYNC_WARPS 8
 #endif
-#ifndef SGB_SYNC_WARPS_REFRESH  // same for the refresh kernel (short compacted env lists: free-running)
-#define SGB_SYNC_WARPS_REFRESH 0
+#ifndef SGB_SYNC_WARPS_REFRESH  // same for the refresh kernel (0.137 -> 0.133 ms per masked reset at 26 % done envs)
+#define SGB_SYNC_WARPS_REFRESH 8
 #endif
 constexpr int kThreads = SGB_THREADS; // threads per CTA (one CTA per SM: the map blob fills most of the shared memory)
 constexpr int kChunk = 8;            // polyline segments per bounding-box chunk
@@ -77,6 +77,10 @@ struct Params {
     int32_t blob_bytes;
     int32_t mode;              // 0 = step, 1 = refresh
     int32_t write_obs;
+    // refresh after a device reset: every agent of a listed env sits on a spawn point, whose centre / boundary
+    // distances come from the spawn table (reset_kernel stored them): phase B is skipped
+    int32_t skip_scan;
+    const float* fresh;        // [B,N,4] dLc, dRc, m4L, m4R of the spawn pose (written by reset_kernel)
     // derived on the host once per launch: kernel parameters live in the constant bank and cost no registers
     float rect_radius;         // circumradius of the rectangle * 1.0001 (conservative reach for the pruning bounds)
     float near2;               // (rect_radius + kFarMargin)^2
@@ -759,7 +763,17 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         // slot arrays as soon as it exists: nothing but the path index stays live across the three scans (the
         // kernel runs at the 64-register cap of a 1024-thread CTA; what is live across a scan gets spilled).
         const PathRec* prp = paths + path;
-        {
+        if (!step_mode && p.skip_scan) {
+            // spawn-table refresh: the scan results of this pose were computed once, at context creation
+            if (slot_ok && lane == 0) {
+                const float4 fr = reinterpret_cast<const float4*>(p.fresh)[(size_t)ts.env[sl] * N + (sl - slot0) % N];
+                ts.sc[0 * AS + sl] = ts.car[0 * AS + sl];
+                ts.sc[1 * AS + sl] = ts.car[3 * AS + sl];
+                ts.sc[2 * AS + sl] = fr.x; ts.sc[3 * AS + sl] = fr.y;
+                ts.sc[4 * AS + sl] = fr.z; ts.sc[5 * AS + sl] = fr.w;
+                ts.flags[sl] = 0;
+            }
+        } else {
             const float px = slot_ok ? ts.px[sl] : 0.0f, py = slot_ok ? ts.py[sl] : 0.0f;
             float rvx[4], rvy[4];   // the agent's rectangle (vertices only: keeps the scans' register footprint small)
 #pragma unroll
@@ -1129,8 +1143,11 @@ struct PlaceParams {
     int32_t B, N;
 };
 
+// spawn table: per centre point (indexed like `yaw`) d_ref, (int) idx_ref, dLc, dRc, m4L, m4R, 0, 0 of an agent placed
+// there — what sgb_refresh computes for that pose, evaluated once at context creation (sgb_api.cu: build_spawn_table)
 __device__ __forceinline__ void place_agent(const sgb_config& cfg, const sgb_buffers& buf, const unsigned char* blob,
-                                            const float* yaw, size_t g, int path, int point, float speed) {
+                                            const float* yaw, size_t g, int path, int point, float speed,
+                                            const float* spawn_tab = nullptr, int agent = 0, float* fresh = nullptr) {
     const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(blob);
     const PathRec* paths = reinterpret_cast<const PathRec*>(blob + hdr->path_off);
     const float2* pts = reinterpret_cast<const float2*>(blob + hdr->pts_off);
@@ -1142,7 +1159,16 @@ __device__ __forceinline__ void place_agent(const sgb_config& cfg, const sgb_buf
     float s, co;
     sincosf(0.0f + psi, &s, &co);
     reinterpret_cast<float4*>(buf.aux)[g] = make_float4(0.0f, speed * co, speed * s, 0.0f);
-    reinterpret_cast<float4*>(buf.carry)[g] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(point + 1)); // search hint
+    if (spawn_tab) {
+        const float4 t0 = reinterpret_cast<const float4*>(spawn_tab)[2 * (size_t)(pr.c_off + point)];
+        const float4 t1 = reinterpret_cast<const float4*>(spawn_tab)[2 * (size_t)(pr.c_off + point) + 1];
+        // the carry of agent 0 holds the vertex part only (its centre part is always fresh)
+        reinterpret_cast<float4*>(buf.carry)[g] = make_float4(t0.x, agent == 0 ? t1.x : fminf(t0.z, t1.x),
+                                                               agent == 0 ? t1.y : fminf(t0.w, t1.y), t0.y);
+        if (fresh) reinterpret_cast<float4*>(fresh)[g] = make_float4(t0.z, t0.w, t1.x, t1.y);
+    } else {
+        reinterpret_cast<float4*>(buf.carry)[g] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(point + 1)); // search hint
+    }
     buf.path_id[g] = path;
 }
 
@@ -1164,6 +1190,9 @@ struct ResetParams {
     uint64_t seed, epoch;
     int64_t env_offset;
     int32_t B, N, path_lo, path_hi, max_tries, all;
+    const float* spawn_tab;    // see place_agent
+    float* fresh;              // [B,N,4] scratch for the observation refresh of fully reset envs
+    int32_t list_full_only;    // 1: only fully reset envs go into `list` (they get a fresh observation)
 };
 
 // one thread per env: sequential bounded rejection sampling (world_state_rt_sim.py:215-311)
@@ -1222,10 +1251,15 @@ __global__ void reset_kernel(const ResetParams p) {
             qx[a] = c.x; qy[a] = c.y;
         }
         const float u = (float)(draw(p.seed, p.epoch, env_g, a, 0, 2) >> 40) * (1.0f / 16777216.0f);
-        place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + a, path, point, u * p.cfg.max_speed);
+        place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + a, path, point, u * p.cfg.max_speed, p.spawn_tab, a, p.fresh);
     }
     if (full) p.buf.step_count[e] = 0; // road_traffic.py:875-877
-    p.list[atomicAdd(p.count, 1)] = e;
+    // collision masks of a touched env are cleared (road_traffic.py:907)
+    for (int a = 0; a < N; a++) {
+        p.buf.agent_flags[(size_t)e * N + a] = 0;
+        if (p.buf.collide_with) p.buf.collide_with[(size_t)e * N + a] = 0;
+    }
+    if (full || !p.list_full_only) p.list[atomicAdd(p.count, 1)] = e;
     if (failed && p.n_failed) atomicAdd(p.n_failed, failed);
 }
 
