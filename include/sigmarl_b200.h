@@ -165,9 +165,14 @@ int sgb_place(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const 
 
 /* Device-side masked reset + respawn after a step.  For envs with done[b]: re-place all N agents by
  * bounded rejection sampling (uniform path in [path_lo, path_hi), uniform point in [3, n/2), every
- * pair >= reset_min_dist apart) and zero step_count; for not-done envs (when cfg.respawn_on_exit)
- * respawn the agents whose flags carry ENTRY/EXIT; then refresh the touched envs (fresh obs written
- * for reset envs only if write_obs).  Counter-based RNG keyed by (seed, step counter `epoch`, global
+ * pair >= reset_min_dist apart) and zero step_count; for not-done envs (when cfg.respawn_on_exit, or
+ * cfg.testing_mode) respawn the agents whose flags ask for it.  Carry, aux and cleared collision flags
+ * of every touched env come from the SPAWN TABLE — what sgb_refresh derives from a pose on a centre
+ * point, computed once at sgb_create by the refresh kernel itself (bit-identical) — so a reset runs no
+ * polyline scan.  If write_obs (or buf->info), the FULLY reset envs additionally get the all-fresh
+ * observation (info block) the reference returns after reset_at; respawned agents of not-done envs
+ * keep their step-time observation, like the reference (road_traffic.py:1462-1472).
+ * Counter-based RNG keyed by (seed, step counter `epoch`, global
  * env index env_offset + b, agent, try) so results do not depend on how envs are sharded over GPUs.
  * Replaces reset_world_at (road_traffic.py:816-923) and _generate_feasible_initial_positions
  * (world_state_rt_sim.py:215-311); distribution-equivalent, not stream-equivalent, to the reference's

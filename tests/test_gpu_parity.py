@@ -292,6 +292,46 @@ def test_step_is_idempotent_under_refresh():
         env.reset_done()
 
 
+@pytest.mark.parametrize("scenario,N", [("cpm_entire", 8), ("cpm_mixed", 6), ("on_ramp_2_multilane", 12)])
+def test_spawn_table_reset_equals_generic_refresh(scenario, N):
+    """A device reset takes carry / boundary distances of the spawn pose from the table built at context creation.
+    They must be bit-identical to what the generic polyline scan (sgb_refresh) derives from the same pose — carry,
+    aux, the all-fresh observation and the info block of reset envs — and respawned agents of not-done envs must
+    keep their step-time observation."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    env = RoadTrafficEnv(EnvConfig(scenario_type=scenario, n_agents=N, rew_method="distance"), num_envs=1024,
+                         device="cuda:0", seed=7, info=True)
+    obs0 = env.reset().clone()
+    carry0, aux0, info0 = env.carry.clone(), env.aux.clone(), env.info.clone()
+    env.refresh(write_obs=True)                      # generic scan of the same poses
+    assert torch.equal(carry0, env.carry) and torch.equal(aux0, env.aux)
+    assert torch.equal(obs0, env.obs) and torch.equal(info0[..., :9], env.info[..., :9])
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ur = torch.as_tensor(UR).cuda()
+    n_reset = n_resp = 0
+    for t in range(12 if scenario == "cpm_entire" else 70):
+        if scenario == "cpm_entire":
+            act = (torch.rand(env.B, N, 2, device="cuda", generator=g) * 2 - 1) * ur
+        else:   # drive forward so that agents also leave through exit segments
+            o = env.obs
+            steer = torch.clamp(1.5 * torch.atan2(o[..., 4], o[..., 3]), -float(UR[1]), float(UR[1]))
+            act = torch.stack([0.6 + 0.3 * torch.rand(env.B, N, device="cuda", generator=g), steer], -1)
+        obs_step = env.step(act)[0].clone()
+        done = env.done.bool().clone()
+        resp = ((env.agent_flags & 12) != 0) & ~done[:, None] & bool(env.cfg.respawn_on_exit)
+        env.reset_done(write_obs=True)
+        obs_r, carry_r, aux_r = env.obs.clone(), env.carry.clone(), env.aux.clone()
+        touched = done | resp.any(1)
+        # envs the reset did not fully re-place keep their step-time observation, respawned agents included
+        assert torch.equal(obs_r[~done], obs_step[~done])
+        env.refresh(write_obs=True)                  # generic scan of everything
+        assert torch.equal(carry_r, env.carry) and torch.equal(aux_r, env.aux)
+        assert torch.equal(obs_r[done], env.obs[done])
+        assert int(env.agent_flags[touched].sum()) == 0
+        n_reset += int(done.sum()); n_resp += int(resp.sum())
+    assert n_reset > 0 and (scenario != "cpm_mixed" or n_resp > 0)
+
+
 def test_vmas_facade_drives_the_same_kernel():
     """The BaseScenario-shaped facade (make_world / world.step / reward / observation / done / reset_world_at)."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv, make_env
