@@ -495,10 +495,16 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                     const float cs = *cs_s, sn = *sn_s;   // heading; read here so that it is not live across the scan
                     const float cr = lx * sn - ly * cs, dt = lx * cs + ly * sn;
                     const float cr2 = lx2 * sn - ly2 * cs, dt2 = lx2 * cs + ly2 * sn;
-                    const bool ga = exhaustive | (q0a <= near2) | (fminf(cr * cr, dt * dt) <= (kCollinear * kCollinear) * len2);
-                    const bool gb = exhaustive | (q0b <= near2) | (fminf(cr2 * cr2, dt2 * dt2) <= (kCollinear * kCollinear) * len2b);
-                    if (ga) hit |= rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y, exhaustive);
-                    if (gb) hit |= rect_cross_seg_L1(rvx, rvy, a2.x, a2.y, e2.x, e2.y, exhaustive);
+                    bool ga = (q0a <= near2) | (fminf(cr * cr, dt * dt) <= (kCollinear * kCollinear) * len2);
+                    bool gb = (q0b <= near2) | (fminf(cr2 * cr2, dt2 * dt2) <= (kCollinear * kCollinear) * len2b);
+                    // ... and its LINE must pass through the rectangle, or no C2 term can be true: the segment's line
+                    // function at the centre, against its largest change over the oriented rectangle
+                    // (half_l |d x u| + half_w |d . u|), with 1e-5 of slack >> the 4e-7 evaluation error of g.
+                    const float gca = lx * (py - a.y) - ly * (px - a.x), gcb = lx2 * (py - a2.y) - ly2 * (px - a2.x);
+                    ga &= fabsf(gca) <= half_l * fabsf(cr) + half_w * fabsf(dt) + 1e-5f;
+                    gb &= fabsf(gcb) <= half_l * fabsf(cr2) + half_w * fabsf(dt2) + 1e-5f;
+                    if (ga | exhaustive) hit |= rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y, true);
+                    if (gb | exhaustive) hit |= rect_cross_seg_L1(rvx, rvy, a2.x, a2.y, e2.x, e2.y, true);
                 }
             }
         }
