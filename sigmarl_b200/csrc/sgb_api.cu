@@ -29,6 +29,7 @@ struct sgb_ctx {
     int32_t num_sms = 0;
     int32_t max_smem_optin = 0;
     int64_t launches = 0;
+    size_t smem_configured[2][3] = {{0, 0, 0}, {0, 0, 0}};   // dynamic-smem opt-in done for <MODE, G> on this device
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // sgb_step_host: chunked copy/compute pipeline
     cudaEvent_t pipe_event[2] = {nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
@@ -247,7 +248,8 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
                  ctx->blob_bytes, smem, ctx->max_smem_optin);
         return SGB_ERR_MAP;
     }
-    static thread_local size_t configured = 0;
+    // the opt-in is per (kernel, device): remember it in the context, which is bound to one device
+    size_t& configured = ctx->smem_configured[MODE][G == 4 ? 0 : (G == 2 ? 1 : 2)];
     if (configured < smem) {
         CK(cudaFuncSetAttribute(env_step_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

@@ -146,13 +146,17 @@ def _oracle_for(env, O, rew_method, mode):
     ("intersection_1", 2, "distance", "kwargs", 256),
     ("on_ramp_2_multilane", 12, "ttc", "kwargs", 256),
     ("roundabout_2", 12, "sparse", "params", 256),
+    ("cpm_entire", 8, "ttc", "params", 256),           # run with n_nearing_agents_observed = 5 below (k > 2 path)
 ])
 def test_cuda_matches_oracle_free_running_with_device_resets(oracle_mod, scenario, N, rew, mode, B):
     """GPU drives (device resets included); every step the oracle is teacher-forced from the GPU's pre-step state."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     O = oracle_mod
-    env = RoadTrafficEnv(EnvConfig(scenario_type=scenario, n_agents=N, mode=mode, rew_method=rew),
+    k_obs = 5 if (scenario, rew) == ("cpm_entire", "ttc") else 2   # 5: neighbours beyond the two kept in registers
+    env = RoadTrafficEnv(EnvConfig(scenario_type=scenario, n_agents=N, mode=mode, rew_method=rew,
+                                   n_nearing_agents_observed=k_obs),
                          num_envs=B, device="cuda:0", seed=7, debug=True)
+    assert env.D == 10 + 11 * min(k_obs, N - 1)
     w = _oracle_for(env, O, rew, mode)
     env.reset()
     rng = np.random.default_rng(0)
