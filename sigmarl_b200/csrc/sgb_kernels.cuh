@@ -934,17 +934,25 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             int nb_j[2] = {0, 0};          // the first two neighbours stay in registers, the rest is re-derived
             float nb_d[2] = {0.0f, 0.0f};
             uint32_t used = 0;
-            if (slot_ok) {
-                for (int kk = 0; kk < k_near && kk < 2; kk++) {
-                    int bj = -1;
-                    float bd = __int_as_float(0x7f800000);
-                    for (int j = 0; j < N; j++) {
-                        float dj = ts.dij[sl * N + j];
-                        if (!((used >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
+            // The lanes of the group split j (lane, lane + G, ...), then a lexicographic (d, j) minimum over the group:
+            // same result as the ascending scan with strict '<' (first minimal index).  All lanes shuffle.
+            for (int kk = 0; kk < k_near && kk < 2; kk++) {
+                int bj = 0x7fffffff;
+                float bd = __int_as_float(0x7f800000);
+                if (slot_ok)
+                    for (int j = lane; j < N; j += G) {
+                        const float dj = ts.dij[sl * N + j];
+                        if (!((used >> j) & 1u) && (dj < bd || bj == 0x7fffffff)) { bd = dj; bj = j; }
                     }
-                    used |= 1u << bj;
-                    if (kk == 0) { nb_j[0] = bj; nb_d[0] = bd; } else { nb_j[1] = bj; nb_d[1] = bd; }   // no dynamic index
+#pragma unroll
+                for (int m = 1; m < G; m <<= 1) {
+                    const float od = __shfl_xor_sync(0xffffffffu, bd, m);
+                    const int oj = __shfl_xor_sync(0xffffffffu, bj, m);
+                    if (oj != 0x7fffffff && (bj == 0x7fffffff || od < bd || (od == bd && oj < bj))) { bd = od; bj = oj; }
                 }
+                if (bj == 0x7fffffff) bj = 0;   // inactive slot
+                used |= 1u << bj;
+                if (kk == 0) { nb_j[0] = bj; nb_d[0] = bd; } else { nb_j[1] = bj; nb_d[1] = bd; }   // no dynamic index
             }
             if (slot_ok) {
                 const size_t g = (size_t)ts.env[sl] * N + i;
@@ -1098,24 +1106,25 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         __syncwarp();   // phase D reads this warp's own slots only
 
         // ================= phase D: per-env outputs ===============================================  @region phase D
-        if (step_mode && ln < n_slots && (ln % N) == 0 && ts.flags[slot0 + ln] >= 0) {
-            const int st = slot0 + ln;
-            const int e = ts.env[st];
-            int any = 0, tries = 0, succ = 0;
-            for (int j = 0; j < N; j++) {
-                const int f = ts.flags[st + j];
-                any |= f;
-                tries += (f & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE | SGB_FLAG_EXIT)) ? 1 : 0;   // :1029-1035
-                succ += (f & (int)SGB_FLAG_EXIT) ? 1 : 0;                                                       // :998-1002
+        if (step_mode) {
+            // one ballot per quantity over the warp (lane 0 of every agent group votes its agent's flags), then the
+            // first lane of each env reads its env's bits
+            const int myfl = (slot_ok && lane == 0) ? ts.flags[sl] : 0;
+            const uint32_t b_hit = __ballot_sync(0xffffffffu, (myfl & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE)) != 0);
+            const uint32_t b_exit = __ballot_sync(0xffffffffu, (myfl & (int)SGB_FLAG_EXIT) != 0);
+            if (ln < EW * env_lanes && ln % env_lanes == 0 && ts.flags[slot0 + (ln / env_lanes) * N] >= 0) {
+                const uint32_t em = (env_lanes >= 32 ? 0xffffffffu : ((1u << env_lanes) - 1u)) << ln;   // this env's lanes
+                const int e = ts.env[slot0 + (ln / env_lanes) * N];
+                const int tries = __popc((b_hit | b_exit) & em);                                                // :1029-1035
+                const int succ = __popc(b_exit & em);                                                           // :998-1002
+                if (p.buf.task_tries && tries) p.buf.task_tries[e] += tries;
+                if (p.buf.task_success && succ) p.buf.task_success[e] += succ;
+                const int step = p.buf.step_count[e] + 1;          // road_traffic.py:954-962
+                p.buf.step_count[e] = step;
+                // road_traffic.py:1451-1457 (training mode) / :1429-1433 (testing mode: only the time limit ends an env)
+                const bool dn = (step == cfg.max_steps - 1) || (!cfg.testing_mode && (b_hit & em) != 0u);
+                p.buf.done[e] = dn ? 1 : 0;
             }
-            if (p.buf.task_tries && tries) p.buf.task_tries[e] += tries;
-            if (p.buf.task_success && succ) p.buf.task_success[e] += succ;
-            const int step = p.buf.step_count[e] + 1;          // road_traffic.py:954-962
-            p.buf.step_count[e] = step;
-            // road_traffic.py:1451-1457 (training mode) / :1429-1433 (testing mode: only the time limit ends an env)
-            const bool dn = (step == cfg.max_steps - 1) ||
-                            (!cfg.testing_mode && (any & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE)));
-            p.buf.done[e] = dn ? 1 : 0;
         }
         phase_sync();   // the next tile's phase A (dealt over the whole group) overwrites these slots
     }
