@@ -409,15 +409,17 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
 }
 
 // boundary: distances of the centre + 4 vertices, and the rectangle-crossing flag.  Pass 0 scans the hint  @region scan_boundary
-// chunk (all points, crossing test on), pass 1 the voted chunks; the segment body exists once (code size
-// matters: the warps of an SM run different phases at the same time and share the instruction caches).
+// chunk (distances + crossing gate), pass 1 the voted chunks; the segment body exists once (code size matters:
+// warps run different phases at the same time and share the instruction caches).  A voted distance chunk
+// evaluates all five points: a per-point refinement of the vote (which points can still improve in this box)
+// was measured to cost more — instructions, registers, shuffles — than the evaluations it saved.
 template <int G>
 __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes,
                                               const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
-                                              float px, float py, const float* cs_s, const float* sn_s, const float* psi_m_s, const float* rvx,
-                                              const float* rvy,
-                                              float rect_radius, float near2, float half_l, float half_w, bool want_dv,
-                                              int lane, float& d_cg, float dv[4], bool& hit_out) {
+                                              float px, float py, const float* cs_s, const float* sn_s,
+                                              const float* psi_m_s, const float* rvx, const float* rvy, float rect_radius,
+                                              float near2, float half_l, float half_w, bool want_dv, int lane, float& d_cg,
+                                              float dv[4], bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
     int c0 = hint_seg / kChunk;
@@ -427,17 +429,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
 #pragma unroll
     for (int v = 0; v < 5; v++) bq[v].init();
     bool hit = false;
-    float gq_pt[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; // group-wide best q per point after the hint chunk
-    const uint32_t gmask = (G >= 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1)));
-    float myvx[(4 + G - 1) / G], myvy[(4 + G - 1) / G], myq[(4 + G - 1) / G];
-#pragma unroll
-    for (int k = 0; k < (4 + G - 1) / G; k++) {         // select without dynamic register indexing
-        const int v = lane + k * G;
-        myvx[k] = v == 0 ? rvx[0] : (v == 1 ? rvx[1] : (v == 2 ? rvx[2] : rvx[3]));
-        myvy[k] = v == 0 ? rvy[0] : (v == 1 ? rvy[1] : (v == 2 ? rvy[2] : rvy[3]));
-        myq[k] = 0.0f;
-    }
-    uint32_t md = 1u << c0, mx = 1u << c0;
+    uint32_t md = 1u << c0, mx = 1u << c0;   // chunks to scan for distances / for crossings
 #pragma unroll 1
     for (int pass = 0; pass < 2; pass++) {
         uint32_t m = md | mx;
@@ -445,28 +437,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
         while (m) {
             const int c = __ffs(m) - 1;
             m &= m - 1;
-            const bool do_x = (mx >> c) & 1u;
-            uint32_t need = 0;
-            if ((md >> c) & 1u) {
-                need = 31u;
-                if (pass && !exhaustive) {
-                    // per-point refinement of the coarse vote: which of the 5 points can still improve in this box.
-                    // The lanes of the group share the test (lane v takes vertex v, lane 0 also the centre) against
-                    // the GROUP-wide best, then OR their bits: one box distance per lane instead of five.
-                    const float4 bx = boxes[c];
-                    need = 0;
-#pragma unroll
-                    for (int k = 0; k < (4 + G - 1) / G; k++)   // this lane's vertices: lane, lane+G, ...
-                        if (lane + k * G < 4 && !(box_lb2(bx, myvx[k], myvy[k]) > myq[k] * 1.01f + 1e-7f))
-                            need |= 2u << (lane + k * G);
-                    // (a chunk that may hold a near segment always gets its centre distances: the crossing gate reads them)
-                    if (lane == 0 && !(box_lb2(bx, px, py) > fmaxf(gq_pt[0] * 1.01f + 1e-7f, near2))) need |= 1u;
-                    // the groups of a warp sit in different iterations here: shuffle within the group's own lanes
-#pragma unroll
-                    for (int k = 1; k < G; k <<= 1) need |= __shfl_xor_sync(gmask, need, k);
-                }
-            }
-            if (!(need | (do_x ? 1u : 0u))) continue;
+            const bool do_x = (mx >> c) & 1u, do_d = (md >> c) & 1u;
             const int s1 = min(c * kChunk + kChunk, nseg);
             for (int s = c * kChunk + lane; s < s1; s += 2 * G) {
                 // two segments per lane-iteration (s, s+G): independent chains; a clamped duplicate is harmless
@@ -475,23 +446,20 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                 const float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
                 const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, len2b = lx2 * lx2 + ly2 * ly2;
                 float q0a = __int_as_float(0x7f800000), q0b = q0a;   // centre -> segment, +inf when not evaluated
-                if (need) {
+                if (do_d) {
                     const float rl = rcp_fast(len2), rl2 = rcp_fast(len2b);
-                    if (need & 1u) {
-                        q0a = seg_q_r(a.x, a.y, lx, ly, rl, px, py);
-                        q0b = seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py);
-                        bq[0].upd(fminf(q0a, q0b));
-                    }
+                    q0a = seg_q_r(a.x, a.y, lx, ly, rl, px, py);
+                    q0b = seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py);
+                    bq[0].upd(fminf(q0a, q0b));
 #pragma unroll
                     for (int v = 0; v < 4; v++)
-                        if (need & (2u << v))
-                            bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, rvx[v], rvy[v]),
-                                                seg_q_r(a2.x, a2.y, lx2, ly2, rl2, rvx[v], rvy[v])));
+                        bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, rvx[v], rvy[v]),
+                                            seg_q_r(a2.x, a2.y, lx2, ly2, rl2, rvx[v], rvy[v])));
                 }
                 if (do_x) {
-                    // Gate of the exact predicate: the segment is near the rectangle (then the chunk is a near chunk
-                    // and q0 was evaluated), or it is collinear with an edge direction within kCollinear — the only
-                    // way fp32 sign noise can fire interX on a far segment.  Everything else is certified "no hit".
+                    // Gate of the exact predicate: the segment is near the rectangle (then its chunk is a near chunk,
+                    // hence a distance chunk, and q0 was evaluated), or it is collinear with an edge direction within
+                    // kCollinear — the only way fp32 sign noise can fire interX on a far segment ...
                     const float cs = *cs_s, sn = *sn_s;   // heading; read here so that it is not live across the scan
                     const float cr = lx * sn - ly * cs, dt = lx * cs + ly * sn;
                     const float cr2 = lx2 * sn - ly2 * cs, dt2 = lx2 * cs + ly2 * sn;
@@ -509,19 +477,12 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
             }
         }
         if (pass) break;
-        // group-wide bound (lanes that got no segment of the hint chunk hold +inf): every point is within
-        // rect_radius of the centre, so a chunk can matter for some point only if lb(centre) <= max best + radius
+        // Vote.  Group-wide bound after the hint chunk (lanes that got no segment hold +inf): every point is within
+        // rect_radius of the centre, so a chunk can matter for some point only if lb(centre) <= max best + radius.
+        float gq = group_min<G>(bq[0].q);
 #pragma unroll
-        for (int v = 0; v < 5; v++) gq_pt[v] = group_min<G>(bq[v].q);
-        float gq = gq_pt[0];
-#pragma unroll
-        for (int v = 1; v < 5; v++) gq = fmaxf(gq, gq_pt[v]);
-#pragma unroll
-        for (int k = 0; k < (4 + G - 1) / G; k++) {
-            const int v = lane + k * G;
-            myq[k] = v == 0 ? gq_pt[1] : (v == 1 ? gq_pt[2] : (v == 2 ? gq_pt[3] : gq_pt[4]));
-        }
-        float thr = fmaxf(sqrtf(gq) + rect_radius + kDistMargin, near_r + kDistMargin);   // near chunks are in md
+        for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
+        float thr = fmaxf(sqrtf(gq) + rect_radius + kDistMargin, near_r + kDistMargin);   // near chunks are distance chunks
         thr = thr * thr;
         md = 0; mx = 0;
         const float pi_f = 3.14159274f, half_pi = 1.57079637f;
