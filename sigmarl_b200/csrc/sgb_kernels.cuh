@@ -256,12 +256,13 @@ __device__ __forceinline__ bool rect_cross_seg_L1(const float* rvx, const float*
     bool hit = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
+        if (!c2[i]) continue;            // C1[i] only matters where C2[i] holds (typically two of the four edges)
         const int j = (i + 1) & 3;
         const float dxi = rvx[j] - rvx[i], dyi = rvy[j] - rvy[i];
         const float Si = msub2(dxi, rvy[i], dyi, rvx[i]);
         const float fa = subr(msub2(dxi, ay, dyi, ax), Si);
         const float fb = subr(msub2(dxi, by, dyi, bx), Si);
-        hit |= (((fa * fb) < 0.0f) & c2[i]);
+        hit |= (fa * fb) < 0.0f;
     }
     return hit;
 }
@@ -463,16 +464,30 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                     const float cs = *cs_s, sn = *sn_s;   // heading; read here so that it is not live across the scan
                     const float cr = lx * sn - ly * cs, dt = lx * cs + ly * sn;
                     const float cr2 = lx2 * sn - ly2 * cs, dt2 = lx2 * cs + ly2 * sn;
-                    bool ga = (q0a <= near2) | (fminf(cr * cr, dt * dt) <= (kCollinear * kCollinear) * len2);
-                    bool gb = (q0b <= near2) | (fminf(cr2 * cr2, dt2 * dt2) <= (kCollinear * kCollinear) * len2b);
+                    const bool cola = fminf(cr * cr, dt * dt) <= (kCollinear * kCollinear) * len2;
+                    const bool colb = fminf(cr2 * cr2, dt2 * dt2) <= (kCollinear * kCollinear) * len2b;
+                    bool ga = (q0a <= near2) | cola, gb = (q0b <= near2) | colb;
                     // ... and its LINE must pass through the rectangle, or no C2 term can be true: the segment's line
                     // function at the centre, against its largest change over the oriented rectangle
                     // (half_l |d x u| + half_w |d . u|), with 1e-5 of slack >> the 4e-7 evaluation error of g.
                     const float gca = lx * (py - a.y) - ly * (px - a.x), gcb = lx2 * (py - a2.y) - ly2 * (px - a2.x);
                     ga &= fabsf(gca) <= half_l * fabsf(cr) + half_w * fabsf(dt) + 1e-5f;
                     gb &= fabsf(gcb) <= half_l * fabsf(cr2) + half_w * fabsf(dt2) + 1e-5f;
-                    if (ga | exhaustive) hit |= rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y, true);
-                    if (gb | exhaustive) hit |= rect_cross_seg_L1(rvx, rvy, a2.x, a2.y, e2.x, e2.y, true);
+                    // Last, for the few segments still in: a segment whose two endpoints lie beyond the same side of the
+                    // rectangle by kFarMargin (in the vehicle frame) is "far" in the sense of the certificate above
+                    // even though it is close to the centre — e.g. the lane boundary next to a centred vehicle — and,
+                    // not being collinear, cannot fire.
+                    auto separated = [&](float ax, float ay, float ddx, float ddy) {
+                        const float rx = ax - px, ry = ay - py;
+                        const float lat = cs * ry - sn * rx, lon = cs * rx + sn * ry;     // endpoint a in the vehicle frame
+                        const float late = lat + (cs * ddy - sn * ddx), lone = lon + (cs * ddx + sn * ddy);   // endpoint b
+                        const float wl = half_w + kFarMargin, ll = half_l + kFarMargin;
+                        return (fminf(lat, late) > wl) | (fmaxf(lat, late) < -wl) | (fminf(lon, lone) > ll) | (fmaxf(lon, lone) < -ll);
+                    };
+                    if (exhaustive || (ga && (cola || !separated(a.x, a.y, lx, ly))))
+                        hit |= rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y, true);
+                    if (exhaustive || (gb && (colb || !separated(a2.x, a2.y, lx2, ly2))))
+                        hit |= rect_cross_seg_L1(rvx, rvy, a2.x, a2.y, e2.x, e2.y, true);
                 }
             }
         }
