@@ -624,6 +624,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     const int n_slots = EW * N;                 // slots this warp uses
     const int lane = ln % G;                    // lane within the agent's group
     const int sl_l = ln / G;                    // slot (within the warp) this lane works for in phases B/C
+    const int i_of_lane = sl_l % N;             // its agent index within the env
     const float rect_radius = p.rect_radius;
     const float r_pos = p.r_pos, r_v = p.r_v, r_dist = p.r_dist;
 
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
         if (!step_mode && p.skip_scan) {
             // spawn-table refresh: the scan results of this pose were computed once, at context creation
             if (slot_ok && lane == 0) {
-                const float4 fr = reinterpret_cast<const float4*>(p.fresh)[(size_t)ts.env[sl] * N + (sl - slot0) % N];
+                const float4 fr = reinterpret_cast<const float4*>(p.fresh)[(size_t)ts.env[sl] * N + i_of_lane];
                 ts.sc[0 * AS + sl] = ts.car[0 * AS + sl];
                 ts.sc[1 * AS + sl] = ts.car[3 * AS + sl];
                 ts.sc[2 * AS + sl] = fr.x; ts.sc[3 * AS + sl] = fr.y;
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
             }
             const bool ex = cfg.exhaustive != 0;
             const bool writer = slot_ok && lane == 0;
-            float* dbg = (p.buf.dbg && writer) ? p.buf.dbg + ((size_t)ts.env[sl] * N + (sl - slot0) % N) * 16 : nullptr;
+            float* dbg = (p.buf.dbg && writer) ? p.buf.dbg + ((size_t)ts.env[sl] * N + i_of_lane) * 16 : nullptr;
             // hint = last closest segment (step) / the spawn point written by place_agent (refresh); any value
             // is valid, a good one lets the first chunk scanned set a tight pruning bound
             const int hint = __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1;
@@ -860,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
 
         // ================= phase C: interactions inside the env, reward, observation ===============  @region phase C1
         {
-            const int i = (sl - slot0) % N;
+            const int i = slot_ok ? i_of_lane : 0;   // (sl - slot0) % N, hoisted out of the tile loop
             const int base = sl - i; // slot of agent 0 of this env
             const float pix = ts.px[sl], piy = ts.py[sl];
             const uint32_t coll = (uint32_t)ts.coll[sl];
