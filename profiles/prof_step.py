@@ -10,6 +10,6 @@ ur = torch.tensor([1.0, 31 * np.pi / 180], device="cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
 for t in range(6):
     env.step((torch.rand(B, 8, 2, device="cuda", generator=g) * 2 - 1) * ur)
-    env.reset_done(write_obs=False)
+    env.reset_done(write_obs=True)
 torch.cuda.synchronize()
 print("done", float(env.done.float().mean()))
