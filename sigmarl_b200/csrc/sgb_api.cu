@@ -238,7 +238,7 @@ int ensure_fresh(sgb_ctx* c, int64_t agents) {
 
 template <int G, int MODE>
 int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
-    const int slots = kThreads / G;
+    const int slots = kSlots;
     const int envs_per_warp = 32 / (p.N * G);
     if (envs_per_warp < 1) return SGB_ERR_ARG;
     const int n_wt = (p.B + envs_per_warp - 1) / envs_per_warp;   // upper bound (a list may hold fewer envs)
@@ -254,9 +254,9 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
         CK(cudaFuncSetAttribute(env_step_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int warps = kThreads / 32;
+    const int warps = cta_threads(G) / 32;
     const int grid = std::min((n_wt + warps - 1) / warps, ctx->num_sms);
-    env_step_kernel<G, MODE><<<grid, kThreads, smem, st>>>(p);
+    env_step_kernel<G, MODE><<<grid, cta_threads(G), smem, st>>>(p);
     ctx->launches++;
     CK(cudaGetLastError());
     return SGB_OK;

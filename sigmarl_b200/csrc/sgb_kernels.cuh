@@ -36,7 +36,12 @@ namespace sgb {
 #ifndef SGB_SYNC_WARPS_REFRESH  // same for the refresh kernel (0.137 -> 0.133 ms per masked reset at 26 % done envs)
 #define SGB_SYNC_WARPS_REFRESH 8
 #endif
-constexpr int kThreads = SGB_THREADS; // threads per CTA (one CTA per SM: the map blob fills most of the shared memory)
+// Threads per CTA (one CTA per SM: the map blob fills most of the shared memory) for G = 4 lanes per agent.  The CTA
+// always holds kSlots agent slots — that fixes the shared-memory footprint next to the map — so with fewer lanes per
+// agent it has fewer threads, and more registers each: G = 4 -> 1024 threads, G = 2 -> 512, G = 1 -> 256.
+constexpr int kThreads = SGB_THREADS;
+constexpr int kSlots = kThreads / 4;
+__host__ __device__ constexpr int cta_threads(int G) { return kSlots * G; }
 constexpr int kChunk = 8;            // polyline segments per bounding-box chunk
 constexpr int kExt = 6;              // extension points behind a centre line (3 short-term pts x interval 2)
 constexpr float kDistMargin = 1e-4f; // [m]  >> fp32 error of a point-segment distance (~3e-6)
@@ -324,7 +329,7 @@ struct TileSmem {
     float* psim;                // heading mod pi (direction-cone tests)
     float* vtx;                 // [8][A]: x0..x3, y0..y3
     float* car;                 // [4][A]: carry of the pre-step pose
-    float* sc;                  // [8][A]: phase-B results: d_ref, idx(int), dLcg, dRcg, min4L, min4R, flags(int), spare
+    float* sc;                  // [6][A]: phase-B results: d_ref, idx(int), dLcg, dRcg, min4L, min4R
     float* dij;                 // [A][N] centre distances
     int* path;
     int* flags;
@@ -334,14 +339,14 @@ struct TileSmem {
 
 // Dynamic shared memory layout: [ slot arrays (size fixed at compile time) | map blob | dij [A][N] ].  With the slot
 // arrays first, every t.x[...] is an LDS/STS at a compile-time constant address + index: no pointer registers.
-constexpr int kSlotFloats = 10 + 8 + 4 + 8 + 4;   // per slot: 10 scalars, vtx[8], car[4], sc[8], path/flags/env/coll
+constexpr int kSlotFloats = 10 + 8 + 4 + 6 + 4;   // per slot: 10 scalars, vtx[8], car[4], sc[6], path/flags/env/coll
 __host__ __device__ constexpr size_t tile_fixed_bytes(int A) { return ((size_t)A * kSlotFloats * sizeof(float) + 127) & ~(size_t)127; }
 template <int A>
 __device__ __forceinline__ void carve_tile(unsigned char* base, TileSmem& t) {
     float* f = reinterpret_cast<float*>(base);
     t.px = f; f += A; t.py = f; f += A; t.ox = f; f += A; t.oy = f; f += A;
     t.cs = f; f += A; t.sn = f; f += A; t.vx = f; f += A; t.vy = f; f += A; t.vabs = f; f += A; t.psim = f; f += A;
-    t.vtx = f; f += 8 * A; t.car = f; f += 4 * A; t.sc = f; f += 8 * A;
+    t.vtx = f; f += 8 * A; t.car = f; f += 4 * A; t.sc = f; f += 6 * A;
     t.path = reinterpret_cast<int*>(f); f += A; t.flags = reinterpret_cast<int*>(f); f += A;
     t.env = reinterpret_cast<int*>(f); f += A;
     t.coll = reinterpret_cast<int*>(f); f += A;
@@ -578,7 +583,7 @@ __device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int 
 // apart and overlap their ALU / MUFU / shared-memory phases.
 // MODE 0 = step, MODE 1 = refresh (rebuild carry / observation from the current pose; no dynamics, no reward).
 template <int G, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
+__global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long mbar;
 
@@ -586,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     const int N = p.N, D = p.D;
     const sgb_config& cfg = p.cfg;
     constexpr bool step_mode = (MODE == 0);
-    constexpr int kWarps = kThreads / 32;
+    constexpr int kWarps = cta_threads(G) / 32;
     constexpr int SPW = 32 / G;                 // agent slots per warp
     const int env_lanes = N * G;                // lanes per env
     const int EW = 32 / env_lanes;              // envs per warp (>= 1, checked by the host)
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     if ((int)blockIdx.x * kWarps >= n_wt) return;  // nothing to do for this CTA: do not even stage the map
     if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)p.blob_bytes);
-        const uint32_t dst = smem_u32(smem + tile_fixed_bytes(kThreads / G));
+        const uint32_t dst = smem_u32(smem + tile_fixed_bytes(kSlots));
         for (int off = 0; off < p.blob_bytes; off += 32768) {
             int n = min(32768, p.blob_bytes - off);
             tma_bulk_g2s(dst + off, p.blob + off, (uint32_t)n, bar);
@@ -612,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     }
     bool map_ready = false;
 
-    constexpr int AS = kThreads / G;            // slot stride of the SoA arrays (all warps)
+    constexpr int AS = kSlots;                  // slot stride of the SoA arrays (all warps)
     unsigned char* const blob_s = smem + tile_fixed_bytes(AS);
     const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(blob_s);
     TileSmem ts;
@@ -632,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) env_step_kernel(const Params p) {
     // 32 KB instruction cache, and 32 free-running warps keep all of it live at once.  Groups of SYNCW warps
     // therefore walk the phases together (named barrier per group): at any time a group executes one phase's
     // code only.  Every warp of the CTA runs the same number of tile iterations so that the barriers match.
-    constexpr int SYNCW = step_mode ? SGB_SYNC_WARPS : SGB_SYNC_WARPS_REFRESH;
+    constexpr int SYNCW = (step_mode ? SGB_SYNC_WARPS : SGB_SYNC_WARPS_REFRESH) * G / 4;   // always 4 groups per CTA
     static_assert(SYNCW <= 1 || (kWarps % (SYNCW > 0 ? SYNCW : 1) == 0 && kWarps / (SYNCW > 0 ? SYNCW : 1) <= 15), "phase-aligned groups must tile the CTA (named barriers 1..15)");
     auto phase_sync = [&]() {
         if (SYNCW >= kWarps) __syncthreads();

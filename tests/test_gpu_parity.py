@@ -147,6 +147,9 @@ def _oracle_for(env, O, rew_method, mode):
     ("on_ramp_2_multilane", 12, "ttc", "kwargs", 256),
     ("roundabout_2", 12, "sparse", "params", 256),
     ("cpm_entire", 8, "ttc", "params", 256),           # run with n_nearing_agents_observed = 5 below (k > 2 path)
+    ("cpm_entire", 15, "ttc_sparse", "params", 128),       # the reference's default n_agents on this map (G = 2)
+    ("cpm_entire", 18, "distance_sparse", "params", 96),   # N > 16: one lane per agent (G = 1 instantiation)
+    ("cpm_entire", 1, "distance", "params", 64),           # single agent: nobody to observe, k = 0
 ])
 def test_cuda_matches_oracle_free_running_with_device_resets(oracle_mod, scenario, N, rew, mode, B):
     """GPU drives (device resets included); every step the oracle is teacher-forced from the GPU's pre-step state."""
