@@ -1,23 +1,28 @@
 // sgb_kernels.cuh — device code of libsigmarl_b200: the fused road-traffic environment step for sm_100a.
 //
-// One persistent CTA per SM.  Each CTA bulk-copies (TMA, cp.async.bulk + mbarrier) the packed map
-// blob into shared memory once, then loops over tiles of whole envs:
+// One persistent CTA per SM (256 agent slots, 256 * G threads).  Each CTA bulk-copies (TMA, cp.async.bulk +
+// mbarrier) the packed map blob into shared memory once, then loops over tiles of whole envs; groups of warps walk
+// the phases together (named barriers) so that one phase's code stays in the instruction cache:
 //   phase A  one thread per agent : kinematic-bicycle Euler tick, rectangle vertices  -> smem
 //   phase B  G lanes per agent    : point->polyline distances (centre line, left/right boundary) and
-//                                   rectangle-vs-boundary crossing tests out of the smem map, pruned
-//                                   with per-chunk bounding boxes; warp-shuffle reductions
-//   phase C  G lanes per agent    : centre distances / rectangle crossings / TTC against the other
-//                                   agents of the env, k-nearest selection, reward, observation -> smem
-//   phase D  one lane per env     : done flag, step counter
+//                                   rectangle-vs-boundary crossing tests out of the smem map: hint chunk, vote
+//                                   over per-chunk boxes / direction cones, walk of the voted chunks;
+//                                   warp-shuffle reductions; then the rectangle pairs of the env
+//   phase C  G lanes per agent    : centre distances / TTC against the other agents of the env, k-nearest
+//                                   selection, reward, observation (written in place), next carry, info block
+//   phase D  per env              : done flag, step counter, evaluation counters (warp ballots)
+// In refresh mode (MODE 1) the same kernel rebuilds carry / observation from the current pose; after a device
+// reset phase B is skipped (spawn table, see place_agent).
 //
 // Arithmetic contract (see DESIGN.md "Exactness"): IEEE sqrt/div, no fast-math.  FMA contraction is
 // left ON for the compiler, but every value that feeds an argmin, a strict-sign collision predicate
 // or the integrated state is written with never-contracted __fmul_rn/__fadd_rn/__fsub_rn in the
-// reference's operation order
-// (helper_scenario.py:829-889, :1148-1229), so those decisions are bit-identical to the reference
-// given the same inputs.  Pruning never changes a result: distance chunks are skipped only when a
-// lower bound exceeds the running best by a margin 30x larger than the fp32 evaluation error, and
-// crossing tests are skipped only when every edge-line sign is certified with a margin.
+// reference's operation order (helper_scenario.py:829-889, :1148-1229), so those decisions are bit-identical
+// to the reference given the same inputs.  Pruning never changes a result: distance chunks are skipped only
+// when a lower bound exceeds the running best by a margin 30x larger than the fp32 evaluation error, and the
+// exact crossing predicate is skipped only for segments that are certified unable to fire it (far from the
+// rectangle and not collinear with an edge, or whose line misses the rectangle) — cfg.exhaustive = 1 bypasses
+// all of it and must give bit-identical outputs.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
