@@ -90,6 +90,19 @@ class RoadTrafficEnv:
     def map_bytes(self):
         return int(self.L.sgb_map_bytes(self._ctx))
 
+    def bind(self, **tensors):
+        """Point kernel inputs / outputs at caller-owned tensors of the same shape and dtype (e.g. slices of a
+        rollout buffer), so that a step writes them in place: ``env.bind(obs=buf.obs[t + 1], reward=buf.reward[t])``.
+        Only ``obs``, ``reward``, ``done`` and ``action`` may be re-bound; state buffers stay owned by the env."""
+        for name, t in tensors.items():
+            if name not in ("obs", "reward", "done", "action"):
+                raise ValueError(f"cannot re-bind {name!r}")
+            cur = getattr(self, name)
+            if t.shape != cur.shape or t.dtype != cur.dtype or t.device != cur.device or not t.is_contiguous():
+                raise ValueError(f"bind({name}): need a contiguous {tuple(cur.shape)} {cur.dtype} tensor on {cur.device}")
+            setattr(self, name, t)
+            setattr(self._buf, name, t.data_ptr())
+
     # ------------------------------------------------------------------ the path
     def step(self, action: torch.Tensor = None, auto_reset: bool = False):
         """One fused-kernel environment step.  Returns views (obs [B,N,D], reward [B,N], done [B] uint8)."""

@@ -53,25 +53,52 @@ class RolloutBuffer:
 
 
 def collect(env, policy: Callable[[torch.Tensor], torch.Tensor], buf: RolloutBuffer,
-            value_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+            value_fn: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, in_place: bool = True):
     """T environment steps.  `policy(obs[B,N,D]) -> action[B,N,2]`; `value_fn(obs) -> [B,N]` (optional).
 
     TorchRL semantics kept (SURVEY.md assumption A5): the stored next-state value of a done env is the value of
-    its step-time observation (before the reset); the observation the policy sees next is the post-reset one."""
-    obs = env.obs
-    for t in range(buf.T):
-        buf.obs[t].copy_(obs)
-        if value_fn is not None:
-            buf.value[t].copy_(value_fn(obs))
-        act = policy(obs)
-        buf.action[t].copy_(act)
-        obs, rew, done = env.step(act)
-        buf.reward[t].copy_(rew)
-        buf.done[t].copy_(done)
-        if value_fn is not None:
-            buf.next_value[t].copy_(value_fn(obs))
-        env.reset_done(write_obs=True)   # fresh observation for reset envs, step-time observation elsewhere
+    its step-time observation (before the reset); the observation the policy sees next is the post-reset one.
+
+    in_place: the env's outputs are bound to the rollout buffer (``RoadTrafficEnv.bind``): step t reads its action
+    from ``buf.action[t]`` and writes ``buf.reward[t]``, ``buf.done[t]`` and — as the next step's input —
+    ``buf.obs[t + 1]`` directly; no per-step stacking or copies (the reference stacks TensorDicts,
+    ``helper_training.py:745-770``).  in_place=False keeps the env's own buffers and copies (same results)."""
+    T = buf.T
+    if not in_place:
         obs = env.obs
+        for t in range(T):
+            buf.obs[t].copy_(obs)
+            if value_fn is not None:
+                buf.value[t].copy_(value_fn(obs))
+            act = policy(obs)
+            buf.action[t].copy_(act)
+            obs, rew, done = env.step(act)
+            buf.reward[t].copy_(rew)
+            buf.done[t].copy_(done)
+            if value_fn is not None:
+                buf.next_value[t].copy_(value_fn(obs))
+            env.reset_done(write_obs=True)   # fresh observation for reset envs, step-time observation elsewhere
+            obs = env.obs
+        return buf
+    own = dict(obs=env.obs, reward=env.reward, done=env.done, action=env.action)
+    buf.obs[0].copy_(env.obs)
+    try:
+        for t in range(T):
+            obs = buf.obs[t]
+            if value_fn is not None:
+                buf.value[t].copy_(value_fn(obs))
+            buf.action[t].copy_(policy(obs))
+            env.bind(action=buf.action[t], reward=buf.reward[t], done=buf.done[t],
+                     obs=buf.obs[t + 1] if t + 1 < T else own["obs"])
+            env.step(None)
+            if value_fn is not None:
+                buf.next_value[t].copy_(value_fn(env.obs))
+            env.reset_done(write_obs=True)
+    finally:
+        own["reward"].copy_(env.reward)
+        own["done"].copy_(env.done)
+        own["action"].copy_(env.action)
+        env.bind(**own)
     return buf
 
 

@@ -47,3 +47,26 @@ def test_collect_fills_buffers_and_keeps_reset_semantics():
     want_a, _ = gae_numpy(buf.reward.cpu().numpy(), buf.value.cpu().numpy(), buf.next_value.cpu().numpy(),
                           buf.done.cpu().numpy().astype(bool), 0.99, 0.9)
     assert np.max(np.abs(adv.cpu().numpy() - want_a)) <= 1e-5
+
+
+def test_in_place_collect_equals_copying_collect():
+    """Binding the env's outputs to the rollout buffer (no per-step copies) must fill exactly the same buffers."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    from sigmarl_b200.rollout import RolloutBuffer, collect
+    bufs = []
+    for in_place in (True, False):
+        env = RoadTrafficEnv(EnvConfig(scenario_type="cpm_mixed", n_agents=4), num_envs=512, device="cuda:0", seed=5)
+        env.reset()
+        buf = RolloutBuffer(12, env.B, env.N, env.D, env.device)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        ur = torch.tensor([1.0, 31 * np.pi / 180], device="cuda")
+        policy = lambda obs: (torch.rand(env.B, env.N, 2, device="cuda", generator=g) * 2 - 1) * ur  # noqa: E731
+        value = lambda obs: obs[..., 0] - obs[..., 7]  # noqa: E731
+        collect(env, policy, buf, value_fn=value, in_place=in_place)
+        bufs.append((buf, env.obs.clone(), env.reward.clone(), env.done.clone(), env.pose.clone()))
+    a, b = bufs
+    for name in ("obs", "action", "reward", "done", "value", "next_value"):
+        assert torch.equal(getattr(a[0], name), getattr(b[0], name)), name
+    for x, y in zip(a[1:], b[1:]):
+        assert torch.equal(x, y)
+    assert a[0].done.sum() > 0
