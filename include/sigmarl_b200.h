@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 110
+#define SGB_VERSION 120
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -181,6 +181,14 @@ int sgb_place(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const 
 int sgb_reset(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
               uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t write_obs,
               int32_t* n_failed, void* stream);
+
+/* Same machinery with an EXPLICIT selection instead of done / collision flags: envs with env_mask[b] != 0 are
+ * reset fully, agents with agent_mask[b,a] != 0 (in envs not reset fully) are respawned, whatever the map or
+ * mode.  Either mask may be NULL.  Replaces reset_world_at(env_index, agent_index) called from outside the
+ * step (road_traffic.py:816-923; evaluation code, vmas Environment.reset_at). */
+int sgb_reset_masked(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* env_mask,
+                     const uint8_t* agent_mask, int32_t path_lo, int32_t path_hi, uint64_t seed, uint64_t epoch,
+                     int64_t env_offset, int32_t max_tries, int32_t write_obs, int32_t* n_failed, void* stream);
 
 /* Same as sgb_reset but for ALL envs regardless of `done` (Environment.reset()). */
 int sgb_reset_all(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,

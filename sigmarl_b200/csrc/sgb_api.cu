@@ -457,13 +457,14 @@ extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* bu
 
 static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
                       uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t write_obs,
-                      int32_t* n_failed, int all, cudaStream_t st) {
+                      int32_t* n_failed, int all, cudaStream_t st, int explicit_sel = 0,
+                      const uint8_t* env_mask = nullptr, const uint8_t* agent_mask = nullptr) {
     if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || path_lo < 0 || path_hi > c->n_paths || path_lo >= path_hi ||
         max_tries <= 0)
         return SGB_ERR_ARG;
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
-    if (!buf->step_count || (!all && !buf->done)) return SGB_ERR_ARG;
+    if (!buf->step_count || (!all && !explicit_sel && !buf->done)) return SGB_ERR_ARG;
     if (write_obs && !buf->obs) return SGB_ERR_ARG;
     rc = ensure_list(c, B);
     if (rc) return rc;
@@ -475,6 +476,7 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     p.n_failed = n_failed; p.seed = seed; p.epoch = epoch; p.env_offset = env_offset;
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
     p.spawn_tab = c->d_spawn; p.fresh = c->d_fresh; p.list_full_only = 1;
+    p.explicit_sel = explicit_sel; p.env_mask = env_mask; p.agent_mask = agent_mask;
     reset_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
     c->launches++;
     CK(cudaGetLastError());
@@ -497,6 +499,14 @@ extern "C" int sgb_reset_all(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
                              void* stream) {
     return reset_impl(c, B, N, buf, path_lo, path_hi, seed, epoch, env_offset, max_tries, buf && buf->obs ? 1 : 0,
                       n_failed, 1, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_reset_masked(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* env_mask,
+                                const uint8_t* agent_mask, int32_t path_lo, int32_t path_hi, uint64_t seed, uint64_t epoch,
+                                int64_t env_offset, int32_t max_tries, int32_t write_obs, int32_t* n_failed, void* stream) {
+    if (!env_mask && !agent_mask) return SGB_ERR_ARG;
+    return reset_impl(c, B, N, buf, path_lo, path_hi, seed, epoch, env_offset, max_tries, write_obs, n_failed, 0,
+                      (cudaStream_t)stream, 1, env_mask, agent_mask);
 }
 
 // Host-buffer step, pipelined: the batch is cut into chunks that alternate between two internal streams, so

@@ -1192,6 +1192,9 @@ struct ResetParams {
     uint64_t seed, epoch;
     int64_t env_offset;
     int32_t B, N, path_lo, path_hi, max_tries, all;
+    const uint8_t* env_mask;   // explicit selection (sgb_reset_masked): envs to reset fully (may be NULL) ...
+    const uint8_t* agent_mask; // ... and agents to respawn; when either is given, done / flags / config are ignored
+    int32_t explicit_sel;
     const float* spawn_tab;    // see place_agent
     float* fresh;              // [B,N,4] scratch for the observation refresh of fully reset envs
     int32_t list_full_only;    // 1: only fully reset envs go into `list` (they get a fresh observation)
@@ -1202,9 +1205,14 @@ __global__ void reset_kernel(const ResetParams p) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.B) return;
     const int N = p.N;
-    const bool full = p.all || p.buf.done[e];
+    const bool full = p.explicit_sel ? (p.env_mask && p.env_mask[e]) : (p.all || p.buf.done[e]);
     uint32_t respawn = 0;
-    if (!full) {
+    if (!full && p.explicit_sel) {
+        if (!p.agent_mask) return;
+        for (int a = 0; a < N; a++)
+            if (p.agent_mask[(size_t)e * N + a]) respawn |= 1u << a;
+        if (!respawn) return;
+    } else if (!full) {
         // training mode (:1449-1472): agents that crossed an entry / exit segment, maps with open paths only;
         // testing mode (:1435-1447): every colliding or leaving agent, on every map
         if (!p.cfg.respawn_on_exit && !p.cfg.testing_mode) return;

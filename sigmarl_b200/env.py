@@ -120,6 +120,18 @@ class RoadTrafficEnv:
                                     self.seed, self.epoch, self.env_offset, self.max_reset_tries, int(write_obs),
                                     C.c_void_p(self.n_failed.data_ptr()), self._stream()), "sgb_reset")
 
+    def reset_masked(self, env_mask: torch.Tensor = None, agent_mask: torch.Tensor = None, write_obs: bool = True):
+        """Explicit selection: fully reset the envs of `env_mask` [B], respawn the agents of `agent_mask` [B,N]
+        (whatever the map / mode) — ``reset_world_at(env_index, agent_index)`` called from outside the step."""
+        self.epoch += 1
+        prep = lambda m: None if m is None else m.to(device=self.device, dtype=torch.uint8).contiguous()  # noqa: E731
+        em, am = prep(env_mask), prep(agent_mask)
+        ptr = lambda m: C.c_void_p(m.data_ptr()) if m is not None else None  # noqa: E731
+        _lib.check(self.L.sgb_reset_masked(self._ctx, self.B, self.N, C.byref(self._buf), ptr(em), ptr(am), self.path_lo,
+                                           self.path_hi, self.seed, self.epoch, self.env_offset, self.max_reset_tries,
+                                           int(write_obs), C.c_void_p(self.n_failed.data_ptr()), self._stream()),
+                   "sgb_reset_masked")
+
     def reset(self):
         """Environment.reset(): (re)place every agent of every env; returns the fresh observation."""
         self.epoch += 1

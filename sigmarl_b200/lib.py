@@ -15,7 +15,7 @@ SGB_REW_EXACT_SPARSE, SGB_REW_TTC, SGB_REW_DISTANCE, SGB_REW_SPARSE = 1, 2, 4, 8
 
 # every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",
-           "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
+           "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
            "sgb_status_string", "sgb_last_error", "sgb_version"]
 
 
@@ -82,6 +82,7 @@ def load_library():
     L.sgb_place.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, vp, vp, vp]
     L.sgb_reset.argtypes = [vp, i32, i32, C.POINTER(Buffers), i32, i32, u64, u64, i64, i32, i32, vp, vp]
     L.sgb_reset_all.argtypes = [vp, i32, i32, C.POINTER(Buffers), i32, i32, u64, u64, i64, i32, vp, vp]
+    L.sgb_reset_masked.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, i32, i32, u64, u64, i64, i32, i32, vp, vp]
     L.sgb_step_host.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, vp, vp, vp]
     L.sgb_gae.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
     L.sgb_launch_count.argtypes = [vp]

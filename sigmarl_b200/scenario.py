@@ -192,26 +192,15 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             e.reset()
             return
         if agent_index is not None:
-            # single-agent respawn: flag the agent as an exit-crosser and let the masked kernel re-place it
-            flags = torch.zeros_like(e.agent_flags)
-            flags[int(env_index), int(agent_index)] = _lib.SGB_FLAG_EXIT
-            keep_f, keep_d = e.agent_flags.clone(), e.done.clone()
-            e.agent_flags.copy_(flags)
-            e.done.zero_()
-            e.reset_done(write_obs=False)
-            keep_f[int(env_index)] = 0
-            e.agent_flags.copy_(keep_f)
-            e.done.copy_(keep_d)
+            # single-agent respawn (any map, any mode); the step-time observation stays, like in the reference
+            m = torch.zeros(e.B, e.N, dtype=torch.uint8, device=e.device)
+            m[int(env_index), int(agent_index)] = 1
+            e.reset_masked(agent_mask=m, write_obs=False)
             return
-        keep_d, keep_f = e.done.clone(), e.agent_flags.clone()
-        e.done.zero_()
-        e.done[int(env_index)] = 1
-        e.agent_flags.zero_()
-        e.reset_done(write_obs=True)
-        keep_f[int(env_index)] = 0
-        e.agent_flags.copy_(keep_f)
-        keep_d[int(env_index)] = 0
-        e.done.copy_(keep_d)
+        m = torch.zeros(e.B, dtype=torch.uint8, device=e.device)
+        m[int(env_index)] = 1
+        e.reset_masked(env_mask=m, write_obs=True)
+        e.done[int(env_index)] = 0
 
     def process_action(self, agent):
         pass
@@ -227,21 +216,13 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
         e = self.env
         is_done = e.done.bool().clone()
         if (e.cfg.respawn_on_exit or e.cfg.testing_mode) and self._stepped:
-            # :1462-1472 — respawn entry/exit crossers of envs that are NOT done (done envs are reset by the caller)
-            keep = e.done.clone()
-            e.done.zero_()
+            # :1462-1472 — respawn entry/exit crossers of envs that are NOT done (done envs are reset by the caller);
+            # :1435-1447 — in testing mode colliding agents are respawned one by one as well
             which = _lib.SGB_FLAG_ENTRY | _lib.SGB_FLAG_EXIT
-            if e.cfg.testing_mode:     # :1435-1447 — colliding agents are respawned one by one as well
+            if e.cfg.testing_mode:
                 which |= _lib.SGB_FLAG_COLLIDE_AGENT | _lib.SGB_FLAG_COLLIDE_LANE
-            crossing = (e.agent_flags & which) != 0
-            crossing &= ~is_done.unsqueeze(1)
-            saved = e.agent_flags.clone()
-            e.agent_flags.mul_(crossing.to(torch.uint8))
-            e.reset_done(write_obs=False)
-            touched = crossing.any(dim=1)
-            saved[touched] = 0
-            e.agent_flags.copy_(saved)
-            e.done.copy_(keep)
+            crossing = ((e.agent_flags & which) != 0) & ~is_done.unsqueeze(1)
+            e.reset_masked(agent_mask=crossing, write_obs=False)
         self._stepped = False
         return is_done
 

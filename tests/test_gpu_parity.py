@@ -392,7 +392,7 @@ def test_library_refuses_bad_arguments():
     from sigmarl_b200 import lib
     L = lib.load_library()
     assert L.sgb_step(None, 1, 1, None, None) == -1
-    assert L.sgb_version() == 110
+    assert L.sgb_version() == 120
 
 
 @pytest.mark.parametrize("name", ["c1_intersection_B4_N2", "cpm_entire_B8_N8_distance", "cpm_mixed_B8_N4_gentle"])
@@ -590,3 +590,30 @@ def test_facade_testing_mode_respawns_colliding_agents_and_never_ends_early():
         n_resp += int(hit.sum())
         sc.env.reset_done(write_obs=True)
     assert n_resp > 0 and int(sc.env.n_failed) == 0
+
+
+def test_reset_world_at_single_agent_on_any_map_and_mode():
+    """reset_world_at(env_index, agent_index) from outside the step (road_traffic.py:816-923) re-places exactly that
+    agent — also on cpm_entire in training mode, where done() itself never respawns anybody — at a feasible point."""
+    from sigmarl_b200 import make_env
+    env = make_env(scenario_type="cpm_entire", num_envs=64, device="cuda:0", n_agents=8, seed=2, max_steps=128, dt=0.1)
+    sc = env.scenario
+    for (b, a) in [(3, 2), (0, 0), (63, 7)]:
+        before, obs_before = sc.env.pose.clone(), sc.env.obs.clone()
+        sc.reset_world_at(env_index=b, agent_index=a)
+        moved = (sc.env.pose != before).any(-1)
+        want = torch.zeros_like(moved)
+        want[b, a] = True
+        assert torch.equal(moved, want)
+        assert torch.equal(sc.env.obs, obs_before), "a respawn keeps the step-time observation"
+        d = (sc.env.pose[b, :, :2] - sc.env.pose[b, a, :2]).norm(dim=-1)
+        d[a] = 1e9
+        assert float(d.min()) >= 0.3669
+        carried = sc.env.carry.clone()
+        sc.env.refresh()
+        assert torch.equal(carried, sc.env.carry), "carry of the respawned agent comes from the spawn table"
+    before = sc.env.pose.clone()
+    sc.reset_world_at(env_index=5)
+    changed = (sc.env.pose != before).any(-1).any(-1)
+    assert bool(changed[5]) and int(changed.sum()) == 1 and int(sc.env.step_count[5]) == 0
+    assert int(sc.env.n_failed) == 0
