@@ -41,6 +41,20 @@ def ncu_traffic():
     return None
 
 
+def ncu_issue():
+    """Issue-slot utilisation / active lanes of the fused step kernel from the committed ncu capture: the bound that
+    actually limits this kernel (DESIGN.md roofline section); static, for context next to the HBM fraction."""
+    p = os.path.join(REPO, "profiles", "ncu_full_r1.json")
+    try:
+        ks = json.load(open(p))
+        k = max(ks, key=lambda d: float(d["gpu__time_duration.sum"].split()[0]))
+        return {"issue_slots_busy_pct": float(k["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0]),
+                "active_lanes_per_warp_inst": float(k["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0]),
+                "warp_inst_per_launch": float(k["smsp__inst_executed.sum"].split()[0]), "source": "profiles/ncu_full_r1.json"}
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -228,6 +242,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "env_step_kernel (fused step)", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "algorithmic_bytes_per_agent_step": ALGO_BYTES(D), "kernel_ms": 1e3 * t_step / K,
+                     "issue_bound": ncu_issue(),
                      "note": "path is fp32-ALU/shared-memory bound, not HBM bound (DESIGN.md roofline section)"},
         "clocks": sampler.summary(),
         "wall_s_timed_region": t_wall,
