@@ -1,12 +1,14 @@
 """Step-kernel micro-bench: ms per launch of env_step_kernel at the headline shape (CUDA events, L2 flushed).
-   SGB_LIBRARY=<variant.so> python profiles/kbench.py [B] [iters]"""
+   SGB_LIBRARY=<variant.so> python profiles/kbench.py [B] [iters] [scenario] [n_agents]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from sigmarl_b200 import EnvConfig, RoadTrafficEnv
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 60
-env = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=B, device="cuda:0", seed=0)
+SC = sys.argv[3] if len(sys.argv) > 3 else "cpm_entire"
+NA = int(sys.argv[4]) if len(sys.argv) > 4 else 8
+env = RoadTrafficEnv(EnvConfig(scenario_type=SC, n_agents=NA), num_envs=B, device="cuda:0", seed=0)
 env.reset()
 ur = torch.tensor([1.0, 31 * np.pi / 180], device="cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -14,7 +16,7 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 ts, tr = [], []
 chk = 0.0
 for t in range(K + 5):
-    env.action.copy_((torch.rand(B, 8, 2, device="cuda", generator=g) * 2 - 1) * ur)
+    env.action.copy_((torch.rand(B, NA, 2, device="cuda", generator=g) * 2 - 1) * ur)
     flush.zero_()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     e[0].record(); env.step(None); e[1].record(); env.reset_done(write_obs=bool(int(os.environ.get('KB_WRITE_OBS', '0')))); e[2].record()
@@ -22,5 +24,5 @@ for t in range(K + 5):
     if t >= 5:
         ts.append(e[0].elapsed_time(e[1])); tr.append(e[1].elapsed_time(e[2]))
     chk += float(env.reward.double().sum()) + float(env.obs.double().sum())
-print(f"{os.environ.get('SGB_LIBRARY', 'default'):40s} step {np.mean(ts):.4f} ms (min {np.min(ts):.4f})  reset+refresh {np.mean(tr):.4f} ms  "
-      f"-> {B * 8 / (np.mean(ts) + np.mean(tr)) / 1e3:.1f} M agent-steps/s   checksum {chk:.6f}")
+print(f"{os.environ.get('SGB_LIBRARY', 'default')[-28:]:28s} {SC} B={B} N={NA} done-rate {float(env.done.float().mean()):.2f} step {np.mean(ts):.4f} ms (min {np.min(ts):.4f})  reset+refresh {np.mean(tr):.4f} ms  "
+      f"-> {B * NA / (np.mean(ts) + np.mean(tr)) / 1e3:.1f} M agent-steps/s   checksum {chk:.6f}")

@@ -477,7 +477,10 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
     p.spawn_tab = c->d_spawn; p.fresh = c->d_fresh; p.list_full_only = 1;
     p.explicit_sel = explicit_sel; p.env_mask = env_mask; p.agent_mask = agent_mask;
-    reset_kernel<<<(B + 127) / 128, 128, 0, st>>>(p);
+    // envs per warp: as few as keep every warp of the launch resident (48 warps per SM), at most 32
+    p.epw = std::max(1, std::min(32, (B + c->num_sms * 48 - 1) / (c->num_sms * 48)));
+    const int64_t n_warps = ((int64_t)B + p.epw - 1) / p.epw;
+    reset_kernel<<<(int)((n_warps * 32 + 255) / 256), 256, 0, st>>>(p);
     c->launches++;
     CK(cudaGetLastError());
     // carry / aux / flags of every touched env are complete (spawn table); what is left is the all-fresh observation

@@ -1195,82 +1195,140 @@ struct ResetParams {
     const uint8_t* env_mask;   // explicit selection (sgb_reset_masked): envs to reset fully (may be NULL) ...
     const uint8_t* agent_mask; // ... and agents to respawn; when either is given, done / flags / config are ignored
     int32_t explicit_sel;
+    int32_t epw;               // envs per warp of reset_kernel
     const float* spawn_tab;    // see place_agent
     float* fresh;              // [B,N,4] scratch for the observation refresh of fully reset envs
     int32_t list_full_only;    // 1: only fully reset envs go into `list` (they get a fresh observation)
 };
 
-// one thread per env: sequential bounded rejection sampling (world_state_rt_sim.py:215-311)
+// One WARP per env: bounded rejection sampling (world_state_rt_sim.py:215-311).  Agents are placed one after the other
+// (each must keep its distance from the ones before it), but the TRIES of an agent run in parallel: lane l evaluates
+// try 32*r + l of round r, a ballot picks the first feasible one — exactly the try the reference's sequential loop
+// would accept — and the winner is broadcast.  Lane a holds agent a's position; at the end every lane places its own
+// agent (parallel loads from the spawn table, parallel stores).  Crowded maps need many tries per agent (on-ramp /
+// roundabout with 12 agents: the sequential one-thread-per-env version spent 0.14 ms per step there).
 __global__ void reset_kernel(const ResetParams p) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.B) return;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int ln = threadIdx.x & 31;
     const int N = p.N;
-    const bool full = p.explicit_sel ? (p.env_mask && p.env_mask[e]) : (p.all || p.buf.done[e]);
-    uint32_t respawn = 0;
-    if (!full && p.explicit_sel) {
-        if (!p.agent_mask) return;
-        for (int a = 0; a < N; a++)
-            if (p.agent_mask[(size_t)e * N + a]) respawn |= 1u << a;
-        if (!respawn) return;
-    } else if (!full) {
-        // training mode (:1449-1472): agents that crossed an entry / exit segment, maps with open paths only;
-        // testing mode (:1435-1447): every colliding or leaving agent, on every map
-        if (!p.cfg.respawn_on_exit && !p.cfg.testing_mode) return;
-        const uint32_t which = p.cfg.testing_mode ? (SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE | SGB_FLAG_ENTRY | SGB_FLAG_EXIT)
-                                                  : (SGB_FLAG_ENTRY | SGB_FLAG_EXIT);
-        for (int a = 0; a < N; a++)
-            if (p.buf.agent_flags[(size_t)e * N + a] & which) respawn |= 1u << a;
-        if (!respawn) return;
+    // a warp looks after `epw` consecutive envs: lane l finds out whether env l needs work, then the warp handles the
+    // touched ones one after the other (epw is chosen by the host so that all warps of the launch are resident)
+    const int e_first = w * p.epw;
+    if (e_first >= p.B) return;
+    bool l_full = false;
+    uint32_t l_respawn = 0;
+    if (ln < p.epw && e_first + ln < p.B) {
+        const int el = e_first + ln;
+        l_full = p.explicit_sel ? (p.env_mask && p.env_mask[el]) : (p.all || p.buf.done[el]);
+        if (!l_full) {
+            if (p.explicit_sel) {
+                if (p.agent_mask)
+                    for (int a = 0; a < N; a++) l_respawn |= p.agent_mask[(size_t)el * N + a] ? (1u << a) : 0u;
+            } else if (p.cfg.respawn_on_exit || p.cfg.testing_mode) {
+                // training mode (:1449-1472): agents that crossed an entry / exit segment, maps with open paths only;
+                // testing mode (:1435-1447): every colliding or leaving agent, on every map
+                const uint32_t which = p.cfg.testing_mode ? (SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE | SGB_FLAG_ENTRY | SGB_FLAG_EXIT)
+                                                          : (SGB_FLAG_ENTRY | SGB_FLAG_EXIT);
+                for (int a = 0; a < N; a++) l_respawn |= (p.buf.agent_flags[(size_t)el * N + a] & which) ? (1u << a) : 0u;
+            }
+        }
     }
+    uint32_t touched = __ballot_sync(0xffffffffu, l_full || l_respawn != 0u);
+  while (touched) {
+    const int src_l = __ffs(touched) - 1;
+    touched &= touched - 1;
+    const int e = e_first + src_l;
+    const bool full = __shfl_sync(0xffffffffu, (int)l_full, src_l) != 0;
+    const uint32_t respawn = __shfl_sync(0xffffffffu, l_respawn, src_l);
+    const uint32_t todo = full ? (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) : respawn;
     const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(p.blob);
     const PathRec* paths = reinterpret_cast<const PathRec*>(p.blob + hdr->path_off);
     const float2* pts = reinterpret_cast<const float2*>(p.blob + hdr->pts_off);
-    float qx[SGB_MAX_AGENTS], qy[SGB_MAX_AGENTS];
-    for (int a = 0; a < N; a++) {
-        float4 ps = reinterpret_cast<const float4*>(p.buf.pose)[(size_t)e * N + a];
-        qx[a] = ps.x; qy[a] = ps.y;
+    float qx = 0.0f, qy = 0.0f;            // lane a: position of agent a
+    if (ln < N) {
+        const float4 ps = reinterpret_cast<const float4*>(p.buf.pose)[(size_t)e * N + ln];
+        qx = ps.x; qy = ps.y;
     }
+    int my_path = p.path_lo, my_point = 3;  // lane a: where agent a goes (if it is placed)
     const uint64_t env_g = (uint64_t)(p.env_offset + e);
     int failed = 0;
+    auto candidate = [&](int a, int tr, int& path, int& point) {
+        path = p.path_lo + (int)(draw(p.seed, p.epoch, env_g, a, tr, 0) % (uint64_t)(p.path_hi - p.path_lo));
+        const int2 on = *reinterpret_cast<const int2*>(&paths[path].c_off);   // c_off, n_c
+        int end = on.y / 2;
+        // testing mode: the range starts as [3, 4) and grows by the try count (world_state_rt_sim.py:254-261)
+        if (p.cfg.testing_mode) end = min(end, 3 + (tr + 1) * (tr + 2) / 2);
+        point = 3 + (int)(draw(p.seed, p.epoch, env_g, a, tr, 1) % (uint64_t)(end - 3 > 0 ? end - 3 : 1));
+        return pts[on.x + point];
+    };
+    // stage 1: the FIRST try of every agent, all agents in parallel (lane a = agent a) — on roomy maps it is
+    // accepted nine times out of ten, so this is where the draws and the dependent map loads should overlap
+    float2 c0 = make_float2(0.0f, 0.0f);
+    if (ln < N && ((todo >> ln) & 1u)) c0 = candidate(ln, 0, my_path, my_point);
+    // stage 2: accept / retry, agent by agent (each must keep its distance from the ones placed before it)
     for (int a = 0; a < N; a++) {
-        if (!full && !((respawn >> a) & 1u)) continue;
-        bool ok = false;
-        int path = p.path_lo, point = 3;
-        for (int tr = 0; tr < p.max_tries && !ok; tr++) {
-            path = p.path_lo + (int)(draw(p.seed, p.epoch, env_g, a, tr, 0) % (uint64_t)(p.path_hi - p.path_lo));
-            const PathRec pr = paths[path];
-            int end = pr.n_c / 2;
-            // testing mode: the range starts as [3, 4) and grows by the try count (world_state_rt_sim.py:254-261)
-            if (p.cfg.testing_mode) end = min(end, 3 + (tr + 1) * (tr + 2) / 2);
-            point = 3 + (int)(draw(p.seed, p.epoch, env_g, a, tr, 1) % (uint64_t)(end - 3 > 0 ? end - 3 : 1));
-            const float2 c = pts[pr.c_off + point];
-            ok = true;
-            // full reset: against agents 0..a-1 (agent 0 always feasible); respawn: against all others
-            const int lim = full ? a : N;
-            for (int o = 0; o < lim; o++) {
-                if (o == a) continue;
-                float dx = c.x - qx[o], dy = c.y - qy[o];
-                if (!(madd2(dx, dx, dy, dy) >= p.cfg.reset_min_dist_sq)) { ok = false; break; }
+        if (!((todo >> a) & 1u)) continue;
+        // full reset: against agents 0..a-1 (agent 0 always feasible); respawn: against all others
+        const uint32_t others = (full ? ((1u << a) - 1u) : (N >= 32 ? 0xffffffffu : ((1u << N) - 1u))) & ~(1u << a);
+        const float cx = __shfl_sync(0xffffffffu, c0.x, a), cy = __shfl_sync(0xffffffffu, c0.y, a);
+        // try 0: every lane o tests the candidate against ITS agent's position, one ballot
+        const float ddx = cx - qx, ddy = cy - qy;
+        const uint32_t bad = __ballot_sync(0xffffffffu, !(madd2(ddx, ddx, ddy, ddy) >= p.cfg.reset_min_dist_sq)) & others;
+        if (!bad || p.max_tries <= 1) {
+            if (bad) failed++;
+            if (ln == a) { qx = cx; qy = cy; }
+            continue;
+        }
+        // tries 1, 2, ...: 32 at a time, lane l evaluates try 1 + r0 + l; a ballot picks the first feasible one,
+        // exactly the try a sequential loop would accept
+        bool placed = false;
+        int w_path = p.path_lo, w_point = 3;
+        float w_x = 0.0f, w_y = 0.0f;
+        for (int r0 = 1; r0 < p.max_tries && !placed; r0 += 32) {
+            const int tr = r0 + ln;
+            const bool live = tr < p.max_tries;
+            int path = p.path_lo, point = 3;
+            float2 c = make_float2(0.0f, 0.0f);
+            if (live) c = candidate(a, tr, path, point);
+            bool ok = live;
+            for (int o = 0; o < N; o++) {            // warp-uniform loop: every lane tests ITS candidate against agent o
+                const float ox = __shfl_sync(0xffffffffu, qx, o), oy = __shfl_sync(0xffffffffu, qy, o);
+                if (!((others >> o) & 1u)) continue;
+                const float dx = c.x - ox, dy = c.y - oy;
+                if (!(madd2(dx, dx, dy, dy) >= p.cfg.reset_min_dist_sq)) ok = false;
             }
-            if (ok) { qx[a] = c.x; qy[a] = c.y; }
+            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+            // if this was the last round and nothing is feasible, the last try is kept (rather than spinning
+            // forever) and reported
+            const bool last_round = r0 + 32 >= p.max_tries;
+            const int src = okm ? (__ffs(okm) - 1) : (last_round ? (p.max_tries - 1 - r0) : -1);
+            if (src >= 0) {
+                w_path = __shfl_sync(0xffffffffu, path, src);
+                w_point = __shfl_sync(0xffffffffu, point, src);
+                w_x = __shfl_sync(0xffffffffu, c.x, src);
+                w_y = __shfl_sync(0xffffffffu, c.y, src);
+                placed = true;
+                if (!okm) failed++;
+            }
         }
-        if (!ok) {   // keep the last candidate rather than spinning forever; report it
-            failed++;
-            const PathRec pr = paths[path];
-            const float2 c = pts[pr.c_off + point];
-            qx[a] = c.x; qy[a] = c.y;
-        }
-        const float u = (float)(draw(p.seed, p.epoch, env_g, a, 0, 2) >> 40) * (1.0f / 16777216.0f);
-        place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + a, path, point, u * p.cfg.max_speed, p.spawn_tab, a, p.fresh);
+        if (ln == a) { qx = w_x; qy = w_y; my_path = w_path; my_point = w_point; }
     }
-    if (full) p.buf.step_count[e] = 0; // road_traffic.py:875-877
+    if (ln < N && ((todo >> ln) & 1u)) {
+        const float u = (float)(draw(p.seed, p.epoch, env_g, ln, 0, 2) >> 40) * (1.0f / 16777216.0f);
+        place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + ln, my_path, my_point, u * p.cfg.max_speed, p.spawn_tab, ln,
+                    p.fresh);
+    }
     // collision masks of a touched env are cleared (road_traffic.py:907)
-    for (int a = 0; a < N; a++) {
-        p.buf.agent_flags[(size_t)e * N + a] = 0;
-        if (p.buf.collide_with) p.buf.collide_with[(size_t)e * N + a] = 0;
+    if (ln < N) {
+        p.buf.agent_flags[(size_t)e * N + ln] = 0;
+        if (p.buf.collide_with) p.buf.collide_with[(size_t)e * N + ln] = 0;
     }
-    if (full || !p.list_full_only) p.list[atomicAdd(p.count, 1)] = e;
-    if (failed && p.n_failed) atomicAdd(p.n_failed, failed);
+    if (ln == 0) {
+        if (full) p.buf.step_count[e] = 0; // road_traffic.py:875-877
+        if (full || !p.list_full_only) p.list[atomicAdd(p.count, 1)] = e;
+        if (failed && p.n_failed) atomicAdd(p.n_failed, failed);
+    }
+  }
 }
 
 // Generalised advantage estimation over a rollout, one thread per (env, agent), reverse scan over T.
