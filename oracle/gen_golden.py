@@ -77,7 +77,26 @@ CONFIGS = {
                                           extra=dict(is_testing_mode=True, rew_method="ttc_sparse"), max_steps=48),
     "cpm_entire_B4_N3_k1": dict(st="cpm_entire", B=4, N=3, T=40, mode="params", seed=7,
                                extra=dict(n_nearing_agents_observed=1)),
+    # non-default observation layouts (observation_provider_rt.py:594-925)
+    "obsvar_cpm_entire_B4_N5_centres": dict(st="cpm_entire", B=4, N=5, T=40, mode="params", seed=21,
+                                           extra=dict(is_observe_vertices=False, is_obs_steering=True,
+                                                      is_observe_ref_path_other_agents=True,
+                                                      is_observe_distance_to_agents=False,
+                                                      is_observe_distance_to_center_line=False)),
+    "obsvar_cpm_mixed_B4_N4_birdview_gentle": dict(st="cpm_mixed", B=4, N=4, T=60, mode="params", seed=22, gentle=True,
+                                                  extra=dict(is_ego_view=False)),
+    "obsvar_intersection_B4_N3_birdview_all": dict(st="intersection_1", B=4, N=3, T=40, mode="kwargs", seed=23,
+                                                  extra=dict(is_ego_view=False, is_observe_vertices=False,
+                                                             is_obs_steering=True,
+                                                             is_observe_ref_path_other_agents=True)),
+    "obsvar_roundabout_2_B4_N6_steer_refs": dict(st="roundabout_2", B=4, N=6, T=30, mode="params", seed=24,
+                                                extra=dict(is_obs_steering=True, is_observe_ref_path_other_agents=True,
+                                                           n_nearing_agents_observed=3)),
 }
+
+OBS_FLAGS = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
+             "is_observe_distance_to_agents", "is_observe_distance_to_center_line",
+             "is_observe_distance_to_boundaries", "is_partial_observation", "is_apply_mask", "is_obs_noise"]
 
 
 def stack_agents(agents, get):
@@ -133,6 +152,13 @@ def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
             acts = []
             for i in range(N):
                 o = last_obs[i]
+                if not sc.parameters.is_ego_view:
+                    # bird view: the observation holds global coordinates; take the same point from the world state
+                    d = ws.ref_paths_agent_related.short_term[:, i, 1] - agents[i].state.pos
+                    r = agents[i].state.rot[:, 0]
+                    o = torch.zeros(B, 5)
+                    o[:, 3] = d[:, 0] * torch.cos(r) + d[:, 1] * torch.sin(r)
+                    o[:, 4] = d[:, 1] * torch.cos(r) - d[:, 0] * torch.sin(r)
                 steer = torch.clamp(1.5 * torch.atan2(o[:, 4], o[:, 3]) + (torch.rand(B) * 2 - 1) * 0.03,
                                     -float(sc.max_steering), float(sc.max_steering))
                 acts.append(torch.stack([0.5 + 0.3 * torch.rand(B), steer], dim=1))
@@ -234,6 +260,9 @@ def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
         norm_distance_lanelet=float(nrm.distance_lanelet),
         is_testing_mode=bool(sc.parameters.is_testing_mode),
         max_ref_path_points=int(ws.params.max_ref_path_points), gentle=bool(gentle),
+        norm_pos_world_x=float(nrm.pos_world[0]), norm_pos_world_y=float(nrm.pos_world[1]),
+        norm_distance_agent=float(nrm.distance_agent),
+        **{f: bool(getattr(sc.parameters, f)) for f in OBS_FLAGS},
     )
     for k, v in cfg.items():
         out["cfg_" + k] = np.asarray(v)

@@ -54,7 +54,25 @@ _CFG_INTS = ["rew_exact_sparse", "rew_has_ttc", "rew_has_distance", "rew_has_spa
 
 class _Cfg(C.Structure):
     _fields_ = ([(n, C.c_float) for n in _CFG_FLOATS] + [(n, C.c_int) for n in _CFG_INTS] +
-                [("reward_reach_goal", C.c_float)])
+                [("reward_reach_goal", C.c_float), ("obs_flags", C.c_int), ("norm_pos_world", C.c_float * 2),
+                 ("norm_dist_agent", C.c_float)])
+
+
+# observation layout flags (ORC_OBS_* in sigmarl_oracle.c) keyed by the reference's parameter names and the value
+# that sets the bit (observation_provider_rt.py:594-925)
+OBS_FLAG_BITS = dict(is_ego_view=(1, False), is_observe_vertices=(2, False), is_obs_steering=(4, True),
+                     is_observe_ref_path_other_agents=(8, True), is_observe_distance_to_agents=(16, False),
+                     is_observe_distance_to_center_line=(32, False))
+
+
+def obs_flags_from(get):
+    """``get(name)`` -> value of the reference parameter (or None when unknown = default)."""
+    fl = 0
+    for name, (bit, when) in OBS_FLAG_BITS.items():
+        v = get(name)
+        if v is not None and bool(v) == when:
+            fl |= bit
+    return fl
 
 
 def f32(x):
@@ -193,6 +211,10 @@ def make_cfg(scenario_type, pmap, c):
     cfg.sample_interval = SAMPLE_INTERVAL
     cfg.testing_mode = int(bool(c.get("testing_mode", False)))
     cfg.reward_reach_goal = float(f32(c.get("reward_reach_goal", 100 / 100)))     # road_traffic.py:217-219
+    cfg.obs_flags = int(c.get("obs_flags", 0))
+    cfg.norm_pos_world[0] = float(x)                                               # road_traffic.py:593-595
+    cfg.norm_pos_world[1] = float(y)
+    cfg.norm_dist_agent = float(f32(AGENT_LENGTH * 10))                            # road_traffic.py:605-607
     return cfg
 
 
@@ -317,4 +339,5 @@ def config_from_golden(g):
                 norm_pos=float(g["cfg_norm_pos"]), norm_v=float(g["cfg_norm_v"]), norm_rot=float(g["cfg_norm_rot"]),
                 norm_dist=float(g["cfg_norm_distance_lanelet"]), rew_method=str(g["cfg_rew_method"]),
                 max_steps=int(g["cfg_max_steps"]), k_near=int(g["cfg_n_nearing_agents_observed"]),
-                testing_mode=bool(g["cfg_is_testing_mode"]))
+                testing_mode=bool(g["cfg_is_testing_mode"]),
+                obs_flags=obs_flags_from(lambda n: g["cfg_" + n] if ("cfg_" + n) in g.files else None))

@@ -52,7 +52,18 @@ typedef struct {
     int k_near, max_steps, is_cpm_entire, sample_interval;
     int testing_mode;        /* parameters.is_testing_mode          road_traffic.py:1050-1055, 1429-1447 */
     float reward_reach_goal; /* rewards.reach_goal                  road_traffic.py:217-219 */
+    /* observation layout (observation_provider_rt.py:594-925); 0 = the default flags */
+    int obs_flags;           /* ORC_OBS_* */
+    float norm_pos_world[2]; /* normalizers.pos_world (bird view)   road_traffic.py:593-595 */
+    float norm_dist_agent;   /* normalizers.distance_agent          road_traffic.py:605-607 */
 } orc_cfg;
+
+#define ORC_OBS_BIRD_VIEW 1       /* is_ego_view = False */
+#define ORC_OBS_CENTRES 2         /* is_observe_vertices = False: pos, rot, length, width instead of 4 vertices */
+#define ORC_OBS_STEERING 4        /* is_obs_steering */
+#define ORC_OBS_REF_OTHERS 8      /* is_observe_ref_path_other_agents */
+#define ORC_OBS_NO_DIST_AGENTS 16 /* is_observe_distance_to_agents = False */
+#define ORC_OBS_NO_DIST_CENTER 32 /* is_observe_distance_to_center_line = False */
 
 typedef struct {
     int B, N;
@@ -438,28 +449,45 @@ static void orc_take_snapshot(const orc_world *w, int b, orc_snap *s) {
     }
 }
 
-/* observation_provider_rt.py:594-925 get_observation, default flags (ego view, partial obs,
- * vertices, distance to agents/boundaries/centre line, no mask/noise/steering). D = 10 + 11 k. */
+/* observation_provider_rt.py:594-925 get_observation for the flag combinations of ORC_OBS_* (partial
+ * observation, distances to the boundaries, no mask / noise).  Default flags: D = 10 + 11 k.
+ * update_state (:345-588) runs at observation(agent 0) time: poses, velocities, steering and vertices of
+ * ALL agents are post-step values; short-term paths / centre / boundary distances are the snapshot `s`
+ * (fresh for agent 0, one step old for agents >= 1). */
 static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, float *obs) {
     int N = w->N;
     const orc_cfg *c = &w->cfg;
+    const int fl = c->obs_flags;
+    const int bird = fl & ORC_OBS_BIRD_VIEW;
     size_t g = AG(b, i);
     const float *pi = &w->pos[g * 2];
     float rot_i = w->rot[g];
     int o = 0;
-    /* own speed: past_vel[i,i,0] = |vel_i| * cos(wrap(0)) / v_norm  (:434-441, :866-869) */
-    {
+    if (bird) {
+        obs[o++] = pi[0] / c->norm_pos_world[0];          /* past_pos[b, i]  :545-552, :866-872 */
+        obs[o++] = pi[1] / c->norm_pos_world[1];
+        obs[o++] = orc_wrap(rot_i) / c->norm_rot;         /* past_rot[b, i]  :556-558, :873-879 */
+        obs[o++] = w->vel[g * 2] / c->norm_v;             /* past_vel[b, i]  :553-555 */
+        obs[o++] = w->vel[g * 2 + 1] / c->norm_v;
+    } else {
+        /* own speed: past_vel[i,i,0] = |vel_i| * cos(wrap(0)) / v_norm  (:434-441, :880-882) */
         float vabs = sqrtf(w->vel[g * 2] * w->vel[g * 2] + w->vel[g * 2 + 1] * w->vel[g * 2 + 1]);
         float rr = orc_wrap(rot_i - rot_i);
         obs[o++] = (vabs * cosf(rr)) / c->norm_v;
     }
-    for (int k = 0; k < ORC_NST; k++) {                   /* own short-term path :444-452 */
-        float loc[2];
-        orc_local(pi, rot_i, &s->short_term[i][2 * k], loc);
-        obs[o++] = loc[0] / c->norm_pos;
-        obs[o++] = loc[1] / c->norm_pos;
+    if (fl & ORC_OBS_STEERING) obs[o++] = orc_wrap(w->steering[g]) / c->norm_rot;    /* :354-358, :394, :883-887 */
+    for (int k = 0; k < ORC_NST; k++) {                   /* own short-term path :444-452 / :567-574 */
+        if (bird) {
+            obs[o++] = s->short_term[i][2 * k] / c->norm_pos_world[0];
+            obs[o++] = s->short_term[i][2 * k + 1] / c->norm_pos_world[1];
+        } else {
+            float loc[2];
+            orc_local(pi, rot_i, &s->short_term[i][2 * k], loc);
+            obs[o++] = loc[0] / c->norm_pos;
+            obs[o++] = loc[1] / c->norm_pos;
+        }
     }
-    obs[o++] = s->d_ref[i] / c->norm_dist;                /* :373-375 */
+    if (!(fl & ORC_OBS_NO_DIST_CENTER)) obs[o++] = s->d_ref[i] / c->norm_dist;       /* :373-375 */
     obs[o++] = s->min_l[i] / c->norm_dist;                /* :376-383 */
     obs[o++] = s->min_r[i] / c->norm_dist;
     /* torch.topk(distances.agents[:, i], k, largest=False) :627-636 */
@@ -471,21 +499,70 @@ static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, flo
             if (!used[j] && (bj < 0 || w->d_agents[g * N + j] < bd)) { bd = w->d_agents[g * N + j]; bj = j; }
         used[bj] = 1;
         size_t gj = AG(b, bj);
-        for (int v = 0; v < 4; v++) {                     /* vertices :484-492 */
-            float loc[2];
-            orc_local(pi, rot_i, &w->vertices[(gj * 5 + v) * 2], loc);
-            obs[o++] = loc[0] / c->norm_pos;
-            obs[o++] = loc[1] / c->norm_pos;
-        }
+        const float *pj = &w->pos[gj * 2];
         float rr = orc_wrap(w->rot[gj] - rot_i);          /* :427 */
-        float vabs = sqrtf(w->vel[gj * 2] * w->vel[gj * 2] + w->vel[gj * 2 + 1] * w->vel[gj * 2 + 1]);
-        obs[o++] = (vabs * cosf(rr)) / c->norm_v;         /* :432-441 */
-        obs[o++] = (vabs * sinf(rr)) / c->norm_v;
-        obs[o++] = bd / c->norm_dist;                     /* :369-371 */
+        if (fl & ORC_OBS_CENTRES) {                       /* :826-836: pos, rot, length, width */
+            if (bird) {
+                obs[o++] = pj[0] / c->norm_pos_world[0];
+                obs[o++] = pj[1] / c->norm_pos_world[1];
+                obs[o++] = orc_wrap(w->rot[gj]) / c->norm_rot;
+            } else {
+                float loc[2];
+                orc_local(pi, rot_i, pj, loc);            /* :418-424 */
+                obs[o++] = loc[0] / c->norm_pos;
+                obs[o++] = loc[1] / c->norm_pos;
+                obs[o++] = rr / c->norm_rot;
+            }
+            obs[o++] = (2.0f * c->half_length) / c->norm_dist_agent;  /* :359-371, :388-393; 2*fl(L/2) == fl(L) */
+            obs[o++] = (2.0f * c->half_width) / c->norm_dist_agent;
+        } else {
+            for (int v = 0; v < 4; v++) {                 /* vertices :484-492 / :559-566 */
+                const float *pv = &w->vertices[(gj * 5 + v) * 2];
+                if (bird) {
+                    obs[o++] = pv[0] / c->norm_pos_world[0];
+                    obs[o++] = pv[1] / c->norm_pos_world[1];
+                } else {
+                    float loc[2];
+                    orc_local(pi, rot_i, pv, loc);
+                    obs[o++] = loc[0] / c->norm_pos;
+                    obs[o++] = loc[1] / c->norm_pos;
+                }
+            }
+        }
+        if (bird) {
+            obs[o++] = w->vel[gj * 2] / c->norm_v;        /* :553-555 */
+            obs[o++] = w->vel[gj * 2 + 1] / c->norm_v;
+        } else {
+            float vabs = sqrtf(w->vel[gj * 2] * w->vel[gj * 2] + w->vel[gj * 2 + 1] * w->vel[gj * 2 + 1]);
+            obs[o++] = (vabs * cosf(rr)) / c->norm_v;     /* :432-441 */
+            obs[o++] = (vabs * sinf(rr)) / c->norm_v;
+        }
+        if (fl & ORC_OBS_STEERING) obs[o++] = orc_wrap(w->steering[gj]) / c->norm_rot;   /* :692-700 */
+        if (!(fl & ORC_OBS_NO_DIST_AGENTS)) obs[o++] = bd / c->norm_dist;                /* :369-371 */
+        if (fl & ORC_OBS_REF_OTHERS)                                                     /* :443-452, :716-724 */
+            for (int k = 0; k < ORC_NST; k++) {
+                if (bird) {
+                    obs[o++] = s->short_term[bj][2 * k] / c->norm_pos_world[0];
+                    obs[o++] = s->short_term[bj][2 * k + 1] / c->norm_pos_world[1];
+                } else {
+                    float loc[2];
+                    orc_local(pi, rot_i, &s->short_term[bj][2 * k], loc);
+                    obs[o++] = loc[0] / c->norm_pos;
+                    obs[o++] = loc[1] / c->norm_pos;
+                }
+            }
     }
 }
 
-int orc_obs_dim(const orc_world *w) { return 10 + 11 * w->cfg.k_near; }
+/* width of the observation for the configured flags */
+int orc_obs_dim(const orc_world *w) {
+    const int fl = w->cfg.obs_flags;
+    int own = ((fl & ORC_OBS_BIRD_VIEW) ? 5 : 1) + ((fl & ORC_OBS_STEERING) ? 1 : 0) + 2 * ORC_NST +
+              ((fl & ORC_OBS_NO_DIST_CENTER) ? 0 : 1) + 2;
+    int per = ((fl & ORC_OBS_CENTRES) ? 5 : 8) + 2 + ((fl & ORC_OBS_STEERING) ? 1 : 0) +
+              ((fl & ORC_OBS_NO_DIST_AGENTS) ? 0 : 1) + ((fl & ORC_OBS_REF_OTHERS) ? 2 * ORC_NST : 0);
+    return own + per * w->cfg.k_near;
+}
 
 /* ---------------------------------------------------------------- the step */
 
