@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 120
+#define SGB_VERSION 121
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -92,7 +92,26 @@ typedef struct {
     int32_t testing_mode;     /* parameters.is_testing_mode: sparse-only reward (:1050-1055), env done only at the
                                  time limit and colliding / leaving agents respawned one by one (:1429-1447),
                                  spawn range growing with the try count (world_state_rt_sim.py:254-261) */
+    uint32_t obs_flags;       /* SGB_OBS_*: observation layout, 0 = the reference's default flags
+                                 observation_provider_rt.py:594-925 */
+    float norm_pos_world_x, norm_pos_world_y; /* normalizers.pos_world (bird view)  road_traffic.py:593-595 */
+    float norm_dist_agent;    /* normalizers.distance_agent (lengths / widths)      road_traffic.py:605-607 */
 } sgb_config;
+
+/* Observation layout flags == the reference's Parameters of the same meaning (helper_common.py:60-118;
+ * observation_provider_rt.py:594-925).  Own part: [pos(2), rot] (bird view) | vel (1 ego, 2 bird) | [steering] |
+ * short-term path (6) | [distance to centre line] | min distance to left, right boundary.  Per observed
+ * neighbour: 4 vertices (8) or pos(2), rot, length, width | vel (2) | [steering] | [distance] | [its
+ * short-term path (6)].  Not offered (sgb_create returns SGB_ERR_UNSUPPORTED for unknown bits;
+ * the Python host layer refuses the parameters in EnvConfig.validate): is_partial_observation = False (the
+ * reference itself crashes there, observation_provider_rt.py:808), boundary points instead of distances,
+ * masks, observation noise. */
+#define SGB_OBS_BIRD_VIEW 1u       /* is_ego_view = False: global coordinates / pos_world                 */
+#define SGB_OBS_CENTRES 2u         /* is_observe_vertices = False: pos, rot, length, width of a neighbour  */
+#define SGB_OBS_STEERING 4u        /* is_obs_steering: own and neighbours' steering angle / (2 pi)         */
+#define SGB_OBS_REF_OTHERS 8u      /* is_observe_ref_path_other_agents                                     */
+#define SGB_OBS_NO_DIST_AGENTS 16u /* is_observe_distance_to_agents = False                                */
+#define SGB_OBS_NO_DIST_CENTER 32u /* is_observe_distance_to_center_line = False                           */
 
 /* Device buffers of one batch of B envs x N agents.  in = read, out = written, io = both. */
 typedef struct {
@@ -137,7 +156,8 @@ typedef struct sgb_ctx sgb_ctx;
 int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, const sgb_config* cfg);
 int sgb_destroy(sgb_ctx* ctx);
 
-/* Observation width D = 10 + 11*k_near (observation_provider_rt.py:594-925, default flags). */
+/* Observation width D for the configured layout: 10 + 11*k_near with the default flags
+ * (observation_provider_rt.py:594-925). */
 int sgb_obs_dim(const sgb_ctx* ctx);
 /* max_ref_path_points the reference would use for this map (road_traffic.py:505-530). */
 int sgb_max_ref_path_points(const sgb_ctx* ctx);

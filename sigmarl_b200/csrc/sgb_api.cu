@@ -29,7 +29,7 @@ struct sgb_ctx {
     int32_t num_sms = 0;
     int32_t max_smem_optin = 0;
     int64_t launches = 0;
-    size_t smem_configured[2][3] = {{0, 0, 0}, {0, 0, 0}};   // dynamic-smem opt-in done for <MODE, G> on this device
+    size_t smem_configured[4][3] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G> on this device
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // sgb_step_host: chunked copy/compute pipeline
     cudaEvent_t pipe_event[2] = {nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
@@ -236,7 +236,7 @@ int ensure_fresh(sgb_ctx* c, int64_t agents) {
     return SGB_OK;
 }
 
-template <int G, int MODE>
+template <int G, int MODE, int OV>
 int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int slots = kSlots;
     const int envs_per_warp = 32 / (p.N * G);
@@ -249,17 +249,24 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
         return SGB_ERR_MAP;
     }
     // the opt-in is per (kernel, device): remember it in the context, which is bound to one device
-    size_t& configured = ctx->smem_configured[MODE][G == 4 ? 0 : (G == 2 ? 1 : 2)];
+    size_t& configured = ctx->smem_configured[MODE + 2 * OV][G == 4 ? 0 : (G == 2 ? 1 : 2)];
     if (configured < smem) {
-        CK(cudaFuncSetAttribute(env_step_kernel<G, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(env_step_kernel<G, MODE, OV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int warps = cta_threads(G) / 32;
     const int grid = std::min((n_wt + warps - 1) / warps, ctx->num_sms);
-    env_step_kernel<G, MODE><<<grid, cta_threads(G), smem, st>>>(p);
+    env_step_kernel<G, MODE, OV><<<grid, cta_threads(G), smem, st>>>(p);
     ctx->launches++;
     CK(cudaGetLastError());
     return SGB_OK;
+}
+
+template <int MODE, int OV>
+int launch_env_group(sgb_ctx* ctx, Params& p, cudaStream_t st, int g) {
+    if (g == 4) return launch_env_kernel<4, MODE, OV>(ctx, p, st);
+    if (g == 2) return launch_env_kernel<2, MODE, OV>(ctx, p, st);
+    return launch_env_kernel<1, MODE, OV>(ctx, p, st);
 }
 
 int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, const int32_t* env_list,
@@ -273,7 +280,7 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.blob = ctx->d_blob;
     p.env_list = env_list;
     p.env_count = env_count;
-    p.B = B; p.N = N; p.D = 10 + 11 * p.cfg.k_near;
+    p.B = B; p.N = N; p.D = obs_dim_of(p.cfg.obs_flags, p.cfg.k_near);
     p.blob_bytes = ctx->blob_bytes;
     p.mode = mode;
     p.write_obs = write_obs;
@@ -283,14 +290,9 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.r_v = 1.0f / ctx->cfg.norm_v;
     p.r_dist = 1.0f / ctx->cfg.norm_dist;
     const int g = pick_group(N);
-    if (mode == 0) {
-        if (g == 4) return launch_env_kernel<4, 0>(ctx, p, st);
-        if (g == 2) return launch_env_kernel<2, 0>(ctx, p, st);
-        return launch_env_kernel<1, 0>(ctx, p, st);
-    }
-    if (g == 4) return launch_env_kernel<4, 1>(ctx, p, st);
-    if (g == 2) return launch_env_kernel<2, 1>(ctx, p, st);
-    return launch_env_kernel<1, 1>(ctx, p, st);
+    // the default observation layout runs the hard-wired (tuned) writer, any other one the flag-driven writer
+    if (p.cfg.obs_flags == 0) return mode == 0 ? launch_env_group<0, 0>(ctx, p, st, g) : launch_env_group<1, 0>(ctx, p, st, g);
+    return mode == 0 ? launch_env_group<0, 1>(ctx, p, st, g) : launch_env_group<1, 1>(ctx, p, st, g);
 }
 
 // Spawn table.  A device reset puts an agent exactly on a centre-line point with the path's yaw, so everything
@@ -363,6 +365,14 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
         return SGB_ERR_NO_DEVICE;
     }
     if (cfg->k_near < 0 || cfg->k_near >= SGB_MAX_AGENTS || cfg->max_steps < 2 || !(cfg->dt > 0.0f)) return SGB_ERR_ARG;
+    constexpr uint32_t kObsKnown = SGB_OBS_BIRD_VIEW | SGB_OBS_CENTRES | SGB_OBS_STEERING | SGB_OBS_REF_OTHERS |
+                                   SGB_OBS_NO_DIST_AGENTS | SGB_OBS_NO_DIST_CENTER;
+    if (cfg->obs_flags & ~kObsKnown) {
+        snprintf(g_err, sizeof g_err, "obs_flags 0x%x: unknown observation layout bits", cfg->obs_flags);
+        return SGB_ERR_UNSUPPORTED;
+    }
+    if ((cfg->obs_flags & SGB_OBS_BIRD_VIEW) && !(cfg->norm_pos_world_x > 0.0f && cfg->norm_pos_world_y > 0.0f)) return SGB_ERR_ARG;
+    if ((cfg->obs_flags & SGB_OBS_CENTRES) && !(cfg->norm_dist_agent > 0.0f)) return SGB_ERR_ARG;
     Packed pk;
     int rc = pack_map(map, pk);
     if (rc != SGB_OK) return rc;
@@ -411,7 +421,7 @@ extern "C" int sgb_destroy(sgb_ctx* c) {
     return SGB_OK;
 }
 
-extern "C" int sgb_obs_dim(const sgb_ctx* c) { return c ? 10 + 11 * c->cfg.k_near : SGB_ERR_ARG; }
+extern "C" int sgb_obs_dim(const sgb_ctx* c) { return c ? obs_dim_of(c->cfg.obs_flags, c->cfg.k_near) : SGB_ERR_ARG; }
 extern "C" int sgb_max_ref_path_points(const sgb_ctx* c) { return c ? c->max_center + kExt + 2 : SGB_ERR_ARG; }
 extern "C" int64_t sgb_launch_count(const sgb_ctx* c) { return c ? c->launches : 0; }
 extern "C" int64_t sgb_map_bytes(const sgb_ctx* c) { return c ? c->blob_bytes : 0; }
@@ -520,7 +530,7 @@ extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
     int rc = check_buffers(buf, 1);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int D = 10 + 11 * c->cfg.k_near;
+    const int D = obs_dim_of(c->cfg.obs_flags, c->cfg.k_near);
     if (!c->pipe_ready) {
         for (int i = 0; i < 2; i++) {
             CK(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));

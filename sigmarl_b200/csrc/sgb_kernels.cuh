@@ -581,13 +581,32 @@ __device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int 
     }
 }
 
+// helper_scenario.py:1276-1289 angle_eliminate_two_pi (fp32: the python scalars are cast to the tensor's dtype)
+__device__ __forceinline__ float wrap_pi(float a) {
+    const float pi_f = 3.14159274101257324f, two_pi = 6.28318548202514648f;
+    float m = pymod(a, two_pi);
+    if (m > pi_f) m -= two_pi;
+    return m;
+}
+
+// Observation width for a layout (observation_provider_rt.py:594-925; see SGB_OBS_* in the header)
+__host__ __device__ inline int obs_dim_of(uint32_t fl, int k_near) {
+    const int own = ((fl & SGB_OBS_BIRD_VIEW) ? 5 : 1) + ((fl & SGB_OBS_STEERING) ? 1 : 0) + 2 * SGB_N_SHORT_TERM +
+                    ((fl & SGB_OBS_NO_DIST_CENTER) ? 0 : 1) + 2;
+    const int per = ((fl & SGB_OBS_CENTRES) ? 5 : 8) + 2 + ((fl & SGB_OBS_STEERING) ? 1 : 0) +
+                    ((fl & SGB_OBS_NO_DIST_AGENTS) ? 0 : 1) + ((fl & SGB_OBS_REF_OTHERS) ? 2 * SGB_N_SHORT_TERM : 0);
+    return own + per * k_near;
+}
+
 // ---- the fused kernel -------------------------------------------------------------------------------------  @region kernel prologue
 // Work decomposition: a WARP owns whole envs.  With G lanes per agent an env takes N*G lanes, a warp holds
 // EW = 32 / (N*G) envs (N = 8, G = 4: exactly one env per warp).  After the CTA-wide map staging there is no
 // CTA barrier any more: every warp runs phases A-D of its envs on its own (only __syncwarp), so warps drift
 // apart and overlap their ALU / MUFU / shared-memory phases.
 // MODE 0 = step, MODE 1 = refresh (rebuild carry / observation from the current pose; no dynamics, no reward).
-template <int G, int MODE>
+// OV 0 = the reference's default observation layout (hard-wired, the tuned path), OV 1 = layout assembled from
+// cfg.obs_flags (write_obs_general); everything else is the same code.
+template <int G, int MODE, int OV>
 __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) unsigned long long mbar;
@@ -963,7 +982,91 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 if (!step_mode) { o_dref = d_ref_n; o_mL = fminf(dLc, m4L); o_mR = fminf(dRc, m4R); o_idx = idx_n; }
                 else if (i == 0) { o_dref = d_ref_n; o_mL = fminf(dLc, c_mL); o_mR = fminf(dRc, c_mR); o_idx = idx_n; }
                 else { o_dref = c_dref; o_mL = c_mL; o_mR = c_mR; o_idx = c_idx; }
-                if (write_obs) {
+                if (OV != 0 && write_obs) {
+                    // ---- general layout (cfg.obs_flags): the last lane of the group writes the agent's own part, the
+                    //      observed neighbours are dealt over the lanes.  What update_state snapshots at
+                    //      observation(agent 0) time (observation_provider_rt.py:345-588): poses, velocities, steering
+                    //      and vertices of ALL agents are post-step; the short-term path of agent j is fresh for
+                    //      j == 0 and one step old for j >= 1 (all fresh after a reset).  Heading and steering are
+                    //      read back from pose / aux (stored in phase A by this phase-aligned group; barrier since).
+                    const uint32_t ofl = cfg.obs_flags;
+                    const bool bird = (ofl & SGB_OBS_BIRD_VIEW) != 0;
+                    const size_t g0 = g - i;                     // agent 0 of this env
+                    const float psi_i = p.buf.pose[4 * g + 2];
+                    const float nwx = cfg.norm_pos_world_x, nwy = cfg.norm_pos_world_y;
+                    // a global point as the observation holds it: ego frame / norm_pos, or global / pos_world
+                    auto put_point = [&](float* dst, float qx, float qy) {
+                        if (bird) { dst[0] = qx / nwx; dst[1] = qy / nwy; }
+                        else {
+                            const float dx = qx - pix, dy = qy - piy;
+                            dst[0] = (dx * cs + dy * sn) * r_pos;
+                            dst[1] = (dy * cs - dx * sn) * r_pos;
+                        }
+                    };
+                    if (lane == G - 1) {
+                        float* q = o;
+                        if (bird) {
+                            q[0] = pix / nwx; q[1] = piy / nwy;
+                            q[2] = wrap_pi(psi_i) / cfg.norm_rot;
+                            q[3] = ts.vx[sl] * r_v; q[4] = ts.vy[sl] * r_v;
+                            q += 5;
+                        } else {
+                            *q++ = ts.vabs[sl] * r_v;
+                        }
+                        if (ofl & SGB_OBS_STEERING) *q++ = wrap_pi(p.buf.aux[4 * g]) / cfg.norm_rot;
+                        float2 st[3];
+                        short_term(cpts, pr_nc, pr_loop, o_idx, st);
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { put_point(q, st[k].x, st[k].y); q += 2; }
+                        if (!(ofl & SGB_OBS_NO_DIST_CENTER)) *q++ = o_dref * r_dist;
+                        q[0] = o_mL * r_dist;
+                        q[1] = o_mR * r_dist;
+                    }
+                    const int own = obs_dim_of(ofl, 0), per = obs_dim_of(ofl, 1) - own;
+                    for (int kk = lane; kk < k_near; kk += G) {
+                        int bj;
+                        float bd;
+                        if (kk == 0) { bj = nb_j[0]; bd = nb_d[0]; }
+                        else if (kk == 1) { bj = nb_j[1]; bd = nb_d[1]; }
+                        else bj = kth_nearest(ts.dij + sl * N, N, kk, &bd);
+                        const int sj = base + bj;
+                        const size_t gj = g0 + bj;
+                        float* q = o + own + per * kk;
+                        const float psi_j = p.buf.pose[4 * gj + 2];
+                        if (ofl & SGB_OBS_CENTRES) {
+                            put_point(q, ts.px[sj], ts.py[sj]);
+                            q[2] = (bird ? wrap_pi(psi_j) : wrap_pi(psi_j - psi_i)) / cfg.norm_rot;
+                            q[3] = (2.0f * cfg.half_length) / cfg.norm_dist_agent;
+                            q[4] = (2.0f * cfg.half_width) / cfg.norm_dist_agent;
+                            q += 5;
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < 4; v++) put_point(q + 2 * v, ts.vtx[v * AS + sj], ts.vtx[(4 + v) * AS + sj]);
+                            q += 8;
+                        }
+                        if (bird) { q[0] = ts.vx[sj] * r_v; q[1] = ts.vy[sj] * r_v; }
+                        else {
+                            const float cj = ts.cs[sj], sj_ = ts.sn[sj];
+                            q[0] = (ts.vabs[sj] * (cj * cs + sj_ * sn)) * r_v;
+                            q[1] = (ts.vabs[sj] * (sj_ * cs - cj * sn)) * r_v;
+                        }
+                        q += 2;
+                        if (ofl & SGB_OBS_STEERING) *q++ = wrap_pi(p.buf.aux[4 * gj]) / cfg.norm_rot;
+                        if (!(ofl & SGB_OBS_NO_DIST_AGENTS)) *q++ = bd * r_dist;
+                        if (ofl & SGB_OBS_REF_OTHERS) {
+                            int pj = ts.path[sj];
+                            pj = (pj < 0 || pj >= hdr->n_paths) ? 0 : pj;
+                            const PathRec* prj = paths + pj;
+                            const int idx_j = __float_as_int((step_mode && bj != 0) ? ts.car[3 * AS + sj] : ts.sc[1 * AS + sj]);
+                            float2 st[3];
+                            short_term(pts + prj->c_off, prj->n_c, prj->is_loop != 0, idx_j, st);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) { put_point(q, st[k].x, st[k].y); q += 2; }
+                        }
+                        if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
+                    }
+                }
+                if (OV == 0 && write_obs) {
                     // ---- point transforms into the ego frame, split evenly over the lanes: 3 short-term points
                     //      of the agent itself + 4 vertices of each observed neighbour (rotation form of
                     //      helper_scenario.py:1241-1273, cos/sin of the heading come from phase A; normalisers

@@ -12,6 +12,8 @@ _LIB_NAME = "libsigmarl_b200.so"
 SGB_MAX_AGENTS = 32
 SGB_FLAG_COLLIDE_AGENT, SGB_FLAG_COLLIDE_LANE, SGB_FLAG_ENTRY, SGB_FLAG_EXIT = 1, 2, 4, 8
 SGB_REW_EXACT_SPARSE, SGB_REW_TTC, SGB_REW_DISTANCE, SGB_REW_SPARSE = 1, 2, 4, 8
+(SGB_OBS_BIRD_VIEW, SGB_OBS_CENTRES, SGB_OBS_STEERING, SGB_OBS_REF_OTHERS, SGB_OBS_NO_DIST_AGENTS,
+ SGB_OBS_NO_DIST_CENTER) = 1, 2, 4, 8, 16, 32
 
 # every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",
@@ -43,7 +45,8 @@ class Config(C.Structure):
     _fields_ = ([(n, C.c_float) for n in CONFIG_FLOATS] +
                 [("rew_flags", C.c_uint32), ("k_near", C.c_int32), ("max_steps", C.c_int32),
                  ("respawn_on_exit", C.c_int32), ("exhaustive", C.c_int32), ("reward_reach_goal", C.c_float),
-                 ("testing_mode", C.c_int32)])
+                 ("testing_mode", C.c_int32), ("obs_flags", C.c_uint32), ("norm_pos_world_x", C.c_float),
+                 ("norm_pos_world_y", C.c_float), ("norm_dist_agent", C.c_float)])
 
 
 BUFFER_FIELDS = ["pose", "aux", "path_id", "carry", "action", "step_count", "obs", "reward", "done",

@@ -17,8 +17,18 @@ TOL = 1e-5
 UR = np.asarray([1.0, 31 * np.pi / 180], np.float32)
 
 
+OBS_FLAG_NAMES = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
+                  "is_observe_distance_to_agents", "is_observe_distance_to_center_line"]
+
+
+def _obs_flags_of_golden(g):
+    """Observation-layout parameters the reference run was configured with (older fixtures: the defaults)."""
+    return {n: bool(g["cfg_" + n]) for n in OBS_FLAG_NAMES if ("cfg_" + n) in g.files}
+
+
 def _env_from_golden(g, B=None, **over):
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    over = {**_obs_flags_of_golden(g), **over}
     cfg = EnvConfig(
         scenario_type=str(g["cfg_scenario_type"]), n_agents=int(g["cfg_N"]), mode=str(g["cfg_mode"]),
         dt=float(g["cfg_dt"]), max_steps=int(g["cfg_max_steps"]), rew_method=str(g["cfg_rew_method"]),
@@ -136,7 +146,8 @@ def test_cuda_reset_obs_matches_reference(path):
 def _oracle_for(env, O, rew_method, mode):
     return O.OracleWorld(env.config.scenario_type, env.B, env.N, mode=mode, rew_method=rew_method,
                          n_nearing_agents_observed=env.config.n_nearing_agents_observed,
-                         max_steps=env.config.max_steps)
+                         max_steps=env.config.max_steps,
+                         obs_flags=O.obs_flags_from(lambda n: getattr(env.config, n)))
 
 
 @pytest.mark.parametrize("scenario,N,rew,mode,B", [
@@ -153,14 +164,40 @@ def _oracle_for(env, O, rew_method, mode):
 ])
 def test_cuda_matches_oracle_free_running_with_device_resets(oracle_mod, scenario, N, rew, mode, B):
     """GPU drives (device resets included); every step the oracle is teacher-forced from the GPU's pre-step state."""
+    k_obs = 5 if (scenario, rew) == ("cpm_entire", "ttc") else 2   # 5: neighbours beyond the two kept in registers
+    env = _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs)
+    assert env.D == 10 + 11 * min(k_obs, N - 1)
+
+
+@pytest.mark.parametrize("scenario,N,rew,mode,B,k_obs,flags", [
+    # every layout flag at once, ego view; G = 4 / 2 / 1 instantiations of the flag-driven writer
+    ("cpm_entire", 8, "distance", "params", 512, 2,
+     dict(is_observe_vertices=False, is_obs_steering=True, is_observe_ref_path_other_agents=True,
+          is_observe_distance_to_agents=False, is_observe_distance_to_center_line=False)),
+    ("on_ramp_2_multilane", 12, "ttc", "kwargs", 256, 3, dict(is_obs_steering=True, is_observe_ref_path_other_agents=True)),
+    ("cpm_entire", 18, "distance_sparse", "params", 64, 4, dict(is_observe_vertices=False, is_obs_steering=True)),
+    # bird view: default fields, and everything switched
+    ("cpm_entire", 8, "ttc_sparse", "params", 512, 2, dict(is_ego_view=False)),
+    ("cpm_mixed", 6, "distance", "params", 256, 5,
+     dict(is_ego_view=False, is_observe_vertices=False, is_obs_steering=True, is_observe_ref_path_other_agents=True,
+          is_observe_distance_to_agents=False, is_observe_distance_to_center_line=False)),
+    ("intersection_1", 3, "distance", "kwargs", 256, 2, dict(is_ego_view=False, is_observe_ref_path_other_agents=True)),
+])
+def test_cuda_observation_layouts_match_oracle(oracle_mod, scenario, N, rew, mode, B, k_obs, flags):
+    """Non-default observation layouts (observation_provider_rt.py:594-925; SGB_OBS_*), GPU vs the oracle that is
+    pinned on the reference's own outputs for these layouts (tests/golden/obsvar_*.npz)."""
+    env = _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, **flags)
+    assert env.D == env.config.obs_dim(N) and env.config.obs_flags() != 0
+
+
+def _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, **flags):
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     O = oracle_mod
-    k_obs = 5 if (scenario, rew) == ("cpm_entire", "ttc") else 2   # 5: neighbours beyond the two kept in registers
     env = RoadTrafficEnv(EnvConfig(scenario_type=scenario, n_agents=N, mode=mode, rew_method=rew,
-                                   n_nearing_agents_observed=k_obs),
+                                   n_nearing_agents_observed=k_obs, **flags),
                          num_envs=B, device="cuda:0", seed=7, debug=True)
-    assert env.D == 10 + 11 * min(k_obs, N - 1)
     w = _oracle_for(env, O, rew, mode)
+    assert env.D == w.D
     env.reset()
     rng = np.random.default_rng(0)
     n_done = n_lane = n_a2a = n_ties = 0
@@ -195,7 +232,8 @@ def test_cuda_matches_oracle_free_running_with_device_resets(oracle_mod, scenari
             assert np.all(np.abs(dbg[..., 0][tie] - w.d_ref[tie]) <= 1e-6), f"{ctx} idx_ref differs without a tie"
             assert np.abs(gi - w.idx_ref)[tie].max() == 1 and tie.sum() <= 4, f"{ctx} too many / non-adjacent ties"
             n_ties += int(tie.sum())
-        ok_rows = ~tie
+        # (a layout that shows other agents' reference paths exposes a neighbour's tie as well: skip the whole env)
+        ok_rows = ~(tie | (tie.any(-1, keepdims=True) & env.config.is_observe_ref_path_other_agents))
         _close("obs", obs.cpu().numpy()[ok_rows], o_obs[ok_rows], ctx)
         _close("reward", rew_.cpu(), o_rew, ctx)
         fl = env.agent_flags.cpu().numpy()
@@ -208,6 +246,7 @@ def test_cuda_matches_oracle_free_running_with_device_resets(oracle_mod, scenari
         env.reset_done()
     assert n_done > 0 and n_lane > 0
     assert n_ties <= 1e-4 * B * N * 30 + 2
+    return env
 
 
 def test_pruned_equals_exhaustive_bitwise_at_c2_size():
@@ -392,7 +431,17 @@ def test_library_refuses_bad_arguments():
     from sigmarl_b200 import lib
     L = lib.load_library()
     assert L.sgb_step(None, 1, 1, None, None) == -1
-    assert L.sgb_version() == 120
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "sigmarl_b200.h")).read()
+    assert f"#define SGB_VERSION {L.sgb_version()}\n" in hdr
+    # an observation-layout bit the library does not know is refused at context creation (SGB_ERR_UNSUPPORTED)
+    from sigmarl_b200 import EnvConfig
+    from sigmarl_b200.maps import MapLibrary
+    m = MapLibrary("intersection_1")
+    cfg = EnvConfig(scenario_type="intersection_1", n_agents=2).lower(m)
+    cfg.obs_flags = 1 << 9
+    ctx = C.c_void_p()
+    desc = m.desc()
+    assert L.sgb_create(C.byref(ctx), 0, C.byref(desc), C.byref(cfg)) == -5 and not ctx.value
 
 
 @pytest.mark.parametrize("name", ["c1_intersection_B4_N2", "cpm_entire_B8_N8_distance", "cpm_mixed_B8_N4_gentle"])
@@ -517,7 +566,7 @@ def _facade_from_golden(g):
         ttc_low=float(g["cfg_ttc_low"]), ttc_high=float(g["cfg_ttc_high"]),
         penalty_near_boundary=float(g["cfg_penalty_near_boundary"]),
         penalty_near_other_agents=float(g["cfg_penalty_near_other_agents"]),
-        is_testing_mode=bool(g["cfg_is_testing_mode"]))
+        is_testing_mode=bool(g["cfg_is_testing_mode"]), **_obs_flags_of_golden(g))
     if str(g["cfg_mode"]) == "params":     # mappo_cavs.py:168-169: scenario.parameters = parameters; make_world(...)
         p = _Params()
         for k, v in kw.items():
