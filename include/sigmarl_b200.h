@@ -100,18 +100,21 @@ typedef struct {
 
 /* Observation layout flags == the reference's Parameters of the same meaning (helper_common.py:60-118;
  * observation_provider_rt.py:594-925).  Own part: [pos(2), rot] (bird view) | vel (1 ego, 2 bird) | [steering] |
- * short-term path (6) | [distance to centre line] | min distance to left, right boundary.  Per observed
+ * short-term path (6) | [distance to centre line] | min distance to left, right boundary (or 5 + 5 boundary points).  Per observed
  * neighbour: 4 vertices (8) or pos(2), rot, length, width | vel (2) | [steering] | [distance] | [its
  * short-term path (6)].  Not offered (sgb_create returns SGB_ERR_UNSUPPORTED for unknown bits;
  * the Python host layer refuses the parameters in EnvConfig.validate): is_partial_observation = False (the
- * reference itself crashes there, observation_provider_rt.py:808), boundary points instead of distances,
- * masks, observation noise. */
+ * reference itself crashes there, observation_provider_rt.py:808), masks, observation noise. */
 #define SGB_OBS_BIRD_VIEW 1u       /* is_ego_view = False: global coordinates / pos_world                 */
 #define SGB_OBS_CENTRES 2u         /* is_observe_vertices = False: pos, rot, length, width of a neighbour  */
 #define SGB_OBS_STEERING 4u        /* is_obs_steering: own and neighbours' steering angle / (2 pi)         */
 #define SGB_OBS_REF_OTHERS 8u      /* is_observe_ref_path_other_agents                                     */
 #define SGB_OBS_NO_DIST_AGENTS 16u /* is_observe_distance_to_agents = False                                */
 #define SGB_OBS_NO_DIST_CENTER 32u /* is_observe_distance_to_center_line = False                           */
+#define SGB_OBS_BOUNDARY_POINTS 64u /* is_observe_distance_to_boundaries = False: 5 points of each boundary
+                                      around the closest one instead of the two distances.  carry.w then keeps, in
+                                      bit 30, whether the pose was written by a reset (the reference samples the
+                                      points with shift +1 there and -2 in a step, world_state_rt.py:531-576, :686-725) */
 
 /* Device buffers of one batch of B envs x N agents.  in = read, out = written, io = both. */
 typedef struct {

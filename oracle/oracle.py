@@ -62,7 +62,7 @@ class _Cfg(C.Structure):
 # that sets the bit (observation_provider_rt.py:594-925)
 OBS_FLAG_BITS = dict(is_ego_view=(1, False), is_observe_vertices=(2, False), is_obs_steering=(4, True),
                      is_observe_ref_path_other_agents=(8, True), is_observe_distance_to_agents=(16, False),
-                     is_observe_distance_to_center_line=(32, False))
+                     is_observe_distance_to_center_line=(32, False), is_observe_distance_to_boundaries=(64, False))
 
 
 def obs_flags_from(get):
@@ -249,7 +249,8 @@ _FIELDS = dict(pos=(np.float32, 2), rot=(np.float32, 1), speed=(np.float32, 1), 
                vel=(np.float32, 2), sideslip=(np.float32, 1), path_id=(np.int32, 1), vertices=(np.float32, 10),
                d_ref=(np.float32, 1), d_left=(np.float32, 5), d_right=(np.float32, 5), d_bound=(np.float32, 1),
                idx_ref=(np.int32, 1), short_term=(np.float32, 6), prev_pos=(np.float32, 2),
-               col_lane=(np.uint8, 1), col_entry=(np.uint8, 1), col_exit=(np.uint8, 1))
+               col_lane=(np.uint8, 1), col_entry=(np.uint8, 1), col_exit=(np.uint8, 1),
+               idx_left=(np.int32, 1), idx_right=(np.int32, 1), near_fresh=(np.uint8, 1))
 
 
 class OracleWorld:

@@ -64,6 +64,8 @@ typedef struct {
 #define ORC_OBS_REF_OTHERS 8      /* is_observe_ref_path_other_agents */
 #define ORC_OBS_NO_DIST_AGENTS 16 /* is_observe_distance_to_agents = False */
 #define ORC_OBS_NO_DIST_CENTER 32 /* is_observe_distance_to_center_line = False */
+#define ORC_OBS_BOUNDARY_POINTS 64 /* is_observe_distance_to_boundaries = False: 5 points of each boundary */
+#define ORC_NNB 5                  /* n_points_nearing_boundary (road_traffic.py:296-298) */
 
 typedef struct {
     int B, N;
@@ -77,6 +79,10 @@ typedef struct {
     float *d_agents;                                      /* [B][N][N] */
     float *d_ref, *d_left, *d_right, *d_bound;            /* [B][N], [B][N][5] */
     int *idx_ref;
+    int *idx_left, *idx_right;                            /* distances.closest_point_on_left_b / right_b [B][N] */
+    uint8_t *near_fresh;                                  /* [B][N] 1: nearing boundary points last written by a
+                                                             reset (n_points_shift = +1, world_state_rt.py:531-576),
+                                                             0: by a step (shift = -2, :686-725) */
     float *short_term;                                    /* [B][N][3][2] */
     float *prev_pos;                                      /* state_buffer latest */
     uint8_t *col_agents, *col_lane, *col_entry, *col_exit;
@@ -191,6 +197,21 @@ static void orc_short_term(const orc_world *w, int path, int idx, float *out) {
     }
 }
 
+/* world_state_rt.py:689-725: nearing boundary points = get_short_term_reference_path on the PADDED boundary
+ * array [P][2] with sample_interval 1, n_points_shift -2 and — as the reference passes it — the CENTRE line's
+ * point count for the loop wrap.  Index -1 is python's "last element" (tail padding = last boundary point). */
+static void orc_nearing_points(const orc_world *w, int path, const float *poly, int idx, int shift, float *out) {
+    const orc_map *m = &w->map;
+    int n = m->n_center[path];
+    for (int k = 0; k < ORC_NNB; k++) {
+        int fi = k + idx + shift;
+        if (m->is_loop[path] && fi >= n - 1) fi = (fi + 1) % n;
+        if (fi < 0) fi += m->P;
+        out[2 * k] = poly[2 * fi];
+        out[2 * k + 1] = poly[2 * fi + 1];
+    }
+}
+
 /* ---------------------------------------------------------------- world-state updates */
 
 #define AG(b, a) ((size_t)(b) * N + (a))
@@ -219,8 +240,8 @@ static void orc_update_distances(orc_world *w, int b, int i) {
     const float *rig = m->right + (size_t)path * m->P * 2;
     int dummy;
     w->d_ref[g] = orc_perp(&w->pos[g * 2], cen, m->P, m->n_center[path], &w->idx_ref[g]);
-    w->d_left[g * 5] = orc_perp(&w->pos[g * 2], lef, m->P, m->n_left[path], &dummy) - w->cfg.half_width;
-    w->d_right[g * 5] = orc_perp(&w->pos[g * 2], rig, m->P, m->n_right[path], &dummy) - w->cfg.half_width;
+    w->d_left[g * 5] = orc_perp(&w->pos[g * 2], lef, m->P, m->n_left[path], &w->idx_left[g]) - w->cfg.half_width;
+    w->d_right[g * 5] = orc_perp(&w->pos[g * 2], rig, m->P, m->n_right[path], &w->idx_right[g]) - w->cfg.half_width;
     for (int c = 0; c < 4; c++) {
         const float *v = &w->vertices[(g * 5 + c) * 2];
         w->d_left[g * 5 + c + 1] = orc_perp(v, lef, m->P, m->n_left[path], &dummy);
@@ -278,6 +299,7 @@ static void orc_refresh_agent(orc_world *w, int b, int i) {
     orc_rect(&w->cfg, &w->pos[g * 2], w->rot[g], &w->vertices[g * 10]);
     orc_update_distances(w, b, i); /* same 11 scans, but vertices are fresh here (:470-476) */
     orc_short_term(w, w->path_id[g], w->idx_ref[g], &w->short_term[g * 6]);
+    w->near_fresh[g] = 1;          /* :531-576 */
 }
 
 /* road_traffic.py:897-923: after (re)placing agents of env b (all agents, or one respawned agent). */
@@ -378,6 +400,7 @@ static float orc_reward(orc_world *w, int b, int i) {
     /* update_state_before_rewarding world_state_rt_sim.py:432-448 */
     if (i == 0) orc_mutual(w, b);
     orc_update_distances(w, b, i);
+    w->near_fresh[g] = 0;   /* update_ref_paths_agent_related (world_state_rt_sim.py:454) rewrites the nearing points */
     if (i == 0) {
         orc_reset_collisions(w, b);
         for (int a = 0; a < N; a++) orc_rect(c, &w->pos[AG(b, a) * 2], w->rot[AG(b, a)], &w->vertices[AG(b, a) * 10]);
@@ -432,6 +455,7 @@ static float orc_reward(orc_world *w, int b, int i) {
 typedef struct {
     float short_term[ORC_MAX_AGENTS][6];
     float d_ref[ORC_MAX_AGENTS], min_l[ORC_MAX_AGENTS], min_r[ORC_MAX_AGENTS];
+    float near_l[ORC_MAX_AGENTS][2 * ORC_NNB], near_r[ORC_MAX_AGENTS][2 * ORC_NNB];
 } orc_snap;
 
 static void orc_take_snapshot(const orc_world *w, int b, orc_snap *s) {
@@ -446,6 +470,14 @@ static void orc_take_snapshot(const orc_world *w, int b, orc_snap *s) {
             if (w->d_right[g * 5 + c] < mr) mr = w->d_right[g * 5 + c];
         }
         s->min_l[j] = ml; s->min_r[j] = mr;
+        if (w->cfg.obs_flags & ORC_OBS_BOUNDARY_POINTS) {
+            /* ref_paths_agent_related.nearing_points_*[:, j]: refreshed together with short_term[:, j]
+             * (world_state_rt.py:668-725), i.e. from the closest boundary index as it stands now */
+            int path = w->path_id[g];
+            int shift = w->near_fresh[g] ? 1 : -2;
+            orc_nearing_points(w, path, w->map.left + (size_t)path * w->map.P * 2, w->idx_left[g], shift, s->near_l[j]);
+            orc_nearing_points(w, path, w->map.right + (size_t)path * w->map.P * 2, w->idx_right[g], shift, s->near_r[j]);
+        }
     }
 }
 
@@ -488,8 +520,24 @@ static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, flo
         }
     }
     if (!(fl & ORC_OBS_NO_DIST_CENTER)) obs[o++] = s->d_ref[i] / c->norm_dist;       /* :373-375 */
-    obs[o++] = s->min_l[i] / c->norm_dist;                /* :376-383 */
-    obs[o++] = s->min_r[i] / c->norm_dist;
+    if (fl & ORC_OBS_BOUNDARY_POINTS) {                   /* :453-470 / :575-588, :903-925 */
+        for (int side = 0; side < 2; side++)
+            for (int k = 0; k < ORC_NNB; k++) {
+                const float *q = side ? &s->near_r[i][2 * k] : &s->near_l[i][2 * k];
+                if (bird) {
+                    obs[o++] = q[0] / c->norm_pos_world[0];
+                    obs[o++] = q[1] / c->norm_pos_world[1];
+                } else {
+                    float loc[2];
+                    orc_local(pi, rot_i, q, loc);
+                    obs[o++] = loc[0] / c->norm_pos;
+                    obs[o++] = loc[1] / c->norm_pos;
+                }
+            }
+    } else {
+        obs[o++] = s->min_l[i] / c->norm_dist;            /* :376-383 */
+        obs[o++] = s->min_r[i] / c->norm_dist;
+    }
     /* torch.topk(distances.agents[:, i], k, largest=False) :627-636 */
     int used[ORC_MAX_AGENTS] = {0};
     for (int kk = 0; kk < c->k_near; kk++) {
@@ -558,7 +606,7 @@ static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, flo
 int orc_obs_dim(const orc_world *w) {
     const int fl = w->cfg.obs_flags;
     int own = ((fl & ORC_OBS_BIRD_VIEW) ? 5 : 1) + ((fl & ORC_OBS_STEERING) ? 1 : 0) + 2 * ORC_NST +
-              ((fl & ORC_OBS_NO_DIST_CENTER) ? 0 : 1) + 2;
+              ((fl & ORC_OBS_NO_DIST_CENTER) ? 0 : 1) + ((fl & ORC_OBS_BOUNDARY_POINTS) ? 4 * ORC_NNB : 2);
     int per = ((fl & ORC_OBS_CENTRES) ? 5 : 8) + 2 + ((fl & ORC_OBS_STEERING) ? 1 : 0) +
               ((fl & ORC_OBS_NO_DIST_AGENTS) ? 0 : 1) + ((fl & ORC_OBS_REF_OTHERS) ? 2 * ORC_NST : 0);
     return own + per * w->cfg.k_near;
@@ -713,6 +761,7 @@ orc_world *orc_create(int B, int N, const orc_map *map, const orc_cfg *cfg) {
     w->path_id = calloc(BN, 4); w->vertices = calloc(BN * 10, 4); w->d_agents = calloc(BN * N, 4);
     w->d_ref = calloc(BN, 4); w->d_left = calloc(BN * 5, 4); w->d_right = calloc(BN * 5, 4);
     w->d_bound = calloc(BN, 4); w->idx_ref = calloc(BN, 4); w->short_term = calloc(BN * 6, 4);
+    w->idx_left = calloc(BN, 4); w->idx_right = calloc(BN, 4); w->near_fresh = calloc(BN, 1);
     w->prev_pos = calloc(BN * 2, 4); w->col_agents = calloc(BN * N, 1); w->col_lane = calloc(BN, 1);
     w->col_entry = calloc(BN, 1); w->col_exit = calloc(BN, 1); w->step = calloc(B, 4);
     return w;
@@ -724,6 +773,7 @@ void orc_destroy(orc_world *w) {
     free(w->path_id); free(w->vertices); free(w->d_agents); free(w->d_ref); free(w->d_left);
     free(w->d_right); free(w->d_bound); free(w->idx_ref); free(w->short_term); free(w->prev_pos);
     free(w->col_agents); free(w->col_lane); free(w->col_entry); free(w->col_exit); free(w->step);
+    free(w->idx_left); free(w->idx_right); free(w->near_fresh);
     free(w);
 }
 
@@ -732,7 +782,7 @@ void *orc_field(orc_world *w, const char *name) {
 #define F(n) if (!strcmp(name, #n)) return (void *)w->n;
     F(pos) F(rot) F(speed) F(steering) F(vel) F(sideslip) F(path_id) F(vertices) F(d_agents) F(d_ref)
     F(d_left) F(d_right) F(d_bound) F(idx_ref) F(short_term) F(prev_pos) F(col_agents) F(col_lane)
-    F(col_entry) F(col_exit) F(step)
+    F(col_entry) F(col_exit) F(step) F(idx_left) F(idx_right) F(near_fresh)
 #undef F
     return NULL;
 }

@@ -8,7 +8,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 SC = sys.argv[3] if len(sys.argv) > 3 else "cpm_entire"
 NA = int(sys.argv[4]) if len(sys.argv) > 4 else 8
-env = RoadTrafficEnv(EnvConfig(scenario_type=SC, n_agents=NA), num_envs=B, device="cuda:0", seed=0)
+# KB_LAYOUT="is_ego_view=0,is_obs_steering=1": observation-layout switches (0 / 1) for the flag-driven writer
+LAYOUT = {k: bool(int(v)) for k, v in (kv.split("=") for kv in os.environ.get("KB_LAYOUT", "").split(",") if kv)}
+env = RoadTrafficEnv(EnvConfig(scenario_type=SC, n_agents=NA, **LAYOUT), num_envs=B, device="cuda:0", seed=0)
 env.reset()
 ur = torch.tensor([1.0, 31 * np.pi / 180], device="cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -24,5 +26,5 @@ for t in range(K + 5):
     if t >= 5:
         ts.append(e[0].elapsed_time(e[1])); tr.append(e[1].elapsed_time(e[2]))
     chk += float(env.reward.double().sum()) + float(env.obs.double().sum())
-print(f"{os.environ.get('SGB_LIBRARY', 'default')[-28:]:28s} {SC} B={B} N={NA} done-rate {float(env.done.float().mean()):.2f} step {np.mean(ts):.4f} ms (min {np.min(ts):.4f})  reset+refresh {np.mean(tr):.4f} ms  "
+print(f"{os.environ.get('SGB_LIBRARY', 'default')[-28:]:28s} {SC} B={B} N={NA} D={env.D} {os.environ.get('KB_LAYOUT', '')} done-rate {float(env.done.float().mean()):.2f} step {np.mean(ts):.4f} ms (min {np.min(ts):.4f})  reset+refresh {np.mean(tr):.4f} ms  "
       f"-> {B * NA / (np.mean(ts) + np.mean(tr)) / 1e3:.1f} M agent-steps/s   checksum {chk:.6f}")

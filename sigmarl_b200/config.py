@@ -53,17 +53,17 @@ class EnvConfig:
     exhaustive: bool = False                # debug: disable the pruned search (results must not change)
     is_testing_mode: bool = False           # road_traffic.py:1050-1055, 1429-1447; world_state_rt_sim.py:254-261
     reward_reach_goal: float = 100 / R_P_NORMALIZER   # road_traffic.py:217-219
-    # observation layout (observation_provider_rt.py:594-925): any combination of these six is supported
+    # observation layout (observation_provider_rt.py:594-925): any combination of these seven is supported
     is_ego_view: bool = True                       # False: bird view (global coordinates / pos_world)
     is_observe_vertices: bool = True               # False: pos, rot, length, width of a neighbour
     is_obs_steering: bool = False
     is_observe_ref_path_other_agents: bool = False
     is_observe_distance_to_agents: bool = True
     is_observe_distance_to_center_line: bool = True
+    is_observe_distance_to_boundaries: bool = True # False: 5 + 5 boundary points around the closest ones
     # flags of the reference that select code OUTSIDE the supported hot path; must keep these values
     is_use_mtv_distance: bool = False
     is_partial_observation: bool = True            # False crashes in the reference itself (:808)
-    is_observe_distance_to_boundaries: bool = True
     is_apply_mask: bool = False
     is_obs_noise: bool = False
     extras: dict = field(default_factory=dict)
@@ -71,8 +71,7 @@ class EnvConfig:
     def validate(self):
         if self.rew_method not in _REW_METHODS:
             raise NotImplementedError(f"rew_method {self.rew_method!r}: supported {_REW_METHODS} (cbf variants are out of scope)")
-        want = dict(is_use_mtv_distance=False, is_partial_observation=True, is_observe_distance_to_boundaries=True,
-                    is_apply_mask=False, is_obs_noise=False)
+        want = dict(is_use_mtv_distance=False, is_partial_observation=True, is_apply_mask=False, is_obs_noise=False)
         for k, v in want.items():
             if getattr(self, k) != v:
                 raise NotImplementedError(f"{k}={getattr(self, k)} selects a non-default observation/reset variant "
@@ -179,14 +178,15 @@ class EnvConfig:
                 (_lib.SGB_OBS_STEERING if self.is_obs_steering else 0) |
                 (_lib.SGB_OBS_REF_OTHERS if self.is_observe_ref_path_other_agents else 0) |
                 (0 if self.is_observe_distance_to_agents else _lib.SGB_OBS_NO_DIST_AGENTS) |
-                (0 if self.is_observe_distance_to_center_line else _lib.SGB_OBS_NO_DIST_CENTER))
+                (0 if self.is_observe_distance_to_center_line else _lib.SGB_OBS_NO_DIST_CENTER) |
+                (0 if self.is_observe_distance_to_boundaries else _lib.SGB_OBS_BOUNDARY_POINTS))
 
     def obs_dim(self, n_agents: int) -> int:
         """Observation width of this layout (== sgb_obs_dim of a context built from it)."""
         fl = self.obs_flags()
         k = min(self.n_nearing_agents_observed, n_agents - 1)
         own = (5 if fl & _lib.SGB_OBS_BIRD_VIEW else 1) + (1 if fl & _lib.SGB_OBS_STEERING else 0) + 6 + \
-              (0 if fl & _lib.SGB_OBS_NO_DIST_CENTER else 1) + 2
+              (0 if fl & _lib.SGB_OBS_NO_DIST_CENTER else 1) + (20 if fl & _lib.SGB_OBS_BOUNDARY_POINTS else 2)
         per = (5 if fl & _lib.SGB_OBS_CENTRES else 8) + 2 + (1 if fl & _lib.SGB_OBS_STEERING else 0) + \
               (0 if fl & _lib.SGB_OBS_NO_DIST_AGENTS else 1) + (6 if fl & _lib.SGB_OBS_REF_OTHERS else 0)
         return own + per * k

@@ -274,7 +274,8 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
                const sgb_config* cfg_override = nullptr) {
     Params p{};
     p.cfg = cfg_override ? *cfg_override : ctx->cfg;
-    p.skip_scan = skip_scan;
+    // spawn-table refresh: the table holds no boundary indices, so a layout with boundary points runs the scans
+    p.skip_scan = (p.cfg.obs_flags & SGB_OBS_BOUNDARY_POINTS) ? 0 : skip_scan;
     p.fresh = ctx->d_fresh;
     p.buf = *buf;
     p.blob = ctx->d_blob;
@@ -366,7 +367,7 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     }
     if (cfg->k_near < 0 || cfg->k_near >= SGB_MAX_AGENTS || cfg->max_steps < 2 || !(cfg->dt > 0.0f)) return SGB_ERR_ARG;
     constexpr uint32_t kObsKnown = SGB_OBS_BIRD_VIEW | SGB_OBS_CENTRES | SGB_OBS_STEERING | SGB_OBS_REF_OTHERS |
-                                   SGB_OBS_NO_DIST_AGENTS | SGB_OBS_NO_DIST_CENTER;
+                                   SGB_OBS_NO_DIST_AGENTS | SGB_OBS_NO_DIST_CENTER | SGB_OBS_BOUNDARY_POINTS;
     if (cfg->obs_flags & ~kObsKnown) {
         snprintf(g_err, sizeof g_err, "obs_flags 0x%x: unknown observation layout bits", cfg->obs_flags);
         return SGB_ERR_UNSUPPORTED;

@@ -589,10 +589,17 @@ __device__ __forceinline__ float wrap_pi(float a) {
     return m;
 }
 
+// carry.w = closest centre index of the pre-step pose.  With SGB_OBS_BOUNDARY_POINTS bit 30 additionally says that the
+// agent's pose was written by a reset / respawn rather than by a step (the reference then holds nearing boundary
+// points taken with n_points_shift = +1 instead of -2, world_state_rt.py:531-576 vs :686-725).
+constexpr int kCarryIdxMask = 0x3fffffff;
+constexpr int kCarryFreshBit = 0x40000000;
+constexpr int kNearPts = 5;      // n_points_nearing_boundary (road_traffic.py:296-298)
+
 // Observation width for a layout (observation_provider_rt.py:594-925; see SGB_OBS_* in the header)
 __host__ __device__ inline int obs_dim_of(uint32_t fl, int k_near) {
     const int own = ((fl & SGB_OBS_BIRD_VIEW) ? 5 : 1) + ((fl & SGB_OBS_STEERING) ? 1 : 0) + 2 * SGB_N_SHORT_TERM +
-                    ((fl & SGB_OBS_NO_DIST_CENTER) ? 0 : 1) + 2;
+                    ((fl & SGB_OBS_NO_DIST_CENTER) ? 0 : 1) + ((fl & SGB_OBS_BOUNDARY_POINTS) ? 4 * kNearPts : 2);
     const int per = ((fl & SGB_OBS_CENTRES) ? 5 : 8) + 2 + ((fl & SGB_OBS_STEERING) ? 1 : 0) +
                     ((fl & SGB_OBS_NO_DIST_AGENTS) ? 0 : 1) + ((fl & SGB_OBS_REF_OTHERS) ? 2 * SGB_N_SHORT_TERM : 0);
     return own + per * k_near;
@@ -615,6 +622,9 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
     const int N = p.N, D = p.D;
     const sgb_config& cfg = p.cfg;
     constexpr bool step_mode = (MODE == 0);
+    // closest-index part of carry.w (the flag-driven layouts may keep a history bit above it, see kCarryFreshBit)
+    auto idx_of = [](float w) { return __float_as_int(w) & kCarryIdxMask; };   // (used by the OV = 1 instantiations only)
+    const bool bpoints = OV != 0 && (p.cfg.obs_flags & SGB_OBS_BOUNDARY_POINTS) != 0;
     constexpr int kWarps = cta_threads(G) / 32;
     constexpr int SPW = 32 / G;                 // agent slots per warp
     const int env_lanes = N * G;                // lanes per env
@@ -780,7 +790,8 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             if (slot_ok && lane == 0) {
                 const float4 fr = reinterpret_cast<const float4*>(p.fresh)[(size_t)ts.env[sl] * N + i_of_lane];
                 ts.sc[0 * AS + sl] = ts.car[0 * AS + sl];
-                ts.sc[1 * AS + sl] = ts.car[3 * AS + sl];
+                if (OV) ts.sc[1 * AS + sl] = __int_as_float(idx_of(ts.car[3 * AS + sl]));
+                else ts.sc[1 * AS + sl] = ts.car[3 * AS + sl];
                 ts.sc[2 * AS + sl] = fr.x; ts.sc[3 * AS + sl] = fr.y;
                 ts.sc[4 * AS + sl] = fr.z; ts.sc[5 * AS + sl] = fr.w;
                 ts.flags[sl] = 0;
@@ -798,7 +809,8 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             float* dbg = (p.buf.dbg && writer) ? p.buf.dbg + ((size_t)ts.env[sl] * N + i_of_lane) * 16 : nullptr;
             // hint = last closest segment (step) / the spawn point written by place_agent (refresh); any value
             // is valid, a good one lets the first chunk scanned set a tight pruning bound
-            const int hint = __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1;
+            const int hint = OV ? idx_of(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1
+                                : __float_as_int(slot_ok ? ts.car[3 * AS + sl] : 0.0f) - 1;
             int h2;
             {
                 float d_ref;
@@ -845,6 +857,25 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 }
             }
             if (writer) ts.flags[sl] = step_mode ? fl : 0;
+            if (bpoints) {
+                // Boundary points instead of boundary distances: the observation needs distances.closest_point_on_left_b
+                // / right_b (world_state_rt.py:597-622), an ARGMIN, so the exact centre-line scan runs on the two
+                // boundaries as well.  What agent i's row shows is the fresh index for i == 0 and last step's for
+                // i >= 1 — a function of the PRE-step position, which is still in the slot arrays.
+                const bool stale = step_mode && i_of_lane != 0;
+                const float qx = (stale && slot_ok) ? ts.ox[sl] : px, qy = (stale && slot_ok) ? ts.oy[sl] : py;
+                const int hb = stale ? hint : h2;
+                int packed = 0;
+#pragma unroll 1
+                for (int side = 0; side < 2; side++) {
+                    float dd;
+                    int ii;
+                    scan_center<G>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
+                                   side ? prp->n_r : prp->n_l, hb, ex, qx, qy, lane, dd, ii);
+                    packed |= ii << (16 * side);
+                }
+                if (writer) ts.psim[sl] = __int_as_float(packed);   // psim (heading mod pi) is dead after the scans
+            }
         }
         // ---- rectangle-rectangle crossings: the N(N-1)/2 unordered pairs of an env are dealt round-robin to  @region pairs
         //      the env's N*G lanes; interX(vertices[lo], vertices[hi]) with lo < hi exactly as
@@ -967,7 +998,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 const float dLc = ts.sc[2 * AS + sl], dRc = ts.sc[3 * AS + sl];
                 const float m4L = ts.sc[4 * AS + sl], m4R = ts.sc[5 * AS + sl];
                 const float c_dref = ts.car[0 * AS + sl], c_mL = ts.car[1 * AS + sl], c_mR = ts.car[2 * AS + sl];
-                const int c_idx = __float_as_int(ts.car[3 * AS + sl]);
+                const int c_idx = OV ? idx_of(ts.car[3 * AS + sl]) : __float_as_int(ts.car[3 * AS + sl]);
                 const bool write_obs = step_mode || p.write_obs;
                 float* o = p.buf.obs + g * D;   // written in place: 128 B per agent, L2 merges the partial sectors
                 const float cs = ts.cs[sl], sn = ts.sn[sl];
@@ -1019,8 +1050,31 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
 #pragma unroll
                         for (int k = 0; k < 3; k++) { put_point(q, st[k].x, st[k].y); q += 2; }
                         if (!(ofl & SGB_OBS_NO_DIST_CENTER)) *q++ = o_dref * r_dist;
-                        q[0] = o_mL * r_dist;
-                        q[1] = o_mR * r_dist;
+                        if (ofl & SGB_OBS_BOUNDARY_POINTS) {
+                            // world_state_rt.py:686-725 (step: shift -2) / :531-576 (reset: shift +1); the loop wrap uses
+                            // the CENTRE line's point count, as the reference passes it; an index outside the boundary
+                            // lands in the reference's tail padding (= last boundary point; -1 is python's last element)
+                            const int packed = __float_as_int(ts.psim[sl]);
+                            const bool from_reset = !step_mode || (i != 0 && (__float_as_int(ts.car[3 * AS + sl]) & kCarryFreshBit));
+                            const int shift = from_reset ? 1 : -2;
+#pragma unroll 1
+                            for (int side = 0; side < 2; side++) {
+                                const float2* bp = pts + (side ? prp->r_off : prp->l_off);
+                                const int n_s = side ? prp->n_r : prp->n_l;
+                                const int ib = (packed >> (16 * side)) & 0xffff;
+                                for (int k = 0; k < kNearPts; k++) {
+                                    int fi = k + ib + shift;
+                                    if (pr_loop && fi >= pr_nc - 1) fi = (fi + 1) % pr_nc;
+                                    if (fi < 0 || fi >= n_s) fi = n_s - 1;
+                                    const float2 b = bp[fi];
+                                    put_point(q, b.x, b.y);
+                                    q += 2;
+                                }
+                            }
+                        } else {
+                            q[0] = o_mL * r_dist;
+                            q[1] = o_mR * r_dist;
+                        }
                     }
                     const int own = obs_dim_of(ofl, 0), per = obs_dim_of(ofl, 1) - own;
                     for (int kk = lane; kk < k_near; kk += G) {
@@ -1057,7 +1111,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                             int pj = ts.path[sj];
                             pj = (pj < 0 || pj >= hdr->n_paths) ? 0 : pj;
                             const PathRec* prj = paths + pj;
-                            const int idx_j = __float_as_int((step_mode && bj != 0) ? ts.car[3 * AS + sj] : ts.sc[1 * AS + sj]);
+                            const int idx_j = idx_of((step_mode && bj != 0) ? ts.car[3 * AS + sj] : ts.sc[1 * AS + sj]);
                             float2 st[3];
                             short_term(pts + prj->c_off, prj->n_c, prj->is_loop != 0, idx_j, st);
 #pragma unroll
@@ -1174,7 +1228,8 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                     nc.x = d_ref_n;
                     nc.y = (i == 0) ? m4L : fminf(dLc, m4L);
                     nc.z = (i == 0) ? m4R : fminf(dRc, m4R);
-                    nc.w = __int_as_float(idx_n);
+                    if (OV) nc.w = __int_as_float(idx_n | ((bpoints && !step_mode) ? kCarryFreshBit : 0));
+                    else nc.w = __int_as_float(idx_n);
                     reinterpret_cast<float4*>(p.buf.carry)[g] = nc;
                     if (p.buf.dbg) p.buf.dbg[g * 16 + 12] = d_bound;
                     if (p.buf.info) {
@@ -1269,7 +1324,9 @@ __device__ __forceinline__ void place_agent(const sgb_config& cfg, const sgb_buf
         const float4 t1 = reinterpret_cast<const float4*>(spawn_tab)[2 * (size_t)(pr.c_off + point) + 1];
         // the carry of agent 0 holds the vertex part only (its centre part is always fresh)
         reinterpret_cast<float4*>(buf.carry)[g] = make_float4(t0.x, agent == 0 ? t1.x : fminf(t0.z, t1.x),
-                                                               agent == 0 ? t1.y : fminf(t0.w, t1.y), t0.y);
+                                                               agent == 0 ? t1.y : fminf(t0.w, t1.y),
+                                                               (cfg.obs_flags & SGB_OBS_BOUNDARY_POINTS)
+                                                                   ? __int_as_float(__float_as_int(t0.y) | kCarryFreshBit) : t0.y);
         if (fresh) reinterpret_cast<float4*>(fresh)[g] = make_float4(t0.z, t0.w, t1.x, t1.y);
     } else {
         reinterpret_cast<float4*>(buf.carry)[g] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(point + 1)); // search hint

@@ -177,6 +177,21 @@ class RoadTrafficEnv:
             self.step_count.copy_(torch.as_tensor(np.asarray(step_count), dtype=torch.int32, device=dev))
         return self.refresh(write_obs=write_obs)
 
+    def set_pose_history(self, from_reset):
+        """Teacher forcing with ``is_observe_distance_to_boundaries=False``: say for which agents [B,N] the injected
+        pose was written by a reset / respawn (True) rather than by a step (False).  The reference samples the nearing
+        boundary points differently in the two cases (world_state_rt.py:531-576 vs :686-725) and agents >= 1 observe
+        the previous write; the library keeps that one bit in ``carry.w`` (bit 30).  ``set_state`` / ``refresh``
+        mark every agent as reset, a step clears the mark."""
+        m = torch.as_tensor(np.asarray(from_reset), device=self.device).to(torch.bool).reshape(self.B, self.N)
+        w = self.carry.view(torch.int32)[..., 3]
+        w.copy_(torch.where(m, w | _lib.CARRY_FRESH_BIT, w & _lib.CARRY_IDX_MASK))
+
+    @property
+    def pose_from_reset(self):
+        """[B,N] bool: the mark described in ``set_pose_history`` (always False for the other layouts)."""
+        return (self.carry.view(torch.int32)[..., 3] & _lib.CARRY_FRESH_BIT) != 0
+
     def step_host(self, h_action: torch.Tensor):
         """End-to-end step with HOST buffers through sgb_step_host (H2D action, D2H obs/reward/done inside)."""
         if self._h is None:

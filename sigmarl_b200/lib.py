@@ -13,7 +13,8 @@ SGB_MAX_AGENTS = 32
 SGB_FLAG_COLLIDE_AGENT, SGB_FLAG_COLLIDE_LANE, SGB_FLAG_ENTRY, SGB_FLAG_EXIT = 1, 2, 4, 8
 SGB_REW_EXACT_SPARSE, SGB_REW_TTC, SGB_REW_DISTANCE, SGB_REW_SPARSE = 1, 2, 4, 8
 (SGB_OBS_BIRD_VIEW, SGB_OBS_CENTRES, SGB_OBS_STEERING, SGB_OBS_REF_OTHERS, SGB_OBS_NO_DIST_AGENTS,
- SGB_OBS_NO_DIST_CENTER) = 1, 2, 4, 8, 16, 32
+ SGB_OBS_NO_DIST_CENTER, SGB_OBS_BOUNDARY_POINTS) = 1, 2, 4, 8, 16, 32, 64
+CARRY_IDX_MASK, CARRY_FRESH_BIT = 0x3fffffff, 0x40000000   # carry.w with SGB_OBS_BOUNDARY_POINTS (see the header)
 
 # every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",

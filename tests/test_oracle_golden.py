@@ -17,6 +17,18 @@ from conftest import golden_files
 TOL = 1e-5
 
 
+def fresh_from_reset(g, t):
+    """[B,N] bool: the agent's nearing boundary points were last written by a reset / respawn rather than by step
+    t-1.  The one piece of history the step depends on besides the pre-step state: the reference fills them with
+    n_points_shift = +1 at a reset and -2 in a step (world_state_rt.py:531-576 vs :686-725).  Includes the reference's
+    env-0 artefact: ``if env_index:`` (road_traffic.py:892-895) is false for env 0, so a reset of env 0 (respawn of
+    agent a in env 0) re-initialises the distances of ALL envs (of agent a in all envs) — SURVEY.md A.7."""
+    if t == 0:
+        return np.ones(g["respawn_mask"][0].shape, bool)
+    rst, rsp = g["reset_mask"][t - 1], g["respawn_mask"][t - 1]
+    return rst[:, None] | rsp | rst[0] | rsp[0][None, :]
+
+
 def _run(O, path):
     g = np.load(path)
     st = str(g["cfg_scenario_type"])
@@ -29,6 +41,7 @@ def _run(O, path):
         gp = pm.global_path(g["pre_scenario_id"][t], g["pre_path_id"][t])
         w.set_state(g["pre_pos"][t], g["pre_rot"][t], g["pre_speed"][t], g["pre_steering"][t], gp)
         w.step_count[:] = g["pre_step"][t]
+        w.near_fresh[:] = fresh_from_reset(g, t)
         obs, rew, done, resp = w.step(g["action"][t])
         for name, got, want in [
             ("pos", w.pos, g["post_pos"][t]), ("rot", w.rot, g["post_rot"][t]),
