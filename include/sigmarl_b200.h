@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 121
+#define SGB_VERSION 122
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -96,6 +96,10 @@ typedef struct {
                                  observation_provider_rt.py:594-925 */
     float norm_pos_world_x, norm_pos_world_y; /* normalizers.pos_world (bird view)  road_traffic.py:593-595 */
     float norm_dist_agent;    /* normalizers.distance_agent (lengths / widths)      road_traffic.py:605-607 */
+    float obs_noise_level;    /* is_obs_noise ? obs_noise_level : 0: obs += level * U[0,1) per element
+                                 (observation_provider_rt.py:611-617); device generator, distribution-equivalent */
+    uint32_t obs_noise_seed;
+    uint32_t reserved0, reserved1; /* keeps sizeof(sgb_config) a multiple of 16 (kernel-parameter alignment) */
 } sgb_config;
 
 /* Observation layout flags == the reference's Parameters of the same meaning (helper_common.py:60-118;
@@ -104,7 +108,7 @@ typedef struct {
  * neighbour: 4 vertices (8) or pos(2), rot, length, width | vel (2) | [steering] | [distance] | [its
  * short-term path (6)].  Not offered (sgb_create returns SGB_ERR_UNSUPPORTED for unknown bits;
  * the Python host layer refuses the parameters in EnvConfig.validate): is_partial_observation = False (the
- * reference itself crashes there, observation_provider_rt.py:808), masks, observation noise. */
+ * reference itself crashes there, observation_provider_rt.py:808) and masks. */
 #define SGB_OBS_BIRD_VIEW 1u       /* is_ego_view = False: global coordinates / pos_world                 */
 #define SGB_OBS_CENTRES 2u         /* is_observe_vertices = False: pos, rot, length, width of a neighbour  */
 #define SGB_OBS_STEERING 4u        /* is_obs_steering: own and neighbours' steering angle / (2 pi)         */

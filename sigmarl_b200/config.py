@@ -61,17 +61,19 @@ class EnvConfig:
     is_observe_distance_to_agents: bool = True
     is_observe_distance_to_center_line: bool = True
     is_observe_distance_to_boundaries: bool = True # False: 5 + 5 boundary points around the closest ones
+    is_obs_noise: bool = False                     # obs += obs_noise_level * U[0,1) (device generator)
+    obs_noise_level: Optional[float] = None        # None -> 0.05 (params, helper_common.py:77) / 0.2 * width (kwargs, :337-339)
+    obs_noise_seed: int = 0
     # flags of the reference that select code OUTSIDE the supported hot path; must keep these values
     is_use_mtv_distance: bool = False
     is_partial_observation: bool = True            # False crashes in the reference itself (:808)
     is_apply_mask: bool = False
-    is_obs_noise: bool = False
     extras: dict = field(default_factory=dict)
 
     def validate(self):
         if self.rew_method not in _REW_METHODS:
             raise NotImplementedError(f"rew_method {self.rew_method!r}: supported {_REW_METHODS} (cbf variants are out of scope)")
-        want = dict(is_use_mtv_distance=False, is_partial_observation=True, is_apply_mask=False, is_obs_noise=False)
+        want = dict(is_use_mtv_distance=False, is_partial_observation=True, is_apply_mask=False)
         for k, v in want.items():
             if getattr(self, k) != v:
                 raise NotImplementedError(f"{k}={getattr(self, k)} selects a non-default observation/reset variant "
@@ -169,6 +171,9 @@ class EnvConfig:
         c.obs_flags = self.obs_flags()
         c.norm_pos_world_x, c.norm_pos_world_y = float(x), float(y)            # road_traffic.py:593-595
         c.norm_dist_agent = float(_f32(AGENT_LENGTH * 10))                     # road_traffic.py:605-607
+        level = self.obs_noise_level if self.obs_noise_level is not None else (0.05 if self.mode == "params" else 0.2 * AGENT_WIDTH)
+        c.obs_noise_level = float(_f32(level)) if self.is_obs_noise else 0.0
+        c.obs_noise_seed = int(self.obs_noise_seed) & 0xffffffff
         return c
 
     def obs_flags(self) -> int:

@@ -292,7 +292,7 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.r_dist = 1.0f / ctx->cfg.norm_dist;
     const int g = pick_group(N);
     // the default observation layout runs the hard-wired (tuned) writer, any other one the flag-driven writer
-    if (p.cfg.obs_flags == 0) return mode == 0 ? launch_env_group<0, 0>(ctx, p, st, g) : launch_env_group<1, 0>(ctx, p, st, g);
+    if (p.cfg.obs_flags == 0 && !(p.cfg.obs_noise_level > 0.0f)) return mode == 0 ? launch_env_group<0, 0>(ctx, p, st, g) : launch_env_group<1, 0>(ctx, p, st, g);
     return mode == 0 ? launch_env_group<0, 1>(ctx, p, st, g) : launch_env_group<1, 1>(ctx, p, st, g);
 }
 
@@ -374,6 +374,7 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     }
     if ((cfg->obs_flags & SGB_OBS_BIRD_VIEW) && !(cfg->norm_pos_world_x > 0.0f && cfg->norm_pos_world_y > 0.0f)) return SGB_ERR_ARG;
     if ((cfg->obs_flags & SGB_OBS_CENTRES) && !(cfg->norm_dist_agent > 0.0f)) return SGB_ERR_ARG;
+    if (!(cfg->obs_noise_level >= 0.0f)) return SGB_ERR_ARG;
     Packed pk;
     int rc = pack_map(map, pk);
     if (rc != SGB_OK) return rc;

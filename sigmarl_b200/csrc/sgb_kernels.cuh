@@ -581,6 +581,14 @@ __device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int 
     }
 }
 
+// splitmix64 finaliser: the counter-based generator of the reset kernels and of the observation noise
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
 // helper_scenario.py:1276-1289 angle_eliminate_two_pi (fp32: the python scalars are cast to the tensor's dtype)
 __device__ __forceinline__ float wrap_pi(float a) {
     const float pi_f = 3.14159274101257324f, two_pi = 6.28318548202514648f;
@@ -1119,6 +1127,20 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                         }
                         if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
                     }
+                    if (cfg.obs_noise_level > 0.0f) {
+                        // observation_provider_rt.py:611-617: obs + level * U[0,1) on every element.  The reference draws
+                        // from torch's global generator; here the draw is a counter-based hash of the agent's own
+                        // post-step state (position, heading, speed bits), its index and the column — i.i.d.-looking,
+                        // reproducible, and independent of how envs are sharded (distribution-equivalent, like resets).
+                        __syncwarp(((G >= 32) ? 0xffffffffu : ((1u << G) - 1u)) << (ln - lane));   // the row is complete
+                        uint64_t key = ((uint64_t)__float_as_uint(pix) << 32) | __float_as_uint(piy);
+                        key = mix64(key) ^ (((uint64_t)__float_as_uint(psi_i) << 32) | __float_as_uint(ts.vabs[sl]));
+                        key = mix64(key ^ ((uint64_t)i << 48) ^ cfg.obs_noise_seed);
+                        for (int d = lane; d < D; d += G) {
+                            const float u = (float)(mix64(key + (uint64_t)d) >> 40) * (1.0f / 16777216.0f);
+                            o[d] += cfg.obs_noise_level * u;
+                        }
+                    }
                 }
                 if (OV == 0 && write_obs) {
                     // ---- point transforms into the ego frame, split evenly over the lanes: 3 short-term points
@@ -1277,12 +1299,6 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
 }
 
 // ---- placement / reset kernels ------------------------------------------------------------------------------  @region other kernels
-__device__ __forceinline__ uint64_t mix64(uint64_t z) {
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
 // counter-based: one 64-bit draw per (seed, epoch, env, agent, try, which)
 __device__ __forceinline__ uint64_t draw(uint64_t seed, uint64_t epoch, uint64_t env, uint32_t agent, uint32_t tr, uint32_t which) {
     uint64_t h = mix64(seed ^ mix64(epoch));

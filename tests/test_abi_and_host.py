@@ -145,9 +145,18 @@ def test_config_matches_reference_constants_in_goldens():
 def test_unsupported_flags_fail_loudly():
     from sigmarl_b200 import EnvConfig, MapLibrary
     m = MapLibrary("cpm_entire")
-    for kw in (dict(is_use_mtv_distance=True), dict(rew_method="cbf"), dict(is_obs_noise=True)):
+    for kw in (dict(is_use_mtv_distance=True), dict(rew_method="cbf"), dict(is_apply_mask=True),
+               dict(is_partial_observation=False)):
         with pytest.raises(NotImplementedError):
             EnvConfig(scenario_type="cpm_entire", **kw).lower(m)
+    # observation layouts and noise ARE supported (ABI 121 / 122): flags, width and noise level reach sgb_config
+    from sigmarl_b200 import lib
+    c = EnvConfig(scenario_type="cpm_entire", n_agents=4, is_ego_view=False, is_obs_steering=True,
+                  is_observe_distance_to_boundaries=False, is_obs_noise=True)
+    low = c.lower(m)
+    assert low.obs_flags == lib.SGB_OBS_BIRD_VIEW | lib.SGB_OBS_STEERING | lib.SGB_OBS_BOUNDARY_POINTS
+    assert abs(low.obs_noise_level - 0.05) < 1e-7 and c.obs_dim(4) == (5 + 1 + 6 + 1 + 20) + 2 * (8 + 2 + 1 + 1)
+    assert EnvConfig(scenario_type="cpm_entire").lower(m).obs_flags == 0 and EnvConfig().obs_dim(8) == 32
     assert EnvConfig(scenario_type="cpm_entire", is_testing_mode=True).lower(m).testing_mode == 1   # supported since ABI 110
     with pytest.raises(ValueError):
         MapLibrary("no_such_map")

@@ -201,6 +201,60 @@ def test_cuda_observation_layouts_match_oracle(oracle_mod, scenario, N, rew, mod
     assert env.D == env.config.obs_dim(N) and env.config.obs_flags() != 0
 
 
+@pytest.mark.parametrize("layout", [dict(), dict(is_ego_view=False, is_obs_steering=True)], ids=["default", "birdview"])
+def test_observation_noise_is_uniform_additive_and_reproducible(layout):
+    """is_obs_noise (observation_provider_rt.py:611-617): obs + level * U[0,1) on every element.  The reference draws
+    from torch's global generator, the library from a counter-based device generator — distribution-equivalent:
+    noisy - clean must lie in [0, level), look uniform, differ between columns / agents / steps, and be a pure
+    function of (seed, state), i.e. reproducible and independent of the env's index (sharding)."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    B, N, level = 4096, 8, 0.05
+    mk = lambda noise, seed=0, nenv=B: RoadTrafficEnv(  # noqa: E731
+        EnvConfig(scenario_type="cpm_entire", n_agents=N, is_obs_noise=noise, obs_noise_seed=seed, **layout),
+        num_envs=nenv, device="cuda:0", seed=3)
+    clean, noisy, noisy2, other_seed = mk(False), mk(True), mk(True), mk(True, seed=1)
+    half = mk(True, nenv=B // 2)
+    assert noisy.D == clean.D
+    g = torch.Generator(device="cuda").manual_seed(1)
+    ur = torch.as_tensor(UR).cuda()
+    for e in (clean, noisy, noisy2, other_seed, half):
+        e.reset()
+    prev = None
+    for t in range(4):
+        act = (torch.rand(B, N, 2, device="cuda", generator=g) * 2 - 1) * ur
+        half.pose.copy_(clean.pose[B // 2:]); half.aux.copy_(clean.aux[B // 2:]); half.carry.copy_(clean.carry[B // 2:])
+        half.path_id.copy_(clean.path_id[B // 2:]); half.step_count.copy_(clean.step_count[B // 2:])
+        for e in (clean, noisy, noisy2, other_seed):
+            e.step(act)
+        half.step(act[B // 2:])
+        d = (noisy.obs - clean.obs).double()
+        # same state trajectory (noise touches the observation only)
+        assert torch.equal(noisy.pose, clean.pose) and torch.equal(noisy.reward, clean.reward)
+        assert float(d.min()) >= -1e-6 and float(d.max()) < level + 1e-6
+        u = d / level
+        n = u.numel()
+        assert abs(float(u.mean()) - 0.5) < 4 / (12 * n) ** 0.5 + 1e-4          # 4 sigma of a uniform mean (+ fp32 rounding)
+        assert abs(float(u.var()) - 1 / 12) < 2e-3
+        cols = u.reshape(-1, noisy.D)
+        assert float((cols.mean(0) - 0.5).abs().max()) < 0.02                   # every column on its own
+        c = torch.corrcoef(cols[:, :6].T)
+        assert float((c - torch.eye(6, device="cuda", dtype=c.dtype)).abs().max()) < 0.03   # columns uncorrelated
+        assert torch.equal(noisy.obs, noisy2.obs)                               # reproducible
+        assert not torch.equal(noisy.obs, other_seed.obs)                       # seed matters
+        assert torch.equal(half.obs, noisy.obs[B // 2:])                        # independent of the env index
+        if prev is not None:
+            assert float(((d - prev).abs() > 1e-4).double().mean()) > 0.95      # fresh draws every step
+        prev = d
+        for e in (clean, noisy, noisy2, other_seed):
+            e.reset_done(write_obs=False)
+        # resets use the same RNG stream in all four envs: the trajectories stay identical
+        assert torch.equal(noisy.pose, clean.pose)
+    # the observation right after a reset is noisy as well (get_observation is the same call)
+    a, b = clean.reset(), noisy.reset()
+    dd = (b - a).double()
+    assert float(dd.min()) >= -1e-6 and float(dd.max()) < level + 1e-6 and float(dd.mean()) > 0.4 * level
+
+
 def _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, **flags):
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     O = oracle_mod
