@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -489,8 +490,11 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
     p.spawn_tab = c->d_spawn; p.fresh = c->d_fresh; p.list_full_only = 1;
     p.explicit_sel = explicit_sel; p.env_mask = env_mask; p.agent_mask = agent_mask;
-    // envs per warp: as few as keep every warp of the launch resident (48 warps per SM), at most 32
-    p.epw = std::max(1, std::min(32, (B + c->num_sms * 48 - 1) / (c->num_sms * 48)));
+    // envs per warp: a warp walks its touched envs one after the other, so few envs per warp keep the dependent-load
+    // chains short; about four waves of resident warps (48 per SM) was the best trade against block-launch overhead
+    // (B = 65536, N = 8, 26 % done: 1 -> 0.084, 2-3 -> 0.082, 6 -> 0.085, 10 -> 0.091 ms per reset + fresh obs)
+    p.epw = std::max(1, std::min(32, (B + c->num_sms * 192 - 1) / (c->num_sms * 192)));
+    if (const char* e = getenv("SGB_RESET_EPW")) p.epw = std::max(1, std::min(32, atoi(e)));   // tuning knob (profiles/kbench.py)
     const int64_t n_warps = ((int64_t)B + p.epw - 1) / p.epw;
     reset_kernel<<<(int)((n_warps * 32 + 255) / 256), 256, 0, st>>>(p);
     c->launches++;
