@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE — function-level known-answer vectors from the UNMODIFIED reference helpers.
+
+Calls the reference's own geometry primitives (``sigmarl/helper_scenario.py``, imported from
+``/root/reference`` behind ``oracle/refshim/install_shims.py``) on seeded random inputs plus the edge cases
+the environment step meets (a point exactly on a polyline vertex, touching / identical / collinear
+rectangles, angles at +-pi, short-term indices at the end of loop and open paths) and stores inputs and
+outputs in ``tests/golden/kat/helpers.npz``.  ``tests/test_oracle_kat.py`` replays them through the C
+oracle's primitives ("function-level known-answer tests against the reference functions").
+
+Re-run (here only):  ``python oracle/gen_kat.py``
+"""
+import os
+import sys
+
+os.environ["CICD_TESTING"] = "true"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+import install_shims  # noqa: E402,F401
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from sigmarl import helper_scenario as H  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden", "kat", "helpers.npz")
+L, W = 0.22, 0.107  # constants.py:630-631
+
+
+def main():
+    torch.manual_seed(1234)
+    out = {}
+
+    # ---- get_perpendicular_distances (helper_scenario.py:829-889): smooth random polylines padded to P points
+    K, P = 96, 40
+    t = torch.linspace(0, 1, P).unsqueeze(0)
+    ph = torch.rand(K, 1) * 6.28
+    poly = torch.stack([2.0 * t + 0.3 * torch.sin(4 * t + ph), 0.8 * torch.cos(3 * t + ph) + 0.2 * t], dim=-1)  # [K,P,2]
+    n_pts = torch.randint(8, P - 3, (K,))
+    for k in range(K):      # tail padding as world_state_rt.py:313-392 (repeat the last real point)
+        poly[k, n_pts[k]:] = poly[k, n_pts[k] - 1]
+    pts = poly[torch.arange(K), torch.randint(0, 8, (K,))] + 0.15 * torch.randn(K, 2)
+    pts[:16] = poly[torch.arange(16), torch.randint(1, 7, (16,))]        # exactly on a vertex: two segments tie at 0
+    pts[16:24] = poly[torch.arange(16, 24), n_pts[16:24] - 1] + 0.05     # beyond the last real point (fix-up :877-879)
+    d, idx = H.get_perpendicular_distances(point=pts.clone(), polyline=poly.clone(), n_points_long_term=n_pts.clone())
+    out.update(perp_poly=poly, perp_n=n_pts, perp_point=pts, perp_dist=d, perp_idx=idx)
+
+    # ---- get_rectangle_vertices (:695-826)
+    c = torch.randn(64, 2) * 2
+    yaw = (torch.rand(64, 1) * 2 - 1) * 7.0
+    yaw[:4, 0] = torch.tensor([0.0, torch.pi / 2, -torch.pi, 3 * torch.pi])
+    v = H.get_rectangle_vertices(center=c, yaw=yaw, width=W, length=L, is_close_shape=True)
+    out.update(rect_center=c, rect_yaw=yaw.squeeze(-1), rect_vertices=v)
+
+    # ---- interX (:1148-1229): rectangle vs rectangle and rectangle vs polyline
+    n = 256
+    ca = torch.randn(n, 2) * 0.2
+    cb = ca + torch.randn(n, 2) * 0.18
+    ya, yb = torch.rand(n, 1) * 6.28, torch.rand(n, 1) * 6.28
+    cb[:8], yb[:8] = ca[:8], ya[:8]                                       # identical rectangles
+    cb[8:16] = ca[8:16] + torch.tensor([L, 0.0]); ya[8:16] = 0.0; yb[8:16] = 0.0      # edge-touching, collinear sides
+    cb[16:24] = ca[16:24] + torch.tensor([L, W]); ya[16:24] = 0.0; yb[16:24] = 0.0    # corner-touching
+    cb[24:32] = ca[24:32] + torch.tensor([0.0, W / 2]); ya[24:32] = 0.0; yb[24:32] = 0.0  # overlapping, parallel
+    ra = H.get_rectangle_vertices(center=ca, yaw=ya, width=W, length=L, is_close_shape=True)
+    rb = H.get_rectangle_vertices(center=cb, yaw=yb, width=W, length=L, is_close_shape=True)
+    out.update(ix_a=ra, ix_b=rb, ix_rr=H.interX(ra.clone(), rb.clone(), False))
+    cp = poly
+    cr = cp[torch.arange(K), torch.randint(0, 8, (K,))] + 0.04 * torch.randn(K, 2)
+    rr = H.get_rectangle_vertices(center=cr, yaw=torch.rand(K, 1) * 6.28, width=W, length=L, is_close_shape=True)
+    out.update(ix_rect=rr, ix_poly=cp, ix_rp=H.interX(rr.clone(), cp.clone(), False))
+
+    # ---- angle_eliminate_two_pi (:1276-1289)
+    a = torch.cat([torch.randn(200) * 8, torch.tensor([0.0, torch.pi, -torch.pi, 2 * torch.pi, -2 * torch.pi,
+                                                        3 * torch.pi, 1e-7, -1e-7, 6.2831855, 3.1415927, 3.1415925])])
+    out.update(wrap_in=a.clone(), wrap_out=H.angle_eliminate_two_pi(a.clone()))
+
+    # ---- transform_from_global_to_local_coordinate (:1241-1273), batched form
+    pi_, pj = torch.randn(64, 2), torch.randn(64, 5, 2)
+    ri = (torch.rand(64, 1) * 2 - 1) * 4
+    out.update(loc_pi=pi_, loc_pj=pj, loc_rot=ri.squeeze(-1),
+               loc_out=H.transform_from_global_to_local_coordinate(pos_i=pi_, pos_j=pj, rot_i=ri))
+
+    # ---- get_short_term_reference_path (:892-957): loop / open, both parameterisations used by the scenario
+    n_c = torch.randint(12, P - 8, (K,))
+    is_loop = torch.rand(K) < 0.5
+    idx0 = torch.stack([torch.randint(1, int(m), ()) for m in n_c])
+    idx0[:12] = n_c[:12] - 1                                              # closest point = last point
+    for name, kw in (("st", dict(n_points_to_return=3, sample_interval=2, n_points_shift=1)),
+                     ("nb", dict(n_points_to_return=5, sample_interval=1, n_points_shift=-2)),
+                     ("nbr", dict(n_points_to_return=5, sample_interval=1, n_points_shift=1))):
+        sp, fi = H.get_short_term_reference_path(polyline=poly.clone(), index_closest_point=idx0.clone(),
+                                                 is_polyline_a_loop=is_loop.clone(), n_points_long_term=n_c.clone(), **kw)
+        out[name + "_pts"], out[name + "_idx"] = sp, fi
+    out.update(st_poly=poly, st_n=n_c, st_loop=is_loop, st_idx0=idx0)
+
+    # ---- decreasing_fcn (:960-996), linear
+    x = torch.cat([torch.rand(100) * 0.6 - 0.1, torch.tensor([0.0, 0.3, 0.02])])
+    out.update(dec_x=x, dec_lin_0_03=H.decreasing_fcn(x.clone(), torch.tensor(0.0), torch.tensor(0.3), "linear"))
+
+    np.savez_compressed(OUT, **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()})
+    print("wrote", OUT, {k: tuple(np.asarray(v).shape) for k, v in out.items() if k.endswith(("dist", "rr", "rp", "out"))},
+          "rect-rect crossings", int(out["ix_rr"].sum()), "rect-poly crossings", int(out["ix_rp"].sum()))
+
+
+if __name__ == "__main__":
+    main()

@@ -184,17 +184,25 @@ static float orc_dec(float x, float x0, float x1) {
     return 1.0f - (x - x0) / denom;
 }
 
-/* helper_scenario.py:892-957 get_short_term_reference_path (n_points_shift=1) */
-static void orc_short_term(const orc_world *w, int path, int idx, float *out) {
-    const orc_map *m = &w->map;
-    int n = m->n_center[path];
-    const float *poly = m->center + (size_t)path * m->P * 2;
-    for (int k = 0; k < ORC_NST; k++) {
-        int fi = k * w->cfg.sample_interval + idx + 1;    /* :928-932 */
-        if (m->is_loop[path] && fi >= n - 1) fi = (fi + 1) % n; /* :941-946 */
+/* helper_scenario.py:892-957 get_short_term_reference_path on one padded polyline [P][2]:
+ * idx_k = k * interval + idx + shift (:928-932); loops wrap with (idx + 1) % n for idx >= n - 1 (:941-946);
+ * a negative index is python's "from the end" of the P-point array. */
+static void orc_path_points(const float *poly, int P, int n, int is_loop, int idx, int count, int interval, int shift,
+                            float *out) {
+    for (int k = 0; k < count; k++) {
+        int fi = k * interval + idx + shift;
+        if (is_loop && fi >= n - 1) fi = (fi + 1) % n;
+        if (fi < 0) fi += P;
         out[2 * k] = poly[2 * fi];
         out[2 * k + 1] = poly[2 * fi + 1];
     }
+}
+
+/* the agent's short-term reference path: 3 points, sample interval 2, n_points_shift = 1 (world_state_rt.py:668-684) */
+static void orc_short_term(const orc_world *w, int path, int idx, float *out) {
+    const orc_map *m = &w->map;
+    orc_path_points(m->center + (size_t)path * m->P * 2, m->P, m->n_center[path], m->is_loop[path], idx, ORC_NST,
+                    w->cfg.sample_interval, 1, out);
 }
 
 /* world_state_rt.py:689-725: nearing boundary points = get_short_term_reference_path on the PADDED boundary
@@ -202,14 +210,7 @@ static void orc_short_term(const orc_world *w, int path, int idx, float *out) {
  * point count for the loop wrap.  Index -1 is python's "last element" (tail padding = last boundary point). */
 static void orc_nearing_points(const orc_world *w, int path, const float *poly, int idx, int shift, float *out) {
     const orc_map *m = &w->map;
-    int n = m->n_center[path];
-    for (int k = 0; k < ORC_NNB; k++) {
-        int fi = k + idx + shift;
-        if (m->is_loop[path] && fi >= n - 1) fi = (fi + 1) % n;
-        if (fi < 0) fi += m->P;
-        out[2 * k] = poly[2 * fi];
-        out[2 * k + 1] = poly[2 * fi + 1];
-    }
+    orc_path_points(poly, m->P, m->n_center[path], m->is_loop[path], idx, ORC_NNB, 1, shift, out);
 }
 
 /* ---------------------------------------------------------------- world-state updates */
@@ -790,6 +791,13 @@ void *orc_field(orc_world *w, const char *name) {
 /* function-level entry points for known-answer tests */
 float orc_test_perp(const float *p, const float *poly, int P, int n, int *idx) { return orc_perp(p, poly, P, n, idx); }
 int orc_test_interx(const float *L1, int n1, const float *L2, int n2) { return orc_interx(L1, n1, L2, n2); }
+float orc_test_wrap(float a) { return orc_wrap(a); }
+void orc_test_local(const float *pi, float rot_i, const float *pj, float *out) { orc_local(pi, rot_i, pj, out); }
+float orc_test_dec(float x, float x0, float x1) { return orc_dec(x, x0, x1); }
+void orc_test_path_points(const float *poly, int P, int n, int is_loop, int idx, int count, int interval, int shift,
+                          float *out) {
+    orc_path_points(poly, P, n, is_loop, idx, count, interval, shift, out);
+}
 void orc_test_rect(float hl, float hw, const float *pos, float yaw, float *out) {
     orc_cfg c; memset(&c, 0, sizeof c); c.half_length = hl; c.half_width = hw; orc_rect(&c, pos, yaw, out);
 }

@@ -1,0 +1,101 @@
+"""CPU: function-level known-answer tests of the C oracle's primitives against the UNMODIFIED reference helpers
+(``sigmarl/helper_scenario.py``; vectors from ``oracle/gen_kat.py`` -> ``tests/golden/kat/helpers.npz``).
+
+Bit-exact for indices, masks and gathered points; 1e-6 abs for fp32 values that go through libm (glibc here,
+ATen / Sleef in the reference)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+KAT = os.path.join(os.path.dirname(__file__), "golden", "kat", "helpers.npz")
+L, W = 0.22, 0.107
+
+
+@pytest.fixture(scope="module")
+def kat():
+    return np.load(KAT)
+
+
+def _p(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def test_perpendicular_distance_and_argmin(oracle_mod, kat):
+    """helper_scenario.py:829-889 incl. the tail fix-up; on-vertex points tie at distance 0 -> first index."""
+    lib = oracle_mod.lib()
+    poly, n, pts = _p(kat["perp_poly"]), kat["perp_n"], _p(kat["perp_point"])
+    P = poly.shape[1]
+    for k in range(poly.shape[0]):
+        idx = C.c_int()
+        d = lib.orc_test_perp(pts[k].ctypes.data, poly[k].ctypes.data, P, int(n[k]), C.byref(idx))
+        assert idx.value == int(kat["perp_idx"][k]), (k, idx.value, int(kat["perp_idx"][k]))
+        assert abs(d - float(kat["perp_dist"][k])) <= 1e-6, (k, d, float(kat["perp_dist"][k]))
+    assert (kat["perp_dist"][:16] == 0).all()          # the fixture really holds the exact ties
+
+
+def test_rectangle_vertices(oracle_mod, kat):
+    """helper_scenario.py:695-826 (closed, 5 vertices)."""
+    lib = oracle_mod.lib()
+    c, yaw, want = _p(kat["rect_center"]), kat["rect_yaw"], kat["rect_vertices"]
+    out = np.zeros((5, 2), np.float32)
+    worst = 0.0
+    for k in range(c.shape[0]):
+        lib.orc_test_rect(np.float32(L / 2), np.float32(W / 2), c[k].ctypes.data, float(yaw[k]), out.ctypes.data)
+        worst = max(worst, float(np.abs(out - want[k]).max()))
+    assert worst <= 1e-6, worst
+
+
+def test_interx_masks_are_bit_exact(oracle_mod, kat):
+    """helper_scenario.py:1148-1229: strict crossing predicate, incl. identical / touching / collinear rectangles."""
+    lib = oracle_mod.lib()
+    a, b = _p(kat["ix_a"]), _p(kat["ix_b"])
+    got = np.array([lib.orc_test_interx(a[k].ctypes.data, 5, b[k].ctypes.data, 5) for k in range(a.shape[0])], bool)
+    assert np.array_equal(got, kat["ix_rr"]), np.where(got != kat["ix_rr"])[0]
+    r, p = _p(kat["ix_rect"]), _p(kat["ix_poly"])
+    got = np.array([lib.orc_test_interx(r[k].ctypes.data, 5, p[k].ctypes.data, p.shape[1]) for k in range(r.shape[0])], bool)
+    assert np.array_equal(got, kat["ix_rp"]), np.where(got != kat["ix_rp"])[0]
+    assert kat["ix_rr"].sum() > 20 and (~kat["ix_rr"]).sum() > 20 and kat["ix_rp"].sum() > 10
+
+
+def test_angle_wrap(oracle_mod, kat):
+    """helper_scenario.py:1276-1289, incl. +-pi, multiples of 2 pi and the fp32 neighbours of pi."""
+    lib = oracle_mod.lib()
+    got = np.array([lib.orc_test_wrap(float(x)) for x in kat["wrap_in"]], np.float32)
+    assert np.abs(got - kat["wrap_out"]).max() <= 1e-6
+    assert np.array_equal(got[-11:], kat["wrap_out"][-11:])      # the special values bit for bit
+
+
+def test_global_to_local_transform(oracle_mod, kat):
+    """helper_scenario.py:1241-1273."""
+    lib = oracle_mod.lib()
+    pi, pj, rot, want = _p(kat["loc_pi"]), _p(kat["loc_pj"]), kat["loc_rot"], kat["loc_out"]
+    out = np.zeros(2, np.float32)
+    worst = 0.0
+    for k in range(pi.shape[0]):
+        for q in range(pj.shape[1]):
+            lib.orc_test_local(pi[k].ctypes.data, float(rot[k]), pj[k, q].ctypes.data, out.ctypes.data)
+            worst = max(worst, float(np.abs(out - want[k, q]).max()))
+    assert worst <= 2e-6, worst
+
+
+@pytest.mark.parametrize("name,count,interval,shift", [("st", 3, 2, 1), ("nb", 5, 1, -2), ("nbr", 5, 1, 1)])
+def test_short_term_and_nearing_points(oracle_mod, kat, name, count, interval, shift):
+    """helper_scenario.py:892-957 with the three parameterisations the scenario uses: short-term reference path
+    (world_state_rt.py:668-684), nearing boundary points in a step (:686-725) and at a reset (:531-576)."""
+    lib = oracle_mod.lib()
+    poly, n, loop, idx0 = _p(kat["st_poly"]), kat["st_n"], kat["st_loop"], kat["st_idx0"]
+    P = poly.shape[1]
+    out = np.zeros((count, 2), np.float32)
+    for k in range(poly.shape[0]):
+        lib.orc_test_path_points(poly[k].ctypes.data, P, int(n[k]), int(loop[k]), int(idx0[k]), count, interval, shift,
+                                 out.ctypes.data)
+        assert np.array_equal(out, kat[name + "_pts"][k]), (name, k, kat[name + "_idx"][k])
+
+
+def test_decreasing_fcn(oracle_mod, kat):
+    """helper_scenario.py:960-996, linear."""
+    lib = oracle_mod.lib()
+    got = np.array([lib.orc_test_dec(float(x), 0.0, np.float32(0.3)) for x in kat["dec_x"]], np.float32)
+    assert np.abs(got - kat["dec_lin_0_03"]).max() <= 1e-7
