@@ -92,6 +92,23 @@ def main():
         out[name + "_pts"], out[name + "_idx"] = sp, fi
     out.update(st_poly=poly, st_n=n_c, st_loop=is_loop, st_idx0=idx0)
 
+    # ---- structural near-ties: an agent that sits exactly on a centre point (every reset pose, world_state_rt_sim.py:
+    #      215-311) against its lane boundaries — the foot of the perpendicular is next to a boundary vertex, two
+    #      segments are within an ulp of each other and torch.norm's rounding (fma) decides the argmin
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle.oracle import PaddedMap  # noqa: E402  (map layout only: the reference's padded [P,2] polylines)
+    for st in ("cpm_mixed", "on_ramp_2_multilane"):
+        pm = PaddedMap(st)
+        rows = []
+        for p in range(pm.n_paths):
+            for k in range(3, int(pm.n_center[p]) // 2):
+                pt = torch.tensor(pm.center[p, k])
+                for side, arr, cnt in ((0, pm.left, pm.n_left), (1, pm.right, pm.n_right)):
+                    _, i1 = H.get_perpendicular_distances(point=pt.clone(), polyline=torch.tensor(arr[p]),
+                                                          n_points_long_term=torch.tensor(int(cnt[p])))
+                    rows.append((p, k, side, int(i1[0])))
+        out["spawn_idx_" + st] = np.asarray(rows, np.int32)
+
     # ---- decreasing_fcn (:960-996), linear
     x = torch.cat([torch.rand(100) * 0.6 - 0.1, torch.tensor([0.0, 0.3, 0.02])])
     out.update(dec_x=x, dec_lin_0_03=H.decreasing_fcn(x.clone(), torch.tensor(0.0), torch.tensor(0.3), "linear"))

@@ -35,6 +35,23 @@ def test_perpendicular_distance_and_argmin(oracle_mod, kat):
     assert (kat["perp_dist"][:16] == 0).all()          # the fixture really holds the exact ties
 
 
+@pytest.mark.parametrize("st", ["cpm_mixed", "on_ramp_2_multilane"])
+def test_boundary_argmin_at_spawn_poses(oracle_mod, kat, st):
+    """Every reset pose (agent exactly on a centre point) against both lane boundaries: structural near-ties that only
+    torch.norm's exact rounding — sqrt(fma(ey, ey, ex*ex)) — resolves like the reference (plain ex*ex + ey*ey gets
+    4 of the 780 cpm_mixed cases wrong)."""
+    lib = oracle_mod.lib()
+    pm = oracle_mod.PaddedMap(st)
+    rows = kat["spawn_idx_" + st]
+    assert len(rows) > 500
+    for p, k, side, want in rows:
+        arr, cnt = (pm.right, pm.n_right) if side else (pm.left, pm.n_left)
+        idx = C.c_int()
+        lib.orc_test_perp(np.ascontiguousarray(pm.center[p, k]).ctypes.data, np.ascontiguousarray(arr[p]).ctypes.data,
+                          pm.P, int(cnt[p]), C.byref(idx))
+        assert idx.value == want, (st, p, k, side, idx.value, want)
+
+
 def test_rectangle_vertices(oracle_mod, kat):
     """helper_scenario.py:695-826 (closed, 5 vertices)."""
     lib = oracle_mod.lib()
