@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 122
+#define SGB_VERSION 123
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -99,7 +99,12 @@ typedef struct {
     float obs_noise_level;    /* is_obs_noise ? obs_noise_level : 0: obs += level * U[0,1) per element
                                  (observation_provider_rt.py:611-617); device generator, distribution-equivalent */
     uint32_t obs_noise_seed;
-    uint32_t reserved0, reserved1; /* keeps sizeof(sgb_config) a multiple of 16 (kernel-parameter alignment) */
+    int32_t reset_fixed_period; /* reset_agent_fixed_duration as a step period, 0 = off: an env is also done at every
+                                 step with timer.step % period == 0.  The reference tests float32(timer.step * dt) %
+                                 duration == 0 (road_traffic.py:1388-1393); the host layer derives the period from
+                                 (dt, duration) and refuses pairs for which that float test is not periodic
+                                 (EnvConfig.fixed_period) */
+    uint32_t reserved1;       /* keeps sizeof(sgb_config) a multiple of 16 (kernel-parameter alignment) */
 } sgb_config;
 
 /* Observation layout flags == the reference's Parameters of the same meaning (helper_common.py:60-118;

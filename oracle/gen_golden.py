@@ -104,7 +104,17 @@ CONFIGS = {
     "obsvar_on_ramp_2_B4_N6_bpoints_birdview": dict(st="on_ramp_2_multilane", B=4, N=6, T=40, mode="kwargs", seed=27,
                                                    extra=dict(is_observe_distance_to_boundaries=False,
                                                               is_ego_view=False, is_observe_vertices=False)),
+    # reset_agent_fixed_duration (road_traffic.py:1388-1393): envs also end every 2 s (training mode) / 1 s of
+    # simulated time (testing mode, dt 0.1); gentle driving so that the fixed-duration reset is what ends episodes
+    "cpm_entire_B4_N3_fixed2s_gentle": dict(st="cpm_entire", B=4, N=3, T=70, mode="params", seed=41, gentle=True,
+                                           extra=dict(reset_agent_fixed_duration=2)),
+    "cpm_mixed_B4_N3_fixed1s_testing_gentle": dict(st="cpm_mixed", B=4, N=3, T=50, mode="params", seed=42, gentle=True,
+                                                  extra=dict(reset_agent_fixed_duration=1, is_testing_mode=True),
+                                                  max_steps=64),
 }
+
+# fixtures of features added after the last hardware session: tests/golden/next/ (tests/conftest.py)
+NEXT = {"cpm_entire_B4_N3_fixed2s_gentle", "cpm_mixed_B4_N3_fixed1s_testing_gentle"}
 
 OBS_FLAGS = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
              "is_observe_distance_to_agents", "is_observe_distance_to_center_line",
@@ -271,6 +281,8 @@ def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
         norm_pos=float(nrm.pos[0]), norm_v=float(nrm.v), norm_rot=float(nrm.rot),
         norm_distance_lanelet=float(nrm.distance_lanelet),
         is_testing_mode=bool(sc.parameters.is_testing_mode),
+        reset_agent_fixed_duration=float(sc.parameters.reset_agent_fixed_duration),
+        is_use_mtv_distance=bool(sc.parameters.is_use_mtv_distance),
         max_ref_path_points=int(ws.params.max_ref_path_points), gentle=bool(gentle),
         norm_pos_world_x=float(nrm.pos_world[0]), norm_pos_world_y=float(nrm.pos_world[1]),
         norm_distance_agent=float(nrm.distance_agent),
@@ -278,8 +290,9 @@ def run(name, st, B, N, T, mode, seed, extra=None, max_steps=128, gentle=False):
     )
     for k, v in cfg.items():
         out["cfg_" + k] = np.asarray(v)
-    os.makedirs(OUT, exist_ok=True)
-    path = os.path.join(OUT, name + ".npz")
+    out_dir = os.path.join(OUT, "next") if name in NEXT else OUT
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, name + ".npz")
     np.savez_compressed(path, **out)
     print(f"{name}: dones={int(out['done'].sum())} respawns={int(out['respawn_mask'].sum())} "
           f"col_agents={int(out['col_agents'].any(-1).sum())} col_lane={int(out['col_lane'].sum())} "

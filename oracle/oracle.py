@@ -55,7 +55,7 @@ _CFG_INTS = ["rew_exact_sparse", "rew_has_ttc", "rew_has_distance", "rew_has_spa
 class _Cfg(C.Structure):
     _fields_ = ([(n, C.c_float) for n in _CFG_FLOATS] + [(n, C.c_int) for n in _CFG_INTS] +
                 [("reward_reach_goal", C.c_float), ("obs_flags", C.c_int), ("norm_pos_world", C.c_float * 2),
-                 ("norm_dist_agent", C.c_float)])
+                 ("norm_dist_agent", C.c_float), ("fixed_duration", C.c_float), ("use_mtv", C.c_int)])
 
 
 # observation layout flags (ORC_OBS_* in sigmarl_oracle.c) keyed by the reference's parameter names and the value
@@ -215,6 +215,8 @@ def make_cfg(scenario_type, pmap, c):
     cfg.norm_pos_world[0] = float(x)                                               # road_traffic.py:593-595
     cfg.norm_pos_world[1] = float(y)
     cfg.norm_dist_agent = float(f32(AGENT_LENGTH * 10))                            # road_traffic.py:605-607
+    cfg.fixed_duration = float(f32(c.get("fixed_duration", 0.0)))                  # road_traffic.py:1388-1393
+    cfg.use_mtv = int(bool(c.get("use_mtv", False)))                               # road_traffic.py:611-614
     return cfg
 
 
@@ -347,4 +349,6 @@ def config_from_golden(g):
                 norm_dist=float(g["cfg_norm_distance_lanelet"]), rew_method=str(g["cfg_rew_method"]),
                 max_steps=int(g["cfg_max_steps"]), k_near=int(g["cfg_n_nearing_agents_observed"]),
                 testing_mode=bool(g["cfg_is_testing_mode"]),
+                fixed_duration=float(g["cfg_reset_agent_fixed_duration"]) if "cfg_reset_agent_fixed_duration" in g.files else 0.0,
+                use_mtv=bool(g["cfg_is_use_mtv_distance"]) if "cfg_is_use_mtv_distance" in g.files else False,
                 obs_flags=obs_flags_from(lambda n: g["cfg_" + n] if ("cfg_" + n) in g.files else None))

@@ -56,6 +56,8 @@ typedef struct {
     int obs_flags;           /* ORC_OBS_* */
     float norm_pos_world[2]; /* normalizers.pos_world (bird view)   road_traffic.py:593-595 */
     float norm_dist_agent;   /* normalizers.distance_agent          road_traffic.py:605-607 */
+    float fixed_duration;    /* reset_agent_fixed_duration [s], 0 = off   road_traffic.py:1388-1393 */
+    int use_mtv;             /* is_use_mtv_distance: distances.type == "mtv"  road_traffic.py:611-614 */
 } orc_cfg;
 
 #define ORC_OBS_BIRD_VIEW 1       /* is_ego_view = False */
@@ -646,6 +648,10 @@ static void *orc_step_range(void *arg) {
         }
         /* done() road_traffic.py:1368-1487: training mode :1449-1457, testing mode :1429-1447 */
         int any = (w->step[b] == w->cfg.max_steps - 1);
+        if (w->cfg.fixed_duration > 0.0f) {   /* :1388-1393: t = timer.step * dt (int tensor * python float -> fp32) */
+            volatile float t = (float)w->step[b] * w->cfg.dt;
+            any |= (fmodf(t, w->cfg.fixed_duration) == 0.0f) && (t != 0.0f);
+        }
         if (!w->cfg.testing_mode)
             for (int a = 0; a < N; a++) {
                 any |= w->col_lane[AG(b, a)];

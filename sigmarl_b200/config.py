@@ -53,6 +53,7 @@ class EnvConfig:
     exhaustive: bool = False                # debug: disable the pruned search (results must not change)
     is_testing_mode: bool = False           # road_traffic.py:1050-1055, 1429-1447; world_state_rt_sim.py:254-261
     reward_reach_goal: float = 100 / R_P_NORMALIZER   # road_traffic.py:217-219
+    reset_agent_fixed_duration: float = 0   # seconds, 0 = off (helper_common.py:120; road_traffic.py:1388-1393)
     # observation layout (observation_provider_rt.py:594-925): any combination of these seven is supported
     is_ego_view: bool = True                       # False: bird view (global coordinates / pos_world)
     is_observe_vertices: bool = True               # False: pos, rot, length, width of a neighbour
@@ -121,6 +122,31 @@ class EnvConfig:
             k_near=min(self.n_nearing_agents_observed, n - 1),      # road_traffic.py:441-443
         )
 
+    def fixed_period(self, dt: float) -> int:
+        """``reset_agent_fixed_duration`` as a period in steps (0 = off).
+
+        The reference ends an env whenever ``t % duration == 0`` with ``t = timer.step * dt`` evaluated in float32
+        (int tensor times python float, ``road_traffic.py:1388-1393``).  For the usual pairs (dt 0.1 / 0.05, whole
+        seconds) the rounded product is the exact multiple and the test fires at every ``duration / dt``-th step; the
+        kernel takes that period.  The float test is replayed here for every step an episode can reach and any pair
+        for which it is NOT ``step % period == 0`` is refused instead of being approximated."""
+        dur = self.reset_agent_fixed_duration
+        if not dur:
+            return 0
+        if dur < 0:
+            raise ValueError("reset_agent_fixed_duration must be >= 0")
+        steps = np.arange(0, max(int(self.max_steps), 2), dtype=np.int64)
+        t = steps.astype(np.float32) * _f32(dt)                      # fp32 product, rounded once
+        hit = (np.fmod(t, _f32(dur)) == 0) & (t != 0)                # torch.remainder == fmod for positive operands
+        fired = steps[hit]
+        if fired.size == 0:
+            return 0                                                 # never fires before the time limit ends the episode
+        period = int(fired[0])
+        if not np.array_equal(hit, (steps % period == 0) & (steps != 0)):
+            raise NotImplementedError(f"reset_agent_fixed_duration={dur} with dt={dt}: the reference's float32 test fires "
+                                      f"at steps {fired.tolist()[:8]}..., which is not periodic")
+        return period
+
     def lane_width(self, maplib) -> float:
         """Lane width the reference derives normalisers / kwargs-thresholds from.  Quirk reproduced on purpose:
         ``_init_params`` reads ``kwargs.pop("scenario_type", "cpm_entire")`` (road_traffic.py:116-123), so when the
@@ -168,6 +194,7 @@ class EnvConfig:
         c.exhaustive = int(self.exhaustive)
         c.reward_reach_goal = float(_f32(self.reward_reach_goal))
         c.testing_mode = int(bool(self.is_testing_mode))
+        c.reset_fixed_period = self.fixed_period(r["dt"])
         c.obs_flags = self.obs_flags()
         c.norm_pos_world_x, c.norm_pos_world_y = float(x), float(y)            # road_traffic.py:593-595
         c.norm_dist_agent = float(_f32(AGENT_LENGTH * 10))                     # road_traffic.py:605-607

@@ -375,7 +375,7 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     }
     if ((cfg->obs_flags & SGB_OBS_BIRD_VIEW) && !(cfg->norm_pos_world_x > 0.0f && cfg->norm_pos_world_y > 0.0f)) return SGB_ERR_ARG;
     if ((cfg->obs_flags & SGB_OBS_CENTRES) && !(cfg->norm_dist_agent > 0.0f)) return SGB_ERR_ARG;
-    if (!(cfg->obs_noise_level >= 0.0f)) return SGB_ERR_ARG;
+    if (!(cfg->obs_noise_level >= 0.0f) || cfg->reset_fixed_period < 0) return SGB_ERR_ARG;
     Packed pk;
     int rc = pack_map(map, pk);
     if (rc != SGB_OK) return rc;

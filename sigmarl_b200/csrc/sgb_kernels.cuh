@@ -1292,7 +1292,9 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 const int step = p.buf.step_count[e] + 1;          // road_traffic.py:954-962
                 p.buf.step_count[e] = step;
                 // road_traffic.py:1451-1457 (training mode) / :1429-1433 (testing mode: only the time limit ends an env)
-                const bool dn = (step == cfg.max_steps - 1) || (!cfg.testing_mode && (b_hit & em) != 0u);
+                // :1388-1393: reset_agent_fixed_duration (both modes) — periodic in timer.step, see sgb_config
+                const bool dn = (step == cfg.max_steps - 1) || (!cfg.testing_mode && (b_hit & em) != 0u) ||
+                                (cfg.reset_fixed_period > 0 && step % cfg.reset_fixed_period == 0);
                 p.buf.done[e] = dn ? 1 : 0;
             }
         }

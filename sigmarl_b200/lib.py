@@ -48,7 +48,7 @@ class Config(C.Structure):
                  ("respawn_on_exit", C.c_int32), ("exhaustive", C.c_int32), ("reward_reach_goal", C.c_float),
                  ("testing_mode", C.c_int32), ("obs_flags", C.c_uint32), ("norm_pos_world_x", C.c_float),
                  ("norm_pos_world_y", C.c_float), ("norm_dist_agent", C.c_float), ("obs_noise_level", C.c_float),
-                 ("obs_noise_seed", C.c_uint32), ("reserved0", C.c_uint32), ("reserved1", C.c_uint32)])
+                 ("obs_noise_seed", C.c_uint32), ("reset_fixed_period", C.c_int32), ("reserved1", C.c_uint32)])
 
 
 BUFFER_FIELDS = ["pose", "aux", "path_id", "carry", "action", "step_count", "obs", "reward", "done",

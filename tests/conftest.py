@@ -12,9 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_files():
+def golden_files(sub=""):
+    """Fixtures recorded from the unmodified reference.  ``sub="next"``: features added after the last hardware
+    session (reset_agent_fixed_duration, MTV distance) — the oracle is pinned on them here on the CPU; their GPU
+    parity tests live in ``test_gpu_zz_next.py`` so that they run after the hardware-verified suite."""
     import glob
-    return sorted(glob.glob(os.path.join(REPO, "tests", "golden", "*.npz")))
+    return sorted(glob.glob(os.path.join(REPO, "tests", "golden", sub, "*.npz")))
+
+
+def all_golden_files():
+    return golden_files() + golden_files("next")
 
 
 @pytest.fixture(scope="session")

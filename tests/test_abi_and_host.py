@@ -160,3 +160,26 @@ def test_unsupported_flags_fail_loudly():
     assert EnvConfig(scenario_type="cpm_entire", is_testing_mode=True).lower(m).testing_mode == 1   # supported since ABI 110
     with pytest.raises(ValueError):
         MapLibrary("no_such_map")
+
+
+def test_fixed_duration_period_equals_the_references_float_test():
+    """EnvConfig.fixed_period: the step period handed to the kernel fires exactly where the reference's
+    ``(timer.step * dt) % reset_agent_fixed_duration == 0`` does (road_traffic.py:1388-1393, evaluated with torch the
+    way the reference evaluates it: int32 tensor times python float), for every step an episode can reach."""
+    import torch
+    from sigmarl_b200 import EnvConfig, MapLibrary
+    steps = torch.arange(700, dtype=torch.int32)
+    for dt in (0.1, 0.05, 0.04, 0.2, 0.07):
+        for dur in (1, 2, 3, 15, 0.5, 1.5):
+            t = steps * dt
+            want = ((t % dur == 0) & (t != 0)).numpy()
+            period = EnvConfig(max_steps=700, reset_agent_fixed_duration=dur).fixed_period(dt)
+            got = (np.arange(700) % period == 0) & (np.arange(700) != 0) if period else np.zeros(700, bool)
+            assert np.array_equal(got, want), (dt, dur, period)
+    m = MapLibrary("cpm_entire")
+    assert EnvConfig(scenario_type="cpm_entire").lower(m).reset_fixed_period == 0
+    assert EnvConfig(scenario_type="cpm_entire", reset_agent_fixed_duration=2).lower(m).reset_fixed_period == 20
+    assert EnvConfig(scenario_type="cpm_entire", mode="kwargs", reset_agent_fixed_duration=15,
+                     max_steps=600).lower(m).reset_fixed_period == 300      # evaluation_itsc25.py:63-73
+    with pytest.raises(ValueError):
+        EnvConfig(reset_agent_fixed_duration=-1).fixed_period(0.1)

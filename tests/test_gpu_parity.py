@@ -31,6 +31,9 @@ def _obs_flags_of_golden(g):
 def _env_from_golden(g, B=None, **over):
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     over = {**_obs_flags_of_golden(g), **over}
+    for name in ("reset_agent_fixed_duration", "is_use_mtv_distance"):       # fixtures of tests/golden/next/
+        if ("cfg_" + name) in g.files:
+            over.setdefault(name, g["cfg_" + name].item())
     cfg = EnvConfig(
         scenario_type=str(g["cfg_scenario_type"]), n_agents=int(g["cfg_N"]), mode=str(g["cfg_mode"]),
         dt=float(g["cfg_dt"]), max_steps=int(g["cfg_max_steps"]), rew_method=str(g["cfg_rew_method"]),
@@ -641,6 +644,9 @@ def _facade_from_golden(g):
         penalty_near_boundary=float(g["cfg_penalty_near_boundary"]),
         penalty_near_other_agents=float(g["cfg_penalty_near_other_agents"]),
         is_testing_mode=bool(g["cfg_is_testing_mode"]), **_obs_flags_of_golden(g))
+    for name in ("reset_agent_fixed_duration", "is_use_mtv_distance"):       # fixtures of tests/golden/next/
+        if ("cfg_" + name) in g.files:
+            kw[name] = g["cfg_" + name].item()
     if str(g["cfg_mode"]) == "params":     # mappo_cavs.py:168-169: scenario.parameters = parameters; make_world(...)
         p = _Params()
         for k, v in kw.items():

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import golden_files
+from conftest import all_golden_files, golden_files
 
 TOL = 1e-5
 
@@ -66,7 +66,7 @@ def _run(O, path):
     return g
 
 
-@pytest.mark.parametrize("path", golden_files(), ids=lambda p: os.path.basename(p)[:-4])
+@pytest.mark.parametrize("path", all_golden_files(), ids=lambda p: os.path.basename(p)[:-4])
 def test_oracle_matches_reference_teacher_forced(oracle_mod, path):
     g = _run(oracle_mod, path)
     # the fixtures must actually exercise the interesting branches
@@ -88,7 +88,7 @@ def test_oracle_reset_obs_matches_reference(oracle_mod):
     """Obs right after an env reset (all quantities fresh): reference reset_at + observation pass."""
     O = oracle_mod
     n_checked = 0
-    for path in golden_files():
+    for path in all_golden_files():
         g = np.load(path)
         st = str(g["cfg_scenario_type"])
         B, N, T = int(g["cfg_B"]), int(g["cfg_N"]), int(g["cfg_T"])
