@@ -111,10 +111,19 @@ CONFIGS = {
     "cpm_mixed_B4_N3_fixed1s_testing_gentle": dict(st="cpm_mixed", B=4, N=3, T=50, mode="params", seed=42, gentle=True,
                                                   extra=dict(reset_agent_fixed_duration=1, is_testing_mode=True),
                                                   max_steps=64),
+    # MTV agent distance (is_use_mtv_distance; helper_scenario.py:1030-1138, world_state_rt_sim.py:360-396): mutual
+    # distances from LAST step's rectangles, thresholds 0 / agent length, agents "collide" only at distance == 0
+    "mtv_cpm_entire_B4_N6_distance": dict(st="cpm_entire", B=4, N=6, T=40, mode="params", seed=51,
+                                         extra=dict(is_use_mtv_distance=True)),
+    "mtv_cpm_mixed_B4_N5_ttc_sparse_gentle": dict(st="cpm_mixed", B=4, N=5, T=70, mode="params", seed=52, gentle=True,
+                                                 extra=dict(is_use_mtv_distance=True, rew_method="ttc_sparse")),
+    "mtv_roundabout_2_B4_N10_kw_k3": dict(st="roundabout_2", B=4, N=10, T=40, mode="kwargs", seed=53, gentle=True,
+                                         extra=dict(is_use_mtv_distance=True, n_nearing_agents_observed=3)),
 }
 
 # fixtures of features added after the last hardware session: tests/golden/next/ (tests/conftest.py)
-NEXT = {"cpm_entire_B4_N3_fixed2s_gentle", "cpm_mixed_B4_N3_fixed1s_testing_gentle"}
+NEXT = {"cpm_entire_B4_N3_fixed2s_gentle", "cpm_mixed_B4_N3_fixed1s_testing_gentle", "mtv_cpm_entire_B4_N6_distance",
+        "mtv_cpm_mixed_B4_N5_ttc_sparse_gentle", "mtv_roundabout_2_B4_N10_kw_k3"}
 
 OBS_FLAGS = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
              "is_observe_distance_to_agents", "is_observe_distance_to_center_line",

@@ -118,5 +118,34 @@ def main():
           "rect-rect crossings", int(out["ix_rr"].sum()), "rect-poly crossings", int(out["ix_rp"].sum()))
 
 
+def main_mtv():
+    """get_distances_between_agents(distance_type="mtv") (helper_scenario.py:1030-1138) -> tests/golden/kat/mtv.npz:
+    rectangles of vehicle size at random poses from far apart to deeply overlapping, plus identical, edge-touching,
+    corner-touching and parallel-overlapping ones; 6 agents per env so that every call holds 15 pairs."""
+    torch.manual_seed(4321)
+    B, N = 160, 6
+    c = torch.randn(B, 1, 2) * 0.5 + torch.randn(B, N, 2) * torch.linspace(0.02, 0.45, B).reshape(B, 1, 1)
+    yaw = torch.rand(B, N, 1) * 6.28
+    yaw[:40] = (yaw[:40] * 0.05)                                          # near-parallel traffic
+    c[0, 1], yaw[0, 1] = c[0, 0], yaw[0, 0]                               # identical rectangles
+    yaw[1, :2] = 0.0; c[1, 1] = c[1, 0] + torch.tensor([L, 0.0])          # edge-touching, collinear sides
+    yaw[2, :2] = 0.0; c[2, 1] = c[2, 0] + torch.tensor([L, W])            # corner-touching
+    yaw[3, :2] = 0.0; c[3, 1] = c[3, 0] + torch.tensor([0.0, W / 2])      # overlapping, parallel
+    yaw[4, 0] = 0.0; yaw[4, 1] = torch.pi / 2; c[4, 1] = c[4, 0] + torch.tensor([0.05, 0.0])   # crossed
+    v = torch.stack([H.get_rectangle_vertices(center=c[:, a], yaw=yaw[:, a], width=W, length=L, is_close_shape=True)
+                     for a in range(N)], dim=1)                           # [B,N,5,2] like WorldStateRT.vertices
+    d = H.get_distances_between_agents(data=v.clone(), distance_type="mtv", is_set_diagonal=True,
+                                       x_semidim=torch.tensor(4.5), y_semidim=torch.tensor(4.0))
+    out = dict(mtv_vertices=v.numpy(), mtv_dist=d.numpy())
+    path = os.path.join(os.path.dirname(OUT), "mtv.npz")
+    np.savez_compressed(path, **out)
+    off = ~np.eye(N, dtype=bool)
+    print("wrote", path, "pairs", B * N * (N - 1) // 2, "negative", int((d.numpy()[:, off] < 0).sum() // 2),
+          "zero", int((d.numpy()[:, off] == 0).sum() // 2), "min", float(d.min()), "max off-diag", float(d.numpy()[:, off].max()))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["mtv"]:
+        main_mtv()
+    else:
+        main()

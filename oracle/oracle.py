@@ -249,6 +249,8 @@ def lib():
         _lib.orc_test_local.argtypes = [C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         _lib.orc_test_dec.restype = C.c_float
         _lib.orc_test_dec.argtypes = [C.c_float] * 3
+        _lib.orc_test_mtv.restype = C.c_float
+        _lib.orc_test_mtv.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_test_path_points.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_void_p]
     return _lib
 

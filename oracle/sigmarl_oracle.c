@@ -227,9 +227,91 @@ static void orc_nearing_points(const orc_world *w, int path, const float *poly, 
 
 #define AG(b, a) ((size_t)(b) * N + (a))
 
-/* world_state_rt_sim.py:360-373 + helper_scenario.py:1012-1029,1140-1143 (c2c) */
+/* helper_scenario.py:1030-1138: MTV-based ("minimum translation vector") distance between two rectangles given by
+ * their first four vertices [4][2], in the reference's operation order.  Per rectangle the two edge directions
+ * v1-v0, v2-v1 are normalised (:1042-1045); all vertices are projected on the axes of the OTHER rectangle; a vertex
+ * outside the other's projection interval on an axis contributes the (signed) gap on that axis, the per-vertex
+ * distance is the Euclidean norm of its two gaps (:1072-1077); the pair's distance is the smallest of the eight
+ * (:1113-1118).  If any vertex lies strictly inside the other rectangle the distance is minus the smaller of the two
+ * rectangles' smallest projection overlaps (:1079-1084, :1119-1124). */
+static void orc_mtv_axes(const float *v, float ax[2][2]) {
+    for (int k = 0; k < 2; k++) {
+        float dx = v[2 * (k + 1)] - v[2 * k], dy = v[2 * (k + 1) + 1] - v[2 * k + 1];   /* torch.diff :1042 */
+        float n = orc_norm2(dx, dy);                                                     /* torch.norm :1043 */
+        ax[k][0] = dx / n;
+        ax[k][1] = dy / n;
+    }
+}
+
+/* vertices of `va` against the axes `axb` of rectangle `vb`: pos[4] = per-vertex Euclidean gap, *min_overlap =
+ * min over the two axes of the projection overlap, returns 1 if some vertex of a is strictly inside b */
+static int orc_mtv_half(const float *va, const float *vb, float axb[2][2], float pos[4], float *min_overlap) {
+    float pbb[4][2], pab[4][2], mx_b[2], mn_b[2], mx_a[2], mn_a[2];
+    for (int v = 0; v < 4; v++)
+        for (int k = 0; k < 2; k++) {
+            pbb[v][k] = vb[2 * v] * axb[k][0] + vb[2 * v + 1] * axb[k][1];              /* (.*.).sum(dim=3) :1060-1062 */
+            pab[v][k] = va[2 * v] * axb[k][0] + va[2 * v + 1] * axb[k][1];              /* :1066-1068 */
+        }
+    for (int k = 0; k < 2; k++) {
+        mx_b[k] = mn_b[k] = pbb[0][k];
+        mx_a[k] = mn_a[k] = pab[0][k];
+        for (int v = 1; v < 4; v++) {
+            if (pbb[v][k] > mx_b[k]) mx_b[k] = pbb[v][k];
+            if (pbb[v][k] < mn_b[k]) mn_b[k] = pbb[v][k];
+            if (pab[v][k] > mx_a[k]) mx_a[k] = pab[v][k];
+            if (pab[v][k] < mn_a[k]) mn_a[k] = pab[v][k];
+        }
+    }
+    float ov[2];
+    for (int k = 0; k < 2; k++)                                                          /* :1079 */
+        ov[k] = (mx_b[k] < mx_a[k] ? mx_b[k] : mx_a[k]) - (mn_b[k] > mn_a[k] ? mn_b[k] : mn_a[k]);
+    *min_overlap = ov[0] < ov[1] ? ov[0] : ov[1];
+    int inside_any = 0;
+    for (int v = 0; v < 4; v++) {
+        float gap[2];
+        int inside = 1;
+        for (int k = 0; k < 2; k++) {                                                    /* :1072-1076 */
+            float lo = (pab[v][k] - mn_b[k]) * (float)(pab[v][k] <= mn_b[k]);
+            float hi = (mx_b[k] - pab[v][k]) * (float)(pab[v][k] >= mx_b[k]);
+            gap[k] = lo + hi;
+            inside &= (pab[v][k] > mn_b[k]) && (pab[v][k] < mx_b[k]);                    /* :1081-1083 */
+        }
+        pos[v] = orc_norm2(gap[0], gap[1]);                                              /* torch.norm(dim=2) :1077 */
+        /* MTVs_Euclidean_negative = -min_overlap * inside; "negative" iff its absolute value is > 0 (:1119-1121) */
+        if (inside && fabsf(-*min_overlap) > 0.0f) inside_any = 1;
+    }
+    return inside_any;
+}
+
+static float orc_mtv(const float *vi, const float *vj) {
+    float axi[2][2], axj[2][2], pos_ij[4], pos_ji[4], ov_j, ov_i;
+    orc_mtv_axes(vi, axi);
+    orc_mtv_axes(vj, axj);
+    int neg = orc_mtv_half(vi, vj, axj, pos_ij, &ov_j);     /* i's vertices on j's axes */
+    neg |= orc_mtv_half(vj, vi, axi, pos_ji, &ov_i);        /* j's vertices on i's axes */
+    float d = pos_ij[0];
+    for (int v = 1; v < 4; v++) if (pos_ij[v] < d) d = pos_ij[v];
+    for (int v = 0; v < 4; v++) if (pos_ji[v] < d) d = pos_ji[v];
+    if (neg) d = -(ov_j < ov_i ? ov_j : ov_i);                                           /* :1122-1124 */
+    return d;
+}
+
+/* world_state_rt_sim.py:360-373 + helper_scenario.py:1012-1029,1140-1143 (c2c) / :1030-1138 (mtv).  MTV mode reads
+ * the stored rectangles: inside a step they are still LAST step's (update_vertices runs after update_distances,
+ * world_state_rt_sim.py:432-448), after a reset they are fresh (world_state_rt.py:469-475). */
 static void orc_mutual(orc_world *w, int b) {
     int N = w->N;
+    if (w->cfg.use_mtv) {
+        for (int i = 0; i < N; i++) {
+            w->d_agents[(AG(b, i)) * N + i] = w->cfg.diag;
+            for (int j = i + 1; j < N; j++) {
+                float d = orc_mtv(&w->vertices[AG(b, i) * 10], &w->vertices[AG(b, j) * 10]);
+                w->d_agents[(AG(b, i)) * N + j] = d;
+                w->d_agents[(AG(b, j)) * N + i] = d;
+            }
+        }
+        return;
+    }
     for (int i = 0; i < N; i++)
         for (int j = 0; j < N; j++) {
             float dx = w->pos[AG(b, i) * 2] - w->pos[AG(b, j) * 2];
@@ -273,6 +355,9 @@ static void orc_update_collisions(orc_world *w, int b) {
     for (int i = 0; i < N; i++) {
         size_t g = AG(b, i);
         const float *vi = &w->vertices[g * 10];
+        if (w->cfg.use_mtv) {          /* :394-396: agents collide iff their mtv-based distance is exactly zero */
+            for (int j = 0; j < N; j++) w->col_agents[g * N + j] = (uint8_t)(w->d_agents[g * N + j] == 0.0f);
+        } else
         for (int j = i + 1; j < N; j++) {
             if (orc_interx(vi, 5, &w->vertices[AG(b, j) * 10], 5)) {
                 w->col_agents[g * N + j] = 1;
@@ -815,3 +900,5 @@ void orc_test_path_points(const float *poly, int P, int n, int is_loop, int idx,
 void orc_test_rect(float hl, float hw, const float *pos, float yaw, float *out) {
     orc_cfg c; memset(&c, 0, sizeof c); c.half_length = hl; c.half_width = hw; orc_rect(&c, pos, yaw, out);
 }
+/* MTV distance of two rectangles given as [>=4][2] vertex arrays (helper_scenario.py:1030-1138) */
+float orc_test_mtv(const float *vi, const float *vj) { return orc_mtv(vi, vj); }

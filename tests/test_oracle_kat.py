@@ -116,3 +116,22 @@ def test_decreasing_fcn(oracle_mod, kat):
     lib = oracle_mod.lib()
     got = np.array([lib.orc_test_dec(float(x), 0.0, np.float32(0.3)) for x in kat["dec_x"]], np.float32)
     assert np.abs(got - kat["dec_lin_0_03"]).max() <= 1e-7
+
+
+def test_mtv_distance_between_rectangles(oracle_mod):
+    """helper_scenario.py:1030-1138 get_distances_between_agents("mtv") — vectors from ``oracle/gen_kat.py mtv``: 2 400
+    rectangle pairs from far apart to deeply overlapping, incl. identical / touching / crossed ones.  Pure fp32
+    arithmetic (no libm besides sqrt), restated in the reference's operation order: bit-exact, sign and exact zeros
+    ("collision" in MTV mode, world_state_rt_sim.py:394-396) included."""
+    lib = oracle_mod.lib()
+    g = np.load(os.path.join(os.path.dirname(KAT), "mtv.npz"))
+    v, want = _p(g["mtv_vertices"]), g["mtv_dist"]
+    B, N = want.shape[:2]
+    got = np.zeros_like(want)
+    for b in range(B):
+        for i in range(N):
+            for j in range(N):
+                got[b, i, j] = want[b, i, i] if i == j else lib.orc_test_mtv(v[b, i].ctypes.data, v[b, j].ctypes.data)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    off = ~np.eye(N, dtype=bool)
+    assert (want[:, off] < 0).sum() > 500 and (want[:, off] == 0).sum() > 0 and np.array_equal(want, want.transpose(0, 2, 1))
