@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 123
+#define SGB_VERSION 124
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -38,7 +38,7 @@ typedef enum {
     SGB_ERR_CUDA = -2,       /* a CUDA runtime call failed; see sgb_last_error() */
     SGB_ERR_NO_DEVICE = -3,  /* no CUDA device / wrong architecture: there is NO CPU fallback */
     SGB_ERR_MAP = -4,        /* map does not fit in shared memory / malformed polyline */
-    SGB_ERR_UNSUPPORTED = -5 /* config flag outside the hot path (e.g. MTV distance, testing mode) */
+    SGB_ERR_UNSUPPORTED = -5 /* config flag outside the hot path (e.g. unknown observation layout bits) */
 } sgb_status;
 
 /* Flat map: the polylines of `map_manager.py:13-40` / `parse_xml.py:785-797` (one entry per reference
@@ -104,7 +104,12 @@ typedef struct {
                                  duration == 0 (road_traffic.py:1388-1393); the host layer derives the period from
                                  (dt, duration) and refuses pairs for which that float test is not periodic
                                  (EnvConfig.fixed_period) */
-    uint32_t reserved1;       /* keeps sizeof(sgb_config) a multiple of 16 (kernel-parameter alignment) */
+    uint32_t use_mtv_distance; /* is_use_mtv_distance (0 / 1): distances.agents = MTV-based (SAT) distance between the
+                                 agents' rectangles (helper_scenario.py:1030-1138) instead of the centre distance; taken,
+                                 like the reference does, from the rectangles of the PRE-step poses
+                                 (world_state_rt_sim.py:432-448), fresh ones after a reset; agents collide iff it is
+                                 exactly 0 (:394-396).  near_agents_low / high then carry the MTV thresholds
+                                 (road_traffic.py:264-270, 632-648).  sizeof(sgb_config) stays a multiple of 16 */
 } sgb_config;
 
 /* Observation layout flags == the reference's Parameters of the same meaning (helper_common.py:60-118;
@@ -246,6 +251,12 @@ int sgb_gae(int32_t T, int32_t B, int32_t N, const float* reward, const float* v
 int64_t sgb_launch_count(const sgb_ctx* ctx);
 /* Bytes of the packed map blob each CTA stages into shared memory. */
 int64_t sgb_map_bytes(const sgb_ctx* ctx);
+
+/* Arithmetic self-test hook (no device needed, nothing on the product path calls it): the MTV-based distance of two
+ * rectangles given as [4][2] vertex arrays, evaluated by the HOST compilation of the same source function the MTV
+ * kernels use (helper_scenario.py:1030-1138).  tests/test_abi_and_host.py replays the reference's known-answer
+ * vectors through it bit-exactly. */
+float sgb_debug_mtv_distance(const float* vertices_i, const float* vertices_j);
 
 const char* sgb_status_string(int status);
 const char* sgb_last_error(void); /* text of the last CUDA error seen by this thread */

@@ -65,8 +65,12 @@ class EnvConfig:
     is_obs_noise: bool = False                     # obs += obs_noise_level * U[0,1) (device generator)
     obs_noise_level: Optional[float] = None        # None -> 0.05 (params, helper_common.py:77) / 0.2 * width (kwargs, :337-339)
     obs_noise_seed: int = 0
-    # flags of the reference that select code OUTSIDE the supported hot path; must keep these values
+    # agent distance (road_traffic.py:611-614): False = centre to centre, True = MTV-based (SAT) distance between the
+    # rectangles (helper_scenario.py:1030-1138) with its own thresholds (road_traffic.py:264-270; same in both modes)
     is_use_mtv_distance: bool = False
+    threshold_near_other_agents_MTV_low: float = 0.0
+    threshold_near_other_agents_MTV_high: float = AGENT_LENGTH
+    # flags of the reference that select code OUTSIDE the supported hot path; must keep these values
     is_partial_observation: bool = True            # False crashes in the reference itself (:808)
     is_apply_mask: bool = False
     extras: dict = field(default_factory=dict)
@@ -74,7 +78,7 @@ class EnvConfig:
     def validate(self):
         if self.rew_method not in _REW_METHODS:
             raise NotImplementedError(f"rew_method {self.rew_method!r}: supported {_REW_METHODS} (cbf variants are out of scope)")
-        want = dict(is_use_mtv_distance=False, is_partial_observation=True, is_apply_mask=False)
+        want = dict(is_partial_observation=True, is_apply_mask=False)
         for k, v in want.items():
             if getattr(self, k) != v:
                 raise NotImplementedError(f"{k}={getattr(self, k)} selects a non-default observation/reset variant "
@@ -108,14 +112,18 @@ class EnvConfig:
                      na_high=AGENT_LENGTH + AGENT_WIDTH, na_low=(AGENT_LENGTH + AGENT_WIDTH) / 2,
                      ttc_low=0.0, ttc_high=3.75, pen_nb=-20 / R_P_NORMALIZER, pen_na=-20 / R_P_NORMALIZER)
         n = self.n_agents or default_n_agents
+        if self.is_use_mtv_distance:                       # road_traffic.py:632-648
+            na_high, na_low = self.threshold_near_other_agents_MTV_high, self.threshold_near_other_agents_MTV_low
+        else:
+            na_high = pick(self.threshold_near_other_agents_c2c_high, d["na_high"])
+            na_low = pick(self.threshold_near_other_agents_c2c_low, d["na_low"])
         return dict(
             n_agents=n,
             dt=pick(self.dt, d["dt"]),
             reward_progress=pick(self.reward_progress, d["reward_progress"]),
             nb_high=pick(self.threshold_near_boundary_high, d["nb_high"]),
             nb_low=pick(self.threshold_near_boundary_low, d["nb_low"]),
-            na_high=pick(self.threshold_near_other_agents_c2c_high, d["na_high"]),
-            na_low=pick(self.threshold_near_other_agents_c2c_low, d["na_low"]),
+            na_high=na_high, na_low=na_low,
             ttc_low=pick(self.ttc_low, d["ttc_low"]), ttc_high=pick(self.ttc_high, d["ttc_high"]),
             pen_nb=pick(self.penalty_near_boundary, d["pen_nb"]),
             pen_na=pick(self.penalty_near_other_agents, d["pen_na"]),
@@ -195,6 +203,7 @@ class EnvConfig:
         c.reward_reach_goal = float(_f32(self.reward_reach_goal))
         c.testing_mode = int(bool(self.is_testing_mode))
         c.reset_fixed_period = self.fixed_period(r["dt"])
+        c.use_mtv_distance = int(bool(self.is_use_mtv_distance))
         c.obs_flags = self.obs_flags()
         c.norm_pos_world_x, c.norm_pos_world_y = float(x), float(y)            # road_traffic.py:593-595
         c.norm_dist_agent = float(_f32(AGENT_LENGTH * 10))                     # road_traffic.py:605-607

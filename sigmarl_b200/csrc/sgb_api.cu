@@ -30,7 +30,7 @@ struct sgb_ctx {
     int32_t num_sms = 0;
     int32_t max_smem_optin = 0;
     int64_t launches = 0;
-    size_t smem_configured[4][3] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G> on this device
+    size_t smem_configured[6][3] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G> on this device
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // sgb_step_host: chunked copy/compute pipeline
     cudaEvent_t pipe_event[2] = {nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
@@ -51,6 +51,12 @@ static int cuda_fail(cudaError_t e, const char* what) {
 
 extern "C" const char* sgb_last_error(void) { return g_err; }
 extern "C" int sgb_version(void) { return SGB_VERSION; }
+extern "C" float sgb_debug_mtv_distance(const float* vi, const float* vj) {
+    // HOST build of the very source the MTV kernels compile (mtv_from_vertices): arithmetic self-test without a GPU
+    float ax[4], ay[4], bx[4], by[4];
+    for (int k = 0; k < 4; k++) { ax[k] = vi[2 * k]; ay[k] = vi[2 * k + 1]; bx[k] = vj[2 * k]; by[k] = vj[2 * k + 1]; }
+    return sgb::mtv_from_vertices(ax, ay, bx, by);
+}
 extern "C" const char* sgb_status_string(int s) {
     switch (s) {
         case SGB_OK: return "ok";
@@ -243,7 +249,9 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int envs_per_warp = 32 / (p.N * G);
     if (envs_per_warp < 1) return SGB_ERR_ARG;
     const int n_wt = (p.B + envs_per_warp - 1) / envs_per_warp;   // upper bound (a list may hold fewer envs)
-    const size_t smem = ((size_t)ctx->blob_bytes + 127) / 128 * 128 + tile_smem_bytes(slots, p.N) + 128;
+    // OV 2 (MTV distance) keeps cos / sin of the pre-step heading per slot behind dij
+    const size_t smem = ((size_t)ctx->blob_bytes + 127) / 128 * 128 + tile_smem_bytes(slots, p.N) + 128 +
+                        (OV == 2 ? 2 * sizeof(float) * (size_t)slots : 0);
     if ((int64_t)smem > ctx->max_smem_optin) {
         snprintf(g_err, sizeof g_err, "map blob %d B + tile arrays need %zu B of shared memory, device offers %d B",
                  ctx->blob_bytes, smem, ctx->max_smem_optin);
@@ -292,6 +300,8 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.r_v = 1.0f / ctx->cfg.norm_v;
     p.r_dist = 1.0f / ctx->cfg.norm_dist;
     const int g = pick_group(N);
+    // MTV agent distance: its own instantiation (flag-driven writer + SAT distance in phase C1)
+    if (p.cfg.use_mtv_distance) return mode == 0 ? launch_env_group<0, 2>(ctx, p, st, g) : launch_env_group<1, 2>(ctx, p, st, g);
     // the default observation layout runs the hard-wired (tuned) writer, any other one the flag-driven writer
     if (p.cfg.obs_flags == 0 && !(p.cfg.obs_noise_level > 0.0f)) return mode == 0 ? launch_env_group<0, 0>(ctx, p, st, g) : launch_env_group<1, 0>(ctx, p, st, g);
     return mode == 0 ? launch_env_group<0, 1>(ctx, p, st, g) : launch_env_group<1, 1>(ctx, p, st, g);
@@ -375,7 +385,7 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     }
     if ((cfg->obs_flags & SGB_OBS_BIRD_VIEW) && !(cfg->norm_pos_world_x > 0.0f && cfg->norm_pos_world_y > 0.0f)) return SGB_ERR_ARG;
     if ((cfg->obs_flags & SGB_OBS_CENTRES) && !(cfg->norm_dist_agent > 0.0f)) return SGB_ERR_ARG;
-    if (!(cfg->obs_noise_level >= 0.0f) || cfg->reset_fixed_period < 0) return SGB_ERR_ARG;
+    if (!(cfg->obs_noise_level >= 0.0f) || cfg->reset_fixed_period < 0 || cfg->use_mtv_distance > 1u) return SGB_ERR_ARG;
     Packed pk;
     int rc = pack_map(map, pk);
     if (rc != SGB_OK) return rc;

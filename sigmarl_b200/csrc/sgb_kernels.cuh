@@ -129,12 +129,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 // Separately-rounded fp32 operations (never contracted into FMA).  The file is compiled with FMA contraction ON;
 // every value that feeds an argmin, a strict-sign predicate or the integrated state is written with these so
 // that it rounds exactly like the reference's one-ATen-op-at-a-time evaluation.
-__device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
+#ifdef __CUDA_ARCH__
+#define SGB_UNROLL _Pragma("unroll")
+#else
+#define SGB_UNROLL
+#endif
+// (__host__ too: the host build of the same source backs the arithmetic self-test hook sgb_debug_mtv_distance; the host
+// compiler runs with -ffp-contract=off, so the plain expressions round separately there as well.)
+#ifdef __CUDA_ARCH__
+__host__ __device__ __forceinline__ float mulr(float a, float b) { return __fmul_rn(a, b); }
+__host__ __device__ __forceinline__ float addr(float a, float b) { return __fadd_rn(a, b); }
+__host__ __device__ __forceinline__ float subr(float a, float b) { return __fsub_rn(a, b); }
+__host__ __device__ __forceinline__ float fmar(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__host__ __device__ __forceinline__ float divr(float a, float b) { return __fdiv_rn(a, b); }
+#else
+__host__ __device__ __forceinline__ float mulr(float a, float b) { return a * b; }
+__host__ __device__ __forceinline__ float addr(float a, float b) { return a + b; }
+__host__ __device__ __forceinline__ float subr(float a, float b) { return a - b; }
+__host__ __device__ __forceinline__ float fmar(float a, float b, float c) { return fmaf(a, b, c); }
+__host__ __device__ __forceinline__ float divr(float a, float b) { return a / b; }
+#endif
 // a*b - c*d and a*b + c*d with three roundings
-__device__ __forceinline__ float msub2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
-__device__ __forceinline__ float madd2(float a, float b, float c, float d) { return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+__host__ __device__ __forceinline__ float msub2(float a, float b, float c, float d) { return subr(mulr(a, b), mulr(c, d)); }
+__host__ __device__ __forceinline__ float madd2(float a, float b, float c, float d) { return addr(mulr(a, b), mulr(c, d)); }
 
 __device__ __noinline__ void sincos_ool(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
 __device__ __noinline__ float tan_ool(float x) { return tanf(x); }
@@ -306,6 +323,79 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
         for (int i = 0; i < 4; i++) hit |= (((g[i] * g[(i + 1) & 3]) < 0.0f) & (((c1 >> (4 * i + j)) & 1u) != 0u));
     }
     return hit;
+}
+
+// MTV-based distance between two rectangles (is_use_mtv_distance; helper_scenario.py:1030-1138), in the reference's  @region mtv
+// operation order with every product / sum rounded on its own (the file compiles with FMA contraction on).  Per
+// rectangle the two edge directions v1-v0, v2-v1 are normalised (:1042-1045); the vertices of a are projected on the
+// axes of b; outside b's projection interval a vertex contributes its signed gap on that axis, its distance is the
+// norm of the two gaps (torch.norm: sqrt(fma(g1, g1, g0*g0)), see seg_q) (:1072-1077).  A vertex strictly inside b
+// makes the pair's distance negative: minus the smallest projection overlap (:1079-1084, :1119-1124).
+__host__ __device__ __forceinline__ void mtv_half(const float* ax, const float* ay, const float* bx, const float* by,
+                                         float& pos_min, float& ov_min, bool& neg) {
+    float ux[2], uy[2], mnb[2], mxb[2];
+SGB_UNROLL
+    for (int k = 0; k < 2; k++) {
+        const float dx = subr(bx[k + 1], bx[k]), dy = subr(by[k + 1], by[k]);             // torch.diff :1042
+        const float n = sqrtf(fmar(dy, dy, mulr(dx, dx)));                                // torch.norm :1043
+        ux[k] = divr(dx, n);
+        uy[k] = divr(dy, n);
+        float mna = 0.0f, mxa = 0.0f;
+SGB_UNROLL
+        for (int v = 0; v < 4; v++) {
+            const float pb = madd2(bx[v], ux[k], by[v], uy[k]);                           // (.*.).sum(dim=3) :1060-1068
+            const float pa = madd2(ax[v], ux[k], ay[v], uy[k]);
+            if (v == 0) { mnb[k] = mxb[k] = pb; mna = mxa = pa; }
+            else { mnb[k] = fminf(mnb[k], pb); mxb[k] = fmaxf(mxb[k], pb); mna = fminf(mna, pa); mxa = fmaxf(mxa, pa); }
+        }
+        const float ov = subr(fminf(mxb[k], mxa), fmaxf(mnb[k], mna));                    // :1079
+        ov_min = (k == 0) ? ov : fminf(ov_min, ov);
+    }
+SGB_UNROLL
+    for (int v = 0; v < 4; v++) {
+        float gap[2];
+        bool inside = true;
+SGB_UNROLL
+        for (int k = 0; k < 2; k++) {
+            const float pa = madd2(ax[v], ux[k], ay[v], uy[k]);                           // same ops as above: same value
+            const float lo = (pa <= mnb[k]) ? subr(pa, mnb[k]) : 0.0f;                    // :1072-1076
+            const float hi = (pa >= mxb[k]) ? subr(mxb[k], pa) : 0.0f;
+            gap[k] = addr(lo, hi);
+            inside = inside && (pa > mnb[k]) && (pa < mxb[k]);                            // :1081-1083
+        }
+        const float d = sqrtf(fmar(gap[1], gap[1], mulr(gap[0], gap[0])));                // torch.norm(dim=2) :1077
+        pos_min = fminf(pos_min, d);
+        neg = neg || (inside && fabsf(ov_min) > 0.0f);                                    // (-overlap * inside).abs() > 0
+    }
+}
+
+// rectangle of a pose exactly as phase A builds it (get_rectangle_vertices, helper_scenario.py:742-826)
+__host__ __device__ __forceinline__ void rect_of_pose(float x, float y, float cy, float sy, float hl, float hw, float* vx, float* vy) {
+    const float nsy = -sy;
+    const float bxs[4] = {hl, hl, -hl, -hl};
+    const float bys[4] = {hw, -hw, -hw, hw};
+SGB_UNROLL
+    for (int k = 0; k < 4; k++) {
+        vx[k] = addr(madd2(cy, bxs[k], nsy, bys[k]), x);
+        vy[k] = addr(madd2(sy, bxs[k], cy, bys[k]), y);
+    }
+}
+
+__host__ __device__ __forceinline__ float mtv_from_vertices(const float* ax, const float* ay, const float* bx, const float* by) {
+    float pos_min = 3.402823466e38f, ov_j, ov_i;    // every per-vertex distance is finite
+    bool neg = false;
+    mtv_half(ax, ay, bx, by, pos_min, ov_j, neg);   // i's vertices on j's axes
+    mtv_half(bx, by, ax, ay, pos_min, ov_i, neg);   // j's vertices on i's axes
+    return neg ? -fminf(ov_j, ov_i) : pos_min;      // :1113-1124
+}
+
+// out of line: called from the MTV instantiations only, keeps their register allocation at the level of the others
+__device__ __noinline__ float mtv_distance(float xi, float yi, float ci, float si, float xj, float yj, float cj, float sj,
+                                           float hl, float hw) {
+    float ax[4], ay[4], bx[4], by[4];
+    rect_of_pose(xi, yi, ci, si, hl, hw, ax, ay);
+    rect_of_pose(xj, yj, cj, sj, hl, hw, bx, by);
+    return mtv_from_vertices(ax, ay, bx, by);
 }
 
 // @region group shuffles
@@ -623,7 +713,9 @@ __host__ __device__ inline int obs_dim_of(uint32_t fl, int k_near) {
 // apart and overlap their ALU / MUFU / shared-memory phases.
 // MODE 0 = step, MODE 1 = refresh (rebuild carry / observation from the current pose; no dynamics, no reward).
 // OV 0 = the reference's default observation layout (hard-wired, the tuned path), OV 1 = layout assembled from
-// cfg.obs_flags (write_obs_general); everything else is the same code.
+// cfg.obs_flags (write_obs_general); everything else is the same code.  OV 2 = OV 1 + the MTV agent distance
+// (cfg.use_mtv_distance): distances.agents from the PRE-step rectangles instead of centre distances, agents collide
+// iff that distance is exactly zero, no interX between rectangles (world_state_rt_sim.py:360-396).
 template <int G, int MODE, int OV>
 __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -633,6 +725,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
     const int N = p.N, D = p.D;
     const sgb_config& cfg = p.cfg;
     constexpr bool step_mode = (MODE == 0);
+    constexpr bool MTV = (OV == 2);
     // closest-index part of carry.w (the flag-driven layouts may keep a history bit above it, see kCarryFreshBit)
     auto idx_of = [](float w) { return __float_as_int(w) & kCarryIdxMask; };   // (used by the OV = 1 instantiations only)
     const bool bpoints = OV != 0 && (p.cfg.obs_flags & SGB_OBS_BOUNDARY_POINTS) != 0;
@@ -668,6 +761,9 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
     TileSmem ts;
     carve_tile<AS>(smem, ts);
     ts.dij = reinterpret_cast<float*>(blob_s + ((p.blob_bytes + 127) & ~127));
+    // MTV only: cos / sin of the PRE-step heading per slot, behind dij (the default layout of the slot arrays is untouched)
+    float* const ocs_a = ts.dij + (size_t)AS * p.N;
+    float* const osn_a = ocs_a + AS;
 
     const int w = tid >> 5, ln = tid & 31;
     const int slot0 = w * SPW;                  // first slot of this warp
@@ -721,6 +817,11 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 float x = pose.x, y = pose.y, psi = pose.z, v = pose.w;
                 ts.ox[st] = x;
                 ts.oy[st] = y;
+                if (MTV) {   // rectangle the reference still holds when it updates the mutual distances (pre-step pose)
+                    float osy, ocy;
+                    sincos_ool(psi, &osy, &ocy);
+                    ocs_a[st] = ocy; osn_a[st] = osy;
+                }
                 if (step_mode) {
                     // helper_training.py:807-836
                     float2 u = reinterpret_cast<const float2*>(p.buf.action)[g];
@@ -891,7 +992,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
         // ---- rectangle-rectangle crossings: the N(N-1)/2 unordered pairs of an env are dealt round-robin to  @region pairs
         //      the env's N*G lanes; interX(vertices[lo], vertices[hi]) with lo < hi exactly as
         //      world_state_rt_sim.py:384-393, result OR-ed into both agents' masks
-        if (step_mode && ln < EW * env_lanes) {
+        if (step_mode && !MTV && ln < EW * env_lanes) {
             const int el = ln / env_lanes;             // env within the warp
             const int q = ln - el * env_lanes;         // lane within the env
             const int sbase = slot0 + el * N;
@@ -935,7 +1036,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             const int i = slot_ok ? i_of_lane : 0;   // (sl - slot0) % N, hoisted out of the tile loop
             const int base = sl - i; // slot of agent 0 of this env
             const float pix = ts.px[sl], piy = ts.py[sl];
-            const uint32_t coll = (uint32_t)ts.coll[sl];
+            uint32_t coll = MTV ? 0u : (uint32_t)ts.coll[sl];
             float ttc_sum = 0.0f, near_sum = 0.0f;
             // ---- C1: the lanes of the group split the other agents j ----
             if (slot_ok) {
@@ -945,6 +1046,12 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                     const float dx = pix - pjx, dy = piy - pjy;
                     const float pp = madd2(dx, dx, dy, dy);
                     float dist = (j == i) ? cfg.diag : sqrtf(pp);  // helper_scenario.py:1012-1029, :1140-1143
+                    if (MTV && j != i) {
+                        // helper_scenario.py:1030-1138 on the rectangles of the pre-step poses (== current ones in a refresh)
+                        dist = mtv_distance(ts.ox[sl], ts.oy[sl], ocs_a[sl], osn_a[sl], ts.ox[sj], ts.oy[sj], ocs_a[sj], osn_a[sj],
+                                            cfg.half_length, cfg.half_width);
+                        if (step_mode && dist == 0.0f) coll |= 1u << j;   // world_state_rt_sim.py:394-396
+                    }
                     ts.dij[sl * N + j] = dist;
                     if (!step_mode) continue;
                     near_sum += dec_lin(dist, cfg.near_agents_low, cfg.near_agents_high);
@@ -974,6 +1081,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             }
             ttc_sum = group_sum<G>(ttc_sum);
             near_sum = group_sum<G>(near_sum);
+            if (MTV) coll = group_or<G>(coll);
             __syncwarp(); // dij of this group is complete
 
             // ---- C2: every lane of the group picks the k nearest (same result in all lanes);  @region C2 topk+obs

@@ -19,7 +19,7 @@ CARRY_IDX_MASK, CARRY_FRESH_BIT = 0x3fffffff, 0x40000000   # carry.w with SGB_OB
 # every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
-           "sgb_status_string", "sgb_last_error", "sgb_version"]
+           "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance"]
 
 
 class SgbError(RuntimeError):
@@ -48,7 +48,7 @@ class Config(C.Structure):
                  ("respawn_on_exit", C.c_int32), ("exhaustive", C.c_int32), ("reward_reach_goal", C.c_float),
                  ("testing_mode", C.c_int32), ("obs_flags", C.c_uint32), ("norm_pos_world_x", C.c_float),
                  ("norm_pos_world_y", C.c_float), ("norm_dist_agent", C.c_float), ("obs_noise_level", C.c_float),
-                 ("obs_noise_seed", C.c_uint32), ("reset_fixed_period", C.c_int32), ("reserved1", C.c_uint32)])
+                 ("obs_noise_seed", C.c_uint32), ("reset_fixed_period", C.c_int32), ("use_mtv_distance", C.c_uint32)])
 
 
 BUFFER_FIELDS = ["pose", "aux", "path_id", "carry", "action", "step_count", "obs", "reward", "done",
@@ -98,6 +98,8 @@ def load_library():
     L.sgb_status_string.restype = C.c_char_p
     L.sgb_last_error.restype = C.c_char_p
     L.sgb_version.restype = C.c_int
+    L.sgb_debug_mtv_distance.argtypes = [vp, vp]
+    L.sgb_debug_mtv_distance.restype = C.c_float
     _lib = L
     return L
 

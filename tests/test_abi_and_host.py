@@ -145,7 +145,7 @@ def test_config_matches_reference_constants_in_goldens():
 def test_unsupported_flags_fail_loudly():
     from sigmarl_b200 import EnvConfig, MapLibrary
     m = MapLibrary("cpm_entire")
-    for kw in (dict(is_use_mtv_distance=True), dict(rew_method="cbf"), dict(is_apply_mask=True),
+    for kw in (dict(rew_method="cbf"), dict(is_apply_mask=True),
                dict(is_partial_observation=False)):
         with pytest.raises(NotImplementedError):
             EnvConfig(scenario_type="cpm_entire", **kw).lower(m)
@@ -158,6 +158,12 @@ def test_unsupported_flags_fail_loudly():
     assert abs(low.obs_noise_level - 0.05) < 1e-7 and c.obs_dim(4) == (5 + 1 + 6 + 1 + 20) + 2 * (8 + 2 + 1 + 1)
     assert EnvConfig(scenario_type="cpm_entire").lower(m).obs_flags == 0 and EnvConfig().obs_dim(8) == 32
     assert EnvConfig(scenario_type="cpm_entire", is_testing_mode=True).lower(m).testing_mode == 1   # supported since ABI 110
+    # MTV agent distance (ABI 124): its own thresholds (road_traffic.py:264-270, 632-648) in both construction modes
+    for mode in ("params", "kwargs"):
+        low = EnvConfig(scenario_type="cpm_entire", mode=mode, is_use_mtv_distance=True).lower(m)
+        assert low.use_mtv_distance == 1 and low.near_agents_low == 0.0 and low.dsafe_sq == 0.0
+        assert low.near_agents_high == float(np.float32(0.22))
+    assert EnvConfig(scenario_type="cpm_entire").lower(m).use_mtv_distance == 0
     with pytest.raises(ValueError):
         MapLibrary("no_such_map")
 
@@ -183,3 +189,22 @@ def test_fixed_duration_period_equals_the_references_float_test():
                      max_steps=600).lower(m).reset_fixed_period == 300      # evaluation_itsc25.py:63-73
     with pytest.raises(ValueError):
         EnvConfig(reset_agent_fixed_duration=-1).fixed_period(0.1)
+
+
+def test_kernel_mtv_source_matches_reference_vectors_on_the_host():
+    """sgb_debug_mtv_distance = the HOST compilation of the source function the MTV kernels use (sgb_kernels.cuh,
+    mtv_from_vertices; every product / sum rounded on its own on both sides): bit-exact against the reference's
+    get_distances_between_agents("mtv") on the 2 400 known-answer pairs — sign, exact zeros and symmetry included.
+    Arithmetic self-test only; the kernel path itself is covered by the -m gpu tests."""
+    from sigmarl_b200.lib import load_library
+    L = load_library()
+    g = np.load(os.path.join(REPO, "tests", "golden", "kat", "mtv.npz"))
+    v, want = np.ascontiguousarray(g["mtv_vertices"][:, :, :4], np.float32), g["mtv_dist"]
+    B, N = want.shape[:2]
+    got = want.copy()
+    for b in range(B):
+        for i in range(N):
+            for j in range(N):
+                if i != j:
+                    got[b, i, j] = L.sgb_debug_mtv_distance(v[b, i].ctypes.data, v[b, j].ctypes.data)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -151,10 +151,16 @@ def test_cuda_reset_obs_matches_reference(path):
 
 
 def _oracle_for(env, O, rew_method, mode):
+    over = {}
+    if env.config.is_use_mtv_distance:     # MTV thresholds, road_traffic.py:264-270, 632-648
+        over.update(use_mtv=True, na_low=env.config.threshold_near_other_agents_MTV_low,
+                    na_high=env.config.threshold_near_other_agents_MTV_high)
+    if env.config.reset_agent_fixed_duration:
+        over.update(fixed_duration=env.config.reset_agent_fixed_duration)
     return O.OracleWorld(env.config.scenario_type, env.B, env.N, mode=mode, rew_method=rew_method,
                          n_nearing_agents_observed=env.config.n_nearing_agents_observed,
                          max_steps=env.config.max_steps,
-                         obs_flags=O.obs_flags_from(lambda n: getattr(env.config, n)))
+                         obs_flags=O.obs_flags_from(lambda n: getattr(env.config, n)), **over)
 
 
 @pytest.mark.parametrize("scenario,N,rew,mode,B", [
