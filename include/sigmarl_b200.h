@@ -258,6 +258,11 @@ int64_t sgb_map_bytes(const sgb_ctx* ctx);
  * vectors through it bit-exactly. */
 float sgb_debug_mtv_distance(const float* vertices_i, const float* vertices_j);
 
+/* Host-only part of sgb_create (no device needed): validates and packs a map exactly as sgb_create would and reports
+ * the size of the blob every CTA stages into shared memory (SGB_ERR_MAP for a degenerate polyline or one with more
+ * than 256 segments).  Lets a build machine without a GPU check that every shipped map is accepted. */
+int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes);
+
 const char* sgb_status_string(int status);
 const char* sgb_last_error(void); /* text of the last CUDA error seen by this thread */
 int sgb_version(void);

@@ -119,11 +119,26 @@ CONFIGS = {
                                                  extra=dict(is_use_mtv_distance=True, rew_method="ttc_sparse")),
     "mtv_roundabout_2_B4_N10_kw_k3": dict(st="roundabout_2", B=4, N=10, T=40, mode="kwargs", seed=53, gentle=True,
                                          extra=dict(is_use_mtv_distance=True, n_nearing_agents_observed=3)),
+    # the remaining maps of constants.py (interchange_1-3, intersection_2-8): open paths, entry / exit respawns
+    "map_interchange_1_B4_N4": dict(st="interchange_1", B=4, N=4, T=40, mode="kwargs", seed=61, gentle=True),
+    "map_interchange_2_B4_N6": dict(st="interchange_2", B=4, N=6, T=40, mode="params", seed=62, gentle=True,
+                                   extra=dict(rew_method="ttc_sparse")),
+    "map_interchange_3_B4_N6": dict(st="interchange_3", B=4, N=6, T=30, mode="kwargs", seed=63),
+    "map_intersection_2_B4_N3": dict(st="intersection_2", B=4, N=3, T=40, mode="params", seed=64, gentle=True),
+    "map_intersection_3_B4_N4": dict(st="intersection_3", B=4, N=4, T=30, mode="kwargs", seed=65),
+    "map_intersection_4_B4_N4": dict(st="intersection_4", B=4, N=4, T=40, mode="params", seed=66, gentle=True,
+                                    extra=dict(rew_method="distance_sparse")),
+    "map_intersection_5_B4_N5": dict(st="intersection_5", B=4, N=5, T=30, mode="kwargs", seed=67),
+    "map_intersection_6_B4_N5": dict(st="intersection_6", B=4, N=5, T=40, mode="params", seed=68, gentle=True),
+    "map_intersection_7_B4_N4": dict(st="intersection_7", B=4, N=4, T=30, mode="kwargs", seed=69),
+    "map_intersection_8_B4_N4": dict(st="intersection_8", B=4, N=4, T=40, mode="params", seed=70, gentle=True,
+                                    extra=dict(rew_method="ttc")),
 }
 
 # fixtures of features added after the last hardware session: tests/golden/next/ (tests/conftest.py)
 NEXT = {"cpm_entire_B4_N3_fixed2s_gentle", "cpm_mixed_B4_N3_fixed1s_testing_gentle", "mtv_cpm_entire_B4_N6_distance",
         "mtv_cpm_mixed_B4_N5_ttc_sparse_gentle", "mtv_roundabout_2_B4_N10_kw_k3"}
+NEXT |= {n for n in CONFIGS if n.startswith("map_")}
 
 OBS_FLAGS = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
              "is_observe_distance_to_agents", "is_observe_distance_to_center_line",

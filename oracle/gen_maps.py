@@ -34,15 +34,7 @@ from sigmarl.constants import SCENARIOS  # noqa: E402
 from sigmarl.map_manager import MapManager  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "sigmarl_b200", "maps")
-SCENARIO_TYPES = [
-    "cpm_entire",
-    "cpm_mixed",
-    "intersection_1",
-    "on_ramp_1",
-    "on_ramp_2_multilane",
-    "roundabout_1",
-    "roundabout_2",
-]
+SCENARIO_TYPES = list(SCENARIOS)   # every scenario_type of constants.py:8-626 (17 maps + pseudo_distance_example)
 OSM_LANE_WIDTH = 0.25  # Parameters.lane_width default (helper_common.py:119)
 
 
@@ -95,4 +87,6 @@ def main():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:]:
+        SCENARIO_TYPES = sys.argv[1:]
     main()

@@ -368,6 +368,13 @@ int build_spawn_table(sgb_ctx* c, const Packed& pk) {
 } // namespace
 
 // ---- C-ABI ---------------------------------------------------------------------------------------------
+extern "C" int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes) {
+    Packed pk;
+    const int rc = pack_map(map, pk);
+    if (blob_bytes) *blob_bytes = rc == SGB_OK ? (int64_t)pk.blob.size() : 0;
+    return rc;
+}
+
 extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, const sgb_config* cfg) {
     if (!out || !map || !cfg) return SGB_ERR_ARG;
     *out = nullptr;

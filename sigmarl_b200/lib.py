@@ -19,7 +19,7 @@ CARRY_IDX_MASK, CARRY_FRESH_BIT = 0x3fffffff, 0x40000000   # carry.w with SGB_OB
 # every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
-           "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance"]
+           "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance", "sgb_debug_pack_map"]
 
 
 class SgbError(RuntimeError):
@@ -98,6 +98,7 @@ def load_library():
     L.sgb_status_string.restype = C.c_char_p
     L.sgb_last_error.restype = C.c_char_p
     L.sgb_version.restype = C.c_int
+    L.sgb_debug_pack_map.argtypes = [C.POINTER(MapDesc), C.POINTER(i64)]
     L.sgb_debug_mtv_distance.argtypes = [vp, vp]
     L.sgb_debug_mtv_distance.restype = C.c_float
     _lib = L

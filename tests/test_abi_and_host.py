@@ -208,3 +208,24 @@ def test_kernel_mtv_source_matches_reference_vectors_on_the_host():
                 if i != j:
                     got[b, i, j] = L.sgb_debug_mtv_distance(v[b, i].ctypes.data, v[b, j].ctypes.data)
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_every_reference_scenario_type_ships_and_packs():
+    """All 18 scenario types of the reference's SCENARIOS table (constants.py:8-626) are shipped as parsed maps
+    (oracle/gen_maps.py) and accepted by the library's map packer (host-only part of sgb_create): no degenerate
+    polyline, at most 256 segments, and a blob that fits the shared memory of one SM next to the slot arrays."""
+    import ctypes as C
+    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.maps import MapLibrary, available_scenarios
+    want = ["cpm_entire", "cpm_mixed", "interchange_1", "interchange_2", "interchange_3"] + \
+           [f"intersection_{i}" for i in range(1, 9)] + \
+           ["on_ramp_1", "on_ramp_2_multilane", "pseudo_distance_example", "roundabout_1", "roundabout_2"]
+    assert available_scenarios() == sorted(want)
+    L = load_library()
+    for st in want:
+        m = MapLibrary(st)
+        d, n = m.desc(), C.c_int64()
+        assert L.sgb_debug_pack_map(C.byref(d), C.byref(n)) == 0, st
+        assert 0 < n.value <= 180368, (st, n.value)            # cpm_entire is the largest map
+        assert m.max_ref_path_points == int(m.n_center.max()) + 8
+    assert L.sgb_debug_pack_map(None, None) != 0

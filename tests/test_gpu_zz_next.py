@@ -103,3 +103,47 @@ def test_mtv_distance_changes_what_it_should_and_nothing_else():
         for i in range(N):
             d = [L.sgb_debug_mtv_distance(v[b, i].ctypes.data, v[b, j].ctypes.data) if j != i else 1e9 for j in range(N)]
             assert abs(obs[1][b, i, 20] - min(d) / norm_dist) <= 1e-5, (b, i)
+
+
+@pytest.mark.parametrize("scenario,N,rew,mode,B", [
+    ("interchange_2", 10, "distance", "params", 256),      # the map's default n_agents, G = 2
+    ("interchange_3", 8, "ttc_sparse", "kwargs", 256),
+    ("intersection_5", 10, "distance_sparse", "kwargs", 256),
+    ("intersection_7", 8, "ttc", "params", 256),
+    ("intersection_4", 6, "sparse", "params", 256),
+    ("interchange_1", 4, "distance", "kwargs", 256),
+])
+def test_new_maps_match_oracle_free_running(oracle_mod, scenario, N, rew, mode, B):
+    """The ten maps shipped after the last hardware session (interchange_1-3, intersection_2-8): GPU with device
+    resets vs the oracle, which is pinned on reference goldens of every one of them (tests/golden/next/map_*.npz)."""
+    env = P._free_run(oracle_mod, scenario, N, rew, mode, B, 2)
+    assert env.D == 10 + 11 * min(2, N - 1)
+
+
+@pytest.mark.parametrize("scenario,N", [("interchange_2", 10), ("intersection_6", 10), ("intersection_8", 8)])
+def test_new_maps_pruned_equals_exhaustive_bitwise(scenario, N):
+    """The pruning certificates (chunk boxes, direction cones, crossing gate) on the new geometries: every output
+    buffer of the pruned kernel equals the exhaustive one bit for bit over 40 steps with device resets."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    B = 4096
+    envs = [RoadTrafficEnv(EnvConfig(scenario_type=scenario, n_agents=N, rew_method="ttc_sparse", exhaustive=ex),
+                           num_envs=B, device="cuda:0", seed=5, debug=True) for ex in (False, True)]
+    for e in envs:
+        e.reset()
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    ur = torch.as_tensor(P.UR).cuda()
+    n_done = 0
+    for t in range(40):
+        if t % 2:
+            act = (torch.rand(B, N, 2, generator=gen, device="cuda") * 2 - 1) * ur
+        else:
+            act = torch.stack([0.4 + 0.4 * torch.rand(B, N, generator=gen, device="cuda"),
+                               (torch.rand(B, N, generator=gen, device="cuda") * 2 - 1) * 0.2], -1)
+        for e in envs:
+            e.step(act.clone())
+        for name in ("pose", "aux", "carry", "obs", "reward", "done", "agent_flags", "collide_with", "step_count", "dbg"):
+            assert torch.equal(getattr(envs[0], name), getattr(envs[1], name)), f"{scenario} t={t} {name}"
+        n_done += int(envs[0].done.sum())
+        for e in envs:
+            e.reset_done()
+    assert n_done > 0 and int(envs[0].n_failed.item()) == 0
