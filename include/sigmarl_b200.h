@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 124
+#define SGB_VERSION 125
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -109,7 +109,11 @@ typedef struct {
                                  like the reference does, from the rectangles of the PRE-step poses
                                  (world_state_rt_sim.py:432-448), fresh ones after a reset; agents collide iff it is
                                  exactly 0 (:394-396).  near_agents_low / high then carry the MTV thresholds
-                                 (road_traffic.py:264-270, 632-648).  sizeof(sgb_config) stays a multiple of 16 */
+                                 (road_traffic.py:264-270, 632-648) */
+    float mask_distance;      /* thresholds.distance_mask_agents (5 agent lengths, road_traffic.py:663); read with
+                                 SGB_OBS_APPLY_MASK */
+    uint32_t reserved0, reserved1, reserved2; /* sizeof(sgb_config) == 200: grows in steps of 16 so that the kernel
+                                 parameters behind it keep their alignment (and the tuned kernels their exact code) */
 } sgb_config;
 
 /* Observation layout flags == the reference's Parameters of the same meaning (helper_common.py:60-118;
@@ -118,7 +122,7 @@ typedef struct {
  * neighbour: 4 vertices (8) or pos(2), rot, length, width | vel (2) | [steering] | [distance] | [its
  * short-term path (6)].  Not offered (sgb_create returns SGB_ERR_UNSUPPORTED for unknown bits;
  * the Python host layer refuses the parameters in EnvConfig.validate): is_partial_observation = False (the
- * reference itself crashes there, observation_provider_rt.py:808) and masks. */
+ * reference itself crashes there, observation_provider_rt.py:808). */
 #define SGB_OBS_BIRD_VIEW 1u       /* is_ego_view = False: global coordinates / pos_world                 */
 #define SGB_OBS_CENTRES 2u         /* is_observe_vertices = False: pos, rot, length, width of a neighbour  */
 #define SGB_OBS_STEERING 4u        /* is_obs_steering: own and neighbours' steering angle / (2 pi)         */
@@ -129,6 +133,11 @@ typedef struct {
                                       around the closest one instead of the two distances.  carry.w then keeps, in
                                       bit 30, whether the pose was written by a reset (the reference samples the
                                       points with shift +1 there and -2 in a step, world_state_rt.py:531-576, :686-725) */
+#define SGB_OBS_APPLY_MASK 128u    /* is_apply_mask: an observed neighbour whose distance is >= mask_distance shows
+                                      constants instead of its state — positions, vertices, reference path and distance 1,
+                                      heading, steering and velocity 0; length / width stay (observation_provider_rt.py:
+                                      638-749).  The reference's second criterion (lanelet relation) only ever fires in bird
+                                      view on OSM maps (:585-588, parse_osm.py:257-262); the host layer refuses that case */
 
 /* Device buffers of one batch of B envs x N agents.  in = read, out = written, io = both. */
 typedef struct {

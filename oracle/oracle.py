@@ -55,14 +55,16 @@ _CFG_INTS = ["rew_exact_sparse", "rew_has_ttc", "rew_has_distance", "rew_has_spa
 class _Cfg(C.Structure):
     _fields_ = ([(n, C.c_float) for n in _CFG_FLOATS] + [(n, C.c_int) for n in _CFG_INTS] +
                 [("reward_reach_goal", C.c_float), ("obs_flags", C.c_int), ("norm_pos_world", C.c_float * 2),
-                 ("norm_dist_agent", C.c_float), ("fixed_duration", C.c_float), ("use_mtv", C.c_int)])
+                 ("norm_dist_agent", C.c_float), ("fixed_duration", C.c_float), ("use_mtv", C.c_int),
+                 ("mask_distance", C.c_float)])
 
 
 # observation layout flags (ORC_OBS_* in sigmarl_oracle.c) keyed by the reference's parameter names and the value
 # that sets the bit (observation_provider_rt.py:594-925)
 OBS_FLAG_BITS = dict(is_ego_view=(1, False), is_observe_vertices=(2, False), is_obs_steering=(4, True),
                      is_observe_ref_path_other_agents=(8, True), is_observe_distance_to_agents=(16, False),
-                     is_observe_distance_to_center_line=(32, False), is_observe_distance_to_boundaries=(64, False))
+                     is_observe_distance_to_center_line=(32, False), is_observe_distance_to_boundaries=(64, False),
+                     is_apply_mask=(128, True))
 
 
 def obs_flags_from(get):
@@ -217,6 +219,7 @@ def make_cfg(scenario_type, pmap, c):
     cfg.norm_dist_agent = float(f32(AGENT_LENGTH * 10))                            # road_traffic.py:605-607
     cfg.fixed_duration = float(f32(c.get("fixed_duration", 0.0)))                  # road_traffic.py:1388-1393
     cfg.use_mtv = int(bool(c.get("use_mtv", False)))                               # road_traffic.py:611-614
+    cfg.mask_distance = float(f32(AGENT_LENGTH * 5))                               # road_traffic.py:663
     return cfg
 
 

@@ -58,6 +58,7 @@ typedef struct {
     float norm_dist_agent;   /* normalizers.distance_agent          road_traffic.py:605-607 */
     float fixed_duration;    /* reset_agent_fixed_duration [s], 0 = off   road_traffic.py:1388-1393 */
     int use_mtv;             /* is_use_mtv_distance: distances.type == "mtv"  road_traffic.py:611-614 */
+    float mask_distance;     /* thresholds.distance_mask_agents (5 agent lengths)   road_traffic.py:663 */
 } orc_cfg;
 
 #define ORC_OBS_BIRD_VIEW 1       /* is_ego_view = False */
@@ -67,6 +68,7 @@ typedef struct {
 #define ORC_OBS_NO_DIST_AGENTS 16 /* is_observe_distance_to_agents = False */
 #define ORC_OBS_NO_DIST_CENTER 32 /* is_observe_distance_to_center_line = False */
 #define ORC_OBS_BOUNDARY_POINTS 64 /* is_observe_distance_to_boundaries = False: 5 points of each boundary */
+#define ORC_OBS_MASK 128          /* is_apply_mask: observed neighbours farther than mask_distance show constants */
 #define ORC_NNB 5                  /* n_points_nearing_boundary (road_traffic.py:296-298) */
 
 typedef struct {
@@ -645,17 +647,23 @@ static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, flo
         size_t gj = AG(b, bj);
         const float *pj = &w->pos[gj * 2];
         float rr = orc_wrap(w->rot[gj] - rot_i);          /* :427 */
+        /* is_apply_mask :638-668: a neighbour at or beyond distance_mask_agents is masked (position-like entries := 1,
+         * angles / velocities := 0, :682-749).  The lanelet-relation mask never fires where this oracle is used: the
+         * lanelet assignment is only computed in bird view (:585-588) and only OSM maps know neighbouring lanelets
+         * (parse_osm.py:257-262); the host layer refuses that combination. */
+        const int masked = (fl & ORC_OBS_MASK) && (bd >= c->mask_distance);
+#define MSK(v, m) (masked ? (m) : (v))
         if (fl & ORC_OBS_CENTRES) {                       /* :826-836: pos, rot, length, width */
             if (bird) {
-                obs[o++] = pj[0] / c->norm_pos_world[0];
-                obs[o++] = pj[1] / c->norm_pos_world[1];
-                obs[o++] = orc_wrap(w->rot[gj]) / c->norm_rot;
+                obs[o++] = MSK(pj[0] / c->norm_pos_world[0], 1.0f);
+                obs[o++] = MSK(pj[1] / c->norm_pos_world[1], 1.0f);
+                obs[o++] = MSK(orc_wrap(w->rot[gj]) / c->norm_rot, 0.0f);
             } else {
                 float loc[2];
                 orc_local(pi, rot_i, pj, loc);            /* :418-424 */
-                obs[o++] = loc[0] / c->norm_pos;
-                obs[o++] = loc[1] / c->norm_pos;
-                obs[o++] = rr / c->norm_rot;
+                obs[o++] = MSK(loc[0] / c->norm_pos, 1.0f);
+                obs[o++] = MSK(loc[1] / c->norm_pos, 1.0f);
+                obs[o++] = MSK(rr / c->norm_rot, 0.0f);
             }
             obs[o++] = (2.0f * c->half_length) / c->norm_dist_agent;  /* :359-371, :388-393; 2*fl(L/2) == fl(L) */
             obs[o++] = (2.0f * c->half_width) / c->norm_dist_agent;
@@ -663,41 +671,42 @@ static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, flo
             for (int v = 0; v < 4; v++) {                 /* vertices :484-492 / :559-566 */
                 const float *pv = &w->vertices[(gj * 5 + v) * 2];
                 if (bird) {
-                    obs[o++] = pv[0] / c->norm_pos_world[0];
-                    obs[o++] = pv[1] / c->norm_pos_world[1];
+                    obs[o++] = MSK(pv[0] / c->norm_pos_world[0], 1.0f);
+                    obs[o++] = MSK(pv[1] / c->norm_pos_world[1], 1.0f);
                 } else {
                     float loc[2];
                     orc_local(pi, rot_i, pv, loc);
-                    obs[o++] = loc[0] / c->norm_pos;
-                    obs[o++] = loc[1] / c->norm_pos;
+                    obs[o++] = MSK(loc[0] / c->norm_pos, 1.0f);
+                    obs[o++] = MSK(loc[1] / c->norm_pos, 1.0f);
                 }
             }
         }
         if (bird) {
-            obs[o++] = w->vel[gj * 2] / c->norm_v;        /* :553-555 */
-            obs[o++] = w->vel[gj * 2 + 1] / c->norm_v;
+            obs[o++] = MSK(w->vel[gj * 2] / c->norm_v, 0.0f);        /* :553-555 */
+            obs[o++] = MSK(w->vel[gj * 2 + 1] / c->norm_v, 0.0f);
         } else {
             float vabs = orc_norm2(w->vel[gj * 2], w->vel[gj * 2 + 1]);
-            obs[o++] = (vabs * cosf(rr)) / c->norm_v;     /* :432-441 */
-            obs[o++] = (vabs * sinf(rr)) / c->norm_v;
+            obs[o++] = MSK((vabs * cosf(rr)) / c->norm_v, 0.0f);     /* :432-441 */
+            obs[o++] = MSK((vabs * sinf(rr)) / c->norm_v, 0.0f);
         }
-        if (fl & ORC_OBS_STEERING) obs[o++] = orc_wrap(w->steering[gj]) / c->norm_rot;   /* :692-700 */
-        if (!(fl & ORC_OBS_NO_DIST_AGENTS)) obs[o++] = bd / c->norm_dist;                /* :369-371 */
+        if (fl & ORC_OBS_STEERING) obs[o++] = MSK(orc_wrap(w->steering[gj]) / c->norm_rot, 0.0f);   /* :692-700 */
+        if (!(fl & ORC_OBS_NO_DIST_AGENTS)) obs[o++] = MSK(bd / c->norm_dist, 1.0f);                /* :369-371 */
         if (fl & ORC_OBS_REF_OTHERS)                                                     /* :443-452, :716-724 */
             for (int k = 0; k < ORC_NST; k++) {
                 if (bird) {
-                    obs[o++] = s->short_term[bj][2 * k] / c->norm_pos_world[0];
-                    obs[o++] = s->short_term[bj][2 * k + 1] / c->norm_pos_world[1];
+                    obs[o++] = MSK(s->short_term[bj][2 * k] / c->norm_pos_world[0], 1.0f);
+                    obs[o++] = MSK(s->short_term[bj][2 * k + 1] / c->norm_pos_world[1], 1.0f);
                 } else {
                     float loc[2];
                     orc_local(pi, rot_i, &s->short_term[bj][2 * k], loc);
-                    obs[o++] = loc[0] / c->norm_pos;
-                    obs[o++] = loc[1] / c->norm_pos;
+                    obs[o++] = MSK(loc[0] / c->norm_pos, 1.0f);
+                    obs[o++] = MSK(loc[1] / c->norm_pos, 1.0f);
                 }
             }
     }
 }
 
+#undef MSK
 /* width of the observation for the configured flags */
 int orc_obs_dim(const orc_world *w) {
     const int fl = w->cfg.obs_flags;

@@ -70,19 +70,25 @@ class EnvConfig:
     is_use_mtv_distance: bool = False
     threshold_near_other_agents_MTV_low: float = 0.0
     threshold_near_other_agents_MTV_high: float = AGENT_LENGTH
+    is_apply_mask: bool = False                    # observed neighbours beyond 5 agent lengths show constants (:638-749)
     # flags of the reference that select code OUTSIDE the supported hot path; must keep these values
     is_partial_observation: bool = True            # False crashes in the reference itself (:808)
-    is_apply_mask: bool = False
     extras: dict = field(default_factory=dict)
 
     def validate(self):
         if self.rew_method not in _REW_METHODS:
             raise NotImplementedError(f"rew_method {self.rew_method!r}: supported {_REW_METHODS} (cbf variants are out of scope)")
-        want = dict(is_partial_observation=True, is_apply_mask=False)
+        want = dict(is_partial_observation=True)
         for k, v in want.items():
             if getattr(self, k) != v:
                 raise NotImplementedError(f"{k}={getattr(self, k)} selects a non-default observation/reset variant "
                                           f"that is outside the accelerated hot path (SURVEY.md §8f-4)")
+        if self.is_apply_mask and not self.is_ego_view and not self.scenario_type.startswith("cpm"):
+            # the only case in which the reference's lanelet-relation mask is live: bird view (the lanelet assignment is
+            # only computed there, observation_provider_rt.py:585-588) on an OSM map (only parse_osm.py:257-262 fills
+            # neighboring_lanelets_idx); ego view and the CPM maps mask by distance alone
+            raise NotImplementedError("is_apply_mask in bird view on an OSM map needs the lanelet-relation mask "
+                                      "(map_manager.py:39-119), which is outside the accelerated hot path")
         if self.mode not in ("params", "kwargs"):
             raise ValueError("mode must be 'params' or 'kwargs'")
 
@@ -204,6 +210,7 @@ class EnvConfig:
         c.testing_mode = int(bool(self.is_testing_mode))
         c.reset_fixed_period = self.fixed_period(r["dt"])
         c.use_mtv_distance = int(bool(self.is_use_mtv_distance))
+        c.mask_distance = float(_f32(AGENT_LENGTH * 5))                        # road_traffic.py:663
         c.obs_flags = self.obs_flags()
         c.norm_pos_world_x, c.norm_pos_world_y = float(x), float(y)            # road_traffic.py:593-595
         c.norm_dist_agent = float(_f32(AGENT_LENGTH * 10))                     # road_traffic.py:605-607
@@ -220,7 +227,8 @@ class EnvConfig:
                 (_lib.SGB_OBS_REF_OTHERS if self.is_observe_ref_path_other_agents else 0) |
                 (0 if self.is_observe_distance_to_agents else _lib.SGB_OBS_NO_DIST_AGENTS) |
                 (0 if self.is_observe_distance_to_center_line else _lib.SGB_OBS_NO_DIST_CENTER) |
-                (0 if self.is_observe_distance_to_boundaries else _lib.SGB_OBS_BOUNDARY_POINTS))
+                (0 if self.is_observe_distance_to_boundaries else _lib.SGB_OBS_BOUNDARY_POINTS) |
+                (_lib.SGB_OBS_APPLY_MASK if self.is_apply_mask else 0))
 
     def obs_dim(self, n_agents: int) -> int:
         """Observation width of this layout (== sgb_obs_dim of a context built from it)."""

@@ -385,13 +385,14 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     }
     if (cfg->k_near < 0 || cfg->k_near >= SGB_MAX_AGENTS || cfg->max_steps < 2 || !(cfg->dt > 0.0f)) return SGB_ERR_ARG;
     constexpr uint32_t kObsKnown = SGB_OBS_BIRD_VIEW | SGB_OBS_CENTRES | SGB_OBS_STEERING | SGB_OBS_REF_OTHERS |
-                                   SGB_OBS_NO_DIST_AGENTS | SGB_OBS_NO_DIST_CENTER | SGB_OBS_BOUNDARY_POINTS;
+                                   SGB_OBS_NO_DIST_AGENTS | SGB_OBS_NO_DIST_CENTER | SGB_OBS_BOUNDARY_POINTS | SGB_OBS_APPLY_MASK;
     if (cfg->obs_flags & ~kObsKnown) {
         snprintf(g_err, sizeof g_err, "obs_flags 0x%x: unknown observation layout bits", cfg->obs_flags);
         return SGB_ERR_UNSUPPORTED;
     }
     if ((cfg->obs_flags & SGB_OBS_BIRD_VIEW) && !(cfg->norm_pos_world_x > 0.0f && cfg->norm_pos_world_y > 0.0f)) return SGB_ERR_ARG;
     if ((cfg->obs_flags & SGB_OBS_CENTRES) && !(cfg->norm_dist_agent > 0.0f)) return SGB_ERR_ARG;
+    if ((cfg->obs_flags & SGB_OBS_APPLY_MASK) && !(cfg->mask_distance > 0.0f)) return SGB_ERR_ARG;
     if (!(cfg->obs_noise_level >= 0.0f) || cfg->reset_fixed_period < 0 || cfg->use_mtv_distance > 1u) return SGB_ERR_ARG;
     Packed pk;
     int rc = pack_map(map, pk);

@@ -1236,6 +1236,24 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
 #pragma unroll
                             for (int k = 0; k < 3; k++) { put_point(q, st[k].x, st[k].y); q += 2; }
                         }
+                        if ((ofl & SGB_OBS_APPLY_MASK) && bd >= cfg.mask_distance) {
+                            // is_apply_mask (observation_provider_rt.py:638-749): a far neighbour shows constants —
+                            // positions / vertices / reference path / distance 1, heading / steering / velocity 0
+                            float* m = o + own + per * kk;
+                            if (ofl & SGB_OBS_CENTRES) { m[0] = 1.0f; m[1] = 1.0f; m[2] = 0.0f; m += 5; }   // length, width stay
+                            else {
+#pragma unroll
+                                for (int v = 0; v < 8; v++) m[v] = 1.0f;
+                                m += 8;
+                            }
+                            m[0] = 0.0f; m[1] = 0.0f; m += 2;
+                            if (ofl & SGB_OBS_STEERING) *m++ = 0.0f;
+                            if (!(ofl & SGB_OBS_NO_DIST_AGENTS)) *m++ = 1.0f;
+                            if (ofl & SGB_OBS_REF_OTHERS) {
+#pragma unroll
+                                for (int k = 0; k < 6; k++) m[k] = 1.0f;
+                            }
+                        }
                         if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
                     }
                     if (cfg.obs_noise_level > 0.0f) {

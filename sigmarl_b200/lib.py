@@ -13,7 +13,7 @@ SGB_MAX_AGENTS = 32
 SGB_FLAG_COLLIDE_AGENT, SGB_FLAG_COLLIDE_LANE, SGB_FLAG_ENTRY, SGB_FLAG_EXIT = 1, 2, 4, 8
 SGB_REW_EXACT_SPARSE, SGB_REW_TTC, SGB_REW_DISTANCE, SGB_REW_SPARSE = 1, 2, 4, 8
 (SGB_OBS_BIRD_VIEW, SGB_OBS_CENTRES, SGB_OBS_STEERING, SGB_OBS_REF_OTHERS, SGB_OBS_NO_DIST_AGENTS,
- SGB_OBS_NO_DIST_CENTER, SGB_OBS_BOUNDARY_POINTS) = 1, 2, 4, 8, 16, 32, 64
+ SGB_OBS_NO_DIST_CENTER, SGB_OBS_BOUNDARY_POINTS, SGB_OBS_APPLY_MASK) = 1, 2, 4, 8, 16, 32, 64, 128
 CARRY_IDX_MASK, CARRY_FRESH_BIT = 0x3fffffff, 0x40000000   # carry.w with SGB_OBS_BOUNDARY_POINTS (see the header)
 
 # every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
@@ -48,7 +48,7 @@ class Config(C.Structure):
                  ("respawn_on_exit", C.c_int32), ("exhaustive", C.c_int32), ("reward_reach_goal", C.c_float),
                  ("testing_mode", C.c_int32), ("obs_flags", C.c_uint32), ("norm_pos_world_x", C.c_float),
                  ("norm_pos_world_y", C.c_float), ("norm_dist_agent", C.c_float), ("obs_noise_level", C.c_float),
-                 ("obs_noise_seed", C.c_uint32), ("reset_fixed_period", C.c_int32), ("use_mtv_distance", C.c_uint32)])
+                 ("obs_noise_seed", C.c_uint32), ("reset_fixed_period", C.c_int32), ("use_mtv_distance", C.c_uint32), ("mask_distance", C.c_float), ("reserved0", C.c_uint32), ("reserved1", C.c_uint32), ("reserved2", C.c_uint32)])
 
 
 BUFFER_FIELDS = ["pose", "aux", "path_id", "carry", "action", "step_count", "obs", "reward", "done",

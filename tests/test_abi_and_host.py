@@ -145,10 +145,10 @@ def test_config_matches_reference_constants_in_goldens():
 def test_unsupported_flags_fail_loudly():
     from sigmarl_b200 import EnvConfig, MapLibrary
     m = MapLibrary("cpm_entire")
-    for kw in (dict(rew_method="cbf"), dict(is_apply_mask=True),
+    for kw in (dict(rew_method="cbf"), dict(scenario_type="roundabout_2", is_apply_mask=True, is_ego_view=False),
                dict(is_partial_observation=False)):
         with pytest.raises(NotImplementedError):
-            EnvConfig(scenario_type="cpm_entire", **kw).lower(m)
+            EnvConfig(**{"scenario_type": "cpm_entire", **kw}).lower(m)
     # observation layouts and noise ARE supported (ABI 121 / 122): flags, width and noise level reach sgb_config
     from sigmarl_b200 import lib
     c = EnvConfig(scenario_type="cpm_entire", n_agents=4, is_ego_view=False, is_obs_steering=True,
@@ -164,6 +164,10 @@ def test_unsupported_flags_fail_loudly():
         assert low.use_mtv_distance == 1 and low.near_agents_low == 0.0 and low.dsafe_sq == 0.0
         assert low.near_agents_high == float(np.float32(0.22))
     assert EnvConfig(scenario_type="cpm_entire").lower(m).use_mtv_distance == 0
+    # observation masks (ABI 125): by distance; ego view on any map, bird view on the CPM maps
+    low = EnvConfig(scenario_type="cpm_entire", is_apply_mask=True, is_ego_view=False).lower(m)
+    assert low.obs_flags == lib.SGB_OBS_APPLY_MASK | lib.SGB_OBS_BIRD_VIEW and low.mask_distance == float(np.float32(1.1))
+    assert EnvConfig(scenario_type="roundabout_2", is_apply_mask=True).lower(MapLibrary("roundabout_2")).obs_flags == lib.SGB_OBS_APPLY_MASK
     with pytest.raises(ValueError):
         MapLibrary("no_such_map")
 

@@ -20,7 +20,7 @@ UR = np.asarray([1.0, 31 * np.pi / 180], np.float32)
 
 OBS_FLAG_NAMES = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
                   "is_observe_distance_to_agents", "is_observe_distance_to_center_line",
-                  "is_observe_distance_to_boundaries"]
+                  "is_observe_distance_to_boundaries", "is_apply_mask"]
 
 
 def _obs_flags_of_golden(g):

@@ -147,3 +147,20 @@ def test_new_maps_pruned_equals_exhaustive_bitwise(scenario, N):
         for e in envs:
             e.reset_done()
     assert n_done > 0 and int(envs[0].n_failed.item()) == 0
+
+
+@pytest.mark.parametrize("scenario,N,rew,mode,B,k_obs,flags", [
+    ("cpm_entire", 8, "distance", "params", 512, 5, dict()),                                        # G = 4
+    ("roundabout_2", 12, "ttc", "kwargs", 256, 4,
+     dict(is_observe_vertices=False, is_obs_steering=True, is_observe_ref_path_other_agents=True)),   # G = 2, OSM, ego view
+    ("cpm_entire", 18, "distance_sparse", "params", 64, 6, dict(is_ego_view=False)),                # G = 1, bird view (CPM)
+    ("cpm_mixed", 6, "ttc_sparse", "params", 256, 3, dict(is_use_mtv_distance=True)),               # masks on MTV distances
+])
+def test_cuda_observation_masks_match_oracle(oracle_mod, scenario, N, rew, mode, B, k_obs, flags):
+    """is_apply_mask (observation_provider_rt.py:638-749): observed neighbours at or beyond 5 agent lengths show the
+    mask constants.  Oracle pinned on tests/golden/next/mask_*.npz (ego view on a CPM and an OSM map, bird view on CPM)."""
+    env = P._free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, is_apply_mask=True, **flags)
+    obs = env.obs.cpu().numpy()
+    own, per = env.config.obs_dim(1), (env.config.obs_dim(N) - env.config.obs_dim(1)) // min(k_obs, N - 1)
+    last = obs[..., own + per * (min(k_obs, N - 1) - 1): own + per * min(k_obs, N - 1)]
+    assert (last[..., :2] == 1.0).all(-1).any(), "no masked neighbour seen: the test would not exercise the mask"
