@@ -15,7 +15,9 @@ import test_gpu_parity as P
 
 pytestmark = pytest.mark.gpu
 
-NEXT = golden_files("next")
+NEXT_ALL = golden_files("next")
+NEXT = [p for p in NEXT_ALL if not os.path.basename(p).startswith("mtv_")]       # fixed duration, maps, masks
+NEXT_MTV = [p for p in NEXT_ALL if os.path.basename(p).startswith("mtv_")]      # the MTV kernels <G,MODE,2> run last
 _ids = lambda p: os.path.basename(p)[:-4]  # noqa: E731
 
 
@@ -54,55 +56,6 @@ def test_fixed_duration_ends_envs_periodically_free_running():
         env.reset_done()
         # a fixed-duration reset zeroes the clock (road_traffic.py:877), so the period restarts
         assert int(env.step_count.max()) == (0 if want else t % 10)
-
-
-@pytest.mark.parametrize("scenario,N,rew,mode,B,k_obs,flags", [
-    ("cpm_entire", 8, "distance", "params", 512, 2, dict()),                         # G = 4, default layout
-    ("roundabout_2", 12, "ttc", "kwargs", 256, 3, dict(is_obs_steering=True)),       # G = 2, crowded map
-    ("cpm_entire", 18, "distance_sparse", "params", 64, 2, dict(is_ego_view=False)), # G = 1, bird view
-    ("cpm_mixed", 6, "ttc_sparse", "params", 256, 5, dict(reset_agent_fixed_duration=1)),
-])
-def test_cuda_mtv_distance_matches_oracle_free_running(oracle_mod, scenario, N, rew, mode, B, k_obs, flags):
-    """is_use_mtv_distance: GPU (device resets included) vs the oracle pinned on tests/golden/next/mtv_*.npz and on the
-    2 400-pair known-answer test: MTV distances from the pre-step rectangles feed the near-agent penalty, the k-nearest
-    selection and the observed distances; rectangles never "collide" unless the distance is exactly zero."""
-    env = P._free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, is_use_mtv_distance=True, **flags)
-    assert env.D == env.config.obs_dim(N)
-
-
-def test_mtv_distance_changes_what_it_should_and_nothing_else():
-    """Same seeds with and without is_use_mtv_distance: poses, lane flags and boundary / centre-line columns of the
-    observation are identical after one step (poses / flags bitwise); the neighbour-distance column equals the MTV distance of the
-    PRE-step rectangles (host build of the kernel's own source function) for the observed neighbour."""
-    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
-    from sigmarl_b200.lib import load_library
-    L = load_library()
-    B, N = 256, 8
-    envs = [RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=N, is_use_mtv_distance=m), num_envs=B,
-                           device="cuda:0", seed=21, debug=True) for m in (False, True)]
-    for e in envs:
-        e.reset()
-    assert torch.equal(envs[0].pose, envs[1].pose)
-    pre = envs[1].pose.cpu().numpy().copy()
-    gen = torch.Generator(device="cuda").manual_seed(3)
-    act = (torch.rand(B, N, 2, generator=gen, device="cuda") * 2 - 1) * torch.as_tensor(P.UR).cuda()
-    obs = [e.step(act.clone())[0].cpu().numpy() for e in envs]
-    torch.cuda.synchronize()
-    assert torch.equal(envs[0].pose, envs[1].pose) and torch.equal(envs[0].carry, envs[1].carry)
-    assert torch.equal(envs[0].agent_flags & 14, envs[1].agent_flags & 14)
-    assert np.abs(obs[0][..., :10] - obs[1][..., :10]).max() <= 1e-6   # hard-wired vs flag-driven writer: same formulas
-    # nearest neighbour by MTV distance, from the pre-step poses
-    hl, hw = 0.11, 0.0535
-    c, s_ = np.cos(pre[..., 2]).astype(np.float32), np.sin(pre[..., 2]).astype(np.float32)
-    bx, by = np.float32([hl, hl, -hl, -hl]), np.float32([hw, -hw, -hw, hw])
-    vx = (c[..., None] * bx - s_[..., None] * by) + pre[..., 0:1]
-    vy = (s_[..., None] * bx + c[..., None] * by) + pre[..., 1:2]
-    v = np.ascontiguousarray(np.stack([vx, vy], -1), np.float32)            # [B,N,4,2]
-    norm_dist = np.float32(0.15 * 3)
-    for b in range(0, B, 16):
-        for i in range(N):
-            d = [L.sgb_debug_mtv_distance(v[b, i].ctypes.data, v[b, j].ctypes.data) if j != i else 1e9 for j in range(N)]
-            assert abs(obs[1][b, i, 20] - min(d) / norm_dist) <= 1e-5, (b, i)
 
 
 @pytest.mark.parametrize("scenario,N,rew,mode,B", [
@@ -154,7 +107,6 @@ def test_new_maps_pruned_equals_exhaustive_bitwise(scenario, N):
     ("roundabout_2", 12, "ttc", "kwargs", 256, 4,
      dict(is_observe_vertices=False, is_obs_steering=True, is_observe_ref_path_other_agents=True)),   # G = 2, OSM, ego view
     ("cpm_entire", 18, "distance_sparse", "params", 64, 6, dict(is_ego_view=False)),                # G = 1, bird view (CPM)
-    ("cpm_mixed", 6, "ttc_sparse", "params", 256, 3, dict(is_use_mtv_distance=True)),               # masks on MTV distances
 ])
 def test_cuda_observation_masks_match_oracle(oracle_mod, scenario, N, rew, mode, B, k_obs, flags):
     """is_apply_mask (observation_provider_rt.py:638-749): observed neighbours at or beyond 5 agent lengths show the
@@ -164,3 +116,75 @@ def test_cuda_observation_masks_match_oracle(oracle_mod, scenario, N, rew, mode,
     own, per = env.config.obs_dim(1), (env.config.obs_dim(N) - env.config.obs_dim(1)) // min(k_obs, N - 1)
     last = obs[..., own + per * (min(k_obs, N - 1) - 1): own + per * min(k_obs, N - 1)]
     assert (last[..., :2] == 1.0).all(-1).any(), "no masked neighbour seen: the test would not exercise the mask"
+
+
+# ---- MTV agent distance: separate kernel instantiations, run after everything else
+@pytest.mark.parametrize("path", NEXT_MTV, ids=_ids)
+@pytest.mark.parametrize("exhaustive", [False, True], ids=["pruned", "exhaustive"])
+def test_cuda_matches_reference_goldens_mtv(path, exhaustive):
+    P.test_cuda_matches_reference_goldens(path, exhaustive)
+
+
+@pytest.mark.parametrize("path", NEXT_MTV, ids=_ids)
+def test_cuda_reset_obs_matches_reference_mtv(path):
+    P.test_cuda_reset_obs_matches_reference(path)
+
+
+@pytest.mark.parametrize("path", NEXT_MTV, ids=_ids)
+def test_facade_info_matches_reference_goldens_mtv(path):
+    P.test_facade_info_matches_reference_goldens(path)
+
+
+@pytest.mark.parametrize("scenario,N,rew,mode,B,k_obs,flags", [
+    ("cpm_entire", 8, "distance", "params", 512, 2, dict()),                         # G = 4, default layout
+    ("roundabout_2", 12, "ttc", "kwargs", 256, 3, dict(is_obs_steering=True)),       # G = 2, crowded map
+    ("cpm_entire", 18, "distance_sparse", "params", 64, 2, dict(is_ego_view=False)), # G = 1, bird view
+    ("cpm_mixed", 6, "ttc_sparse", "params", 256, 5, dict(reset_agent_fixed_duration=1)),
+])
+def test_cuda_mtv_distance_matches_oracle_free_running(oracle_mod, scenario, N, rew, mode, B, k_obs, flags):
+    """is_use_mtv_distance: GPU (device resets included) vs the oracle pinned on tests/golden/next/mtv_*.npz and on the
+    2 400-pair known-answer test: MTV distances from the pre-step rectangles feed the near-agent penalty, the k-nearest
+    selection and the observed distances; rectangles never "collide" unless the distance is exactly zero."""
+    env = P._free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, is_use_mtv_distance=True, **flags)
+    assert env.D == env.config.obs_dim(N)
+
+
+def test_mtv_distance_changes_what_it_should_and_nothing_else():
+    """Same seeds with and without is_use_mtv_distance: poses, lane flags and boundary / centre-line columns of the
+    observation are identical after one step (poses / flags bitwise); the neighbour-distance column equals the MTV distance of the
+    PRE-step rectangles (host build of the kernel's own source function) for the observed neighbour."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    from sigmarl_b200.lib import load_library
+    L = load_library()
+    B, N = 256, 8
+    envs = [RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=N, is_use_mtv_distance=m), num_envs=B,
+                           device="cuda:0", seed=21, debug=True) for m in (False, True)]
+    for e in envs:
+        e.reset()
+    assert torch.equal(envs[0].pose, envs[1].pose)
+    pre = envs[1].pose.cpu().numpy().copy()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    act = (torch.rand(B, N, 2, generator=gen, device="cuda") * 2 - 1) * torch.as_tensor(P.UR).cuda()
+    obs = [e.step(act.clone())[0].cpu().numpy() for e in envs]
+    torch.cuda.synchronize()
+    assert torch.equal(envs[0].pose, envs[1].pose) and torch.equal(envs[0].carry, envs[1].carry)
+    assert torch.equal(envs[0].agent_flags & 14, envs[1].agent_flags & 14)
+    assert np.abs(obs[0][..., :10] - obs[1][..., :10]).max() <= 1e-6   # hard-wired vs flag-driven writer: same formulas
+    # nearest neighbour by MTV distance, from the pre-step poses
+    hl, hw = 0.11, 0.0535
+    c, s_ = np.cos(pre[..., 2]).astype(np.float32), np.sin(pre[..., 2]).astype(np.float32)
+    bx, by = np.float32([hl, hl, -hl, -hl]), np.float32([hw, -hw, -hw, hw])
+    vx = (c[..., None] * bx - s_[..., None] * by) + pre[..., 0:1]
+    vy = (s_[..., None] * bx + c[..., None] * by) + pre[..., 1:2]
+    v = np.ascontiguousarray(np.stack([vx, vy], -1), np.float32)            # [B,N,4,2]
+    norm_dist = np.float32(0.15 * 3)
+    for b in range(0, B, 16):
+        for i in range(N):
+            d = [L.sgb_debug_mtv_distance(v[b, i].ctypes.data, v[b, j].ctypes.data) if j != i else 1e9 for j in range(N)]
+            assert abs(obs[1][b, i, 20] - min(d) / norm_dist) <= 1e-5, (b, i)
+
+
+def test_cuda_observation_masks_on_mtv_distances_match_oracle(oracle_mod):
+    """The mask threshold applies to whatever distances.agents holds — here the MTV distance (kernel variant <G,MODE,2>)."""
+    test_cuda_observation_masks_match_oracle(oracle_mod, "cpm_mixed", 6, "ttc_sparse", "params", 256, 3,
+                                             dict(is_use_mtv_distance=True))
