@@ -367,6 +367,24 @@ int build_spawn_table(sgb_ctx* c, const Packed& pk) {
 
 } // namespace
 
+// device half of sgb_create; on any failure the caller destroys the context (sgb_destroy copes with a partial one)
+static int init_device_state(sgb_ctx* c, const Packed& pk) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int32_t)prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) {
+        snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library is built for sm_100a only", c->device, prop.major, prop.minor);
+        return SGB_ERR_NO_DEVICE;
+    }
+    CK(cudaMalloc(&c->d_blob, pk.blob.size()));
+    CK(cudaMemcpy(c->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_yaw, pk.yaw.size() * sizeof(float)));
+    CK(cudaMemcpy(c->d_yaw, pk.yaw.data(), pk.yaw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    c->n_points = (int32_t)pk.yaw.size();
+    return build_spawn_table(c, pk);
+}
+
 // ---- C-ABI ---------------------------------------------------------------------------------------------
 extern "C" int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes) {
     Packed pk;
@@ -405,22 +423,8 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     c->n_paths = map->n_paths;
     c->max_center = pk.max_center;
     c->blob_bytes = (int32_t)pk.blob.size();
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    c->num_sms = prop.multiProcessorCount;
-    c->max_smem_optin = (int32_t)prop.sharedMemPerBlockOptin;
-    if (prop.major < 10) {
-        snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-        delete c;
-        return SGB_ERR_NO_DEVICE;
-    }
-    CK(cudaMalloc(&c->d_blob, pk.blob.size()));
-    CK(cudaMemcpy(c->d_blob, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&c->d_yaw, pk.yaw.size() * sizeof(float)));
-    CK(cudaMemcpy(c->d_yaw, pk.yaw.data(), pk.yaw.size() * sizeof(float), cudaMemcpyHostToDevice));
-    c->n_points = (int32_t)pk.yaw.size();
-    rc = build_spawn_table(c, pk);
-    if (rc != SGB_OK) { sgb_destroy(c); return rc; }
+    rc = init_device_state(c, pk);
+    if (rc != SGB_OK) { sgb_destroy(c); return rc; }   // frees whatever was allocated before the failure
     *out = c;
     return SGB_OK;
 }
