@@ -120,15 +120,21 @@ class RoadTrafficEnv:
                                     self.seed, self.epoch, self.env_offset, self.max_reset_tries, int(write_obs),
                                     C.c_void_p(self.n_failed.data_ptr()), self._stream()), "sgb_reset")
 
-    def reset_masked(self, env_mask: torch.Tensor = None, agent_mask: torch.Tensor = None, write_obs: bool = True):
+    def reset_masked(self, env_mask: torch.Tensor = None, agent_mask: torch.Tensor = None, write_obs: bool = True,
+                     path_range=None):
         """Explicit selection: fully reset the envs of `env_mask` [B], respawn the agents of `agent_mask` [B,N]
-        (whatever the map / mode) — ``reset_world_at(env_index, agent_index)`` called from outside the step."""
+        (whatever the map / mode) — ``reset_world_at(env_index, agent_index)`` called from outside the step.
+        `path_range` = (lo, hi) restricts the paths drawn from for this call (``predefined_ref_path_idx`` respawns,
+        world_state_rt_sim.py:241-242); default: the env's own range."""
         self.epoch += 1
+        path_lo, path_hi = (self.path_lo, self.path_hi) if path_range is None else (int(path_range[0]), int(path_range[1]))
+        if not (0 <= path_lo < path_hi <= self.map.n_paths):
+            raise ValueError(f"path_range {path_range} outside [0, {self.map.n_paths}]")
         prep = lambda m: None if m is None else m.to(device=self.device, dtype=torch.uint8).contiguous()  # noqa: E731
         em, am = prep(env_mask), prep(agent_mask)
         ptr = lambda m: C.c_void_p(m.data_ptr()) if m is not None else None  # noqa: E731
-        _lib.check(self.L.sgb_reset_masked(self._ctx, self.B, self.N, C.byref(self._buf), ptr(em), ptr(am), self.path_lo,
-                                           self.path_hi, self.seed, self.epoch, self.env_offset, self.max_reset_tries,
+        _lib.check(self.L.sgb_reset_masked(self._ctx, self.B, self.N, C.byref(self._buf), ptr(em), ptr(am), path_lo,
+                                           path_hi, self.seed, self.epoch, self.env_offset, self.max_reset_tries,
                                            int(write_obs), C.c_void_p(self.n_failed.data_ptr()), self._stream()),
                    "sgb_reset_masked")
 

@@ -163,6 +163,10 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             known.setdefault("scenario_type", "cpm_entire")
             cfg = EnvConfig(mode="kwargs", **known)
         self.config = cfg
+        # evaluation set-up (helper_common.py:110-118; road_traffic.py:842-853): fixed reference paths and start poses
+        par = getattr(self, "parameters", None)
+        predef = kwargs.get("predefined_ref_path_idx", getattr(par, "predefined_ref_path_idx", None))
+        init_state = kwargs.get("init_state", getattr(par, "init_state", None))
         self.env = RoadTrafficEnv(cfg, num_envs=batch_dim, device=device, seed=seed, env_offset=env_offset, debug=debug,
                                   info=True)
         self.n_agents = self.env.N
@@ -183,11 +187,41 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             steering=torch.tensor(MAX_STEERING, device=dev, dtype=torch.float32),
             dist=torch.tensor(cfg.lane_width(m) * 3, device=dev, dtype=torch.float32))
         self._zeros_bn = torch.zeros(batch_dim, device=dev, dtype=torch.float32)
+        self._predef_paths = self._init_state = None
+        if predef is not None:
+            if init_state is None or len(predef) != self.env.N or len(init_state) != self.env.N:
+                raise ValueError("predefined_ref_path_idx needs init_state, both with one entry per agent")
+            lo, hi = self.env.path_lo, self.env.path_hi          # indices count within the scenario's path set
+            ids = torch.as_tensor([int(i) for i in predef], dtype=torch.int32) + lo
+            if int(ids.min()) < lo or int(ids.max()) >= hi:
+                raise ValueError(f"predefined_ref_path_idx {list(predef)} outside the {hi - lo} paths of {cfg.scenario_type}")
+            self._predef_paths = ids.to(dev)
+            self._init_state = torch.as_tensor(init_state, dtype=torch.float32).reshape(self.env.N, 3).to(dev)
         return world
+
+    def _reset_to_init_state(self, env_index: Optional[int]):
+        """world_state_rt_sim.py:99-125: every agent at its (x, y, rot) of ``init_state`` on its predefined path, speed,
+        velocity, steering and side-slip zero; then what any reset re-derives (sgb_refresh, all-fresh observation)."""
+        e = self.env
+        sl = slice(None) if env_index is None else int(env_index)
+        e.pose[sl, :, 0:3] = self._init_state
+        e.pose[sl, :, 3] = 0.0
+        e.aux[sl] = 0.0
+        e.path_id[sl] = self._predef_paths
+        e.step_count[sl] = 0
+        e.done[sl] = 0
+        mask = None
+        if env_index is not None:
+            mask = torch.zeros(e.B, dtype=torch.uint8, device=e.device)
+            mask[int(env_index)] = 1
+        e.refresh(env_mask=mask, write_obs=True)
 
     # -- road_traffic.py:816
     def reset_world_at(self, env_index: Optional[int] = None, agent_index: Optional[int] = None):
         e = self.env
+        if agent_index is None and self._predef_paths is not None:
+            self._reset_to_init_state(env_index)     # road_traffic.py:842-853
+            return
         if env_index is None:
             e.reset()
             return
@@ -195,12 +229,19 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             # single-agent respawn (any map, any mode); the step-time observation stays, like in the reference
             m = torch.zeros(e.B, e.N, dtype=torch.uint8, device=e.device)
             m[int(env_index), int(agent_index)] = 1
-            e.reset_masked(agent_mask=m, write_obs=False)
+            e.reset_masked(agent_mask=m, write_obs=False, path_range=self._respawn_range(int(agent_index)))
             return
         m = torch.zeros(e.B, dtype=torch.uint8, device=e.device)
         m[int(env_index)] = 1
         e.reset_masked(env_mask=m, write_obs=True)
         e.done[int(env_index)] = 0
+
+    def _respawn_range(self, agent_index: int):
+        """Path range a respawn of this agent draws from: its predefined path if there is one, else the env's set."""
+        if self._predef_paths is None:
+            return None
+        p = int(self._predef_paths[agent_index])
+        return (p, p + 1)
 
     def process_action(self, agent):
         pass
@@ -222,7 +263,13 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             if e.cfg.testing_mode:
                 which |= _lib.SGB_FLAG_COLLIDE_AGENT | _lib.SGB_FLAG_COLLIDE_LANE
             crossing = ((e.agent_flags & which) != 0) & ~is_done.unsqueeze(1)
-            e.reset_masked(agent_mask=crossing, write_obs=False)
+            if self._predef_paths is None:
+                e.reset_masked(agent_mask=crossing, write_obs=False)
+            else:   # every agent comes back on ITS predefined path (world_state_rt_sim.py:241-242): one launch per agent
+                for a in torch.nonzero(crossing.any(dim=0)).flatten().tolist():
+                    col = torch.zeros_like(crossing)
+                    col[:, a] = crossing[:, a]
+                    e.reset_masked(agent_mask=col, write_obs=False, path_range=self._respawn_range(a))
         self._stepped = False
         return is_done
 

@@ -118,6 +118,54 @@ def test_cuda_observation_masks_match_oracle(oracle_mod, scenario, N, rew, mode,
     assert (last[..., :2] == 1.0).all(-1).any(), "no masked neighbour seen: the test would not exercise the mask"
 
 
+def test_facade_predefined_paths_and_init_state(oracle_mod):
+    """parameters.predefined_ref_path_idx / init_state (helper_common.py:110-118; road_traffic.py:842-853;
+    world_state_rt_sim.py:99-125, 241-242 — the evaluation set-up of eva_at25): every (full) reset puts the agents at the
+    given poses with zero speed on the given paths; a single-agent respawn draws a point on that agent's own path."""
+    from sigmarl_b200 import make_env
+    O = oracle_mod
+    pm = O.PaddedMap("cpm_entire")
+    paths = [0, 5, 12]
+    init = [[float(pm.center[p, 10 + 7 * i, 0]), float(pm.center[p, 10 + 7 * i, 1]), float(pm.yaw[p, 10 + 7 * i])]
+            for i, p in enumerate(paths)]
+    B, N = 8, 3
+    env = make_env(scenario_type="cpm_entire", num_envs=B, device="cuda:0", n_agents=N, seed=1, max_steps=32,
+                   predefined_ref_path_idx=paths, init_state=init)
+    sc, e = env.scenario, env.scenario.env
+
+    def check_init(rows):
+        torch.cuda.synchronize()
+        assert np.array_equal(e.pose.cpu().numpy()[rows][..., :3], np.broadcast_to(np.float32(init), (len(rows), N, 3)))
+        assert float(e.pose[rows][..., 3].abs().max()) == 0.0 and float(e.aux[rows].abs().max()) == 0.0
+        assert np.array_equal(e.path_id.cpu().numpy()[rows], np.broadcast_to(np.int32(paths), (len(rows), N)))
+        assert int(e.step_count[rows].abs().max()) == 0
+        w = O.OracleWorld("cpm_entire", B, N, mode="kwargs", max_steps=32)
+        w.set_state(e.pos.cpu().numpy(), e.rot.cpu().numpy(), e.speed.cpu().numpy(), e.steering.cpu().numpy(),
+                    e.path_id.cpu().numpy())
+        want = O.fresh_obs(w)
+        assert np.abs(e.obs.cpu().numpy()[rows] - want[rows]).max() <= 1e-5
+
+    check_init(list(range(B)))
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for t in range(6):
+        acts = [torch.stack([0.5 + 0.3 * torch.rand(B, generator=gen, device="cuda"),
+                             (torch.rand(B, generator=gen, device="cuda") * 2 - 1) * 0.1], -1) for _ in range(N)]
+        env.step(acts)
+    assert float((e.pos.cpu() - torch.as_tensor(init)[:, :2]).abs().max()) > 0.05      # they did move
+    env.reset_at(3)                                                                     # full reset of one env
+    check_init([3])
+    assert float((e.pos[0].cpu() - torch.as_tensor(init)[:, :2]).abs().max()) > 0.05   # ... and only that env
+    before = e.pose.clone()
+    sc.reset_world_at(env_index=5, agent_index=1)                                        # respawn: own path, new point
+    torch.cuda.synchronize()
+    assert int(e.path_id[5, 1]) == paths[1] and not torch.equal(e.pose[5, 1], before[5, 1])
+    cen = pm.center[paths[1], :int(pm.n_center[paths[1]])]
+    assert np.abs(cen - e.pos[5, 1].cpu().numpy()).sum(-1).min() == 0.0                # exactly on a centre point of path 5
+    keep = torch.ones(B, N, dtype=torch.bool)
+    keep[5, 1] = False
+    assert torch.equal(e.pose.cpu()[keep], before.cpu()[keep])
+
+
 # ---- MTV agent distance: separate kernel instantiations, run after everything else
 @pytest.mark.parametrize("path", NEXT_MTV, ids=_ids)
 @pytest.mark.parametrize("exhaustive", [False, True], ids=["pruned", "exhaustive"])
