@@ -1,0 +1,165 @@
+"""CPU: host-side logic of the VMAS-shaped facade (sigmarl_b200/scenario.py) with the CUDA environment replaced by a
+recording stand-in.  Nothing is computed here — the stand-in only owns CPU tensors of the right shapes and logs which
+library entry points the facade would call with which masks / path ranges — so this checks indexing, broadcasting,
+argument plumbing and error behaviour of the facade; the arithmetic behind it is covered by the -m gpu tests
+(the product path itself refuses to run without the CUDA library and a device, see test_abi_and_host.py)."""
+import numpy as np
+import pytest
+import torch
+
+from sigmarl_b200 import EnvConfig, lib as L
+from sigmarl_b200 import scenario as S
+from sigmarl_b200.maps import MapLibrary
+
+
+class _RecordingEnv:
+    """Shape-compatible stand-in for RoadTrafficEnv: state tensors on the CPU, every launch recorded in ``calls``."""
+
+    def __init__(self, cfg, num_envs=4, device="cpu", seed=0, env_offset=0, debug=False, info=False, **kw):
+        self.config = cfg
+        self.map = MapLibrary(cfg.scenario_type)
+        self.cfg = cfg.lower(self.map)            # the real lowering / validation runs
+        r = cfg.resolved(cfg.lane_width(self.map), self.map.default_n_agents)
+        self.B, self.N, self.dt, self.device = int(num_envs), int(r["n_agents"]), r["dt"], torch.device("cpu")
+        self.D = cfg.obs_dim(self.N)
+        self.path_lo, self.path_hi = self.map.default_path_range(cfg.cpm_scenario_probabilities)
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype)  # noqa: E731
+        B, N = self.B, self.N
+        self.pose, self.aux, self.carry, self.action = z(B, N, 4), z(B, N, 4), z(B, N, 4), z(B, N, 2)
+        self.path_id, self.step_count = z(B, N, dtype=torch.int32), z(B, dtype=torch.int32)
+        self.obs, self.reward, self.done = z(B, N, self.D), z(B, N), z(B, dtype=torch.uint8)
+        self.agent_flags, self.collide_with = z(B, N, dtype=torch.uint8), z(B, N, dtype=torch.int32)
+        self.info = z(B, N, L.SGB_INFO_DIM)
+        self.task_tries, self.task_success = z(B, dtype=torch.int32), z(B, dtype=torch.int32)
+        self.calls = []
+
+    def step(self, action=None):
+        self.calls.append(("step",))
+        self.step_count += 1
+
+    def reset(self):
+        self.calls.append(("reset",))
+
+    def refresh(self, env_mask=None, write_obs=False):
+        self.calls.append(("refresh", None if env_mask is None else env_mask.clone(), bool(write_obs)))
+
+    def reset_masked(self, env_mask=None, agent_mask=None, write_obs=True, path_range=None):
+        self.calls.append(("reset_masked", None if env_mask is None else env_mask.clone(),
+                           None if agent_mask is None else agent_mask.clone(), bool(write_obs), path_range))
+
+
+@pytest.fixture
+def facade(monkeypatch):
+    monkeypatch.setattr(S, "RoadTrafficEnv", _RecordingEnv)
+
+    def make(num_envs=4, **kw):
+        sc = S.ScenarioRoadTrafficB200()
+        world = sc.env_make_world(num_envs, "cpu", **kw)
+        return sc, world, sc.env
+    return make
+
+
+def test_world_surface_and_views(facade):
+    """Attribute surface the trainer reads (road_traffic.py:104-110, 770-814; helper_training.py:791-861)."""
+    sc, world, e = facade(scenario_type="cpm_entire", n_agents=3)
+    assert world.batch_dim == 4 and len(world.agents) == 3 and world.dt == 0.05          # kwargs mode
+    a = world.agents[1]
+    assert a.dynamics.needed_action_size == 2 and a.u_range == [1.0, pytest.approx(31 * np.pi / 180)]
+    e.pose[:, 1] = torch.tensor([1.0, 2.0, 0.5, 0.7])
+    e.aux[:, 1] = torch.tensor([0.1, 0.3, 0.4, 0.05])
+    assert a.state.pos.shape == (4, 2) and a.state.rot.shape == (4, 1) and a.state.speed.shape == (4, 1)
+    assert torch.equal(a.state.pos[0], torch.tensor([1.0, 2.0])) and float(a.state.steering[0]) == pytest.approx(0.1)
+    assert torch.equal(a.state.vel[0], torch.tensor([0.3, 0.4])) and float(a.state.sideslip_angle[0]) == pytest.approx(0.05)
+    a.action.u = torch.full((4, 2), 0.25)
+    assert torch.equal(e.action[:, 1], torch.full((4, 2), 0.25)) and float(e.action[:, 0].abs().max()) == 0.0
+    assert sc.reward(a).shape == (4,) and sc.observation(a).shape == (4, e.D)
+    info = sc.info(a)
+    assert len(info) == 39 and info["pos"].shape == (4, 2) and info["ref"].shape == (4, 6)
+
+
+def test_reset_world_at_plumbing(facade):
+    sc, world, e = facade(scenario_type="cpm_mixed", n_agents=4)
+    sc.reset_world_at(None)
+    assert e.calls[-1] == ("reset",)
+    sc.reset_world_at(2)
+    kind, em, am, wo, pr = e.calls[-1]
+    assert kind == "reset_masked" and em.tolist() == [0, 0, 1, 0] and am is None and wo and pr is None
+    sc.reset_world_at(env_index=1, agent_index=3)
+    kind, em, am, wo, pr = e.calls[-1]
+    assert em is None and int(am.sum()) == 1 and int(am[1, 3]) == 1 and not wo and pr is None
+
+
+def test_done_respawns_only_crossers_of_running_envs(facade):
+    """road_traffic.py:1462-1472: entry / exit crossers are respawned inside done() unless their env is done anyway;
+    cpm_entire has no entries / exits; testing mode respawns colliding agents too (:1435-1447)."""
+    sc, world, e = facade(scenario_type="cpm_mixed", n_agents=3)
+    e.agent_flags[0, 1] = L.SGB_FLAG_EXIT
+    e.agent_flags[1, 2] = L.SGB_FLAG_EXIT | L.SGB_FLAG_COLLIDE_LANE
+    e.agent_flags[2, 0] = L.SGB_FLAG_COLLIDE_AGENT
+    e.done[1] = 1
+    world.step()
+    d = sc.done()
+    assert d.tolist() == [False, True, False, False]
+    kind, em, am, wo, pr = e.calls[-1]
+    assert kind == "reset_masked" and am.nonzero().tolist() == [[0, 1]] and not wo
+    n = len(e.calls)
+    sc.done()                                   # without a step in between nothing is respawned twice
+    assert len(e.calls) == n
+    sc2, world2, e2 = facade(scenario_type="cpm_entire", n_agents=3)
+    e2.agent_flags[0, 1] = L.SGB_FLAG_COLLIDE_LANE
+    world2.step(); sc2.done()
+    assert [c[0] for c in e2.calls] == ["step"]
+    sc3, world3, e3 = facade(scenario_type="cpm_entire", n_agents=3, is_testing_mode=True)
+    e3.agent_flags[0, 1] = L.SGB_FLAG_COLLIDE_LANE
+    world3.step(); sc3.done()
+    assert e3.calls[-1][0] == "reset_masked" and e3.calls[-1][2].nonzero().tolist() == [[0, 1]]
+
+
+def test_predefined_paths_and_init_state(facade):
+    """road_traffic.py:842-853, world_state_rt_sim.py:99-125, 241-242."""
+    init = [[1.0, 2.0, 0.1], [3.0, 1.0, -0.2], [2.0, 2.5, 3.0]]
+    sc, world, e = facade(scenario_type="cpm_mixed", n_agents=3, predefined_ref_path_idx=[0, 5, 7], init_state=init)
+    lo = e.path_lo                                # cpm_mixed: the intersection set does not start at global path 0
+    e.pose.fill_(9.0); e.aux.fill_(9.0); e.step_count.fill_(7); e.done.fill_(1)
+    sc.reset_world_at(None)
+    assert torch.equal(e.pose[..., :3], torch.tensor(init).expand(4, 3, 3)) and float(e.pose[..., 3].abs().max()) == 0
+    assert float(e.aux.abs().max()) == 0 and int(e.step_count.max()) == 0 and int(e.done.max()) == 0
+    assert e.path_id.tolist() == [[lo, lo + 5, lo + 7]] * 4
+    assert e.calls[-1][0] == "refresh" and e.calls[-1][1] is None and e.calls[-1][2]
+    e.pose.fill_(9.0); e.step_count.fill_(7)
+    sc.reset_world_at(2)                          # one env only
+    assert torch.equal(e.pose[2, :, :3], torch.tensor(init)) and float(e.pose[0].min()) == 9.0
+    assert e.step_count.tolist() == [7, 7, 0, 7] and e.calls[-1][1].tolist() == [0, 0, 1, 0]
+    sc.reset_world_at(env_index=3, agent_index=1)   # respawn on the agent's own path
+    assert e.calls[-1][0] == "reset_masked" and e.calls[-1][4] == (lo + 5, lo + 6)
+    e.agent_flags[0, 0] = L.SGB_FLAG_EXIT
+    e.agent_flags[1, 2] = L.SGB_FLAG_EXIT
+    e.agent_flags[3, 2] = L.SGB_FLAG_ENTRY
+    e.done.zero_()
+    n = len(e.calls)
+    world.step(); sc.done()
+    new = e.calls[n + 1:]
+    assert [(c[0], c[4]) for c in new] == [("reset_masked", (lo, lo + 1)), ("reset_masked", (lo + 7, lo + 8))]
+    assert new[0][2].nonzero().tolist() == [[0, 0]] and new[1][2].nonzero().tolist() == [[1, 2], [3, 2]]
+    with pytest.raises(ValueError):
+        facade(scenario_type="cpm_mixed", n_agents=3, predefined_ref_path_idx=[0, 5], init_state=init)
+    with pytest.raises(ValueError):
+        facade(scenario_type="cpm_mixed", n_agents=3, predefined_ref_path_idx=[0, 5, 999], init_state=init)
+
+
+def test_parameters_object_reaches_the_config(facade):
+    """mappo_cavs.py:168-169: ``scenario.parameters = parameters`` before make_world; flags of the reference map onto
+    EnvConfig, including the ones whose class defaults are ON in helper_common.py (MTV distance, masks, noise)."""
+    class P:
+        scenario_type, n_agents, dt, max_steps, rew_method = "roundabout_2", 5, 0.1, 64, "ttc_sparse"
+        is_use_mtv_distance, is_apply_mask, is_obs_noise, obs_noise_level = True, True, True, 0.05
+        is_ego_view, n_nearing_agents_observed, reset_agent_fixed_duration = True, 3, 2
+        is_using_cbf = False                      # unknown to EnvConfig: ignored
+    sc = S.ScenarioRoadTrafficB200()
+    sc.parameters = P()
+    sc.env_make_world(8, "cpu")
+    c = sc.env.cfg
+    assert sc.config.mode == "params" and sc.env.N == 5 and c.use_mtv_distance == 1 and c.reset_fixed_period == 20
+    assert c.obs_flags == L.SGB_OBS_APPLY_MASK and abs(c.obs_noise_level - 0.05) < 1e-7 and c.k_near == 3
+    assert c.near_agents_low == 0.0 and c.near_agents_high == float(np.float32(0.22))
+    assert c.rew_flags == L.SGB_REW_TTC | L.SGB_REW_SPARSE
