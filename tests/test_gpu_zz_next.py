@@ -233,7 +233,9 @@ def test_facade_info_matches_reference_goldens_mtv(path):
 @pytest.mark.parametrize("scenario,N,rew,mode,B,k_obs,flags", [
     ("cpm_entire", 8, "distance", "params", 512, 2, dict()),                         # G = 4, default layout
     ("roundabout_2", 12, "ttc", "kwargs", 256, 3, dict(is_obs_steering=True)),       # G = 2, crowded map
-    ("cpm_entire", 18, "distance_sparse", "params", 64, 2, dict(is_ego_view=False)), # G = 1, bird view
+    ("interchange_2", 17, "distance_sparse", "params", 64, 2, dict(is_ego_view=False)),  # G = 1, bird view (with the 2 KB of
+                                                                                         # MTV arrays cpm_entire holds N <= 16)
+    ("cpm_entire", 15, "ttc_sparse", "kwargs", 128, 2, dict()),                      # the reference's default N on this map
     ("cpm_mixed", 6, "ttc_sparse", "params", 256, 5, dict(reset_agent_fixed_duration=1)),
 ])
 def test_cuda_mtv_distance_matches_oracle_free_running(oracle_mod, scenario, N, rew, mode, B, k_obs, flags):
