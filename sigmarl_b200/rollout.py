@@ -121,3 +121,70 @@ def all_gather_advantages(buf: RolloutBuffer, group=None):
     for full in (buf.adv_all, buf.target_all):
         dist.all_gather_into_tensor(full.view(-1), full[buf.rank].reshape(-1), group=group)
     return buf.adv_all, buf.target_all
+
+
+# ---- evaluation recordings ("out_td") --------------------------------------------------------------------------
+# The reference's evaluation keeps the rollout's TensorDict ("out_td") and reads a handful of info entries from it
+# (helper_common.py:581-611 trim_td, helper_training.py:1638-1698 reduce_out_td): leaves named
+# ("agents", "info", key) with shape [num_envs, T, n_agents, F].  tensordict is not a dependency of this library, so
+# the same layout is kept as a nested dict of tensors (``TensorDict(nested, batch_size=[B, T])`` wraps it as is).
+OUT_TD_KEYS = ("pos", "rot", "vel", "ref", "ref_lanelet_ids", "is_collision_with_agents",
+               "is_collision_with_lanelets")          # helper_common.py:591-599
+
+
+def record_out_td(env, policy: Callable, T: int, keys=OUT_TD_KEYS, reset_done: bool = True):
+    """Drive a VMAS(-like) environment of ``ScenarioRoadTrafficB200`` for T steps and stack what evaluation reads.
+
+    `env`: ``vmas.Environment`` or ``VmasLikeEnvironment``; `policy(list of obs [B,D]) -> list of actions [B,2]``.
+    Returns ``{"agents": {"observation": [B,T,N,D], "action": [B,T,N,2], "reward": [B,T,N,1],
+    "info": {key: [B,T,N,F]}}, "done": [B,T,1]}`` — step-time values, i.e. what ``env.step`` returned at step t
+    (TorchRL's ("next", ...) entries); bool entries stay bool (reduce_out_td's ``> 0.5`` accepts both).  Done envs
+    are reset between steps like TorchRL's collector does (``reset_at``) unless `reset_done` is False."""
+    agents = env.agents
+    obs = [env.scenario.observation(a).clone() for a in agents]
+    rec = dict(observation=[], action=[], reward=[], done=[], info={k: [] for k in keys})
+    for _ in range(T):
+        acts = policy(obs)
+        rec["observation"].append(torch.stack(obs, dim=1))
+        rec["action"].append(torch.stack([a.reshape(obs[0].shape[0], -1) for a in acts], dim=1))
+        obs, rews, dones, infos = env.step(acts)
+        rec["reward"].append(torch.stack(rews, dim=1).unsqueeze(-1))
+        rec["done"].append(dones.reshape(-1, 1).clone())
+        B = dones.shape[0]
+        for k in keys:
+            rec["info"][k].append(torch.stack([torch.as_tensor(i[k]).reshape(B, -1) for i in infos], dim=1))
+        if reset_done and bool(dones.any()):
+            for b in torch.nonzero(dones).flatten().tolist():
+                env.reset_at(b)
+            obs = [env.scenario.observation(a).clone() for a in agents]
+    st = lambda xs: torch.stack(xs, dim=1)  # noqa: E731   [B, T, ...]
+    return {"agents": {"observation": st(rec["observation"]), "action": st(rec["action"]), "reward": st(rec["reward"]),
+                       "info": {k: st(v) for k, v in rec["info"].items()}},
+            "done": st(rec["done"])}
+
+
+def trim_out_td(out_td: dict, keys=OUT_TD_KEYS) -> dict:
+    """helper_common.py:581-611 trim_td: keep only the selected ("agents", "info", key) leaves."""
+    return {"agents": {"info": {k: out_td["agents"]["info"][k] for k in keys}}}
+
+
+def reduce_out_td(out_td: dict, convert_collisions_to_bool: bool = True) -> dict:
+    """helper_training.py:1638-1698 reduce_out_td for a single-env recording: (1, T, A, F) -> (T, A, F) leaves
+    ``pos, rot (T, A), vel, is_collision_with_agents, is_collision_with_lanelets``; same errors on other shapes."""
+    info = out_td["agents"]["info"]
+
+    def squeeze_b1(name):
+        if name not in info:
+            raise KeyError(f"Missing key ('agents', 'info', '{name}') in out_td")
+        x = info[name]
+        if x.dim() < 4:
+            raise ValueError(f"Expected a tensor with 4 dims (1,T,A,F), got shape {tuple(x.shape)}")
+        if x.shape[0] != 1:
+            raise ValueError(f"Expected leading batch size 1, got {x.shape[0]}")
+        return x.squeeze(0)
+
+    col_a, col_l = squeeze_b1("is_collision_with_agents"), squeeze_b1("is_collision_with_lanelets")
+    if convert_collisions_to_bool:
+        col_a, col_l = col_a > 0.5 if col_a.dtype != torch.bool else col_a, col_l > 0.5 if col_l.dtype != torch.bool else col_l
+    return {"pos": squeeze_b1("pos"), "rot": squeeze_b1("rot").squeeze(-1), "vel": squeeze_b1("vel"),
+            "is_collision_with_agents": col_a, "is_collision_with_lanelets": col_l}

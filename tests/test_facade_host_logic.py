@@ -163,3 +163,31 @@ def test_parameters_object_reaches_the_config(facade):
     assert c.obs_flags == L.SGB_OBS_APPLY_MASK and abs(c.obs_noise_level - 0.05) < 1e-7 and c.k_near == 3
     assert c.near_agents_low == 0.0 and c.near_agents_high == float(np.float32(0.22))
     assert c.rew_flags == L.SGB_REW_TTC | L.SGB_REW_SPARSE
+
+
+def test_out_td_recording_layout(facade):
+    """helper_common.py:581-611 / helper_training.py:1638-1698: leaves ("agents", "info", key) shaped [B, T, A, F]."""
+    from sigmarl_b200.rollout import OUT_TD_KEYS, record_out_td, reduce_out_td, trim_out_td
+    monkey_sc = S.ScenarioRoadTrafficB200()
+    env = S.VmasLikeEnvironment(monkey_sc, num_envs=1, device="cpu", max_steps=16, scenario_type="cpm_entire", n_agents=3)
+    e = monkey_sc.env
+    e.pose[0, :, 0] = torch.tensor([1.0, 2.0, 3.0])
+    e.agent_flags[0, 2] = L.SGB_FLAG_COLLIDE_LANE
+    policy = lambda obs: [torch.full((1, 2), 0.1 * (i + 1)) for i in range(len(obs))]  # noqa: E731
+    out = record_out_td(env, policy, T=5)
+    info = out["agents"]["info"]
+    assert set(info) == set(OUT_TD_KEYS)
+    assert info["pos"].shape == (1, 5, 3, 2) and info["rot"].shape == (1, 5, 3, 1) and info["ref"].shape == (1, 5, 3, 6)
+    assert info["is_collision_with_lanelets"].shape == (1, 5, 3, 1) and info["is_collision_with_lanelets"].dtype == torch.bool
+    assert info["ref_lanelet_ids"].shape == (1, 5, 3, e.map.n_lanelets_all)
+    assert out["agents"]["observation"].shape == (1, 5, 3, e.D) and out["agents"]["action"].shape == (1, 5, 3, 2)
+    assert out["agents"]["reward"].shape == (1, 5, 3, 1) and out["done"].shape == (1, 5, 1)
+    assert torch.equal(out["agents"]["action"][0, :, 1], torch.full((5, 2), 0.2))
+    assert info["pos"][0, :, :, 0].tolist() == [[1.0, 2.0, 3.0]] * 5
+    red = reduce_out_td(out)
+    assert red["pos"].shape == (5, 3, 2) and red["rot"].shape == (5, 3) and red["is_collision_with_lanelets"].shape == (5, 3, 1)
+    assert red["is_collision_with_lanelets"][:, 2].all() and not red["is_collision_with_agents"].any()
+    assert set(trim_out_td(out)["agents"]["info"]) == set(OUT_TD_KEYS)
+    two = {"agents": {"info": {k: torch.cat([v, v]) for k, v in info.items()}}}
+    with pytest.raises(ValueError):
+        reduce_out_td(two)
