@@ -129,6 +129,12 @@ CONFIGS = {
     "mask_cpm_mixed_B4_N5_birdview_k3": dict(st="cpm_mixed", B=4, N=5, T=50, mode="params", seed=83, gentle=True,
                                             extra=dict(is_apply_mask=True, is_ego_view=False,
                                                        n_nearing_agents_observed=3)),
+    # more agents than a 4-lane group layout holds: the reference's default n_agents on cpm_entire (15; two lanes per
+    # agent on the GPU) and 18 (one lane per agent)
+    "big_cpm_entire_B4_N15_ttc_sparse": dict(st="cpm_entire", B=4, N=15, T=30, mode="params", seed=95,
+                                            extra=dict(rew_method="ttc_sparse")),
+    "big_cpm_entire_B2_N18_distance_k4": dict(st="cpm_entire", B=2, N=18, T=30, mode="kwargs", seed=96, gentle=True,
+                                             extra=dict(n_nearing_agents_observed=4)),
     # the remaining maps of constants.py (interchange_1-3, intersection_2-8): open paths, entry / exit respawns
     "map_interchange_1_B4_N4": dict(st="interchange_1", B=4, N=4, T=40, mode="kwargs", seed=61, gentle=True),
     "map_interchange_2_B4_N6": dict(st="interchange_2", B=4, N=6, T=40, mode="params", seed=62, gentle=True,
@@ -148,7 +154,7 @@ CONFIGS = {
 # fixtures of features added after the last hardware session: tests/golden/next/ (tests/conftest.py)
 NEXT = {"cpm_entire_B4_N3_fixed2s_gentle", "cpm_mixed_B4_N3_fixed1s_testing_gentle", "mtv_cpm_entire_B4_N6_distance",
         "mtv_cpm_mixed_B4_N5_ttc_sparse_gentle", "mtv_roundabout_2_B4_N10_kw_k3"}
-NEXT |= {n for n in CONFIGS if n.startswith(("map_", "mask_"))}
+NEXT |= {n for n in CONFIGS if n.startswith(("map_", "mask_", "big_"))}
 
 OBS_FLAGS = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
              "is_observe_distance_to_agents", "is_observe_distance_to_center_line",
