@@ -1,8 +1,11 @@
-"""GPU parity for the features added after the round's last hardware session (fixtures in tests/golden/next/):
-``reset_agent_fixed_duration`` (road_traffic.py:1388-1393) and the MTV agent distance (``is_use_mtv_distance``,
-helper_scenario.py:1030-1138).  The oracle is pinned on the same fixtures on the CPU (test_oracle_golden.py); these
-run the CUDA path through the C-ABI against them, with exactly the checks of test_gpu_parity.py.  The file sorts after
-the rest of the suite on purpose: it is the part that has not been on a B200 yet.
+"""GPU parity for everything added after the round's last hardware session (fixtures in tests/golden/next/):
+``reset_agent_fixed_duration`` (road_traffic.py:1388-1393), the ten remaining maps, observation masks
+(``is_apply_mask``), goldens at 15 / 18 agents, predefined paths / ``init_state`` in the facade, a mirror of the
+reference's own integration test, and — last, because it runs its own kernel instantiations — the MTV agent distance
+(``is_use_mtv_distance``, helper_scenario.py:1030-1138).  The oracle is pinned on the same fixtures on the CPU
+(test_oracle_golden.py); these run the CUDA path through the C-ABI against them, with exactly the checks of
+test_gpu_parity.py.  The file sorts after the rest of the suite on purpose: it is the part that has not been on a B200
+yet.
 """
 import os
 
