@@ -117,6 +117,33 @@ class WorldB200:
         pass  # state is overwritten by reset_world_at (vmas zeroes it first; nothing reads the zeros)
 
 
+class _Observations:
+    """``observation_provider.observations`` as far as callers outside the scenario read it: ``nearing_agents_indices``
+    [B, N, k] (observation_provider_rt.py:627-636; read by helper_training.py:240, 254 through ``scenario.observations``).
+    The kernel selects the k nearest agents on the fly and does not store their indices; this view recomputes them on
+    demand from the current positions with the reference's own formula (helper_scenario.py:1012-1029, 1140-1143:
+    centre distances, own entry := world diagonal, ``torch.topk(largest=False)``)."""
+
+    def __init__(self, scenario):
+        self._sc = scenario
+
+    @property
+    def n_nearing_agents(self):
+        return int(self._sc.env.cfg.k_near)
+
+    @property
+    def nearing_agents_indices(self) -> torch.Tensor:
+        e = self._sc.env
+        if e.config.is_use_mtv_distance:
+            raise NotImplementedError("nearing_agents_indices is recomputed from centre distances; with "
+                                      "is_use_mtv_distance the selection uses the MTV distance inside the kernel")
+        pos = e.pose[..., 0:2]
+        d = torch.sqrt(((pos.unsqueeze(2) - pos.unsqueeze(1)) ** 2).sum(-1))
+        diag = math.sqrt(float(self._sc._norm["pos_world"][0]) ** 2 + float(self._sc._norm["pos_world"][1]) ** 2)
+        d.diagonal(dim1=-2, dim2=-1).fill_(diag)
+        return torch.topk(d, k=self.n_nearing_agents, dim=-1, largest=False).indices
+
+
 class ScenarioRoadTrafficB200(_VmasBaseScenario):
     def __init__(self):
         if _HAVE_VMAS:  # pragma: no cover
@@ -187,6 +214,8 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             steering=torch.tensor(MAX_STEERING, device=dev, dtype=torch.float32),
             dist=torch.tensor(cfg.lane_width(m) * 3, device=dev, dtype=torch.float32))
         self._zeros_bn = torch.zeros(batch_dim, device=dev, dtype=torch.float32)
+        self.observations = _Observations(self)                      # the (stale) name helper_training.py:240 uses
+        self.observation_provider = type("ObservationProvider", (), dict(observations=self.observations))()
         self._predef_paths = self._init_state = None
         if predef is not None:
             if init_state is None or len(predef) != self.env.N or len(init_state) != self.env.N:

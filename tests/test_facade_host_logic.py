@@ -191,3 +191,17 @@ def test_out_td_recording_layout(facade):
     two = {"agents": {"info": {k: torch.cat([v, v]) for k, v in info.items()}}}
     with pytest.raises(ValueError):
         reduce_out_td(two)
+
+
+def test_nearing_agents_indices_view(facade):
+    """scenario.observations.nearing_agents_indices (helper_training.py:240, 254; observation_provider_rt.py:627-636)."""
+    sc, world, e = facade(num_envs=2, scenario_type="cpm_entire", n_agents=4, n_nearing_agents_observed=2)
+    e.pose[0, :, 0] = torch.tensor([0.0, 1.0, 1.5, 4.0])      # env 0: agents on a line
+    e.pose[1, :, 1] = torch.tensor([0.0, 3.0, 0.4, 0.5])
+    idx = sc.observations.nearing_agents_indices
+    assert idx.shape == (2, 4, 2) and sc.observation_provider.observations is sc.observations
+    assert idx[0].tolist() == [[1, 2], [2, 0], [1, 0], [2, 1]]
+    assert idx[1].tolist() == [[2, 3], [3, 2], [3, 0], [2, 0]]
+    sc2, _, _ = facade(scenario_type="cpm_entire", n_agents=3, is_use_mtv_distance=True)
+    with pytest.raises(NotImplementedError):
+        sc2.observations.nearing_agents_indices
