@@ -179,6 +179,8 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
 
     # -- road_traffic.py:104
     def make_world(self, batch_dim: int, device, **kwargs):
+        if getattr(self, "_parameters_from_kwargs", False):      # a second make_world on a kwargs-mode scenario
+            self.parameters = None
         seed = kwargs.pop("seed", 0)
         env_offset = kwargs.pop("env_offset", 0)
         debug = kwargs.pop("debug", False)
@@ -199,7 +201,21 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
         self.n_agents = self.env.N
         self.max_speed, self.max_steering = MAX_SPEED, torch.tensor(MAX_STEERING, device=self.env.device)
         world = WorldB200(self.env, self)
-        world.parameters = getattr(self, "parameters", None)
+        if getattr(self, "parameters", None) is None:
+            # kwargs mode: the reference builds its own Parameters from the kwargs (road_traffic.py:317-361); callers read
+            # these attributes through ``scenario.parameters`` (helper_training.py:207-253, 596-641, 709-741)
+            import types
+            self._parameters_from_kwargs = True
+            self.parameters = types.SimpleNamespace(
+                **{k: getattr(cfg, k) for k in cfg.__dataclass_fields__ if k not in ("extras", "mode", "exhaustive")})
+            self.parameters.n_agents, self.parameters.num_vmas_envs = self.env.N, batch_dim
+            self.parameters.dt, self.parameters.device = self.env.dt, self.env.device
+            for flag in ("is_using_cbf", "is_using_cbf_training", "is_using_cbf_testing", "is_using_centralized_cbf",
+                         "is_apply_cbf_action", "is_using_prioritized_marl", "is_using_opponent_modeling",
+                         "is_communication_noise", "is_real_time_rendering"):
+                setattr(self.parameters, flag, False)        # policy-side branches outside this library
+            self.parameters.communication_noise_level = 0.0
+        world.parameters = self.parameters
         self._world = world
         # evaluation counters (road_traffic.py:763-768): incremented by the kernel, same tensors
         self.num_task_tries = self.env.task_tries

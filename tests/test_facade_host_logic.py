@@ -205,3 +205,14 @@ def test_nearing_agents_indices_view(facade):
     sc2, _, _ = facade(scenario_type="cpm_entire", n_agents=3, is_use_mtv_distance=True)
     with pytest.raises(NotImplementedError):
         sc2.observations.nearing_agents_indices
+
+
+def test_kwargs_mode_exposes_parameters(facade):
+    """helper_training.py:207-253, 709-741 read scenario.parameters.* whatever the construction mode."""
+    sc, world, e = facade(num_envs=6, scenario_type="roundabout_2", n_agents=5, n_nearing_agents_observed=3)
+    p = sc.parameters
+    assert (p.num_vmas_envs, p.n_agents, p.n_nearing_agents_observed, p.scenario_type) == (6, 5, 3, "roundabout_2")
+    assert p.dt == 0.05 and not p.is_using_cbf_testing and not p.is_using_prioritized_marl and world.parameters is p
+    assert sc.config.mode == "kwargs"
+    sc.env_make_world(3, "cpu", scenario_type="cpm_entire", n_agents=2)      # re-made: still kwargs mode
+    assert sc.config.mode == "kwargs" and sc.parameters.num_vmas_envs == 3 and sc.env.dt == 0.05
