@@ -226,10 +226,15 @@ def test_every_reference_scenario_type_ships_and_packs():
            ["on_ramp_1", "on_ramp_2_multilane", "pseudo_distance_example", "roundabout_1", "roundabout_2"]
     assert available_scenarios() == sorted(want)
     L = load_library()
+    blob_bytes = dict(cpm_entire=180368, cpm_mixed=34352, interchange_1=7472, interchange_2=31904, interchange_3=30624,
+                      intersection_1=3296, intersection_2=5424, intersection_3=8096, intersection_4=10576,
+                      intersection_5=13920, intersection_6=13776, intersection_7=10592, intersection_8=8688,
+                      on_ramp_1=4896, on_ramp_2_multilane=29328, pseudo_distance_example=2112, roundabout_1=6736,
+                      roundabout_2=36656)
     for st in want:
         m = MapLibrary(st)
         d, n = m.desc(), C.c_int64()
         assert L.sgb_debug_pack_map(C.byref(d), C.byref(n)) == 0, st
-        assert 0 < n.value <= 180368, (st, n.value)            # cpm_entire is the largest map
+        assert n.value == blob_bytes[st], (st, n.value)        # layout pinned: a change here invalidates the hardware runs
         assert m.max_ref_path_points == int(m.n_center.max()) + 8
     assert L.sgb_debug_pack_map(None, None) != 0
