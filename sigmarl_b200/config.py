@@ -29,6 +29,33 @@ def _f32(x):
     return np.float32(x)
 
 
+# Parameters / kwargs of the reference that change the environment step but are supported at ONE value only (the
+# reference's default): given anything else the host layer refuses instead of silently computing the default.
+FIXED_PARAMETERS = dict(
+    n_points_short_term=3,                       # road_traffic.py:273-275  (observation width, reward weights)
+    sample_interval_ref_path=2,                  # road_traffic.py:316
+    n_points_nearing_boundary=5,                 # road_traffic.py:296-298
+    n_observed_steps=1,                          # road_traffic.py:284-286
+    is_challenging_initial_state_buffer=False,   # road_traffic.py:857-870; crashes in the reference once it replays
+    max_steering=MAX_STEERING, max_speed=MAX_SPEED,   # road_traffic.py:288-294 (AGENTS table)
+    lane_width=0.25,                             # helper_common.py:119: the OSM maps were parsed with it (parse_osm.py:283-306)
+)
+
+
+def check_fixed_parameters(get, scenario_type: str):
+    """``get(name)`` -> the caller's value or None.  Raises NotImplementedError for an unsupported value."""
+    for name, want in FIXED_PARAMETERS.items():
+        v = get(name)
+        if v is None:
+            continue
+        if name == "lane_width" and scenario_type.startswith("cpm"):
+            continue                              # the CPM maps come from the XML file, lane_width is not used for them
+        same = (bool(v) == want) if isinstance(want, bool) else abs(float(v) - float(want)) <= 1e-9 * max(1.0, abs(want))
+        if not same:
+            raise NotImplementedError(f"{name}={v!r}: this library supports {name}={want!r} only (sigmarl_b200/config.py "
+                                      f"FIXED_PARAMETERS)")
+
+
 @dataclass
 class EnvConfig:
     scenario_type: str = "cpm_entire"

@@ -22,7 +22,7 @@ from typing import Dict, Optional
 
 import torch
 
-from .config import AGENT_LENGTH, AGENT_WIDTH, EnvConfig, MAX_SPEED, MAX_STEERING
+from .config import AGENT_LENGTH, AGENT_WIDTH, EnvConfig, MAX_SPEED, MAX_STEERING, check_fixed_parameters
 from .env import RoadTrafficEnv
 from . import lib as _lib
 
@@ -192,6 +192,9 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             known.setdefault("scenario_type", "cpm_entire")
             cfg = EnvConfig(mode="kwargs", **known)
         self.config = cfg
+        # hot-path parameters that exist at one value only: refuse anything else, whichever way it was passed
+        _par = getattr(self, "parameters", None)
+        check_fixed_parameters(lambda n: kwargs[n] if n in kwargs else getattr(_par, n, None), cfg.scenario_type)
         # evaluation set-up (helper_common.py:110-118; road_traffic.py:842-853): fixed reference paths and start poses
         par = getattr(self, "parameters", None)
         predef = kwargs.get("predefined_ref_path_idx", getattr(par, "predefined_ref_path_idx", None))

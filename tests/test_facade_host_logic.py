@@ -216,3 +216,24 @@ def test_kwargs_mode_exposes_parameters(facade):
     assert sc.config.mode == "kwargs"
     sc.env_make_world(3, "cpu", scenario_type="cpm_entire", n_agents=2)      # re-made: still kwargs mode
     assert sc.config.mode == "kwargs" and sc.parameters.num_vmas_envs == 3 and sc.env.dt == 0.05
+
+
+def test_single_valued_parameters_are_refused_not_ignored(facade):
+    """Parameters that change the step but exist at one value only (config.FIXED_PARAMETERS) fail loudly, whether they
+    arrive as kwargs or on a Parameters object; their supported values pass."""
+    for kw in (dict(n_points_short_term=5), dict(sample_interval_ref_path=1), dict(is_challenging_initial_state_buffer=True),
+               dict(n_observed_steps=3), dict(max_speed=2.0)):
+        with pytest.raises(NotImplementedError):
+            facade(scenario_type="cpm_entire", n_agents=2, **kw)
+    with pytest.raises(NotImplementedError):
+        facade(scenario_type="roundabout_2", n_agents=2, lane_width=0.3)       # OSM boundaries depend on it
+    facade(scenario_type="cpm_entire", n_agents=2, lane_width=0.3)             # ... the CPM maps do not
+    facade(scenario_type="roundabout_2", n_agents=2, lane_width=0.25, n_points_short_term=3,
+           is_challenging_initial_state_buffer=False, is_real_time_rendering=True)
+
+    class P:
+        scenario_type, n_agents, is_challenging_initial_state_buffer = "cpm_entire", 2, True
+    sc = S.ScenarioRoadTrafficB200()
+    sc.parameters = P()
+    with pytest.raises(NotImplementedError):
+        sc.env_make_world(2, "cpu")
