@@ -48,9 +48,15 @@ def ncu_issue():
     try:
         ks = json.load(open(p))
         k = max(ks, key=lambda d: float(d["gpu__time_duration.sum"].split()[0]))
-        return {"issue_slots_busy_pct": float(k["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0]),
-                "active_lanes_per_warp_inst": float(k["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0]),
-                "warp_inst_per_launch": float(k["smsp__inst_executed.sum"].split()[0]), "source": "profiles/ncu_full_r1.json"}
+        busy = float(k["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0])
+        lanes = float(k["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0])
+        winst = float(k["smsp__inst_executed.sum"].split()[0])
+        return {"issue_slots_busy_pct": busy, "active_lanes_per_warp_inst": lanes, "warp_inst_per_launch": winst,
+                # share of the SMs' lane-issue capacity (4 schedulers x 32 lanes per clock) doing useful work: the
+                # "fp32 / ALU roofline" reading SURVEY.md §8d asks for next to the HBM fraction
+                "lane_issue_frac": busy / 100.0 * lanes / 32.0,
+                "thread_inst_per_agent_step": winst * lanes / (65536 * 8),   # the capture's shape: 65536 envs x 8 agents
+                "source": "profiles/ncu_full_r1.json"}
     except Exception:
         return None
 
