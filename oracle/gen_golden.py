@@ -135,6 +135,13 @@ CONFIGS = {
                                             extra=dict(rew_method="ttc_sparse")),
     "big_cpm_entire_B2_N18_distance_k4": dict(st="cpm_entire", B=2, N=18, T=30, mode="kwargs", seed=96, gentle=True,
                                              extra=dict(n_nearing_agents_observed=4)),
+    # lanelet-relation mask (map_manager.py:39-119): bird view + is_apply_mask on OSM maps
+    "mask_roundabout_2_B4_N8_birdview_lanelets_k4": dict(st="roundabout_2", B=4, N=8, T=40, mode="params", seed=84,
+                                                        gentle=True, extra=dict(is_apply_mask=True, is_ego_view=False,
+                                                                                n_nearing_agents_observed=4)),
+    "mask_intersection_5_B4_N6_birdview_lanelets": dict(st="intersection_5", B=4, N=6, T=40, mode="kwargs", seed=85,
+                                                       extra=dict(is_apply_mask=True, is_ego_view=False,
+                                                                  is_observe_vertices=False, n_nearing_agents_observed=3)),
     # the remaining maps of constants.py (interchange_1-3, intersection_2-8): open paths, entry / exit respawns
     "map_interchange_1_B4_N4": dict(st="interchange_1", B=4, N=4, T=40, mode="kwargs", seed=61, gentle=True),
     "map_interchange_2_B4_N6": dict(st="interchange_2", B=4, N=6, T=40, mode="params", seed=62, gentle=True,

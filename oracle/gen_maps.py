@@ -82,6 +82,20 @@ def main():
         out["osm_lane_width"] = np.float64(OSM_LANE_WIDTH)
         out["n_lanelets_all"] = np.int32(len(p.lanelets_all))   # width of ref_lanelet_ids (world_state_rt.py:152)
         np.savez_compressed(os.path.join(OUT, f"{st}.npz"), **out)
+        # lanelet table for the lanelet-relation observation mask (map_manager.py:39-119; only the OSM parser knows
+        # neighbouring lanelets, parse_osm.py:257-262): every lanelet's centre line + adjacency matrix, kept in a file of
+        # its own so that the polyline files above stay byte-stable
+        nb = p.neighboring_lanelets_idx
+        if len(nb):
+            cl = [np.asarray(l["center_line"].detach().cpu().numpy(), np.float32) for l in p.lanelets_all]
+            adj = np.zeros((len(cl), len(cl)), np.uint8)
+            for i, lst in enumerate(nb):
+                for j in lst:
+                    if 0 <= j < len(cl):
+                        adj[i, j] = 1
+            np.savez_compressed(os.path.join(OUT, f"{st}.lanelets.npz"), center_xy=np.concatenate(cl),
+                                center_off=np.asarray(np.concatenate([[0], np.cumsum([len(a) for a in cl])]), np.int32),
+                                adjacency=adj)
         nmax = int(np.diff(out["all_center_off"]).max())
         print(f"{st}: {len(p.reference_paths)} paths, max centre pts {nmax}, loops {int(out['all_is_loop'].sum())}")
 

@@ -40,7 +40,9 @@ class _Map(C.Structure):
     _fields_ = [("n_paths", C.c_int), ("P", C.c_int),
                 ("center", C.c_void_p), ("left", C.c_void_p), ("right", C.c_void_p),
                 ("n_center", C.c_void_p), ("n_left", C.c_void_p), ("n_right", C.c_void_p),
-                ("is_loop", C.c_void_p), ("yaw", C.c_void_p)]
+                ("is_loop", C.c_void_p), ("yaw", C.c_void_p),
+                ("n_lanelets", C.c_int), ("lanelet_xy", C.c_void_p), ("lanelet_off", C.c_void_p),
+                ("lanelet_adj", C.c_void_p)]
 
 
 _CFG_FLOATS = ["dt", "max_speed", "max_steering", "max_acc", "max_steering_rate", "l_wb", "lr_over_lwb",
@@ -74,6 +76,8 @@ def obs_flags_from(get):
         v = get(name)
         if v is not None and bool(v) == when:
             fl |= bit
+    if (fl & 128) and (fl & 1):
+        fl |= 256      # ORC_OBS_MASK_LANELETS: bird view + masks -> the lanelet-relation mask is live (on maps with a table)
     return fl
 
 
@@ -137,6 +141,14 @@ class PaddedMap:
                 cnt[i] = b.shape[0]
             self.yaw[i, :p["yaw"].shape[0]] = p["yaw"]
             self.is_loop[i] = p["is_loop"]
+        # lanelet table (OSM maps only): lanelet-relation observation mask, map_manager.py:39-119
+        lp = os.path.join(MAPS, f"{scenario_type}.lanelets.npz")
+        self.lanelet_xy = self.lanelet_off = self.lanelet_adj = None
+        if os.path.exists(lp):
+            zl = np.load(lp)
+            self.lanelet_xy = np.ascontiguousarray(zl["center_xy"], np.float32)
+            self.lanelet_off = np.ascontiguousarray(zl["center_off"], np.int32)
+            self.lanelet_adj = np.ascontiguousarray(zl["adjacency"], np.uint8)
 
     def global_path(self, scenario_id, path_id):
         """(scenario_id, path_id) of the reference (world_state_rt_sim.py:313-358) -> global index."""
@@ -276,6 +288,10 @@ class OracleWorld:
         self._keep = [np.ascontiguousarray(a) for a in
                       (p.center, p.left, p.right, p.n_center, p.n_left, p.n_right, p.is_loop, p.yaw)]
         m = _Map(p.n_paths, p.P, *[a.ctypes.data for a in self._keep])
+        if p.lanelet_xy is not None:
+            m.n_lanelets = len(p.lanelet_off) - 1
+            m.lanelet_xy, m.lanelet_off, m.lanelet_adj = (p.lanelet_xy.ctypes.data, p.lanelet_off.ctypes.data,
+                                                          p.lanelet_adj.ctypes.data)
         self.B, self.N = B, N
         self.h = self.L.orc_create(B, N, C.byref(m), C.byref(self.cfg))
         assert self.h, "orc_create failed"

@@ -35,6 +35,11 @@ typedef struct {
     const int *n_center, *n_left, *n_right;
     const uint8_t *is_loop;
     const float *yaw;                      /* [n_paths][P] center_line_yaw (n_center-1 valid) */
+    /* lanelet table for the lanelet-relation observation mask (map_manager.py:39-119); n_lanelets = 0: none */
+    int n_lanelets;
+    const float *lanelet_xy;               /* centre lines of all lanelets, concatenated [lanelet_off[n]][2] */
+    const int *lanelet_off;                /* [n_lanelets + 1] */
+    const uint8_t *lanelet_adj;            /* [n_lanelets][n_lanelets]: j in neighboring_lanelets_idx[i] */
 } orc_map;
 
 typedef struct {
@@ -69,6 +74,7 @@ typedef struct {
 #define ORC_OBS_NO_DIST_CENTER 32 /* is_observe_distance_to_center_line = False */
 #define ORC_OBS_BOUNDARY_POINTS 64 /* is_observe_distance_to_boundaries = False: 5 points of each boundary */
 #define ORC_OBS_MASK 128          /* is_apply_mask: observed neighbours farther than mask_distance show constants */
+#define ORC_OBS_MASK_LANELETS 256 /* + mask neighbours on non-adjacent lanelets (bird view, OSM maps; :646-664) */
 #define ORC_NNB 5                  /* n_points_nearing_boundary (road_traffic.py:296-298) */
 
 typedef struct {
@@ -554,7 +560,34 @@ typedef struct {
     float short_term[ORC_MAX_AGENTS][6];
     float d_ref[ORC_MAX_AGENTS], min_l[ORC_MAX_AGENTS], min_r[ORC_MAX_AGENTS];
     float near_l[ORC_MAX_AGENTS][2 * ORC_NNB], near_r[ORC_MAX_AGENTS][2 * ORC_NNB];
+    int lanelet[ORC_MAX_AGENTS];          /* map.current_lanelet_idx (determine_current_lanelet at update_state, :585-588) */
 } orc_snap;
+
+/* map_manager.py:39-89 determine_current_lanelet for one position: the lanelet whose centre line holds the closest
+ * point (squared distance, torch.sum((a - c)**2)), first minimal lanelet index.  Centre lines are padded with ZEROS to
+ * the longest one (:58-66), so every shorter lanelet also "has" the point (0, 0). */
+static int orc_current_lanelet(const orc_map *m, const float pos[2]) {
+    int max_len = 0, best = 0;
+    float best_d = INFINITY;
+    for (int l = 0; l < m->n_lanelets; l++)
+        if (m->lanelet_off[l + 1] - m->lanelet_off[l] > max_len) max_len = m->lanelet_off[l + 1] - m->lanelet_off[l];
+    for (int l = 0; l < m->n_lanelets; l++) {
+        float dmin = INFINITY;
+        int n = m->lanelet_off[l + 1] - m->lanelet_off[l];
+        for (int k = 0; k < n; k++) {
+            float dx = pos[0] - m->lanelet_xy[2 * (m->lanelet_off[l] + k)];
+            float dy = pos[1] - m->lanelet_xy[2 * (m->lanelet_off[l] + k) + 1];
+            float d = dx * dx + dy * dy;
+            if (d < dmin) dmin = d;
+        }
+        if (n < max_len) {
+            float d = pos[0] * pos[0] + pos[1] * pos[1];
+            if (d < dmin) dmin = d;
+        }
+        if (dmin < best_d) { best_d = dmin; best = l; }
+    }
+    return best;
+}
 
 static void orc_take_snapshot(const orc_world *w, int b, orc_snap *s) {
     int N = w->N;
@@ -568,6 +601,8 @@ static void orc_take_snapshot(const orc_world *w, int b, orc_snap *s) {
             if (w->d_right[g * 5 + c] < mr) mr = w->d_right[g * 5 + c];
         }
         s->min_l[j] = ml; s->min_r[j] = mr;
+        if ((w->cfg.obs_flags & ORC_OBS_MASK_LANELETS) && w->map.n_lanelets > 0)
+            s->lanelet[j] = orc_current_lanelet(&w->map, &w->pos[g * 2]);
         if (w->cfg.obs_flags & ORC_OBS_BOUNDARY_POINTS) {
             /* ref_paths_agent_related.nearing_points_*[:, j]: refreshed together with short_term[:, j]
              * (world_state_rt.py:668-725), i.e. from the closest boundary index as it stands now */
@@ -648,10 +683,13 @@ static void orc_observe(const orc_world *w, int b, int i, const orc_snap *s, flo
         const float *pj = &w->pos[gj * 2];
         float rr = orc_wrap(w->rot[gj] - rot_i);          /* :427 */
         /* is_apply_mask :638-668: a neighbour at or beyond distance_mask_agents is masked (position-like entries := 1,
-         * angles / velocities := 0, :682-749).  The lanelet-relation mask never fires where this oracle is used: the
-         * lanelet assignment is only computed in bird view (:585-588) and only OSM maps know neighbouring lanelets
-         * (parse_osm.py:257-262); the host layer refuses that combination. */
-        const int masked = (fl & ORC_OBS_MASK) && (bd >= c->mask_distance);
+         * angles / velocities := 0, :682-749).  The lanelet-relation mask is live only where the lanelet assignment is
+         * computed — bird view (:585-588) — and only on maps that know neighbouring lanelets (OSM, parse_osm.py:
+         * 257-262): ORC_OBS_MASK_LANELETS, set by the host layer for exactly that case. */
+        int masked = (fl & ORC_OBS_MASK) && (bd >= c->mask_distance);
+        /* :646-664 + map_manager.py:91-119: also masked if its lanelet is not the ego's or a neighbour of it */
+        if ((fl & ORC_OBS_MASK_LANELETS) && w->map.n_lanelets > 0)
+            masked |= !w->map.lanelet_adj[(size_t)s->lanelet[i] * w->map.n_lanelets + s->lanelet[bj]];
 #define MSK(v, m) (masked ? (m) : (v))
         if (fl & ORC_OBS_CENTRES) {                       /* :826-836: pos, rot, length, width */
             if (bird) {

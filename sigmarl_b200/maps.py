@@ -19,7 +19,7 @@ SAMPLE_INTERVAL_REF_PATH = 2  # road_traffic.py:316
 
 
 def available_scenarios():
-    return sorted(f[:-4] for f in os.listdir(MAP_DIR) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(MAP_DIR) if f.endswith(".npz") and not f.endswith(".lanelets.npz"))
 
 
 class MapLibrary:
@@ -82,6 +82,14 @@ class MapLibrary:
         # road_traffic.py:505-530
         self.max_ref_path_points = int(n_c.max()) + N_POINTS_SHORT_TERM * SAMPLE_INTERVAL_REF_PATH + 2
         self.has_loops = bool(self.is_loop.any())
+        # lanelet table (lanelet-relation observation mask, map_manager.py:39-119): OSM maps only
+        lp = os.path.join(MAP_DIR, f"{scenario_type}.lanelets.npz")
+        self.lanelet_xy = self.lanelet_off = self.lanelet_adj = None
+        if os.path.exists(lp):
+            zl = np.load(lp)
+            self.lanelet_xy = np.ascontiguousarray(zl["center_xy"], np.float32)
+            self.lanelet_off = np.ascontiguousarray(zl["center_off"], np.int32)
+            self.lanelet_adj = np.ascontiguousarray(zl["adjacency"], np.uint8)
 
     @property
     def n_center(self):
