@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 125
+#define SGB_VERSION 126
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -136,8 +136,11 @@ typedef struct {
 #define SGB_OBS_APPLY_MASK 128u    /* is_apply_mask: an observed neighbour whose distance is >= mask_distance shows
                                       constants instead of its state — positions, vertices, reference path and distance 1,
                                       heading, steering and velocity 0; length / width stay (observation_provider_rt.py:
-                                      638-749).  The reference's second criterion (lanelet relation) only ever fires in bird
-                                      view on OSM maps (:585-588, parse_osm.py:257-262); the host layer refuses that case */
+                                      638-749) */
+#define SGB_OBS_MASK_LANELETS 256u /* with SGB_OBS_APPLY_MASK: the reference's second criterion — a neighbour is also masked
+                                      unless its current lanelet is the ego's or adjacent to it (:646-664; map_manager.py:
+                                      39-119).  Live in the reference only in bird view (the lanelet assignment is computed
+                                      there, :585-588) on OSM maps (parse_osm.py:257-262); needs sgb_set_lanelets */
 
 /* Device buffers of one batch of B envs x N agents.  in = read, out = written, io = both. */
 typedef struct {
@@ -181,6 +184,14 @@ typedef struct sgb_ctx sgb_ctx;
  * set-up (road_traffic.py:104-110, 112-768). */
 int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, const sgb_config* cfg);
 int sgb_destroy(sgb_ctx* ctx);
+
+/* Lanelet table for SGB_OBS_MASK_LANELETS: the centre lines of ALL lanelets of the map (MapManager.parser.lanelets_all,
+ * concatenated, center_off[n_lanelets + 1]) and the adjacency matrix [n_lanelets][n_lanelets] (adjacency[i][j] != 0 iff
+ * j is in parser.neighboring_lanelets_idx[i]).  Host pointers, copied to the device.  Replaces
+ * MapManager.determine_current_lanelet / determine_masked_agents_by_lanelets (map_manager.py:39-119), which the
+ * flag-driven observation writer then evaluates per observed neighbour. */
+int sgb_set_lanelets(sgb_ctx* ctx, int32_t n_lanelets, const float* center_xy, const int32_t* center_off,
+                     const uint8_t* adjacency);
 
 /* Observation width D for the configured layout: 10 + 11*k_near with the default flags
  * (observation_provider_rt.py:594-925). */
@@ -271,6 +282,8 @@ float sgb_debug_mtv_distance(const float* vertices_i, const float* vertices_j);
  * the size of the blob every CTA stages into shared memory (SGB_ERR_MAP for a degenerate polyline or one with more
  * than 256 segments).  Lets a build machine without a GPU check that every shipped map is accepted. */
 int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes);
+/* Host build of the kernels' current_lanelet() on a host-resident lanelet table (arithmetic self-test). */
+int sgb_debug_current_lanelet(int32_t n_lanelets, const float* center_xy, const int32_t* center_off, float x, float y);
 
 const char* sgb_status_string(int status);
 const char* sgb_last_error(void); /* text of the last CUDA error seen by this thread */

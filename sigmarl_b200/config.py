@@ -110,12 +110,6 @@ class EnvConfig:
             if getattr(self, k) != v:
                 raise NotImplementedError(f"{k}={getattr(self, k)} selects a non-default observation/reset variant "
                                           f"that is outside the accelerated hot path (SURVEY.md §8f-4)")
-        if self.is_apply_mask and not self.is_ego_view and not self.scenario_type.startswith("cpm"):
-            # the only case in which the reference's lanelet-relation mask is live: bird view (the lanelet assignment is
-            # only computed there, observation_provider_rt.py:585-588) on an OSM map (only parse_osm.py:257-262 fills
-            # neighboring_lanelets_idx); ego view and the CPM maps mask by distance alone
-            raise NotImplementedError("is_apply_mask in bird view on an OSM map needs the lanelet-relation mask "
-                                      "(map_manager.py:39-119), which is outside the accelerated hot path")
         if self.mode not in ("params", "kwargs"):
             raise ValueError("mode must be 'params' or 'kwargs'")
 
@@ -239,6 +233,11 @@ class EnvConfig:
         c.use_mtv_distance = int(bool(self.is_use_mtv_distance))
         c.mask_distance = float(_f32(AGENT_LENGTH * 5))                        # road_traffic.py:663
         c.obs_flags = self.obs_flags()
+        if self.is_apply_mask and not self.is_ego_view and maplib.lanelet_xy is not None:
+            # the reference's lanelet-relation mask is live exactly here: bird view (the lanelet assignment is only
+            # computed there, observation_provider_rt.py:585-588) on a map that knows neighbouring lanelets (OSM maps,
+            # parse_osm.py:257-262).  Ego view and the CPM maps mask by distance alone, in the reference too.
+            c.obs_flags |= _lib.SGB_OBS_MASK_LANELETS
         c.norm_pos_world_x, c.norm_pos_world_y = float(x), float(y)            # road_traffic.py:593-595
         c.norm_dist_agent = float(_f32(AGENT_LENGTH * 10))                     # road_traffic.py:605-607
         level = self.obs_noise_level if self.obs_noise_level is not None else (0.05 if self.mode == "params" else 0.2 * AGENT_WIDTH)

@@ -19,6 +19,10 @@ struct sgb_ctx {
     float* d_yaw = nullptr;          // yaw per centre point, indexed like the blob's centre points
     float* d_spawn = nullptr;        // spawn table [centre points][8] (sgb_kernels.cuh: place_agent)
     float* d_fresh = nullptr;        // [fresh_cap][4] scratch: spawn-pose boundary distances for the observation refresh
+    float* d_lanelet_xy = nullptr;   // sgb_set_lanelets: centre lines of all lanelets / offsets / adjacency matrix
+    int32_t* d_lanelet_off = nullptr;
+    uint8_t* d_lanelet_adj = nullptr;
+    int32_t n_lanelets = 0, lanelet_max_len = 0;
     int64_t fresh_cap = 0;           // capacity of d_fresh in agents
     int32_t n_points = 0;            // centre points incl. extension slots (rows of d_yaw / d_spawn)
     int32_t* d_list = nullptr;       // [cap] compacted env indices for a masked refresh
@@ -56,6 +60,12 @@ extern "C" float sgb_debug_mtv_distance(const float* vi, const float* vj) {
     float ax[4], ay[4], bx[4], by[4];
     for (int k = 0; k < 4; k++) { ax[k] = vi[2 * k]; ay[k] = vi[2 * k + 1]; bx[k] = vj[2 * k]; by[k] = vj[2 * k + 1]; }
     return sgb::mtv_from_vertices(ax, ay, bx, by);
+}
+extern "C" int sgb_debug_current_lanelet(int32_t n, const float* xy, const int32_t* off, float x, float y) {
+    if (n <= 0 || !xy || !off) return SGB_ERR_ARG;
+    int max_len = 0;
+    for (int l = 0; l < n; l++) max_len = std::max(max_len, off[l + 1] - off[l]);
+    return sgb::current_lanelet(reinterpret_cast<const float2*>(xy), off, n, max_len, x, y);   // host build of the kernels' function
 }
 extern "C" const char* sgb_status_string(int s) {
     switch (s) {
@@ -299,6 +309,17 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.r_pos = 1.0f / ctx->cfg.norm_pos;
     p.r_v = 1.0f / ctx->cfg.norm_v;
     p.r_dist = 1.0f / ctx->cfg.norm_dist;
+    if (p.cfg.obs_flags & SGB_OBS_MASK_LANELETS) {
+        if (!ctx->d_lanelet_xy || !(p.cfg.obs_flags & SGB_OBS_APPLY_MASK)) {
+            snprintf(g_err, sizeof g_err, "SGB_OBS_MASK_LANELETS needs SGB_OBS_APPLY_MASK and a lanelet table (sgb_set_lanelets)");
+            return SGB_ERR_ARG;
+        }
+        p.lanelet_xy = reinterpret_cast<const float2*>(ctx->d_lanelet_xy);
+        p.lanelet_off = ctx->d_lanelet_off;
+        p.lanelet_adj = ctx->d_lanelet_adj;
+        p.n_lanelets = ctx->n_lanelets;
+        p.lanelet_max_len = ctx->lanelet_max_len;
+    }
     const int g = pick_group(N);
     // MTV agent distance: its own instantiation (flag-driven writer + SAT distance in phase C1)
     if (p.cfg.use_mtv_distance) return mode == 0 ? launch_env_group<0, 2>(ctx, p, st, g) : launch_env_group<1, 2>(ctx, p, st, g);
@@ -403,7 +424,8 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     }
     if (cfg->k_near < 0 || cfg->k_near >= SGB_MAX_AGENTS || cfg->max_steps < 2 || !(cfg->dt > 0.0f)) return SGB_ERR_ARG;
     constexpr uint32_t kObsKnown = SGB_OBS_BIRD_VIEW | SGB_OBS_CENTRES | SGB_OBS_STEERING | SGB_OBS_REF_OTHERS |
-                                   SGB_OBS_NO_DIST_AGENTS | SGB_OBS_NO_DIST_CENTER | SGB_OBS_BOUNDARY_POINTS | SGB_OBS_APPLY_MASK;
+                                   SGB_OBS_NO_DIST_AGENTS | SGB_OBS_NO_DIST_CENTER | SGB_OBS_BOUNDARY_POINTS | SGB_OBS_APPLY_MASK |
+                                   SGB_OBS_MASK_LANELETS;
     if (cfg->obs_flags & ~kObsKnown) {
         snprintf(g_err, sizeof g_err, "obs_flags 0x%x: unknown observation layout bits", cfg->obs_flags);
         return SGB_ERR_UNSUPPORTED;
@@ -438,11 +460,36 @@ extern "C" int sgb_destroy(sgb_ctx* c) {
     cudaFree(c->d_count);
     cudaFree(c->d_spawn);
     cudaFree(c->d_fresh);
+    cudaFree(c->d_lanelet_xy);
+    cudaFree(c->d_lanelet_off);
+    cudaFree(c->d_lanelet_adj);
     if (c->pipe_ready) {
         for (int i = 0; i < 2; i++) { cudaStreamDestroy(c->pipe_stream[i]); cudaEventDestroy(c->pipe_event[i]); }
         cudaEventDestroy(c->pipe_start);
     }
     delete c;
+    return SGB_OK;
+}
+
+extern "C" int sgb_set_lanelets(sgb_ctx* c, int32_t n, const float* xy, const int32_t* off, const uint8_t* adj) {
+    if (!c || n <= 0 || n > 4096 || !xy || !off || !adj || off[0] != 0) return SGB_ERR_ARG;
+    int max_len = 0;
+    for (int l = 0; l < n; l++) {
+        if (off[l + 1] <= off[l]) return SGB_ERR_ARG;       // every lanelet has at least one centre point
+        max_len = std::max(max_len, off[l + 1] - off[l]);
+    }
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->d_lanelet_xy); cudaFree(c->d_lanelet_off); cudaFree(c->d_lanelet_adj);
+    c->d_lanelet_xy = nullptr; c->d_lanelet_off = nullptr; c->d_lanelet_adj = nullptr;
+    c->n_lanelets = 0;
+    CK(cudaMalloc(&c->d_lanelet_xy, sizeof(float) * 2 * (size_t)off[n]));
+    CK(cudaMemcpy(c->d_lanelet_xy, xy, sizeof(float) * 2 * (size_t)off[n], cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_lanelet_off, sizeof(int32_t) * ((size_t)n + 1)));
+    CK(cudaMemcpy(c->d_lanelet_off, off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_lanelet_adj, (size_t)n * n));
+    CK(cudaMemcpy(c->d_lanelet_adj, adj, (size_t)n * n, cudaMemcpyHostToDevice));
+    c->n_lanelets = n;
+    c->lanelet_max_len = max_len;
     return SGB_OK;
 }
 

@@ -95,6 +95,11 @@ struct Params {
     float rect_radius;         // circumradius of the rectangle * 1.0001 (conservative reach for the pruning bounds)
     float near2;               // (rect_radius + kFarMargin)^2
     float r_pos, r_v, r_dist;  // reciprocals of the observation normalisers
+    // lanelet table (SGB_OBS_MASK_LANELETS; sgb_set_lanelets), global memory — appended, so nothing above moves
+    const float2* lanelet_xy;      // centre lines of all lanelets, concatenated
+    const int32_t* lanelet_off;    // [n_lanelets + 1]
+    const uint8_t* lanelet_adj;    // [n_lanelets][n_lanelets]
+    int32_t n_lanelets, lanelet_max_len;
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------------
@@ -323,6 +328,29 @@ __device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx,
         for (int i = 0; i < 4; i++) hit |= (((g[i] * g[(i + 1) & 3]) < 0.0f) & (((c1 >> (4 * i + j)) & 1u) != 0u));
     }
     return hit;
+}
+
+// map_manager.py:39-89 determine_current_lanelet for one position: the lanelet whose centre line holds the closest  @region lanelet
+// point — squared distance, every product rounded (torch.sum((a - c)**2)), first minimal lanelet.  The reference pads
+// the centre lines with ZEROS to the longest one (:58-66): every shorter lanelet also "has" the point (0, 0).
+__host__ __device__ inline int current_lanelet(const float2* xy, const int32_t* off, int n_lanelets, int max_len, float px, float py) {
+    int best = 0;
+    float best_d = 3.402823466e38f;
+    for (int l = 0; l < n_lanelets; l++) {
+        const int o0 = off[l], n = off[l + 1] - o0;
+        float dmin = 3.402823466e38f;
+        for (int k = 0; k < n; k++) {
+            const float2 c = xy[o0 + k];
+            const float dx = subr(px, c.x), dy = subr(py, c.y);
+            dmin = fminf(dmin, madd2(dx, dx, dy, dy));
+        }
+        if (n < max_len) dmin = fminf(dmin, madd2(px, px, py, py));
+        if (dmin < best_d) { best_d = dmin; best = l; }
+    }
+    return best;
+}
+__device__ __noinline__ int current_lanelet_ool(const float2* xy, const int32_t* off, int n_lanelets, int max_len, float px, float py) {
+    return current_lanelet(xy, off, n_lanelets, max_len, px, py);
 }
 
 // MTV-based distance between two rectangles (is_use_mtv_distance; helper_scenario.py:1030-1138), in the reference's  @region mtv
@@ -1236,7 +1264,16 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
 #pragma unroll
                             for (int k = 0; k < 3; k++) { put_point(q, st[k].x, st[k].y); q += 2; }
                         }
-                        if ((ofl & SGB_OBS_APPLY_MASK) && bd >= cfg.mask_distance) {
+                        bool masked = (ofl & SGB_OBS_APPLY_MASK) && bd >= cfg.mask_distance;
+                        if (!masked && (ofl & SGB_OBS_MASK_LANELETS)) {
+                            // + the lanelet relation (observation_provider_rt.py:646-664, map_manager.py:91-119): masked
+                            // unless the neighbour's current lanelet is the ego's or adjacent to it (post-step positions)
+                            const int li = current_lanelet_ool(p.lanelet_xy, p.lanelet_off, p.n_lanelets, p.lanelet_max_len, pix, piy);
+                            const int lj = current_lanelet_ool(p.lanelet_xy, p.lanelet_off, p.n_lanelets, p.lanelet_max_len,
+                                                               ts.px[sj], ts.py[sj]);
+                            masked = p.lanelet_adj[li * p.n_lanelets + lj] == 0;
+                        }
+                        if (masked) {
                             // is_apply_mask (observation_provider_rt.py:638-749): a far neighbour shows constants —
                             // positions / vertices / reference path / distance 1, heading / steering / velocity 0
                             float* m = o + own + per * kk;

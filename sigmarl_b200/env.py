@@ -44,6 +44,11 @@ class RoadTrafficEnv:
         d = self.map.desc()
         with torch.cuda.device(idx):
             _lib.check(self.L.sgb_create(C.byref(self._ctx), idx, C.byref(d), C.byref(self.cfg)), "sgb_create")
+        if self.cfg.obs_flags & _lib.SGB_OBS_MASK_LANELETS:      # lanelet table for the lanelet-relation observation mask
+            m = self.map
+            with torch.cuda.device(idx):
+                _lib.check(self.L.sgb_set_lanelets(self._ctx, len(m.lanelet_off) - 1, m.lanelet_xy.ctypes.data,
+                                                   m.lanelet_off.ctypes.data, m.lanelet_adj.ctypes.data), "sgb_set_lanelets")
         self.D = self.L.sgb_obs_dim(self._ctx)
         B, N, dev = self.B, self.N, self.device
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)  # noqa: E731

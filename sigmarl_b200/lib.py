@@ -13,13 +13,14 @@ SGB_MAX_AGENTS = 32
 SGB_FLAG_COLLIDE_AGENT, SGB_FLAG_COLLIDE_LANE, SGB_FLAG_ENTRY, SGB_FLAG_EXIT = 1, 2, 4, 8
 SGB_REW_EXACT_SPARSE, SGB_REW_TTC, SGB_REW_DISTANCE, SGB_REW_SPARSE = 1, 2, 4, 8
 (SGB_OBS_BIRD_VIEW, SGB_OBS_CENTRES, SGB_OBS_STEERING, SGB_OBS_REF_OTHERS, SGB_OBS_NO_DIST_AGENTS,
- SGB_OBS_NO_DIST_CENTER, SGB_OBS_BOUNDARY_POINTS, SGB_OBS_APPLY_MASK) = 1, 2, 4, 8, 16, 32, 64, 128
+ SGB_OBS_NO_DIST_CENTER, SGB_OBS_BOUNDARY_POINTS, SGB_OBS_APPLY_MASK, SGB_OBS_MASK_LANELETS) = 1, 2, 4, 8, 16, 32, 64, 128, 256
 CARRY_IDX_MASK, CARRY_FRESH_BIT = 0x3fffffff, 0x40000000   # carry.w with SGB_OBS_BOUNDARY_POINTS (see the header)
 
 # every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
-           "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance", "sgb_debug_pack_map"]
+           "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance", "sgb_debug_pack_map",
+           "sgb_set_lanelets", "sgb_debug_current_lanelet"]
 
 
 class SgbError(RuntimeError):
@@ -98,6 +99,8 @@ def load_library():
     L.sgb_status_string.restype = C.c_char_p
     L.sgb_last_error.restype = C.c_char_p
     L.sgb_version.restype = C.c_int
+    L.sgb_set_lanelets.argtypes = [vp, i32, vp, vp, vp]
+    L.sgb_debug_current_lanelet.argtypes = [i32, vp, vp, C.c_float, C.c_float]
     L.sgb_debug_pack_map.argtypes = [C.POINTER(MapDesc), C.POINTER(i64)]
     L.sgb_debug_mtv_distance.argtypes = [vp, vp]
     L.sgb_debug_mtv_distance.restype = C.c_float

@@ -145,8 +145,7 @@ def test_config_matches_reference_constants_in_goldens():
 def test_unsupported_flags_fail_loudly():
     from sigmarl_b200 import EnvConfig, MapLibrary
     m = MapLibrary("cpm_entire")
-    for kw in (dict(rew_method="cbf"), dict(scenario_type="roundabout_2", is_apply_mask=True, is_ego_view=False),
-               dict(is_partial_observation=False)):
+    for kw in (dict(rew_method="cbf"), dict(is_partial_observation=False)):
         with pytest.raises(NotImplementedError):
             EnvConfig(**{"scenario_type": "cpm_entire", **kw}).lower(m)
     # observation layouts and noise ARE supported (ABI 121 / 122): flags, width and noise level reach sgb_config
@@ -168,6 +167,9 @@ def test_unsupported_flags_fail_loudly():
     low = EnvConfig(scenario_type="cpm_entire", is_apply_mask=True, is_ego_view=False).lower(m)
     assert low.obs_flags == lib.SGB_OBS_APPLY_MASK | lib.SGB_OBS_BIRD_VIEW and low.mask_distance == float(np.float32(1.1))
     assert EnvConfig(scenario_type="roundabout_2", is_apply_mask=True).lower(MapLibrary("roundabout_2")).obs_flags == lib.SGB_OBS_APPLY_MASK
+    # ... and the lanelet-relation criterion exactly where the reference applies it: bird view on an OSM map (ABI 126)
+    low = EnvConfig(scenario_type="roundabout_2", is_apply_mask=True, is_ego_view=False).lower(MapLibrary("roundabout_2"))
+    assert low.obs_flags == lib.SGB_OBS_APPLY_MASK | lib.SGB_OBS_BIRD_VIEW | lib.SGB_OBS_MASK_LANELETS
     with pytest.raises(ValueError):
         MapLibrary("no_such_map")
 
@@ -238,3 +240,37 @@ def test_every_reference_scenario_type_ships_and_packs():
         assert n.value == blob_bytes[st], (st, n.value)        # layout pinned: a change here invalidates the hardware runs
         assert m.max_ref_path_points == int(m.n_center.max()) + 8
     assert L.sgb_debug_pack_map(None, None) != 0
+
+
+def test_kernel_current_lanelet_matches_the_references_formula_on_the_host():
+    """sgb_debug_current_lanelet = host build of the kernels' current_lanelet().  Checked against the reference's
+    determine_current_lanelet (map_manager.py:39-89) restated with torch exactly as written there — centre lines padded
+    with zeros to the longest one, torch.sum((a - c) ** 2), min over points, argmin over lanelets — on random positions
+    and on the lanelets' own points (exact ties between lanelets that share an end point) of every OSM map."""
+    import torch
+    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.maps import MapLibrary, available_scenarios
+    L = load_library()
+    rng = np.random.default_rng(0)
+    n_maps = n_ties = 0
+    for st in available_scenarios():
+        m = MapLibrary(st)
+        if m.lanelet_xy is None:
+            continue
+        n_maps += 1
+        off, xy = m.lanelet_off, m.lanelet_xy
+        n = len(off) - 1
+        max_len = int(np.diff(off).max())
+        padded = torch.zeros(n, max_len, 2)
+        for l in range(n):
+            padded[l, :off[l + 1] - off[l]] = torch.from_numpy(xy[off[l]:off[l + 1]])
+        pts = np.concatenate([rng.uniform([-0.5, -0.5], [m.world_x_dim + 0.5, m.world_y_dim + 0.5], (300, 2)),
+                              xy[rng.integers(0, len(xy), 100)], np.zeros((1, 2))]).astype(np.float32)
+        d = torch.sum((torch.from_numpy(pts)[:, None, None, :] - padded[None]) ** 2, dim=3)
+        mind, _ = torch.min(d, dim=2)
+        want = torch.argmin(mind, dim=1).numpy()
+        n_ties += int((mind == mind.min(dim=1, keepdim=True).values).sum(dim=1).gt(1).sum())
+        got = np.asarray([L.sgb_debug_current_lanelet(n, xy.ctypes.data, off.ctypes.data, float(x), float(y)) for x, y in pts])
+        assert np.array_equal(got, want), (st, np.where(got != want)[0][:5])
+        assert m.lanelet_adj.shape == (n, n) and m.lanelet_adj.diagonal()[:n - 4].all()   # (a lanelet is its own neighbour)
+    assert n_maps == 16 and n_ties > 50

@@ -110,6 +110,9 @@ def test_new_maps_pruned_equals_exhaustive_bitwise(scenario, N):
     ("roundabout_2", 12, "ttc", "kwargs", 256, 4,
      dict(is_observe_vertices=False, is_obs_steering=True, is_observe_ref_path_other_agents=True)),   # G = 2, OSM, ego view
     ("cpm_entire", 18, "distance_sparse", "params", 64, 6, dict(is_ego_view=False)),                # G = 1, bird view (CPM)
+    # bird view on OSM maps: the lanelet-relation criterion is live as well (SGB_OBS_MASK_LANELETS, sgb_set_lanelets)
+    ("roundabout_2", 12, "distance", "params", 256, 4, dict(is_ego_view=False)),
+    ("interchange_2", 8, "ttc_sparse", "kwargs", 256, 3, dict(is_ego_view=False, is_observe_vertices=False)),
 ])
 def test_cuda_observation_masks_match_oracle(oracle_mod, scenario, N, rew, mode, B, k_obs, flags):
     """is_apply_mask (observation_provider_rt.py:638-749): observed neighbours at or beyond 5 agent lengths show the
