@@ -309,6 +309,11 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.r_pos = 1.0f / ctx->cfg.norm_pos;
     p.r_v = 1.0f / ctx->cfg.norm_v;
     p.r_dist = 1.0f / ctx->cfg.norm_dist;
+    if ((p.cfg.obs_flags & SGB_OBS_MASK_LANELETS) && (p.cfg.k_near == 0 || (mode != 0 && !write_obs))) {
+        // nobody is observed in this launch (e.g. the spawn-table build inside sgb_create, which runs before the caller
+        // can upload a lanelet table): the lanelet criterion has nothing to act on
+        p.cfg.obs_flags &= ~SGB_OBS_MASK_LANELETS;
+    }
     if (p.cfg.obs_flags & SGB_OBS_MASK_LANELETS) {
         if (!ctx->d_lanelet_xy || !(p.cfg.obs_flags & SGB_OBS_APPLY_MASK)) {
             snprintf(g_err, sizeof g_err, "SGB_OBS_MASK_LANELETS needs SGB_OBS_APPLY_MASK and a lanelet table (sgb_set_lanelets)");
