@@ -125,10 +125,13 @@ def test_config_matches_reference_constants_in_goldens():
     """...and both agree with what the reference run itself reported (cfg_* entries of the goldens)."""
     import glob
     from sigmarl_b200 import EnvConfig, MapLibrary
-    for p in sorted(glob.glob(os.path.join(REPO, "tests", "golden", "*.npz"))):
+    for p in sorted(glob.glob(os.path.join(REPO, "tests", "golden", "*.npz")) +
+                    glob.glob(os.path.join(REPO, "tests", "golden", "next", "*.npz"))):
         g = np.load(p)
         st, mode = str(g["cfg_scenario_type"]), str(g["cfg_mode"])
         extra = {}
+        if "cfg_is_use_mtv_distance" in g.files:          # MTV thresholds (road_traffic.py:264-270, 632-648)
+            extra["is_use_mtv_distance"] = bool(g["cfg_is_use_mtv_distance"])
         if "ttc_sparse" in p and "cpm_mixed" in p:
             extra["threshold_near_other_agents_c2c_low"] = 0.1635
         c = EnvConfig(scenario_type=st, n_agents=int(g["cfg_N"]), mode=mode, rew_method=str(g["cfg_rew_method"]),
