@@ -282,6 +282,9 @@ float sgb_debug_mtv_distance(const float* vertices_i, const float* vertices_j);
  * the size of the blob every CTA stages into shared memory (SGB_ERR_MAP for a degenerate polyline or one with more
  * than 256 segments).  Lets a build machine without a GPU check that every shipped map is accepted. */
 int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes);
+/* ... and a copy of the packed blob itself (layout: BlobHeader / PathRec in sgb_kernels.cuh), so that the pruning
+ * certificates stored in it (chunk boxes, direction cones) can be validated against the polylines on the host. */
+int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity);
 /* Host build of the kernels' current_lanelet() on a host-resident lanelet table (arithmetic self-test). */
 int sgb_debug_current_lanelet(int32_t n_lanelets, const float* center_xy, const int32_t* center_off, float x, float y);
 

@@ -418,6 +418,14 @@ extern "C" int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes) 
     if (blob_bytes) *blob_bytes = rc == SGB_OK ? (int64_t)pk.blob.size() : 0;
     return rc;
 }
+extern "C" int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity) {
+    Packed pk;
+    const int rc = pack_map(map, pk);
+    if (rc != SGB_OK) return rc;
+    if (!out || capacity < (int64_t)pk.blob.size()) return SGB_ERR_ARG;
+    std::memcpy(out, pk.blob.data(), pk.blob.size());
+    return SGB_OK;
+}
 
 extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, const sgb_config* cfg) {
     if (!out || !map || !cfg) return SGB_ERR_ARG;

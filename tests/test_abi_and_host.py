@@ -277,3 +277,57 @@ def test_kernel_current_lanelet_matches_the_references_formula_on_the_host():
         assert np.array_equal(got, want), (st, np.where(got != want)[0][:5])
         assert m.lanelet_adj.shape == (n, n) and m.lanelet_adj.diagonal()[:n - 4].all()   # (a lanelet is its own neighbour)
     assert n_maps == 16 and n_ties > 50
+
+
+def test_packed_blob_certificates_hold_on_every_map():
+    """The pruned search is exact only if what the packer stores is conservative: every chunk's box must contain the
+    chunk's points, every boundary chunk's direction cone (fp16 mid angle / half width, mod pi) must contain the
+    directions of its segments, and the points must be the map's polylines (+ the 6 extension points of a centre line,
+    world_state_rt.py:279-311).  Checked on the host for all 18 maps from a copy of the blob sgb_create would upload."""
+    import ctypes as C
+    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.maps import MapLibrary, available_scenarios
+    L = load_library()
+    K, EXT = 8, 6                                   # kChunk, kExt (sgb_kernels.cuh)
+    n_cones = n_wide = 0
+    for st in available_scenarios():
+        m = MapLibrary(st)
+        d, n = m.desc(), C.c_int64()
+        assert L.sgb_debug_pack_map(C.byref(d), C.byref(n)) == 0
+        raw = np.zeros(n.value, np.uint8)
+        assert L.sgb_debug_pack_map_blob(C.byref(d), raw.ctypes.data, n.value) == 0
+        hdr = raw[:32].view(np.int32)
+        n_paths, path_off, pts_off, box_off, total, cone_off = (int(x) for x in hdr[:6])
+        assert n_paths == m.n_paths and total == n.value
+        recs = raw[path_off:path_off + 48 * n_paths].view(np.int32).reshape(n_paths, 12)
+        pts = raw[pts_off:box_off].view(np.float32).reshape(-1, 2)
+        boxes = raw[box_off:cone_off].view(np.float32).reshape(-1, 4)
+        cones = raw[cone_off:total].view(np.float16).reshape(-1, 2).astype(np.float64)
+        for i in range(n_paths):
+            c_off, n_c, l_off, n_l, r_off, n_r, cbox, lbox, rbox, is_loop, lcone, rcone = (int(x) for x in recs[i])
+            cen = m.center_xy[m.center_off[i]:m.center_off[i + 1]]
+            assert n_c == len(cen) and np.array_equal(pts[c_off:c_off + n_c], cen) and is_loop == int(m.is_loop[i])
+            step = cen[-1] - cen[-2]
+            ext = cen[-1] + np.arange(1, EXT + 1, dtype=np.float32)[:, None] * step
+            assert np.array_equal(pts[c_off + n_c:c_off + n_c + EXT], ext.astype(np.float32))
+            for off, cnt, box0, cone0, want in ((c_off, n_c, cbox, None, cen),
+                                                (l_off, n_l, lbox, lcone, m.left_xy[m.left_off[i]:m.left_off[i + 1]]),
+                                                (r_off, n_r, rbox, rcone, m.right_xy[m.right_off[i]:m.right_off[i + 1]])):
+                assert cnt == len(want) and np.array_equal(pts[off:off + cnt], want)
+                for c, s0 in enumerate(range(0, cnt - 1, K)):
+                    s1 = min(s0 + K, cnt - 1)
+                    seg = want[s0:s1 + 1].astype(np.float64)
+                    x0, y0, x1, y1 = boxes[box0 + c]
+                    assert (seg[:, 0] >= x0).all() and (seg[:, 0] <= x1).all() and (seg[:, 1] >= y0).all() and (seg[:, 1] <= y1).all()
+                    if cone0 is None:
+                        continue
+                    mid, half = cones[cone0 + c]
+                    n_cones += 1
+                    if half >= np.pi / 2:
+                        n_wide += 1
+                        continue
+                    dv = np.diff(seg, axis=0)
+                    ang = np.arctan2(dv[:, 1], dv[:, 0])
+                    rel = np.mod(ang - mid + np.pi / 2, np.pi) - np.pi / 2          # difference of undirected lines
+                    assert np.abs(rel).max() <= half - np.arcsin(0.01) + 1e-3, (st, i, c, np.abs(rel).max(), half)
+    assert n_cones > 1500 and n_wide < 0.05 * n_cones
