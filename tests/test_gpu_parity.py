@@ -322,8 +322,9 @@ def _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, **flags):
             # may differ from the oracle's by an ulp (libm); an agent within ~1e-7 m of the border between two lanelets'
             # nearest-point cells can come out on the other lanelet (expected < 1e-5 per agent-step)
             bad = (np.abs(obs.cpu().numpy() - o_obs).max(-1) > TOL) & ok_rows
-            assert bad.sum() <= 1, f"{ctx} {int(bad.sum())} rows differ in one step"
-            n_ties += int(bad.sum())
+            # (one agent on the other lanelet changes the rows of everybody who observes it: at most one env per step)
+            assert bad.any(-1).sum() <= 1, f"{ctx} rows differ in {int(bad.any(-1).sum())} envs in one step"
+            n_ties += int(bad.any(-1).sum())
             ok_rows &= ~bad
         _close("obs", obs.cpu().numpy()[ok_rows], o_obs[ok_rows], ctx)
         _close("reward", rew_.cpu(), o_rew, ctx)
