@@ -285,6 +285,14 @@ int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes);
 /* ... and a copy of the packed blob itself (layout: BlobHeader / PathRec in sgb_kernels.cuh), so that the pruning
  * certificates stored in it (chunk boxes, direction cones) can be validated against the polylines on the host. */
 int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity);
+/* Host run of the kernels' own polyline scans (scan_center / scan_boundary with one lane per agent) for n independent
+ * poses on a freshly packed blob: the pruned search (exhaustive = 0) must give exactly what the exhaustive one
+ * (exhaustive = 1) gives.  out[16 * i]: d_ref, idx_ref, then per side (left at 2, right at 9) d_cg, 4 vertex
+ * distances, crossing flag.  hint_idx is the carried closest index (any value is valid).  The host compiler does not
+ * contract a*b+c into FMAs, the device does: the certificates must (and do) hold under either rounding. */
+int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const int32_t* path, const float* x, const float* y,
+                         const float* psi, const int32_t* hint_idx, float half_length, float half_width,
+                         int32_t exhaustive, float* out);
 /* Host build of the kernels' current_lanelet() on a host-resident lanelet table (arithmetic self-test). */
 int sgb_debug_current_lanelet(int32_t n_lanelets, const float* center_xy, const int32_t* center_off, float x, float y);
 

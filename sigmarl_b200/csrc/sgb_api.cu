@@ -418,6 +418,55 @@ extern "C" int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes) 
     if (blob_bytes) *blob_bytes = rc == SGB_OK ? (int64_t)pk.blob.size() : 0;
     return rc;
 }
+// Host run of the kernels' own polyline scans (scan_center<1>, scan_boundary<1>: one lane per agent, the group
+// reductions are the identity) on a freshly packed blob — the phase-B glue of env_step_kernel for `n` independent poses.
+// out[16 * i]: 0 d_ref, 1 idx_ref, then per side (left at 2, right at 9): d_cg, d_vertex[4], hit, spare.  Lets a
+// machine without a GPU check that the pruned search equals the exhaustive one (`exhaustive` = 0 / 1) on any map.
+extern "C" int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const int32_t* path, const float* x, const float* y,
+                                    const float* psi, const int32_t* hint_idx, float half_length, float half_width,
+                                    int32_t exhaustive, float* out) {
+    if (n < 0 || !path || !x || !y || !psi || !hint_idx || !out) return SGB_ERR_ARG;
+    Packed pk;
+    const int rc = pack_map(map, pk);
+    if (rc != SGB_OK) return rc;
+    const unsigned char* blob = pk.blob.data();
+    const BlobHeader* h = reinterpret_cast<const BlobHeader*>(blob);
+    const PathRec* paths = reinterpret_cast<const PathRec*>(blob + h->path_off);
+    const float2* pts = reinterpret_cast<const float2*>(blob + h->pts_off);
+    const float4* boxes = reinterpret_cast<const float4*>(blob + h->box_off);
+    const __half2* cones = reinterpret_cast<const __half2*>(blob + h->cone_off);
+    const float rect_radius = std::sqrt(half_length * half_length + half_width * half_width) * 1.0001f;   // launch_env
+    const float near2 = (rect_radius + kFarMargin) * (rect_radius + kFarMargin);
+    for (int i = 0; i < n; i++) {
+        if (path[i] < 0 || path[i] >= h->n_paths) return SGB_ERR_ARG;
+        const PathRec* prp = paths + path[i];
+        const float px = x[i], py = y[i];
+        const float sy = sinf(psi[i]), cy = cosf(psi[i]);
+        float rvx[4], rvy[4];
+        sgb::rect_of_pose(px, py, cy, sy, half_length, half_width, rvx, rvy);     // phase A's vertices
+        const float psim = fmaf(-3.14159274f, floorf(psi[i] * 0.318309873f), psi[i]);   // phase A's heading mod pi
+        float* o = out + 16 * (size_t)i;
+        for (int k = 0; k < 16; k++) o[k] = 0.0f;
+        float d_ref;
+        int idx_ref;
+        sgb::scan_center<1>(pts + prp->c_off, boxes + prp->cbox, prp->n_c, hint_idx[i] - 1, exhaustive != 0, px, py, 0, d_ref, idx_ref);
+        o[0] = d_ref; o[1] = (float)idx_ref;
+        const int h2 = idx_ref - 1;
+        for (int side = 0; side < 2; side++) {
+            float dc, dvv[4];
+            bool hit;
+            sgb::scan_boundary<1>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
+                                  cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, exhaustive != 0, px, py,
+                                  &cy, &sy, &psim, rvx, rvy, rect_radius, near2, half_length, half_width, true, 0, dc, dvv, hit);
+            float* q = o + (side ? 9 : 2);
+            q[0] = dc;
+            for (int v = 0; v < 4; v++) q[1 + v] = dvv[v];
+            q[5] = hit ? 1.0f : 0.0f;
+        }
+    }
+    return SGB_OK;
+}
+
 extern "C" int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity) {
     Packed pk;
     const int rc = pack_map(map, pk);

@@ -136,9 +136,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 // that it rounds exactly like the reference's one-ATen-op-at-a-time evaluation.
 #ifdef __CUDA_ARCH__
 #define SGB_UNROLL _Pragma("unroll")
+#define SGB_INF __int_as_float(0x7f800000)
+#define SGB_FFS(x) __ffs(x)
+#define SGB_SHFL_XOR(v, m) __shfl_xor_sync(0xffffffffu, v, m)
 #else
+// host build of the scan functions (one lane per agent: the group reductions are the identity) — backs the
+// sgb_debug_scan_* hooks, which check pruned == exhaustive without a device
 #define SGB_UNROLL
+#define SGB_INF __builtin_huge_valf()
+#define SGB_FFS(x) __builtin_ffs((int)(x))
+#define SGB_SHFL_XOR(v, m) (v)
 #endif
+#define SGB_HD __host__ __device__
 // (__host__ too: the host build of the same source backs the arithmetic self-test hook sgb_debug_mtv_distance; the host
 // compiler runs with -ffp-contract=off, so the plain expressions round separately there as well.)
 #ifdef __CUDA_ARCH__
@@ -162,7 +171,7 @@ __device__ __noinline__ void sincos_ool(float x, float* sn, float* cs) { sincosf
 __device__ __noinline__ float tan_ool(float x) { return tanf(x); }
 __device__ __noinline__ float atan_ool(float x) { return atanf(x); }
 
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+SGB_HD __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // torch `%` (sign of the divisor) for a positive divisor
 __device__ __forceinline__ float pymod(float a, float m) {
@@ -185,8 +194,8 @@ __device__ __forceinline__ float dec_lin(float x, float x0, float x1) {
 struct Best {
     float qmin, qlim, d;
     int idx;
-    __device__ __forceinline__ void init() { qmin = __int_as_float(0x7f800000); qlim = qmin; d = qmin; idx = 0x7fffffff; }
-    __device__ __forceinline__ void upd(float qq, int s) {
+    SGB_HD __forceinline__ void init() { qmin = SGB_INF; qlim = qmin; d = qmin; idx = 0x7fffffff; }
+    SGB_HD __forceinline__ void upd(float qq, int s) {
         if (qq <= qlim) {
             float dd = sqrtf(qq);
             if (dd < d || (dd == d && s < idx)) { d = dd; idx = s; }
@@ -199,15 +208,15 @@ struct Best {
 // @region BestQ
 struct BestQ {
     float q;
-    __device__ __forceinline__ void init() { q = __int_as_float(0x7f800000); }
-    __device__ __forceinline__ void upd(float qq) { q = fminf(q, qq); }
+    SGB_HD __forceinline__ void init() { q = SGB_INF; }
+    SGB_HD __forceinline__ void upd(float qq) { q = fminf(q, qq); }
     // conservative "a box at squared distance lb2 cannot improve on q": lb > sqrt(q) + 3e-6 is implied
-    __device__ __forceinline__ bool box_useless(float lb2) const { return lb2 > q * 1.01f + 1e-7f; }
+    SGB_HD __forceinline__ bool box_useless(float lb2) const { return lb2 > q * 1.01f + 1e-7f; }
 };
 
 // squared point-segment distance, operation order of helper_scenario.py:856-871 (IEEE division): used for the  @region seg_q exact (centre)
 // centre line, whose argmin must be bit-identical to the reference
-__device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, float len2, float px, float py) {
+SGB_HD __forceinline__ float seg_q(float ax, float ay, float lx, float ly, float len2, float px, float py) {
     const float vx = subr(px, ax), vy = subr(py, ay);
     float t = madd2(vx, lx, vy, ly) / len2;
     t = clampf(t, 0.0f, 1.0f);
@@ -216,11 +225,11 @@ __device__ __forceinline__ float seg_q(float ax, float ay, float lx, float ly, f
     // torch.norm over the two components (:871) is sqrt(fma(ey, ey, ex * ex)) in ATen's CPU reduction (FMA-capable
     // x86): the second square is not rounded on its own.  1 ulp from ex*ex + ey*ey in 8 % of the cases — which decides
     // the argmin when the foot of the perpendicular sits next to a vertex (measured on 1.5e6 pairs: 0 mismatches, DESIGN.md "Exactness")
-    return __fmaf_rn(ey, ey, mulr(ex, ex));
+    return fmar(ey, ey, mulr(ex, ex));
 }
 // same with the projection parameter computed as dot * (1/len2): t differs from the reference's quotient by  @region seg_q_r (boundary)
 // <= 1.5 ulp, i.e. the distance by ~1e-8 m.  Used for the boundaries only (one reciprocal shared by 5 points).
-__device__ __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly, float rlen2, float px, float py) {
+SGB_HD __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly, float rlen2, float px, float py) {
     float vx = px - ax, vy = py - ay;
     float t = (vx * lx + vy * ly) * rlen2;
     t = fminf(fmaxf(t, 0.0f), 1.0f);
@@ -230,25 +239,29 @@ __device__ __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly,
 }
 
 // 1/x with MUFU.RCP (<= 1 ulp): only used where the result feeds continuous outputs  @region rcp/box_lb
-__device__ __forceinline__ float rcp_fast(float x) {
+SGB_HD __forceinline__ float rcp_fast(float x) {
+#ifdef __CUDA_ARCH__
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#else
+    return 1.0f / x;
+#endif
 }
 
 // distance from a point to an axis-aligned box (lower bound for every polyline point inside it)
-__device__ __forceinline__ float box_lb2(float4 bx, float px, float py) {
+SGB_HD __forceinline__ float box_lb2(float4 bx, float px, float py) {
     float dx = fmaxf(fmaxf(bx.x - px, px - bx.z), 0.0f);
     float dy = fmaxf(fmaxf(bx.y - py, py - bx.w), 0.0f);
     return dx * dx + dy * dy;
 }
-__device__ __forceinline__ float box_lb(float4 bx, float px, float py) { return sqrtf(box_lb2(bx, px, py)); }
+SGB_HD __forceinline__ float box_lb(float4 bx, float px, float py) { return sqrtf(box_lb2(bx, px, py)); }
 
 // The agent's rectangle as interX sees it (helper_scenario.py:1148-1229): closed 5-vertex polyline.  @region Rect.finish
 struct Rect {
     float vx[4], vy[4];    // vertices 0..3 (vertex 4 == vertex 0)
     float dx[4], dy[4], S[4]; // per edge i: v[i] -> v[i+1]
-    __device__ __forceinline__ void finish() {
+    SGB_HD __forceinline__ void finish() {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             int j = (i + 1) & 3;
@@ -262,7 +275,7 @@ struct Rect {
 // interX of the rectangle (as L1) against ONE segment a->b of L2; exact predicate.  C2 first: when all four  @region rect_cross_seg_L1
 // vertices lie strictly on one side of (or on) the segment's line no edge can cross it, and the four C1 terms
 // are skipped (same values as the reference would compute, just not evaluated).
-__device__ __forceinline__ bool rect_cross_seg_L1(const float* rvx, const float* rvy, float ax, float ay, float bx, float by,
+SGB_HD __forceinline__ bool rect_cross_seg_L1(const float* rvx, const float* rvy, float ax, float ay, float bx, float by,
                                                   bool no_filter = false) {
     // Takes the bare vertices: the edge vectors / S_i and the bounding box are rebuilt here, in the same fp32
     // operations as Rect::finish(), because this function runs for few segments (see the gate in scan_boundary)
@@ -304,7 +317,7 @@ __device__ __forceinline__ bool rect_cross_seg_L1(const float* rvx, const float*
 
 // interX(L1 = rectangle lo, L2 = rectangle hi), 4 x 4 edge pairs.  C1 first: f_i at hi's four vertices; if no  @region rect_cross_rect
 // edge line of lo separates two consecutive vertices of hi there is no crossing and C2 is not evaluated.
-__device__ __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx, const float* hy) {
+SGB_HD __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx, const float* hy) {
     uint32_t c1 = 0; // bit 4*i + j
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -359,7 +372,7 @@ __device__ __noinline__ int current_lanelet_ool(const float2* xy, const int32_t*
 // axes of b; outside b's projection interval a vertex contributes its signed gap on that axis, its distance is the
 // norm of the two gaps (torch.norm: sqrt(fma(g1, g1, g0*g0)), see seg_q) (:1072-1077).  A vertex strictly inside b
 // makes the pair's distance negative: minus the smallest projection overlap (:1079-1084, :1119-1124).
-__host__ __device__ __forceinline__ void mtv_half(const float* ax, const float* ay, const float* bx, const float* by,
+SGB_HD __forceinline__ void mtv_half(const float* ax, const float* ay, const float* bx, const float* by,
                                          float& pos_min, float& ov_min, bool& neg) {
     float ux[2], uy[2], mnb[2], mxb[2];
 SGB_UNROLL
@@ -398,7 +411,7 @@ SGB_UNROLL
 }
 
 // rectangle of a pose exactly as phase A builds it (get_rectangle_vertices, helper_scenario.py:742-826)
-__host__ __device__ __forceinline__ void rect_of_pose(float x, float y, float cy, float sy, float hl, float hw, float* vx, float* vy) {
+SGB_HD __forceinline__ void rect_of_pose(float x, float y, float cy, float sy, float hl, float hw, float* vx, float* vy) {
     const float nsy = -sy;
     const float bxs[4] = {hl, hl, -hl, -hl};
     const float bys[4] = {hw, -hw, -hw, hw};
@@ -409,7 +422,7 @@ SGB_UNROLL
     }
 }
 
-__host__ __device__ __forceinline__ float mtv_from_vertices(const float* ax, const float* ay, const float* bx, const float* by) {
+SGB_HD __forceinline__ float mtv_from_vertices(const float* ax, const float* ay, const float* bx, const float* by) {
     float pos_min = 3.402823466e38f, ov_j, ov_i;    // every per-vertex distance is finite
     bool neg = false;
     mtv_half(ax, ay, bx, by, pos_min, ov_j, neg);   // i's vertices on j's axes
@@ -428,21 +441,21 @@ __device__ __noinline__ float mtv_distance(float xi, float yi, float ci, float s
 
 // @region group shuffles
 template <int G>
-__device__ __forceinline__ float group_min(float v) {
+SGB_HD __forceinline__ float group_min(float v) {
 #pragma unroll
-    for (int m = 1; m < G; m <<= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, m));
+    for (int m = 1; m < G; m <<= 1) v = fminf(v, SGB_SHFL_XOR(v, m));
     return v;
 }
 template <int G>
-__device__ __forceinline__ uint32_t group_or(uint32_t v) {
+SGB_HD __forceinline__ uint32_t group_or(uint32_t v) {
 #pragma unroll
-    for (int m = 1; m < G; m <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, m);
+    for (int m = 1; m < G; m <<= 1) v |= SGB_SHFL_XOR(v, m);
     return v;
 }
 template <int G>
-__device__ __forceinline__ float group_sum(float v) {
+SGB_HD __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int m = 1; m < G; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    for (int m = 1; m < G; m <<= 1) v += SGB_SHFL_XOR(v, m);
     return v;
 }
 
@@ -468,7 +481,7 @@ struct TileSmem {
 constexpr int kSlotFloats = 10 + 8 + 4 + 6 + 4;   // per slot: 10 scalars, vtx[8], car[4], sc[6], path/flags/env/coll
 __host__ __device__ constexpr size_t tile_fixed_bytes(int A) { return ((size_t)A * kSlotFloats * sizeof(float) + 127) & ~(size_t)127; }
 template <int A>
-__device__ __forceinline__ void carve_tile(unsigned char* base, TileSmem& t) {
+SGB_HD __forceinline__ void carve_tile(unsigned char* base, TileSmem& t) {
     float* f = reinterpret_cast<float*>(base);
     t.px = f; f += A; t.py = f; f += A; t.ox = f; f += A; t.oy = f; f += A;
     t.cs = f; f += A; t.sn = f; f += A; t.vx = f; f += A; t.vy = f; f += A; t.vabs = f; f += A; t.psim = f; f += A;
@@ -491,7 +504,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int A, int N) {
 
 // centre line: min distance + closest index from (px,py)  @region scan_center
 template <int G>
-__device__ __forceinline__ void scan_center(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_c,
+SGB_HD __forceinline__ void scan_center(const float2* __restrict__ pts, const float4* __restrict__ boxes, int n_c,
                                             int hint_seg, bool exhaustive, float px, float py, int lane, float& d_out,
                                             int& idx_out) {
     const int nseg = n_c - 1;
@@ -523,7 +536,7 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
     m = group_or<G>(m) & (nch >= 32 ? 0xffffffffu : ((1u << nch) - 1u)) & ~(1u << c0);
 #pragma unroll 1
     while (m) {
-        const int c = __ffs(m) - 1;
+        const int c = SGB_FFS(m) - 1;
         m &= m - 1;
         chunk(c);
     }
@@ -532,8 +545,8 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
     int idx = b.idx;
 #pragma unroll
     for (int k = 1; k < G; k <<= 1) {
-        float od = __shfl_xor_sync(0xffffffffu, d, k);
-        int oi = __shfl_xor_sync(0xffffffffu, idx, k);
+        float od = SGB_SHFL_XOR(d, k);
+        int oi = SGB_SHFL_XOR(idx, k);
         if (od < d || (od == d && oi < idx)) { d = od; idx = oi; }
     }
     d_out = d;
@@ -546,7 +559,7 @@ __device__ __forceinline__ void scan_center(const float2* __restrict__ pts, cons
 // evaluates all five points: a per-point refinement of the vote (which points can still improve in this box)
 // was measured to cost more — instructions, registers, shuffles — than the evaluations it saved.
 template <int G>
-__device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes,
+SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const float4* __restrict__ boxes,
                                               const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
                                               float px, float py, const float* cs_s, const float* sn_s,
                                               const float* psi_m_s, const float* rvx, const float* rvy, float rect_radius,
@@ -567,7 +580,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
         uint32_t m = md | mx;
 #pragma unroll 1
         while (m) {
-            const int c = __ffs(m) - 1;
+            const int c = SGB_FFS(m) - 1;
             m &= m - 1;
             const bool do_x = (mx >> c) & 1u, do_d = (md >> c) & 1u;
             const int s1 = min(c * kChunk + kChunk, nseg);
@@ -577,7 +590,7 @@ __device__ __forceinline__ void scan_boundary(const float2* __restrict__ pts, co
                 const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
                 const float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
                 const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, len2b = lx2 * lx2 + ly2 * ly2;
-                float q0a = __int_as_float(0x7f800000), q0b = q0a;   // centre -> segment, +inf when not evaluated
+                float q0a = SGB_INF, q0b = q0a;   // centre -> segment, +inf when not evaluated
                 if (do_d) {
                     const float rl = rcp_fast(len2), rl2 = rcp_fast(len2b);
                     q0a = seg_q_r(a.x, a.y, lx, ly, rl, px, py);

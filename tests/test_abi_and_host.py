@@ -331,3 +331,69 @@ def test_packed_blob_certificates_hold_on_every_map():
                     rel = np.mod(ang - mid + np.pi / 2, np.pi) - np.pi / 2          # difference of undirected lines
                     assert np.abs(rel).max() <= half - np.arcsin(0.01) + 1e-3, (st, i, c, np.abs(rel).max(), half)
     assert n_cones > 1500 and n_wide < 0.05 * n_cones
+
+
+def _scan_batch(L, m, path, pos, psi, hint, exhaustive):
+    import ctypes as C
+    d = m.desc()
+    xs, ys = np.ascontiguousarray(pos[:, 0]), np.ascontiguousarray(pos[:, 1])
+    out = np.zeros((len(path), 16), np.float32)
+    rc = L.sgb_debug_scan_batch(C.byref(d), len(path), path.ctypes.data, xs.ctypes.data, ys.ctypes.data, psi.ctypes.data,
+                                hint.ctypes.data, C.c_float(0.11), C.c_float(0.0535), int(exhaustive), out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def _scan_poses(m, n, rng):
+    """Poses around the map's centre lines: lateral / longitudinal noise of 6 cm (half of them touch a boundary),
+    headings along the path +- 0.5 rad (a tenth exactly along it: collinear edges), hints from exact to random."""
+    path = rng.integers(0, m.n_paths, n).astype(np.int32)
+    nc = m.n_center[path]
+    k = (rng.random(n) * (nc - 1)).astype(np.int64)
+    yaw_off = np.concatenate([[0], np.cumsum(m.n_center - 1)])
+    yaw = m.center_yaw[np.minimum(yaw_off[path] + k, yaw_off[path + 1] - 1)]
+    pos = (m.center_xy[m.center_off[path] + k] + rng.normal(0, 0.06, (n, 2))).astype(np.float32)
+    psi = (yaw + rng.normal(0, 0.5, n)).astype(np.float32)
+    psi[:n // 10] = yaw[:n // 10]
+    hint = np.where(rng.random(n) < 0.7, k + 1 + rng.integers(-3, 4, n), rng.integers(0, nc)).astype(np.int32)
+    return path, pos, psi, hint
+
+
+def test_pruned_scans_equal_exhaustive_scans_on_the_host_for_every_map(oracle_mod):
+    """sgb_debug_scan_batch runs the kernels' OWN scan_center / scan_boundary source (host build, one lane per agent)
+    through the phase-B glue on a freshly packed blob.  (1) On all 18 maps the pruned search — hint chunk, box votes,
+    direction cones / bands, crossing gate — returns bit for bit what the exhaustive one returns: closest index,
+    centre / vertex distances, lane-crossing flags (about half of the poses cross a boundary).  (2) The result is the
+    reference's: closest index and crossing flags equal the oracle's get_perpendicular_distances / interX restatement
+    exactly, distances to 1e-6."""
+    import ctypes as C
+    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.maps import MapLibrary, available_scenarios
+    L, O = load_library(), oracle_mod
+    ol = O.lib()
+    rng = np.random.default_rng(0)
+    n_hits = n_checked = 0
+    for st in available_scenarios():
+        m = MapLibrary(st)
+        path, pos, psi, hint = _scan_poses(m, 1500, rng)
+        pruned, full = (_scan_batch(L, m, path, pos, psi, hint, ex) for ex in (0, 1))
+        assert np.array_equal(pruned.view(np.uint32), full.view(np.uint32)), st
+        n_hits += int(full[:, 7].sum() + full[:, 14].sum())
+        pm = O.PaddedMap(st)
+        if pm.n_paths != m.n_paths:
+            continue                                    # cpm_mixed: the oracle numbers the three path sets separately
+        for i in range(0, 1500, 25):
+            p = int(path[i])
+            idx = C.c_int()
+            pt = np.ascontiguousarray(pos[i])
+            d = ol.orc_test_perp(pt.ctypes.data, pm.center[p].ctypes.data, pm.P, int(pm.n_center[p]), C.byref(idx))
+            assert idx.value == int(full[i, 1]) and abs(d - full[i, 0]) <= 1e-6, (st, i)
+            rect = np.zeros((5, 2), np.float32)
+            ol.orc_test_rect(C.c_float(0.11), C.c_float(0.0535), pt.ctypes.data, C.c_float(float(psi[i])), rect.ctypes.data)
+            for side, poly, cnt in ((0, pm.left, pm.n_left), (1, pm.right, pm.n_right)):
+                hit = ol.orc_test_interx(rect.ctypes.data, 5, poly[p].ctypes.data, pm.P)
+                assert bool(hit) == bool(full[i, 7 + 7 * side]), (st, i, side)
+                dcg = ol.orc_test_perp(pt.ctypes.data, poly[p].ctypes.data, pm.P, int(cnt[p]), C.byref(idx))
+                assert abs(dcg - full[i, 2 + 7 * side]) <= 1e-6, (st, i, side)
+            n_checked += 1
+    assert n_hits > 10000 and n_checked > 900
