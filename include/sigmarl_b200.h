@@ -293,6 +293,10 @@ int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity
 int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const int32_t* path, const float* x, const float* y,
                          const float* psi, const int32_t* hint_idx, float half_length, float half_width,
                          int32_t exhaustive, float* out);
+/* Work counters of sgb_debug_scan_batch on this thread since the last reset: 0 segment evaluations of the centre-line
+ * scans, 1 of the boundary scans (each covers the centre + 4 vertices), 2 chunk boxes tested in the votes, 3 exact
+ * crossing predicates, 4 centre scans, 5 boundary scans.  For sizing changes to the pruning logic without a GPU. */
+void sgb_debug_scan_counters(int64_t* out8, int32_t reset);
 /* Host build of the kernels' current_lanelet() on a host-resident lanelet table (arithmetic self-test). */
 int sgb_debug_current_lanelet(int32_t n_lanelets, const float* center_xy, const int32_t* center_off, float x, float y);
 

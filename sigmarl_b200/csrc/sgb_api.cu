@@ -467,6 +467,10 @@ extern "C" int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const in
     return SGB_OK;
 }
 
+extern "C" void sgb_debug_scan_counters(int64_t* out8, int32_t reset) {
+    for (int i = 0; i < 8; i++) { if (out8) out8[i] = sgb::g_scan_counters[i]; if (reset) sgb::g_scan_counters[i] = 0; }
+}
+
 extern "C" int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity) {
     Packed pk;
     const int rc = pack_map(map, pk);

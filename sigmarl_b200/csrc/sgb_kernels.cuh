@@ -148,6 +148,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 #define SGB_SHFL_XOR(v, m) (v)
 #endif
 #define SGB_HD __host__ __device__
+// work counters of the host build (sgb_debug_scan_counters): 0 segment evaluations of the centre scan, 1 of the
+// boundary scans (each covers 5 points), 2 chunk boxes tested in the votes, 3 exact crossing predicates, 4 scans
+static thread_local long long g_scan_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // host only
+#ifdef __CUDA_ARCH__
+#define SGB_COUNT(i, n)
+#else
+#define SGB_COUNT(i, n) (g_scan_counters[i] += (n))
+#endif
 // (__host__ too: the host build of the same source backs the arithmetic self-test hook sgb_debug_mtv_distance; the host
 // compiler runs with -ffp-contract=off, so the plain expressions round separately there as well.)
 #ifdef __CUDA_ARCH__
@@ -525,6 +533,7 @@ SGB_HD __forceinline__ void scan_center(const float2* __restrict__ pts, const fl
             const float q2 = seg_q(a2.x, a2.y, lx2, ly2, madd2(lx2, lx2, ly2, ly2), px, py);
             b.upd(q1, s);
             b.upd(q2, s2);
+            SGB_COUNT(0, 2);
         }
     };
     chunk(c0);
@@ -532,6 +541,8 @@ SGB_HD __forceinline__ void scan_center(const float2* __restrict__ pts, const fl
     thr = thr * thr;
     uint32_t m = 0;
     for (int c = lane; c < nch; c += G) m |= (box_lb2(boxes[c], px, py) > thr) ? 0u : (1u << c);
+    SGB_COUNT(2, (nch + G - 1) / G);
+    SGB_COUNT(4, 1);
     if (exhaustive) m = 0xffffffffu;
     m = group_or<G>(m) & (nch >= 32 ? 0xffffffffu : ((1u << nch) - 1u)) & ~(1u << c0);
 #pragma unroll 1
@@ -592,6 +603,7 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
                 const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, len2b = lx2 * lx2 + ly2 * ly2;
                 float q0a = SGB_INF, q0b = q0a;   // centre -> segment, +inf when not evaluated
                 if (do_d) {
+                    SGB_COUNT(1, 2);
                     const float rl = rcp_fast(len2), rl2 = rcp_fast(len2b);
                     q0a = seg_q_r(a.x, a.y, lx, ly, rl, px, py);
                     q0b = seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py);
@@ -628,10 +640,14 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
                         const float wl = half_w + kFarMargin, ll = half_l + kFarMargin;
                         return (fminf(lat, late) > wl) | (fmaxf(lat, late) < -wl) | (fminf(lon, lone) > ll) | (fmaxf(lon, lone) < -ll);
                     };
-                    if (exhaustive || (ga && (cola || !separated(a.x, a.y, lx, ly))))
+                    if (exhaustive || (ga && (cola || !separated(a.x, a.y, lx, ly)))) {
+                        SGB_COUNT(3, 1);
                         hit |= rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y, true);
-                    if (exhaustive || (gb && (colb || !separated(a2.x, a2.y, lx2, ly2))))
+                    }
+                    if (exhaustive || (gb && (colb || !separated(a2.x, a2.y, lx2, ly2)))) {
+                        SGB_COUNT(3, 1);
                         hit |= rect_cross_seg_L1(rvx, rvy, a2.x, a2.y, e2.x, e2.y, true);
+                    }
                 }
             }
         }
@@ -647,6 +663,8 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
         const float pi_f = 3.14159274f, half_pi = 1.57079637f;
         const float psi_m = *psi_m_s, cs = *cs_s, sn = *sn_s;
         const float acs = fabsf(cs), asn = fabsf(sn);
+        SGB_COUNT(2, (nch + G - 1) / G);
+        SGB_COUNT(5, 1);
         for (int c = lane; c < nch; c += G) {   // branch-free; c0 is masked out below
             const float4 bx = boxes[c];
             const float2 cone = __half22float2(cones[c]);
