@@ -237,3 +237,67 @@ def test_single_valued_parameters_are_refused_not_ignored(facade):
     sc.parameters = P()
     with pytest.raises(NotImplementedError):
         sc.env_make_world(2, "cpu")
+
+
+class _ToyEnv:
+    """Deterministic stand-in with RoadTrafficEnv's rollout surface (obs / reward / done / action buffers, bind, step,
+    reset_done): obs' = obs + mean(action), reward = sum(action), done every 3rd step for env b == t % B; a reset writes
+    a recognisable fresh observation.  Lets the two collectors of rollout.collect be compared on the CPU."""
+
+    def __init__(self, B=4, N=2, D=3):
+        self.B, self.N, self.D, self.device = B, N, D, torch.device("cpu")
+        self.obs, self.reward = torch.zeros(B, N, D), torch.zeros(B, N)
+        self.done, self.action = torch.zeros(B, dtype=torch.uint8), torch.zeros(B, N, 2)
+        self.t = 0
+
+    def bind(self, **tensors):
+        for k, v in tensors.items():
+            assert k in ("obs", "reward", "done", "action") and v.shape == getattr(self, k).shape
+            setattr(self, k, v)
+
+    def step(self, action=None):
+        if action is not None:
+            self.action.copy_(action)
+        prev = self._prev_obs if hasattr(self, "_prev_obs") else torch.zeros(self.B, self.N, self.D)
+        self.obs.copy_(prev + self.action.mean(-1, keepdim=True))
+        self.reward.copy_(self.action.sum(-1))
+        self.done.zero_()
+        if self.t % 3 == 2:
+            self.done[self.t % self.B] = 1
+        self.t += 1
+        self._prev_obs = self.obs.clone()
+        return self.obs, self.reward, self.done
+
+    def reset_done(self, write_obs=True):
+        m = self.done.bool()
+        if m.any():
+            self.obs[m] = -100.0 - self.t
+            self._prev_obs = self.obs.clone()
+
+
+def test_in_place_and_copying_collectors_agree_on_the_cpu():
+    """rollout.collect (helper_training.py:686-788's replacement): with in_place=True the env's outputs are bound to the
+    rollout buffer — step t reads buf.action[t], writes buf.reward[t], buf.done[t] and buf.obs[t + 1] — and must leave
+    exactly what the copying collector leaves, including the post-reset observations of done envs and the env's own
+    buffers being restored afterwards."""
+    from sigmarl_b200.rollout import RolloutBuffer, collect
+    T = 8
+    res = []
+    for in_place in (False, True):
+        env = _ToyEnv()
+        env._prev_obs = torch.ones(env.B, env.N, env.D)
+        env.obs.fill_(1.0)
+        own = dict(obs=env.obs, reward=env.reward, done=env.done, action=env.action)
+        g = torch.Generator().manual_seed(0)
+        policy = lambda obs: torch.rand(4, 2, 2, generator=g) + 0.01 * obs[..., :2]  # noqa: E731
+        value = lambda obs: obs[..., 0] * 2.0  # noqa: E731
+        buf = collect(env, policy, RolloutBuffer(T, env.B, env.N, env.D, "cpu"), value_fn=value, in_place=in_place)
+        assert all(getattr(env, k) is v for k, v in own.items())          # bindings restored
+        res.append((buf, env.obs.clone(), env.reward.clone(), env.done.clone()))
+    a, b = res
+    for name in ("obs", "action", "reward", "done", "value", "next_value"):
+        assert torch.equal(getattr(a[0], name), getattr(b[0], name)), name
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    assert int(a[0].done.sum()) == 2 and (a[0].obs[3, 2] <= -100).all()      # the reset env's next observation is the fresh one
+    # TorchRL semantics: next_value of the done step is the value of the step-time observation, not of the fresh one
+    assert float(a[0].next_value[2, 2].min()) > -100.0
