@@ -365,7 +365,7 @@ def test_pruned_scans_equal_exhaustive_scans_on_the_host_for_every_map(oracle_mo
     direction cones / bands, crossing gate — returns bit for bit what the exhaustive one returns: closest index,
     centre / vertex distances, lane-crossing flags (about half of the poses cross a boundary).  (2) The result is the
     reference's: closest index and crossing flags equal the oracle's get_perpendicular_distances / interX restatement
-    exactly, distances to 1e-6."""
+    exactly, the centre-line distance bit for bit, the boundary distances (reciprocal form) to 1e-6."""
     import ctypes as C
     from sigmarl_b200.lib import load_library
     from sigmarl_b200.maps import MapLibrary, available_scenarios
@@ -382,12 +382,12 @@ def test_pruned_scans_equal_exhaustive_scans_on_the_host_for_every_map(oracle_mo
         pm = O.PaddedMap(st)
         if pm.n_paths != m.n_paths:
             continue                                    # cpm_mixed: the oracle numbers the three path sets separately
-        for i in range(0, 1500, 25):
+        for i in range(0, 1500, 3):
             p = int(path[i])
             idx = C.c_int()
             pt = np.ascontiguousarray(pos[i])
             d = ol.orc_test_perp(pt.ctypes.data, pm.center[p].ctypes.data, pm.P, int(pm.n_center[p]), C.byref(idx))
-            assert idx.value == int(full[i, 1]) and abs(d - full[i, 0]) <= 1e-6, (st, i)
+            assert idx.value == int(full[i, 1]) and d == full[i, 0], (st, i)      # the pinned centre scan: bit-identical
             rect = np.zeros((5, 2), np.float32)
             ol.orc_test_rect(C.c_float(0.11), C.c_float(0.0535), pt.ctypes.data, C.c_float(float(psi[i])), rect.ctypes.data)
             for side, poly, cnt in ((0, pm.left, pm.n_left), (1, pm.right, pm.n_right)):
@@ -396,4 +396,4 @@ def test_pruned_scans_equal_exhaustive_scans_on_the_host_for_every_map(oracle_mo
                 dcg = ol.orc_test_perp(pt.ctypes.data, poly[p].ctypes.data, pm.P, int(cnt[p]), C.byref(idx))
                 assert abs(dcg - full[i, 2 + 7 * side]) <= 1e-6, (st, i, side)
             n_checked += 1
-    assert n_hits > 10000 and n_checked > 900
+    assert n_hits > 10000 and n_checked > 8000
