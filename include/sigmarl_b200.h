@@ -297,6 +297,10 @@ int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const int32_t* path
  * scans, 1 of the boundary scans (each covers the centre + 4 vertices), 2 chunk boxes tested in the votes, 3 exact
  * crossing predicates, 4 centre scans, 5 boundary scans.  For sizing changes to the pruning logic without a GPU. */
 void sgb_debug_scan_counters(int64_t* out8, int32_t reset);
+/* Host builds of the kernels' small helpers: which 0 wrap_pi(in[0]); 1 dec_lin(in[0], in[1], in[2]); 2 kth_nearest over
+ * in[1..n-1] with rank (int)in[0] -> out[0] index, out[1] distance.  And short_term() on a padded polyline. */
+int sgb_debug_helper(int32_t which, const float* in, int32_t n, float* out);
+int sgb_debug_short_term(const float* poly_xy, int32_t n_center, int32_t is_loop, int32_t idx, float* out6);
 /* Host build of the kernels' current_lanelet() on a host-resident lanelet table (arithmetic self-test). */
 int sgb_debug_current_lanelet(int32_t n_lanelets, const float* center_xy, const int32_t* center_off, float x, float y);
 

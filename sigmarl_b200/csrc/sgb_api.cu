@@ -467,6 +467,30 @@ extern "C" int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const in
     return SGB_OK;
 }
 
+// Host builds of the kernels' small helpers, against the reference's known-answer vectors (tests/test_abi_and_host.py):
+// which 0 wrap_pi(in[0]) (angle_eliminate_two_pi), 1 dec_lin(in[0], in[1], in[2]) (decreasing_fcn, linear),
+// 2 kth_nearest(in[1..N], N = n - 1, kk = (int)in[0]) -> out[0] index, out[1] distance (torch.topk order)
+extern "C" int sgb_debug_helper(int32_t which, const float* in, int32_t n, float* out) {
+    if (!in || !out) return SGB_ERR_ARG;
+    if (which == 0) { out[0] = sgb::wrap_pi(in[0]); return SGB_OK; }
+    if (which == 1) { out[0] = sgb::dec_lin(in[0], in[1], in[2]); return SGB_OK; }
+    if (which == 2 && n >= 2 && n - 1 <= SGB_MAX_AGENTS) {
+        float d = 0.0f;
+        out[0] = (float)sgb::kth_nearest(in + 1, n - 1, (int)in[0], &d);
+        out[1] = d;
+        return SGB_OK;
+    }
+    return SGB_ERR_ARG;
+}
+// ... and of short_term() (get_short_term_reference_path with shift 1, interval 2) on a padded polyline [n_pts][2]
+extern "C" int sgb_debug_short_term(const float* poly_xy, int32_t n_c, int32_t is_loop, int32_t idx, float* out6) {
+    if (!poly_xy || !out6) return SGB_ERR_ARG;
+    float2 st[3];
+    sgb::short_term(reinterpret_cast<const float2*>(poly_xy), n_c, is_loop != 0, idx, st);
+    for (int k = 0; k < 3; k++) { out6[2 * k] = st[k].x; out6[2 * k + 1] = st[k].y; }
+    return SGB_OK;
+}
+
 extern "C" void sgb_debug_scan_counters(int64_t* out8, int32_t reset) {
     for (int i = 0; i < 8; i++) { if (out8) out8[i] = sgb::g_scan_counters[i]; if (reset) sgb::g_scan_counters[i] = 0; }
 }

@@ -182,14 +182,14 @@ __device__ __noinline__ float atan_ool(float x) { return atanf(x); }
 SGB_HD __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // torch `%` (sign of the divisor) for a positive divisor
-__device__ __forceinline__ float pymod(float a, float m) {
+SGB_HD __forceinline__ float pymod(float a, float m) {
     float r = fmodf(a, m);
     if (r != 0.0f && r < 0.0f) r += m;
     return r;
 }
 
 // helper_scenario.py:960-996 decreasing_fcn(type="linear")
-__device__ __forceinline__ float dec_lin(float x, float x0, float x1) {
+SGB_HD __forceinline__ float dec_lin(float x, float x0, float x1) {
     x = clampf(x, x0, x1);
     return 1.0f - (x - x0) / (x1 - x0);
 }
@@ -706,13 +706,13 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
 }
 
 // index (and distance) of the rank-kk nearest agent: torch.topk(k, largest=False) order, ties -> lower index  @region kth_nearest/short_term
-__device__ __forceinline__ int kth_nearest(const float* dij, int N, int kk, float* d_out) {
+SGB_HD __forceinline__ int kth_nearest(const float* dij, int N, int kk, float* d_out) {
     uint32_t used = 0;
     int bj = 0;
     float bd = 0.0f;
     for (int q = 0; q <= kk; q++) {
         bj = -1;
-        bd = __int_as_float(0x7f800000);
+        bd = SGB_INF;
         for (int j = 0; j < N; j++) {
             float dj = dij[j];
             if (!((used >> j) & 1u) && (bj < 0 || dj < bd)) { bd = dj; bj = j; }
@@ -724,8 +724,8 @@ __device__ __forceinline__ int kth_nearest(const float* dij, int N, int kk, floa
 }
 
 // helper_scenario.py:892-957 short-term reference path (n_points_shift = 1, sample interval 2)
-__device__ __forceinline__ void short_term(const float2* __restrict__ cpts, int n_c, bool is_loop, int idx, float2 out[3]) {
-#pragma unroll
+SGB_HD __forceinline__ void short_term(const float2* __restrict__ cpts, int n_c, bool is_loop, int idx, float2 out[3]) {
+SGB_UNROLL
     for (int k = 0; k < SGB_N_SHORT_TERM; k++) {
         int fi = 2 * k + idx + 1;
         if (is_loop && fi >= n_c - 1) fi = (fi + 1) % n_c;
@@ -742,7 +742,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
 }
 
 // helper_scenario.py:1276-1289 angle_eliminate_two_pi (fp32: the python scalars are cast to the tensor's dtype)
-__device__ __forceinline__ float wrap_pi(float a) {
+SGB_HD __forceinline__ float wrap_pi(float a) {
     const float pi_f = 3.14159274101257324f, two_pi = 6.28318548202514648f;
     float m = pymod(a, two_pi);
     if (m > pi_f) m -= two_pi;

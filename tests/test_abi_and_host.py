@@ -397,3 +397,40 @@ def test_pruned_scans_equal_exhaustive_scans_on_the_host_for_every_map(oracle_mo
                 assert abs(dcg - full[i, 2 + 7 * side]) <= 3e-6, (st, i, side)   # reciprocal form: a few ulps of a 4 m coordinate
             n_checked += 1
     assert n_hits > 10000 and n_checked > 8000
+
+
+def test_kernel_helpers_match_the_references_known_answers_on_the_host():
+    """Host builds of the kernels' small helper functions (sgb_debug_helper / sgb_debug_short_term) against the vectors the
+    UNMODIFIED reference helpers produced (oracle/gen_kat.py -> tests/golden/kat/helpers.npz): angle_eliminate_two_pi
+    (helper_scenario.py:1276-1289) and decreasing_fcn (:960-996) to 1e-6 (fmodf / division), the short-term reference
+    path gather (:892-957, loop and open paths, closest point = last point) bit for bit; and kth_nearest against
+    torch.topk(largest=False) incl. ties."""
+    import ctypes as C
+    import torch
+    from sigmarl_b200.lib import load_library
+    L = load_library()
+    k = np.load(os.path.join(REPO, "tests", "golden", "kat", "helpers.npz"))
+    out = np.zeros(8, np.float32)
+    for x, want in zip(k["wrap_in"], k["wrap_out"]):
+        assert L.sgb_debug_helper(0, np.float32([x]).ctypes.data, 1, out.ctypes.data) == 0
+        assert abs(out[0] - want) <= 1e-6 or abs(abs(out[0] - want) - 2 * np.pi) <= 1e-6, (x, out[0], want)
+    for x, want in zip(k["dec_x"], k["dec_lin_0_03"]):
+        assert L.sgb_debug_helper(1, np.float32([x, 0.0, 0.3]).ctypes.data, 3, out.ctypes.data) == 0
+        assert abs(out[0] - want) <= 1e-6, (x, out[0], want)
+    poly, n_c, loop, idx0 = k["st_poly"], k["st_n"], k["st_loop"], k["st_idx0"]
+    for i in range(poly.shape[0]):
+        p = np.ascontiguousarray(poly[i], np.float32)
+        assert L.sgb_debug_short_term(p.ctypes.data, int(n_c[i]), int(loop[i]), int(idx0[i]), out.ctypes.data) == 0
+        assert np.array_equal(out[:6].reshape(3, 2), k["st_pts"][i]), i
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        n = int(rng.integers(2, 33))
+        d = rng.random(n).astype(np.float32)
+        if n > 3:
+            d[rng.integers(0, n)] = d[rng.integers(0, n)]          # exact ties
+        kk = int(rng.integers(0, n))
+        vals, idx = torch.topk(torch.from_numpy(d), k=kk + 1, largest=False)
+        assert L.sgb_debug_helper(2, np.concatenate([[np.float32(kk)], d]).astype(np.float32).ctypes.data, n + 1, out.ctypes.data) == 0
+        assert out[1] == float(vals[kk]), (d, kk)
+        # torch.topk does not promise an order among equal values; the kernel (like a stable sort) takes the lower index
+        assert int(out[0]) == int(np.argsort(d, kind="stable")[kk]), (d, kk)
