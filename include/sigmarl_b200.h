@@ -301,6 +301,10 @@ void sgb_debug_scan_counters(int64_t* out8, int32_t reset);
  * in[1..n-1] with rank (int)in[0] -> out[0] index, out[1] distance.  And short_term() on a padded polyline. */
 int sgb_debug_helper(int32_t which, const float* in, int32_t n, float* out);
 int sgb_debug_short_term(const float* poly_xy, int32_t n_center, int32_t is_loop, int32_t idx, float* out6);
+/* Rectangle-pair crossing for n pose pairs (x, y, psi): out[i] bit 0 = the kernels' rect_cross_rect (host build), bit 1 =
+ * the far-and-not-collinear gate of the pair loop would skip the pair (a skipped pair must never cross). */
+int sgb_debug_pair_batch(int32_t n, const float* lo_xyp, const float* hi_xyp, float half_length, float half_width,
+                         uint8_t* out);
 /* Host build of the kernels' current_lanelet() on a host-resident lanelet table (arithmetic self-test). */
 int sgb_debug_current_lanelet(int32_t n_lanelets, const float* center_xy, const int32_t* center_off, float x, float y);
 

@@ -491,6 +491,32 @@ extern "C" int sgb_debug_short_term(const float* poly_xy, int32_t n_c, int32_t i
     return SGB_OK;
 }
 
+// Rectangle-pair crossing (interX(vertices[lo], vertices[hi]), world_state_rt_sim.py:384-393) for n pose pairs
+// (x, y, psi each): out[i] bit 0 = the kernels' rect_cross_rect (host build), bit 1 = "the pair gate would skip it".
+// The gate itself is inline in env_step_kernel; the four lines below restate it (keep in sync) — what is checked is the
+// certificate: a skipped pair never crosses.
+extern "C" int sgb_debug_pair_batch(int32_t n, const float* lo3, const float* hi3, float half_length, float half_width,
+                                    uint8_t* out) {
+    if (n < 0 || !lo3 || !hi3 || !out) return SGB_ERR_ARG;
+    const float rect_radius = std::sqrt(half_length * half_length + half_width * half_width) * 1.0001f;
+    for (int i = 0; i < n; i++) {
+        const float* a = lo3 + 3 * (size_t)i;
+        const float* b = hi3 + 3 * (size_t)i;
+        const float c1 = cosf(a[2]), s1 = sinf(a[2]), c2 = cosf(b[2]), s2 = sinf(b[2]);
+        sgb::Rect rl;
+        float hx[4], hy[4];
+        sgb::rect_of_pose(a[0], a[1], c1, s1, half_length, half_width, rl.vx, rl.vy);
+        sgb::rect_of_pose(b[0], b[1], c2, s2, half_length, half_width, hx, hy);
+        rl.finish();
+        const float ddx = b[0] - a[0], ddy = b[1] - a[1];
+        const float cr = c1 * s2 - s1 * c2, dt = c1 * c2 + s1 * s2;
+        const float reach = 2.0f * rect_radius + kFarMargin;
+        const bool skip = ddx * ddx + ddy * ddy > reach * reach && fminf(fabsf(cr), fabsf(dt)) > kCollinear;
+        out[i] = (uint8_t)((sgb::rect_cross_rect(rl, hx, hy) ? 1 : 0) | (skip ? 2 : 0));
+    }
+    return SGB_OK;
+}
+
 extern "C" void sgb_debug_scan_counters(int64_t* out8, int32_t reset) {
     for (int i = 0; i < 8; i++) { if (out8) out8[i] = sgb::g_scan_counters[i]; if (reset) sgb::g_scan_counters[i] = 0; }
 }

@@ -21,7 +21,7 @@ EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points"
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
            "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance", "sgb_debug_pack_map",
            "sgb_set_lanelets", "sgb_debug_current_lanelet", "sgb_debug_pack_map_blob", "sgb_debug_scan_batch", "sgb_debug_scan_counters",
-           "sgb_debug_helper", "sgb_debug_short_term"]
+           "sgb_debug_helper", "sgb_debug_short_term", "sgb_debug_pair_batch"]
 
 
 class SgbError(RuntimeError):
@@ -103,6 +103,7 @@ def load_library():
     L.sgb_set_lanelets.argtypes = [vp, i32, vp, vp, vp]
     L.sgb_debug_current_lanelet.argtypes = [i32, vp, vp, C.c_float, C.c_float]
     L.sgb_debug_scan_batch.argtypes = [C.POINTER(MapDesc), i32, vp, vp, vp, vp, vp, C.c_float, C.c_float, i32, vp]
+    L.sgb_debug_pair_batch.argtypes = [i32, vp, vp, C.c_float, C.c_float, vp]
     L.sgb_debug_helper.argtypes = [i32, vp, i32, vp]
     L.sgb_debug_short_term.argtypes = [vp, i32, i32, i32, vp]
     L.sgb_debug_scan_counters.argtypes = [vp, i32]

@@ -434,3 +434,31 @@ def test_kernel_helpers_match_the_references_known_answers_on_the_host():
         assert out[1] == float(vals[kk]), (d, kk)
         # torch.topk does not promise an order among equal values; the kernel (like a stable sort) takes the lower index
         assert int(out[0]) == int(np.argsort(d, kind="stable")[kk]), (d, kk)
+
+
+def test_rectangle_pair_crossing_on_the_host(oracle_mod):
+    """Host build of the kernels' rect_cross_rect == the oracle's interX restatement on rectangle pairs from touching to
+    far apart (incl. identical / parallel / collinear ones), and the pair gate's certificate: a pair the gate skips
+    (far and not collinear) never crosses."""
+    import ctypes as C
+    from sigmarl_b200.lib import load_library
+    L, ol = load_library(), oracle_mod.lib()
+    rng = np.random.default_rng(3)
+    n = 60000
+    lo = np.zeros((n, 3), np.float32)
+    lo[:, :2] = rng.uniform(0, 4, (n, 2)); lo[:, 2] = rng.uniform(-7, 7, n)
+    hi = lo.copy()
+    hi[:, :2] += rng.normal(0, 1, (n, 2)).astype(np.float32) * rng.choice([0.05, 0.15, 0.4, 2.0], (n, 1)).astype(np.float32)
+    hi[:, 2] = np.where(rng.random(n) < 0.3, lo[:, 2] + rng.integers(0, 4, n) * np.float32(np.pi / 2), rng.uniform(-7, 7, n))
+    hi[:50] = lo[:50]                                             # identical rectangles
+    out = np.zeros(n, np.uint8)
+    assert L.sgb_debug_pair_batch(n, lo.ctypes.data, hi.ctypes.data, C.c_float(0.11), C.c_float(0.0535), out.ctypes.data) == 0
+    cross, skip = (out & 1) != 0, (out & 2) != 0
+    assert not (cross & skip).any()
+    assert 0.1 < cross.mean() < 0.9 and 0.1 < skip.mean() < 0.9
+    ra, rb = np.zeros((5, 2), np.float32), np.zeros((5, 2), np.float32)
+    for i in range(0, n, 20):
+        pa, pb = np.ascontiguousarray(lo[i, :2]), np.ascontiguousarray(hi[i, :2])     # (named: the pointers must stay valid)
+        ol.orc_test_rect(C.c_float(0.11), C.c_float(0.0535), pa.ctypes.data, C.c_float(float(lo[i, 2])), ra.ctypes.data)
+        ol.orc_test_rect(C.c_float(0.11), C.c_float(0.0535), pb.ctypes.data, C.c_float(float(hi[i, 2])), rb.ctypes.data)
+        assert bool(ol.orc_test_interx(ra.ctypes.data, 5, rb.ctypes.data, 5)) == bool(cross[i]), i
