@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 126
+#define SGB_VERSION 127
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -96,8 +96,10 @@ typedef struct {
                                  observation_provider_rt.py:594-925 */
     float norm_pos_world_x, norm_pos_world_y; /* normalizers.pos_world (bird view)  road_traffic.py:593-595 */
     float norm_dist_agent;    /* normalizers.distance_agent (lengths / widths)      road_traffic.py:605-607 */
-    float obs_noise_level;    /* is_obs_noise ? obs_noise_level : 0: obs += level * U[0,1) per element
-                                 (observation_provider_rt.py:611-617); device generator, distribution-equivalent */
+    float obs_noise_level;    /* is_obs_noise ? obs_noise_level : 0: obs += level * U[0,1) per element, fresh draws per
+                                 call (observation_provider_rt.py:611-617); counter-based device generator keyed by
+                                 (obs_noise_seed, API-call counter, global env index, agent, column):
+                                 distribution-equivalent, independent of sharding */
     uint32_t obs_noise_seed;
     int32_t reset_fixed_period; /* reset_agent_fixed_duration as a step period, 0 = off: an env is also done at every
                                  step with timer.step % period == 0.  The reference tests float32(timer.step * dt) %
@@ -192,6 +194,11 @@ int sgb_destroy(sgb_ctx* ctx);
  * flag-driven observation writer then evaluates per observed neighbour. */
 int sgb_set_lanelets(sgb_ctx* ctx, int32_t n_lanelets, const float* center_xy, const int32_t* center_off,
                      const uint8_t* adjacency);
+
+/* Global index of this context's env 0 when a batch is sharded over several contexts / GPUs (default 0).  The reset
+ * entry points take it as an argument (and remember it); the observation noise is keyed by it as well, so that noisy
+ * observations do not depend on how envs are sharded.  Has no counterpart in the reference (single process). */
+int sgb_set_env_offset(sgb_ctx* ctx, int64_t env_offset);
 
 /* Observation width D for the configured layout: 10 + 11*k_near with the default flags
  * (observation_provider_rt.py:594-925). */

@@ -34,6 +34,8 @@ struct sgb_ctx {
     int32_t num_sms = 0;
     int32_t max_smem_optin = 0;
     int64_t launches = 0;
+    uint64_t noise_epoch = 0;        // counts API calls that can write an observation: part of the noise key
+    int64_t env_offset = 0;          // global index of env 0 (sgb_set_env_offset / the reset entry points)
     size_t smem_configured[6][3] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G> on this device
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // sgb_step_host: chunked copy/compute pipeline
     cudaEvent_t pipe_event[2] = {nullptr, nullptr};
@@ -52,6 +54,23 @@ static int cuda_fail(cudaError_t e, const char* what) {
         cudaError_t _e = (call);                             \
         if (_e != cudaSuccess) return cuda_fail(_e, #call);  \
     } while (0)
+
+// Every entry point that touches the device runs on the CONTEXT's device and leaves the caller's current device as it
+// found it (a host framework such as PyTorch keeps its own notion of the current device).
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) : dev(device) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+};
+#define GUARD(ctx)                                                   \
+    DeviceGuard _guard((ctx)->device);                               \
+    if (_guard.err != cudaSuccess) return cuda_fail(_guard.err, "cudaSetDevice(context device)")
 
 extern "C" const char* sgb_last_error(void) { return g_err; }
 extern "C" int sgb_version(void) { return SGB_VERSION; }
@@ -284,14 +303,21 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
 template <int MODE, int OV>
 int launch_env_group(sgb_ctx* ctx, Params& p, cudaStream_t st, int g) {
     if (g == 4) return launch_env_kernel<4, MODE, OV>(ctx, p, st);
+#ifdef SGB_DEV_ONLY_G4   // development builds (profiles/scripts/variants.sh): compile the headline instantiations only
+    snprintf(g_err, sizeof g_err, "development build: only the four-lanes-per-agent kernels were compiled");
+    return SGB_ERR_UNSUPPORTED;
+#else
     if (g == 2) return launch_env_kernel<2, MODE, OV>(ctx, p, st);
     return launch_env_kernel<1, MODE, OV>(ctx, p, st);
+#endif
 }
 
 int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, const int32_t* env_list,
                const int32_t* env_count, int write_obs, cudaStream_t st, int skip_scan = 0,
-               const sgb_config* cfg_override = nullptr) {
+               const sgb_config* cfg_override = nullptr, int64_t env_first = 0) {
     Params p{};
+    p.noise_epoch = ctx->noise_epoch;
+    p.env_base = ctx->env_offset + env_first;   // global index of buf's env 0 (env_first: chunked launches)
     p.cfg = cfg_override ? *cfg_override : ctx->cfg;
     // spawn-table refresh: the table holds no boundary indices, so a layout with boundary points runs the scans
     p.skip_scan = (p.cfg.obs_flags & SGB_OBS_BOUNDARY_POINTS) ? 0 : skip_scan;
@@ -326,6 +352,13 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
         p.lanelet_max_len = ctx->lanelet_max_len;
     }
     const int g = pick_group(N);
+#ifdef SGB_DEV_ONLY_G4
+    if (p.cfg.use_mtv_distance || p.cfg.obs_flags != 0 || p.cfg.obs_noise_level > 0.0f) {
+        snprintf(g_err, sizeof g_err, "development build: only the default observation layout was compiled");
+        return SGB_ERR_UNSUPPORTED;
+    }
+    return mode == 0 ? launch_env_group<0, 0>(ctx, p, st, g) : launch_env_group<1, 0>(ctx, p, st, g);
+#endif
     // MTV agent distance: its own instantiation (flag-driven writer + SAT distance in phase C1)
     if (p.cfg.use_mtv_distance) return mode == 0 ? launch_env_group<0, 2>(ctx, p, st, g) : launch_env_group<1, 2>(ctx, p, st, g);
     // the default observation layout runs the hard-wired (tuned) writer, any other one the flag-driven writer
@@ -553,7 +586,8 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     Packed pk;
     int rc = pack_map(map, pk);
     if (rc != SGB_OK) return rc;
-    CK(cudaSetDevice(device));
+    DeviceGuard guard(device);       // the caller's current device is restored on return
+    if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
     sgb_ctx* c = new (std::nothrow) sgb_ctx();
     if (!c) return SGB_ERR_ARG;
     c->device = device;
@@ -569,7 +603,7 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
 
 extern "C" int sgb_destroy(sgb_ctx* c) {
     if (!c) return SGB_ERR_ARG;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);    // frees happen on the context's device; the caller's current device is restored
     cudaFree(c->d_blob);
     cudaFree(c->d_yaw);
     cudaFree(c->d_list);
@@ -594,7 +628,7 @@ extern "C" int sgb_set_lanelets(sgb_ctx* c, int32_t n, const float* xy, const in
         if (off[l + 1] <= off[l]) return SGB_ERR_ARG;       // every lanelet has at least one centre point
         max_len = std::max(max_len, off[l + 1] - off[l]);
     }
-    CK(cudaSetDevice(c->device));
+    GUARD(c);
     cudaFree(c->d_lanelet_xy); cudaFree(c->d_lanelet_off); cudaFree(c->d_lanelet_adj);
     c->d_lanelet_xy = nullptr; c->d_lanelet_off = nullptr; c->d_lanelet_adj = nullptr;
     c->n_lanelets = 0;
@@ -609,6 +643,12 @@ extern "C" int sgb_set_lanelets(sgb_ctx* c, int32_t n, const float* xy, const in
     return SGB_OK;
 }
 
+extern "C" int sgb_set_env_offset(sgb_ctx* c, int64_t env_offset) {
+    if (!c || env_offset < 0) return SGB_ERR_ARG;
+    c->env_offset = env_offset;
+    return SGB_OK;
+}
+
 extern "C" int sgb_obs_dim(const sgb_ctx* c) { return c ? obs_dim_of(c->cfg.obs_flags, c->cfg.k_near) : SGB_ERR_ARG; }
 extern "C" int sgb_max_ref_path_points(const sgb_ctx* c) { return c ? c->max_center + kExt + 2 : SGB_ERR_ARG; }
 extern "C" int64_t sgb_launch_count(const sgb_ctx* c) { return c ? c->launches : 0; }
@@ -618,6 +658,8 @@ extern "C" int sgb_step(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf
     if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || c->cfg.k_near > N - 1) return SGB_ERR_ARG;
     int rc = check_buffers(buf, 1);
     if (rc) return rc;
+    GUARD(c);
+    c->noise_epoch++;
     return launch_env(c, B, N, buf, 0, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
 
@@ -627,6 +669,8 @@ extern "C" int sgb_refresh(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* 
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
     if (write_obs && !buf->obs) return SGB_ERR_ARG;
+    GUARD(c);
+    c->noise_epoch++;
     cudaStream_t st = (cudaStream_t)stream;
     if (!env_mask) return launch_env(c, B, N, buf, 1, nullptr, nullptr, write_obs, st);
     rc = ensure_list(c, B);
@@ -643,6 +687,7 @@ extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* bu
     if (!c || B <= 0 || N <= 0 || !path || !point || !speed) return SGB_ERR_ARG;
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
+    GUARD(c);
     PlaceParams p{};
     p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw;
     p.agent_mask = agent_mask; p.path = path; p.point = point; p.speed = speed; p.B = B; p.N = N;
@@ -664,6 +709,9 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     if (rc) return rc;
     if (!buf->step_count || (!all && !explicit_sel && !buf->done)) return SGB_ERR_ARG;
     if (write_obs && !buf->obs) return SGB_ERR_ARG;
+    GUARD(c);
+    c->noise_epoch++;
+    c->env_offset = env_offset;      // the observation noise is keyed by the GLOBAL env index as well
     rc = ensure_list(c, B);
     if (rc) return rc;
     rc = ensure_fresh(c, (int64_t)B * N);
@@ -717,9 +765,13 @@ extern "C" int sgb_reset_masked(sgb_ctx* c, int32_t B, int32_t N, const sgb_buff
 // the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).
 extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
                              float* h_obs, float* h_reward, uint8_t* h_done, void* stream) {
-    if (!c || !h_action || !h_obs || !h_reward || !h_done || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS) return SGB_ERR_ARG;
+    if (!c || !h_action || !h_obs || !h_reward || !h_done || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS ||
+        c->cfg.k_near > N - 1)
+        return SGB_ERR_ARG;
     int rc = check_buffers(buf, 1);
     if (rc) return rc;
+    GUARD(c);
+    c->noise_epoch++;
     cudaStream_t st = (cudaStream_t)stream;
     const int D = obs_dim_of(c->cfg.obs_flags, c->cfg.k_near);
     if (!c->pipe_ready) {
@@ -748,7 +800,7 @@ extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
         if (sub.task_tries) sub.task_tries += e0;
         if (sub.task_success) sub.task_success += e0;
         CK(cudaMemcpyAsync(sub.action, h_action + a0 * 2, (size_t)nb * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
-        rc = launch_env(c, nb, N, &sub, 0, nullptr, nullptr, 1, s);
+        rc = launch_env(c, nb, N, &sub, 0, nullptr, nullptr, 1, s, 0, nullptr, e0);
         if (rc) return rc;
         CK(cudaMemcpyAsync(h_obs + a0 * D, sub.obs, (size_t)nb * N * D * sizeof(float), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_reward + a0, sub.reward, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -766,6 +818,13 @@ extern "C" int sgb_gae(int32_t T, int32_t B, int32_t N, const float* reward, con
                        const uint8_t* done, float gamma, float lmbda, float* adv, float* target, void* stream) {
     if (T <= 0 || B <= 0 || N <= 0 || !reward || !value || !next_value || !done || !adv || !target) return SGB_ERR_ARG;
     const int bn = B * N;
+    // no context here: run on the device that owns the buffers, and leave the caller's current device alone
+    int dev = 0;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, reward) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+    else if (cudaGetDevice(&dev) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaGetDevice");
+    DeviceGuard guard(dev);
+    if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
     gae_kernel<<<(bn + 255) / 256, 256, 0, (cudaStream_t)stream>>>(T, bn, N, reward, value, next_value, done, gamma, lmbda,
                                                                   adv, target);
     CK(cudaGetLastError());

@@ -100,6 +100,9 @@ struct Params {
     const int32_t* lanelet_off;    // [n_lanelets + 1]
     const uint8_t* lanelet_adj;    // [n_lanelets][n_lanelets]
     int32_t n_lanelets, lanelet_max_len;
+    // observation noise key (appended): API-call counter and the global index of this launch's env 0
+    uint64_t noise_epoch;
+    int64_t env_base;
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------------
@@ -237,12 +240,17 @@ SGB_HD __forceinline__ float seg_q(float ax, float ay, float lx, float ly, float
 }
 // same with the projection parameter computed as dot * (1/len2): t differs from the reference's quotient by  @region seg_q_r (boundary)
 // <= 1.5 ulp, i.e. the distance by ~1e-8 m.  Used for the boundaries only (one reciprocal shared by 5 points).
+SGB_HD __forceinline__ float sat01(float x) {
+#ifdef __CUDA_ARCH__
+    return __saturatef(x);            // folds into the producing FMUL as .SAT
+#else
+    return fminf(fmaxf(x, 0.0f), 1.0f);
+#endif
+}
 SGB_HD __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly, float rlen2, float px, float py) {
-    float vx = px - ax, vy = py - ay;
-    float t = (vx * lx + vy * ly) * rlen2;
-    t = fminf(fmaxf(t, 0.0f), 1.0f);
-    float cx = ax + lx * t, cy = ay + ly * t;
-    float ex = cx - px, ey = cy - py;
+    const float vx = px - ax, vy = py - ay;
+    const float t = sat01((vx * lx + vy * ly) * rlen2);
+    const float ex = fmaf(lx, t, -vx), ey = fmaf(ly, t, -vy);   // (a + l t) - p, one FMA per component
     return ex * ex + ey * ey;
 }
 
@@ -523,10 +531,13 @@ SGB_HD __forceinline__ void scan_center(const float2* __restrict__ pts, const fl
     b.init();
     // Every lane takes two segments per iteration (s and s+G): two independent dependency chains in flight.
     // When s+G runs past the chunk the index is clamped, i.e. a segment is evaluated twice — harmless for a min.
+    // (fixed trip count kChunk / 2G — ONE pass with four lanes per agent; indices past a short last chunk are clamped)
+    constexpr int NIT = kChunk / (2 * G);
     auto chunk = [&](int c) {
-        const int s1 = min(c * kChunk + kChunk, nseg);
-        for (int s = c * kChunk + lane; s < s1; s += 2 * G) {
-            const int s2 = min(s + G, s1 - 1);
+        const int s_last = min(c * kChunk + kChunk, nseg) - 1;
+#pragma unroll 1
+        for (int it = 0; it < NIT; it++) {
+            const int s = min(c * kChunk + lane + it * 2 * G, s_last), s2 = min(s + G, s_last);
             const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
             const float lx = e.x - a.x, ly = e.y - a.y, lx2 = e2.x - a2.x, ly2 = e2.y - a2.y;
             const float q1 = seg_q(a.x, a.y, lx, ly, madd2(lx, lx, ly, ly), px, py);
@@ -594,10 +605,12 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
             const int c = SGB_FFS(m) - 1;
             m &= m - 1;
             const bool do_x = (mx >> c) & 1u, do_d = (md >> c) & 1u;
-            const int s1 = min(c * kChunk + kChunk, nseg);
-            for (int s = c * kChunk + lane; s < s1; s += 2 * G) {
-                // two segments per lane-iteration (s, s+G): independent chains; a clamped duplicate is harmless
-                const int s2 = min(s + G, s1 - 1);
+            const int s_last = min(c * kChunk + kChunk, nseg) - 1;
+#pragma unroll 1
+            for (int it = 0; it < kChunk / (2 * G); it++) {
+                // two segments per lane-iteration (s, s+G): independent chains; a clamped duplicate is harmless (and
+                // the trip count is fixed: a single pass with four lanes per agent)
+                const int s = min(c * kChunk + lane + it * 2 * G, s_last), s2 = min(s + G, s_last);
                 const float2 a = pts[s], e = pts[s + 1], a2 = pts[s2], e2 = pts[s2 + 1];
                 const float lx = e.x - a.x, ly = e.y - a.y, len2 = lx * lx + ly * ly;
                 const float lx2 = e2.x - a2.x, ly2 = e2.y - a2.y, len2b = lx2 * lx2 + ly2 * ly2;
@@ -1325,14 +1338,16 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                         if (p.buf.dbg && kk < 2) p.buf.dbg[g * 16 + 13 + kk] = (float)bj;
                     }
                     if (cfg.obs_noise_level > 0.0f) {
-                        // observation_provider_rt.py:611-617: obs + level * U[0,1) on every element.  The reference draws
-                        // from torch's global generator; here the draw is a counter-based hash of the agent's own
-                        // post-step state (position, heading, speed bits), its index and the column — i.i.d.-looking,
-                        // reproducible, and independent of how envs are sharded (distribution-equivalent, like resets).
+                        // observation_provider_rt.py:611-617: obs + level * U[0,1) on every element, fresh draws on every
+                        // call (torch.rand_like).  The reference draws from torch's global generator; here the draw is a
+                        // counter-based hash of (seed, API-call counter, GLOBAL env index, agent, column): independent
+                        // between envs, agents, columns and steps — also for agents whose state does not change, and for
+                        // envs started from the same initial state — reproducible, and independent of how envs are
+                        // sharded over GPUs (distribution-equivalent, like the reset draws).
                         __syncwarp(((G >= 32) ? 0xffffffffu : ((1u << G) - 1u)) << (ln - lane));   // the row is complete
-                        uint64_t key = ((uint64_t)__float_as_uint(pix) << 32) | __float_as_uint(piy);
-                        key = mix64(key) ^ (((uint64_t)__float_as_uint(psi_i) << 32) | __float_as_uint(ts.vabs[sl]));
-                        key = mix64(key ^ ((uint64_t)i << 48) ^ cfg.obs_noise_seed);
+                        uint64_t key = mix64((uint64_t)cfg.obs_noise_seed ^ mix64(p.noise_epoch));
+                        key = mix64(key ^ (uint64_t)(p.env_base + ts.env[sl]));
+                        key = mix64(key ^ ((uint64_t)i << 48));
                         for (int d = lane; d < D; d += G) {
                             const float u = (float)(mix64(key + (uint64_t)d) >> 40) * (1.0f / 16777216.0f);
                             o[d] += cfg.obs_noise_level * u;

@@ -49,6 +49,7 @@ class RoadTrafficEnv:
             with torch.cuda.device(idx):
                 _lib.check(self.L.sgb_set_lanelets(self._ctx, len(m.lanelet_off) - 1, m.lanelet_xy.ctypes.data,
                                                    m.lanelet_off.ctypes.data, m.lanelet_adj.ctypes.data), "sgb_set_lanelets")
+        _lib.check(self.L.sgb_set_env_offset(self._ctx, self.env_offset), "sgb_set_env_offset")
         self.D = self.L.sgb_obs_dim(self._ctx)
         B, N, dev = self.B, self.N, self.device
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)  # noqa: E731
@@ -110,12 +111,14 @@ class RoadTrafficEnv:
 
     # ------------------------------------------------------------------ the path
     def step(self, action: torch.Tensor = None, auto_reset: bool = False):
-        """One fused-kernel environment step.  Returns views (obs [B,N,D], reward [B,N], done [B] uint8)."""
+        """One fused-kernel environment step.  Returns views (obs [B,N,D], reward [B,N], done [B] uint8).
+        auto_reset: done envs are reset right away and `obs` then holds their post-reset observation (what the policy
+        acts on next), reward / done stay the step's."""
         if action is not None:
             self.action.copy_(action.reshape(self.B, self.N, 2))
         _lib.check(self.L.sgb_step(self._ctx, self.B, self.N, C.byref(self._buf), self._stream()), "sgb_step")
         if auto_reset:
-            self.reset_done(write_obs=False)
+            self.reset_done(write_obs=True)
         return self.obs, self.reward, self.done
 
     def reset_done(self, write_obs: bool = True):

@@ -21,7 +21,7 @@ EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points"
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
            "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance", "sgb_debug_pack_map",
            "sgb_set_lanelets", "sgb_debug_current_lanelet", "sgb_debug_pack_map_blob", "sgb_debug_scan_batch", "sgb_debug_scan_counters",
-           "sgb_debug_helper", "sgb_debug_short_term", "sgb_debug_pair_batch"]
+           "sgb_debug_helper", "sgb_debug_short_term", "sgb_debug_pair_batch", "sgb_set_env_offset"]
 
 
 class SgbError(RuntimeError):
@@ -82,6 +82,7 @@ def load_library():
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     L.sgb_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(MapDesc), C.POINTER(Config)]
     L.sgb_destroy.argtypes = [vp]
+    L.sgb_set_env_offset.argtypes = [vp, i64]
     L.sgb_obs_dim.argtypes = [vp]
     L.sgb_max_ref_path_points.argtypes = [vp]
     L.sgb_step.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp]

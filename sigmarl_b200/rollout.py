@@ -59,10 +59,12 @@ def collect(env, policy: Callable[[torch.Tensor], torch.Tensor], buf: RolloutBuf
     TorchRL semantics kept (SURVEY.md assumption A5): the stored next-state value of a done env is the value of
     its step-time observation (before the reset); the observation the policy sees next is the post-reset one.
 
-    in_place: the env's outputs are bound to the rollout buffer (``RoadTrafficEnv.bind``): step t reads its action
-    from ``buf.action[t]`` and writes ``buf.reward[t]``, ``buf.done[t]`` and — as the next step's input —
-    ``buf.obs[t + 1]`` directly; no per-step stacking or copies (the reference stacks TensorDicts,
-    ``helper_training.py:745-770``).  in_place=False keeps the env's own buffers and copies (same results)."""
+    in_place: the env's outputs are bound to the rollout buffer (``RoadTrafficEnv.bind``): step t writes
+    ``buf.reward[t]``, ``buf.done[t]`` and — as the next step's input — ``buf.obs[t + 1]`` directly; no per-step
+    stacking or copies (the reference stacks TensorDicts, ``helper_training.py:745-770``).  in_place=False keeps the
+    env's own buffers and copies (same results).  In both modes ``buf.action[t]`` holds the policy's RAW output: the
+    step kernel clamps its own copy in place (``helper_training.py:807-818`` clamps ``agent.action.u``, not the
+    collector's tensordict), so PPO evaluates log-probabilities on the action that was sampled."""
     T = buf.T
     if not in_place:
         obs = env.obs
@@ -80,7 +82,7 @@ def collect(env, policy: Callable[[torch.Tensor], torch.Tensor], buf: RolloutBuf
             env.reset_done(write_obs=True)   # fresh observation for reset envs, step-time observation elsewhere
             obs = env.obs
         return buf
-    own = dict(obs=env.obs, reward=env.reward, done=env.done, action=env.action)
+    own = dict(obs=env.obs, reward=env.reward, done=env.done)
     buf.obs[0].copy_(env.obs)
     try:
         for t in range(T):
@@ -88,16 +90,14 @@ def collect(env, policy: Callable[[torch.Tensor], torch.Tensor], buf: RolloutBuf
             if value_fn is not None:
                 buf.value[t].copy_(value_fn(obs))
             buf.action[t].copy_(policy(obs))
-            env.bind(action=buf.action[t], reward=buf.reward[t], done=buf.done[t],
-                     obs=buf.obs[t + 1] if t + 1 < T else own["obs"])
-            env.step(None)
+            env.bind(reward=buf.reward[t], done=buf.done[t], obs=buf.obs[t + 1] if t + 1 < T else own["obs"])
+            env.step(buf.action[t])        # copied into the env's own action buffer, which the kernel clamps
             if value_fn is not None:
                 buf.next_value[t].copy_(value_fn(env.obs))
             env.reset_done(write_obs=True)
     finally:
         own["reward"].copy_(env.reward)
         own["done"].copy_(env.done)
-        own["action"].copy_(env.action)
         env.bind(**own)
     return buf
 

@@ -60,7 +60,8 @@ def test_in_place_collect_equals_copying_collect():
         buf = RolloutBuffer(12, env.B, env.N, env.D, env.device)
         g = torch.Generator(device="cuda").manual_seed(3)
         ur = torch.tensor([1.0, 31 * np.pi / 180], device="cuda")
-        policy = lambda obs: (torch.rand(env.B, env.N, 2, device="cuda", generator=g) * 2 - 1) * ur  # noqa: E731
+        # 1.5 x the action range: the kernel clamps its own copy, the buffer must keep the RAW policy output
+        policy = lambda obs: (torch.rand(env.B, env.N, 2, device="cuda", generator=g) * 2 - 1) * ur * 1.5  # noqa: E731
         value = lambda obs: obs[..., 0] - obs[..., 7]  # noqa: E731
         collect(env, policy, buf, value_fn=value, in_place=in_place)
         bufs.append((buf, env.obs.clone(), env.reward.clone(), env.done.clone(), env.pose.clone()))
@@ -70,3 +71,5 @@ def test_in_place_collect_equals_copying_collect():
     for x, y in zip(a[1:], b[1:]):
         assert torch.equal(x, y)
     assert a[0].done.sum() > 0
+    assert float(a[0].action[..., 0].abs().max()) > 1.2        # raw (unclamped) actions were stored ...
+    assert float(env.action[..., 0].abs().max()) <= 1.0        # ... while the env stepped on the clamped copy
