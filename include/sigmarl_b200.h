@@ -295,7 +295,9 @@ int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity
 /* Host run of the kernels' own polyline scans (scan_center / scan_boundary with one lane per agent) for n independent
  * poses on a freshly packed blob: the pruned search (exhaustive = 0) must give exactly what the exhaustive one
  * (exhaustive = 1) gives.  out[16 * i]: d_ref, idx_ref, then per side (left at 2, right at 9) d_cg, 4 vertex
- * distances, crossing flag.  hint_idx is the carried closest index (any value is valid).  The host compiler does not
+ * distances, crossing flag.  exhaustive | 2: as the product kernels run without a debug buffer — all four vertex slots
+ * hold the minimum over the vertices, the only vertex quantity anything downstream consumes.  hint_idx is the carried
+ * closest index (any value is valid).  The host compiler does not
  * contract a*b+c into FMAs, the device does: the certificates must (and do) hold under either rounding. */
 int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const int32_t* path, const float* x, const float* y,
                          const float* psi, const int32_t* hint_idx, float half_length, float half_width,

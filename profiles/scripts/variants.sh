@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/variants.log
 for so in build/variants/*.so; do
-  SGB_LIBRARY=$PWD/$so python profiles/kbench.py 65536 30 >> gpurun_out/variants.log 2>&1
+  SGB_LIBRARY=$PWD/$so timeout 120 python profiles/kbench.py 65536 30 >> gpurun_out/variants.log 2>&1
   if [ "$1" = "check" ] && [ "$(basename $so)" != "base.so" ]; then
     SGB_LIBRARY=$PWD/$so timeout 300 python profiles/exact_check.py 32768 12 >> gpurun_out/variants.log 2>&1
   fi

@@ -116,7 +116,12 @@ void add_boxes(std::vector<float>& boxes, const float* xy, int n_pts) {
             x0 = std::min(x0, xy[2 * k]); x1 = std::max(x1, xy[2 * k]);
             y0 = std::min(y0, xy[2 * k + 1]); y1 = std::max(y1, xy[2 * k + 1]);
         }
-        boxes.insert(boxes.end(), {x0, y0, x1, y1});
+        // stored as centre + half extents; the half extents are rounded UP from the exact distances between the
+        // (rounded) centre and the extremes, so the stored box contains every point of the chunk
+        const float cx = 0.5f * (x0 + x1), cy = 0.5f * (y0 + y1);
+        auto up = [](double v) { float f = (float)v; return (double)f < v ? std::nextafterf(f, INFINITY) : f; };
+        boxes.insert(boxes.end(), {cx, cy, up(std::max((double)cx - x0, (double)x1 - cx)),
+                                   up(std::max((double)cy - y0, (double)y1 - cy))});
     }
 }
 
@@ -332,6 +337,8 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.write_obs = write_obs;
     p.rect_radius = std::sqrt(ctx->cfg.half_length * ctx->cfg.half_length + ctx->cfg.half_width * ctx->cfg.half_width) * 1.0001f;
     p.near2 = (p.rect_radius + kFarMargin) * (p.rect_radius + kFarMargin);
+    p.band_l = ctx->cfg.half_length + 1e-3f;
+    p.band_w = ctx->cfg.half_width + 1e-3f;
     p.r_pos = 1.0f / ctx->cfg.norm_pos;
     p.r_v = 1.0f / ctx->cfg.norm_v;
     p.r_dist = 1.0f / ctx->cfg.norm_dist;
@@ -470,6 +477,10 @@ extern "C" int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const in
     const __half2* cones = reinterpret_cast<const __half2*>(blob + h->cone_off);
     const float rect_radius = std::sqrt(half_length * half_length + half_width * half_width) * 1.0001f;   // launch_env
     const float near2 = (rect_radius + kFarMargin) * (rect_radius + kFarMargin);
+    // bit 1 of `exhaustive`: run the scans the way the product kernels do when no debug buffer is bound — only the
+    // minimum over the four vertices is exact then (all four outputs hold it), which allows a tighter chunk vote
+    const bool want_dv = (exhaustive & 2) == 0;
+    exhaustive &= 1;
     for (int i = 0; i < n; i++) {
         if (path[i] < 0 || path[i] >= h->n_paths) return SGB_ERR_ARG;
         const PathRec* prp = paths + path[i];
@@ -490,7 +501,8 @@ extern "C" int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const in
             bool hit;
             sgb::scan_boundary<1>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
                                   cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, exhaustive != 0, px, py,
-                                  &cy, &sy, &psim, rvx, rvy, rect_radius, near2, half_length, half_width, true, 0, dc, dvv, hit);
+                                  &cy, &sy, &psim, rvx, rvy, rect_radius, near2, half_length, half_width, half_length + 1e-3f,
+                                  half_width + 1e-3f, want_dv, 0, dc, dvv, hit);
             float* q = o + (side ? 9 : 2);
             q[0] = dc;
             for (int v = 0; v < 4; v++) q[1 + v] = dvv[v];

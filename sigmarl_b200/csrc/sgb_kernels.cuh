@@ -103,6 +103,7 @@ struct Params {
     // observation noise key (appended): API-call counter and the global index of this launch's env 0
     uint64_t noise_epoch;
     int64_t env_base;
+    float band_l, band_w;      // half_length / half_width + 1 mm: the edge-line bands of the far-candidate vote
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------------
@@ -265,12 +266,15 @@ SGB_HD __forceinline__ float rcp_fast(float x) {
 #endif
 }
 
-// distance from a point to an axis-aligned box (lower bound for every polyline point inside it)
-SGB_HD __forceinline__ float box_lb2(float4 bx, float px, float py) {
-    float dx = fmaxf(fmaxf(bx.x - px, px - bx.z), 0.0f);
-    float dy = fmaxf(fmaxf(bx.y - py, py - bx.w), 0.0f);
+// squared distance from a point to an axis-aligned box (lower bound for every polyline point inside it).  Boxes are
+// stored as (centre x, centre y, half extent x, half extent y) — half extents rounded up so that the box still holds
+// every point after the centre's rounding (pack_map) — so the test is |p - c| - h per axis, and the crossing vote
+// reuses p - c.
+SGB_HD __forceinline__ float box_lb2_rel(float4 bx, float rx, float ry) {   // (rx, ry) = box centre - point
+    const float dx = fmaxf(fabsf(rx) - bx.z, 0.0f), dy = fmaxf(fabsf(ry) - bx.w, 0.0f);
     return dx * dx + dy * dy;
 }
+SGB_HD __forceinline__ float box_lb2(float4 bx, float px, float py) { return box_lb2_rel(bx, bx.x - px, bx.y - py); }
 SGB_HD __forceinline__ float box_lb(float4 bx, float px, float py) { return sqrtf(box_lb2(bx, px, py)); }
 
 // The agent's rectangle as interX sees it (helper_scenario.py:1148-1229): closed 5-vertex polyline.  @region Rect.finish
@@ -585,7 +589,8 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
                                               const __half2* __restrict__ cones, int n_b, int hint_seg, bool exhaustive,
                                               float px, float py, const float* cs_s, const float* sn_s,
                                               const float* psi_m_s, const float* rvx, const float* rvy, float rect_radius,
-                                              float near2, float half_l, float half_w, bool want_dv, int lane, float& d_cg,
+                                              float near2, float half_l, float half_w, float band_l, float band_w, bool want_dv, int lane,
+                                              float& d_cg,
                                               float dv[4], bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
@@ -667,10 +672,23 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
         if (pass) break;
         // Vote.  Group-wide bound after the hint chunk (lanes that got no segment hold +inf): every point is within
         // rect_radius of the centre, so a chunk can matter for some point only if lb(centre) <= max best + radius.
-        float gq = group_min<G>(bq[0].q);
+        float thr;
+        if (want_dv) {   // debug buffer: every vertex' own minimum must be exact
+            float gq = group_min<G>(bq[0].q);
 #pragma unroll
-        for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
-        float thr = fmaxf(sqrtf(gq) + rect_radius + kDistMargin, near_r + kDistMargin);   // near chunks are distance chunks
+            for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
+            thr = sqrtf(gq) + rect_radius;
+        } else {
+            // Consumers read the centre's minimum and the minimum OVER the four vertices (carry, observation, reward,
+            // info), never a single vertex' distance.  A chunk can lower the vertex minimum m4 only if some vertex is
+            // within m4 of it, i.e. lb(centre) <= m4 + radius; it can lower the centre's minimum only if lb(centre) is
+            // within that.  Bounding with the BEST vertex instead of the worst one cuts the chunk evaluations per scan
+            // from 2.08 to 1.57, and what a warp pays (maximum over its 8 agents) by a quarter (tests/tools/chunk_sim.py).
+            const float q0 = group_min<G>(bq[0].q);
+            const float q4 = group_min<G>(fminf(fminf(bq[1].q, bq[2].q), fminf(bq[3].q, bq[4].q)));
+            thr = fmaxf(sqrtf(q4) + rect_radius, sqrtf(q0));
+        }
+        thr = fmaxf(thr + kDistMargin, near_r + kDistMargin);   // near chunks are distance chunks
         thr = thr * thr;
         md = 0; mx = 0;
         const float pi_f = 3.14159274f, half_pi = 1.57079637f;
@@ -681,7 +699,9 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
         for (int c = lane; c < nch; c += G) {   // branch-free; c0 is masked out below
             const float4 bx = boxes[c];
             const float2 cone = __half22float2(cones[c]);
-            const float lb2 = box_lb2(bx, px, py);
+            const float bcx = bx.x - px, bcy = bx.y - py;   // box centre, relative
+            const float hx = bx.z, hy = bx.w;
+            const float lb2 = box_lb2_rel(bx, bcx, bcy);
             const uint32_t bit = 1u << c;
             md |= (lb2 > thr) ? 0u : bit;
             // Crossing candidates: near chunks, and far chunks on which interX could fire through sign noise.  That
@@ -692,10 +712,8 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
             // between / around the two lines (band widened by 1 mm >> the 1e-7 m error of vertices and cos/sin).
             float da = fabsf(psi_m - cone.x);
             da = fminf(da, pi_f - da);                       // angle between heading and cone axis, mod pi
-            const float bcx = 0.5f * (bx.x + bx.z) - px, bcy = 0.5f * (bx.y + bx.w) - py;   // box centre, relative
-            const float hx = 0.5f * (bx.z - bx.x), hy = 0.5f * (bx.w - bx.y);
-            const bool side_band = fabsf(cs * bcy - sn * bcx) <= hx * asn + hy * acs + (half_w + 1e-3f);
-            const bool face_band = fabsf(cs * bcx + sn * bcy) <= hx * acs + hy * asn + (half_l + 1e-3f);
+            const bool side_band = fabsf(cs * bcy - sn * bcx) <= hx * asn + (hy * acs + band_w);
+            const bool face_band = fabsf(cs * bcx + sn * bcy) <= hx * acs + (hy * asn + band_l);
             const bool far_cand = ((da <= cone.y) & side_band) | (((half_pi - da) <= cone.y) & face_band);
             mx |= (!(lb2 > near2) | far_cand) ? bit : 0u;
         }
@@ -1017,7 +1035,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 scan_boundary<G>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
                                  cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, ex, px, py,
                                  ts.cs + sl, ts.sn + sl, ts.psim + sl, rvx, rvy, rect_radius, p.near2, cfg.half_length,
-                                 cfg.half_width, p.buf.dbg != nullptr, lane, dc, dvv, hit);
+                                 cfg.half_width, p.band_l, p.band_w, p.buf.dbg != nullptr, lane, dc, dvv, hit);
                 if (hit) fl = (int)SGB_FLAG_COLLIDE_LANE;
                 if (writer) {
                     dc = dc - cfg.half_width;                                   // world_state_rt.py:608-610
@@ -1161,6 +1179,40 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             const int k_near = cfg.k_near;
             int nb_j[2] = {0, 0};          // the first two neighbours stay in registers, the rest is re-derived
             float nb_d[2] = {0.0f, 0.0f};
+            if (G == 4) {
+                // Four lanes per agent, N <= 8: lane l owns the candidates j = l and l + 4.  A candidate is the 64-bit
+                // key (distance bits, j): distances are >= 0 (MTV: order-preserving bit flip), so the unsigned order of
+                // the keys IS the lexicographic (d, j) order of torch.topk's "smallest first, lower index on ties".
+                // Two group minima (the second with the first winner struck out) = 4 shuffle rounds in all.
+                uint64_t key[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int j = lane + 4 * h;
+                    key[h] = ~0ull;
+                    if (slot_ok && j < N) {
+                        uint32_t b = __float_as_uint(ts.dij[sl * N + j]);
+                        if (MTV) b ^= (b >> 31) ? 0xffffffffu : 0x80000000u;
+                        key[h] = ((uint64_t)b << 32) | (uint32_t)j;
+                    }
+                }
+                uint64_t first = ~0ull;
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++) {
+                    uint64_t b = key[0] < key[1] ? key[0] : key[1];
+#pragma unroll
+                    for (int m = 1; m < 4; m <<= 1) {
+                        const uint64_t o = __shfl_xor_sync(0xffffffffu, b, m);
+                        b = o < b ? o : b;
+                    }
+                    int bj = (int)(uint32_t)b;
+                    if (b == ~0ull) bj = 0;                                   // inactive slot
+                    const float bd = ts.dij[(slot_ok ? sl : slot0) * N + bj];
+                    if (kk == 0) { nb_j[0] = bj; nb_d[0] = bd; first = b; } else { nb_j[1] = bj; nb_d[1] = bd; }
+                    // strike the winner out (j is unique, the low word identifies it)
+                    if ((uint32_t)key[0] == (uint32_t)first && first != ~0ull) key[0] = ~0ull;
+                    if ((uint32_t)key[1] == (uint32_t)first && first != ~0ull) key[1] = ~0ull;
+                }
+            } else {
             uint32_t used = 0;
             // The lanes of the group split j (lane, lane + G, ...), then a lexicographic (d, j) minimum over the group:
             // same result as the ascending scan with strict '<' (first minimal index).  All lanes shuffle.
@@ -1181,6 +1233,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 if (bj == 0x7fffffff) bj = 0;   // inactive slot
                 used |= 1u << bj;
                 if (kk == 0) { nb_j[0] = bj; nb_d[0] = bd; } else { nb_j[1] = bj; nb_d[1] = bd; }   // no dynamic index
+            }
             }
             if (slot_ok) {
                 const size_t g = (size_t)ts.env[sl] * N + i;
@@ -1386,8 +1439,8 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                         o[8] = o_mL * r_dist;
                         o[9] = o_mR * r_dist;
                     }
-                    if (lane == 1 % G) {
-                        for (int kk = 0; kk < k_near; kk++) {
+                    {   // the neighbours' velocity / distance entries, one neighbour per lane
+                        for (int kk = lane; kk < k_near; kk += G) {
                             int bj;
                             float bd;
                             if (kk == 0) { bj = nb_j[0]; bd = nb_d[0]; }

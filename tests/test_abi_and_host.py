@@ -317,7 +317,10 @@ def test_packed_blob_certificates_hold_on_every_map():
                 for c, s0 in enumerate(range(0, cnt - 1, K)):
                     s1 = min(s0 + K, cnt - 1)
                     seg = want[s0:s1 + 1].astype(np.float64)
-                    x0, y0, x1, y1 = boxes[box0 + c]
+                    bcx, bcy, bhx, bhy = (float(v) for v in boxes[box0 + c])      # centre + (padded) half extents
+                    x0, y0, x1, y1 = bcx - bhx, bcy - bhy, bcx + bhx, bcy + bhy
+                    tol = 4e-7 * max(1.0, float(np.abs(seg).max()))               # a few fp32 ulps of a coordinate
+                    assert bhx - 0.5 * np.ptp(seg[:, 0]) < tol and bhy - 0.5 * np.ptp(seg[:, 1]) < tol   # and tight
                     assert (seg[:, 0] >= x0).all() and (seg[:, 0] <= x1).all() and (seg[:, 1] >= y0).all() and (seg[:, 1] <= y1).all()
                     if cone0 is None:
                         continue
@@ -378,6 +381,13 @@ def test_pruned_scans_equal_exhaustive_scans_on_the_host_for_every_map(oracle_mo
         path, pos, psi, hint = _scan_poses(m, 1500, rng)
         pruned, full = (_scan_batch(L, m, path, pos, psi, hint, ex) for ex in (0, 1))
         assert np.array_equal(pruned.view(np.uint32), full.view(np.uint32)), st
+        # the product mode (no debug buffer: only the minimum over the four vertices is kept exact, which lets the
+        # chunk vote use the best vertex instead of the worst): everything downstream consumes equals the exhaustive scan
+        lean = _scan_batch(L, m, path, pos, psi, hint, 2)
+        want = full.copy()
+        for o in (3, 10):
+            want[:, o:o + 4] = full[:, o:o + 4].min(1, keepdims=True)
+        assert np.array_equal(lean.view(np.uint32), want.view(np.uint32)), st
         n_hits += int(full[:, 7].sum() + full[:, 14].sum())
         pm = O.PaddedMap(st)
         if pm.n_paths != m.n_paths:

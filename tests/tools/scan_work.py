@@ -31,7 +31,7 @@ for t in range(25):
     obs,rew,done,_=w.step(act,n_threads=8)
     path=w.path_id.copy().astype(np.int32).reshape(-1); pos=w.pos.copy().reshape(-1,2); psi=w.rot.copy().astype(np.float32).reshape(-1)
     xs=np.ascontiguousarray(pos[:,0]); ys=np.ascontiguousarray(pos[:,1]); out=np.zeros((B*N,16),np.float32)
-    rc=L.sgb_debug_scan_batch(C.byref(d),B*N,path.ctypes.data,xs.ctypes.data,ys.ctypes.data,psi.ctypes.data,hint.ctypes.data,C.c_float(0.11),C.c_float(0.0535),0,out.ctypes.data)
+    rc=L.sgb_debug_scan_batch(C.byref(d),B*N,path.ctypes.data,xs.ctypes.data,ys.ctypes.data,psi.ctypes.data,hint.ctypes.data,C.c_float(0.11),C.c_float(0.0535),2,out.ctypes.data)
     assert rc==0
     assert np.array_equal(out[:,1].astype(np.int32), w.idx_ref.reshape(-1)), "idx mismatch vs oracle"
     tot+=B*N
