@@ -89,7 +89,10 @@ class EnvConfig:
     is_observe_distance_to_agents: bool = True
     is_observe_distance_to_center_line: bool = True
     is_observe_distance_to_boundaries: bool = True # False: 5 + 5 boundary points around the closest ones
-    is_obs_noise: bool = False                     # obs += obs_noise_level * U[0,1) (device generator)
+    # obs += obs_noise_level * U[0,1) (device generator).  NB the reference's own defaults are ON — Parameters
+    # (helper_common.py:76) and make_world(**kwargs) (road_traffic.py:336) — and the drop-in facade applies them
+    # (ScenarioRoadTrafficB200.make_world / EnvConfig.from_parameters); this raw engine config defaults to noise-free.
+    is_obs_noise: bool = False
     obs_noise_level: Optional[float] = None        # None -> 0.05 (params, helper_common.py:77) / 0.2 * width (kwargs, :337-339)
     obs_noise_seed: int = 0
     # agent distance (road_traffic.py:611-614): False = centre to centre, True = MTV-based (SAT) distance between the

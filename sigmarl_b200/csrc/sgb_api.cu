@@ -414,15 +414,18 @@ int build_spawn_table(sgb_ctx* c, const Packed& pk) {
     int rc = launch_env(c, M, 1, &b, 1, nullptr, nullptr, 0, nullptr, 0, &one);
     if (rc == SGB_OK && cudaDeviceSynchronize() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "spawn table kernels");
     if (rc != SGB_OK) { cleanup(); return rc; }
-    std::vector<float> dbg((size_t)M * 16), tab((size_t)M * 8, 0.0f);
+    std::vector<float> dbg((size_t)M * 16), car((size_t)M * 4), tab((size_t)M * 8, 0.0f);
     cudaMemcpy(dbg.data(), b.dbg, sizeof(float) * dbg.size(), cudaMemcpyDeviceToHost);
+    cudaMemcpy(car.data(), b.carry, sizeof(float) * car.size(), cudaMemcpyDeviceToHost);
     for (int r = 0; r < M; r++) {
         const float* d = &dbg[(size_t)r * 16];
         float* t = &tab[(size_t)r * 8];
         t[0] = d[0]; t[1] = d[1];                // d_ref, idx_ref (int bits)
         t[2] = d[2]; t[3] = d[7];                // dLc, dRc (already minus half width)
-        t[4] = std::min(std::min(d[3], d[4]), std::min(d[5], d[6]));
-        t[5] = std::min(std::min(d[8], d[9]), std::min(d[10], d[11]));
+        // minimum over the vertices: what the refresh wrote into the carry of agent 0 (the very value a generic
+        // refresh of this pose computes — one root of the minimal squared distance)
+        t[4] = car[(size_t)r * 4 + 1];
+        t[5] = car[(size_t)r * 4 + 2];
     }
     cleanup();
     CK(cudaMalloc(&c->d_spawn, sizeof(float) * tab.size()));
@@ -497,12 +500,12 @@ extern "C" int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const in
         o[0] = d_ref; o[1] = (float)idx_ref;
         const int h2 = idx_ref - 1;
         for (int side = 0; side < 2; side++) {
-            float dc, dvv[4];
+            float dc, dvv[4], m4;
             bool hit;
             sgb::scan_boundary<1>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
                                   cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, exhaustive != 0, px, py,
                                   &cy, &sy, &psim, rvx, rvy, rect_radius, near2, half_length, half_width, half_length + 1e-3f,
-                                  half_width + 1e-3f, want_dv, 0, dc, dvv, hit);
+                                  half_width + 1e-3f, want_dv, 0, dc, dvv, m4, hit);
             float* q = o + (side ? 9 : 2);
             q[0] = dc;
             for (int v = 0; v < 4; v++) q[1 + v] = dvv[v];

@@ -266,6 +266,18 @@ SGB_HD __forceinline__ float rcp_fast(float x) {
 #endif
 }
 
+// sqrt with MUFU.SQRT (max relative error 2^-23): pruning bounds (which carry a 1e-4 m margin) and the boundary
+// distances (continuous outputs, 1e-5 tolerance) — never a value that feeds an argmin or a predicate
+SGB_HD __forceinline__ float sqrt_fast(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
 // squared distance from a point to an axis-aligned box (lower bound for every polyline point inside it).  Boxes are
 // stored as (centre x, centre y, half extent x, half extent y) — half extents rounded up so that the box still holds
 // every point after the centre's rounding (pack_map) — so the test is |p - c| - h per axis, and the crossing vote
@@ -529,8 +541,8 @@ SGB_HD __forceinline__ void scan_center(const float2* __restrict__ pts, const fl
                                             int& idx_out) {
     const int nseg = n_c - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
-    int c0 = hint_seg / kChunk;
-    c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
+    static_assert(kChunk == 8, "hint chunk: shift by log2(kChunk)");
+    const int c0 = max(0, min(hint_seg >> 3, nch - 1));
     Best b;
     b.init();
     // Every lane takes two segments per iteration (s and s+G): two independent dependency chains in flight.
@@ -555,7 +567,11 @@ SGB_HD __forceinline__ void scan_center(const float2* __restrict__ pts, const fl
     float thr = group_min<G>(b.d) + kDistMargin;
     thr = thr * thr;
     uint32_t m = 0;
-    for (int c = lane; c < nch; c += G) m |= (box_lb2(boxes[c], px, py) > thr) ? 0u : (1u << c);
+    for (int c = lane; c < nch; c += 2 * G) {   // two boxes per lane and iteration
+        const int c2 = c + G;
+        m |= (box_lb2(boxes[c], px, py) > thr) ? 0u : (1u << c);
+        m |= (c2 >= nch || box_lb2(boxes[c2 < nch ? c2 : c], px, py) > thr) ? 0u : (1u << (c2 & 31));
+    }
     SGB_COUNT(2, (nch + G - 1) / G);
     SGB_COUNT(4, 1);
     if (exhaustive) m = 0xffffffffu;
@@ -591,11 +607,11 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
                                               const float* psi_m_s, const float* rvx, const float* rvy, float rect_radius,
                                               float near2, float half_l, float half_w, float band_l, float band_w, bool want_dv, int lane,
                                               float& d_cg,
-                                              float dv[4], bool& hit_out) {
+                                              float dv[4], float& m4_out, bool& hit_out) {
     const int nseg = n_b - 1;
     const int nch = (nseg + kChunk - 1) / kChunk;
-    int c0 = hint_seg / kChunk;
-    c0 = c0 < 0 ? 0 : (c0 >= nch ? nch - 1 : c0);
+    static_assert(kChunk == 8, "hint chunk: shift by log2(kChunk)");
+    const int c0 = max(0, min(hint_seg >> 3, nch - 1));
     const float near_r = rect_radius + kFarMargin;   // segments farther than this from the centre cannot touch the rectangle
     BestQ bq[5]; // 0 = centre, 1..4 = vertices
 #pragma unroll
@@ -677,7 +693,7 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
             float gq = group_min<G>(bq[0].q);
 #pragma unroll
             for (int v = 1; v < 5; v++) gq = fmaxf(gq, group_min<G>(bq[v].q));
-            thr = sqrtf(gq) + rect_radius;
+            thr = sqrt_fast(gq) + rect_radius;
         } else {
             // Consumers read the centre's minimum and the minimum OVER the four vertices (carry, observation, reward,
             // info), never a single vertex' distance.  A chunk can lower the vertex minimum m4 only if some vertex is
@@ -686,7 +702,7 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
             // from 2.08 to 1.57, and what a warp pays (maximum over its 8 agents) by a quarter (tests/tools/chunk_sim.py).
             const float q0 = group_min<G>(bq[0].q);
             const float q4 = group_min<G>(fminf(fminf(bq[1].q, bq[2].q), fminf(bq[3].q, bq[4].q)));
-            thr = fmaxf(sqrtf(q4) + rect_radius, sqrtf(q0));
+            thr = fmaxf(sqrt_fast(q4) + rect_radius, sqrt_fast(q0));
         }
         thr = fmaxf(thr + kDistMargin, near_r + kDistMargin);   // near chunks are distance chunks
         thr = thr * thr;
@@ -696,26 +712,31 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
         const float acs = fabsf(cs), asn = fabsf(sn);
         SGB_COUNT(2, (nch + G - 1) / G);
         SGB_COUNT(5, 1);
-        for (int c = lane; c < nch; c += G) {   // branch-free; c0 is masked out below
+        // Crossing candidates: near chunks, and far chunks on which interX could fire through sign noise.  That
+        // needs a segment collinear (within kCollinear) with an edge whose LINE also passes through the chunk
+        // (DESIGN.md "Exactness").  The side edges lie on the two lines parallel to the heading at lateral offset
+        // +-half_width from the centre, the front/back edges on the two lines along the normal at +-half_length:
+        // the chunk qualifies if its direction cone contains that direction and its box reaches into the band
+        // between / around the two lines (band widened by 1 mm >> the 1e-7 m error of vertices and cos/sin).
+        auto test_box = [&](int c, uint32_t bit) {   // branch-free; c0 is masked out below
             const float4 bx = boxes[c];
             const float2 cone = __half22float2(cones[c]);
             const float bcx = bx.x - px, bcy = bx.y - py;   // box centre, relative
             const float hx = bx.z, hy = bx.w;
             const float lb2 = box_lb2_rel(bx, bcx, bcy);
-            const uint32_t bit = 1u << c;
             md |= (lb2 > thr) ? 0u : bit;
-            // Crossing candidates: near chunks, and far chunks on which interX could fire through sign noise.  That
-            // needs a segment collinear (within kCollinear) with an edge whose LINE also passes through the chunk
-            // (DESIGN.md "Exactness").  The side edges lie on the two lines parallel to the heading at lateral offset
-            // +-half_width from the centre, the front/back edges on the two lines along the normal at +-half_length:
-            // the chunk qualifies if its direction cone contains that direction and its box reaches into the band
-            // between / around the two lines (band widened by 1 mm >> the 1e-7 m error of vertices and cos/sin).
             float da = fabsf(psi_m - cone.x);
             da = fminf(da, pi_f - da);                       // angle between heading and cone axis, mod pi
             const bool side_band = fabsf(cs * bcy - sn * bcx) <= hx * asn + (hy * acs + band_w);
             const bool face_band = fabsf(cs * bcx + sn * bcy) <= hx * acs + (hy * asn + band_l);
             const bool far_cand = ((da <= cone.y) & side_band) | (((half_pi - da) <= cone.y) & face_band);
             mx |= (!(lb2 > near2) | far_cand) ? bit : 0u;
+        };
+        // two boxes per lane and iteration: independent dependency chains, half the loop overhead
+        for (int c = lane; c < nch; c += 2 * G) {
+            const int c2 = c + G;
+            test_box(c, 1u << c);
+            test_box(c2 < nch ? c2 : c, c2 < nch ? (1u << c2) : 0u);
         }
         if (exhaustive) { md = 0xffffffffu; mx = 0xffffffffu; }
         {
@@ -725,13 +746,15 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
         md = group_or<G>(md);
         mx = group_or<G>(mx);
     }
-    d_cg = sqrtf(group_min<G>(bq[0].q));
-    if (want_dv) {   // per-vertex distances are only reported in the debug buffer; consumers read their minimum
+    d_cg = sqrt_fast(group_min<G>(bq[0].q));
+    // consumers read the minimum over the vertices: ONE root of the minimal square in either mode, so that the value
+    // does not depend on whether a debug buffer is bound (the spawn table is built with one)
+    m4_out = sqrt_fast(group_min<G>(fminf(fminf(bq[1].q, bq[2].q), fminf(bq[3].q, bq[4].q))));
+    if (want_dv) {   // per-vertex distances are only reported in the debug buffer
 #pragma unroll
-        for (int v = 0; v < 4; v++) dv[v] = sqrtf(group_min<G>(bq[v + 1].q));
+        for (int v = 0; v < 4; v++) dv[v] = sqrt_fast(group_min<G>(bq[v + 1].q));
     } else {
-        const float m4 = sqrtf(group_min<G>(fminf(fminf(bq[1].q, bq[2].q), fminf(bq[3].q, bq[4].q))));
-        dv[0] = dv[1] = dv[2] = dv[3] = m4;
+        dv[0] = dv[1] = dv[2] = dv[3] = m4_out;
     }
     hit_out = group_or<G>(hit ? 1u : 0u) != 0u;
 }
@@ -875,6 +898,16 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
         else if (SYNCW > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + w / (SYNCW > 0 ? SYNCW : 1)), "r"(SYNCW * 32) : "memory");
         else __syncwarp();
     };
+    // rectangle pairs of an env: pair index -> (lo, hi), lo < hi, row-major over the upper triangle (pairs before row
+    // lo number lo (2N - 1 - lo) / 2; the row comes from a float root, corrected by at most one step); packed lo | hi << 8
+    auto decode_pair = [&](int pi) {
+        int lo = (int)((float)(2 * N - 1) * 0.5f - sqrt_fast((float)((2 * N - 1) * (2 * N - 1)) * 0.25f - 2.0f * (float)pi));
+        lo = max(0, min(lo, N - 2));
+        if (lo * (2 * N - 1 - lo) / 2 > pi) lo--;
+        else if ((lo + 1) * (2 * N - 2 - lo) / 2 <= pi) lo++;
+        return lo | ((lo + 1 + (pi - lo * (2 * N - 1 - lo) / 2)) << 8);
+    };
+    const int pair_first = (N >= 2) ? decode_pair(min(ln % env_lanes, N * (N - 1) / 2 - 1)) : 0;
     const int stride_wt = gridDim.x * kWarps;
     const int n_iter = SYNCW > 1 ? (n_wt - (int)blockIdx.x * kWarps + stride_wt - 1) / stride_wt : (1 << 30);
     for (int it = 0, wt = blockIdx.x * kWarps + w; it < n_iter && (SYNCW > 1 || wt < n_wt); it++, wt += stride_wt) {
@@ -1030,17 +1063,17 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             // One rolled loop over {left, right}: a single copy of the scan in the instruction stream.
 #pragma unroll 1
             for (int side = 0; side < 2; side++) {
-                float dc, dvv[4];
+                float dc, dvv[4], m4;
                 bool hit;
                 scan_boundary<G>(pts + (side ? prp->r_off : prp->l_off), boxes + (side ? prp->rbox : prp->lbox),
                                  cones + (side ? prp->rcone : prp->lcone), side ? prp->n_r : prp->n_l, h2, ex, px, py,
                                  ts.cs + sl, ts.sn + sl, ts.psim + sl, rvx, rvy, rect_radius, p.near2, cfg.half_length,
-                                 cfg.half_width, p.band_l, p.band_w, p.buf.dbg != nullptr, lane, dc, dvv, hit);
+                                 cfg.half_width, p.band_l, p.band_w, p.buf.dbg != nullptr, lane, dc, dvv, m4, hit);
                 if (hit) fl = (int)SGB_FLAG_COLLIDE_LANE;
                 if (writer) {
                     dc = dc - cfg.half_width;                                   // world_state_rt.py:608-610
                     ts.sc[(2 + side) * AS + sl] = dc;
-                    ts.sc[(4 + side) * AS + sl] = fminf(fminf(dvv[0], dvv[1]), fminf(dvv[2], dvv[3]));
+                    ts.sc[(4 + side) * AS + sl] = m4;
                     if (dbg) {
                         dbg[side ? 7 : 2] = dc;
 #pragma unroll
@@ -1089,9 +1122,9 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             if (ts.flags[sbase] >= 0) {
                 const int n_pairs = N * (N - 1) / 2;
                 for (int pi = q; pi < n_pairs; pi += env_lanes) {
-                    int lo = 0, rem = pi;               // pair index -> (lo, hi), lo < hi
-                    while (rem >= N - 1 - lo) { rem -= N - 1 - lo; lo++; }
-                    const int hi = lo + 1 + rem;
+                    // (lo, hi) of a lane's FIRST pair was decoded once, before the tile loop
+                    const int packed = (pi == q) ? pair_first : decode_pair(pi);
+                    const int lo = packed & 0xff, hi = packed >> 8;
                     {
                         // Gate (same certificate as for boundary segments): rectangles whose centres are farther
                         // apart than two circumradii + kFarMargin cannot touch, and interX can then only fire

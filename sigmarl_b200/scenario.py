@@ -190,6 +190,9 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
         else:
             known = {k: v for k, v in kwargs.items() if k in EnvConfig.__dataclass_fields__}
             known.setdefault("scenario_type", "cpm_entire")
+            # the reference's kwargs-mode defaults (road_traffic.py:304-361) where they differ from EnvConfig's own
+            # (the raw engine config defaults to noise-free observations): is_obs_noise=True, level 0.2 * agent width
+            known.setdefault("is_obs_noise", True)
             cfg = EnvConfig(mode="kwargs", **known)
         self.config = cfg
         # hot-path parameters that exist at one value only: refuse anything else, whichever way it was passed

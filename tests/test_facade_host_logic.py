@@ -218,6 +218,27 @@ def test_kwargs_mode_exposes_parameters(facade):
     assert sc.config.mode == "kwargs" and sc.parameters.num_vmas_envs == 3 and sc.env.dt == 0.05
 
 
+def test_kwargs_mode_defaults_are_the_references(facade):
+    """make_world(**kwargs) without explicit values builds the Parameters of road_traffic.py:304-361: dt 0.05, two observed
+    neighbours, ego view with vertices / all three distances, no mask, no MTV distance, no steering / neighbour paths —
+    and observation noise ON at 0.2 x agent width (:336-339).  (The raw EnvConfig defaults to noise-free; the facade is
+    the drop-in and applies the reference's default.)"""
+    sc, _, e = facade(scenario_type="cpm_entire")
+    p, c = sc.parameters, e.cfg
+    assert (p.n_agents, p.dt, p.n_nearing_agents_observed) == (15, 0.05, 2)
+    assert p.is_ego_view and p.is_observe_vertices and p.is_observe_distance_to_agents
+    assert p.is_observe_distance_to_boundaries and p.is_observe_distance_to_center_line and p.is_partial_observation
+    assert not (p.is_apply_mask or p.is_use_mtv_distance or p.is_obs_steering or p.is_observe_ref_path_other_agents)
+    assert not p.is_testing_mode and p.reset_agent_fixed_duration == 0 and tuple(p.cpm_scenario_probabilities) == (1.0, 0.0, 0.0)
+    assert p.is_obs_noise is True and abs(c.obs_noise_level - np.float32(0.2 * 0.107)) < 1e-9
+    assert c.obs_flags == 0 and c.use_mtv_distance == 0 and c.k_near == 2
+    # an explicit value wins, in either direction
+    sc, _, e = facade(scenario_type="cpm_entire", is_obs_noise=False)
+    assert sc.parameters.is_obs_noise is False and e.cfg.obs_noise_level == 0.0
+    sc, _, e = facade(scenario_type="cpm_entire", obs_noise_level=0.01)
+    assert abs(e.cfg.obs_noise_level - np.float32(0.01)) < 1e-9
+
+
 def test_single_valued_parameters_are_refused_not_ignored(facade):
     """Parameters that change the step but exist at one value only (config.FIXED_PARAMETERS) fail loudly, whether they
     arrive as kwargs or on a Parameters object; their supported values pass."""

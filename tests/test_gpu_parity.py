@@ -473,7 +473,8 @@ def test_spawn_table_reset_equals_generic_refresh(scenario, N):
 def test_vmas_facade_drives_the_same_kernel():
     """The BaseScenario-shaped facade (make_world / world.step / reward / observation / done / reset_world_at)."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv, make_env
-    env = make_env(scenario_type="cpm_mixed", num_envs=64, device="cuda:0", n_agents=4, seed=3, max_steps=128)
+    env = make_env(scenario_type="cpm_mixed", num_envs=64, device="cuda:0", n_agents=4, seed=3, max_steps=128,
+                   is_obs_noise=False)     # (the facade's kwargs-mode default is the reference's: noise on)
     sc = env.scenario
     ref = RoadTrafficEnv(EnvConfig(scenario_type="cpm_mixed", n_agents=4, mode="kwargs"), num_envs=64, device="cuda:0", seed=3)
     ref.reset()
@@ -658,7 +659,8 @@ def _facade_from_golden(g):
         ttc_low=float(g["cfg_ttc_low"]), ttc_high=float(g["cfg_ttc_high"]),
         penalty_near_boundary=float(g["cfg_penalty_near_boundary"]),
         penalty_near_other_agents=float(g["cfg_penalty_near_other_agents"]),
-        is_testing_mode=bool(g["cfg_is_testing_mode"]), **_obs_flags_of_golden(g))
+        is_testing_mode=bool(g["cfg_is_testing_mode"]), is_obs_noise=False,    # the goldens were recorded without noise
+        **_obs_flags_of_golden(g))
     for name in ("reset_agent_fixed_duration", "is_use_mtv_distance"):       # fixtures of tests/golden/next/
         if ("cfg_" + name) in g.files:
             kw[name] = g["cfg_" + name].item()

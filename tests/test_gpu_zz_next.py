@@ -136,7 +136,7 @@ def test_facade_predefined_paths_and_init_state(oracle_mod):
             for i, p in enumerate(paths)]
     B, N = 8, 3
     env = make_env(scenario_type="cpm_entire", num_envs=B, device="cuda:0", n_agents=N, seed=1, max_steps=32,
-                   predefined_ref_path_idx=paths, init_state=init)
+                   predefined_ref_path_idx=paths, init_state=init, is_obs_noise=False)
     sc, e = env.scenario, env.scenario.env
 
     def check_init(rows):
