@@ -266,6 +266,16 @@ int sgb_reset_all(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, in
 int sgb_step_host(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
                   float* h_obs, float* h_reward, uint8_t* h_done, void* stream);
 
+/* sgb_step_host followed, chunk by chunk inside the same copy / compute pipeline, by the masked device reset of
+ * sgb_reset (same arguments, same draws as an unchunked call): `h_obs` then holds what a host-resident policy acts on
+ * NEXT — the all-fresh post-reset observation for the envs that finished in this step, the step-time observation for
+ * the others — while `h_reward` / `h_done` are the step's.  One call = one iteration of the collector loop
+ * (helper_training.py:745-770: env.step, then reset of the done envs). */
+int sgb_step_reset_host(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
+                        float* h_obs, float* h_reward, uint8_t* h_done, int32_t path_lo, int32_t path_hi,
+                        uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t* n_failed,
+                        void* stream);
+
 /* "Next" row: generalised advantage estimation over a finished rollout, written straight
  * into caller-provided buffers (e.g. this rank's slot of the all-gather buffer).  All pointers are device
  * memory; reward / value / next_value / adv / target are [T,B,N] fp32, done is [T,B] bytes (terminated ==

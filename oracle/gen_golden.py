@@ -61,9 +61,15 @@ CONFIGS = {
     "cpm_mixed_B8_N6_ttc_sparse": dict(st="cpm_mixed", B=8, N=6, T=60, mode="params", seed=3,
                                        extra=dict(rew_method="ttc_sparse",
                                                   threshold_near_other_agents_c2c_low=0.1635)),
-    # NB: cpm_mixed with merge-in/merge-out path sets (cpm_scenario_probabilities != [1,0,0]) cannot be
-    # generated: the reference's own unbounded rejection sampling (world_state_rt_sim.py:232-311) never
-    # terminates there for N >= 2 and N = 1 crashes in observation_provider_rt.py:790 (probed).
+    # cpm_mixed with the merge-in / merge-out path sets (cpm_scenario_probabilities != [1,0,0]; one scenario id per env,
+    # world_state_rt_sim.py:313-358).  Those sets hold 4 short paths each (31 spawn points): at the reset distance of
+    # 0.367 m at most 3 (merge-in) / 2 (merge-out) agents fit, so the reference's unbounded rejection sampling
+    # (:232-311) only terminates reliably for N <= 2 (probed: N = 4 spins forever; N = 1 crashes in
+    # observation_provider_rt.py:790).  N = 2 works and is recorded below.
+    "sets_cpm_mixed_B4_N2_merge_in_gentle": dict(st="cpm_mixed", B=4, N=2, T=60, mode="params", seed=71, gentle=True,
+                                                extra=dict(cpm_scenario_probabilities=[0.0, 1.0, 0.0])),
+    "sets_cpm_mixed_B8_N2_all_sets": dict(st="cpm_mixed", B=8, N=2, T=60, mode="params", seed=72,
+                                         extra=dict(cpm_scenario_probabilities=[0.3, 0.3, 0.4], rew_method="ttc_sparse")),
     "on_ramp_2_B8_N12": dict(st="on_ramp_2_multilane", B=8, N=12, T=40, mode="kwargs", seed=5),
     "roundabout_2_B8_N12_ttc": dict(st="roundabout_2", B=8, N=12, T=40, mode="params", seed=6,
                                    extra=dict(rew_method="ttc")),
@@ -161,7 +167,7 @@ CONFIGS = {
 # fixtures of features added after the last hardware session: tests/golden/next/ (tests/conftest.py)
 NEXT = {"cpm_entire_B4_N3_fixed2s_gentle", "cpm_mixed_B4_N3_fixed1s_testing_gentle", "mtv_cpm_entire_B4_N6_distance",
         "mtv_cpm_mixed_B4_N5_ttc_sparse_gentle", "mtv_roundabout_2_B4_N10_kw_k3"}
-NEXT |= {n for n in CONFIGS if n.startswith(("map_", "mask_", "big_"))}
+NEXT |= {n for n in CONFIGS if n.startswith(("map_", "mask_", "big_", "sets_"))}
 
 OBS_FLAGS = ["is_ego_view", "is_observe_vertices", "is_obs_steering", "is_observe_ref_path_other_agents",
              "is_observe_distance_to_agents", "is_observe_distance_to_center_line",

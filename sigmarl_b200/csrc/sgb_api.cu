@@ -41,6 +41,9 @@ struct sgb_ctx {
     cudaEvent_t pipe_event[2] = {nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
     bool pipe_ready = false;
+    int32_t* pipe_list[2] = {nullptr, nullptr};         // per-stream reset scratch of sgb_step_reset_host
+    int32_t* pipe_count[2] = {nullptr, nullptr};
+    int32_t pipe_list_cap = 0;
 };
 
 static thread_local char g_err[256] = "";
@@ -319,14 +322,14 @@ int launch_env_group(sgb_ctx* ctx, Params& p, cudaStream_t st, int g) {
 
 int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, const int32_t* env_list,
                const int32_t* env_count, int write_obs, cudaStream_t st, int skip_scan = 0,
-               const sgb_config* cfg_override = nullptr, int64_t env_first = 0) {
+               const sgb_config* cfg_override = nullptr, int64_t env_first = 0, const float* fresh = nullptr) {
     Params p{};
     p.noise_epoch = ctx->noise_epoch;
     p.env_base = ctx->env_offset + env_first;   // global index of buf's env 0 (env_first: chunked launches)
     p.cfg = cfg_override ? *cfg_override : ctx->cfg;
     // spawn-table refresh: the table holds no boundary indices, so a layout with boundary points runs the scans
     p.skip_scan = (p.cfg.obs_flags & SGB_OBS_BOUNDARY_POINTS) ? 0 : skip_scan;
-    p.fresh = ctx->d_fresh;
+    p.fresh = fresh ? fresh : ctx->d_fresh;
     p.buf = *buf;
     p.blob = ctx->d_blob;
     p.env_list = env_list;
@@ -632,6 +635,7 @@ extern "C" int sgb_destroy(sgb_ctx* c) {
         for (int i = 0; i < 2; i++) { cudaStreamDestroy(c->pipe_stream[i]); cudaEventDestroy(c->pipe_event[i]); }
         cudaEventDestroy(c->pipe_start);
     }
+    for (int i = 0; i < 2; i++) { cudaFree(c->pipe_list[i]); cudaFree(c->pipe_count[i]); }
     delete c;
     return SGB_OK;
 }
@@ -713,10 +717,20 @@ extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* bu
     return SGB_OK;
 }
 
+// scratch of one reset: compacted list of the fully reset envs + its length, spawn-pose distances of the re-placed
+// agents.  The context owns one set (ensure_list / ensure_fresh); the chunked host pipeline keeps one per stream.
+struct ResetScratch {
+    int32_t* list = nullptr;
+    int32_t* count = nullptr;
+    float* fresh = nullptr;
+    int64_t env_first = 0;      // index of buf's env 0 within the batch the caller's env_offset refers to
+};
+
 static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
                       uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t write_obs,
                       int32_t* n_failed, int all, cudaStream_t st, int explicit_sel = 0,
-                      const uint8_t* env_mask = nullptr, const uint8_t* agent_mask = nullptr) {
+                      const uint8_t* env_mask = nullptr, const uint8_t* agent_mask = nullptr,
+                      const ResetScratch* scratch = nullptr) {
     if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || path_lo < 0 || path_hi > c->n_paths || path_lo >= path_hi ||
         max_tries <= 0)
         return SGB_ERR_ARG;
@@ -725,18 +739,23 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     if (!buf->step_count || (!all && !explicit_sel && !buf->done)) return SGB_ERR_ARG;
     if (write_obs && !buf->obs) return SGB_ERR_ARG;
     GUARD(c);
-    c->noise_epoch++;
-    c->env_offset = env_offset;      // the observation noise is keyed by the GLOBAL env index as well
-    rc = ensure_list(c, B);
-    if (rc) return rc;
-    rc = ensure_fresh(c, (int64_t)B * N);
-    if (rc) return rc;
-    CK(cudaMemsetAsync(c->d_count, 0, sizeof(int32_t), st));
+    ResetScratch own;
+    if (!scratch) {
+        c->noise_epoch++;
+        c->env_offset = env_offset;      // the observation noise is keyed by the GLOBAL env index as well
+        rc = ensure_list(c, B);
+        if (rc) return rc;
+        rc = ensure_fresh(c, (int64_t)B * N);
+        if (rc) return rc;
+        own.list = c->d_list; own.count = c->d_count; own.fresh = c->d_fresh;
+        scratch = &own;
+    }
+    CK(cudaMemsetAsync(scratch->count, 0, sizeof(int32_t), st));
     ResetParams p{};
-    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.list = c->d_list; p.count = c->d_count;
-    p.n_failed = n_failed; p.seed = seed; p.epoch = epoch; p.env_offset = env_offset;
+    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.list = scratch->list; p.count = scratch->count;
+    p.n_failed = n_failed; p.seed = seed; p.epoch = epoch; p.env_offset = env_offset + scratch->env_first;
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
-    p.spawn_tab = c->d_spawn; p.fresh = c->d_fresh; p.list_full_only = 1;
+    p.spawn_tab = c->d_spawn; p.fresh = scratch->fresh; p.list_full_only = 1;
     p.explicit_sel = explicit_sel; p.env_mask = env_mask; p.agent_mask = agent_mask;
     // envs per warp: a warp walks its touched envs one after the other, so few envs per warp keep the dependent-load
     // chains short; about four waves of resident warps (48 per SM) was the best trade against block-launch overhead
@@ -751,7 +770,8 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     // (and info block) of the FULLY reset envs — respawned agents keep their step-time observation, like the
     // reference — which needs the other agents of the env but no polyline scan
     if (!write_obs && !buf->info) return SGB_OK;
-    return launch_env(c, B, N, buf, 1, c->d_list, c->d_count, write_obs, st, 1);
+    return launch_env(c, B, N, buf, 1, scratch->list, scratch->count, write_obs, st, 1, nullptr, scratch->env_first,
+                      scratch->fresh);
 }
 
 extern "C" int sgb_reset(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, int32_t path_lo, int32_t path_hi,
@@ -777,18 +797,17 @@ extern "C" int sgb_reset_masked(sgb_ctx* c, int32_t B, int32_t N, const sgb_buff
 }
 
 // Host-buffer step, pipelined: the batch is cut into chunks that alternate between two internal streams, so
-// the H2D copy of chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).
-extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
-                             float* h_obs, float* h_reward, uint8_t* h_done, void* stream) {
-    if (!c || !h_action || !h_obs || !h_reward || !h_done || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS ||
-        c->cfg.k_near > N - 1)
-        return SGB_ERR_ARG;
-    int rc = check_buffers(buf, 1);
-    if (rc) return rc;
-    GUARD(c);
-    c->noise_epoch++;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int D = obs_dim_of(c->cfg.obs_flags, c->cfg.k_near);
+// the H2D copy of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).
+// With `rs` the chunk also runs the masked device reset (+ fresh observations) before its observation goes out, so
+// that the host receives what its policy acts on next.
+struct HostReset {
+    int32_t path_lo, path_hi, max_tries;
+    uint64_t seed, epoch;
+    int64_t env_offset;
+    int32_t* n_failed;
+};
+
+static int ensure_pipe(sgb_ctx* c, int chunk_envs, int N) {
     if (!c->pipe_ready) {
         for (int i = 0; i < 2; i++) {
             CK(cudaStreamCreateWithFlags(&c->pipe_stream[i], cudaStreamNonBlocking));
@@ -797,12 +816,55 @@ extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
         CK(cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
         c->pipe_ready = true;
     }
-    const int n_chunks = B >= 8192 ? 8 : (B >= 1024 ? 2 : 1);
+    if (c->pipe_list_cap < chunk_envs) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(c->pipe_list[i]);
+            c->pipe_list[i] = nullptr;
+            CK(cudaMalloc(&c->pipe_list[i], sizeof(int32_t) * (size_t)chunk_envs));
+            if (!c->pipe_count[i]) CK(cudaMalloc(&c->pipe_count[i], sizeof(int32_t)));
+        }
+        c->pipe_list_cap = chunk_envs;
+    }
+    (void)N;
+    return SGB_OK;
+}
+
+static int step_host_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action, float* h_obs,
+                          float* h_reward, uint8_t* h_done, const HostReset* rs, cudaStream_t st) {
+    if (!c || !h_action || !h_obs || !h_reward || !h_done || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS ||
+        c->cfg.k_near > N - 1)
+        return SGB_ERR_ARG;
+    int rc = check_buffers(buf, 1);
+    if (rc) return rc;
+    if (rs && (rs->path_lo < 0 || rs->path_hi > c->n_paths || rs->path_lo >= rs->path_hi || rs->max_tries <= 0)) return SGB_ERR_ARG;
+    GUARD(c);
+    // noise key: the step and the reset count as the two API calls they replace (sgb_step, sgb_reset)
+    const uint64_t epoch_step = ++c->noise_epoch;
+    const uint64_t epoch_reset = rs ? ++c->noise_epoch : epoch_step;
+    const int D = obs_dim_of(c->cfg.obs_flags, c->cfg.k_near);
+    // Chunks of whole kernel waves: one wave = one env-tile per resident warp (num_sms CTAs x warps per CTA x envs per
+    // warp), so a chunk of two waves keeps every SM busy for exactly two tile iterations and the map is staged once
+    // per SM and chunk.  Enough chunks that the copies of neighbouring chunks overlap the kernels; small batches run
+    // as one launch.
+    const int g = pick_group(N);
+    const int wave = c->num_sms * (cta_threads(g) / 32) * std::max(1, 32 / (N * g));
+    int waves = 2;
+    if (const char* e = getenv("SGB_HOST_CHUNK_WAVES")) waves = std::max(1, std::min(64, atoi(e)));   // tuning knob
+    int chunk = waves * wave;
+    if (B < 2 * chunk) chunk = B;
+    const int n_chunks = (B + chunk - 1) / chunk;
+    rc = ensure_pipe(c, chunk, N);
+    if (rc) return rc;
+    if (rs) {
+        c->env_offset = rs->env_offset;
+        rc = ensure_fresh(c, (int64_t)B * N);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(c->pipe_start, st));
     for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(c->pipe_stream[i], c->pipe_start, 0));
     for (int k = 0; k < n_chunks; k++) {
         cudaStream_t s = c->pipe_stream[k & 1];
-        const int e0 = (int)((int64_t)B * k / n_chunks), e1 = (int)((int64_t)B * (k + 1) / n_chunks);
+        const int e0 = k * chunk, e1 = std::min(B, e0 + chunk);
         const int nb = e1 - e0;
         if (nb <= 0) continue;
         const size_t a0 = (size_t)e0 * N;
@@ -815,18 +877,43 @@ extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers
         if (sub.task_tries) sub.task_tries += e0;
         if (sub.task_success) sub.task_success += e0;
         CK(cudaMemcpyAsync(sub.action, h_action + a0 * 2, (size_t)nb * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+        c->noise_epoch = epoch_step;
         rc = launch_env(c, nb, N, &sub, 0, nullptr, nullptr, 1, s, 0, nullptr, e0);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(h_obs + a0 * D, sub.obs, (size_t)nb * N * D * sizeof(float), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_reward + a0, sub.reward, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(h_done + e0, sub.done, (size_t)nb, cudaMemcpyDeviceToHost, s));
+        if (rs) {
+            // reset / respawn of this chunk's envs, keyed by the GLOBAL env index: same draws as an unchunked sgb_reset
+            ResetScratch sc;
+            sc.list = c->pipe_list[k & 1]; sc.count = c->pipe_count[k & 1];
+            sc.fresh = c->d_fresh + a0 * 4; sc.env_first = e0;
+            c->noise_epoch = epoch_reset;
+            rc = reset_impl(c, nb, N, &sub, rs->path_lo, rs->path_hi, rs->seed, rs->epoch, rs->env_offset, rs->max_tries, 1,
+                            rs->n_failed, 0, s, 0, nullptr, nullptr, &sc);
+            if (rc) return rc;
+        }
+        CK(cudaMemcpyAsync(h_obs + a0 * D, sub.obs, (size_t)nb * N * D * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < 2; i++) {
         CK(cudaEventRecord(c->pipe_event[i], c->pipe_stream[i]));
         CK(cudaStreamWaitEvent(st, c->pipe_event[i], 0));
     }
+    c->noise_epoch = epoch_reset;
     CK(cudaStreamSynchronize(st));
     return SGB_OK;
+}
+
+extern "C" int sgb_step_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
+                             float* h_obs, float* h_reward, uint8_t* h_done, void* stream) {
+    return step_host_impl(c, B, N, buf, h_action, h_obs, h_reward, h_done, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int sgb_step_reset_host(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const float* h_action,
+                                   float* h_obs, float* h_reward, uint8_t* h_done, int32_t path_lo, int32_t path_hi,
+                                   uint64_t seed, uint64_t epoch, int64_t env_offset, int32_t max_tries, int32_t* n_failed,
+                                   void* stream) {
+    HostReset rs{path_lo, path_hi, max_tries, seed, epoch, env_offset, n_failed};
+    return step_host_impl(c, B, N, buf, h_action, h_obs, h_reward, h_done, &rs, (cudaStream_t)stream);
 }
 
 extern "C" int sgb_gae(int32_t T, int32_t B, int32_t N, const float* reward, const float* value, const float* next_value,

@@ -248,9 +248,10 @@ SGB_HD __forceinline__ float sat01(float x) {
     return fminf(fmaxf(x, 0.0f), 1.0f);
 #endif
 }
-SGB_HD __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly, float rlen2, float px, float py) {
+// (sx, sy) = l / |l|^2: the projection parameter is v . s, scaled once per segment instead of once per point
+SGB_HD __forceinline__ float seg_q_r(float ax, float ay, float lx, float ly, float sx, float sy, float px, float py) {
     const float vx = px - ax, vy = py - ay;
-    const float t = sat01((vx * lx + vy * ly) * rlen2);
+    const float t = sat01(vx * sx + vy * sy);
     const float ex = fmaf(lx, t, -vx), ey = fmaf(ly, t, -vy);   // (a + l t) - p, one FMA per component
     return ex * ex + ey * ey;
 }
@@ -639,13 +640,14 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
                 if (do_d) {
                     SGB_COUNT(1, 2);
                     const float rl = rcp_fast(len2), rl2 = rcp_fast(len2b);
-                    q0a = seg_q_r(a.x, a.y, lx, ly, rl, px, py);
-                    q0b = seg_q_r(a2.x, a2.y, lx2, ly2, rl2, px, py);
+                    const float sx = lx * rl, sy = ly * rl, sx2 = lx2 * rl2, sy2 = ly2 * rl2;
+                    q0a = seg_q_r(a.x, a.y, lx, ly, sx, sy, px, py);
+                    q0b = seg_q_r(a2.x, a2.y, lx2, ly2, sx2, sy2, px, py);
                     bq[0].upd(fminf(q0a, q0b));
 #pragma unroll
                     for (int v = 0; v < 4; v++)
-                        bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, rl, rvx[v], rvy[v]),
-                                            seg_q_r(a2.x, a2.y, lx2, ly2, rl2, rvx[v], rvy[v])));
+                        bq[v + 1].upd(fminf(seg_q_r(a.x, a.y, lx, ly, sx, sy, rvx[v], rvy[v]),
+                                            seg_q_r(a2.x, a2.y, lx2, ly2, sx2, sy2, rvx[v], rvy[v])));
                 }
                 if (do_x) {
                     // Gate of the exact predicate: the segment is near the rectangle (then its chunk is a near chunk,
@@ -1152,7 +1154,11 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 }
             }
         }
+#ifdef SGB_NO_BC_SYNC
+        __syncwarp();
+#else
         phase_sync();   // alignment only (phase C reads this warp's slots), but dropping it costs 12 %: I-cache
+#endif
 
         // ================= phase C: interactions inside the env, reward, observation ===============  @region phase C1
         {

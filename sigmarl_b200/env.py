@@ -206,18 +206,27 @@ class RoadTrafficEnv:
         """[B,N] bool: the mark described in ``set_pose_history`` (always False for the other layouts)."""
         return (self.carry.view(torch.int32)[..., 3] & _lib.CARRY_FRESH_BIT) != 0
 
-    def step_host(self, h_action: torch.Tensor):
-        """End-to-end step with HOST buffers through sgb_step_host (H2D action, D2H obs/reward/done inside)."""
+    def step_host(self, h_action: torch.Tensor, reset_done: bool = False):
+        """End-to-end step with HOST buffers through sgb_step_host (H2D action, D2H obs/reward/done inside).
+        reset_done: sgb_step_reset_host — done envs are reset inside the same pipeline and the returned observation
+        is the one the policy acts on next (post-reset for the envs that finished, step-time for the others)."""
         if self._h is None:
             pin = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype).pin_memory()  # noqa: E731
             self._h = dict(obs=pin(self.B, self.N, self.D), reward=pin(self.B, self.N),
                            done=pin(self.B, dtype=torch.uint8))
         h = self._h
         assert h_action.device.type == "cpu" and h_action.dtype == torch.float32 and h_action.is_contiguous()
-        _lib.check(self.L.sgb_step_host(self._ctx, self.B, self.N, C.byref(self._buf),
-                                        C.c_void_p(h_action.data_ptr()), C.c_void_p(h["obs"].data_ptr()),
-                                        C.c_void_p(h["reward"].data_ptr()), C.c_void_p(h["done"].data_ptr()),
-                                        self._stream()), "sgb_step_host")
+        ptrs = (C.c_void_p(h_action.data_ptr()), C.c_void_p(h["obs"].data_ptr()), C.c_void_p(h["reward"].data_ptr()),
+                C.c_void_p(h["done"].data_ptr()))
+        if reset_done:
+            self.epoch += 1
+            _lib.check(self.L.sgb_step_reset_host(self._ctx, self.B, self.N, C.byref(self._buf), *ptrs, self.path_lo,
+                                                  self.path_hi, self.seed, self.epoch, self.env_offset,
+                                                  self.max_reset_tries, C.c_void_p(self.n_failed.data_ptr()),
+                                                  self._stream()), "sgb_step_reset_host")
+        else:
+            _lib.check(self.L.sgb_step_host(self._ctx, self.B, self.N, C.byref(self._buf), *ptrs, self._stream()),
+                       "sgb_step_host")
         return h["obs"], h["reward"], h["done"]
 
     # ------------------------------------------------------------------ reference-named views

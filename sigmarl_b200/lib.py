@@ -21,7 +21,7 @@ EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points"
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
            "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance", "sgb_debug_pack_map",
            "sgb_set_lanelets", "sgb_debug_current_lanelet", "sgb_debug_pack_map_blob", "sgb_debug_scan_batch", "sgb_debug_scan_counters",
-           "sgb_debug_helper", "sgb_debug_short_term", "sgb_debug_pair_batch", "sgb_set_env_offset"]
+           "sgb_debug_helper", "sgb_debug_short_term", "sgb_debug_pair_batch", "sgb_set_env_offset", "sgb_step_reset_host"]
 
 
 class SgbError(RuntimeError):
@@ -92,6 +92,7 @@ def load_library():
     L.sgb_reset_all.argtypes = [vp, i32, i32, C.POINTER(Buffers), i32, i32, u64, u64, i64, i32, vp, vp]
     L.sgb_reset_masked.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, i32, i32, u64, u64, i64, i32, i32, vp, vp]
     L.sgb_step_host.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, vp, vp, vp]
+    L.sgb_step_reset_host.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, vp, vp, i32, i32, u64, u64, i64, i32, vp, vp]
     L.sgb_gae.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
     L.sgb_launch_count.argtypes = [vp]
     L.sgb_launch_count.restype = i64

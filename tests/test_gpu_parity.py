@@ -212,17 +212,18 @@ def test_cuda_observation_layouts_match_oracle(oracle_mod, scenario, N, rew, mod
 
 @pytest.mark.parametrize("layout", [dict(), dict(is_ego_view=False, is_obs_steering=True)], ids=["default", "birdview"])
 def test_observation_noise_is_uniform_additive_and_reproducible(layout):
-    """is_obs_noise (observation_provider_rt.py:611-617): obs + level * U[0,1) on every element.  The reference draws
-    from torch's global generator, the library from a counter-based device generator — distribution-equivalent:
-    noisy - clean must lie in [0, level), look uniform, differ between columns / agents / steps, and be a pure
-    function of (seed, state), i.e. reproducible and independent of the env's index (sharding)."""
+    """is_obs_noise (observation_provider_rt.py:611-617): obs + level * U[0,1) on every element, fresh draws on every
+    call (torch.rand_like).  The reference draws from torch's global generator, the library from a counter-based device
+    generator keyed by (seed, API-call counter, GLOBAL env index, agent, column) — distribution-equivalent: noisy - clean
+    must lie in [0, level), look uniform, differ between columns / agents / envs / steps (also when the state does NOT
+    change, and between envs in identical states), be reproducible, and not depend on how envs are sharded."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     B, N, level = 4096, 8, 0.05
-    mk = lambda noise, seed=0, nenv=B: RoadTrafficEnv(  # noqa: E731
+    mk = lambda noise, seed=0, nenv=B, off=0: RoadTrafficEnv(  # noqa: E731
         EnvConfig(scenario_type="cpm_entire", n_agents=N, is_obs_noise=noise, obs_noise_seed=seed, **layout),
-        num_envs=nenv, device="cuda:0", seed=3)
+        num_envs=nenv, device="cuda:0", seed=3, env_offset=off)
     clean, noisy, noisy2, other_seed = mk(False), mk(True), mk(True), mk(True, seed=1)
-    half = mk(True, nenv=B // 2)
+    half = mk(True, nenv=B // 2, off=B // 2)        # the second shard of the same batch
     assert noisy.D == clean.D
     g = torch.Generator(device="cuda").manual_seed(1)
     ur = torch.as_tensor(UR).cuda()
@@ -250,11 +251,11 @@ def test_observation_noise_is_uniform_additive_and_reproducible(layout):
         assert float((c - torch.eye(6, device="cuda", dtype=c.dtype)).abs().max()) < 0.03   # columns uncorrelated
         assert torch.equal(noisy.obs, noisy2.obs)                               # reproducible
         assert not torch.equal(noisy.obs, other_seed.obs)                       # seed matters
-        assert torch.equal(half.obs, noisy.obs[B // 2:])                        # independent of the env index
+        assert torch.equal(half.obs, noisy.obs[B // 2:])                        # sharding does not
         if prev is not None:
             assert float(((d - prev).abs() > 1e-4).double().mean()) > 0.95      # fresh draws every step
         prev = d
-        for e in (clean, noisy, noisy2, other_seed):
+        for e in (clean, noisy, noisy2, other_seed, half):
             e.reset_done(write_obs=False)
         # resets use the same RNG stream in all four envs: the trajectories stay identical
         assert torch.equal(noisy.pose, clean.pose)
@@ -262,6 +263,21 @@ def test_observation_noise_is_uniform_additive_and_reproducible(layout):
     a, b = clean.reset(), noisy.reset()
     dd = (b - a).double()
     assert float(dd.min()) >= -1e-6 and float(dd.max()) < level + 1e-6 and float(dd.mean()) > 0.4 * level
+    # The noise is NOT a function of the state: (1) envs put into the very same state draw different noise, (2) a
+    # refresh of an unchanged state draws new noise (a deterministic policy must not see B copies of one rollout).
+    for e in (clean, noisy):
+        for name in ("pose", "aux", "carry", "path_id"):
+            t_ = getattr(e, name)
+            t_.copy_(t_[:1].expand_as(t_).clone())
+    o_clean = clean.refresh(write_obs=True).clone()
+    o1 = noisy.refresh(write_obs=True).clone()
+    o2 = noisy.refresh(write_obs=True).clone()
+    assert torch.equal(o_clean, o_clean[:1].expand_as(o_clean))                # identical states, identical clean rows
+    n1, n2 = (o1 - o_clean).double() / level, (o2 - o_clean).double() / level
+    assert float((n1[1:] - n1[:1]).abs().mean()) > 0.25                         # |U - U'| has mean 1/3
+    assert float((n1 - n2).abs().mean()) > 0.25
+    cc = torch.corrcoef(torch.stack([n1[0].flatten(), n1[1].flatten(), n2[0].flatten()]))
+    assert float((cc - torch.eye(3, device="cuda", dtype=cc.dtype)).abs().max()) < 0.2
 
 
 def _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, **flags):
@@ -501,9 +517,10 @@ def test_vmas_facade_drives_the_same_kernel():
         ref.carry.copy_(sc.env.carry); ref.step_count.copy_(sc.env.step_count)
 
 
-@pytest.mark.parametrize("B", [512, 8192 + 40])
+@pytest.mark.parametrize("B", [512, 2 * 9472 + 40])
 def test_host_buffer_step_matches_device_step(B):
-    """sgb_step_host (chunked copy / compute pipeline for B >= 1024) == sgb_step on every buffer, incl. info."""
+    """sgb_step_host (chunked copy / compute pipeline: chunks of two kernel waves = 9472 envs at N = 8, so the larger size
+    runs as three chunks over both streams) == sgb_step on every buffer, incl. info."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     a = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=B, device="cuda:0", seed=4, info=True)
     b = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=B, device="cuda:0", seed=4, info=True)
@@ -517,6 +534,36 @@ def test_host_buffer_step_matches_device_step(B):
         for name in ("pose", "aux", "carry", "agent_flags", "collide_with", "step_count", "info", "task_tries", "task_success"):
             assert torch.equal(getattr(a, name), getattr(b, name)), name
         a.reset_done(); b.reset_done()
+
+
+@pytest.mark.parametrize("B,scenario,N", [(300, "cpm_mixed", 4), (2 * 9472 + 40, "cpm_entire", 8)])
+def test_host_buffer_step_with_reset_delivers_the_post_reset_observation(B, scenario, N):
+    """sgb_step_reset_host = one collector iteration for a host-resident policy: step, then (chunk by chunk, inside the
+    copy / compute pipeline) the masked device reset; the host gets reward / done of the step and the observation to act
+    on NEXT — post-reset for the envs that finished, step-time for the rest.  Must equal sgb_step + sgb_reset(write_obs)
+    on every buffer, with the same reset draws whatever the chunking."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    mk = lambda: RoadTrafficEnv(EnvConfig(scenario_type=scenario, n_agents=N), num_envs=B, device="cuda:0", seed=4,  # noqa: E731
+                                info=True, env_offset=1000)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    n_done = 0
+    for _ in range(4):
+        act = ((torch.rand(B, N, 2) * 2 - 1) * torch.as_tensor(UR)).contiguous().pin_memory()
+        h_obs, h_rew, h_done = a.step_host(act, reset_done=True)
+        _, rew, done = b.step(act.cuda())
+        rew, done = rew.clone(), done.clone()
+        b.reset_done(write_obs=True)
+        torch.cuda.synchronize()
+        assert torch.equal(h_rew, rew.cpu()) and torch.equal(h_done, done.cpu())
+        assert torch.equal(h_obs, b.obs.cpu()), "host observation == step-time obs with the reset envs' rows refreshed"
+        for name in ("pose", "aux", "carry", "path_id", "agent_flags", "collide_with", "step_count", "obs", "n_failed"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        n_done += int(done.sum())
+        d = done.bool().cpu()
+        if d.any():     # the rows of finished envs really are fresh ones: own speed entry == |v| of the NEW pose / v_max
+            assert torch.allclose(h_obs[d][..., 0], a.speed.cpu()[d], atol=1e-6)
+    assert n_done > 0
 
 
 def test_library_refuses_bad_arguments():
