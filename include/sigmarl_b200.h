@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 127
+#define SGB_VERSION 128
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -169,6 +169,12 @@ typedef struct {
     float*   dbg;         /* out [B,N,16] internals for parity tests; may be NULL:                  */
                           /*   0 d_ref 1 (int)idx_ref 2..6 dL[0..4] 7..11 dR[0..4] 12 d_bound       */
                           /*   13 nearest-agent index 14 second-nearest index 15 reserved           */
+    int32_t* scenario_id; /* io [B] path set of the env (sgb_set_path_sets): written by a full reset, read by   */
+                          /*   respawns — ref_paths_agent_related.scenario_id - 1 (world_state_rt_sim.py:313-358); */
+                          /*   may be NULL unless a reset is asked to draw from the path sets (path_lo = -1)    */
+    uint32_t* nan_flags;  /* io [1] sticky health word, may be NULL: bit 0 = a non-finite pose / observation /  */
+                          /*   reward was produced by a step (the reference asserts on these, road_traffic.py:   */
+                          /*   1245-1246); the caller clears it                                                  */
 } sgb_buffers;
 
 #define SGB_INFO_DIM 16
@@ -194,6 +200,14 @@ int sgb_destroy(sgb_ctx* ctx);
  * flag-driven observation writer then evaluates per observed neighbour. */
 int sgb_set_lanelets(sgb_ctx* ctx, int32_t n_lanelets, const float* center_xy, const int32_t* center_off,
                      const uint8_t* adjacency);
+
+/* Path sets of a map (cpm_mixed: intersection / merge-in / merge-out).  The reference draws ONE set per env at every
+ * full reset — scenario_id ~ multinomial(cpm_scenario_probabilities) — places all agents of the env on paths of that
+ * set, and keeps the set for single-agent respawns (world_state_rt_sim.py:313-358; road_traffic.py:333-334).
+ * set_lo / set_hi: global path index ranges [lo, hi) of the n_sets <= 4 sets; probability: their weights (normalised
+ * here).  A reset called with path_lo = -1 then draws per env from these sets (counter-based, keyed by the global env
+ * index like every reset draw) and needs buf->scenario_id; any other path_lo keeps the explicit range. */
+int sgb_set_path_sets(sgb_ctx* ctx, int32_t n_sets, const int32_t* set_lo, const int32_t* set_hi, const float* probability);
 
 /* Global index of this context's env 0 when a batch is sharded over several contexts / GPUs (default 0).  The reset
  * entry points take it as an argument (and remember it); the observation noise is keyed by it as well, so that noisy
@@ -289,43 +303,8 @@ int64_t sgb_launch_count(const sgb_ctx* ctx);
 /* Bytes of the packed map blob each CTA stages into shared memory. */
 int64_t sgb_map_bytes(const sgb_ctx* ctx);
 
-/* Arithmetic self-test hook (no device needed, nothing on the product path calls it): the MTV-based distance of two
- * rectangles given as [4][2] vertex arrays, evaluated by the HOST compilation of the same source function the MTV
- * kernels use (helper_scenario.py:1030-1138).  tests/test_abi_and_host.py replays the reference's known-answer
- * vectors through it bit-exactly. */
-float sgb_debug_mtv_distance(const float* vertices_i, const float* vertices_j);
-
-/* Host-only part of sgb_create (no device needed): validates and packs a map exactly as sgb_create would and reports
- * the size of the blob every CTA stages into shared memory (SGB_ERR_MAP for a degenerate polyline or one with more
- * than 256 segments).  Lets a build machine without a GPU check that every shipped map is accepted. */
-int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes);
-/* ... and a copy of the packed blob itself (layout: BlobHeader / PathRec in sgb_kernels.cuh), so that the pruning
- * certificates stored in it (chunk boxes, direction cones) can be validated against the polylines on the host. */
-int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64_t capacity);
-/* Host run of the kernels' own polyline scans (scan_center / scan_boundary with one lane per agent) for n independent
- * poses on a freshly packed blob: the pruned search (exhaustive = 0) must give exactly what the exhaustive one
- * (exhaustive = 1) gives.  out[16 * i]: d_ref, idx_ref, then per side (left at 2, right at 9) d_cg, 4 vertex
- * distances, crossing flag.  exhaustive | 2: as the product kernels run without a debug buffer — all four vertex slots
- * hold the minimum over the vertices, the only vertex quantity anything downstream consumes.  hint_idx is the carried
- * closest index (any value is valid).  The host compiler does not
- * contract a*b+c into FMAs, the device does: the certificates must (and do) hold under either rounding. */
-int sgb_debug_scan_batch(const sgb_map_desc* map, int32_t n, const int32_t* path, const float* x, const float* y,
-                         const float* psi, const int32_t* hint_idx, float half_length, float half_width,
-                         int32_t exhaustive, float* out);
-/* Work counters of sgb_debug_scan_batch on this thread since the last reset: 0 segment evaluations of the centre-line
- * scans, 1 of the boundary scans (each covers the centre + 4 vertices), 2 chunk boxes tested in the votes, 3 exact
- * crossing predicates, 4 centre scans, 5 boundary scans.  For sizing changes to the pruning logic without a GPU. */
-void sgb_debug_scan_counters(int64_t* out8, int32_t reset);
-/* Host builds of the kernels' small helpers: which 0 wrap_pi(in[0]); 1 dec_lin(in[0], in[1], in[2]); 2 kth_nearest over
- * in[1..n-1] with rank (int)in[0] -> out[0] index, out[1] distance.  And short_term() on a padded polyline. */
-int sgb_debug_helper(int32_t which, const float* in, int32_t n, float* out);
-int sgb_debug_short_term(const float* poly_xy, int32_t n_center, int32_t is_loop, int32_t idx, float* out6);
-/* Rectangle-pair crossing for n pose pairs (x, y, psi): out[i] bit 0 = the kernels' rect_cross_rect (host build), bit 1 =
- * the far-and-not-collinear gate of the pair loop would skip the pair (a skipped pair must never cross). */
-int sgb_debug_pair_batch(int32_t n, const float* lo_xyp, const float* hi_xyp, float half_length, float half_width,
-                         uint8_t* out);
-/* Host build of the kernels' current_lanelet() on a host-resident lanelet table (arithmetic self-test). */
-int sgb_debug_current_lanelet(int32_t n_lanelets, const float* center_xy, const int32_t* center_off, float x, float y);
+/* Host-side self-test hooks (sgb_debug_*) are NOT part of this library: they are declared in sigmarl_b200_test.h and
+ * exist only in libsigmarl_b200_test.so, which the test suite builds from the same sources with -DSGB_TEST_HOOKS. */
 
 const char* sgb_status_string(int status);
 const char* sgb_last_error(void); /* text of the last CUDA error seen by this thread */

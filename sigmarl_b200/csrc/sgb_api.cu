@@ -9,6 +9,9 @@
 #include <vector>
 
 #include "sgb_kernels.cuh"
+#ifdef SGB_TEST_HOOKS
+#include "../../include/sigmarl_b200_test.h"
+#endif
 
 using namespace sgb;
 
@@ -34,6 +37,9 @@ struct sgb_ctx {
     int32_t num_sms = 0;
     int32_t max_smem_optin = 0;
     int64_t launches = 0;
+    int32_t n_sets = 0;              // sgb_set_path_sets
+    int32_t set_lo[4] = {0, 0, 0, 0}, set_hi[4] = {0, 0, 0, 0};
+    float set_cum[4] = {1.0f, 1.0f, 1.0f, 1.0f};
     uint64_t noise_epoch = 0;        // counts API calls that can write an observation: part of the noise key
     int64_t env_offset = 0;          // global index of env 0 (sgb_set_env_offset / the reset entry points)
     size_t smem_configured[6][3] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G> on this device
@@ -77,6 +83,7 @@ struct DeviceGuard {
 
 extern "C" const char* sgb_last_error(void) { return g_err; }
 extern "C" int sgb_version(void) { return SGB_VERSION; }
+#ifdef SGB_TEST_HOOKS   // host-side self-test hooks: libsigmarl_b200_test.so only (include/sigmarl_b200_test.h)
 extern "C" float sgb_debug_mtv_distance(const float* vi, const float* vj) {
     // HOST build of the very source the MTV kernels compile (mtv_from_vertices): arithmetic self-test without a GPU
     float ax[4], ay[4], bx[4], by[4];
@@ -89,6 +96,7 @@ extern "C" int sgb_debug_current_lanelet(int32_t n, const float* xy, const int32
     for (int l = 0; l < n; l++) max_len = std::max(max_len, off[l + 1] - off[l]);
     return sgb::current_lanelet(reinterpret_cast<const float2*>(xy), off, n, max_len, x, y);   // host build of the kernels' function
 }
+#endif
 extern "C" const char* sgb_status_string(int s) {
     switch (s) {
         case SGB_OK: return "ok";
@@ -458,6 +466,7 @@ static int init_device_state(sgb_ctx* c, const Packed& pk) {
 }
 
 // ---- C-ABI ---------------------------------------------------------------------------------------------
+#ifdef SGB_TEST_HOOKS
 extern "C" int sgb_debug_pack_map(const sgb_map_desc* map, int64_t* blob_bytes) {
     Packed pk;
     const int rc = pack_map(map, pk);
@@ -581,6 +590,8 @@ extern "C" int sgb_debug_pack_map_blob(const sgb_map_desc* map, void* out, int64
     return SGB_OK;
 }
 
+#endif   // SGB_TEST_HOOKS
+
 extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, const sgb_config* cfg) {
     if (!out || !map || !cfg) return SGB_ERR_ARG;
     *out = nullptr;
@@ -662,6 +673,30 @@ extern "C" int sgb_set_lanelets(sgb_ctx* c, int32_t n, const float* xy, const in
     return SGB_OK;
 }
 
+extern "C" int sgb_set_path_sets(sgb_ctx* c, int32_t n_sets, const int32_t* set_lo, const int32_t* set_hi,
+                                 const float* probability) {
+    if (!c || n_sets < 1 || n_sets > 4 || !set_lo || !set_hi || !probability) return SGB_ERR_ARG;
+    double tot = 0.0;
+    for (int i = 0; i < n_sets; i++) {
+        if (set_lo[i] < 0 || set_hi[i] > c->n_paths || set_lo[i] >= set_hi[i] || !(probability[i] >= 0.0f)) return SGB_ERR_ARG;
+        tot += probability[i];
+    }
+    if (!(tot > 0.0)) return SGB_ERR_ARG;
+    int last_nz = 0;
+    for (int i = 0; i < n_sets; i++)
+        if (probability[i] > 0.0f) last_nz = i;
+    double acc = 0.0;
+    for (int i = 0; i < 4; i++) {
+        const int k = std::min(i, n_sets - 1);
+        if (i < n_sets) acc += probability[i] / tot;
+        c->set_lo[i] = set_lo[k]; c->set_hi[i] = set_hi[k];
+        // the last set with a non-zero weight takes whatever rounding leaves: a zero-weight set is never drawn
+        c->set_cum[i] = (i >= last_nz) ? 2.0f : (float)acc;
+    }
+    c->n_sets = n_sets;
+    return SGB_OK;
+}
+
 extern "C" int sgb_set_env_offset(sgb_ctx* c, int64_t env_offset) {
     if (!c || env_offset < 0) return SGB_ERR_ARG;
     c->env_offset = env_offset;
@@ -731,9 +766,16 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
                       int32_t* n_failed, int all, cudaStream_t st, int explicit_sel = 0,
                       const uint8_t* env_mask = nullptr, const uint8_t* agent_mask = nullptr,
                       const ResetScratch* scratch = nullptr) {
-    if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || path_lo < 0 || path_hi > c->n_paths || path_lo >= path_hi ||
-        max_tries <= 0)
+    if (!c || B <= 0 || N <= 0 || N > SGB_MAX_AGENTS || max_tries <= 0) return SGB_ERR_ARG;
+    const bool use_sets = path_lo == -1;        // draw per env from the context's path sets
+    if (use_sets) {
+        if (c->n_sets <= 0 || !buf || !buf->scenario_id) {
+            snprintf(g_err, sizeof g_err, "path_lo = -1 needs sgb_set_path_sets and buf->scenario_id");
+            return SGB_ERR_ARG;
+        }
+    } else if (path_lo < 0 || path_hi > c->n_paths || path_lo >= path_hi) {
         return SGB_ERR_ARG;
+    }
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
     if (!buf->step_count || (!all && !explicit_sel && !buf->done)) return SGB_ERR_ARG;
@@ -757,6 +799,11 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
     p.spawn_tab = c->d_spawn; p.fresh = scratch->fresh; p.list_full_only = 1;
     p.explicit_sel = explicit_sel; p.env_mask = env_mask; p.agent_mask = agent_mask;
+    if (use_sets) {
+        p.n_sets = c->n_sets;
+        p.path_lo = c->set_lo[0]; p.path_hi = c->set_hi[0];
+        for (int i = 0; i < 4; i++) { p.set_lo[i] = c->set_lo[i]; p.set_hi[i] = c->set_hi[i]; p.set_cum[i] = c->set_cum[i]; }
+    }
     // envs per warp: a warp walks its touched envs one after the other, so few envs per warp keep the dependent-load
     // chains short; about four waves of resident warps (48 per SM) was the best trade against block-launch overhead
     // (B = 65536, N = 8, 26 % done: 1 -> 0.084, 2-3 -> 0.082, 6 -> 0.085, 10 -> 0.091 ms per reset + fresh obs)
@@ -836,23 +883,26 @@ static int step_host_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* b
         return SGB_ERR_ARG;
     int rc = check_buffers(buf, 1);
     if (rc) return rc;
-    if (rs && (rs->path_lo < 0 || rs->path_hi > c->n_paths || rs->path_lo >= rs->path_hi || rs->max_tries <= 0)) return SGB_ERR_ARG;
+    if (rs && rs->path_lo != -1 && (rs->path_lo < 0 || rs->path_hi > c->n_paths || rs->path_lo >= rs->path_hi)) return SGB_ERR_ARG;
+    if (rs && rs->max_tries <= 0) return SGB_ERR_ARG;
     GUARD(c);
     // noise key: the step and the reset count as the two API calls they replace (sgb_step, sgb_reset)
     const uint64_t epoch_step = ++c->noise_epoch;
     const uint64_t epoch_reset = rs ? ++c->noise_epoch : epoch_step;
     const int D = obs_dim_of(c->cfg.obs_flags, c->cfg.k_near);
     // Chunks of whole kernel waves: one wave = one env-tile per resident warp (num_sms CTAs x warps per CTA x envs per
-    // warp), so a chunk of two waves keeps every SM busy for exactly two tile iterations and the map is staged once
-    // per SM and chunk.  Enough chunks that the copies of neighbouring chunks overlap the kernels; small batches run
-    // as one launch.
+    // warp), so a chunk of k waves keeps every SM busy for exactly k tile iterations and the map is staged once per SM
+    // and chunk.  About four waves per chunk, at least two chunks once there is work for two (measured at 65536 x 8
+    // on one B200: 14 / 7 / 5 / 4 / 2 / 1 chunks -> 1.76 / 1.62 / 1.59 / 1.57 / 1.72 / 1.72 ms per call); small
+    // batches run as one launch.
     const int g = pick_group(N);
     const int wave = c->num_sms * (cta_threads(g) / 32) * std::max(1, 32 / (N * g));
-    int waves = 2;
+    int waves = 4;
     if (const char* e = getenv("SGB_HOST_CHUNK_WAVES")) waves = std::max(1, std::min(64, atoi(e)));   // tuning knob
-    int chunk = waves * wave;
-    if (B < 2 * chunk) chunk = B;
-    const int n_chunks = (B + chunk - 1) / chunk;
+    int n_chunks = B >= 2 * wave ? std::max(2, (B + waves * wave - 1) / (waves * wave)) : 1;
+    int chunk = (B + n_chunks - 1) / n_chunks;
+    if (n_chunks > 1) chunk = (chunk + wave - 1) / wave * wave;
+    n_chunks = (B + chunk - 1) / chunk;
     rc = ensure_pipe(c, chunk, N);
     if (rc) return rc;
     if (rs) {
@@ -876,6 +926,7 @@ static int step_host_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* b
         if (sub.info) sub.info += a0 * SGB_INFO_DIM;
         if (sub.task_tries) sub.task_tries += e0;
         if (sub.task_success) sub.task_success += e0;
+        if (sub.scenario_id) sub.scenario_id += e0;
         CK(cudaMemcpyAsync(sub.action, h_action + a0 * 2, (size_t)nb * N * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
         c->noise_epoch = epoch_step;
         rc = launch_env(c, nb, N, &sub, 0, nullptr, nullptr, 1, s, 0, nullptr, e0);

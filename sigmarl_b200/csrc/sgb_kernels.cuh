@@ -154,11 +154,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
 #define SGB_HD __host__ __device__
 // work counters of the host build (sgb_debug_scan_counters): 0 segment evaluations of the centre scan, 1 of the
 // boundary scans (each covers 5 points), 2 chunk boxes tested in the votes, 3 exact crossing predicates, 4 scans
-static thread_local long long g_scan_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // host only
-#ifdef __CUDA_ARCH__
-#define SGB_COUNT(i, n)
-#else
+#ifdef SGB_TEST_HOOKS
+static thread_local long long g_scan_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // host build of the test library only
+#endif
+#if defined(SGB_TEST_HOOKS) && !defined(__CUDA_ARCH__)
 #define SGB_COUNT(i, n) (g_scan_counters[i] += (n))
+#else
+#define SGB_COUNT(i, n)
 #endif
 // (__host__ too: the host build of the same source backs the arithmetic self-test hook sgb_debug_mtv_distance; the host
 // compiler runs with -ffp-contract=off, so the plain expressions round separately there as well.)
@@ -1545,6 +1547,10 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                         rew_total = clampf(rew, -1.0f, 1.0f);
                         p.buf.reward[g] = rew_total;
                         p.buf.agent_flags[g] = (uint8_t)fl;
+                        // health word (optional): the reference asserts that positions / rewards hold no NaN / inf
+                        // (road_traffic.py:1245-1246); a non-finite term makes the sum non-finite
+                        if (p.buf.nan_flags && !(fabsf(pix + piy + ts.vabs[sl] + rew_total + d_ref_n + d_bound) < SGB_INF))
+                            atomicOr(p.buf.nan_flags, 1u);
                         if (p.buf.collide_with) p.buf.collide_with[g] = coll;
                     } else {
                         p.buf.agent_flags[g] = 0;
@@ -1681,6 +1687,10 @@ struct ResetParams {
     const float* spawn_tab;    // see place_agent
     float* fresh;              // [B,N,4] scratch for the observation refresh of fully reset envs
     int32_t list_full_only;    // 1: only fully reset envs go into `list` (they get a fresh observation)
+    // path sets (sgb_set_path_sets; cpm_mixed): n_sets > 0 -> a full reset draws the env's set, a respawn keeps it
+    int32_t n_sets;
+    int32_t set_lo[4], set_hi[4];
+    float set_cum[4];          // cumulative probabilities, set_cum[n_sets - 1] >= 1
 };
 
 // One WARP per env: bounded rejection sampling (world_state_rt_sim.py:215-311).  Agents are placed one after the other
@@ -1731,11 +1741,28 @@ __global__ void reset_kernel(const ResetParams p) {
         const float4 ps = reinterpret_cast<const float4*>(p.buf.pose)[(size_t)e * N + ln];
         qx = ps.x; qy = ps.y;
     }
-    int my_path = p.path_lo, my_point = 3;  // lane a: where agent a goes (if it is placed)
     const uint64_t env_g = (uint64_t)(p.env_offset + e);
+    // The paths this env draws from.  With path sets (cpm_mixed, world_state_rt_sim.py:313-358) a full reset draws
+    // ONE set for the whole env — multinomial(cpm_scenario_probabilities) in the reference, the env's own counter-based
+    // draw here (every lane computes the same value) — and a respawn keeps the env's set.
+    int path_lo = p.path_lo, path_hi = p.path_hi;
+    if (p.n_sets > 0) {
+        int sid;
+        if (full) {
+            const float u = (float)(draw(p.seed, p.epoch, env_g, 0, 0, 3) >> 40) * (1.0f / 16777216.0f);
+            sid = 0;
+            while (sid < p.n_sets - 1 && !(u < p.set_cum[sid])) sid++;
+            if (ln == 0) p.buf.scenario_id[e] = sid;
+        } else {
+            sid = min(max(p.buf.scenario_id[e], 0), p.n_sets - 1);
+        }
+        path_lo = p.set_lo[sid];
+        path_hi = p.set_hi[sid];
+    }
+    int my_path = path_lo, my_point = 3;  // lane a: where agent a goes (if it is placed)
     int failed = 0;
     auto candidate = [&](int a, int tr, int& path, int& point) {
-        path = p.path_lo + (int)(draw(p.seed, p.epoch, env_g, a, tr, 0) % (uint64_t)(p.path_hi - p.path_lo));
+        path = path_lo + (int)(draw(p.seed, p.epoch, env_g, a, tr, 0) % (uint64_t)(path_hi - path_lo));
         const int2 on = *reinterpret_cast<const int2*>(&paths[path].c_off);   // c_off, n_c
         int end = on.y / 2;
         // testing mode: the range starts as [3, 4) and grows by the try count (world_state_rt_sim.py:254-261)
@@ -1764,12 +1791,12 @@ __global__ void reset_kernel(const ResetParams p) {
         // tries 1, 2, ...: 32 at a time, lane l evaluates try 1 + r0 + l; a ballot picks the first feasible one,
         // exactly the try a sequential loop would accept
         bool placed = false;
-        int w_path = p.path_lo, w_point = 3;
+        int w_path = path_lo, w_point = 3;
         float w_x = 0.0f, w_y = 0.0f;
         for (int r0 = 1; r0 < p.max_tries && !placed; r0 += 32) {
             const int tr = r0 + ln;
             const bool live = tr < p.max_tries;
-            int path = p.path_lo, point = 3;
+            int path = path_lo, point = 3;
             float2 c = make_float2(0.0f, 0.0f);
             if (live) c = candidate(a, tr, path, point);
             bool ok = live;

@@ -38,7 +38,10 @@ class RoadTrafficEnv:
         self.dt = r["dt"]
         self.seed, self.env_offset, self.epoch = int(seed), int(env_offset), 0
         self.max_reset_tries = int(max_reset_tries)
-        self.path_lo, self.path_hi = self.map.default_path_range(self.config.cpm_scenario_probabilities)
+        # paths a reset draws from: one range, or (cpm_mixed with several weighted sets) a set drawn per env
+        rng = self.map.default_path_range(self.config.cpm_scenario_probabilities)
+        self.per_env_path_sets = rng is None
+        self.path_lo, self.path_hi = (-1, 0) if rng is None else rng
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._ctx = C.c_void_p()
         d = self.map.desc()
@@ -50,6 +53,10 @@ class RoadTrafficEnv:
                 _lib.check(self.L.sgb_set_lanelets(self._ctx, len(m.lanelet_off) - 1, m.lanelet_xy.ctypes.data,
                                                    m.lanelet_off.ctypes.data, m.lanelet_adj.ctypes.data), "sgb_set_lanelets")
         _lib.check(self.L.sgb_set_env_offset(self._ctx, self.env_offset), "sgb_set_env_offset")
+        if self.per_env_path_sets:
+            lo, hi, pr = self.map.path_sets(self.config.cpm_scenario_probabilities)
+            _lib.check(self.L.sgb_set_path_sets(self._ctx, len(lo), lo.ctypes.data, hi.ctypes.data, pr.ctypes.data),
+                       "sgb_set_path_sets")
         self.D = self.L.sgb_obs_dim(self._ctx)
         B, N, dev = self.B, self.N, self.device
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype, device=dev)  # noqa: E731
@@ -67,6 +74,12 @@ class RoadTrafficEnv:
         self.task_tries = z(B, dtype=torch.int32) if info else None
         self.task_success = z(B, dtype=torch.int32) if info else None
         self.n_failed = z(1, dtype=torch.int32)
+        # path set of every env (reference: ref_paths_agent_related.scenario_id - 1 on cpm_mixed, 0 elsewhere); written
+        # by the device reset when it draws a set per env, otherwise constant
+        self.scenario_id = z(B, dtype=torch.int32)
+        if not self.per_env_path_sets:
+            self.scenario_id.fill_(int(self.map.set_of_path(np.asarray([self.path_lo]))[0]))
+        self.nan_flags = z(1, dtype=torch.int32)           # sticky health word (bit 0: a step produced NaN / inf)
         self._buf = _lib.Buffers()
         for name in _lib.BUFFER_FIELDS:
             t = getattr(self, name)
@@ -136,7 +149,7 @@ class RoadTrafficEnv:
         world_state_rt_sim.py:241-242); default: the env's own range."""
         self.epoch += 1
         path_lo, path_hi = (self.path_lo, self.path_hi) if path_range is None else (int(path_range[0]), int(path_range[1]))
-        if not (0 <= path_lo < path_hi <= self.map.n_paths):
+        if path_range is not None and not (0 <= path_lo < path_hi <= self.map.n_paths):
             raise ValueError(f"path_range {path_range} outside [0, {self.map.n_paths}]")
         prep = lambda m: None if m is None else m.to(device=self.device, dtype=torch.uint8).contiguous()  # noqa: E731
         em, am = prep(env_mask), prep(agent_mask)

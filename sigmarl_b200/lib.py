@@ -16,13 +16,15 @@ SGB_REW_EXACT_SPARSE, SGB_REW_TTC, SGB_REW_DISTANCE, SGB_REW_SPARSE = 1, 2, 4, 8
  SGB_OBS_NO_DIST_CENTER, SGB_OBS_BOUNDARY_POINTS, SGB_OBS_APPLY_MASK, SGB_OBS_MASK_LANELETS) = 1, 2, 4, 8, 16, 32, 64, 128, 256
 CARRY_IDX_MASK, CARRY_FRESH_BIT = 0x3fffffff, 0x40000000   # carry.w with SGB_OBS_BOUNDARY_POINTS (see the header)
 
-# every symbol include/sigmarl_b200.h declares (tests/test_abi.py checks the two lists agree)
+# every symbol include/sigmarl_b200.h declares (tests/test_abi_and_host.py checks the two lists agree)
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
-           "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_debug_mtv_distance", "sgb_debug_pack_map",
-           "sgb_set_lanelets", "sgb_debug_current_lanelet", "sgb_debug_pack_map_blob", "sgb_debug_scan_batch", "sgb_debug_scan_counters",
-           "sgb_debug_helper", "sgb_debug_short_term", "sgb_debug_pair_batch", "sgb_set_env_offset", "sgb_step_reset_host"]
-
+           "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_set_lanelets", "sgb_set_env_offset", "sgb_step_reset_host",
+           "sgb_set_path_sets"]
+# ... and include/sigmarl_b200_test.h: host-side self-test hooks, present only in libsigmarl_b200_test.so (test suite)
+TEST_EXPORTS = ["sgb_debug_mtv_distance", "sgb_debug_pack_map", "sgb_debug_current_lanelet", "sgb_debug_pack_map_blob",
+                "sgb_debug_scan_batch", "sgb_debug_scan_counters", "sgb_debug_helper", "sgb_debug_short_term",
+                "sgb_debug_pair_batch"]
 
 class SgbError(RuntimeError):
     pass
@@ -54,7 +56,7 @@ class Config(C.Structure):
 
 
 BUFFER_FIELDS = ["pose", "aux", "path_id", "carry", "action", "step_count", "obs", "reward", "done",
-                 "agent_flags", "collide_with", "info", "task_tries", "task_success", "dbg"]
+                 "agent_flags", "collide_with", "info", "task_tries", "task_success", "dbg", "scenario_id", "nan_flags"]
 SGB_INFO_DIM = 16
 
 
@@ -83,6 +85,7 @@ def load_library():
     L.sgb_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(MapDesc), C.POINTER(Config)]
     L.sgb_destroy.argtypes = [vp]
     L.sgb_set_env_offset.argtypes = [vp, i64]
+    L.sgb_set_path_sets.argtypes = [vp, i32, vp, vp, vp]
     L.sgb_obs_dim.argtypes = [vp]
     L.sgb_max_ref_path_points.argtypes = [vp]
     L.sgb_step.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp]
@@ -103,6 +106,25 @@ def load_library():
     L.sgb_last_error.restype = C.c_char_p
     L.sgb_version.restype = C.c_int
     L.sgb_set_lanelets.argtypes = [vp, i32, vp, vp, vp]
+    _lib = L
+    return L
+
+
+_test_lib = None
+
+
+def load_test_library():
+    """TEST INFRASTRUCTURE: libsigmarl_b200_test.so = the same sources compiled with the host-side self-test hooks
+    (include/sigmarl_b200_test.h; `make -C sigmarl_b200/csrc test`).  Nothing in this package calls it."""
+    global _test_lib
+    if _test_lib is not None:
+        return _test_lib
+    path = os.environ.get("SGB_TEST_LIBRARY", os.path.join(HERE, "libsigmarl_b200_test.so"))
+    if not os.path.exists(path):
+        raise SgbError(f"{path} not found: build it with `make -C sigmarl_b200/csrc test`")
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.sgb_version.restype = C.c_int
     L.sgb_debug_current_lanelet.argtypes = [i32, vp, vp, C.c_float, C.c_float]
     L.sgb_debug_scan_batch.argtypes = [C.POINTER(MapDesc), i32, vp, vp, vp, vp, vp, C.c_float, C.c_float, i32, vp]
     L.sgb_debug_pair_batch.argtypes = [i32, vp, vp, C.c_float, C.c_float, vp]
@@ -114,7 +136,7 @@ def load_library():
     L.sgb_debug_pack_map.argtypes = [C.POINTER(MapDesc), C.POINTER(i64)]
     L.sgb_debug_mtv_distance.argtypes = [vp, vp]
     L.sgb_debug_mtv_distance.restype = C.c_float
-    _lib = L
+    _test_lib = L
     return L
 
 

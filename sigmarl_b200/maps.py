@@ -105,15 +105,34 @@ class MapLibrary:
         return (offs[scenario_id] + path_id).astype(np.int32)
 
     def default_path_range(self, cpm_scenario_probabilities=(1.0, 0.0, 0.0)):
-        """Path range a reset samples from.  ``cpm_mixed`` with probabilities (1,0,0) (``config.json:35``)
-        draws from the intersection set; mixing sets per env is not supported (the reference itself cannot
-        place >= 2 agents on the merge-in / merge-out sets, see oracle/gen_golden.py)."""
+        """Path range a reset samples from, or ``None`` when every env draws its own path set (``path_sets``).
+        ``cpm_mixed`` with probabilities (1,0,0) (``config.json:35``) draws from the intersection set."""
         if self.set_names == ["all"]:
             return self.set_range["all"]
-        p = list(cpm_scenario_probabilities)
-        if p[1] != 0 or p[2] != 0:
-            raise NotImplementedError("cpm_mixed resets are supported for cpm_scenario_probabilities=[1,0,0] only")
-        return self.set_range["intersection"]
+        p = [float(x) for x in cpm_scenario_probabilities]
+        if len(p) != len(self.set_names) or min(p) < 0 or sum(p) <= 0:
+            raise ValueError(f"cpm_scenario_probabilities must be {len(self.set_names)} non-negative weights, got {p}")
+        nz = [i for i, x in enumerate(p) if x > 0]
+        if len(nz) == 1:
+            return self.set_range[self.set_names[nz[0]]]
+        return None
+
+    def path_sets(self, cpm_scenario_probabilities=(1.0, 0.0, 0.0)):
+        """(lo[], hi[], probability[]) of the map's path sets for ``sgb_set_path_sets``: the reference draws one set
+        per env at every full reset (``world_state_rt_sim.py:313-358``)."""
+        lo = np.asarray([self.set_range[s][0] for s in self.set_names], np.int32)
+        hi = np.asarray([self.set_range[s][1] for s in self.set_names], np.int32)
+        p = np.asarray(list(cpm_scenario_probabilities) if len(self.set_names) > 1 else [1.0], np.float32)
+        return lo, hi, p
+
+    def set_of_path(self, path_id):
+        """Index of the path set a global path index belongs to (reference: scenario_id - 1 on cpm_mixed)."""
+        path_id = np.asarray(path_id)
+        out = np.zeros(path_id.shape, np.int32)
+        for k, s in enumerate(self.set_names):
+            lo, hi = self.set_range[s]
+            out[(path_id >= lo) & (path_id < hi)] = k
+        return out
 
     def desc(self):
         """ctypes ``sgb_map_desc`` over this object's numpy arrays (keep ``self`` alive while it is used)."""

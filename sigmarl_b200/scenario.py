@@ -242,6 +242,9 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
         if predef is not None:
             if init_state is None or len(predef) != self.env.N or len(init_state) != self.env.N:
                 raise ValueError("predefined_ref_path_idx needs init_state, both with one entry per agent")
+            if getattr(self.env, "per_env_path_sets", False):
+                raise NotImplementedError("predefined_ref_path_idx with several weighted cpm_scenario_probabilities: the "
+                                          "indices would count within a path set that is drawn per env")
             lo, hi = self.env.path_lo, self.env.path_hi          # indices count within the scenario's path set
             ids = torch.as_tensor([int(i) for i in predef], dtype=torch.int32) + lo
             if int(ids.min()) < lo or int(ids.max()) >= hi:

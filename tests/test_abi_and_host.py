@@ -28,6 +28,17 @@ def test_header_symbols_are_exported(L):
     for name in declared:
         assert hasattr(L, name), name
     assert L.sgb_version() == int(re.search(r"#define SGB_VERSION (\d+)", hdr).group(1))
+    # the host-side self-test hooks live in their own header and their own library (test infrastructure): the product
+    # library must not export a single one of them, the test library all of them
+    thdr = open(os.path.join(REPO, "include", "sigmarl_b200_test.h")).read()
+    hooks = sorted(set(re.findall(r"\b(sgb_debug_[a-z_]+)\s*\(", thdr)))
+    assert hooks == sorted(lib.TEST_EXPORTS) and "sgb_debug" not in hdr.replace("sgb_debug_*", "")
+    T = lib.load_test_library()
+    for name in hooks:
+        assert hasattr(T, name), name
+        with pytest.raises(AttributeError):
+            getattr(L, name)
+    assert T.sgb_version() == L.sgb_version()
 
 
 def test_struct_layouts_match_header():
@@ -177,6 +188,25 @@ def test_unsupported_flags_fail_loudly():
         MapLibrary("no_such_map")
 
 
+def test_cpm_mixed_path_sets():
+    """cpm_scenario_probabilities (road_traffic.py:333-334; world_state_rt_sim.py:313-358): one weighted set -> a plain
+    path range; several -> a set is drawn per env (ABI 128: sgb_set_path_sets, path_lo = -1)."""
+    from sigmarl_b200 import MapLibrary
+    m = MapLibrary("cpm_mixed")
+    assert m.set_range == dict(intersection=(0, 24), merge_in=(24, 28), merge_out=(28, 32))
+    assert m.default_path_range((1.0, 0.0, 0.0)) == (0, 24) and m.default_path_range([0, 1, 0]) == (24, 28)
+    assert m.default_path_range([0, 0, 2.0]) == (28, 32) and m.default_path_range([0.3, 0.3, 0.4]) is None
+    lo, hi, pr = m.path_sets([0.3, 0.3, 0.4])
+    assert lo.tolist() == [0, 24, 28] and hi.tolist() == [24, 28, 32] and np.allclose(pr, [0.3, 0.3, 0.4])
+    assert m.set_of_path([0, 23, 24, 27, 28, 31]).tolist() == [0, 0, 1, 1, 2, 2]
+    with pytest.raises(ValueError):
+        m.default_path_range([0.5, 0.5])
+    with pytest.raises(ValueError):
+        m.default_path_range([0, 0, 0])
+    e = MapLibrary("cpm_entire")
+    assert e.default_path_range([1, 0, 0]) == (0, e.n_paths) and e.path_sets()[2].tolist() == [1.0]
+
+
 def test_fixed_duration_period_equals_the_references_float_test():
     """EnvConfig.fixed_period: the step period handed to the kernel fires exactly where the reference's
     ``(timer.step * dt) % reset_agent_fixed_duration == 0`` does (road_traffic.py:1388-1393, evaluated with torch the
@@ -205,7 +235,7 @@ def test_kernel_mtv_source_matches_reference_vectors_on_the_host():
     mtv_from_vertices; every product / sum rounded on its own on both sides): bit-exact against the reference's
     get_distances_between_agents("mtv") on the 2 400 known-answer pairs — sign, exact zeros and symmetry included.
     Arithmetic self-test only; the kernel path itself is covered by the -m gpu tests."""
-    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.lib import load_test_library as load_library
     L = load_library()
     g = np.load(os.path.join(REPO, "tests", "golden", "kat", "mtv.npz"))
     v, want = np.ascontiguousarray(g["mtv_vertices"][:, :, :4], np.float32), g["mtv_dist"]
@@ -224,7 +254,7 @@ def test_every_reference_scenario_type_ships_and_packs():
     (oracle/gen_maps.py) and accepted by the library's map packer (host-only part of sgb_create): no degenerate
     polyline, at most 256 segments, and a blob that fits the shared memory of one SM next to the slot arrays."""
     import ctypes as C
-    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.lib import load_test_library as load_library
     from sigmarl_b200.maps import MapLibrary, available_scenarios
     want = ["cpm_entire", "cpm_mixed", "interchange_1", "interchange_2", "interchange_3"] + \
            [f"intersection_{i}" for i in range(1, 9)] + \
@@ -251,7 +281,7 @@ def test_kernel_current_lanelet_matches_the_references_formula_on_the_host():
     with zeros to the longest one, torch.sum((a - c) ** 2), min over points, argmin over lanelets — on random positions
     and on the lanelets' own points (exact ties between lanelets that share an end point) of every OSM map."""
     import torch
-    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.lib import load_test_library as load_library
     from sigmarl_b200.maps import MapLibrary, available_scenarios
     L = load_library()
     rng = np.random.default_rng(0)
@@ -285,7 +315,7 @@ def test_packed_blob_certificates_hold_on_every_map():
     directions of its segments, and the points must be the map's polylines (+ the 6 extension points of a centre line,
     world_state_rt.py:279-311).  Checked on the host for all 18 maps from a copy of the blob sgb_create would upload."""
     import ctypes as C
-    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.lib import load_test_library as load_library
     from sigmarl_b200.maps import MapLibrary, available_scenarios
     L = load_library()
     K, EXT = 8, 6                                   # kChunk, kExt (sgb_kernels.cuh)
@@ -370,7 +400,7 @@ def test_pruned_scans_equal_exhaustive_scans_on_the_host_for_every_map(oracle_mo
     reference's: closest index and crossing flags equal the oracle's get_perpendicular_distances / interX restatement
     exactly, the centre-line distance bit for bit, the boundary distances (reciprocal form) to 3e-6."""
     import ctypes as C
-    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.lib import load_test_library as load_library
     from sigmarl_b200.maps import MapLibrary, available_scenarios
     L, O = load_library(), oracle_mod
     ol = O.lib()
@@ -417,7 +447,7 @@ def test_kernel_helpers_match_the_references_known_answers_on_the_host():
     torch.topk(largest=False) incl. ties."""
     import ctypes as C
     import torch
-    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.lib import load_test_library as load_library
     L = load_library()
     k = np.load(os.path.join(REPO, "tests", "golden", "kat", "helpers.npz"))
     out = np.zeros(8, np.float32)
@@ -451,7 +481,7 @@ def test_rectangle_pair_crossing_on_the_host(oracle_mod):
     far apart (incl. identical / parallel / collinear ones), and the pair gate's certificate: a pair the gate skips
     (far and not collinear) never crosses."""
     import ctypes as C
-    from sigmarl_b200.lib import load_library
+    from sigmarl_b200.lib import load_test_library as load_library
     L, ol = load_library(), oracle_mod.lib()
     rng = np.random.default_rng(3)
     n = 60000

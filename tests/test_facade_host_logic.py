@@ -22,7 +22,9 @@ class _RecordingEnv:
         r = cfg.resolved(cfg.lane_width(self.map), self.map.default_n_agents)
         self.B, self.N, self.dt, self.device = int(num_envs), int(r["n_agents"]), r["dt"], torch.device("cpu")
         self.D = cfg.obs_dim(self.N)
-        self.path_lo, self.path_hi = self.map.default_path_range(cfg.cpm_scenario_probabilities)
+        rng = self.map.default_path_range(cfg.cpm_scenario_probabilities)
+        self.per_env_path_sets = rng is None
+        self.path_lo, self.path_hi = (-1, 0) if rng is None else rng
         z = lambda *s, dtype=torch.float32: torch.zeros(*s, dtype=dtype)  # noqa: E731
         B, N = self.B, self.N
         self.pose, self.aux, self.carry, self.action = z(B, N, 4), z(B, N, 4), z(B, N, 4), z(B, N, 2)

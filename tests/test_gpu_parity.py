@@ -519,8 +519,8 @@ def test_vmas_facade_drives_the_same_kernel():
 
 @pytest.mark.parametrize("B", [512, 2 * 9472 + 40])
 def test_host_buffer_step_matches_device_step(B):
-    """sgb_step_host (chunked copy / compute pipeline: chunks of two kernel waves = 9472 envs at N = 8, so the larger size
-    runs as three chunks over both streams) == sgb_step on every buffer, incl. info."""
+    """sgb_step_host (chunked copy / compute pipeline: whole kernel waves of 4736 envs at N = 8, at least two chunks from
+    two waves on — the larger size runs as chunks of 14208 + 4776 envs on two streams) == sgb_step on every buffer."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     a = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=B, device="cuda:0", seed=4, info=True)
     b = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=B, device="cuda:0", seed=4, info=True)
@@ -564,6 +564,145 @@ def test_host_buffer_step_with_reset_delivers_the_post_reset_observation(B, scen
         if d.any():     # the rows of finished envs really are fresh ones: own speed entry == |v| of the NEW pose / v_max
             assert torch.allclose(h_obs[d][..., 0], a.speed.cpu()[d], atol=1e-6)
     assert n_done > 0
+
+
+RESET_FIXTURES = sorted(os.listdir(os.path.join(os.path.dirname(__file__), "golden", "resets"))) \
+    if os.path.isdir(os.path.join(os.path.dirname(__file__), "golden", "resets")) else []
+
+
+@pytest.mark.parametrize("fixture", RESET_FIXTURES, ids=lambda f: f[:-4])
+def test_device_reset_draws_follow_the_references_distribution(fixture):
+    """SURVEY.md §8f-3.  The device reset is distribution-equivalent, not stream-equivalent, to the reference's
+    (world_state_rt_sim.py:215-358): path ~ U{paths of the env's set}, point ~ U[3, n/2), speed ~ U(0, v_max), agents placed
+    one after the other with rejection on the distance to the ones before; on cpm_mixed one path set per env ~
+    multinomial(cpm_scenario_probabilities).  Checked against (1) the law itself where it is known in closed form (first
+    agent, speeds, set frequencies) and (2) what the UNMODIFIED reference drew in 1200-2400 full resets
+    (oracle/gen_reset_draws.py -> tests/golden/resets/): two-sample tests on every agent's path / point / speed marginals
+    and on the distances between agents, i.e. on the conditional acceptance.  Every test at alpha = 1e-3 (seeds are
+    fixed on both sides, so this is a deterministic regression check, not a flaky one)."""
+    from scipy import stats
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    ALPHA = 1e-3
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resets", fixture))
+    st, N = str(g["cfg_scenario_type"]), int(g["cfg_N"])
+    probs = tuple(float(x) for x in g["cfg_probabilities"])
+    B = 16384
+    env = RoadTrafficEnv(EnvConfig(scenario_type=st, n_agents=N, cpm_scenario_probabilities=probs), num_envs=B,
+                         device="cuda:0", seed=5)
+    m = env.map
+    path, pos, speed, sid = [], [], [], []
+    for _ in range(4):
+        env.reset()
+        torch.cuda.synchronize()
+        assert int(env.n_failed) == 0
+        path.append(env.path_id.cpu().numpy()); pos.append(env.pos.cpu().numpy()); speed.append(env.speed.cpu().numpy())
+        sid.append(env.scenario_id.cpu().numpy())
+    path, pos, speed, sid = (np.concatenate(x) for x in (path, pos, speed, sid))
+    S = len(path)
+    # point index of every spawn pose: the pose IS a centre point of its path
+    point = np.full((S, N), -1, np.int64)
+    for p in range(m.n_paths):
+        c = m.center_xy[m.center_off[p]:m.center_off[p + 1]]
+        sel = np.argwhere(path == p)
+        if len(sel):
+            d = np.abs(pos[sel[:, 0], sel[:, 1]][:, None, :] - c[None]).sum(-1)
+            k = d.argmin(1)
+            assert (d[np.arange(len(k)), k] == 0).all(), "a spawn pose is exactly a centre point"
+            point[sel[:, 0], sel[:, 1]] = k
+    n_c = m.n_center[path]
+    assert (point >= 3).all() and (point < n_c // 2).all()
+    set_of = m.set_of_path(path)
+    assert (set_of == sid[:, None]).all(), "all agents of an env drive on paths of the env's set"
+    lo = np.asarray([m.set_range[s][0] for s in m.set_names])
+    n_set = np.asarray([m.set_range[s][1] - m.set_range[s][0] for s in m.set_names])
+    # reference sample in the same terms (its path ids count within the set; scenario ids are 1-based on cpm_mixed)
+    r_sid = np.maximum(g["scenario_id"].astype(np.int64) - 1, 0)
+    r_path = lo[r_sid] + g["path_id"]
+    r_point, r_speed, r_pos = g["point_id"].astype(np.int64), g["speed"], g["pos"]
+    r_nc = m.n_center[r_path]
+    assert (r_point >= 3).all() and (r_point < r_nc // 2).all()
+    u_of = lambda pt, nc: (pt - 3 + 0.5) / (nc // 2 - 3)  # noqa: E731   point index as a fraction of its range
+
+    def chi2_two_sample(a, b, n_bins):
+        ca, cb = np.bincount(a, minlength=n_bins).astype(float), np.bincount(b, minlength=n_bins).astype(float)
+        keep = (ca + cb) > 0
+        return stats.chi2_contingency(np.stack([ca[keep], cb[keep]]))[1]
+
+    # (1) closed-form parts of the law
+    if len(m.set_names) > 1 and sum(x > 0 for x in probs) > 1:
+        want = np.asarray(probs) / sum(probs)
+        assert stats.chisquare(np.bincount(sid, minlength=len(want)), want * S)[1] > ALPHA, "path-set frequencies"
+        assert stats.chisquare(np.bincount(r_sid[:, 0], minlength=len(want)), want * len(r_sid))[1] > ALPHA
+    for k in range(len(m.set_names)):                      # first agent: always feasible -> uniform path, uniform point
+        sel = sid == k
+        if sel.sum() < 200:
+            continue
+        assert stats.chisquare(np.bincount(path[sel, 0] - lo[k], minlength=n_set[k]))[1] > ALPHA, "first agent: uniform path"
+        pt, nc = point[sel, 0], n_c[sel, 0]
+        for n in np.unique(nc):                                # uniform point in [3, n/2), per path length
+            q = pt[nc == n] - 3
+            if len(q) >= 500:
+                assert stats.chisquare(np.bincount(q, minlength=n // 2 - 3))[1] > ALPHA, "first agent: uniform point"
+    assert stats.kstest(speed.ravel() / 1.0, "uniform")[1] > ALPHA, "speed ~ U(0, v_max)"
+    d_min = np.sqrt(((pos[:, :, None] - pos[:, None]) ** 2).sum(-1) + np.eye(N) * 1e6).min()
+    assert d_min >= 0.3669 and np.sqrt(((r_pos[:, :, None] - r_pos[:, None]) ** 2).sum(-1) + np.eye(N) * 1e6).min() >= 0.3669
+    # (2) against the reference's own draws, agent by agent (later agents carry the rejection's conditioning)
+    for a in range(N):
+        assert chi2_two_sample(path[:, a], r_path[:, a], m.n_paths) > ALPHA, f"agent {a}: path marginal"
+        assert stats.ks_2samp(u_of(point[:, a], n_c[:, a]), u_of(r_point[:, a], r_nc[:, a]))[1] > ALPHA, f"agent {a}: point"
+        assert stats.ks_2samp(speed[:, a], r_speed[:, a])[1] > ALPHA, f"agent {a}: speed"
+        assert chi2_two_sample(point[:, a], r_point[:, a], int(max(point.max(), r_point.max())) + 1) > ALPHA, f"agent {a}: point index"
+    for a in range(1, N):                                  # conditional acceptance: distance to the agents placed before
+        d_gpu = np.sqrt(((pos[:, a, None] - pos[:, :a]) ** 2).sum(-1)).min(-1)
+        d_ref = np.sqrt(((r_pos[:, a, None] - r_pos[:, :a]) ** 2).sum(-1)).min(-1)
+        assert stats.ks_2samp(d_gpu, d_ref)[1] > ALPHA, f"agent {a}: distance to the nearest agent placed before it"
+
+
+def test_respawns_keep_the_path_set_of_their_env():
+    """cpm_mixed with several weighted sets: a single-agent respawn draws from the set its env was given at the last
+    full reset (world_state_rt_sim.py:327-330), a full reset draws a new set."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    B, N = 4096, 2
+    env = RoadTrafficEnv(EnvConfig(scenario_type="cpm_mixed", n_agents=N, cpm_scenario_probabilities=(0.2, 0.5, 0.3)),
+                         num_envs=B, device="cuda:0", seed=9)
+    env.reset()
+    sid0 = env.scenario_id.clone()
+    assert len(torch.unique(sid0)) == 3
+    for _ in range(5):
+        before = env.pose.clone()
+        env.reset_masked(agent_mask=torch.ones(B, N, dtype=torch.bool))      # respawn every agent, no env reset
+        torch.cuda.synchronize()
+        assert torch.equal(env.scenario_id, sid0)
+        assert np.array_equal(env.map.set_of_path(env.path_id.cpu().numpy()), np.repeat(sid0.cpu().numpy()[:, None], N, 1))
+        assert float((env.pose != before).any(-1).float().mean()) > 0.8
+    env.reset_masked(env_mask=torch.ones(B, dtype=torch.bool))
+    assert not torch.equal(env.scenario_id, sid0)                             # new sets after a full reset
+    # one step + device reset: the done envs draw new sets, the others keep theirs
+    g = torch.Generator(device="cuda").manual_seed(0)
+    env.step((torch.rand(B, N, 2, device="cuda", generator=g) * 2 - 1) * torch.as_tensor(UR).cuda())
+    sid1, done = env.scenario_id.clone(), env.done.bool().clone()
+    env.reset_done()
+    assert torch.equal(env.scenario_id[~done], sid1[~done]) and bool((env.scenario_id[done] != sid1[done]).any())
+    assert np.array_equal(env.map.set_of_path(env.path_id.cpu().numpy()), np.repeat(env.scenario_id.cpu().numpy()[:, None], N, 1))
+
+
+def test_nan_flag_word_reports_non_finite_state():
+    """Optional health word (sgb_buffers.nan_flags): the reference asserts that positions hold no NaN / inf
+    (road_traffic.py:1245-1246); the step kernel sets bit 0 when a step produces a non-finite pose / reward."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    env = RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=8), num_envs=256, device="cuda:0", seed=1)
+    env.reset()
+    act = torch.zeros(256, 8, 2, device="cuda")
+    act[..., 0] = 0.5
+    env.step(act)
+    assert int(env.nan_flags) == 0
+    env.pose[17, 3, 0] = float("nan")
+    env.step(act)
+    assert int(env.nan_flags) & 1
+    env.nan_flags.zero_()
+    env.reset()
+    env.step(act)
+    assert int(env.nan_flags) == 0
 
 
 def test_library_refuses_bad_arguments():

@@ -10,7 +10,7 @@ import numpy as np, ctypes as C, sys, time
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
-from sigmarl_b200.lib import load_library
+from sigmarl_b200.lib import load_test_library as load_library
 from sigmarl_b200.maps import MapLibrary, available_scenarios
 import test_abi_and_host as T
 L=load_library()

@@ -12,7 +12,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, ctypes as C
 from oracle import oracle as O
-from sigmarl_b200.lib import load_library
+from sigmarl_b200.lib import load_test_library as load_library
 from sigmarl_b200.maps import MapLibrary
 L=load_library()
 st = sys.argv[1] if len(sys.argv) > 1 else "cpm_entire"
