@@ -27,7 +27,9 @@ from sigmarl.scenarios.road_traffic import ScenarioRoadTraffic  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden", "resets")
 CONFIGS = {
     "cpm_entire_N4": dict(st="cpm_entire", N=4, B=8, rounds=300, seed=101),
-    "cpm_mixed_N2_sets": dict(st="cpm_mixed", N=2, B=8, rounds=300, seed=102, extra=dict(cpm_scenario_probabilities=[0.3, 0.3, 0.4])),
+    # (merge-out is left out: 2 of its 31 spawn points have no feasible partner point, so the reference's unbounded
+    # rejection loop spins forever in ~6 % of the resets of a two-agent env there)
+    "cpm_mixed_N2_sets": dict(st="cpm_mixed", N=2, B=8, rounds=200, seed=102, extra=dict(cpm_scenario_probabilities=[0.4, 0.6, 0.0])),
     "on_ramp_2_N6": dict(st="on_ramp_2_multilane", N=6, B=8, rounds=150, seed=103),
 }
 

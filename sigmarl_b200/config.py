@@ -35,7 +35,6 @@ FIXED_PARAMETERS = dict(
     n_points_short_term=3,                       # road_traffic.py:273-275  (observation width, reward weights)
     sample_interval_ref_path=2,                  # road_traffic.py:316
     n_points_nearing_boundary=5,                 # road_traffic.py:296-298
-    n_observed_steps=1,                          # road_traffic.py:284-286
     is_challenging_initial_state_buffer=False,   # road_traffic.py:857-870; crashes in the reference once it replays
     max_steering=MAX_STEERING, max_speed=MAX_SPEED,   # road_traffic.py:288-294 (AGENTS table)
     lane_width=0.25,                             # helper_common.py:119: the OSM maps were parsed with it (parse_osm.py:283-306)
@@ -43,7 +42,16 @@ FIXED_PARAMETERS = dict(
 
 
 def check_fixed_parameters(get, scenario_type: str):
-    """``get(name)`` -> the caller's value or None.  Raises NotImplementedError for an unsupported value."""
+    """``get(name)`` -> the caller's value or None.  Raises NotImplementedError for an unsupported value.
+
+    ``n_observed_steps`` / ``n_stored_steps`` (road_traffic.py:280-286) are accepted at any value the reference accepts
+    (1 <= observed <= stored): the reference keeps ring buffers of ``n_stored_steps`` past states
+    (observation_provider_rt.py:49-339) but ``get_observation`` only ever reads ``get_latest()`` (:415-424, :681-919), so
+    the number of "observed" steps never reaches the observation — here as there, the latest step is what is observed."""
+    n_obs, n_sto = get("n_observed_steps"), get("n_stored_steps")
+    n_obs, n_sto = (1 if n_obs is None else int(n_obs)), (5 if n_sto is None else int(n_sto))
+    if not (1 <= n_obs <= n_sto):                 # the reference's own asserts, observation_provider_rt.py:90-98
+        raise ValueError(f"need 1 <= n_observed_steps ({n_obs}) <= n_stored_steps ({n_sto})")
     for name, want in FIXED_PARAMETERS.items():
         v = get(name)
         if v is None:

@@ -369,6 +369,12 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
         p.n_lanelets = ctx->n_lanelets;
         p.lanelet_max_len = ctx->lanelet_max_len;
     }
+    // the kernels index agents and observation elements with 32 bits
+    if ((uint64_t)B * (uint64_t)N * (uint64_t)std::max(p.D, (int32_t)SGB_INFO_DIM) >= (1ull << 32)) {
+        snprintf(g_err, sizeof g_err, "B * N * max(D, 16) = %llu does not fit 32-bit indexing: shard the batch",
+                 (unsigned long long)B * N * std::max(p.D, (int32_t)SGB_INFO_DIM));
+        return SGB_ERR_ARG;
+    }
     const int g = pick_group(N);
 #ifdef SGB_DEV_ONLY_G4
     if (p.cfg.use_mtv_distance || p.cfg.obs_flags != 0 || p.cfg.obs_noise_level > 0.0f) {

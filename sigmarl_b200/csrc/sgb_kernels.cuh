@@ -937,7 +937,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             int e = -1;
             if (active) {
                 e = p.env_list ? p.env_list[ei] : ei;
-                const size_t g = (size_t)e * N + i;
+                const uint32_t g = (uint32_t)e * (uint32_t)N + (uint32_t)i;   // B * N * D < 2^32 is checked by the host
                 float4 pose = reinterpret_cast<const float4*>(p.buf.pose)[g];
                 float delta = p.buf.aux[4 * g];
                 float4 car = reinterpret_cast<const float4*>(p.buf.carry)[g];
@@ -1013,6 +1013,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
 
         // ================= phase B: G lanes per agent, polyline queries out of the smem map =======  @region phase B glue
         const bool slot_ok = (sl_l < n_slots) && (ts.flags[slot0 + sl_l] >= 0);
+        __syncwarp();   // every lane has read the slot's "active" mark before lane 0 of the group overwrites it below
         // a warp-tile past the end of a short batch: skip it (with phase alignment it runs on dummy-safe data
         // instead, so that every warp arrives at every barrier)
         if (SYNCW <= 1 && !__any_sync(0xffffffffu, slot_ok)) continue;
@@ -1119,6 +1120,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
         // ---- rectangle-rectangle crossings: the N(N-1)/2 unordered pairs of an env are dealt round-robin to  @region pairs
         //      the env's N*G lanes; interX(vertices[lo], vertices[hi]) with lo < hi exactly as
         //      world_state_rt_sim.py:384-393, result OR-ed into both agents' masks
+        __syncwarp();   // flags / scan results of all groups of this warp are in shared memory (racecheck-clean)
         if (step_mode && !MTV && ln < EW * env_lanes) {
             const int el = ln / env_lanes;             // env within the warp
             const int q = ln - el * env_lanes;         // lane within the env
@@ -1277,7 +1279,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             }
             }
             if (slot_ok) {
-                const size_t g = (size_t)ts.env[sl] * N + i;
+                const uint32_t g = (uint32_t)ts.env[sl] * (uint32_t)N + (uint32_t)i;   // 32-bit: see launch_env
                 const float d_ref_n = ts.sc[0 * AS + sl];
                 const int idx_n = __float_as_int(ts.sc[1 * AS + sl]);
                 const float dLc = ts.sc[2 * AS + sl], dRc = ts.sc[3 * AS + sl];
@@ -1285,7 +1287,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                 const float c_dref = ts.car[0 * AS + sl], c_mL = ts.car[1 * AS + sl], c_mR = ts.car[2 * AS + sl];
                 const int c_idx = OV ? idx_of(ts.car[3 * AS + sl]) : __float_as_int(ts.car[3 * AS + sl]);
                 const bool write_obs = step_mode || p.write_obs;
-                float* o = p.buf.obs + g * D;   // written in place: 128 B per agent, L2 merges the partial sectors
+                float* o = p.buf.obs + g * (uint32_t)D;   // written in place: 128 B per agent, L2 merges the partial sectors
                 const float cs = ts.cs[sl], sn = ts.sn[sl];
                 const float2* cpts = pts + prp->c_off;
                 const int pr_nc = prp->n_c;
@@ -1307,7 +1309,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                     //      read back from pose / aux (stored in phase A by this phase-aligned group; barrier since).
                     const uint32_t ofl = cfg.obs_flags;
                     const bool bird = (ofl & SGB_OBS_BIRD_VIEW) != 0;
-                    const size_t g0 = g - i;                     // agent 0 of this env
+                    const uint32_t g0 = g - (uint32_t)i;         // agent 0 of this env
                     const float psi_i = p.buf.pose[4 * g + 2];
                     const float nwx = cfg.norm_pos_world_x, nwy = cfg.norm_pos_world_y;
                     // a global point as the observation holds it: ego frame / norm_pos, or global / pos_world
@@ -1369,7 +1371,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                         else if (kk == 1) { bj = nb_j[1]; bd = nb_d[1]; }
                         else bj = kth_nearest(ts.dij + sl * N, N, kk, &bd);
                         const int sj = base + bj;
-                        const size_t gj = g0 + bj;
+                        const uint32_t gj = g0 + (uint32_t)bj;
                         float* q = o + own + per * kk;
                         const float psi_j = p.buf.pose[4 * gj + 2];
                         if (ofl & SGB_OBS_CENTRES) {

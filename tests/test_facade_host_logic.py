@@ -245,8 +245,17 @@ def test_single_valued_parameters_are_refused_not_ignored(facade):
     """Parameters that change the step but exist at one value only (config.FIXED_PARAMETERS) fail loudly, whether they
     arrive as kwargs or on a Parameters object; their supported values pass."""
     for kw in (dict(n_points_short_term=5), dict(sample_interval_ref_path=1), dict(is_challenging_initial_state_buffer=True),
-               dict(n_observed_steps=3), dict(max_speed=2.0)):
+               dict(max_speed=2.0)):
         with pytest.raises(NotImplementedError):
+            facade(scenario_type="cpm_entire", n_agents=2, **kw)
+    # n_observed_steps: accepted wherever the reference accepts it (1 <= observed <= stored, observation_provider_rt.py:
+    # 90-98) and, as in the reference — whose get_observation only reads get_latest() — without effect on the observation
+    a = facade(scenario_type="cpm_entire", n_agents=2, n_observed_steps=3)[2]
+    b = facade(scenario_type="cpm_entire", n_agents=2)[2]
+    assert a.D == b.D and bytes(a.cfg) == bytes(b.cfg)
+    facade(scenario_type="cpm_entire", n_agents=2, n_observed_steps=5, n_stored_steps=5)
+    for kw in (dict(n_observed_steps=0), dict(n_observed_steps=6), dict(n_observed_steps=3, n_stored_steps=2)):
+        with pytest.raises(ValueError):
             facade(scenario_type="cpm_entire", n_agents=2, **kw)
     with pytest.raises(NotImplementedError):
         facade(scenario_type="roundabout_2", n_agents=2, lane_width=0.3)       # OSM boundaries depend on it

@@ -280,6 +280,14 @@ def test_observation_noise_is_uniform_additive_and_reproducible(layout):
     assert float((cc - torch.eye(3, device="cuda", dtype=cc.dtype)).abs().max()) < 0.2
 
 
+# closest-index ties per configuration of the oracle-vs-GPU free runs, as measured on a B200 (see _free_run)
+TIES_MEASURED = {
+    # every other configuration of the free runs: 0 (round 2, B200, 3.0e6 agent-steps in all)
+    "on_ramp_2_multilane|N=12|ttc|kwargs|k=2|": 1,                                                     # 1.1e-5 per agent-step
+    "on_ramp_2_multilane|N=12|ttc|kwargs|k=3|is_obs_steering=1,is_observe_ref_path_other_agents=1": 1,
+}
+
+
 def _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, **flags):
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
     O = oracle_mod
@@ -353,7 +361,14 @@ def _free_run(oracle_mod, scenario, N, rew, mode, B, k_obs, **flags):
         n_done += int(o_done.sum()); n_lane += int(w.col_lane.sum()); n_a2a += int(w.col_agents.sum())
         env.reset_done()
     assert n_done > 0 and n_lane > 0
-    assert n_ties <= 1e-4 * B * N * 30 + 2
+    # Tie budget: certified closest-index ties between CUDA libm and glibc poses.  The counts are
+    # deterministic (fixed seeds); the measured ones are listed in TIES_MEASURED and the run may use three times that
+    # (plus two), far below the 1e-4 per agent-step this used to tolerate; no configuration may exceed 2e-5 per agent-step.
+    key = f"{scenario}|N={N}|{rew}|{mode}|k={k_obs}|" + ",".join(f"{k}={int(v)}" for k, v in sorted(flags.items()))
+    print(f"TIES {key} -> {n_ties} in {B * N * 30} agent-steps ({n_ties / (B * N * 30):.2e})")
+    assert n_ties <= 3 * TIES_MEASURED.get(key, 0) + 2, f"{key}: {n_ties} ties, measured before: {TIES_MEASURED.get(key, 0)}"
+    assert n_ties <= max(2, 2e-5 * B * N * 30), f"{key}: tie rate {n_ties / (B * N * 30):.2e} > 2e-5"
+    env.n_ties = n_ties
     return env
 
 
@@ -587,8 +602,10 @@ def test_device_reset_draws_follow_the_references_distribution(fixture):
     st, N = str(g["cfg_scenario_type"]), int(g["cfg_N"])
     probs = tuple(float(x) for x in g["cfg_probabilities"])
     B = 16384
+    # (the reference's rejection loop is unbounded; the device reset gives up after max_reset_tries and reports it —
+    # with enough tries nothing is reported and the two laws coincide)
     env = RoadTrafficEnv(EnvConfig(scenario_type=st, n_agents=N, cpm_scenario_probabilities=probs), num_envs=B,
-                         device="cuda:0", seed=5)
+                         device="cuda:0", seed=5, max_reset_tries=4096)
     m = env.map
     path, pos, speed, sid = [], [], [], []
     for _ in range(4):
