@@ -134,15 +134,20 @@ def bind_to_gpu_numa(index):
     return None
 
 
-def action_sampler(kind, B, N, dev, gen):
+def action_sampler(kind, B, N, dev, gen, env=None):
     import torch
     ur = torch.tensor([1.0, 31 * np.pi / 180], device=dev)
-    if kind == "uniform":       # SURVEY.md §8d distribution (i): U(-1,1)^2 * [v_max, delta_max]
+    if kind == "uniform" or env is None:       # SURVEY.md §8d distribution (i): U(-1,1)^2 * [v_max, delta_max]
         return lambda: (torch.rand(B, N, 2, device=dev, generator=gen) * 2 - 1) * ur, "U(-1,1)^2*[1.0, 31deg]"
-    # (ii) "gentle": speeds 0.3-0.8 m/s, small steering — long episodes, agents spread along their paths
-    lo = torch.tensor([0.3, -0.15], device=dev)
-    hi = torch.tensor([0.8, 0.15], device=dev)
-    return lambda: lo + (hi - lo) * torch.rand(B, N, 2, device=dev, generator=gen), "gentle: v in U(0.3,0.8), steering in U(-0.15,0.15)"
+
+    # (ii) "gentle": pure pursuit on the 2nd short-term reference point of the observation (ego frame, obs[3:5]) with a
+    # little steering noise, speeds 0.5-0.8 m/s — agents follow their paths, episodes run long, the population spreads
+    def pursuit():
+        a = torch.rand(B, N, 2, device=dev, generator=gen)
+        o = env.obs
+        steer = torch.clamp(1.5 * torch.atan2(o[..., 4], o[..., 3]) + (a[..., 1] * 2 - 1) * 0.03, -float(ur[1]), float(ur[1]))
+        return torch.stack([0.5 + 0.3 * a[..., 0], steer], -1)
+    return pursuit, "gentle: pure pursuit on the short-term reference path, v in U(0.5,0.8)"
 
 
 def cpu_baseline_sample(scenario, n_envs, n_agents, steps, threads, rew_method="distance", seed=0):
@@ -298,7 +303,7 @@ def run_ours(args):
     env.reset()
     D = env.D
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    new_action, action_desc = action_sampler(args.actions, B, N, dev, gen)
+    new_action, action_desc = action_sampler(args.actions, B, N, dev, gen, env)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -307,7 +312,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm ----------------
-    for _ in range(W):
+    for _ in range(W if args.actions == "uniform" else max(W, 60)):     # path following: let the population spread first
         env.step(new_action())
         env.reset_done(write_obs=True)
     barrier()
