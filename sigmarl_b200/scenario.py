@@ -20,6 +20,7 @@ minimal stand-in with the same surface is used (vmas is not installable in the b
 import math
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 
 from .config import AGENT_LENGTH, AGENT_WIDTH, EnvConfig, MAX_SPEED, MAX_STEERING, check_fixed_parameters
@@ -229,6 +230,11 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
         dev = self.env.device
         m = self.env.map
         self._lanelet_ids = torch.as_tensor(m.lanelet_ids, device=dev)
+        # the reference's path_id counts within the env's path set (world_state_rt_sim.py:313-358: cpm_mixed keeps one
+        # list of paths per scenario_id); the library's is global over the map
+        gp = np.arange(m.n_paths)
+        first = np.asarray([m.set_range[s][0] for s in m.set_names], np.int32)
+        self._path_in_set = torch.as_tensor((gp - first[m.set_of_path(gp)]).astype(np.int32), device=dev)
         self._norm = dict(                                                   # road_traffic.py:587-608
             pos_world=torch.tensor([m.world_x_dim, m.world_y_dim], device=dev, dtype=torch.float32),
             v=torch.tensor(MAX_SPEED, device=dev, dtype=torch.float32),
@@ -358,7 +364,7 @@ class ScenarioRoadTrafficB200(_VmasBaseScenario):
             "is_collision_with_lanelets": (fl & _lib.SGB_FLAG_COLLIDE_LANE) != 0,
             "is_reach_goal": (fl & _lib.SGB_FLAG_EXIT) != 0,
             "ref_lanelet_ids": self._lanelet_ids[e.path_id[:, i].long()],
-            "path_id": e.path_id[:, i],
+            "path_id": self._path_in_set[e.path_id[:, i].long()],
             # no CBF: nominal == applied == the policy's (clamped) action (:1527-1545)
             "applied_action_vel": act_vel, "applied_action_steer": act_steer,
             "nominal_action_vel": act_vel, "nominal_action_steer": act_steer,

@@ -257,8 +257,8 @@ def test_mtv_distance_changes_what_it_should_and_nothing_else():
     observation are identical after one step (poses / flags bitwise); the neighbour-distance column equals the MTV distance of the
     PRE-step rectangles (host build of the kernel's own source function) for the observed neighbour."""
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
-    from sigmarl_b200.lib import load_library
-    L = load_library()
+    from sigmarl_b200.lib import load_test_library
+    L = load_test_library()    # host build of the kernel's mtv_from_vertices (test hooks live in libsigmarl_b200_test.so)
     B, N = 256, 8
     envs = [RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=N, is_use_mtv_distance=m), num_envs=B,
                            device="cuda:0", seed=21, debug=True) for m in (False, True)]
