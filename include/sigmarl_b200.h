@@ -15,6 +15,11 @@
  *     device, a [B]-byte scratch mask).
  *   - All launches are asynchronous on the `stream` passed (a cudaStream_t cast to void*; NULL = the
  *     legacy default stream).  A context is bound to one device; it is not thread-safe.
+ *   - The library's kernels are launched with programmatic stream serialization: a kernel may BEGIN
+ *     (block scheduling, staging of the read-only map) while the library's previous kernel on the
+ *     same stream drains, and waits (griddepcontrol.wait) before it reads or writes any caller
+ *     buffer — stream order of all buffer accesses is kept.  SGB_NO_PDL=1 in the environment at
+ *     sgb_create time launches them the plain way.
  *   - Layouts are row-major, env-major / agent-minor: index (b, a) -> b*N + a.
  *   - All arithmetic is fp32 with the reference's operation order (no FMA contraction on anything
  *     that feeds an argmin or a collision predicate); masks are bytes.

@@ -29,7 +29,9 @@ struct sgb_ctx {
     int64_t fresh_cap = 0;           // capacity of d_fresh in agents
     int32_t n_points = 0;            // centre points incl. extension slots (rows of d_yaw / d_spawn)
     int32_t* d_list = nullptr;       // [cap] compacted env indices for a masked refresh
-    int32_t* d_count = nullptr;      // number of entries of d_list
+    int32_t* d_count = nullptr;      // [4]: 0 / 1 the reset's list length (alternating, see ResetParams::count_next), 2 sgb_refresh's
+    int count_phase = 0;
+    bool pdl = true;                 // programmatic dependent launch between the library's kernels (SGB_NO_PDL=1 turns it off)
     int32_t list_cap = 0;
     int32_t blob_bytes = 0;
     int32_t n_paths = 0;
@@ -48,7 +50,8 @@ struct sgb_ctx {
     cudaEvent_t pipe_start = nullptr;
     bool pipe_ready = false;
     int32_t* pipe_list[2] = {nullptr, nullptr};         // per-stream reset scratch of sgb_step_reset_host
-    int32_t* pipe_count[2] = {nullptr, nullptr};
+    int32_t* pipe_count[2] = {nullptr, nullptr};         // [2] each, alternating like d_count
+    int pipe_phase[2] = {0, 0};
     int32_t pipe_list_cap = 0;
 };
 
@@ -274,7 +277,10 @@ int ensure_list(sgb_ctx* c, int B) {
     cudaFree(c->d_list);
     c->d_list = nullptr;
     CK(cudaMalloc(&c->d_list, sizeof(int32_t) * (size_t)B));
-    if (!c->d_count) CK(cudaMalloc(&c->d_count, sizeof(int32_t)));
+    if (!c->d_count) {
+        CK(cudaMalloc(&c->d_count, 4 * sizeof(int32_t)));
+        CK(cudaMemset(c->d_count, 0, 4 * sizeof(int32_t)));
+    }
     c->list_cap = B;
     return SGB_OK;
 }
@@ -285,6 +291,22 @@ int ensure_fresh(sgb_ctx* c, int64_t agents) {
     c->d_fresh = nullptr;
     CK(cudaMalloc(&c->d_fresh, sizeof(float) * 4 * (size_t)agents));
     c->fresh_cap = agents;
+    return SGB_OK;
+}
+
+// Launch of a kernel that calls pdl_wait() (sgb_kernels.cuh): with programmatic stream serialization it may begin — map
+// staging, block scheduling — while the previous kernel of the stream drains.  Harmless after anything that is not such a
+// kernel (the dependency is then the usual full one).
+template <typename P>
+int launch_chained(sgb_ctx* ctx, void (*kernel)(const P), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const P& p) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = ctx->pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&lc, kernel, p));
     return SGB_OK;
 }
 
@@ -310,9 +332,9 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     }
     const int warps = cta_threads(G) / 32;
     const int grid = std::min((n_wt + warps - 1) / warps, ctx->num_sms);
-    env_step_kernel<G, MODE, OV><<<grid, cta_threads(G), smem, st>>>(p);
+    const int rc = launch_chained(ctx, env_step_kernel<G, MODE, OV>, dim3(grid), dim3(cta_threads(G)), smem, st, p);
+    if (rc) return rc;
     ctx->launches++;
-    CK(cudaGetLastError());
     return SGB_OK;
 }
 
@@ -630,6 +652,7 @@ extern "C" int sgb_create(sgb_ctx** out, int device, const sgb_map_desc* map, co
     c->n_paths = map->n_paths;
     c->max_center = pk.max_center;
     c->blob_bytes = (int32_t)pk.blob.size();
+    if (const char* e = getenv("SGB_NO_PDL")) c->pdl = atoi(e) == 0;
     rc = init_device_state(c, pk);
     if (rc != SGB_OK) { sgb_destroy(c); return rc; }   // frees whatever was allocated before the failure
     *out = c;
@@ -735,11 +758,11 @@ extern "C" int sgb_refresh(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* 
     if (!env_mask) return launch_env(c, B, N, buf, 1, nullptr, nullptr, write_obs, st);
     rc = ensure_list(c, B);
     if (rc) return rc;
-    CK(cudaMemsetAsync(c->d_count, 0, sizeof(int32_t), st));
-    mask_to_list_kernel<<<(B + 255) / 256, 256, 0, st>>>(env_mask, B, c->d_list, c->d_count);
+    CK(cudaMemsetAsync(c->d_count + 2, 0, sizeof(int32_t), st));
+    mask_to_list_kernel<<<(B + 255) / 256, 256, 0, st>>>(env_mask, B, c->d_list, c->d_count + 2);
     c->launches++;
     CK(cudaGetLastError());
-    return launch_env(c, B, N, buf, 1, c->d_list, c->d_count, write_obs, st);
+    return launch_env(c, B, N, buf, 1, c->d_list, c->d_count + 2, write_obs, st);
 }
 
 extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, const uint8_t* agent_mask,
@@ -762,7 +785,8 @@ extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* bu
 // agents.  The context owns one set (ensure_list / ensure_fresh); the chunked host pipeline keeps one per stream.
 struct ResetScratch {
     int32_t* list = nullptr;
-    int32_t* count = nullptr;
+    int32_t* count = nullptr;   // two counters used alternately; *phase says which one this reset appends to
+    int* phase = nullptr;
     float* fresh = nullptr;
     int64_t env_first = 0;      // index of buf's env 0 within the batch the caller's env_offset refers to
 };
@@ -795,12 +819,17 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
         if (rc) return rc;
         rc = ensure_fresh(c, (int64_t)B * N);
         if (rc) return rc;
-        own.list = c->d_list; own.count = c->d_count; own.fresh = c->d_fresh;
+        own.list = c->d_list; own.count = c->d_count; own.phase = &c->count_phase; own.fresh = c->d_fresh;
         scratch = &own;
     }
-    CK(cudaMemsetAsync(scratch->count, 0, sizeof(int32_t), st));
+    // list length: two counters used alternately — this reset appends to one (cleared by the reset before it) and clears
+    // the other for the reset after it, so no memset sits between the kernels of a step -> reset -> refresh -> step chain
+    int32_t* const count_cur = scratch->count + *scratch->phase;
+    int32_t* const count_nxt = scratch->count + (*scratch->phase ^ 1);
+    *scratch->phase ^= 1;
     ResetParams p{};
-    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.list = scratch->list; p.count = scratch->count;
+    p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw; p.list = scratch->list; p.count = count_cur;
+    p.count_next = count_nxt;
     p.n_failed = n_failed; p.seed = seed; p.epoch = epoch; p.env_offset = env_offset + scratch->env_first;
     p.B = B; p.N = N; p.path_lo = path_lo; p.path_hi = path_hi; p.max_tries = max_tries; p.all = all;
     p.spawn_tab = c->d_spawn; p.fresh = scratch->fresh; p.list_full_only = 1;
@@ -816,14 +845,15 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     p.epw = std::max(1, std::min(32, (B + c->num_sms * 192 - 1) / (c->num_sms * 192)));
     if (const char* e = getenv("SGB_RESET_EPW")) p.epw = std::max(1, std::min(32, atoi(e)));   // tuning knob (profiles/kbench.py)
     const int64_t n_warps = ((int64_t)B + p.epw - 1) / p.epw;
-    reset_kernel<<<(int)((n_warps * 32 + 255) / 256), 256, 0, st>>>(p);
+    rc = launch_chained(c, reset_kernel, dim3((unsigned)((n_warps * 32 + 255) / 256)), dim3(256), 0, st, p);
+    if (rc) return rc;
     c->launches++;
     CK(cudaGetLastError());
     // carry / aux / flags of every touched env are complete (spawn table); what is left is the all-fresh observation
     // (and info block) of the FULLY reset envs — respawned agents keep their step-time observation, like the
     // reference — which needs the other agents of the env but no polyline scan
     if (!write_obs && !buf->info) return SGB_OK;
-    return launch_env(c, B, N, buf, 1, scratch->list, scratch->count, write_obs, st, 1, nullptr, scratch->env_first,
+    return launch_env(c, B, N, buf, 1, scratch->list, count_cur, write_obs, st, 1, nullptr, scratch->env_first,
                       scratch->fresh);
 }
 
@@ -874,7 +904,10 @@ static int ensure_pipe(sgb_ctx* c, int chunk_envs, int N) {
             cudaFree(c->pipe_list[i]);
             c->pipe_list[i] = nullptr;
             CK(cudaMalloc(&c->pipe_list[i], sizeof(int32_t) * (size_t)chunk_envs));
-            if (!c->pipe_count[i]) CK(cudaMalloc(&c->pipe_count[i], sizeof(int32_t)));
+            if (!c->pipe_count[i]) {
+                CK(cudaMalloc(&c->pipe_count[i], 2 * sizeof(int32_t)));
+                CK(cudaMemset(c->pipe_count[i], 0, 2 * sizeof(int32_t)));
+            }
         }
         c->pipe_list_cap = chunk_envs;
     }
@@ -942,7 +975,7 @@ static int step_host_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* b
         if (rs) {
             // reset / respawn of this chunk's envs, keyed by the GLOBAL env index: same draws as an unchunked sgb_reset
             ResetScratch sc;
-            sc.list = c->pipe_list[k & 1]; sc.count = c->pipe_count[k & 1];
+            sc.list = c->pipe_list[k & 1]; sc.count = c->pipe_count[k & 1]; sc.phase = &c->pipe_phase[k & 1];
             sc.fresh = c->d_fresh + a0 * 4; sc.env_first = e0;
             c->noise_epoch = epoch_reset;
             rc = reset_impl(c, nb, N, &sub, rs->path_lo, rs->path_hi, rs->seed, rs->epoch, rs->env_offset, rs->max_tries, 1,

@@ -121,6 +121,15 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still running — as soon as every CTA of the predecessor has executed
+// launch_dependents (or exited) and an SM has room.  Everything before pdl_wait() must touch nothing the predecessor
+// writes (here: mbarrier set-up and the bulk copy of the read-only map); pdl_wait() returns once the predecessor has
+// completed and its writes are visible.  EVERY CTA waits before it exits, so that "this grid has completed" implies "its
+// predecessors have" for the grid that comes next.  Launched without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase) {
     asm volatile(
         "{\n"
@@ -858,18 +867,25 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // refresh over a compacted env list: the number of envs is only known on the device
-    const int n_envs = p.env_list ? *p.env_count : p.B;
-    const int n_wt = (n_envs + EW - 1) / EW;    // warp-tiles
-    if ((int)blockIdx.x * kWarps >= n_wt) return;  // nothing to do for this CTA: do not even stage the map
-    if (tid == 0) {
+    pdl_launch_dependents();   // the next kernel of the stream may move in as soon as this grid's CTAs leave their SMs
+    // Stage the map BEFORE waiting for the predecessor: the blob is read-only, so its 180 KB per SM travel while the
+    // previous kernel (reset / refresh / the previous step) drains.  Only when the number of envs is known up front: over
+    // a compacted list (length only known on the device, often short) a CTA stages once it knows that it has work.
+    auto stage_map = [&]() {
         mbar_expect_tx(bar, (uint32_t)p.blob_bytes);
         const uint32_t dst = smem_u32(smem + tile_fixed_bytes(kSlots));
         for (int off = 0; off < p.blob_bytes; off += 32768) {
             int n = min(32768, p.blob_bytes - off);
             tma_bulk_g2s(dst + off, p.blob + off, (uint32_t)n, bar);
         }
-    }
+    };
+    const bool early = p.env_list == nullptr && (int)blockIdx.x * kWarps < (p.B + EW - 1) / EW;
+    if (early && tid == 0) stage_map();
+    pdl_wait();                // state buffers, env list and its length are the predecessor's outputs
+    const int n_envs = p.env_list ? *p.env_count : p.B;
+    const int n_wt = (n_envs + EW - 1) / EW;    // warp-tiles
+    if ((int)blockIdx.x * kWarps >= n_wt) return;  // nothing to do for this CTA (then nothing was staged either)
+    if (!early && tid == 0) stage_map();
     bool map_ready = false;
 
     constexpr int AS = kSlots;                  // slot stride of the SoA arrays (all warps)
@@ -1677,7 +1693,8 @@ struct ResetParams {
     const unsigned char* blob;
     const float* yaw;
     int32_t* list;             // [B] out: compacted indices of the envs that need a refresh
-    int32_t* count;            // out: number of entries (zeroed by the host before the launch)
+    int32_t* count;            // out: number of entries (zero on entry: cleared by the previous reset, see count_next)
+    int32_t* count_next;       // the counter the NEXT reset on this scratch appends to: cleared here (no memset between the kernels)
     int32_t* n_failed;
     uint64_t seed, epoch;
     int64_t env_offset;
@@ -1702,6 +1719,9 @@ struct ResetParams {
 // agent (parallel loads from the spawn table, parallel stores).  Crowded maps need many tries per agent (on-ramp /
 // roundabout with 12 agents: the sequential one-thread-per-env version spent 0.14 ms per step there).
 __global__ void reset_kernel(const ResetParams p) {
+    pdl_launch_dependents();
+    pdl_wait();                // done / flags / poses are the step kernel's outputs
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.count_next) *p.count_next = 0;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int ln = threadIdx.x & 31;
     const int N = p.N;
