@@ -221,13 +221,15 @@ def rollout_record(args, dev, world, rank, barrier):
     import torch
     import torch.distributed as dist
     from sigmarl_b200 import EnvConfig, RoadTrafficEnv
-    from sigmarl_b200.rollout import RolloutBuffer, all_gather_advantages, collect, compute_gae
+    from sigmarl_b200.rollout import RolloutBuffer, all_gather_advantages, collect, compute_gae, gae_allgather
 
     B, N, T = args.rollout_envs, args.agents, args.horizon
     env = RoadTrafficEnv(EnvConfig(scenario_type=args.scenario, n_agents=N, mode="params", rew_method=args.rew_method),
                          num_envs=B, device=dev, seed=args.seed, env_offset=rank * B)
     env.reset()
-    buf = RolloutBuffer(T, B, N, env.D, dev, world=world, rank=rank)
+    # gather buffers in symmetric (peer-mapped) memory: GAE and the all-gather are ONE kernel (sgb_gae_allgather)
+    fused = world > 1 and not args.nccl_gather
+    buf = RolloutBuffer(T, B, N, env.D, dev, world=world, rank=rank, symmetric=fused)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     sample, _ = action_sampler(args.actions, B, N, dev, gen)
     acts = torch.stack([sample() for _ in range(T)])
@@ -240,29 +242,53 @@ def rollout_record(args, dev, world, rank, barrier):
         step["t"] += 1
         return a
 
-    def one():
+    def one(mode):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         collect(env, policy, buf)
         ev[1].record()
-        compute_gae(buf, 0.99, 0.9)
-        ev[2].record()
-        all_gather_advantages(buf)
+        if mode == "fused":
+            ev[2].record()
+            gae_allgather(buf, 0.99, 0.9, multicast=args.multicast)
+        else:
+            compute_gae(buf, 0.99, 0.9)
+            ev[2].record()
+            all_gather_advantages(buf)
         ev[3].record()
         return ev
 
-    one()
+    one("nccl")
+    check = None
+    if fused:
+        # the fused kernel must leave exactly what GAE + NCCL all-gather leave
+        torch.cuda.synchronize()
+        want = (buf.adv_all.clone(), buf.target_all.clone())
+        buf.adv_all.zero_(); buf.target_all.zero_()
+        gae_allgather(buf, 0.99, 0.9, multicast=args.multicast)
+        torch.cuda.synchronize()
+        same = torch.tensor([int(torch.equal(want[0], buf.adv_all) and torch.equal(want[1], buf.target_all))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        check = bool(int(same))
+        if not check:
+            raise SystemExit("sgb_gae_allgather differs from sgb_gae + NCCL all_gather")
+        del want
+        one("fused")
     barrier()
     K = args.rollouts
     l0 = env.launches
-    evs = [one() for _ in range(K)]
-    barrier()
-    t = torch.tensor([sum(e[0].elapsed_time(e[3]) for e in evs), sum(e[0].elapsed_time(e[1]) for e in evs),
-                      sum(e[1].elapsed_time(e[2]) for e in evs), sum(e[2].elapsed_time(e[3]) for e in evs)],
-                     device=dev, dtype=torch.float64) * 1e-3
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_all, t_col, t_gae, t_ag = [float(x) for x in t]
+
+    def timed(mode):
+        evs = [one(mode) for _ in range(K)]
+        barrier()
+        t = torch.tensor([sum(e[0].elapsed_time(e[3]) for e in evs), sum(e[0].elapsed_time(e[1]) for e in evs),
+                          sum(e[1].elapsed_time(e[2]) for e in evs), sum(e[2].elapsed_time(e[3]) for e in evs)],
+                         device=dev, dtype=torch.float64) * 1e-3
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    t_all, t_col, t_gae, t_ag = timed("fused" if fused else "nccl")
+    launches = env.launches - l0 + K
     gathered = 2 * T * B * N * 4 * world            # advantage + value target of every rank, received by each rank
     rec = {"value": world * B * N * T * K / t_all, "unit": "agent-steps/s",
            "workload": f"{args.scenario} num_envs={B} n_agents={N} per GPU, T={T} (BASELINE configs[4] per-GPU shape): rollout + GAE "
@@ -271,11 +297,20 @@ def rollout_record(args, dev, world, rank, barrier):
            "breakdown_ms": {"collect": 1e3 * t_col / K, "gae": 1e3 * t_gae / K, "all_gather": 1e3 * t_ag / K},
            "all_gather_share": t_ag / t_all, "gathered_bytes_per_rank": gathered,
            "all_gather_gbs_per_rank": (gathered * (world - 1) / world) / (t_ag / K) / 1e9 if world > 1 and t_ag > 0 else None,
-           "collective": "NCCL all_gather_into_tensor, in place ([world, T, B, N] buffers; GAE writes this rank's slot)" if world > 1
-                         else "none at 1 GPU (the gather is the identity)",
-           "gpu_launches": env.launches - l0 + K,
+           "collective": ("sgb_gae_allgather: GAE fused with the all-gather — one kernel stores every value into all ranks' "
+                          "[world, T, B, N] buffers over NVLink peer memory (torch symmetric memory; "
+                          + ("NVSwitch multicast stores" if args.multicast else "one store per peer")
+                          + "), barriers before / after; breakdown_ms.gae is 0 and all_gather is the fused kernel") if fused
+                         else ("NCCL all_gather_into_tensor, in place ([world, T, B, N] buffers; GAE writes this rank's slot)" if world > 1
+                               else "none at 1 GPU (the gather is the identity)"),
+           "gpu_launches": launches,
            "policy": "pre-generated actions / values (the NN forward is outside the path)",
            "gae_checked_against": "numpy restatement of the TorchRL recurrence (TorchRL is not installable here)"}
+    if fused:
+        n_all, n_col, n_gae, n_ag = timed("nccl")
+        rec["fused_equals_gae_plus_nccl_all_gather"] = check
+        rec["nccl_two_step_ms"] = {"gae": 1e3 * n_gae / K, "all_gather": 1e3 * n_ag / K,
+                                   "note": "same rollouts with sgb_gae + NCCL all_gather_into_tensor, for comparison"}
     env.close()
     del env, buf, acts
     torch.cuda.empty_cache()
@@ -424,6 +459,9 @@ def main():
     ap.add_argument("--ref-envs", type=int, default=4096, help="bounded sample for the CPU arm")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="rollout record: sgb_gae + NCCL all-gather instead of the fused kernel")
+    ap.add_argument("--multicast", type=lambda v: {"auto": None, "1": True, "0": False}[v], default=None,
+                    help="fused GAE + all-gather: 1 = NVSwitch multicast stores, 0 / auto = one store per peer (default)")
     ap.add_argument("--no-rollout", action="store_true", help="skip the rollout + GAE + all-gather sub-record")
     ap.add_argument("--rollout-envs", type=int, default=32768, help="envs per GPU of the rollout sub-record")
     ap.add_argument("--rollouts", type=int, default=3, help="timed rollouts of the sub-record")

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SGB_VERSION 128
+#define SGB_VERSION 129
 #define SGB_MAX_AGENTS 32       /* agents per env (collide_with is a 32-bit mask) */
 #define SGB_N_SHORT_TERM 3      /* n_points_short_term   (road_traffic.py:273-275) */
 
@@ -302,6 +302,21 @@ int sgb_step_reset_host(sgb_ctx* ctx, int32_t B, int32_t N, const sgb_buffers* b
  * advantage normalisation) and the done expansion of mappo_cavs.py:342-355. */
 int sgb_gae(int32_t T, int32_t B, int32_t N, const float* reward, const float* value, const float* next_value,
             const uint8_t* done, float gamma, float lmbda, float* adv, float* target, void* stream);
+
+/* The same scan fused with the design's one collective (mappo_cavs.py:357-378 consumes the result): the
+ * all-gather of advantage / value target at PPO-update time.  Every rank holds [world,T,B,N] gather buffers in memory that
+ * is mapped into its peers (CUDA IPC / cuMem symmetric memory; one process per GPU of ONE node); `adv_peers[w]` /
+ * `target_peers[w]` (host arrays of `world` device pointers) are the bases of rank w's buffers AS MAPPED ON THIS DEVICE
+ * (w == rank: the local ones).  Each value is stored, as it is computed, into slot `rank` of every rank's buffer over
+ * NVLink; with `adv_multicast` / `target_multicast` (NVLS multicast mappings of the same buffers, both or neither) ONE
+ * multimem store per value is replicated by the switch instead.  No staging copy and no separate collective.
+ * Ordering is the caller's: a cross-rank barrier on `stream` BEFORE the call (every rank is done reading the previous
+ * contents) and AFTER it (all ranks' stores have landed) — e.g. torch symmetric memory's `handle.barrier()`.
+ * world == 1 degenerates to sgb_gae into slot 0. */
+int sgb_gae_allgather(int32_t T, int32_t B, int32_t N, const float* reward, const float* value, const float* next_value,
+                      const uint8_t* done, float gamma, float lmbda, int32_t world, int32_t rank,
+                      float* const* adv_peers, float* const* target_peers, float* adv_multicast, float* target_multicast,
+                      void* stream);
 
 /* Number of kernels this context has launched since creation (for launch accounting in benchmarks). */
 int64_t sgb_launch_count(const sgb_ctx* ctx);

@@ -1022,3 +1022,46 @@ extern "C" int sgb_gae(int32_t T, int32_t B, int32_t N, const float* reward, con
     CK(cudaGetLastError());
     return SGB_OK;
 }
+
+extern "C" int sgb_gae_allgather(int32_t T, int32_t B, int32_t N, const float* reward, const float* value,
+                                 const float* next_value, const uint8_t* done, float gamma, float lmbda, int32_t world,
+                                 int32_t rank, float* const* adv_peers, float* const* target_peers, float* adv_multicast,
+                                 float* target_multicast, void* stream) {
+    if (T <= 0 || B <= 0 || N <= 0 || !reward || !value || !next_value || !done) return SGB_ERR_ARG;
+    if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !adv_peers || !target_peers) return SGB_ERR_ARG;
+    if ((adv_multicast == nullptr) != (target_multicast == nullptr)) return SGB_ERR_ARG;
+    GaePeers peers{};
+    for (int w = 0; w < world; w++) {
+        if (!adv_peers[w] || !target_peers[w]) return SGB_ERR_ARG;
+        peers.adv[w] = adv_peers[w];
+        peers.tgt[w] = target_peers[w];
+    }
+    peers.adv_mc = adv_multicast;
+    peers.tgt_mc = target_multicast;
+    const int bn = B * N;
+    int dev = 0;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, reward) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device;
+    else if (cudaGetDevice(&dev) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaGetDevice");
+    DeviceGuard guard(dev);
+    if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+    // 16-byte path: four consecutive columns per thread belong to one env and every base is 16-byte aligned
+    bool vec = (N % 4 == 0);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    vec = vec && al16(reward) && al16(value) && al16(next_value);
+    for (int w = 0; w < world; w++) vec = vec && al16(adv_peers[w]) && al16(target_peers[w]);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = vec ? bn / 4 : bn;
+    const int grid = (threads + 255) / 256;
+    if (adv_multicast)
+        gae_allgather_kernel<true, 1><<<(bn + 255) / 256, 256, 0, st>>>(T, bn, N, reward, value, next_value, done, gamma, lmbda,
+                                                                        peers, world, rank);
+    else if (vec)
+        gae_allgather_kernel<false, 4><<<grid, 256, 0, st>>>(T, bn, N, reward, value, next_value, done, gamma, lmbda, peers,
+                                                             world, rank);
+    else
+        gae_allgather_kernel<false, 1><<<grid, 256, 0, st>>>(T, bn, N, reward, value, next_value, done, gamma, lmbda, peers,
+                                                             world, rank);
+    CK(cudaGetLastError());
+    return SGB_OK;
+}

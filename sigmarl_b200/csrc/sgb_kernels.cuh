@@ -1887,6 +1887,81 @@ __global__ void gae_kernel(int T, int BN, int N, const float* __restrict__ rewar
     }
 }
 
+// The same scan FUSED with the design's one collective (all-gather of advantage / value target at
+// PPO-update time): every rank keeps [world, T, B*N] gather buffers in peer-mapped (symmetric) memory and each value is
+// stored, as soon as it exists, into slot `rank` of EVERY rank's buffer — plain stores to the peers' mappings over
+// NVLink / NVSwitch, or ONE multimem.st to the buffers' multicast address, which the switch replicates to all ranks
+// (NVLS).  No staging copy, no separate collective launch; the scan's loads and the remote stores overlap element by
+// element.  Ordering is the caller's job: a cross-rank barrier on the stream before (everybody is done reading the last
+// rollout's values) and after (all stores have landed) — sgb_gae_allgather in the header.
+constexpr int kMaxPeers = 16;
+struct GaePeers {
+    float* adv[kMaxPeers];      // base of rank w's [world, T, BN] advantage buffer as mapped on THIS device
+    float* tgt[kMaxPeers];
+    float* adv_mc;              // multicast mapping of the same buffers (NULL: store to every peer)
+    float* tgt_mc;
+};
+__device__ __forceinline__ void multimem_st(float* p, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+// V = 4: one thread scans four consecutive (env, agent) columns (same env: N % 4 == 0) with 16-byte loads and stores —
+// a warp's store to a peer is then 512 contiguous bytes, which the links carry better than 128 (measured on 4 B200s:
+// see DESIGN.md §5).  V = 1 is the general layout.
+template <bool MC, int V>
+__global__ void __launch_bounds__(256) gae_allgather_kernel(int T, int BN, int N, const float* __restrict__ reward,
+                                                            const float* __restrict__ value,
+                                                            const float* __restrict__ next_value,
+                                                            const uint8_t* __restrict__ done, float gamma, float lmbda,
+                                                            const GaePeers peers, int world, int rank) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) * V;
+    if (k >= BN) return;
+    const int b = k / N;
+    const int B = BN / N;
+    const size_t slot = (size_t)rank * T * BN;
+    float a[V];
+#pragma unroll
+    for (int j = 0; j < V; j++) a[j] = 0.0f;
+#pragma unroll 2
+    for (int t = T - 1; t >= 0; t--) {
+        const size_t o = (size_t)t * BN + k;
+        const float nd = 1.0f - (float)done[(size_t)t * B + b];
+        float r[V], v[V], nv[V], tg[V];
+        if (V == 4) {
+            *reinterpret_cast<float4*>(r) = *reinterpret_cast<const float4*>(reward + o);
+            *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(value + o);
+            *reinterpret_cast<float4*>(nv) = *reinterpret_cast<const float4*>(next_value + o);
+        } else {
+            r[0] = reward[o]; v[0] = value[o]; nv[0] = next_value[o];
+        }
+#pragma unroll
+        for (int j = 0; j < V; j++) {
+            const float delta = r[j] + gamma * nv[j] * nd - v[j];
+            a[j] = delta + gamma * lmbda * nd * a[j];
+            tg[j] = a[j] + v[j];
+        }
+        if (MC) {
+#pragma unroll
+            for (int j = 0; j < V; j++) {
+                multimem_st(peers.adv_mc + slot + o + j, a[j]);
+                multimem_st(peers.tgt_mc + slot + o + j, tg[j]);
+            }
+        } else {
+            for (int w = 0; w < world; w++) {
+                const int dst = (rank + w) % world;          // own copy first, then round the ring: spreads the links
+                if (V == 4) {
+                    *reinterpret_cast<float4*>(peers.adv[dst] + slot + o) = *reinterpret_cast<const float4*>(a);
+                    *reinterpret_cast<float4*>(peers.tgt[dst] + slot + o) = *reinterpret_cast<const float4*>(tg);
+                } else {
+                    peers.adv[dst][slot + o] = a[0];
+                    peers.tgt[dst][slot + o] = tg[0];
+                }
+            }
+        }
+    }
+}
+
 // byte mask -> compacted index list (order is irrelevant: envs are independent)
 __global__ void mask_to_list_kernel(const uint8_t* mask, int B, int32_t* list, int32_t* count) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;

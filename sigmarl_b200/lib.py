@@ -20,7 +20,7 @@ CARRY_IDX_MASK, CARRY_FRESH_BIT = 0x3fffffff, 0x40000000   # carry.w with SGB_OB
 EXPORTS = ["sgb_create", "sgb_destroy", "sgb_obs_dim", "sgb_max_ref_path_points", "sgb_step", "sgb_refresh",
            "sgb_place", "sgb_reset", "sgb_reset_all", "sgb_reset_masked", "sgb_step_host", "sgb_gae", "sgb_launch_count", "sgb_map_bytes",
            "sgb_status_string", "sgb_last_error", "sgb_version", "sgb_set_lanelets", "sgb_set_env_offset", "sgb_step_reset_host",
-           "sgb_set_path_sets"]
+           "sgb_set_path_sets", "sgb_gae_allgather"]
 # ... and include/sigmarl_b200_test.h: host-side self-test hooks, present only in libsigmarl_b200_test.so (test suite)
 TEST_EXPORTS = ["sgb_debug_mtv_distance", "sgb_debug_pack_map", "sgb_debug_current_lanelet", "sgb_debug_pack_map_blob",
                 "sgb_debug_scan_batch", "sgb_debug_scan_counters", "sgb_debug_helper", "sgb_debug_short_term",
@@ -97,6 +97,7 @@ def load_library():
     L.sgb_step_host.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, vp, vp, vp]
     L.sgb_step_reset_host.argtypes = [vp, i32, i32, C.POINTER(Buffers), vp, vp, vp, vp, i32, i32, u64, u64, i64, i32, vp, vp]
     L.sgb_gae.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
+    L.sgb_gae_allgather.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp, vp]
     L.sgb_launch_count.argtypes = [vp]
     L.sgb_launch_count.restype = i64
     L.sgb_map_bytes.argtypes = [vp]

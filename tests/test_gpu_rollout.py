@@ -73,3 +73,35 @@ def test_in_place_collect_equals_copying_collect():
     assert a[0].done.sum() > 0
     assert float(a[0].action[..., 0].abs().max()) > 1.2        # raw (unclamped) actions were stored ...
     assert float(env.action[..., 0].abs().max()) <= 1.0        # ... while the env stepped on the clamped copy
+
+
+@pytest.mark.parametrize("T,B,N", [(32, 257, 5), (32, 257, 8)])
+def test_fused_gae_allgather_on_one_rank_equals_gae(T, B, N):
+    """sgb_gae_allgather with world == 1 (the only peer is this rank's own buffer) leaves exactly what sgb_gae leaves;
+    N = 5: one column per thread, N = 8: four columns per thread with 16-byte loads / stores."""
+    from sigmarl_b200.rollout import RolloutBuffer, compute_gae, gae_allgather
+    g = torch.Generator(device="cuda").manual_seed(4)
+    buf = RolloutBuffer(T, B, N, 4, "cuda:0")
+    for name in ("reward", "value", "next_value"):
+        getattr(buf, name).copy_(torch.randn(T, B, N, device="cuda", generator=g))
+    buf.done.copy_((torch.rand(T, B, device="cuda", generator=g) < 0.1).to(torch.uint8))
+    a, t = compute_gae(buf, 0.99, 0.9)
+    a, t = a.clone(), t.clone()
+    buf.adv_all.zero_(); buf.target_all.zero_()
+    a_all, t_all = gae_allgather(buf, 0.99, 0.9)
+    assert torch.equal(a_all[0], a) and torch.equal(t_all[0], t)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one node (peer memory)")
+@pytest.mark.parametrize("multicast", ["0", "1"])
+def test_fused_gae_allgather_across_two_gpus_equals_gae_plus_nccl_all_gather(multicast):
+    """Two ranks, symmetric-memory gather buffers: the fused kernel (peer stores / NVSwitch multicast stores) leaves in
+    EVERY rank's buffers bit for bit what sgb_gae + NCCL all_gather_into_tensor leave (tests/tools/fused_gather_check.py)."""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(repo, "tests", "tools", "fused_gather_check.py"), multicast]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=repo)
+    assert out.returncode == 0 and out.stdout.count("FUSED-GATHER-OK") == 2, out.stdout[-2000:] + out.stderr[-4000:]
