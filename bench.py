@@ -229,7 +229,22 @@ def rollout_record(args, dev, world, rank, barrier):
     env.reset()
     # gather buffers in symmetric (peer-mapped) memory: GAE and the all-gather are ONE kernel (sgb_gae_allgather)
     fused = world > 1 and not args.nccl_gather
-    buf = RolloutBuffer(T, B, N, env.D, dev, world=world, rank=rank, symmetric=fused)
+    fused_note = None
+    if fused:
+        # symmetric memory needs peer mappings between all GPUs of the node; if the box refuses them, every rank falls
+        # back to sgb_gae + NCCL all-gather together (still GPU kernels + NCCL; the record says which one ran)
+        try:
+            buf = RolloutBuffer(T, B, N, env.D, dev, world=world, rank=rank, symmetric=True)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:      # noqa: BLE001
+            fused_note = f"symmetric memory unavailable ({type(e).__name__}: {str(e)[:120]})"
+            ok = torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok):
+            fused = False
+            fused_note = fused_note or "symmetric memory unavailable on another rank"
+    if not fused:
+        buf = RolloutBuffer(T, B, N, env.D, dev, world=world, rank=rank)
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     sample, _ = action_sampler(args.actions, B, N, dev, gen)
     acts = torch.stack([sample() for _ in range(T)])
@@ -306,6 +321,8 @@ def rollout_record(args, dev, world, rank, barrier):
            "gpu_launches": launches,
            "policy": "pre-generated actions / values (the NN forward is outside the path)",
            "gae_checked_against": "numpy restatement of the TorchRL recurrence (TorchRL is not installable here)"}
+    if fused_note:
+        rec["fused_gather_note"] = fused_note
     if fused:
         n_all, n_col, n_gae, n_ag = timed("nccl")
         rec["fused_equals_gae_plus_nccl_all_gather"] = check

@@ -790,14 +790,18 @@ SGB_HD __forceinline__ int kth_nearest(const float* dij, int N, int kk, float* d
     return bj;
 }
 
-// helper_scenario.py:892-957 short-term reference path (n_points_shift = 1, sample interval 2)
+// helper_scenario.py:892-957 short-term reference path (n_points_shift = 1, sample interval 2).  Loop paths wrap with
+// (fi + 1) % n_c for fi >= n_c - 1 (:941-946).  idx is a closest-point index, 1 <= idx <= n_c - 1, so fi + 1 <= n_c + 5 <
+// 2 n_c (pack_map refuses paths with fewer than 8 points) and the modulo is ONE conditional subtraction — an integer
+// remainder by a run-time divisor costs ~25 instructions, and this one was unrolled into 2.7 KB of a kernel that lives
+// on its instruction cache.  The clamp keeps a corrupt carry index inside the path's points + extension slots.
+SGB_HD __forceinline__ int short_term_index(int fi, int n_c, bool is_loop) {
+    if (is_loop && fi >= n_c - 1) { fi += 1; fi = fi >= n_c ? fi - n_c : fi; }
+    return max(0, min(fi, n_c + kExt - 1));
+}
 SGB_HD __forceinline__ void short_term(const float2* __restrict__ cpts, int n_c, bool is_loop, int idx, float2 out[3]) {
 SGB_UNROLL
-    for (int k = 0; k < SGB_N_SHORT_TERM; k++) {
-        int fi = 2 * k + idx + 1;
-        if (is_loop && fi >= n_c - 1) fi = (fi + 1) % n_c;
-        out[k] = cpts[fi];
-    }
+    for (int k = 0; k < SGB_N_SHORT_TERM; k++) out[k] = cpts[short_term_index(2 * k + idx + 1, n_c, is_loop)];
 }
 
 // splitmix64 finaliser: the counter-based generator of the reset kernels and of the observation noise
@@ -928,6 +932,9 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
         return lo | ((lo + 1 + (pi - lo * (2 * N - 1 - lo) / 2)) << 8);
     };
     const int pair_first = (N >= 2) ? decode_pair(min(ln % env_lanes, N * (N - 1) / 2 - 1)) : 0;
+    // first lane of every env of the warp: slot of the env's agent 0 (phase D), -1 for all other lanes — computed once,
+    // the two integer divisions by a run-time divisor cost 44 instructions per tile iteration otherwise
+    const int lead_slot = (ln < EW * env_lanes && ln % env_lanes == 0) ? slot0 + (ln / env_lanes) * N : -1;
     const int stride_wt = gridDim.x * kWarps;
     const int n_iter = SYNCW > 1 ? (n_wt - (int)blockIdx.x * kWarps + stride_wt - 1) / stride_wt : (1 << 30);
     for (int it = 0, wt = blockIdx.x * kWarps + w; it < n_iter && (SYNCW > 1 || wt < n_wt); it++, wt += stride_wt) {
@@ -1476,9 +1483,7 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
                         float qx, qy;
                         float* dst;
                         if (t < 3) {
-                            int fi = 2 * t + o_idx + 1;                                  // helper_scenario.py:928-946
-                            if (pr_loop && fi >= pr_nc - 1) fi = (fi + 1) % pr_nc;
-                            const float2 q = cpts[fi];
+                            const float2 q = cpts[short_term_index(2 * t + o_idx + 1, pr_nc, pr_loop)];   // helper_scenario.py:928-946
                             qx = q.x; qy = q.y;
                             dst = o + 1 + 2 * t;
                         } else {
@@ -1607,9 +1612,9 @@ __global__ void __launch_bounds__(cta_threads(G), 1) env_step_kernel(const Param
             const int myfl = (slot_ok && lane == 0) ? ts.flags[sl] : 0;
             const uint32_t b_hit = __ballot_sync(0xffffffffu, (myfl & (int)(SGB_FLAG_COLLIDE_AGENT | SGB_FLAG_COLLIDE_LANE)) != 0);
             const uint32_t b_exit = __ballot_sync(0xffffffffu, (myfl & (int)SGB_FLAG_EXIT) != 0);
-            if (ln < EW * env_lanes && ln % env_lanes == 0 && ts.flags[slot0 + (ln / env_lanes) * N] >= 0) {
+            if (lead_slot >= 0 && ts.flags[lead_slot] >= 0) {
                 const uint32_t em = (env_lanes >= 32 ? 0xffffffffu : ((1u << env_lanes) - 1u)) << ln;   // this env's lanes
-                const int e = ts.env[slot0 + (ln / env_lanes) * N];
+                const int e = ts.env[lead_slot];
                 const int tries = __popc((b_hit | b_exit) & em);                                                // :1029-1035
                 const int succ = __popc(b_exit & em);                                                           // :998-1002
                 if (p.buf.task_tries && tries) p.buf.task_tries[e] += tries;
