@@ -8,6 +8,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler is attached
+
 #include "sgb_kernels.cuh"
 #ifdef SGB_TEST_HOOKS
 #include "../../include/sigmarl_b200_test.h"
@@ -80,6 +82,13 @@ struct DeviceGuard {
         if (prev >= 0 && prev != dev) cudaSetDevice(prev);
     }
 };
+// NVTX range over an API call (the reference's counterpart: timer.step_duration, road_traffic.py:955-962): shows up as
+// "sgb_step" / "sgb_reset" / ... on the CPU timeline of nsys / ncu --nvtx, brackets the launches the call enqueues
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 #define GUARD(ctx)                                                   \
     DeviceGuard _guard((ctx)->device);                               \
     if (_guard.err != cudaSuccess) return cuda_fail(_guard.err, "cudaSetDevice(context device)")
@@ -742,6 +751,7 @@ extern "C" int sgb_step(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf
     int rc = check_buffers(buf, 1);
     if (rc) return rc;
     GUARD(c);
+    NvtxRange _nvtx("sgb_step");
     c->noise_epoch++;
     return launch_env(c, B, N, buf, 0, nullptr, nullptr, 1, (cudaStream_t)stream);
 }
@@ -753,6 +763,7 @@ extern "C" int sgb_refresh(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* 
     if (rc) return rc;
     if (write_obs && !buf->obs) return SGB_ERR_ARG;
     GUARD(c);
+    NvtxRange _nvtx("sgb_refresh");
     c->noise_epoch++;
     cudaStream_t st = (cudaStream_t)stream;
     if (!env_mask) return launch_env(c, B, N, buf, 1, nullptr, nullptr, write_obs, st);
@@ -771,6 +782,7 @@ extern "C" int sgb_place(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* bu
     int rc = check_buffers(buf, 0);
     if (rc) return rc;
     GUARD(c);
+    NvtxRange _nvtx("sgb_place");
     PlaceParams p{};
     p.cfg = c->cfg; p.buf = *buf; p.blob = c->d_blob; p.yaw = c->d_yaw;
     p.agent_mask = agent_mask; p.path = path; p.point = point; p.speed = speed; p.B = B; p.N = N;
@@ -811,6 +823,7 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
     if (!buf->step_count || (!all && !explicit_sel && !buf->done)) return SGB_ERR_ARG;
     if (write_obs && !buf->obs) return SGB_ERR_ARG;
     GUARD(c);
+    NvtxRange _nvtx("sgb_reset");
     ResetScratch own;
     if (!scratch) {
         c->noise_epoch++;
@@ -925,6 +938,7 @@ static int step_host_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* b
     if (rs && rs->path_lo != -1 && (rs->path_lo < 0 || rs->path_hi > c->n_paths || rs->path_lo >= rs->path_hi)) return SGB_ERR_ARG;
     if (rs && rs->max_tries <= 0) return SGB_ERR_ARG;
     GUARD(c);
+    NvtxRange _nvtx("sgb_step_host");
     // noise key: the step and the reset count as the two API calls they replace (sgb_step, sgb_reset)
     const uint64_t epoch_step = ++c->noise_epoch;
     const uint64_t epoch_reset = rs ? ++c->noise_epoch : epoch_step;
