@@ -368,6 +368,11 @@ int launch_env(sgb_ctx* ctx, int B, int N, const sgb_buffers* buf, int mode, con
     p.cfg = cfg_override ? *cfg_override : ctx->cfg;
     // spawn-table refresh: the table holds no boundary indices, so a layout with boundary points runs the scans
     p.skip_scan = (p.cfg.obs_flags & SGB_OBS_BOUNDARY_POINTS) ? 0 : skip_scan;
+    {   // small batches read the few map entries a spawn-table refresh needs from global memory (see map_global)
+        const int g = pick_group(N);
+        const int wave = ctx->num_sms * (cta_threads(g) / 32) * std::max(1, 32 / (N * g));
+        if (p.skip_scan && B <= 4 * wave) p.skip_scan = 2;
+    }
     p.fresh = fresh ? fresh : ctx->d_fresh;
     p.buf = *buf;
     p.blob = ctx->d_blob;
