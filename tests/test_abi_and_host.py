@@ -41,6 +41,25 @@ def test_header_symbols_are_exported(L):
     assert T.sgb_version() == L.sgb_version()
 
 
+def test_fused_gae_allgather_refuses_bad_arguments(L):
+    """sgb_gae_allgather validates before it touches a device (no compute here): world / rank ranges, NULL buffers,
+    NULL peer entries, one multicast mapping without the other."""
+    one = (C.c_void_p * 1)(0x1000)
+    null1 = (C.c_void_p * 1)(None)
+    vp = C.c_void_p
+    good = lambda: [4, 8, 2, vp(0x1000), vp(0x2000), vp(0x3000), vp(0x4000), 0.99, 0.9]  # noqa: E731
+    assert L.sgb_gae_allgather(*good(), 0, 0, one, one, None, None, None) == -1           # world < 1
+    assert L.sgb_gae_allgather(*good(), 17, 0, one, one, None, None, None) == -1          # world > 16
+    assert L.sgb_gae_allgather(*good(), 1, 1, one, one, None, None, None) == -1           # rank outside the world
+    assert L.sgb_gae_allgather(*good(), 1, 0, None, one, None, None, None) == -1          # no peer table
+    assert L.sgb_gae_allgather(*good(), 1, 0, null1, one, None, None, None) == -1         # NULL peer entry
+    assert L.sgb_gae_allgather(*good(), 1, 0, one, one, vp(0x5000), None, None) == -1     # half a multicast pair
+    bad = good(); bad[3] = None
+    assert L.sgb_gae_allgather(*bad, 1, 0, one, one, None, None, None) == -1              # NULL reward
+    bad = good(); bad[0] = 0
+    assert L.sgb_gae_allgather(*bad, 1, 0, one, one, None, None, None) == -1              # T = 0
+
+
 def test_struct_layouts_match_header():
     from sigmarl_b200 import lib
     hdr = open(os.path.join(REPO, "include", "sigmarl_b200.h")).read()

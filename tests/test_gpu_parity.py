@@ -977,3 +977,37 @@ def test_reset_world_at_single_agent_on_any_map_and_mode():
     changed = (sc.env.pose != before).any(-1).any(-1)
     assert bool(changed[5]) and int(changed.sum()) == 1 and int(sc.env.step_count[5]) == 0
     assert int(sc.env.n_failed) == 0
+
+
+def test_programmatic_dependent_launch_changes_nothing_but_overlap(monkeypatch):
+    """The library chains its kernels with programmatic dependent launch (griddepcontrol) and keeps the
+    reset's list length in two alternating counters instead of a memset between the kernels.  Same seeds with the chain
+    switched off (SGB_NO_PDL=1, read at context creation): every buffer stays bit-identical through a mixed sequence of
+    steps, masked resets with and without fresh observations, explicit respawns and masked refreshes."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    B, N = 4096, 8
+    envs = []
+    for no_pdl in ("0", "1"):
+        monkeypatch.setenv("SGB_NO_PDL", no_pdl)
+        envs.append(RoadTrafficEnv(EnvConfig(scenario_type="cpm_entire", n_agents=N), num_envs=B, device="cuda:0", seed=11))
+    monkeypatch.delenv("SGB_NO_PDL")
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for e in envs:
+        e.reset()
+    names = ("pose", "aux", "carry", "path_id", "agent_flags", "collide_with", "step_count", "obs", "reward", "done", "n_failed")
+    for t in range(12):
+        act = (torch.rand(B, N, 2, generator=gen, device="cuda") * 2 - 1) * torch.as_tensor(UR).cuda()
+        mask = torch.rand(B, generator=gen, device="cuda") < 0.1
+        amask = torch.rand(B, N, generator=gen, device="cuda") < 0.05
+        for e in envs:
+            e.step(act.clone())
+            e.reset_done(write_obs=(t % 2 == 0))          # back-to-back kernels: step -> reset (-> refresh)
+            if t % 3 == 0:
+                e.refresh(env_mask=mask, write_obs=True)   # its own counter slot
+            if t % 4 == 1:
+                e.reset_masked(agent_mask=amask, write_obs=True)
+            e.reset_done(write_obs=True)                   # a second reset right behind the first: alternating counters
+        torch.cuda.synchronize()
+        for name in names:
+            assert torch.equal(getattr(envs[0], name), getattr(envs[1], name)), (t, name)
+    assert int(envs[0].done.sum()) >= 0 and int(envs[0].n_failed) == 0
