@@ -46,7 +46,8 @@ struct sgb_ctx {
     float set_cum[4] = {1.0f, 1.0f, 1.0f, 1.0f};
     uint64_t noise_epoch = 0;        // counts API calls that can write an observation: part of the noise key
     int64_t env_offset = 0;          // global index of env 0 (sgb_set_env_offset / the reset entry points)
-    size_t smem_configured[6][3] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G> on this device
+    size_t smem_configured[6][4] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G (and MB = 2)> on this device
+    int32_t smem_per_sm = 0;
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // sgb_step_host: chunked copy/compute pipeline
     cudaEvent_t pipe_event[2] = {nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
@@ -319,6 +320,23 @@ int launch_chained(sgb_ctx* ctx, void (*kernel)(const P), dim3 grid, dim3 block,
     return SGB_OK;
 }
 
+template <int G, int MODE, int OV, int MB>
+int launch_env_kernel_mb(sgb_ctx* ctx, Params& p, cudaStream_t st, size_t smem, int n_wt) {
+    // the opt-in is per (kernel, device): remember it in the context, which is bound to one device
+    size_t& configured = ctx->smem_configured[MODE + 2 * OV][G == 4 ? 0 : (G == 2 ? (MB == 2 ? 3 : 1) : 2)];
+    if (configured < smem) {
+        CK(cudaFuncSetAttribute(env_step_kernel<G, MODE, OV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int warps = cta_threads(G) / 32;
+    // persistent grid: as many CTAs as are resident at once
+    const int grid = std::min((n_wt + warps - 1) / warps, ctx->num_sms * MB);
+    const int rc = launch_chained(ctx, env_step_kernel<G, MODE, OV, MB>, dim3(grid), dim3(cta_threads(G)), smem, st, p);
+    if (rc) return rc;
+    ctx->launches++;
+    return SGB_OK;
+}
+
 template <int G, int MODE, int OV>
 int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
     const int slots = kSlots;
@@ -333,18 +351,11 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
                  ctx->blob_bytes, smem, ctx->max_smem_optin);
         return SGB_ERR_MAP;
     }
-    // the opt-in is per (kernel, device): remember it in the context, which is bound to one device
-    size_t& configured = ctx->smem_configured[MODE + 2 * OV][G == 4 ? 0 : (G == 2 ? 1 : 2)];
-    if (configured < smem) {
-        CK(cudaFuncSetAttribute(env_step_kernel<G, MODE, OV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    const int warps = cta_threads(G) / 32;
-    const int grid = std::min((n_wt + warps - 1) / warps, ctx->num_sms);
-    const int rc = launch_chained(ctx, env_step_kernel<G, MODE, OV>, dim3(grid), dim3(cta_threads(G)), smem, st, p);
-    if (rc) return rc;
-    ctx->launches++;
-    return SGB_OK;
+    // two-lane kernels (512 threads): two CTAs per SM when the map leaves room for two sets of tile arrays (each CTA also
+    // costs 1 KB of system-reserved shared memory) — see env_step_kernel's MB
+    if (G == 2 && 2 * (smem + 1024) <= (size_t)ctx->smem_per_sm)
+        return launch_env_kernel_mb<G, MODE, OV, (G == 2 ? 2 : 1)>(ctx, p, st, smem, n_wt);
+    return launch_env_kernel_mb<G, MODE, OV, 1>(ctx, p, st, smem, n_wt);
 }
 
 template <int MODE, int OV>
@@ -495,6 +506,7 @@ static int init_device_state(sgb_ctx* c, const Packed& pk) {
     CK(cudaGetDeviceProperties(&prop, c->device));
     c->num_sms = prop.multiProcessorCount;
     c->max_smem_optin = (int32_t)prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = (int32_t)prop.sharedMemPerMultiprocessor;
     if (prop.major < 10) {
         snprintf(g_err, sizeof g_err, "device %d is sm_%d%d; this library is built for sm_100a only", c->device, prop.major, prop.minor);
         return SGB_ERR_NO_DEVICE;
