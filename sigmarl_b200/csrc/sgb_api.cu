@@ -46,7 +46,7 @@ struct sgb_ctx {
     float set_cum[4] = {1.0f, 1.0f, 1.0f, 1.0f};
     uint64_t noise_epoch = 0;        // counts API calls that can write an observation: part of the noise key
     int64_t env_offset = 0;          // global index of env 0 (sgb_set_env_offset / the reset entry points)
-    size_t smem_configured[6][4] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G (and MB = 2)> on this device
+    size_t smem_configured[6][5] = {};   // dynamic-smem opt-in done for <MODE + 2 * OV, G (and MB = 2)> on this device
     int32_t smem_per_sm = 0;
     cudaStream_t pipe_stream[2] = {nullptr, nullptr};   // sgb_step_host: chunked copy/compute pipeline
     cudaEvent_t pipe_event[2] = {nullptr, nullptr};
@@ -323,7 +323,7 @@ int launch_chained(sgb_ctx* ctx, void (*kernel)(const P), dim3 grid, dim3 block,
 template <int G, int MODE, int OV, int MB>
 int launch_env_kernel_mb(sgb_ctx* ctx, Params& p, cudaStream_t st, size_t smem, int n_wt) {
     // the opt-in is per (kernel, device): remember it in the context, which is bound to one device
-    size_t& configured = ctx->smem_configured[MODE + 2 * OV][G == 4 ? 0 : (G == 2 ? (MB == 2 ? 3 : 1) : 2)];
+    size_t& configured = ctx->smem_configured[MODE + 2 * OV][G == 4 ? 0 : (G == 2 ? 1 : 2) + (MB == 2 ? 2 : 0)];
     if (configured < smem) {
         CK(cudaFuncSetAttribute(env_step_kernel<G, MODE, OV, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
@@ -351,10 +351,10 @@ int launch_env_kernel(sgb_ctx* ctx, Params& p, cudaStream_t st) {
                  ctx->blob_bytes, smem, ctx->max_smem_optin);
         return SGB_ERR_MAP;
     }
-    // two-lane kernels (512 threads): two CTAs per SM when the map leaves room for two sets of tile arrays (each CTA also
-    // costs 1 KB of system-reserved shared memory) — see env_step_kernel's MB
-    if (G == 2 && 2 * (smem + 1024) <= (size_t)ctx->smem_per_sm)
-        return launch_env_kernel_mb<G, MODE, OV, (G == 2 ? 2 : 1)>(ctx, p, st, smem, n_wt);
+    // two- and one-lane kernels (512 / 256 threads): two CTAs per SM when the map leaves room for two sets of tile arrays
+    // (each CTA also costs 1 KB of system-reserved shared memory) — see env_step_kernel's MB
+    if (G <= 2 && 2 * (smem + 1024) <= (size_t)ctx->smem_per_sm)
+        return launch_env_kernel_mb<G, MODE, OV, (G <= 2 ? 2 : 1)>(ctx, p, st, smem, n_wt);
     return launch_env_kernel_mb<G, MODE, OV, 1>(ctx, p, st, smem, n_wt);
 }
 
