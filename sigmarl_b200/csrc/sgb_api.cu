@@ -869,13 +869,24 @@ static int reset_impl(sgb_ctx* c, int32_t B, int32_t N, const sgb_buffers* buf, 
         p.path_lo = c->set_lo[0]; p.path_hi = c->set_hi[0];
         for (int i = 0; i < 4; i++) { p.set_lo[i] = c->set_lo[i]; p.set_hi[i] = c->set_hi[i]; p.set_cum[i] = c->set_cum[i]; }
     }
-    // envs per warp: a warp walks its touched envs one after the other, so few envs per warp keep the dependent-load
-    // chains short; about four waves of resident warps (48 per SM) was the best trade against block-launch overhead
-    // (B = 65536, N = 8, 26 % done: 1 -> 0.084, 2-3 -> 0.082, 6 -> 0.085, 10 -> 0.091 ms per reset + fresh obs)
-    p.epw = std::max(1, std::min(32, (B + c->num_sms * 192 - 1) / (c->num_sms * 192)));
+    // envs per warp: a warp inspects `epw` consecutive envs and deals the touched ones to its sub-warps (32 / W at a time).
+    // Many envs per warp fill the sub-warps (a quarter of the envs is touched per step under random actions), few keep
+    // more warps in flight for the dependent loads: B / (32 warps per SM), at most 16 (measured at 65536 x 8, 26 % done,
+    // reset only: epw 3 -> 0.0445, 8 -> 0.0377, 16 -> 0.0371, 32 -> 0.0459 ms)
+    p.epw = std::max(1, std::min(16, B / (c->num_sms * 32)));
+    // small batches: too few envs per warp to fill sub-warps — one warp per env (32 tries of an agent at a time, which
+    // crowded maps need), a few envs per warp (8 192 envs: sub-warps 0.029 / 0.050 ms on cpm_entire x 8 / roundabout x 12,
+    // warp per env 0.026 / 0.047)
+    // (sub-warps of 16 lanes for 9 - 16 agents were measured too and are slower than a warp per env — 32 768 envs:
+    // roundabout x 12 0.1105 vs 0.1060 ms, cpm_entire x 15 0.128 vs 0.117 — crowded envs want all 32 tries at once)
+    const bool sub_warps = p.epw >= 4 && N <= 8;
+    if (!sub_warps) p.epw = std::max(1, std::min(32, (B + c->num_sms * 192 - 1) / (c->num_sms * 192)));
     if (const char* e = getenv("SGB_RESET_EPW")) p.epw = std::max(1, std::min(32, atoi(e)));   // tuning knob (profiles/kbench.py)
     const int64_t n_warps = ((int64_t)B + p.epw - 1) / p.epw;
-    rc = launch_chained(c, reset_kernel, dim3((unsigned)((n_warps * 32 + 255) / 256)), dim3(256), 0, st, p);
+    // lanes per env: 8 (four envs in flight per warp) for large batches of up to 8 agents, a whole warp otherwise
+    const dim3 rgrid((unsigned)((n_warps * 32 + 255) / 256));
+    rc = sub_warps ? launch_chained(c, reset_kernel<8>, rgrid, dim3(256), 0, st, p)
+                   : launch_chained(c, reset_kernel<32>, rgrid, dim3(256), 0, st, p);
     if (rc) return rc;
     c->launches++;
     CK(cudaGetLastError());

@@ -1728,24 +1728,35 @@ struct ResetParams {
     float set_cum[4];          // cumulative probabilities, set_cum[n_sets - 1] >= 1
 };
 
-// One WARP per env: bounded rejection sampling (world_state_rt_sim.py:215-311).  Agents are placed one after the other
-// (each must keep its distance from the ones before it), but the TRIES of an agent run in parallel: lane l evaluates
-// try 32*r + l of round r, a ballot picks the first feasible one — exactly the try the reference's sequential loop
-// would accept — and the winner is broadcast.  Lane a holds agent a's position; at the end every lane places its own
-// agent (parallel loads from the spawn table, parallel stores).  Crowded maps need many tries per agent (on-ramp /
-// roundabout with 12 agents: the sequential one-thread-per-env version spent 0.14 ms per step there).
-#ifndef SGB_RESET_MIN_BLOCKS
-#define SGB_RESET_MIN_BLOCKS 6     // 40 registers, 48 resident warps per SM: the kernel is latency-bound (0.0500 -> 0.0465 ms per masked reset)
-#endif
-__global__ void __launch_bounds__(256, SGB_RESET_MIN_BLOCKS) reset_kernel(const ResetParams p) {
+// One SUB-WARP of W lanes per env (W = 8 or 32, W >= N), 32 / W envs in flight per warp: bounded rejection sampling
+// (world_state_rt_sim.py:215-311).  Agents are placed one after the other (each must keep its distance from the ones
+// before it), but the TRIES of an agent run in parallel: lane l of the sub-warp evaluates try W*r + l of round r, a ballot
+// picks the first feasible one — exactly the try the reference's sequential loop would accept — and the winner is
+// broadcast.  Lane a holds agent a's position; at the end every lane places its own agent (parallel loads from the spawn
+// table, parallel stores).  Every shuffle / ballot names its sub-warp's lanes only, so the sub-warps of a warp run
+// independently (different envs need different numbers of tries).  The draws are keyed by (seed, epoch, GLOBAL env,
+// agent, try): which lanes evaluate them does not change a result.  History: one thread per env 0.155 ms per masked reset
+// at the headline shape and 0.14 ms on crowded maps; one warp per env 0.049 -> 0.0465; four envs per warp (W = 8; large
+// batches of up to 8 agents) 0.037.
+// Register budget: the warp-per-env form is latency-bound and runs best at 40 registers / 48 resident warps per SM
+// (0.0500 -> 0.0465 ms per masked reset at the headline shape); the sub-warp forms keep more state (their masks and lane
+// arithmetic) and run best without spills at 64 registers / 32 warps (0.0415 with 40 registers, 0.0371 with 64).
+template <int W>
+__global__ void __launch_bounds__(256, W == 32 ? 6 : 4) reset_kernel(const ResetParams p) {
     pdl_launch_dependents();
     pdl_wait();                // done / flags / poses are the step kernel's outputs
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.count_next) *p.count_next = 0;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int ln = threadIdx.x & 31;
     const int N = p.N;
-    // a warp looks after `epw` consecutive envs: lane l finds out whether env l needs work, then the warp handles the
-    // touched ones one after the other (epw is chosen by the host so that all warps of the launch are resident)
+    constexpr int S = 32 / W;                       // envs in flight per warp
+    const int sg = ln / W;                          // sub-warp of this lane
+    const int sl = ln - sg * W;                     // lane within the sub-warp (= agent index for sl < N)
+    const int base = sg * W;                        // first lane of the sub-warp
+    const uint32_t wmask = W == 32 ? 0xffffffffu : ((1u << W) - 1u);
+    const uint32_t sgmask = wmask << base;          // the sub-warp's lanes: the mask of all its shuffles / ballots
+    // a warp looks after `epw` consecutive envs: lane l finds out whether env l needs work, then the touched ones are
+    // dealt to the sub-warps, S at a time
     const int e_first = w * p.epw;
     if (e_first >= p.B) return;
     bool l_full = false;
@@ -1768,18 +1779,30 @@ __global__ void __launch_bounds__(256, SGB_RESET_MIN_BLOCKS) reset_kernel(const 
     }
     uint32_t touched = __ballot_sync(0xffffffffu, l_full || l_respawn != 0u);
   while (touched) {
-    const int src_l = __ffs(touched) - 1;
-    touched &= touched - 1;
+    // sub-warp s takes the s-th lowest touched env of this round (warp-uniform arithmetic, no communication)
+    int src_l = -1;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        if (touched) {
+            const int bit = __ffs(touched) - 1;
+            touched &= touched - 1;
+            if (s == sg) src_l = bit;
+        }
+    }
+    // the env's selection sits in lane src_l of the WARP: fetch it before the sub-warps go their own ways
+    const bool full_w = __shfl_sync(0xffffffffu, (int)l_full, max(src_l, 0)) != 0;
+    const uint32_t respawn_w = __shfl_sync(0xffffffffu, l_respawn, max(src_l, 0));
+    if (src_l >= 0) {
     const int e = e_first + src_l;
-    const bool full = __shfl_sync(0xffffffffu, (int)l_full, src_l) != 0;
-    const uint32_t respawn = __shfl_sync(0xffffffffu, l_respawn, src_l);
+    const bool full = full_w;
+    const uint32_t respawn = respawn_w;
     const uint32_t todo = full ? (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) : respawn;
     const BlobHeader* hdr = reinterpret_cast<const BlobHeader*>(p.blob);
     const PathRec* paths = reinterpret_cast<const PathRec*>(p.blob + hdr->path_off);
     const float2* pts = reinterpret_cast<const float2*>(p.blob + hdr->pts_off);
-    float qx = 0.0f, qy = 0.0f;            // lane a: position of agent a
-    if (ln < N) {
-        const float4 ps = reinterpret_cast<const float4*>(p.buf.pose)[(size_t)e * N + ln];
+    float qx = 0.0f, qy = 0.0f;            // lane a of the sub-warp: position of agent a
+    if (sl < N) {
+        const float4 ps = reinterpret_cast<const float4*>(p.buf.pose)[(size_t)e * N + sl];
         qx = ps.x; qy = ps.y;
     }
     const uint64_t env_g = (uint64_t)(p.env_offset + e);
@@ -1793,7 +1816,7 @@ __global__ void __launch_bounds__(256, SGB_RESET_MIN_BLOCKS) reset_kernel(const 
             const float u = (float)(draw(p.seed, p.epoch, env_g, 0, 0, 3) >> 40) * (1.0f / 16777216.0f);
             sid = 0;
             while (sid < p.n_sets - 1 && !(u < p.set_cum[sid])) sid++;
-            if (ln == 0) p.buf.scenario_id[e] = sid;
+            if (sl == 0) p.buf.scenario_id[e] = sid;
         } else {
             sid = min(max(p.buf.scenario_id[e], 0), p.n_sets - 1);
         }
@@ -1814,70 +1837,72 @@ __global__ void __launch_bounds__(256, SGB_RESET_MIN_BLOCKS) reset_kernel(const 
     // stage 1: the FIRST try of every agent, all agents in parallel (lane a = agent a) — on roomy maps it is
     // accepted nine times out of ten, so this is where the draws and the dependent map loads should overlap
     float2 c0 = make_float2(0.0f, 0.0f);
-    if (ln < N && ((todo >> ln) & 1u)) c0 = candidate(ln, 0, my_path, my_point);
+    if (sl < N && ((todo >> sl) & 1u)) c0 = candidate(sl, 0, my_path, my_point);
     // stage 2: accept / retry, agent by agent (each must keep its distance from the ones placed before it)
     for (int a = 0; a < N; a++) {
-        if (!((todo >> a) & 1u)) continue;
+        if (!((todo >> a) & 1u)) continue;     // (uniform within the sub-warp)
         // full reset: against agents 0..a-1 (agent 0 always feasible); respawn: against all others
         const uint32_t others = (full ? ((1u << a) - 1u) : (N >= 32 ? 0xffffffffu : ((1u << N) - 1u))) & ~(1u << a);
-        const float cx = __shfl_sync(0xffffffffu, c0.x, a), cy = __shfl_sync(0xffffffffu, c0.y, a);
+        const float cx = __shfl_sync(sgmask, c0.x, base + a), cy = __shfl_sync(sgmask, c0.y, base + a);
         // try 0: every lane o tests the candidate against ITS agent's position, one ballot
         const float ddx = cx - qx, ddy = cy - qy;
-        const uint32_t bad = __ballot_sync(0xffffffffu, !(madd2(ddx, ddx, ddy, ddy) >= p.cfg.reset_min_dist_sq)) & others;
+        const uint32_t bad = ((__ballot_sync(sgmask, !(madd2(ddx, ddx, ddy, ddy) >= p.cfg.reset_min_dist_sq)) >> base) & wmask) & others;
         if (!bad || p.max_tries <= 1) {
             if (bad) failed++;
-            if (ln == a) { qx = cx; qy = cy; }
+            if (sl == a) { qx = cx; qy = cy; }
             continue;
         }
-        // tries 1, 2, ...: 32 at a time, lane l evaluates try 1 + r0 + l; a ballot picks the first feasible one,
+        // tries 1, 2, ...: W at a time, lane l evaluates try 1 + r0 + l; a ballot picks the first feasible one,
         // exactly the try a sequential loop would accept
         bool placed = false;
         int w_path = path_lo, w_point = 3;
         float w_x = 0.0f, w_y = 0.0f;
-        for (int r0 = 1; r0 < p.max_tries && !placed; r0 += 32) {
-            const int tr = r0 + ln;
+        for (int r0 = 1; r0 < p.max_tries && !placed; r0 += W) {
+            const int tr = r0 + sl;
             const bool live = tr < p.max_tries;
             int path = path_lo, point = 3;
             float2 c = make_float2(0.0f, 0.0f);
             if (live) c = candidate(a, tr, path, point);
             bool ok = live;
-            for (int o = 0; o < N; o++) {            // warp-uniform loop: every lane tests ITS candidate against agent o
-                const float ox = __shfl_sync(0xffffffffu, qx, o), oy = __shfl_sync(0xffffffffu, qy, o);
+            for (int o = 0; o < N; o++) {            // sub-warp-uniform loop: every lane tests ITS candidate against agent o
+                const float ox = __shfl_sync(sgmask, qx, base + o), oy = __shfl_sync(sgmask, qy, base + o);
                 if (!((others >> o) & 1u)) continue;
                 const float dx = c.x - ox, dy = c.y - oy;
                 if (!(madd2(dx, dx, dy, dy) >= p.cfg.reset_min_dist_sq)) ok = false;
             }
-            const uint32_t okm = __ballot_sync(0xffffffffu, ok);
+            const uint32_t okm = (__ballot_sync(sgmask, ok) >> base) & wmask;
             // if this was the last round and nothing is feasible, the last try is kept (rather than spinning
             // forever) and reported
-            const bool last_round = r0 + 32 >= p.max_tries;
+            const bool last_round = r0 + W >= p.max_tries;
             const int src = okm ? (__ffs(okm) - 1) : (last_round ? (p.max_tries - 1 - r0) : -1);
             if (src >= 0) {
-                w_path = __shfl_sync(0xffffffffu, path, src);
-                w_point = __shfl_sync(0xffffffffu, point, src);
-                w_x = __shfl_sync(0xffffffffu, c.x, src);
-                w_y = __shfl_sync(0xffffffffu, c.y, src);
+                w_path = __shfl_sync(sgmask, path, base + src);
+                w_point = __shfl_sync(sgmask, point, base + src);
+                w_x = __shfl_sync(sgmask, c.x, base + src);
+                w_y = __shfl_sync(sgmask, c.y, base + src);
                 placed = true;
                 if (!okm) failed++;
             }
         }
-        if (ln == a) { qx = w_x; qy = w_y; my_path = w_path; my_point = w_point; }
+        if (sl == a) { qx = w_x; qy = w_y; my_path = w_path; my_point = w_point; }
     }
-    if (ln < N && ((todo >> ln) & 1u)) {
-        const float u = (float)(draw(p.seed, p.epoch, env_g, ln, 0, 2) >> 40) * (1.0f / 16777216.0f);
-        place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + ln, my_path, my_point, u * p.cfg.max_speed, p.spawn_tab, ln,
+    if (sl < N && ((todo >> sl) & 1u)) {
+        const float u = (float)(draw(p.seed, p.epoch, env_g, sl, 0, 2) >> 40) * (1.0f / 16777216.0f);
+        place_agent(p.cfg, p.buf, p.blob, p.yaw, (size_t)e * N + sl, my_path, my_point, u * p.cfg.max_speed, p.spawn_tab, sl,
                     p.fresh);
     }
     // collision masks of a touched env are cleared (road_traffic.py:907)
-    if (ln < N) {
-        p.buf.agent_flags[(size_t)e * N + ln] = 0;
-        if (p.buf.collide_with) p.buf.collide_with[(size_t)e * N + ln] = 0;
+    if (sl < N) {
+        p.buf.agent_flags[(size_t)e * N + sl] = 0;
+        if (p.buf.collide_with) p.buf.collide_with[(size_t)e * N + sl] = 0;
     }
-    if (ln == 0) {
+    if (sl == 0) {
         if (full) p.buf.step_count[e] = 0; // road_traffic.py:875-877
         if (full || !p.list_full_only) p.list[atomicAdd(p.count, 1)] = e;
         if (failed && p.n_failed) atomicAdd(p.n_failed, failed);
     }
+    }
+    __syncwarp();   // the sub-warps meet again before the next round is dealt
   }
 }
 
