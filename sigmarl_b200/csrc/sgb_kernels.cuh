@@ -38,9 +38,9 @@ namespace sgb {
 #ifndef SGB_SYNC_WARPS          // warps per phase-aligned group in the step kernel (0/1 = free-running warps)
 #define SGB_SYNC_WARPS 8
 #endif
-#ifndef SGB_SYNC_WARPS_REFRESH  // same for the refresh kernel (0.137 -> 0.133 ms per masked reset at 26 % done envs)
-#define SGB_SYNC_WARPS_REFRESH 8
-#endif
+#ifndef SGB_SYNC_WARPS_REFRESH  // same for the refresh kernel.  Free-running: what it mostly runs is the spawn-table refresh of
+#define SGB_SYNC_WARPS_REFRESH 0 // reset envs (no scans, little code), where the group barriers only cost (reset + refresh at the
+#endif                           // headline shape 0.0668 -> 0.0647 ms); with scans, groups of 8 were 3 % faster (0.137 -> 0.133)
 // Threads per CTA (one CTA per SM: the map blob fills most of the shared memory) for G = 4 lanes per agent.  The CTA
 // always holds kSlots agent slots — that fixes the shared-memory footprint next to the map — so with fewer lanes per
 // agent it has fewer threads, and more registers each: G = 4 -> 1024 threads, G = 2 -> 512, G = 1 -> 256.
