@@ -359,6 +359,23 @@ SGB_HD __forceinline__ bool rect_cross_seg_L1(const float* rvx, const float* rvy
     return hit;
 }
 
+// One out-of-line copy for the boundary scans: the predicate runs for ~0.2 segments per agent-step but was inlined twice
+// into scan_boundary (two segments per lane-iteration), in the middle of the hottest loop of a kernel that lives on its
+// instruction cache (0.2949 -> 0.2908 ms).  Scalars by value: an array argument would force the caller's vertex
+// registers into local memory.  (Moving the rectangle-pair predicate and the rank >= 2 neighbour search out of line as
+// well made the kernel slower again, 0.2962 ms: the pair predicate runs too often for a call.)
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ bool rect_cross_seg_ool(float x0, float x1, float x2, float x3, float y0, float y1, float y2, float y3,
+                                                float ax, float ay, float bx, float by) {
+    const float rvx[4] = {x0, x1, x2, x3}, rvy[4] = {y0, y1, y2, y3};
+    return rect_cross_seg_L1(rvx, rvy, ax, ay, bx, by, true);
+}
+#define SGB_RECT_CROSS_SEG(rvx, rvy, ax, ay, bx, by) \
+    rect_cross_seg_ool(rvx[0], rvx[1], rvx[2], rvx[3], rvy[0], rvy[1], rvy[2], rvy[3], ax, ay, bx, by)
+#else
+#define SGB_RECT_CROSS_SEG(rvx, rvy, ax, ay, bx, by) rect_cross_seg_L1(rvx, rvy, ax, ay, bx, by, true)
+#endif
+
 // interX(L1 = rectangle lo, L2 = rectangle hi), 4 x 4 edge pairs.  C1 first: f_i at hi's four vertices; if no  @region rect_cross_rect
 // edge line of lo separates two consecutive vertices of hi there is no crossing and C2 is not evaluated.
 SGB_HD __forceinline__ bool rect_cross_rect(const Rect& lo, const float* hx, const float* hy) {
@@ -689,11 +706,11 @@ SGB_HD __forceinline__ void scan_boundary(const float2* __restrict__ pts, const 
                     };
                     if (exhaustive || (ga && (cola || !separated(a.x, a.y, lx, ly)))) {
                         SGB_COUNT(3, 1);
-                        hit |= rect_cross_seg_L1(rvx, rvy, a.x, a.y, e.x, e.y, true);
+                        hit |= SGB_RECT_CROSS_SEG(rvx, rvy, a.x, a.y, e.x, e.y);
                     }
                     if (exhaustive || (gb && (colb || !separated(a2.x, a2.y, lx2, ly2)))) {
                         SGB_COUNT(3, 1);
-                        hit |= rect_cross_seg_L1(rvx, rvy, a2.x, a2.y, e2.x, e2.y, true);
+                        hit |= SGB_RECT_CROSS_SEG(rvx, rvy, a2.x, a2.y, e2.x, e2.y);
                     }
                 }
             }
