@@ -1011,3 +1011,46 @@ def test_programmatic_dependent_launch_changes_nothing_but_overlap(monkeypatch):
         for name in names:
             assert torch.equal(getattr(envs[0], name), getattr(envs[1], name)), (t, name)
     assert int(envs[0].done.sum()) >= 0 and int(envs[0].n_failed) == 0
+
+
+def test_sub_warp_reset_equals_warp_per_env_reset():
+    """Large batches of up to 8 agents are reset four envs per warp (sub-warps of 8 lanes, reset_kernel<8>), small ones one
+    env per warp (reset_kernel<32>).  The draws are keyed by (seed, epoch, global env, agent, try), not by lanes: a batch of
+    20 480 envs (sub-warps) and the same envs as four shards of 5 120 (warp per env) must stay bit-identical through full
+    resets, masked resets of done envs and explicit respawns — on a roomy map and on a crowded one (many retries)."""
+    from sigmarl_b200 import EnvConfig, RoadTrafficEnv
+    for scenario, N in (("cpm_entire", 8), ("on_ramp_2_multilane", 8)):
+        B, S = 20480, 4
+        cfg = EnvConfig(scenario_type=scenario, n_agents=N)
+        full = RoadTrafficEnv(cfg, num_envs=B, device="cuda:0", seed=17, max_reset_tries=512)
+        shards = [RoadTrafficEnv(cfg, num_envs=B // S, device="cuda:0", seed=17, env_offset=k * (B // S), max_reset_tries=512)
+                  for k in range(S)]
+        full.reset()
+        for h in shards:
+            h.reset()
+        gen = torch.Generator(device="cuda").manual_seed(2)
+        names = ("pose", "aux", "carry", "path_id", "agent_flags", "step_count", "obs")
+
+        def same(tag):
+            torch.cuda.synchronize()
+            for name in names:
+                cat = torch.cat([getattr(h, name) for h in shards])
+                assert torch.equal(getattr(full, name), cat), (scenario, tag, name)
+            assert int(full.n_failed) == sum(int(h.n_failed) for h in shards)
+
+        same("reset")
+        for t in range(6):
+            act = (torch.rand(B, N, 2, generator=gen, device="cuda") * 2 - 1) * torch.as_tensor(UR).cuda()
+            amask = torch.rand(B, N, generator=gen, device="cuda") < 0.1
+            full.step(act)
+            full.reset_done(write_obs=True)
+            for k, h in enumerate(shards):
+                sl = slice(k * (B // S), (k + 1) * (B // S))
+                h.step(act[sl])
+                h.reset_done(write_obs=True)
+            same(f"step {t}")
+            if t % 2 == 1:
+                full.reset_masked(agent_mask=amask, write_obs=True)
+                for k, h in enumerate(shards):
+                    h.reset_masked(agent_mask=amask[k * (B // S):(k + 1) * (B // S)], write_obs=True)
+                same(f"respawn {t}")
