@@ -41,6 +41,19 @@ def test_header_symbols_are_exported(L):
     assert T.sgb_version() == L.sgb_version()
 
 
+def test_integration_stub_lists_the_structs_as_the_library_binds_them():
+    """INTEGRATION.md shows the ctypes stub a maintainer of the reference would add: its sgb_buffers field list and the
+    tail of its sgb_config must be the ones sigmarl_b200/lib.py binds (and the header declares, see the layout test)."""
+    from sigmarl_b200 import lib
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    blk = doc[doc.index("class Buffers(C.Structure)"):doc.index("ctx = C.c_void_p()")]
+    names = re.findall(r'"([a-z_]+)"', blk)
+    assert names == lib.BUFFER_FIELDS, (names, lib.BUFFER_FIELDS)
+    cfg = doc[doc.index("class Config(C.Structure)"):doc.index("class Buffers(C.Structure)")]
+    tail = [n for n, _ in lib.Config._fields_ if n not in lib.CONFIG_FLOATS and not n.startswith("reserved")]
+    assert [n for n in re.findall(r'"([a-z_]+)"', cfg) if n in tail] == tail
+
+
 def test_fused_gae_allgather_refuses_bad_arguments(L):
     """sgb_gae_allgather validates before it touches a device (no compute here): world / rank ranges, NULL buffers,
     NULL peer entries, one multicast mapping without the other."""
